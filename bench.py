@@ -1,0 +1,358 @@
+"""Benchmark of the voice-detector batch path (BASELINE.json metric: audio-hours/sec detected).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--mode fp32|bf16]
+
+Workload (BASELINE.json configs[1]): the 1,000-clip corpus of 10-minute mono 22,050 Hz clips, processed
+one batch of clips per step; a step is `--clips-per-step` clips per GPU (weak scaling) through the whole
+hot path (virtual 3 s padding -> K1 features -> K2/K3 classifier -> K5 averaging -> K6 regions).  Clips
+are synthetic (seeded noise + speech-like bursts), drawn round-robin from a pool resident in HBM that is
+larger than L2; weights are the seeded synthetic checkpoint (the shipped one is a missing blob).
+
+`value`  = audio-hours per second with the PCM already resident in HBM (ss_detect_device);
+`e2e`    = the same through the reference-facing C-ABI call with pinned HOST buffers (ss_detect_host:
+           H2D of the clip and D2H of the region list inside the timed region);
+`roofline` = the classifier (dominant kernel family) against the measured bf16 tensor peak, its time taken
+           with CUDA events on the launching stream; `roofline_features` = K1 against measured HBM.
+`cpu_baseline` = the oracle port of the reference's CPU detector timed on this host's cores on a bounded
+           sample of the same clip (rank 0, N=1 only).
+`--impl reference` times that CPU path alone (the reference is pure Python and cannot travel; the
+oracle is its arithmetic on the same torch-CPU kernels — see oracle/model.py).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CLIP_S = 600.0
+SR = 22050
+WINDOWS_PER_CLIP = 1005
+FLOP_PER_WINDOW_MASK = 6_359_672_832          # convs on the mask path, 2 x MAC, BN folded
+FEATURE_BYTES_PER_CLIP = 4 * (13_230_000 + 132_300) + WINDOWS_PER_CLIP * 128 * 256 * 4   # PCM once + mel once
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return {"hbm_gbs": d["hbm_gbs"], "tflops_burst": d["bf16_tflops"],
+                "tflops_sustained": d["bf16_tflops_sustained"], "source": "measured"}
+    return {"hbm_gbs": 6650.0, "tflops_burst": 1590.0, "tflops_sustained": 1400.0, "source": "fallback"}
+
+
+def load_state_dict():
+    from softspoken_b200 import checkpoint
+    with open(os.path.join(ROOT, "tests", "golden", "head_seed0.json")) as f:
+        head = json.load(f)
+    return checkpoint.synthetic_state_dict(0, head)
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.proc = index, [], None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([c.strip() for c in line.split(",")])
+        except Exception:
+            pass
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 6 for n, v in zip(names, r[2:6]) if v == "Active"})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm
+def cpu_detector_sample(sd, seconds_budget: float, threads: int):
+    """The reference's CPU detector (oracle port) on a bounded sample of one 10-minute clip: batches of 32
+    windows (worker.py:71-79) until `seconds_budget` is spent, then averaging + regions of what was run."""
+    from oracle import model as om
+    from oracle import postproc as pp
+    from softspoken_b200 import synth
+    torch.set_num_threads(threads)
+    audio = synth.synth_audio(CLIP_S, 0)
+    padded = pp.pad_audio(audio)
+    starts = pp.plan_windows(CLIP_S)
+    preds, t0, done = [], time.perf_counter(), 0
+    while done < len(starts) and (done == 0 or time.perf_counter() - t0 < seconds_budget):
+        idx = starts[done:done + 32]
+        x = torch.stack([torch.from_numpy(padded[i:i + 66150]) for i in idx])
+        _, mk = om.forward(sd, x, want_spec=True)          # the reference computes the spec head too
+        preds.append(mk.numpy())
+        done += len(idx)
+    lg = np.vstack(preds)
+    secs = ((done - 1) * 13230 + 66150) / SR
+    pp.find_speech_regions(pp.average_overlapping(lg, secs))
+    dt = time.perf_counter() - t0
+    audio_hours = done * 0.6 / 3600.0                      # each window advances the clip by 0.6 s
+    return audio_hours / dt, done, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sd = load_state_dict()
+    threads = os.cpu_count() or 1
+    for _ in range(args.warmup):
+        cpu_detector_sample(sd, 0.0, threads)               # one batch of 32 windows
+    vals, windows, t_total = [], 0, 0.0
+    for _ in range(args.steps):
+        v, n, dt = cpu_detector_sample(sd, args.ref_step_seconds, threads)
+        vals.append(v); windows += n; t_total += dt
+    value = (windows * 0.6 / 3600.0) / t_total
+    line = {
+        "impl": "reference", "metric": "audio_hours_per_sec", "value": value, "unit": "audio-hours/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_total / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "config2: 10-min mono 22.05 kHz clip of the 1000-clip corpus, CPU detector on a bounded "
+                               f"sample (~{args.ref_step_seconds:.0f} s of batches of 32 windows per step)"},
+        "cpu_baseline": {"value": value, "unit": "audio-hours/s", "cores": threads, "kind": "port",
+                         "sample": f"{windows} windows in {t_total:.1f} s over {args.steps} steps"},
+        "e2e": {"value": value, "unit": "audio-hours/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "x_realtime": value * 3600.0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def device_clips(n_clips: int, device, seed0: int):
+    """Pool of synthetic 10-minute clips generated on the device (noise + AM harmonic bursts), quantised to
+    PCM_16 levels like a decoded wav."""
+    n = int(CLIP_S * SR)
+    out = []
+    t = torch.arange(n, device=device, dtype=torch.float32) / SR
+    for c in range(n_clips):
+        g = torch.Generator(device=device).manual_seed(seed0 + c)
+        x = torch.randn(n, device=device, generator=g) * 0.05
+        rng = np.random.default_rng(seed0 + c)
+        for _ in range(60):
+            s = float(rng.uniform(0, CLIP_S - 2.0)); ln = float(rng.uniform(0.5, 2.0)); f0 = float(rng.uniform(120, 240))
+            i0, i1 = int(s * SR), int((s + ln) * SR)
+            tt = t[i0:i1] - s
+            env = torch.sin(np.pi * tt / ln) ** 2 * (0.6 + 0.4 * torch.sin(2 * np.pi * 4.0 * tt))
+            h = sum(torch.sin(2 * np.pi * k * f0 * tt) / k for k in range(1, 9))
+            x[i0:i1] += 0.25 * env * h
+        x = torch.clamp(torch.round(x * 32767.0), -32768, 32767) / 32768.0
+        out.append(x.contiguous())
+    return out
+
+
+def run_b200(args):
+    import torch.distributed as dist
+    from softspoken_b200 import _lib, dist as ssdist
+    from softspoken_b200.engine import Engine
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=device)
+
+    sd = load_state_dict()
+    eng = Engine(sd, local, max_batch=args.max_batch, mode=args.mode)
+    n = int(CLIP_S * SR)
+    cap = 4096
+    eng.reserve(n, cap)
+    C = args.clips_per_step
+    pool = device_clips(args.pool, device, seed0=1000 * rank)
+    pinned = [p.cpu().pin_memory() for p in pool]
+    reg_bufs = [(torch.empty((cap, 2), dtype=torch.int32, device=device), torch.zeros(1, dtype=torch.int32, device=device))
+                for _ in range(C)]
+    stream = torch.cuda.current_stream(device)
+
+    def sync_all():
+        torch.cuda.synchronize(device)
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize(device)
+
+    import ctypes as Cc
+    from softspoken_b200._lib import lib, check, MODES
+
+    def step_device(s):
+        trip = []
+        for j in range(C):
+            clip = pool[(s * C + j) % len(pool)]
+            reg, cnt = reg_bufs[j]
+            check(lib.ss_detect_device(eng._ctx, Cc.c_void_p(clip.data_ptr()), n, MODES[args.mode],
+                                       Cc.c_void_p(reg.data_ptr()), Cc.c_void_p(cnt.data_ptr()), cap, None,
+                                       Cc.c_void_p(stream.cuda_stream)))
+        if world > 1:                                   # config 3: detections gathered to rank 0
+            for j in range(C):
+                reg, cnt = reg_bufs[j]
+                k = int(cnt.item())
+                fi = torch.full((k, 1), (s * C + j) * world + rank, dtype=torch.int32, device=device)
+                trip.append(torch.cat([fi, reg[:k]], 1).cpu().numpy())
+            ssdist.gather_detections(np.concatenate(trip) if trip else np.zeros((0, 3), np.int32), device)
+
+    def step_host(s):
+        total_regions = 0
+        trip = []
+        for j in range(C):
+            clip = pinned[(s * C + j) % len(pinned)]
+            bins = eng.detect_host(clip, cap=cap)
+            total_regions += len(bins)
+            if world > 1:
+                trip.append(np.concatenate([np.full((len(bins), 1), (s * C + j) * world + rank, np.int32), bins], 1))
+        if world > 1:
+            ssdist.gather_detections(np.concatenate(trip) if trip else np.zeros((0, 3), np.int32), device)
+        return total_regions
+
+    def timed(fn, steps, warmup):
+        for s in range(warmup):
+            fn(s)
+        sync_all()
+        sampler = ClockSampler(local) if rank == 0 else None
+        if sampler:
+            sampler.start()
+        l0 = _lib.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record(stream)
+        last = None
+        for s in range(steps):
+            last = fn(warmup + s)
+        e1.record(stream)
+        sync_all()
+        wall = time.perf_counter() - t0
+        dev_s = e0.elapsed_time(e1) / 1e3
+        launches = _lib.launch_count() - l0
+        clocks = sampler.stop() if sampler else None
+        # host-driven paths (detect_host) are timed by the wall clock between the two synchronisations;
+        # device-resident paths by CUDA events on the launching stream
+        return dev_s, wall, launches, clocks, last
+
+    dev_s, wall_s, launches, clocks, _ = timed(step_device, args.steps, args.warmup)
+    t_dev = max(dev_s, 1e-9) if world == 1 else wall_s        # multi-rank steps include the host-side gather
+    e_dev_s, e_wall_s, _, _, n_regions = timed(step_host, args.steps, max(1, args.warmup // 2))
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    t_dev = max_over_ranks(t_dev)
+    t_e2e = max_over_ranks(e_wall_s)
+    hours = args.steps * C * world * CLIP_S / 3600.0
+    value = hours / t_dev
+    e2e = hours / t_e2e
+
+    # ---- per-kernel-family times for the roofline: one clip's 1,005 windows, CUDA events on torch's stream
+    pk = peaks()
+    clip = pool[0]
+    padded = eng.pad(clip)
+    starts = torch.arange(WINDOWS_PER_CLIP, device=device, dtype=torch.int64) * 13230
+
+    def ev_time(fn, reps):
+        fn(); torch.cuda.synchronize(device)
+        ts = []
+        for _ in range(reps):
+            flush = torch.empty(256 << 20, dtype=torch.uint8, device=device).zero_()   # > L2
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream); fn(); b.record(stream)
+            torch.cuda.synchronize(device)
+            ts.append(a.elapsed_time(b) / 1e3)
+            del flush
+        return sum(ts) / len(ts)
+
+    t_feat = ev_time(lambda: eng.features(padded, starts), 5)
+    mel = eng.features(padded, starts)
+    t_cls = ev_time(lambda: eng.classify(mel, mode=args.mode), 2)
+    achieved_tf = FLOP_PER_WINDOW_MASK * WINDOWS_PER_CLIP / t_cls / 1e12
+    achieved_gbs = FEATURE_BYTES_PER_CLIP / t_feat / 1e9
+
+    line = None
+    if rank == 0:
+        line = {
+            "metric": "audio_hours_per_sec", "value": value, "unit": "audio-hours/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_dev / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32" if args.mode == "fp32" else "bf16", "data": "synthetic",
+            "config": {"workload": f"config2: 1000x10-min mono 22.05 kHz corpus, step = {C} clip(s)/GPU "
+                                   f"({C * WINDOWS_PER_CLIP} windows) through pad+features+classifier+average+regions",
+                       "classifier_mode": args.mode, "clips_per_step_per_gpu": C, "pool_clips": len(pool),
+                       "l2": f"inputs larger than L2: pool of {len(pool)} clips x 53 MB rotates; "
+                             "classifier activations stream through a per-batch workspace",
+                       "max_batch_windows": args.max_batch, "parallelism": f"files sharded over {world} GPU(s)"},
+            "x_realtime": value * 3600.0,
+            "e2e": {"value": e2e, "unit": "audio-hours/s", "h2d_bytes_per_step": C * n * 4,
+                    "d2h_bytes_per_step": int(C * 4 + (n_regions or 0) * 8), "x_realtime": e2e * 3600.0},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {"bound": "tensor", "kernel": "classifier (conv stack, ss_classify)", "achieved": achieved_tf,
+                         "peak": pk["tflops_sustained"], "unit": "TFLOP/s", "frac": achieved_tf / pk["tflops_sustained"],
+                         "frac_of_burst_peak": achieved_tf / pk["tflops_burst"], "traffic": None,
+                         "peak_source": pk["source"], "ms_per_clip": 1e3 * t_cls,
+                         "algorithmic_flops_per_launch_group": FLOP_PER_WINDOW_MASK * WINDOWS_PER_CLIP},
+            "roofline_features": {"bound": "hbm", "kernel": "features_kernel (K1)", "achieved": achieved_gbs,
+                                  "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": achieved_gbs / pk["hbm_gbs"],
+                                  "traffic": None, "peak_source": pk["source"], "ms_per_clip": 1e3 * t_feat,
+                                  "algorithmic_bytes_per_launch": FEATURE_BYTES_PER_CLIP},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            v, nwin, dt = cpu_detector_sample(sd, args.cpu_seconds, threads)
+            line["cpu_baseline"] = {"value": v, "unit": "audio-hours/s", "cores": threads, "kind": "port",
+                                    "sample": f"{nwin} windows (batches of 32) of one 10-min clip in {dt:.1f} s, "
+                                              "oracle port of the reference CPU detector incl. spec head"}
+        print(json.dumps(line), flush=True)
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--mode", default=os.environ.get("SS_BENCH_MODE", "fp32"), choices=["fp32", "bf16"])
+    ap.add_argument("--clips-per-step", type=int, default=1)
+    ap.add_argument("--pool", type=int, default=4)
+    ap.add_argument("--max-batch", type=int, default=32)
+    ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    ap.add_argument("--ref-step-seconds", type=float, default=10.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,151 @@
+/*
+ * softspoken_b200 — C ABI of the B200-native voice-detector batch path.
+ *
+ * The reference (AVianEco/Softspoken) has no FFI: its hot path is duck-typed
+ * Python.  Each entry point below replaces one reference
+ * function or group of functions, cited as file:line relative to the reference
+ * tree; INTEGRATION.md shows the ctypes stub a maintainer adds on the
+ * reference side.  Conventions:
+ *
+ *   - extern "C", plain pointers and sizes, no C++/torch types;
+ *   - every function returns 0 on success or a negative SS_E_* code and never
+ *     throws; ss_last_error() gives the message of the calling thread's last
+ *     failure;
+ *   - "_dev" pointers are device pointers on the context's GPU, owned by the
+ *     caller; "_host" pointers are host memory (pinned or pageable);
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default
+ *     stream); device entry points only enqueue work, host entry points
+ *     synchronise before returning;
+ *   - a context allocates device memory only in ss_ctx_create (weights, classifier
+ *     workspace) and ss_ctx_reserve (file-level scratch); the compute entry points
+ *     never allocate; a context is used by one host thread at a time;
+ *   - there is no CPU fallback: without a CUDA device ss_ctx_create fails.
+ */
+#ifndef SOFTSPOKEN_B200_H
+#define SOFTSPOKEN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SS_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define SS_API __attribute__((visibility("default")))
+#else
+#define SS_API
+#endif
+
+/* status codes */
+#define SS_OK 0
+#define SS_E_ARG (-1)      /* bad argument */
+#define SS_E_CUDA (-2)     /* CUDA runtime error (message in ss_last_error) */
+#define SS_E_BLOB (-3)     /* malformed / incompatible weight blob */
+#define SS_E_CAPACITY (-4) /* output capacity or context limit exceeded */
+#define SS_E_NODEVICE (-5) /* no usable CUDA device */
+
+/* classifier arithmetic (ss_classify `mode`) */
+#define SS_MODE_FP32 0 /* CUDA-core float32 direct convolution: parity mode */
+#define SS_MODE_BF16 1 /* tcgen05 / TMEM implicit GEMM, bf16 operands, fp32 accumulate */
+
+typedef struct ss_ctx ss_ctx;
+
+/* Half-open range [begin, end) of float32 elements inside one device buffer. */
+typedef struct ss_interval {
+  int64_t begin;
+  int64_t end;
+} ss_interval;
+
+SS_API int ss_abi_version(void);
+SS_API const char* ss_last_error(void);
+
+/* Compile-time constant of the kernels by name ("sample_rate", "window_samples",
+ * "step_samples", "pad_samples", "n_frames", "n_mels", "gap_bins", ...), so the host side can
+ * assert it matches root/code/backend/settings.py:4-16 and NNDetector.py:67-75. */
+SS_API int ss_get_constant(const char* name, double* value);
+
+SS_API int ss_device_count(int* count);
+/* Number of CUDA kernels this library has launched in the process so far (bench.py `gpu_launches`). */
+SS_API int ss_launch_count(uint64_t* count);
+
+/* Replaces NNDetector.__init__ model construction + load_checkpoint
+ * (root/code/frontend/NNDetector.py:21-53): `blob` is the packed, BN-folded state dict
+ * (softspoken_b200/checkpoint.py:pack_blob).  `max_batch_windows` bounds the windows one
+ * classifier pass holds in its workspace (larger calls are split internally). */
+SS_API int ss_ctx_create(int device, const void* blob, size_t blob_bytes, int max_batch_windows, ss_ctx** ctx);
+SS_API int ss_ctx_destroy(ss_ctx* ctx);
+SS_API int ss_ctx_device_bytes(ss_ctx* ctx, size_t* bytes);
+/* Size the file-level scratch of ss_detect_* for clips of up to `max_samples` samples and up to
+ * `region_cap` regions per clip.  Grows only; a detect call beyond the reservation fails with
+ * SS_E_CAPACITY instead of allocating. */
+SS_API int ss_ctx_reserve(ss_ctx* ctx, int64_t max_samples, int region_cap);
+
+/* NNDetector.plan_detection_job (NNDetector.py:65-80): number of 3 s windows of a clip of
+ * `n_samples` samples at 22,050 Hz once padded (worker.py:58-62); starts are i * 13230. */
+SS_API int64_t ss_plan_windows(int64_t n_samples);
+/* NNDetector.average_overlapping_detections `output_length` (NNDetector.py:168) for a padded length. */
+SS_API int64_t ss_timeline_bins(int64_t n_padded);
+
+/* worker.py:58-62 on the device: dst[0:pad)=0, dst[pad:pad+n)=src, dst[pad+n:n+2pad)=0. */
+SS_API int ss_pad(ss_ctx* ctx, const float* pcm_dev, int64_t n_samples, float* padded_dev, void* stream);
+
+/* K1 — window gather + MelSpectrogram + sqrt(log10(x+1)) + [:, :, :256]
+ * (NNDetector.py:90-96; pytorch_neural_nets.py:92-99,144-153).
+ * pcm_dev: padded clip, n_padded floats.  win_start_dev: n_windows int64 sample offsets (each
+ * start + 65536 <= n_padded is required; samples beyond 65535 of a window never matter).
+ * mel_out_dev: [n_windows][128 mel][256 frames] float32. */
+SS_API int ss_features(ss_ctx* ctx, const float* pcm_dev, int64_t n_padded, const int64_t* win_start_dev,
+                int n_windows, float* mel_out_dev, void* stream);
+
+/* K2-K4 — SpecUNet_2D.forward after the front end (pytorch_neural_nets.py:156-195).
+ * mel_dev: [n_windows][128][256].  logits_dev: [n_windows][256] raw mask logits (no sigmoid).
+ * spec_out_dev: NULL, or [n_windows][2][128][256] for the separation head the reference
+ * computes and discards (worker.py:78-79). */
+SS_API int ss_classify(ss_ctx* ctx, const float* mel_dev, int n_windows, float* logits_dev,
+                float* spec_out_dev, int mode, void* stream);
+
+/* K5 — NNDetector.average_overlapping_detections (NNDetector.py:168-186): float64 overlap-add
+ * mean in window order.  avg_dev: out_len doubles (NaN where count == 0), count_dev: out_len int32. */
+SS_API int ss_average(ss_ctx* ctx, const float* logits_dev, int n_windows, int64_t out_len, double* avg_dev,
+               int32_t* count_dev, void* stream);
+
+/* K6 — NNDetector.find_speech_regions (NNDetector.py:109-141) in bin space: avg > threshold runs
+ * (end inclusive), merged when next_start - cur_end <= gap_bins.  regions_dev: [cap][2] int32
+ * (start_bin, end_bin); n_regions_dev: one int32 = number found (may exceed cap; only cap stored). */
+SS_API int ss_regions(ss_ctx* ctx, const double* avg_dev, const int32_t* count_dev, int64_t out_len,
+               double threshold, int gap_bins, int32_t* regions_dev, int32_t* n_regions_dev, int cap,
+               void* stream);
+
+/* K7 — SilenceWorker.run inner loop `audio[:, s:e] = 0.0` (silencer_ui.py:974-985) for a table of
+ * element ranges inside one packed float32 buffer of n_elems elements. */
+SS_API int ss_silence(ss_ctx* ctx, float* pcm_dev, int64_t n_elems, const ss_interval* intervals_dev,
+               int n_intervals, void* stream);
+
+/* File-level path on device-resident audio: pad -> K1 -> K2/K3 -> K5 -> K6
+ * (ProcessWorker.run per-file body, worker.py:57-97).  pcm_dev is the UNPADDED clip.
+ * Results stay on the device; regions as in ss_regions.  logits_out_dev may be NULL. */
+SS_API int ss_detect_device(ss_ctx* ctx, const float* pcm_dev, int64_t n_samples, int mode,
+                     int32_t* regions_dev, int32_t* n_regions_dev, int cap, float* logits_out_dev,
+                     void* stream);
+
+/* Same with HOST buffers (the reference-facing call: load_audio output in, region bins out).
+ * The clip is streamed to the device in chunks of windows (chunk k+1 uploads on a copy stream while
+ * chunk k computes; consecutive chunks overlap by 52,920 samples because window starts stay on the
+ * global i * 13230 grid), logits accumulate on the device, K5/K6 run once on the whole timeline and
+ * the regions are copied back.  Synchronises.  n_regions receives the number found; at most `cap`
+ * pairs are written.  logits_host: NULL or [n_windows][256]. */
+SS_API int ss_detect_host(ss_ctx* ctx, const float* pcm_host, int64_t n_samples, int mode,
+                   int32_t* regions_host, int cap, int* n_regions, float* logits_host);
+
+/* SilenceWorker.run on one HOST buffer `(channels, n)` float32: zero [begin, end) of every
+ * interval (element offsets into the flattened buffer) on the device and copy the result back. */
+SS_API int ss_silence_host(ss_ctx* ctx, float* pcm_host, int64_t n_elems, const ss_interval* intervals_host,
+                    int n_intervals);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SOFTSPOKEN_B200_H */

@@ -1,0 +1,180 @@
+// Shared declarations of the softspoken_b200 kernels (internal; the public ABI is include/softspoken_b200.h).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <string>
+
+#include "../../include/softspoken_b200.h"
+
+namespace ss {
+
+// ---- constants of the path (mirrors softspoken_b200/spec.py; checked through ss_get_constant) ----
+constexpr int kSampleRate = 22050;                 // settings.py:16
+constexpr int kWindowSamples = 66150;              // NNDetector.py:74
+constexpr int kWindowSamplesUsed = 65536;          // frame 255 ends at sample 65535
+constexpr int kStepSamples = 13230;                // NNDetector.py:75
+constexpr int kPadSamples = 66150;                 // worker.py:59
+constexpr int kWin = 512;                          // settings.py:5
+constexpr int kHop = 256;                          // settings.py:6
+constexpr int kNfft = 2048;                        // pytorch_neural_nets.py:94
+constexpr int kFrames = 256;                       // pytorch_neural_nets.py:150
+constexpr int kMels = 128;                         // pytorch_neural_nets.py:87
+constexpr int kFreqs = 1025;
+constexpr int kMaxMelTaps = 64;
+constexpr int kGapBins = 42;                       // 0.5 s break (worker.py:97) on the 256/3 Hz timeline
+constexpr int kNumSMs = 148;
+
+void set_error(const char* fmt, ...);
+void count_launch(int n = 1);   // every kernel launch of this library is counted (ss_launch_count)
+
+#define SS_CUDA_CHECK(expr)                                                                  \
+  do {                                                                                       \
+    cudaError_t _e = (expr);                                                                 \
+    if (_e != cudaSuccess) {                                                                 \
+      ss::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return SS_E_CUDA;                                                                      \
+    }                                                                                        \
+  } while (0)
+
+#define SS_REQUIRE(cond, code, ...)  \
+  do {                               \
+    if (!(cond)) {                   \
+      ss::set_error(__VA_ARGS__);    \
+      return (code);                 \
+    }                                \
+  } while (0)
+
+// One folded convolution: weights [taps][C_in][C_out] float32, bias [C_out].
+struct ConvW {
+  const float* w = nullptr;
+  const float* b = nullptr;
+  int cin = 0, cout = 0, taps = 0;
+};
+
+struct ResBlockW {
+  ConvW res, c1, c2;
+};
+
+// Front-end tables living on the device.
+struct FrontEnd {
+  const float* window = nullptr;      // [512] Hann (from the checkpoint)
+  const float* tw_a_re = nullptr;     // [512] window[n] *  cos(2 pi n / 2048)
+  const float* tw_a_im = nullptr;     // [512] window[n] * -sin(2 pi n / 2048)
+  const float2* tw512 = nullptr;      // [512] exp(-2 pi i k / 512)
+  const float2* tw1024 = nullptr;     // [512] exp(-2 pi i m / 1024), m < 512
+  const int* mel_start = nullptr;     // [128]
+  const int* mel_count = nullptr;     // [128]
+  const int* mel_offs = nullptr;      // [128]
+  const float* mel_taps = nullptr;    // [n_taps]
+  int n_taps = 0;
+};
+
+enum { RB_CONV1 = 0, RB_CONV2, RB_CONV3, RB_CONV4, RB_BOTTLENECK, RB_ENCODER_OUT, RB_CONV6, RB_CONV7,
+       RB_CONV8, RB_CONV9, RB_SPEC, RB_COUNT };
+
+struct HeadW {
+  const float* flat_w = nullptr;  // [128 mel][32][4]
+  const float* flat_b = nullptr;  // [4]
+  const float* res_w = nullptr;   // [1][4][4]
+  const float* res_b = nullptr;
+  const float* c1_w = nullptr;    // [3][4][4]
+  const float* c1_b = nullptr;
+  const float* c2_w = nullptr;    // [3][4][4]
+  const float* c2_b = nullptr;
+  const float* out_w = nullptr;   // [4]
+  const float* out_b = nullptr;   // [1]
+  const float* spec_w = nullptr;  // [1][32][2]
+  const float* spec_b = nullptr;  // [2]
+};
+
+// fp32 activation workspace for `max_batch` windows (NHWC).
+struct WorkspaceF32 {
+  float* conv1 = nullptr;   // [B,128,256,32]
+  float* pool1 = nullptr;   // [B,64,128,32]
+  float* conv2 = nullptr;   // [B,64,128,64]
+  float* pool2 = nullptr;   // [B,32,64,64]
+  float* conv3 = nullptr;   // [B,32,64,96]
+  float* pool3 = nullptr;   // [B,16,32,96]
+  float* conv4 = nullptr;   // [B,16,32,128]
+  float* pool4 = nullptr;   // [B,8,16,128]
+  float* bott = nullptr;    // [B,8,16,128]
+  float* enc = nullptr;     // [B,8,16,128]
+  float* conv6 = nullptr;   // [B,16,32,96]
+  float* conv7 = nullptr;   // [B,32,64,64]
+  float* conv8 = nullptr;   // [B,64,128,32]
+  float* conv9 = nullptr;   // [B,128,256,32]
+  float* spec = nullptr;    // [B,128,256,32]
+  float* tmp_t = nullptr;   // conv1 output of the block in flight (max size)
+  float* tmp_r = nullptr;   // residual branch of the block in flight (max size)
+};
+
+}  // namespace ss
+
+struct ss_ctx {
+  int device = 0;
+  int max_batch = 0;
+  size_t device_bytes = 0;
+  float* blob_dev = nullptr;          // the whole float payload of the weight blob
+  ss::FrontEnd fe;
+  ss::ResBlockW rb[ss::RB_COUNT];
+  ss::HeadW head;
+  ss::WorkspaceF32 ws;
+  void* tc = nullptr;                 // tensor-core (bf16) state, see conv_tc.cu
+  // file-level scratch (ss_detect_*): grown only inside ss_ctx_reserve_file
+  int64_t file_cap_samples = 0;
+  float* file_mel = nullptr;
+  float* file_logits = nullptr;
+  double* file_avg = nullptr;
+  int32_t* file_cnt = nullptr;
+  int32_t* file_regions = nullptr;
+  int32_t* file_nreg = nullptr;
+  int32_t* scan_tmp = nullptr;        // K6 per-block counts
+  int64_t scan_tmp_len = 0;
+  int file_region_cap = 0;
+  int64_t file_cap_windows = 0;
+  int64_t chunk_windows = 0;          // windows per streamed chunk of ss_detect_*
+  float* intervals = nullptr;         // device interval table of ss_silence_host
+  float* stage_buf[2] = {nullptr, nullptr};   // H2D staging of ss_detect_host (unpadded chunk samples)
+  int64_t stage_cap = 0;
+  cudaEvent_t ev_copied[2] = {nullptr, nullptr};
+  cudaEvent_t ev_consumed[2] = {nullptr, nullptr};
+  cudaStream_t compute_stream = nullptr;
+  cudaStream_t copy_stream = nullptr;
+};
+
+namespace ss {
+
+// features.cu
+int features_init();
+int launch_features(const ss_ctx* ctx, const float* pcm, int64_t n_padded, const int64_t* starts, int n_windows,
+                    float* mel, cudaStream_t st);
+// Virtual padded clip: padded index idx in [valid_begin, valid_end) reads pcm[idx - offset], the rest are 0.
+// starts == nullptr -> window w starts at (w_base + w) * 13230.
+int launch_features_virtual(const ss_ctx* ctx, const float* pcm, int64_t valid_begin, int64_t valid_end,
+                            int64_t offset, const int64_t* starts, int64_t w_base, int n_windows, float* mel,
+                            cudaStream_t st);
+int launch_pad(const float* src, int64_t n, float* dst, cudaStream_t st);
+int launch_window_starts(int64_t* starts, int64_t n_windows, cudaStream_t st);
+// conv_fp32.cu
+int classify_fp32(ss_ctx* ctx, const float* mel, int n_windows, float* logits, float* spec_out, cudaStream_t st);
+// head.cu
+int launch_mask_head_f32(const ss_ctx* ctx, const float* conv9_nhwc, int n_windows, float* logits, cudaStream_t st);
+int launch_spec_out_f32(const ss_ctx* ctx, const float* spec_nhwc, int n_windows, float* spec_out_nchw, cudaStream_t st);
+// postproc.cu
+int launch_average(const float* logits, int n_windows, int64_t out_len, double* avg, int32_t* cnt, cudaStream_t st);
+int launch_regions(const double* avg, const int32_t* cnt, int64_t out_len, double threshold, int gap_bins,
+                   int32_t* regions, int32_t* n_regions, int cap, int32_t* scan_tmp, int64_t scan_tmp_len,
+                   cudaStream_t st);
+int64_t regions_scan_tmp_len(int64_t out_len);
+// silence.cu
+// zero [begin - shift, end - shift) ∩ [0, n_elems) of pcm for every interval
+int launch_silence(float* pcm, int64_t n_elems, int64_t shift, const ss_interval* iv, int n_intervals, cudaStream_t st);
+// conv_tc.cu
+int tc_create(ss_ctx* ctx, const float* blob_host_payload);
+void tc_destroy(ss_ctx* ctx);
+int classify_bf16(ss_ctx* ctx, const float* mel, int n_windows, float* logits, float* spec_out, cudaStream_t st);
+
+}  // namespace ss

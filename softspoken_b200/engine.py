@@ -1,0 +1,192 @@
+"""Thin Python face of the C ABI: one `Engine` = one `ss_ctx` on one GPU.
+
+PyTorch is used for device memory and streams only (tensors in, tensors out,
+`torch.cuda.current_stream()` handed to the kernels); every computation is a
+call into libsoftspoken_b200.so.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib, checkpoint, spec
+from ._lib import lib, check
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+class Engine:
+    def __init__(self, state_dict, device: int | torch.device = 0, max_batch: int = 32, mode: str = "fp32"):
+        if not torch.cuda.is_available() or _lib.device_count() == 0:
+            raise _lib.SoftspokenError(_lib.SS_E_NODEVICE,
+                                       "no CUDA device: softspoken_b200 has no CPU fallback")
+        dev = torch.device(device) if not isinstance(device, int) else torch.device("cuda", device)
+        self.device = torch.device("cuda", dev.index if dev.index is not None else torch.cuda.current_device())
+        self.mode = mode
+        self.max_batch = int(max_batch)
+        blob = checkpoint.pack_blob(state_dict)
+        self._blob = blob
+        ctx = C.c_void_p()
+        check(lib.ss_ctx_create(self.device.index, blob, len(blob), self.max_batch, C.byref(ctx)))
+        self._ctx = ctx
+        self._reserved_samples = -1
+        self._region_cap = 0
+        for name, want in (("sample_rate", spec.SAMPLE_RATE), ("window_samples", spec.WINDOW_SAMPLES),
+                           ("step_samples", spec.STEP_SAMPLES), ("pad_samples", spec.PAD_SAMPLES),
+                           ("n_frames", spec.N_FRAMES), ("n_mels", spec.N_MELS), ("gap_bins", spec.GAP_BINS),
+                           ("threshold", spec.THRESHOLD), ("hop_length", spec.HOP_LENGTH)):
+            got = _lib.get_constant(name)
+            if got != want:
+                raise RuntimeError(f"kernel constant {name}={got} disagrees with settings ({want})")
+
+    # ------------------------------------------------------------------ lifetime
+    def close(self) -> None:
+        if getattr(self, "_ctx", None):
+            lib.ss_ctx_destroy(self._ctx)
+            self._ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _mode(self, mode: Optional[str]) -> int:
+        m = mode or self.mode
+        if m not in _lib.MODES:
+            raise ValueError(f"unknown mode {m!r}; expected one of {sorted(_lib.MODES)}")
+        return _lib.MODES[m]
+
+    def device_bytes(self) -> int:
+        n = C.c_size_t()
+        check(lib.ss_ctx_device_bytes(self._ctx, C.byref(n)))
+        return n.value
+
+    def reserve(self, max_samples: int, region_cap: int = 1 << 16) -> None:
+        if max_samples > self._reserved_samples or region_cap > self._region_cap:
+            check(lib.ss_ctx_reserve(self._ctx, max(int(max_samples), self._reserved_samples, 0),
+                                     max(int(region_cap), self._region_cap)))
+            self._reserved_samples = max(int(max_samples), self._reserved_samples)
+            self._region_cap = max(int(region_cap), self._region_cap)
+
+    # ------------------------------------------------------------------ kernel-level entry points
+    def pad(self, pcm: torch.Tensor) -> torch.Tensor:
+        pcm = self._f32(pcm)
+        out = torch.empty(pcm.numel() + 2 * spec.PAD_SAMPLES, dtype=torch.float32, device=self.device)
+        check(lib.ss_pad(self._ctx, _ptr(pcm), pcm.numel(), _ptr(out), self._stream()))
+        return out
+
+    def features(self, padded: torch.Tensor, starts: torch.Tensor) -> torch.Tensor:
+        """padded f32 `[n]`, starts int64 `[W]` -> mel `[W,128,256]` (K1)."""
+        padded = self._f32(padded)
+        starts = starts.to(device=self.device, dtype=torch.int64).contiguous()
+        W = starts.numel()
+        mel = torch.empty((W, spec.N_MELS, spec.N_FRAMES), dtype=torch.float32, device=self.device)
+        check(lib.ss_features(self._ctx, _ptr(padded), padded.numel(), _ptr(starts), W, _ptr(mel), self._stream()))
+        return mel
+
+    def classify(self, mel: torch.Tensor, want_spec: bool = False, mode: Optional[str] = None):
+        """mel `[W,128,256]` -> logits `[W,256]` (and spec `[W,2,128,256]`) (K2-K4)."""
+        mel = self._f32(mel)
+        W = mel.shape[0]
+        logits = torch.empty((W, spec.N_FRAMES), dtype=torch.float32, device=self.device)
+        spec_out = (torch.empty((W, 2, spec.N_MELS, spec.N_FRAMES), dtype=torch.float32, device=self.device)
+                    if want_spec else None)
+        check(lib.ss_classify(self._ctx, _ptr(mel), W, _ptr(logits), _ptr(spec_out), self._mode(mode),
+                              self._stream()))
+        return (logits, spec_out) if want_spec else logits
+
+    def average(self, logits: torch.Tensor, out_len: int) -> Tuple[torch.Tensor, torch.Tensor]:
+        """logits `[W,256]` -> (avg f64 `[out_len]`, count i32 `[out_len]`) (K5)."""
+        logits = self._f32(logits).reshape(-1, spec.N_FRAMES) if logits.numel() else logits
+        W = logits.shape[0] if logits.numel() else 0
+        avg = torch.empty(out_len, dtype=torch.float64, device=self.device)
+        cnt = torch.empty(out_len, dtype=torch.int32, device=self.device)
+        check(lib.ss_average(self._ctx, _ptr(logits) if W else None, W, out_len, _ptr(avg), _ptr(cnt),
+                             self._stream()))
+        return avg, cnt
+
+    def regions(self, avg: torch.Tensor, cnt: torch.Tensor, threshold: float = spec.THRESHOLD,
+                gap_bins: int = spec.GAP_BINS, cap: int = 1 << 16) -> np.ndarray:
+        """-> int32 `[R,2]` (start_bin, end_bin inclusive) on the host (K6)."""
+        out_len = avg.numel()
+        self.reserve(max(self._reserved_samples, int(out_len * 3 / 256 * spec.SAMPLE_RATE) + 1), cap)
+        reg = torch.empty((cap, 2), dtype=torch.int32, device=self.device)
+        n = torch.zeros(1, dtype=torch.int32, device=self.device)
+        check(lib.ss_regions(self._ctx, _ptr(avg), _ptr(cnt), out_len, float(threshold), int(gap_bins), _ptr(reg),
+                             _ptr(n), cap, self._stream()))
+        k = int(n.item())
+        if k > cap:
+            raise _lib.SoftspokenError(_lib.SS_E_CAPACITY, f"{k} regions exceed capacity {cap}")
+        return reg[:k].cpu().numpy()
+
+    def silence(self, pcm: torch.Tensor, intervals: torch.Tensor) -> None:
+        """In place: zero element ranges `intervals` int64 `[K,2]` of the flat f32 buffer `pcm` (K7)."""
+        assert pcm.is_cuda and pcm.dtype == torch.float32 and pcm.is_contiguous()
+        iv = intervals.to(device=self.device, dtype=torch.int64).contiguous()
+        check(lib.ss_silence(self._ctx, _ptr(pcm), pcm.numel(), _ptr(iv), iv.shape[0], self._stream()))
+
+    # ------------------------------------------------------------------ file-level entry points
+    def detect_device(self, pcm: torch.Tensor, mode: Optional[str] = None, cap: int = 1 << 16,
+                      want_logits: bool = False):
+        """Unpadded device clip -> (regions i32 `[cap,2]` device, n i32 `[1]` device[, logits])."""
+        pcm = self._f32(pcm)
+        n = pcm.numel()
+        self.reserve(n, cap)
+        reg = torch.empty((cap, 2), dtype=torch.int32, device=self.device)
+        cnt = torch.zeros(1, dtype=torch.int32, device=self.device)
+        W = lib.ss_plan_windows(n)
+        lg = torch.empty((W, spec.N_FRAMES), dtype=torch.float32, device=self.device) if want_logits else None
+        check(lib.ss_detect_device(self._ctx, _ptr(pcm), n, self._mode(mode), _ptr(reg), _ptr(cnt), cap, _ptr(lg),
+                                   self._stream()))
+        return (reg, cnt, lg) if want_logits else (reg, cnt)
+
+    def detect_host(self, audio: np.ndarray | torch.Tensor, mode: Optional[str] = None, cap: int = 1 << 16,
+                    want_logits: bool = False):
+        """Host float32 mono clip (what `load_audio` returns) -> int32 `[R,2]` region bins (host)."""
+        if isinstance(audio, torch.Tensor):
+            assert audio.device.type == "cpu" and audio.dtype == torch.float32 and audio.is_contiguous()
+            n, ptr = audio.numel(), C.c_void_p(audio.data_ptr())
+        else:
+            audio = np.ascontiguousarray(audio, dtype=np.float32)
+            n, ptr = audio.size, C.c_void_p(audio.ctypes.data)
+        self.reserve(n, cap)
+        reg = np.empty((cap, 2), dtype=np.int32)
+        k = C.c_int()
+        W = lib.ss_plan_windows(n)
+        lg = np.empty((W, spec.N_FRAMES), dtype=np.float32) if want_logits else None
+        check(lib.ss_detect_host(self._ctx, ptr, n, self._mode(mode), C.c_void_p(reg.ctypes.data), cap,
+                                 C.byref(k), C.c_void_p(lg.ctypes.data) if want_logits else None))
+        if k.value > cap:
+            raise _lib.SoftspokenError(_lib.SS_E_CAPACITY, f"{k.value} regions exceed capacity {cap}")
+        out = reg[:k.value].copy()
+        return (out, lg) if want_logits else out
+
+    def silence_host(self, audio: np.ndarray, intervals: np.ndarray) -> None:
+        """In place on a host float32 buffer (any shape, C-contiguous); `intervals` int64 `[K,2]` flat offsets."""
+        assert audio.dtype == np.float32 and audio.flags.c_contiguous and audio.flags.writeable
+        iv = np.ascontiguousarray(intervals, dtype=np.int64).reshape(-1, 2)
+        self.reserve(max(self._reserved_samples, 0), max(self._region_cap, 1))
+        check(lib.ss_silence_host(self._ctx, C.c_void_p(audio.ctypes.data), audio.size,
+                                  C.c_void_p(iv.ctypes.data), iv.shape[0]))
+
+    def _f32(self, t: torch.Tensor) -> torch.Tensor:
+        if not isinstance(t, torch.Tensor):
+            t = torch.as_tensor(np.asarray(t))
+        return t.to(device=self.device, dtype=torch.float32).contiguous()
+
+
+def plan_windows(n_samples: int) -> int:
+    return int(lib.ss_plan_windows(int(n_samples)))
+
+
+def timeline_bins(n_padded: int) -> int:
+    return int(lib.ss_timeline_bins(int(n_padded)))

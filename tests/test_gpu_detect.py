@@ -1,0 +1,123 @@
+"""End-to-end on the GPU: synthetic wav -> regions -> CSV rows, bit-exact vs the reference goldens."""
+import os
+import types
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN, load_golden
+from softspoken_b200 import spec, synth, wavio
+
+pytestmark = pytest.mark.gpu
+
+
+class _PM:
+    def __init__(self, files):
+        self.files = list(files)
+
+    def get_unprocessed_list(self):
+        return list(self.files)
+
+
+@pytest.fixture(scope="module")
+def detector(sd_seed0, tmp_path_factory):
+    from softspoken_b200 import checkpoint, settings
+    from softspoken_b200.detector import NNDetector
+    d = tmp_path_factory.mktemp("ckpt")
+    path = str(d / "model_checkpoint.pth")
+    checkpoint.save_checkpoint(sd_seed0, path, epoch=7)
+    old = settings.model_dir, settings.model_name
+    settings.model_dir, settings.model_name = str(d), "model_checkpoint.pth"
+    det = NNDetector(_PM([]), mode="fp32")
+    settings.model_dir, settings.model_name = old
+    assert det.load_checkpoint(det.model, path) == 8          # epoch + 1 (NNDetector.py:49-50)
+    yield det
+    det.model.engine.close()
+
+
+@pytest.fixture(scope="module")
+def wavs(tmp_path_factory):
+    d = tmp_path_factory.mktemp("data")
+    a, b = str(d / "clip_seed0.wav"), str(d / "clip_seed1.wav")
+    wavio.write_wav_pcm16(a, synth.synth_pcm16(60.0, 0), 22050)
+    wavio.write_wav_pcm16(b, synth.synth_pcm16(20.0, 1), 22050)
+    return str(d), [a, b]
+
+
+def _margin_report(det, audio):
+    from oracle import postproc as pp
+    times, lg = det.detect_file(audio, want_logits=True)
+    avg, cnt = pp.average_idx(lg.reshape(-1, 1, 256), (len(audio) + 132300) / 22050)
+    return times, lg, pp.min_threshold_margin(avg, cnt)
+
+
+def test_detect_file_matches_golden_rows(detector, clip60):
+    from oracle import postproc as pp
+    want = open(os.path.join(GOLDEN, "detections_seed0.csv")).read().splitlines()[1:23]
+    times, lg, margin = _margin_report(detector, clip60)
+    ref_lg = load_golden("model_seed0.npz")["logits"][:, 0]
+    err = float(np.max(np.abs(lg - ref_lg)))
+    print(f"logit err {err:.3e}; min |avg - 0.1| margin of this clip {margin:.3e}")
+    assert err < margin, "logit error exceeds the threshold margin: bit-exact regions are not decidable"
+    rows = pp.detection_rows("/data/clip_seed0.wav", times, 1)
+    got = pp.csv_text(rows).splitlines()[1:]
+    assert got == want
+
+
+@pytest.mark.parametrize("fast", [True, False])
+def test_process_worker_csv_bit_exact(detector, wavs, tmp_path, fast):
+    """ProcessWorker + DetectionProject over two files == the CSV the reference wrote (IDs continue)."""
+    from softspoken_b200.worker import DetectionProject, ProcessWorker
+    d, files = wavs
+    csv = str(tmp_path / f"det_{fast}.csv")
+    project = DetectionProject(types.SimpleNamespace(current_project={"detections_file": csv}))
+    detector.files_to_process = files
+    detector.detections_project = {f: [] for f in files}
+    planned = detector.plan_detection_job()
+    assert [len(v) for v in planned.values()] == [105, 39]
+    w = ProcessWorker(detector, project, planned, fast=fast)
+    w.run()
+    text = open(csv).read().replace(d, "/data")
+    assert text == open(os.path.join(GOLDEN, "detections_seed0.csv")).read()
+    assert len(w.signals.fileDone.log) == 2 and len(w.signals.finished.log) == 1
+    # a re-opened project continues the IDs (silencer_ui.py:794-812; worker.py:107-112)
+    again = DetectionProject(types.SimpleNamespace(current_project={"detections_file": csv}))
+    assert int(again.df["ID"].max()) == 32
+
+
+def test_process_batch_api_shapes_and_values(detector, clip60):
+    from oracle import postproc as pp
+    g = load_golden("model_seed0.npz")
+    padded = pp.pad_audio(clip60)
+    sp, mk = detector.process_batch(padded, g["starts"][32:64])
+    assert sp.shape == (32, 2, 128, 256) and mk.shape == (32, 1, 256)
+    assert sp.dtype == np.float32 and mk.dtype == np.float32
+    assert np.max(np.abs(mk - g["logits"][32:64])) <= 1e-4 * np.max(np.abs(g["logits"]))
+    assert np.max(np.abs(sp[9] - g["spec_w41"])) <= 1e-4 * np.max(np.abs(g["spec_w41"]))
+
+
+def test_streamed_chunks_equal_resident(detector):
+    """Long-recording path (BASELINE config 4 in miniature): > 1 chunk of 1024 windows streamed from the
+    host must give bitwise the logits and regions of the device-resident run."""
+    eng = detector.model.engine
+    audio = synth.synth_audio(13 * 60 + 7.3, 3)                # 1,318 windows -> 2 chunks
+    reg_h, lg_h = eng.detect_host(audio, want_logits=True)
+    reg_d, n_d, lg_d = eng.detect_device(torch.from_numpy(audio).cuda(), want_logits=True)
+    assert lg_h.shape[0] == 1318 > 1024
+    assert np.array_equal(lg_h, lg_d.cpu().numpy())
+    assert np.array_equal(reg_h, reg_d[: int(n_d.item())].cpu().numpy())
+    # and equal to the kernel-by-kernel pipeline on the materialised padded clip
+    padded = eng.pad(torch.from_numpy(audio).cuda())
+    starts = torch.arange(1318, dtype=torch.int64) * spec.STEP_SAMPLES
+    lg_k = eng.classify(eng.features(padded, starts))
+    assert torch.equal(lg_k, lg_d)
+
+
+def test_short_and_empty_clips(detector):
+    eng = detector.model.engine
+    for n in [0, 1, 100, 13229, 13230, 13231, 66150]:
+        audio = synth.synth_audio(n / 22050 + 1e-9, 5)[:n]
+        reg, lg = eng.detect_host(audio, want_logits=True)
+        assert lg.shape[0] == max(5, int(np.ceil((n + 66150) / 13230)))
+        assert reg.ndim == 2 and reg.shape[1] == 2

@@ -1,0 +1,83 @@
+"""K7 on the GPU: bit-exact silenced buffers vs the real SilenceWorker goldens and the oracle."""
+import hashlib
+
+import numpy as np
+import pandas as pd
+import pytest
+import torch
+
+from conftest import load_golden
+from test_oracle_silence import _inputs
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def engine(sd_seed0):
+    from softspoken_b200.engine import Engine
+    eng = Engine(sd_seed0, 0, max_batch=1, mode="fp32")
+    yield eng
+    eng.close()
+
+
+def test_silence_worker_matches_reference(engine):
+    from softspoken_b200.silencer import SilenceWorker, coerce_erase
+    g = load_golden("silence_cases.npz")
+    store = _inputs(g)
+    df = pd.DataFrame({"file_path": g["rows_path"], "file_name": g["rows_name"], "start_time": g["rows_start"],
+                       "end_time": g["rows_end"], "erase": g["rows_erase"]})
+    written = {}
+    sw = SilenceWorker(coerce_erase(df), "/out", engine=engine,
+                       reader=lambda p: (store[p][0].copy(), store[p][1]),
+                       writer=lambda p, a, sr: written.__setitem__(p, (np.array(a), sr)))
+    sw.run()
+    assert list(written) == list(g["out_paths"])
+    for i, (path, (a, sr)) in enumerate(written.items()):
+        assert a.shape == tuple(g[f"out{i}_shape"]) and sr == int(g[f"out{i}_sr"])
+        assert hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest() == str(g[f"out{i}_sha256"])
+    assert len(sw.signals.finished.log) == 1 and len(sw.signals.fileComplete.log) == 3
+
+
+def test_silence_device_property_random(engine):
+    """Random interval tables (unaligned, overlapping, empty, out of range) on a packed corpus buffer."""
+    rng = np.random.default_rng(4)
+    for n in [1, 3, 4, 5, 17, 4096, 100003]:
+        buf = rng.normal(size=n).astype(np.float32)
+        buf[buf == 0] = 1.0
+        k = int(rng.integers(0, 40))
+        b = rng.integers(-5, n + 5, k)
+        e = b + rng.integers(-3, max(4, n // 3), k)
+        want = buf.copy()
+        for bb, ee in zip(b, e):
+            lo, hi = max(0, int(bb)), min(n, int(ee))
+            if hi > lo:
+                want[lo:hi] = 0.0
+        # device entry point, buffer at an odd element offset so heads/tails are exercised
+        big = torch.zeros(n + 3, device="cuda")
+        view = big[1:1 + n]
+        view.copy_(torch.from_numpy(buf))
+        engine.silence(view, torch.from_numpy(np.stack([b, e], 1).astype(np.int64)) if k else torch.zeros((0, 2), dtype=torch.int64))
+        assert np.array_equal(view.cpu().numpy(), want), n
+        assert float(big[0]) == 0.0 and float(big[n + 1]) == 0.0
+        # host entry point
+        h = buf.copy()
+        engine.silence_host(h, np.stack([b, e], 1).astype(np.int64) if k else np.zeros((0, 2), np.int64))
+        assert np.array_equal(h, want), n
+
+
+def test_config5_shape_intervals(engine):
+    """SURVEY §8d config 5 in miniature: intervals over a packed multi-clip buffer vs the oracle."""
+    from oracle import silence as osil
+    from softspoken_b200 import synth
+    from softspoken_b200.silencer import interval_table
+    n_files, clip_n, sr = 6, 22050 * 20, 22050
+    files, start, end = synth.synth_review_rows(60, n_files, clip_s=20.0, seed=0)
+    rng = np.random.default_rng(9)
+    corpus = rng.normal(0, 0.1, (n_files, clip_n)).astype(np.float32)
+    want = np.stack([osil.silence_buffer(corpus[f], sr, [(s, e) for ff, s, e in zip(files, start, end) if ff == f])[0]
+                     for f in range(n_files)])
+    table = np.concatenate([interval_table([(s, e) for ff, s, e in zip(files, start, end) if ff == f], sr, 1, clip_n,
+                                           base=f * clip_n) for f in range(n_files)])
+    dev = torch.from_numpy(corpus).cuda().reshape(-1)
+    engine.silence(dev, torch.from_numpy(table))
+    assert np.array_equal(dev.cpu().numpy().reshape(n_files, clip_n), want)

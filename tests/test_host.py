@@ -1,0 +1,173 @@
+"""Host-side logic (no GPU): checkpoint packing, wav I/O, row/CSV building, silence indices, sharding."""
+import os
+import struct
+import types
+
+import numpy as np
+import pandas as pd
+import pytest
+import torch
+
+from conftest import GOLDEN, load_golden
+from softspoken_b200 import checkpoint, spec, synth, wavio
+
+
+def test_blob_layout_roundtrip(sd_seed0):
+    blob = checkpoint.pack_blob(sd_seed0)
+    magic, version, n, _ = struct.unpack_from("<IIII", blob, 0)
+    assert magic == checkpoint.BLOB_MAGIC and version == checkpoint.BLOB_VERSION
+    table = {}
+    for i in range(n):
+        name, off, cnt = struct.unpack_from("<48sQQ", blob, 16 + 64 * i)
+        table[name.rstrip(b"\0").decode()] = (off, cnt)
+    payload = np.frombuffer(blob, dtype=np.float32, offset=16 + 64 * n)
+    assert all(off % 4 == 0 for off, _ in table.values())        # 16-byte aligned entries
+    folded = checkpoint.fold_state_dict(sd_seed0)
+    off, cnt = table["conv6.c1.w"]
+    w = payload[off:off + cnt].reshape(9, 256, 96)               # [tap][C_in][C_out]
+    ref = folded["conv6.c1.w"].numpy()                           # [C_out, C_in, 3, 3]
+    assert np.array_equal(w[4], ref[:, :, 1, 1].T) and np.array_equal(w[2], ref[:, :, 0, 2].T)
+    off, cnt = table["conv_flatten.w"]
+    assert np.array_equal(payload[off:off + cnt].reshape(128, 32, 4)[5, 7], sd_seed0["conv_flatten.weight"][:, 7, 5, 0].numpy())
+    off, cnt = table["mel_taps"]
+    assert cnt == 1469
+
+
+def test_strict_state_dict_validation(sd_seed0):
+    bad = dict(sd_seed0)
+    bad.pop("conv8.conv1.0.weight")
+    with pytest.raises(RuntimeError, match="Missing key"):
+        checkpoint.validate_state_dict(bad)
+    bad = dict(sd_seed0)
+    bad["conv8.conv1.0.weight"] = torch.zeros(3)
+    with pytest.raises(RuntimeError, match="size mismatch"):
+        checkpoint.validate_state_dict(bad)
+    bad = dict(sd_seed0)
+    bad["mel_spectrogram.mel_scale.fb"] = torch.ones(1025, 128)   # dense bank: band wider than the kernel walks
+    with pytest.raises(ValueError):
+        checkpoint.pack_blob(bad)
+
+
+def test_checkpoint_file_format(sd_seed0, tmp_path):
+    p = str(tmp_path / "model_checkpoint.pth")
+    checkpoint.save_checkpoint(sd_seed0, p, epoch=3)
+    ck = torch.load(p, map_location="cpu", weights_only=True)      # exactly how the reference loads it
+    assert set(ck) == {"model_state_dict", "epoch"} and ck["epoch"] == 3
+    assert list(ck["model_state_dict"]) == [k for k, _, _ in checkpoint.state_dict_spec()]
+    assert checkpoint.normalise_model_path(".\\root\\models\\x\\model.pth") == "./root/models/x/model.pth"
+
+
+def test_wav_roundtrip_and_header(tmp_path):
+    pcm = synth.synth_pcm16(1.5, 2)
+    p = str(tmp_path / "a.wav")
+    wavio.write_wav_pcm16(p, pcm, 22050)
+    x, sr = wavio.read_wav(p)
+    assert sr == 22050 and x.dtype == np.float32 and np.array_equal(x, synth.synth_audio(1.5, 2))
+    assert wavio.duration_and_rate(p) == (len(pcm) / 22050, 22050)
+    st = np.stack([pcm, -pcm], axis=1)
+    p2 = str(tmp_path / "st.wav")
+    wavio.write_wav_pcm16(p2, st, 44100)
+    y, sr2 = wavio.read_wav(p2)
+    assert y.shape == (2, len(pcm)) and sr2 == 44100 and np.array_equal(y[0], x)
+    p3 = str(tmp_path / "f.wav")
+    wavio.write_wav_float32(p3, x, 8000)
+    z, _ = wavio.read_wav(p3)
+    assert np.array_equal(z, x)
+    with open(str(tmp_path / "bad.wav"), "wb") as f:
+        f.write(b"not a wav")
+    with pytest.raises(wavio.WavError):
+        wavio.read_wav(str(tmp_path / "bad.wav"))
+    from softspoken_b200.worker import load_audio
+    assert load_audio(str(tmp_path / "bad.wav")) == (None, None)      # voice_activity.py:39-41
+    mono, _ = load_audio(p)
+    assert np.array_equal(mono, x)
+    with pytest.raises(NotImplementedError):
+        load_audio(p2)                                                 # 44,100 Hz needs the resampler (f1)
+
+
+def test_rows_and_csv_from_golden_regions(tmp_path):
+    """Host row building + DetectionProject CSV == the text the reference wrote, given the reference's regions."""
+    from softspoken_b200.detector import bin_time_str, plan_windows_from_duration, region_bins_to_times
+    from softspoken_b200.worker import DetectionProject, append_rows
+    g = load_golden("postproc_seed0.npz")
+    want = open(os.path.join(GOLDEN, "detections_seed0.csv")).read().splitlines(keepends=True)
+    bins = np.array([[round(float(s) * 256 / 3), round(float(e) * 256 / 3)] for s, e in g["regions"]])
+    assert [[bin_time_str(a), bin_time_str(b)] for a, b in bins] == g["regions"].tolist()
+    proj = DetectionProject(types.SimpleNamespace(current_project={"detections_file": str(tmp_path / "d.csv")}))
+    append_rows(proj, "/data/clip_seed0.wav", region_bins_to_times(bins))
+    proj.save_detections()
+    assert open(str(tmp_path / "d.csv")).read() == "".join(want[:23])
+    p = load_golden("plan.npz")
+    for d, n in zip(p["durations"], p["n_windows"]):
+        assert len(plan_windows_from_duration(float(d))) == int(n)
+
+
+def test_silence_index_rule_matches_oracle():
+    from oracle import silence as osil
+    from softspoken_b200.silencer import coerce_erase, interval_table, row_to_samples
+    rng = np.random.default_rng(0)
+    for _ in range(2000):
+        sr = int(rng.choice([8000, 22050, 44100, 48000]))
+        n = int(rng.integers(1, 10 * sr))
+        st = float(np.round(rng.uniform(-1, 11), int(rng.integers(0, 8))))
+        et = st + float(rng.uniform(-0.5, 4))
+        assert row_to_samples(st, et, sr, n) == osil.interval_to_samples(st, et, sr, n)
+    # rows: normal, inverted (dropped), clamped to the end, fully beyond the end (dropped); 2 channels at base 100
+    t = interval_table([(0.5, 1.0), (2.0, 1.0), (4.0, 99.0), (9.0, 99.0)], 1000, 2, 5000, base=100)
+    assert t.tolist() == [[600, 1100], [5600, 6100], [4100, 5100], [9100, 10100]]
+    g = load_golden("erase_coercion.npz")
+    df = coerce_erase(pd.DataFrame({"erase": [None if v == "nan" else v for v in g["raw"]]}))
+    assert np.array_equal(df["erase"].to_numpy(), g["coerced"])
+
+
+def test_shard_files_lpt():
+    from softspoken_b200.dist import shard_files
+    assert shard_files([600.0] * 8, 4) == [[0, 4], [1, 5], [2, 6], [3, 7]]      # equal durations: round-robin
+    sh = shard_files([10, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1], 2)
+    assert sorted(sum(sh, [])) == list(range(11)) and sh[0] == [0]
+    assert shard_files([], 3) == [[], [], []]
+
+
+def _gloo_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from softspoken_b200.dist import gather_detections, shard_files
+    files = [f"/data/f{i}.wav" for i in range(7)]
+    mine = shard_files([600.0 - i for i in range(7)], world)[rank]
+    rng = np.random.default_rng(0)
+    per_file = {i: np.sort(rng.integers(0, 5000, (i % 4, 2)), axis=1) for i in range(7)}   # file 0 and 4: no regions
+    local = np.concatenate([np.concatenate([np.full((len(per_file[i]), 1), i), per_file[i]], 1) for i in mine]
+                           + [np.zeros((0, 3), np.int64)]).astype(np.int32)
+    out = gather_detections(local)
+    if rank == 0:
+        want = np.concatenate([np.concatenate([np.full((len(per_file[i]), 1), i), per_file[i]], 1)
+                               for i in range(7)]).astype(np.int32)
+        q.put(bool(np.array_equal(out, want)))
+    else:
+        q.put(out is None)
+    dist.destroy_process_group()
+
+
+def test_gather_detections_gloo_world2():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(60)
+    assert res == [True, True]
+
+
+def test_rows_from_triplets_assigns_ids_in_file_order():
+    from softspoken_b200.dist import rows_from_triplets
+    trip = np.array([[0, 10, 20], [2, 5, 6], [2, 100, 300]], np.int32)
+    rows = rows_from_triplets(["/d/a.wav", "/d/b.wav", "/e/c.wav"], trip)
+    assert [r["ID"] for r in rows] == [1, 2, 3]
+    assert [r["file_name"] for r in rows] == ["a.wav", "c.wav", "c.wav"]
+    assert rows[0]["start_time"] == float("0.1172") - 3

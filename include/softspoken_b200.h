@@ -145,6 +145,12 @@ SS_API int ss_detect_host(ss_ctx* ctx, const float* pcm_host, int64_t n_samples,
 SS_API int ss_silence_host(ss_ctx* ctx, float* pcm_host, int64_t n_elems, const ss_interval* intervals_host,
                     int n_intervals);
 
+/* Test instrumentation (parity localisation, not part of the drop-in surface): copy internal activation
+ * `which` of the last SS_MODE_BF16 ss_classify call to out_dev as NCHW float32 and report its shape.
+ * Also surfaces a tcgen05 pipeline time-out of that call as SS_E_CUDA. */
+SS_API int ss_debug_activation(ss_ctx* ctx, int which, int n_windows, float* out_dev, int* C, int* H, int* W,
+                               void* stream);
+
 #ifdef __cplusplus
 }
 #endif

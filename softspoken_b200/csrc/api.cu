@@ -184,6 +184,9 @@ int run_windows(ss_ctx* ctx, const float* pcm, int64_t valid_begin, int64_t vali
 }
 
 }  // namespace
+
+int check_ctx_public(ss_ctx* ctx) { return check_ctx(ctx); }
+
 }  // namespace ss
 
 using namespace ss;
@@ -569,3 +572,11 @@ int ss_silence_host(ss_ctx* ctx, float* pcm_host, int64_t n_elems, const ss_inte
 }
 
 }  // extern "C"
+
+extern "C" int ss_debug_activation(ss_ctx* ctx, int which, int n_windows, float* out_dev, int* C, int* H, int* W,
+                                   void* stream) {
+  int rc = ss::check_ctx_public(ctx);
+  if (rc) return rc;
+  SS_REQUIRE(C && H && W && n_windows >= 0, SS_E_ARG, "bad ss_debug_activation arguments");
+  return ss::tc_debug_dump(ctx, which, n_windows, out_dev, C, H, W, static_cast<cudaStream_t>(stream));
+}

@@ -1,19 +1,731 @@
-// K2 (throughput mode) — tcgen05 / TMEM implicit-GEMM classifier.  Placeholder until the tensor-core path lands.
+// K2 (throughput mode) — tcgen05 / TMEM implicit-GEMM implementation of the residual U-Net trunk.
+//
+// Replaces the same reference ops as conv_fp32.cu (ResBlock x11, MaxPool2d x4, Upsample x4, torch.cat x4;
+// root/code/backend/pytorch_neural_nets.py:7-41,102-123,156-185) with bf16 operands and fp32 accumulation
+// on the 5th-generation tensor cores.
+//
+// Layout.  Every activation tensor is "planar-8, zero-padded": [B][C/8][H+2][W+2][8] bf16 — one 16-byte
+// vector of 8 channels per padded pixel, one plane per 8 channels, a one-pixel zero border around each
+// image.  With q = y (W+2) + x the flattened padded position, a 3x3 convolution is a sum of nine shifted
+// GEMMs:  out[q, :] = sum_tap  in[q + dy (W+2) + dx, :] . w[tap]   — no im2col, no boundary logic.
+//
+// Kernel.  One CTA owns MT*128 consecutive positions of one image and all N = C_out channels:
+//   * producer warp: per 16-channel K-chunk, two 1-D bulk copies (cp.async.bulk, one per 8-channel plane)
+//     bring the run of positions plus a (W+3)-position halo on each side into shared memory, a third brings
+//     the chunk's packed weights; an mbarrier ring (full/empty) double-buffers the stages;
+//   * MMA warp: one thread issues tcgen05.mma (M=128, N, K=16, kind::f16, bf16 x bf16 -> fp32 in TMEM).
+//     Shared memory holds K-major, un-swizzled core matrices (8 positions x 16 bytes), so the A operand of
+//     tap (dy, dx) is simply the same buffer with the descriptor start address advanced by
+//     (dy (W+2) + dx) * 16 bytes: the halo tile is loaded once and used nine times;
+//   * a second source (the ResBlock's 1x1 residual branch on the block input) accumulates into the same
+//     TMEM tile, so `out = relu(conv2(t) + residual(x))` is one launch;
+//   * 4 epilogue warps: tcgen05.ld the fp32 accumulators, add the folded-BN bias, ReLU, force the border
+//     positions to zero, pack to bf16 and store 16-byte vectors (512 contiguous bytes per warp and plane).
+//     With `upsample` set each value is stored to the 2x2 block of the next level's tensor at a plane
+//     offset, which is how nearest-Upsample and torch.cat([skip, up]) are realised without a pass of
+//     their own.
+// Two CTAs are resident per SM (<= 113 KB shared memory, 256 TMEM columns each), so one CTA's epilogue
+// overlaps the other's MMA stream.
+#include <cuda_bf16.h>
+
+#include <vector>
+
 #include "ss_common.cuh"
 
 namespace ss {
 
-int tc_create(ss_ctx* ctx, const float* blob_host_payload) {
-  (void)ctx; (void)blob_host_payload;
+namespace {
+
+using bf16 = __nv_bfloat16;
+
+constexpr int kStages = 2;
+constexpr int kTcThreads = 192;           // warps 0-3 epilogue, warp 4 producer, warp 5 MMA issuer
+constexpr int kGuardBytes = 1 << 17;      // slack before/after every activation allocation (halo over-reads)
+constexpr uint32_t kSpinLimit = 1u << 22;
+
+// ------------------------------------------------------------------------------------------- PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug must not hang the GPU.  Returns false (and flags the error) on timeout.
+__device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, int* err, int code) {
+  for (uint32_t i = 0; i < kSpinLimit; ++i)
+    if (mbar_try_wait(bar, parity)) return true;
+  atomicExch(err, code);
+  return false;
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major, un-swizzled shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, version 1):
+//   [0,14) start >> 4 | [16,30) LBO >> 4 (stride between the two 16-byte K chunks) |
+//   [32,46) SBO >> 4 (stride between 8-row core matrices) | [46,48) version = 1 | [61,64) layout = 0.
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return (uint64_t)((addr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
+         ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | ((uint64_t)1 << 46);
+}
+// Instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = BF16, both K-major, M = 128.
+__host__ __device__ constexpr uint32_t instr_desc(int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+
+// --------------------------------------------------------------------------------------------- parameters
+struct TcSource {
+  const bf16* in;      // planar-8 padded tensor at the layer's resolution
+  int planes_total;    // C/8 of that tensor
+  int plane0;          // first plane this convolution reads
+  int n_chunks;        // C_in / 16
+  int taps;            // 9 (3x3) or 1 (1x1, centre)
+  const bf16* w;       // packed [n_chunks][taps][2][N][8]
+};
+
+struct TcConv {
+  TcSource src[2];
+  int n_src;
+  int H, W;            // resolution of the inputs (and of the accumulator grid)
+  const float* bias;   // [N]
+  int relu;
+  bf16* out;
+  int out_planes_total, out_plane0, upsample;
+  int MT;              // 128-position tiles per CTA
+  int* err;
+};
+
+template <int N>
+__global__ void __launch_bounds__(kTcThreads)
+conv_tc_kernel(const TcConv p) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int Wp = p.W + 2, Hp = p.H + 2;
+  const int HpWp = Hp * Wp;
+  const int halo = Wp + 1;
+  const int L = p.MT * 128 + 2 * halo;                  // positions staged per plane
+  const uint32_t a_bytes = (uint32_t)L * 32u;           // two planes
+  const uint32_t w_bytes_max = 9u * N * 32u;
+  const uint32_t stage_bytes = a_bytes + w_bytes_max;
+  unsigned char* stage0 = smem;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * stage_bytes);   // full[2], empty[2], acc
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.y;
+  const int q0 = halo + blockIdx.x * p.MT * 128;        // first output position of this CTA
+  const int lo = q0 - halo;                             // first staged position
+
+  const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + kStages), accbar = smem_u32(bars + 2 * kStages);
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(full0 + 8 * s, 1);
+      mbar_init(empty0 + 8 * s, 1);
+    }
+    mbar_init(accbar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 4) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "n"(256));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  int total = 0;
+  for (int s = 0; s < p.n_src; ++s) total += p.src[s].n_chunks;
+
+  if (warp == 4) {
+    // ===================================================================== producer
+    if (lane == 0) {
+      int it = 0;
+      bool ok = true;
+      for (int s = 0; s < p.n_src && ok; ++s) {
+        const TcSource& src = p.src[s];
+        const uint32_t w_bytes = (uint32_t)src.taps * N * 32u;
+        for (int kc = 0; kc < src.n_chunks && ok; ++kc, ++it) {
+          const int st = it % kStages;
+          const uint32_t ph = (uint32_t)(it / kStages) & 1u;
+          ok = mbar_wait(empty0 + 8 * st, ph ^ 1u, p.err, 1);
+          if (!ok) break;
+          const uint32_t dst = smem_u32(stage0 + (size_t)st * stage_bytes);
+          mbar_expect_tx(full0 + 8 * st, a_bytes + w_bytes);
+          const bf16* plane = src.in + (((int64_t)b * src.planes_total + src.plane0 + 2 * kc) * HpWp + lo) * 8;
+          bulk_g2s(dst, plane, (uint32_t)L * 16u, full0 + 8 * st);
+          bulk_g2s(dst + (uint32_t)L * 16u, plane + (int64_t)HpWp * 8, (uint32_t)L * 16u, full0 + 8 * st);
+          bulk_g2s(dst + a_bytes, src.w + (int64_t)kc * src.taps * N * 16, w_bytes, full0 + 8 * st);
+        }
+      }
+    }
+  } else if (warp == 5) {
+    // ===================================================================== MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = instr_desc(N);
+      int it = 0;
+      bool ok = true;
+      for (int s = 0; s < p.n_src && ok; ++s) {
+        const TcSource& src = p.src[s];
+        for (int kc = 0; kc < src.n_chunks && ok; ++kc, ++it) {
+          const int st = it % kStages;
+          const uint32_t ph = (uint32_t)(it / kStages) & 1u;
+          ok = mbar_wait(full0 + 8 * st, ph, p.err, 2);
+          if (!ok) break;
+          tc_fence_after();
+          const uint32_t a0 = smem_u32(stage0 + (size_t)st * stage_bytes);
+          const uint32_t w0 = a0 + a_bytes;
+          for (int tap = 0; tap < src.taps; ++tap) {
+            const int off = (src.taps == 9) ? ((tap / 3 - 1) * Wp + (tap % 3 - 1)) : 0;
+            const uint64_t db = smem_desc(w0 + (uint32_t)tap * N * 32u, N * 16u, 128u);
+            for (int mt = 0; mt < p.MT; ++mt) {
+              const uint64_t da = smem_desc(a0 + (uint32_t)(mt * 128 + halo + off) * 16u, (uint32_t)L * 16u, 128u);
+              tc_mma(tmem_base + (uint32_t)(mt * N), da, db, idesc, (it | tap) ? 1u : 0u);
+            }
+          }
+          tc_commit(empty0 + 8 * st);         // frees the stage once the MMAs that read it retire
+        }
+      }
+      tc_commit(accbar);                      // accumulators complete (also releases the epilogue after a timeout)
+    }
+  } else {
+    // ===================================================================== epilogue (warps 0-3)
+    if (mbar_wait(accbar, 0, p.err, 3)) {
+      tc_fence_after();
+      const int Wp2 = 2 * p.W + 2;
+      const int64_t out_plane_stride = p.upsample ? (int64_t)(2 * p.H + 2) * Wp2 * 8 : (int64_t)HpWp * 8;
+      bf16* out_img = p.out + ((int64_t)b * p.out_planes_total + p.out_plane0) * out_plane_stride;
+      for (int mt = 0; mt < p.MT; ++mt) {
+        const int pos = q0 + mt * 128 + warp * 32 + lane;
+        const int y = pos / Wp, x = pos - y * Wp;
+        const bool interior = (y >= 1) && (y <= p.H) && (x >= 1) && (x <= p.W);
+        const bool in_tensor = pos < HpWp;
+#pragma unroll
+        for (int n0 = 0; n0 < N; n0 += 32) {
+          uint32_t v[32];
+          tc_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(mt * N + n0), v);
+          uint4 pk[4];
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            uint32_t w[4];
+#pragma unroll
+            for (int h = 0; h < 4; ++h) {
+              float f0 = __uint_as_float(v[g * 8 + 2 * h]) + __ldg(p.bias + n0 + g * 8 + 2 * h);
+              float f1 = __uint_as_float(v[g * 8 + 2 * h + 1]) + __ldg(p.bias + n0 + g * 8 + 2 * h + 1);
+              if (p.relu) { f0 = fmaxf(f0, 0.f); f1 = fmaxf(f1, 0.f); }
+              if (!interior) { f0 = 0.f; f1 = 0.f; }
+              __nv_bfloat162 h2 = __floats2bfloat162_rn(f0, f1);
+              w[h] = *reinterpret_cast<uint32_t*>(&h2);
+            }
+            pk[g] = make_uint4(w[0], w[1], w[2], w[3]);
+          }
+          if (!p.upsample) {
+            if (in_tensor) {
+#pragma unroll
+              for (int g = 0; g < 4; ++g)
+                *reinterpret_cast<uint4*>(out_img + (int64_t)(n0 / 8 + g) * out_plane_stride + (int64_t)pos * 8) = pk[g];
+            }
+          } else if (interior) {
+            const int64_t up = (int64_t)(2 * y - 1) * Wp2 + (2 * x - 1);
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              bf16* o = out_img + (int64_t)(n0 / 8 + g) * out_plane_stride + up * 8;
+              *reinterpret_cast<uint4*>(o) = pk[g];
+              *reinterpret_cast<uint4*>(o + 8) = pk[g];
+              *reinterpret_cast<uint4*>(o + (int64_t)Wp2 * 8) = pk[g];
+              *reinterpret_cast<uint4*>(o + (int64_t)Wp2 * 8 + 8) = pk[g];
+            }
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(256));
+  }
+}
+
+// ------------------------------------------------------------------------------------------ small kernels
+// mel f32 [B][128][256] -> channel 0 of plane 0 of a 16-channel planar tensor (planes 0,1; rest stays zero)
+__global__ void mel_to_planar(const float* __restrict__ mel, bf16* __restrict__ out, int64_t n_pix) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_pix) return;
+  const int x = (int)(i % kFrames);
+  const int y = (int)((i / kFrames) % kMels);
+  const int64_t b = i / ((int64_t)kFrames * kMels);
+  const int Wp = kFrames + 2, Hp = kMels + 2;
+  const float m = __ldg(mel + i);
+  __nv_bfloat162 h2 = __floats2bfloat162_rn(m, 0.f);
+  uint4 v = make_uint4(*reinterpret_cast<uint32_t*>(&h2), 0u, 0u, 0u);
+  *reinterpret_cast<uint4*>(out + ((b * 2) * Hp * Wp + (int64_t)(y + 1) * Wp + (x + 1)) * 8) = v;
+}
+
+__device__ __forceinline__ uint32_t bmax2(uint32_t a, uint32_t b) {
+  __nv_bfloat162 r = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&a), *reinterpret_cast<__nv_bfloat162*>(&b));
+  return *reinterpret_cast<uint32_t*>(&r);
+}
+__device__ __forceinline__ uint4 bmax8(uint4 a, uint4 b) {
+  return make_uint4(bmax2(a.x, b.x), bmax2(a.y, b.y), bmax2(a.z, b.z), bmax2(a.w, b.w));
+}
+
+// MaxPool2d(2) on planar tensors: in planes [plane0, plane0+planes) of a tensor with in_planes_total planes at
+// H x W  ->  out [B][planes][H/2+2][W/2+2][8].
+__global__ void pool_planar(const bf16* __restrict__ in, int in_planes_total, int plane0, int planes, int H, int W,
+                            bf16* __restrict__ out, int64_t total) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int W2 = W >> 1, H2 = H >> 1;
+  const int x = (int)(i % W2);
+  int64_t r = i / W2;
+  const int y = (int)(r % H2); r /= H2;
+  const int pl = (int)(r % planes);
+  const int64_t b = r / planes;
+  const int Wp = W + 2, Hp = H + 2, Wq = W2 + 2, Hq = H2 + 2;
+  const uint4* src = reinterpret_cast<const uint4*>(in) + ((b * in_planes_total + plane0 + pl) * Hp + (2 * y + 1)) * (int64_t)Wp + (2 * x + 1);
+  const uint4 m = bmax8(bmax8(__ldg(src), __ldg(src + 1)), bmax8(__ldg(src + Wp), __ldg(src + Wp + 1)));
+  reinterpret_cast<uint4*>(out)[((b * planes + pl) * Hq + (y + 1)) * (int64_t)Wq + (x + 1)] = m;
+}
+
+__device__ __forceinline__ void unpack8(uint4 v, float (&f)[8]) {
+  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+  for (int h = 0; h < 4; ++h) {
+    const float2 t = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[h]));
+    f[2 * h] = t.x;
+    f[2 * h + 1] = t.y;
+  }
+}
+
+// Mask head on planar bf16 conv9 [B][4][130][258][8] (same arithmetic as head.cu:mask_head_f32, fp32 math).
+__global__ void __launch_bounds__(kFrames)
+mask_head_planar(const bf16* __restrict__ conv9, HeadW hw, float* __restrict__ logits) {
+  __shared__ float xf[4][kFrames + 2];
+  __shared__ float c1[4][kFrames + 2];
+  const int t = threadIdx.x, b = blockIdx.x;
+  const int Wp = kFrames + 2, Hp = kMels + 2;
+  const uint4* base = reinterpret_cast<const uint4*>(conv9) + (int64_t)b * 4 * Hp * Wp;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int h = 0; h < kMels; ++h) {
+    const float4* wrow = reinterpret_cast<const float4*>(hw.flat_w + (int64_t)h * 32 * 4);
+#pragma unroll
+    for (int pl = 0; pl < 4; ++pl) {
+      float a[8];
+      unpack8(__ldg(base + ((int64_t)pl * Hp + (h + 1)) * Wp + (t + 1)), a);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float4 w = __ldg(wrow + pl * 8 + k);
+        acc[0] = fmaf(a[k], w.x, acc[0]);
+        acc[1] = fmaf(a[k], w.y, acc[1]);
+        acc[2] = fmaf(a[k], w.z, acc[2]);
+        acc[3] = fmaf(a[k], w.w, acc[3]);
+      }
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < 4; ++c) xf[c][t + 1] = fmaxf(acc[c] + __ldg(hw.flat_b + c), 0.f);
+  if (t < 4) {
+    xf[t][0] = 0.f; xf[t][kFrames + 1] = 0.f;
+    c1[t][0] = 0.f; c1[t][kFrames + 1] = 0.f;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int co = 0; co < 4; ++co) {
+    float v = __ldg(hw.c1_b + co);
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+#pragma unroll
+      for (int ci = 0; ci < 4; ++ci) v = fmaf(__ldg(hw.c1_w + (k * 4 + ci) * 4 + co), xf[ci][t + k], v);
+    c1[co][t + 1] = fmaxf(v, 0.f);
+  }
+  __syncthreads();
+  float logit = __ldg(hw.out_b);
+#pragma unroll
+  for (int co = 0; co < 4; ++co) {
+    float v = __ldg(hw.c2_b + co);
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+#pragma unroll
+      for (int ci = 0; ci < 4; ++ci) v = fmaf(__ldg(hw.c2_w + (k * 4 + ci) * 4 + co), c1[ci][t + k], v);
+    float r = __ldg(hw.res_b + co);
+#pragma unroll
+    for (int ci = 0; ci < 4; ++ci) r = fmaf(__ldg(hw.res_w + ci * 4 + co), xf[ci][t + 1], r);
+    logit = fmaf(__ldg(hw.out_w + co), fmaxf(v + r, 0.f), logit);
+  }
+  logits[(int64_t)b * kFrames + t] = logit;
+}
+
+// spec head tail on planar bf16 [B][4][130][258][8] -> NCHW f32 [B][2][128][256]
+__global__ void spec_out_planar(const bf16* __restrict__ x, HeadW hw, float* __restrict__ out, int64_t n_pixels) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_pixels) return;
+  const int xx = (int)(i % kFrames);
+  const int yy = (int)((i / kFrames) % kMels);
+  const int64_t b = i / ((int64_t)kFrames * kMels);
+  const int Wp = kFrames + 2, Hp = kMels + 2;
+  const uint4* base = reinterpret_cast<const uint4*>(x) + (int64_t)b * 4 * Hp * Wp + (int64_t)(yy + 1) * Wp + (xx + 1);
+  float a0 = __ldg(hw.spec_b), a1 = __ldg(hw.spec_b + 1);
+#pragma unroll
+  for (int pl = 0; pl < 4; ++pl) {
+    float a[8];
+    unpack8(__ldg(base + (int64_t)pl * Hp * Wp), a);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      a0 = fmaf(a[k], __ldg(hw.spec_w + (pl * 8 + k) * 2), a0);
+      a1 = fmaf(a[k], __ldg(hw.spec_w + (pl * 8 + k) * 2 + 1), a1);
+    }
+  }
+  const int64_t plane = (int64_t)kMels * kFrames, pix = i % plane;
+  out[(b * 2) * plane + pix] = fmaxf(a0, 0.f);
+  out[(b * 2 + 1) * plane + pix] = fmaxf(a1, 0.f);
+}
+
+// planar bf16 -> NCHW f32 (debug / parity localisation only)
+__global__ void planar_to_nchw(const bf16* __restrict__ in, int planes_total, int plane0, int C, int H, int W,
+                               float* __restrict__ out, int64_t total) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int x = (int)(i % W);
+  int64_t r = i / W;
+  const int y = (int)(r % H); r /= H;
+  const int c = (int)(r % C);
+  const int64_t b = r / C;
+  const int Wp = W + 2, Hp = H + 2;
+  out[i] = __bfloat162float(in[(((b * planes_total + plane0 + c / 8) * Hp + (y + 1)) * (int64_t)Wp + (x + 1)) * 8 + (c & 7)]);
+}
+
+// ------------------------------------------------------------------------------------------- host state
+struct Tensor {
+  bf16* alloc = nullptr;   // includes guards
+  bf16* data = nullptr;
+  int planes = 0, H = 0, W = 0;
+  size_t bytes = 0;
+};
+
+struct PackedConv {
+  bf16* w = nullptr;
+  int n_chunks = 0, taps = 0, n = 0;
+};
+
+struct TcBlock {
+  PackedConv res, c1, c2;
+  float* bias2 = nullptr;   // b2 + b_res (the fused second launch)
+  const float* bias1 = nullptr;
+};
+
+struct TcState {
+  int max_batch = 0;
+  TcBlock rb[RB_COUNT];
+  Tensor x0, m4, m3, m2, m1, p1, p2, p3, p4, bott, c9, spec;
+  Tensor t[RB_COUNT];
+  int* err = nullptr;
+  size_t bytes = 0;
+};
+
+int alloc_tensor(TcState* st, Tensor* t, int B, int C, int H, int W) {
+  t->planes = C / 8;
+  t->H = H;
+  t->W = W;
+  const size_t body = (size_t)B * t->planes * (H + 2) * (W + 2) * 8 * sizeof(bf16);
+  t->bytes = body + 2 * (size_t)kGuardBytes;
+  SS_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&t->alloc), t->bytes));
+  SS_CUDA_CHECK(cudaMemset(t->alloc, 0, t->bytes));     // zero borders + guards, never overwritten with non-zero
+  t->data = reinterpret_cast<bf16*>(reinterpret_cast<unsigned char*>(t->alloc) + kGuardBytes);
+  st->bytes += t->bytes;
   return SS_OK;
 }
 
-void tc_destroy(ss_ctx* ctx) { (void)ctx; }
+// w: [taps][cin][cout] f32 (host) -> packed bf16 [chunk][tap][2][cout][8] on the device
+int pack_conv(TcState* st, const float* w, int taps, int cin, int cout, PackedConv* out) {
+  const int n_chunks = (cin + 15) / 16;
+  std::vector<bf16> h((size_t)n_chunks * taps * 2 * cout * 8);
+  for (int kc = 0; kc < n_chunks; ++kc)
+    for (int t = 0; t < taps; ++t)
+      for (int hh = 0; hh < 2; ++hh)
+        for (int n = 0; n < cout; ++n)
+          for (int j = 0; j < 8; ++j) {
+            const int c = kc * 16 + hh * 8 + j;
+            const float v = (c < cin) ? w[((size_t)t * cin + c) * cout + n] : 0.f;
+            h[((((size_t)kc * taps + t) * 2 + hh) * cout + n) * 8 + j] = __float2bfloat16(v);
+          }
+  SS_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&out->w), h.size() * sizeof(bf16)));
+  SS_CUDA_CHECK(cudaMemcpy(out->w, h.data(), h.size() * sizeof(bf16), cudaMemcpyHostToDevice));
+  st->bytes += h.size() * sizeof(bf16);
+  out->n_chunks = n_chunks;
+  out->taps = taps;
+  out->n = cout;
+  return SS_OK;
+}
+
+size_t conv_smem_bytes(int N, int W, int MT) {
+  const size_t L = (size_t)MT * 128 + 2 * (W + 3);
+  return kStages * (L * 32 + 9 * (size_t)N * 32) + 128;
+}
+
+int pick_mt(int N, int H, int W) {
+  int mt = 256 / N;                                   // 256 TMEM columns per CTA
+  if (N == 96) mt = 2;
+  const int need = (H * (W + 2) - 2 + 127) / 128;     // tiles that cover one image
+  if (mt > need) mt = need;
+  while (mt > 1 && conv_smem_bytes(N, W, mt) > 112 * 1024) --mt;
+  return mt;
+}
+
+template <int N>
+int launch_conv_n(const TcConv& p, int B, cudaStream_t st) {
+  const size_t smem = conv_smem_bytes(N, p.W, p.MT);
+  static size_t configured = 0;
+  if (smem > configured) {
+    SS_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  const int positions = p.H * (p.W + 2) - 2;          // (1,1) .. (H,W) in flattened padded coordinates
+  const int units = (positions + p.MT * 128 - 1) / (p.MT * 128);
+  conv_tc_kernel<N><<<dim3(units, B), kTcThreads, smem, st>>>(p);
+  SS_CUDA_CHECK(cudaGetLastError());
+  count_launch();
+  return SS_OK;
+}
+
+int launch_conv(const TcConv& p, int N, int B, cudaStream_t st) {
+  switch (N) {
+    case 32: return launch_conv_n<32>(p, B, st);
+    case 64: return launch_conv_n<64>(p, B, st);
+    case 96: return launch_conv_n<96>(p, B, st);
+    case 128: return launch_conv_n<128>(p, B, st);
+  }
+  set_error("unsupported C_out %d", N);
+  return SS_E_ARG;
+}
+
+// One ResBlock: t = relu(conv3x3(x) + b1);  out = relu(conv3x3(t) + conv1x1(x) + b2 + b_res).
+int tc_res_block(TcState* s, int which, const Tensor& x, int x_plane0, int cin, Tensor& out, int out_plane0,
+                 int upsample, int B, cudaStream_t st) {
+  const TcBlock& rb = s->rb[which];
+  Tensor& t = s->t[which];
+  const int N = rb.c1.n;
+  TcConv p{};
+  p.n_src = 1;
+  (void)cin;
+  p.src[0] = TcSource{x.data, x.planes, x_plane0, rb.c1.n_chunks, 9, rb.c1.w};
+  p.H = x.H; p.W = x.W;
+  p.bias = rb.bias1;
+  p.relu = 1;
+  p.out = t.data; p.out_planes_total = t.planes; p.out_plane0 = 0; p.upsample = 0;
+  p.MT = pick_mt(N, x.H, x.W);
+  p.err = s->err;
+  int rc = launch_conv(p, N, B, st);
+  if (rc) return rc;
+  TcConv q{};
+  q.n_src = 2;
+  q.src[0] = TcSource{t.data, t.planes, 0, rb.c2.n_chunks, 9, rb.c2.w};
+  q.src[1] = TcSource{x.data, x.planes, x_plane0, rb.res.n_chunks, 1, rb.res.w};
+  q.H = x.H; q.W = x.W;
+  q.bias = rb.bias2;
+  q.relu = 1;
+  q.out = out.data; q.out_planes_total = out.planes; q.out_plane0 = out_plane0; q.upsample = upsample;
+  q.MT = p.MT;
+  q.err = s->err;
+  return launch_conv(q, N, B, st);
+}
+
+int tc_pool(const Tensor& in, int plane0, int planes, Tensor& out, int B, cudaStream_t st) {
+  const int64_t total = (int64_t)B * planes * (in.H / 2) * (in.W / 2);
+  pool_planar<<<(int)((total + 255) / 256), 256, 0, st>>>(in.data, in.planes, plane0, planes, in.H, in.W, out.data, total);
+  SS_CUDA_CHECK(cudaGetLastError());
+  count_launch();
+  return SS_OK;
+}
+
+}  // namespace
+
+int tc_create(ss_ctx* ctx, const float* hp) {
+  (void)hp;
+  return SS_OK;
+}
+
+// Built lazily on the first bf16 call so that fp32-only users do not pay for the second workspace.
+static int tc_build(ss_ctx* ctx) {
+  if (ctx->tc) return SS_OK;
+  TcState* s = new TcState();
+  ctx->tc = s;
+  s->max_batch = ctx->max_batch;
+  const int B = ctx->max_batch;
+  int rc;
+  // weights: read the folded f32 tensors back from the device blob (already validated at ss_ctx_create)
+  for (int i = 0; i < RB_COUNT; ++i) {
+    const ResBlockW& rb = ctx->rb[i];
+    auto fetch = [&](const ConvW& c, std::vector<float>* w, std::vector<float>* bias) -> int {
+      w->resize((size_t)c.taps * c.cin * c.cout);
+      bias->resize(c.cout);
+      SS_CUDA_CHECK(cudaMemcpy(w->data(), c.w, w->size() * 4, cudaMemcpyDeviceToHost));
+      SS_CUDA_CHECK(cudaMemcpy(bias->data(), c.b, bias->size() * 4, cudaMemcpyDeviceToHost));
+      return SS_OK;
+    };
+    std::vector<float> w, b1, b2, br;
+    if ((rc = fetch(rb.c1, &w, &b1))) return rc;
+    if ((rc = pack_conv(s, w.data(), 9, rb.c1.cin, rb.c1.cout, &s->rb[i].c1))) return rc;
+    if ((rc = fetch(rb.c2, &w, &b2))) return rc;
+    if ((rc = pack_conv(s, w.data(), 9, rb.c2.cin, rb.c2.cout, &s->rb[i].c2))) return rc;
+    if ((rc = fetch(rb.res, &w, &br))) return rc;
+    if ((rc = pack_conv(s, w.data(), 1, rb.res.cin, rb.res.cout, &s->rb[i].res))) return rc;
+    for (size_t k = 0; k < b2.size(); ++k) b2[k] += br[k];
+    SS_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&s->rb[i].bias2), b2.size() * 4));
+    SS_CUDA_CHECK(cudaMemcpy(s->rb[i].bias2, b2.data(), b2.size() * 4, cudaMemcpyHostToDevice));
+    s->rb[i].bias1 = rb.c1.b;
+  }
+  SS_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&s->err), sizeof(int)));
+  SS_CUDA_CHECK(cudaMemset(s->err, 0, sizeof(int)));
+#define T(t, C, H, W) do { if ((rc = alloc_tensor(s, &s->t, B, C, H, W))) return rc; } while (0)
+  T(x0, 16, 128, 256);
+  T(m4, 64, 128, 256);
+  T(p1, 32, 64, 128);
+  T(m3, 128, 64, 128);
+  T(p2, 64, 32, 64);
+  T(m2, 192, 32, 64);
+  T(p3, 96, 16, 32);
+  T(m1, 256, 16, 32);
+  T(p4, 128, 8, 16);
+  T(bott, 128, 8, 16);
+  T(c9, 32, 128, 256);
+  T(spec, 32, 128, 256);
+  T(t[RB_CONV1], 32, 128, 256);
+  T(t[RB_CONV2], 64, 64, 128);
+  T(t[RB_CONV3], 96, 32, 64);
+  T(t[RB_CONV4], 128, 16, 32);
+  T(t[RB_BOTTLENECK], 128, 8, 16);
+  T(t[RB_ENCODER_OUT], 128, 8, 16);
+  T(t[RB_CONV6], 96, 16, 32);
+  T(t[RB_CONV7], 64, 32, 64);
+  T(t[RB_CONV8], 32, 64, 128);
+  T(t[RB_CONV9], 32, 128, 256);
+  T(t[RB_SPEC], 32, 128, 256);
+#undef T
+  ctx->device_bytes += s->bytes;
+  return SS_OK;
+}
+
+void tc_destroy(ss_ctx* ctx) {
+  TcState* s = static_cast<TcState*>(ctx->tc);
+  if (!s) return;
+  Tensor* ts[] = {&s->x0, &s->m4, &s->m3, &s->m2, &s->m1, &s->p1, &s->p2, &s->p3, &s->p4, &s->bott, &s->c9, &s->spec};
+  for (Tensor* t : ts) if (t->alloc) cudaFree(t->alloc);
+  for (int i = 0; i < RB_COUNT; ++i) {
+    if (s->t[i].alloc) cudaFree(s->t[i].alloc);
+    if (s->rb[i].c1.w) cudaFree(s->rb[i].c1.w);
+    if (s->rb[i].c2.w) cudaFree(s->rb[i].c2.w);
+    if (s->rb[i].res.w) cudaFree(s->rb[i].res.w);
+    if (s->rb[i].bias2) cudaFree(s->rb[i].bias2);
+  }
+  if (s->err) cudaFree(s->err);
+  delete s;
+  ctx->tc = nullptr;
+}
 
 int classify_bf16(ss_ctx* ctx, const float* mel, int n_windows, float* logits, float* spec_out, cudaStream_t st) {
-  (void)ctx; (void)mel; (void)n_windows; (void)logits; (void)spec_out; (void)st;
-  set_error("SS_MODE_BF16 is not available in this build");
-  return SS_E_ARG;
+  int rc = tc_build(ctx);
+  if (rc) return rc;
+  TcState* s = static_cast<TcState*>(ctx->tc);
+  for (int b0 = 0; b0 < n_windows; b0 += s->max_batch) {
+    const int B = (n_windows - b0 < s->max_batch) ? (n_windows - b0) : s->max_batch;
+#define SS_TRY(e) do { if ((rc = (e))) return rc; } while (0)
+    const int64_t n_pix = (int64_t)B * kMels * kFrames;
+    mel_to_planar<<<(int)((n_pix + 255) / 256), 256, 0, st>>>(mel + (int64_t)b0 * kMels * kFrames, s->x0.data, n_pix);
+    SS_CUDA_CHECK(cudaGetLastError());
+    count_launch();
+    SS_TRY(tc_res_block(s, RB_CONV1, s->x0, 0, 16, s->m4, 0, 0, B, st));
+    SS_TRY(tc_pool(s->m4, 0, 4, s->p1, B, st));
+    SS_TRY(tc_res_block(s, RB_CONV2, s->p1, 0, 32, s->m3, 0, 0, B, st));
+    SS_TRY(tc_pool(s->m3, 0, 8, s->p2, B, st));
+    SS_TRY(tc_res_block(s, RB_CONV3, s->p2, 0, 64, s->m2, 0, 0, B, st));
+    SS_TRY(tc_pool(s->m2, 0, 12, s->p3, B, st));
+    SS_TRY(tc_res_block(s, RB_CONV4, s->p3, 0, 96, s->m1, 0, 0, B, st));
+    SS_TRY(tc_pool(s->m1, 0, 16, s->p4, B, st));
+    SS_TRY(tc_res_block(s, RB_BOTTLENECK, s->p4, 0, 128, s->bott, 0, 0, B, st));
+    SS_TRY(tc_res_block(s, RB_ENCODER_OUT, s->bott, 0, 128, s->m1, 16, 1, B, st));   // -> up, cat after conv4
+    SS_TRY(tc_res_block(s, RB_CONV6, s->m1, 0, 256, s->m2, 12, 1, B, st));
+    SS_TRY(tc_res_block(s, RB_CONV7, s->m2, 0, 192, s->m3, 8, 1, B, st));
+    SS_TRY(tc_res_block(s, RB_CONV8, s->m3, 0, 128, s->m4, 4, 1, B, st));
+    SS_TRY(tc_res_block(s, RB_CONV9, s->m4, 0, 64, s->c9, 0, 0, B, st));
+    mask_head_planar<<<B, kFrames, 0, st>>>(s->c9.data, ctx->head, logits + (int64_t)b0 * kFrames);
+    SS_CUDA_CHECK(cudaGetLastError());
+    count_launch();
+    if (spec_out) {
+      SS_TRY(tc_res_block(s, RB_SPEC, s->c9, 0, 32, s->spec, 0, 0, B, st));
+      spec_out_planar<<<(int)((n_pix + 255) / 256), 256, 0, st>>>(s->spec.data, ctx->head,
+                                                                 spec_out + (int64_t)b0 * 2 * kMels * kFrames, n_pix);
+      SS_CUDA_CHECK(cudaGetLastError());
+      count_launch();
+    }
+#undef SS_TRY
+  }
+  return SS_OK;
+}
+
+// Debug / parity localisation: copy one internal activation of the last bf16 classify call to NCHW f32.
+// which: 0 conv1, 1 conv2, 2 conv3, 3 conv4, 4 bottleneck, 5 up(encoder_out), 6 up(conv6), 7 up(conv7),
+//        8 up(conv8), 9 conv9, 10 t(conv1_1.conv1), 11 x0 (16 ch).
+int tc_debug_dump(ss_ctx* ctx, int which, int n_windows, float* out, int* C, int* H, int* W, cudaStream_t st) {
+  TcState* s = static_cast<TcState*>(ctx->tc);
+  SS_REQUIRE(s, SS_E_ARG, "bf16 path not initialised");
+  struct Sel { const Tensor* t; int plane0, c; };
+  const Sel table[] = {{&s->m4, 0, 32}, {&s->m3, 0, 64}, {&s->m2, 0, 96}, {&s->m1, 0, 128}, {&s->bott, 0, 128},
+                       {&s->m1, 16, 128}, {&s->m2, 12, 96}, {&s->m3, 8, 64}, {&s->m4, 4, 32}, {&s->c9, 0, 32},
+                       {&s->t[RB_CONV1], 0, 32}, {&s->x0, 0, 16}};
+  SS_REQUIRE(which >= 0 && which < (int)(sizeof(table) / sizeof(table[0])), SS_E_ARG, "bad activation id %d", which);
+  const Sel& e = table[which];
+  *C = e.c; *H = e.t->H; *W = e.t->W;
+  if (out) {
+    const int64_t total = (int64_t)n_windows * e.c * e.t->H * e.t->W;
+    planar_to_nchw<<<(int)((total + 255) / 256), 256, 0, st>>>(e.t->data, e.t->planes, e.plane0, e.c, e.t->H, e.t->W, out, total);
+    SS_CUDA_CHECK(cudaGetLastError());
+  }
+  int herr = 0;
+  SS_CUDA_CHECK(cudaMemcpyAsync(&herr, s->err, sizeof(int), cudaMemcpyDeviceToHost, st));
+  SS_CUDA_CHECK(cudaStreamSynchronize(st));
+  SS_REQUIRE(herr == 0, SS_E_CUDA, "tcgen05 pipeline timed out (role code %d)", herr);
+  return SS_OK;
 }
 
 }  // namespace ss

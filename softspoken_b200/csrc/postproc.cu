@@ -174,6 +174,9 @@ int launch_regions(const double* avg, const int32_t* cnt, int64_t out_len, doubl
   }
   const int n_blocks = (int)((out_len + kTile - 1) / kTile);
   SS_REQUIRE(scan_tmp_len >= 2 * (int64_t)n_blocks, SS_E_CAPACITY, "scan scratch too small");
+  // Two distinct runs are at least 2 bins apart, so gap 0 and 1 both mean "never merge"; a look-back of at
+  // least one bin is still needed to find where a run starts and ends.
+  if (gap_bins < 1) gap_bins = 1;
   const size_t smem = kTile + 2 * gap_bins;
   regions_kernel<0><<<n_blocks, kScanThreads, smem, st>>>(avg, cnt, out_len, threshold, gap_bins, scan_tmp, regions, cap);
   SS_CUDA_CHECK(cudaGetLastError());

@@ -28,7 +28,8 @@ constexpr int kGapBins = 42;                       // 0.5 s break (worker.py:97)
 constexpr int kNumSMs = 148;
 
 void set_error(const char* fmt, ...);
-void count_launch(int n = 1);   // every kernel launch of this library is counted (ss_launch_count)
+void count_launch(int n = 1);
+int check_ctx_public(ss_ctx* ctx);   // every kernel launch of this library is counted (ss_launch_count)
 
 #define SS_CUDA_CHECK(expr)                                                                  \
   do {                                                                                       \
@@ -176,5 +177,6 @@ int launch_silence(float* pcm, int64_t n_elems, int64_t shift, const ss_interval
 int tc_create(ss_ctx* ctx, const float* blob_host_payload);
 void tc_destroy(ss_ctx* ctx);
 int classify_bf16(ss_ctx* ctx, const float* mel, int n_windows, float* logits, float* spec_out, cudaStream_t st);
+int tc_debug_dump(ss_ctx* ctx, int which, int n_windows, float* out, int* C, int* H, int* W, cudaStream_t st);
 
 }  // namespace ss

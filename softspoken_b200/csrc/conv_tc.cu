@@ -30,262 +30,17 @@
 
 #include <vector>
 
+#include "conv_tc_kernel.cuh"
 #include "ss_common.cuh"
 
 namespace ss {
 
 namespace {
 
-using bf16 = __nv_bfloat16;
+using namespace ss::tc;
 
-constexpr int kStages = 2;
-constexpr int kTcThreads = 192;           // warps 0-3 epilogue, warp 4 producer, warp 5 MMA issuer
 constexpr int kGuardBytes = 1 << 17;      // slack before/after every activation allocation (halo over-reads)
-constexpr uint32_t kSpinLimit = 1u << 22;
-
-// ------------------------------------------------------------------------------------------- PTX helpers
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(bar), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-// Bounded wait: a protocol bug must not hang the GPU.  Returns false (and flags the error) on timeout.
-__device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity, int* err, int code) {
-  for (uint32_t i = 0; i < kSpinLimit; ++i)
-    if (mbar_try_wait(bar, parity)) return true;
-  atomicExch(err, code);
-  return false;
-}
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-               "l"(src), "r"(bytes), "r"(bar)
-               : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
-      "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
-// K-major, un-swizzled shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, version 1):
-//   [0,14) start >> 4 | [16,30) LBO >> 4 (stride between the two 16-byte K chunks) |
-//   [32,46) SBO >> 4 (stride between 8-row core matrices) | [46,48) version = 1 | [61,64) layout = 0.
-__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-  return (uint64_t)((addr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
-         ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | ((uint64_t)1 << 46);
-}
-// Instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = BF16, both K-major, M = 128.
-__host__ __device__ constexpr uint32_t instr_desc(int n) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-}
-
-// --------------------------------------------------------------------------------------------- parameters
-struct TcSource {
-  const bf16* in;      // planar-8 padded tensor at the layer's resolution
-  int planes_total;    // C/8 of that tensor
-  int plane0;          // first plane this convolution reads
-  int n_chunks;        // C_in / 16
-  int taps;            // 9 (3x3) or 1 (1x1, centre)
-  const bf16* w;       // packed [n_chunks][taps][2][N][8]
-};
-
-struct TcConv {
-  TcSource src[2];
-  int n_src;
-  int H, W;            // resolution of the inputs (and of the accumulator grid)
-  const float* bias;   // [N]
-  int relu;
-  bf16* out;
-  int out_planes_total, out_plane0, upsample;
-  int MT;              // 128-position tiles per CTA
-  int* err;
-};
-
-template <int N>
-__global__ void __launch_bounds__(kTcThreads)
-conv_tc_kernel(const TcConv p) {
-  extern __shared__ __align__(128) unsigned char smem[];
-  const int Wp = p.W + 2, Hp = p.H + 2;
-  const int HpWp = Hp * Wp;
-  const int halo = Wp + 1;
-  const int L = p.MT * 128 + 2 * halo;                  // positions staged per plane
-  const uint32_t a_bytes = (uint32_t)L * 32u;           // two planes
-  const uint32_t w_bytes_max = 9u * N * 32u;
-  const uint32_t stage_bytes = a_bytes + w_bytes_max;
-  unsigned char* stage0 = smem;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * stage_bytes);   // full[2], empty[2], acc
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 1);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int b = blockIdx.y;
-  const int q0 = halo + blockIdx.x * p.MT * 128;        // first output position of this CTA
-  const int lo = q0 - halo;                             // first staged position
-
-  const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + kStages), accbar = smem_u32(bars + 2 * kStages);
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < kStages; ++s) {
-      mbar_init(full0 + 8 * s, 1);
-      mbar_init(empty0 + 8 * s, 1);
-    }
-    mbar_init(accbar, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (warp == 4) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                 "n"(256));
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  int total = 0;
-  for (int s = 0; s < p.n_src; ++s) total += p.src[s].n_chunks;
-
-  if (warp == 4) {
-    // ===================================================================== producer
-    if (lane == 0) {
-      int it = 0;
-      bool ok = true;
-      for (int s = 0; s < p.n_src && ok; ++s) {
-        const TcSource& src = p.src[s];
-        const uint32_t w_bytes = (uint32_t)src.taps * N * 32u;
-        for (int kc = 0; kc < src.n_chunks && ok; ++kc, ++it) {
-          const int st = it % kStages;
-          const uint32_t ph = (uint32_t)(it / kStages) & 1u;
-          ok = mbar_wait(empty0 + 8 * st, ph ^ 1u, p.err, 1);
-          if (!ok) break;
-          const uint32_t dst = smem_u32(stage0 + (size_t)st * stage_bytes);
-          mbar_expect_tx(full0 + 8 * st, a_bytes + w_bytes);
-          const bf16* plane = src.in + (((int64_t)b * src.planes_total + src.plane0 + 2 * kc) * HpWp + lo) * 8;
-          bulk_g2s(dst, plane, (uint32_t)L * 16u, full0 + 8 * st);
-          bulk_g2s(dst + (uint32_t)L * 16u, plane + (int64_t)HpWp * 8, (uint32_t)L * 16u, full0 + 8 * st);
-          bulk_g2s(dst + a_bytes, src.w + (int64_t)kc * src.taps * N * 16, w_bytes, full0 + 8 * st);
-        }
-      }
-    }
-  } else if (warp == 5) {
-    // ===================================================================== MMA issuer
-    if (lane == 0) {
-      constexpr uint32_t idesc = instr_desc(N);
-      int it = 0;
-      bool ok = true;
-      for (int s = 0; s < p.n_src && ok; ++s) {
-        const TcSource& src = p.src[s];
-        for (int kc = 0; kc < src.n_chunks && ok; ++kc, ++it) {
-          const int st = it % kStages;
-          const uint32_t ph = (uint32_t)(it / kStages) & 1u;
-          ok = mbar_wait(full0 + 8 * st, ph, p.err, 2);
-          if (!ok) break;
-          tc_fence_after();
-          const uint32_t a0 = smem_u32(stage0 + (size_t)st * stage_bytes);
-          const uint32_t w0 = a0 + a_bytes;
-          for (int tap = 0; tap < src.taps; ++tap) {
-            const int off = (src.taps == 9) ? ((tap / 3 - 1) * Wp + (tap % 3 - 1)) : 0;
-            const uint64_t db = smem_desc(w0 + (uint32_t)tap * N * 32u, N * 16u, 128u);
-            for (int mt = 0; mt < p.MT; ++mt) {
-              const uint64_t da = smem_desc(a0 + (uint32_t)(mt * 128 + halo + off) * 16u, (uint32_t)L * 16u, 128u);
-              tc_mma(tmem_base + (uint32_t)(mt * N), da, db, idesc, (it | tap) ? 1u : 0u);
-            }
-          }
-          tc_commit(empty0 + 8 * st);         // frees the stage once the MMAs that read it retire
-        }
-      }
-      tc_commit(accbar);                      // accumulators complete (also releases the epilogue after a timeout)
-    }
-  } else {
-    // ===================================================================== epilogue (warps 0-3)
-    if (mbar_wait(accbar, 0, p.err, 3)) {
-      tc_fence_after();
-      const int Wp2 = 2 * p.W + 2;
-      const int64_t out_plane_stride = p.upsample ? (int64_t)(2 * p.H + 2) * Wp2 * 8 : (int64_t)HpWp * 8;
-      bf16* out_img = p.out + ((int64_t)b * p.out_planes_total + p.out_plane0) * out_plane_stride;
-      for (int mt = 0; mt < p.MT; ++mt) {
-        const int pos = q0 + mt * 128 + warp * 32 + lane;
-        const int y = pos / Wp, x = pos - y * Wp;
-        const bool interior = (y >= 1) && (y <= p.H) && (x >= 1) && (x <= p.W);
-        const bool in_tensor = pos < HpWp;
-#pragma unroll
-        for (int n0 = 0; n0 < N; n0 += 32) {
-          uint32_t v[32];
-          tc_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(mt * N + n0), v);
-          uint4 pk[4];
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            uint32_t w[4];
-#pragma unroll
-            for (int h = 0; h < 4; ++h) {
-              float f0 = __uint_as_float(v[g * 8 + 2 * h]) + __ldg(p.bias + n0 + g * 8 + 2 * h);
-              float f1 = __uint_as_float(v[g * 8 + 2 * h + 1]) + __ldg(p.bias + n0 + g * 8 + 2 * h + 1);
-              if (p.relu) { f0 = fmaxf(f0, 0.f); f1 = fmaxf(f1, 0.f); }
-              if (!interior) { f0 = 0.f; f1 = 0.f; }
-              __nv_bfloat162 h2 = __floats2bfloat162_rn(f0, f1);
-              w[h] = *reinterpret_cast<uint32_t*>(&h2);
-            }
-            pk[g] = make_uint4(w[0], w[1], w[2], w[3]);
-          }
-          if (!p.upsample) {
-            if (in_tensor) {
-#pragma unroll
-              for (int g = 0; g < 4; ++g)
-                *reinterpret_cast<uint4*>(out_img + (int64_t)(n0 / 8 + g) * out_plane_stride + (int64_t)pos * 8) = pk[g];
-            }
-          } else if (interior) {
-            const int64_t up = (int64_t)(2 * y - 1) * Wp2 + (2 * x - 1);
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              bf16* o = out_img + (int64_t)(n0 / 8 + g) * out_plane_stride + up * 8;
-              *reinterpret_cast<uint4*>(o) = pk[g];
-              *reinterpret_cast<uint4*>(o + 8) = pk[g];
-              *reinterpret_cast<uint4*>(o + (int64_t)Wp2 * 8) = pk[g];
-              *reinterpret_cast<uint4*>(o + (int64_t)Wp2 * 8 + 8) = pk[g];
-            }
-          }
-        }
-      }
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 4) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(256));
-  }
-}
+constexpr size_t kSmemBudget = 200 * 1024; // dynamic shared memory of the persistent conv kernel
 
 // ------------------------------------------------------------------------------------------ small kernels
 // mel f32 [B][128][256] -> channel 0 of plane 0 of a 16-channel planar tensor (planes 0,1; rest stays zero)
@@ -339,61 +94,83 @@ __device__ __forceinline__ void unpack8(uint4 v, float (&f)[8]) {
 }
 
 // Mask head on planar bf16 conv9 [B][4][130][258][8] (same arithmetic as head.cu:mask_head_f32, fp32 math).
-__global__ void __launch_bounds__(kFrames)
+// grid (8 frame chunks, B): a CTA produces 32 logits; its 288 threads are 8 mel-row groups x 36 frames
+// (32 + a 2-frame halo each side for the two k=3 1-D convolutions), so the K = 4096 reduction of
+// conv_flatten is spread over 8 x more threads than one-thread-per-frame and the loads stay coalesced.
+constexpr int kHeadFrames = 32, kHeadHalo = 2, kHeadCols = kHeadFrames + 2 * kHeadHalo, kHeadGroups = 8;
+
+__global__ void __launch_bounds__(kHeadCols * kHeadGroups)
 mask_head_planar(const bf16* __restrict__ conv9, HeadW hw, float* __restrict__ logits) {
-  __shared__ float xf[4][kFrames + 2];
-  __shared__ float c1[4][kFrames + 2];
-  const int t = threadIdx.x, b = blockIdx.x;
+  __shared__ float part[kHeadGroups][4][kHeadCols];
+  __shared__ float xf[4][kHeadCols];
+  __shared__ float c1[4][kHeadCols];
+  const int f = threadIdx.x % kHeadCols, hg = threadIdx.x / kHeadCols;
+  const int b = blockIdx.y;
+  const int t = blockIdx.x * kHeadFrames - kHeadHalo + f;          // frame of this column
+  const bool valid = (t >= 0) && (t < kFrames);
   const int Wp = kFrames + 2, Hp = kMels + 2;
   const uint4* base = reinterpret_cast<const uint4*>(conv9) + (int64_t)b * 4 * Hp * Wp;
   float acc[4] = {0.f, 0.f, 0.f, 0.f};
-  for (int h = 0; h < kMels; ++h) {
-    const float4* wrow = reinterpret_cast<const float4*>(hw.flat_w + (int64_t)h * 32 * 4);
+  if (valid) {
+    const int rows = kMels / kHeadGroups;
+    for (int h = hg * rows; h < (hg + 1) * rows; ++h) {
+      const float4* wrow = reinterpret_cast<const float4*>(hw.flat_w + (int64_t)h * 32 * 4);
 #pragma unroll
-    for (int pl = 0; pl < 4; ++pl) {
-      float a[8];
-      unpack8(__ldg(base + ((int64_t)pl * Hp + (h + 1)) * Wp + (t + 1)), a);
+      for (int pl = 0; pl < 4; ++pl) {
+        float a[8];
+        unpack8(__ldg(base + ((int64_t)pl * Hp + (h + 1)) * Wp + (t + 1)), a);
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const float4 w = __ldg(wrow + pl * 8 + k);
-        acc[0] = fmaf(a[k], w.x, acc[0]);
-        acc[1] = fmaf(a[k], w.y, acc[1]);
-        acc[2] = fmaf(a[k], w.z, acc[2]);
-        acc[3] = fmaf(a[k], w.w, acc[3]);
+        for (int k = 0; k < 8; ++k) {
+          const float4 w = __ldg(wrow + pl * 8 + k);
+          acc[0] = fmaf(a[k], w.x, acc[0]);
+          acc[1] = fmaf(a[k], w.y, acc[1]);
+          acc[2] = fmaf(a[k], w.z, acc[2]);
+          acc[3] = fmaf(a[k], w.w, acc[3]);
+        }
       }
     }
   }
 #pragma unroll
-  for (int c = 0; c < 4; ++c) xf[c][t + 1] = fmaxf(acc[c] + __ldg(hw.flat_b + c), 0.f);
-  if (t < 4) {
-    xf[t][0] = 0.f; xf[t][kFrames + 1] = 0.f;
-    c1[t][0] = 0.f; c1[t][kFrames + 1] = 0.f;
+  for (int c = 0; c < 4; ++c) part[hg][c][f] = acc[c];
+  __syncthreads();
+  if (hg == 0) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      float v = 0.f;
+#pragma unroll
+      for (int g = 0; g < kHeadGroups; ++g) v += part[g][c][f];
+      xf[c][f] = valid ? fmaxf(v + __ldg(hw.flat_b + c), 0.f) : 0.f;     // zero padding outside [0, 256)
+    }
   }
   __syncthreads();
+  if (hg == 0 && f >= 1 && f < kHeadCols - 1) {
 #pragma unroll
-  for (int co = 0; co < 4; ++co) {
-    float v = __ldg(hw.c1_b + co);
+    for (int co = 0; co < 4; ++co) {
+      float v = __ldg(hw.c1_b + co);
 #pragma unroll
-    for (int k = 0; k < 3; ++k)
+      for (int k = 0; k < 3; ++k)
 #pragma unroll
-      for (int ci = 0; ci < 4; ++ci) v = fmaf(__ldg(hw.c1_w + (k * 4 + ci) * 4 + co), xf[ci][t + k], v);
-    c1[co][t + 1] = fmaxf(v, 0.f);
+        for (int ci = 0; ci < 4; ++ci) v = fmaf(__ldg(hw.c1_w + (k * 4 + ci) * 4 + co), xf[ci][f + k - 1], v);
+      c1[co][f] = valid ? fmaxf(v, 0.f) : 0.f;
+    }
   }
   __syncthreads();
-  float logit = __ldg(hw.out_b);
+  if (hg == 0 && f >= kHeadHalo && f < kHeadCols - kHeadHalo) {
+    float logit = __ldg(hw.out_b);
 #pragma unroll
-  for (int co = 0; co < 4; ++co) {
-    float v = __ldg(hw.c2_b + co);
+    for (int co = 0; co < 4; ++co) {
+      float v = __ldg(hw.c2_b + co);
 #pragma unroll
-    for (int k = 0; k < 3; ++k)
+      for (int k = 0; k < 3; ++k)
 #pragma unroll
-      for (int ci = 0; ci < 4; ++ci) v = fmaf(__ldg(hw.c2_w + (k * 4 + ci) * 4 + co), c1[ci][t + k], v);
-    float r = __ldg(hw.res_b + co);
+        for (int ci = 0; ci < 4; ++ci) v = fmaf(__ldg(hw.c2_w + (k * 4 + ci) * 4 + co), c1[ci][f + k - 1], v);
+      float r = __ldg(hw.res_b + co);
 #pragma unroll
-    for (int ci = 0; ci < 4; ++ci) r = fmaf(__ldg(hw.res_w + ci * 4 + co), xf[ci][t + 1], r);
-    logit = fmaf(__ldg(hw.out_w + co), fmaxf(v + r, 0.f), logit);
+      for (int ci = 0; ci < 4; ++ci) r = fmaf(__ldg(hw.res_w + ci * 4 + co), xf[ci][f], r);
+      logit = fmaf(__ldg(hw.out_w + co), fmaxf(v + r, 0.f), logit);
+    }
+    logits[(int64_t)b * kFrames + t] = logit;
   }
-  logits[(int64_t)b * kFrames + t] = logit;
 }
 
 // spec head tail on planar bf16 [B][4][130][258][8] -> NCHW f32 [B][2][128][256]
@@ -498,31 +275,35 @@ int pack_conv(TcState* st, const float* w, int taps, int cin, int cout, PackedCo
   return SS_OK;
 }
 
-size_t conv_smem_bytes(int N, int W, int MT) {
-  const size_t L = (size_t)MT * 128 + 2 * (W + 3);
-  return kStages * (L * 32 + 9 * (size_t)N * 32) + 128;
-}
+constexpr size_t kSmemTail = (2 * kMaxStages + 4) * 8 + 128 * 4 + 16;   // barriers + bias + TMEM slot
 
 int pick_mt(int N, int H, int W) {
-  int mt = 256 / N;                                   // 256 TMEM columns per CTA
-  if (N == 96) mt = 2;
+  int mt = kAccCols / N;                              // one 256-column TMEM buffer per work unit
   const int need = (H * (W + 2) - 2 + 127) / 128;     // tiles that cover one image
   if (mt > need) mt = need;
-  while (mt > 1 && conv_smem_bytes(N, W, mt) > 112 * 1024) --mt;
+  while (mt > 1 && 3 * stage_bytes(N, W, mt) + kSmemTail > kSmemBudget) --mt;   // keep >= 3 stages in flight
   return mt;
 }
 
 template <int N>
-int launch_conv_n(const TcConv& p, int B, cudaStream_t st) {
-  const size_t smem = conv_smem_bytes(N, p.W, p.MT);
-  static size_t configured = 0;
-  if (smem > configured) {
-    SS_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
+int launch_conv_n(TcConv p, int B, cudaStream_t st) {
+  const size_t sb = stage_bytes(N, p.W, p.MT);
+  int stages = (int)((kSmemBudget - kSmemTail) / sb);
+  if (stages > kMaxStages) stages = kMaxStages;
+  SS_REQUIRE(stages >= 2, SS_E_ARG, "conv stage of %zu bytes does not fit twice in shared memory", sb);
+  p.stages = stages;
+  const size_t smem = (size_t)stages * sb + kSmemTail;
+  static bool configured = false;
+  if (!configured) {
+    SS_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)kSmemBudget));
+    configured = true;
   }
   const int positions = p.H * (p.W + 2) - 2;          // (1,1) .. (H,W) in flattened padded coordinates
-  const int units = (positions + p.MT * 128 - 1) / (p.MT * 128);
-  conv_tc_kernel<N><<<dim3(units, B), kTcThreads, smem, st>>>(p);
+  p.units_per_image = (positions + p.MT * 128 - 1) / (p.MT * 128);
+  p.total_units = p.units_per_image * B;
+  const int grid = p.total_units < kNumSMs ? p.total_units : kNumSMs;
+  conv_tc_kernel<N><<<grid, kTcThreads, smem, st>>>(p);
   SS_CUDA_CHECK(cudaGetLastError());
   count_launch();
   return SS_OK;
@@ -688,7 +469,8 @@ int classify_bf16(ss_ctx* ctx, const float* mel, int n_windows, float* logits, f
     SS_TRY(tc_res_block(s, RB_CONV7, s->m2, 0, 192, s->m3, 8, 1, B, st));
     SS_TRY(tc_res_block(s, RB_CONV8, s->m3, 0, 128, s->m4, 4, 1, B, st));
     SS_TRY(tc_res_block(s, RB_CONV9, s->m4, 0, 64, s->c9, 0, 0, B, st));
-    mask_head_planar<<<B, kFrames, 0, st>>>(s->c9.data, ctx->head, logits + (int64_t)b0 * kFrames);
+    mask_head_planar<<<dim3(kFrames / kHeadFrames, B), kHeadCols * kHeadGroups, 0, st>>>(s->c9.data, ctx->head,
+                                                                                          logits + (int64_t)b0 * kFrames);
     SS_CUDA_CHECK(cudaGetLastError());
     count_launch();
     if (spec_out) {

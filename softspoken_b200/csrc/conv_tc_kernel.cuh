@@ -1,0 +1,305 @@
+// The tcgen05 implicit-GEMM convolution kernel of conv_tc.cu (see that file's header for the layout).
+//
+// Persistent, warp-specialised, one CTA per SM:
+//   warp 4     producer  — cp.async.bulk (1-D TMA) of activation runs + packed weights into an smem ring
+//   warp 5     MMA       — one thread issues tcgen05.mma into one of two 256-column TMEM accumulator buffers
+//   warps 0-3  epilogue  — tcgen05.ld -> bias / ReLU / border mask -> bf16 -> 16-byte global stores
+// The three roles are decoupled by mbarriers (full/empty per smem stage, acc_full/acc_empty per TMEM
+// buffer), so the loads of unit k+1, the MMAs of unit k and the epilogue of unit k-1 overlap.
+#pragma once
+
+#include <cuda_bf16.h>
+
+#include "ss_common.cuh"
+
+namespace ss {
+namespace tc {
+
+using bf16 = __nv_bfloat16;
+
+constexpr int kMaxStages = 8;
+constexpr int kTcThreads = 192;
+constexpr int kAccCols = 256;             // TMEM columns per accumulator buffer (two buffers = all 512)
+constexpr uint32_t kSpinLimit = 1u << 22;
+
+// ------------------------------------------------------------------------------------------- PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug must not hang the GPU.  Returns false (and flags the error) on timeout.
+__device__ __noinline__ bool mbar_wait(uint32_t bar, uint32_t parity, int* err, int code) {
+#pragma unroll 1
+  for (uint32_t i = 0; i < kSpinLimit; ++i)
+    if (mbar_try_wait(bar, parity)) return true;
+  atomicExch(err, code);
+  return false;
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major, un-swizzled shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, version 1):
+//   [0,14) start >> 4 | [16,30) LBO >> 4 (stride between the two 16-byte K chunks) |
+//   [32,46) SBO >> 4 (stride between 8-row core matrices) | [46,48) version = 1 | [61,64) layout = 0.
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return (uint64_t)((addr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
+         ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | ((uint64_t)1 << 46);
+}
+// Instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = BF16, both K-major, M = 128.
+__host__ __device__ constexpr uint32_t instr_desc(int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+
+// --------------------------------------------------------------------------------------------- parameters
+struct TcSource {
+  const bf16* in;      // planar-8 padded tensor at the layer's resolution
+  int planes_total;    // C/8 of that tensor
+  int plane0;          // first plane this convolution reads
+  int n_chunks;        // C_in / 16
+  int taps;            // 9 (3x3) or 1 (1x1, centre)
+  const bf16* w;       // packed [n_chunks][taps][2][N][8]
+};
+
+struct TcConv {
+  TcSource src[2];
+  int n_src;
+  int H, W;            // resolution of the inputs (and of the accumulator grid)
+  const float* bias;   // [N]
+  int relu;
+  bf16* out;
+  int out_planes_total, out_plane0, upsample;
+  int MT;              // 128-position tiles per work unit
+  int units_per_image, total_units;
+  int stages;          // smem ring depth (<= kMaxStages)
+  int* err;
+};
+
+__host__ __device__ inline size_t stage_bytes(int N, int W, int MT) {
+  return ((size_t)MT * 128 + 2 * (size_t)(W + 3)) * 32 + 9 * (size_t)N * 32;
+}
+
+template <int N>
+__global__ void __launch_bounds__(kTcThreads, 1)
+conv_tc_kernel(const TcConv p) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int Wp = p.W + 2, Hp = p.H + 2;
+  const int HpWp = Hp * Wp;
+  const int halo = Wp + 1;
+  const int L = p.MT * 128 + 2 * halo;                  // positions staged per plane
+  const uint32_t a_bytes = (uint32_t)L * 32u;           // two planes
+  const uint32_t stage_sz = a_bytes + 9u * N * 32u;
+  const int S = p.stages;
+  unsigned char* stage0 = smem;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)S * stage_sz);
+  // bars: full[kMaxStages] | empty[kMaxStages] | acc_full[2] | acc_empty[2]
+  float* bias_s = reinterpret_cast<float*>(bars + 2 * kMaxStages + 4);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bias_s + N);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + kMaxStages);
+  const uint32_t accf0 = smem_u32(bars + 2 * kMaxStages), acce0 = smem_u32(bars + 2 * kMaxStages + 2);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < S; ++s) {
+      mbar_init(full0 + 8 * s, 1);
+      mbar_init(empty0 + 8 * s, 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(accf0 + 8 * i, 1);
+      mbar_init(acce0 + 8 * i, 4);       // one arrival per epilogue warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int i = threadIdx.x; i < N; i += kTcThreads) bias_s[i] = p.bias[i];
+  if (warp == 4) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "n"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 4) {
+    // ===================================================================== producer
+    if (lane == 0) {
+      int it = 0;
+      bool ok = true;
+      for (int u = blockIdx.x; u < p.total_units && ok; u += gridDim.x) {
+        const int b = u / p.units_per_image;
+        const int lo = (u - b * p.units_per_image) * p.MT * 128;   // first staged position (= q0 - halo)
+        for (int s = 0; s < p.n_src && ok; ++s) {
+          const TcSource& src = p.src[s];
+          const uint32_t w_bytes = (uint32_t)src.taps * N * 32u;
+          for (int kc = 0; kc < src.n_chunks; ++kc, ++it) {
+            const int st = it % S;
+            const uint32_t ph = (uint32_t)(it / S) & 1u;
+            ok = mbar_wait(empty0 + 8 * st, ph ^ 1u, p.err, 1);
+            if (!ok) break;
+            const uint32_t dst = smem_u32(stage0 + (size_t)st * stage_sz);
+            mbar_expect_tx(full0 + 8 * st, a_bytes + w_bytes);
+            const bf16* plane = src.in + (((int64_t)b * src.planes_total + src.plane0 + 2 * kc) * HpWp + lo) * 8;
+            bulk_g2s(dst, plane, (uint32_t)L * 16u, full0 + 8 * st);
+            bulk_g2s(dst + (uint32_t)L * 16u, plane + (int64_t)HpWp * 8, (uint32_t)L * 16u, full0 + 8 * st);
+            bulk_g2s(dst + a_bytes, src.w + (int64_t)kc * src.taps * N * 16, w_bytes, full0 + 8 * st);
+          }
+        }
+      }
+    }
+  } else if (warp == 5) {
+    // ===================================================================== MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = instr_desc(N);
+      int it = 0, k = 0;
+      bool ok = true;
+      for (int u = blockIdx.x; u < p.total_units && ok; u += gridDim.x, ++k) {
+        const int buf = k & 1;
+        ok = mbar_wait(acce0 + 8 * buf, (((uint32_t)k >> 1) & 1u) ^ 1u, p.err, 4);   // epilogue drained this buffer
+        if (!ok) break;
+        tc_fence_after();
+        const uint32_t acc = tmem_base + (uint32_t)(buf * kAccCols);
+        bool first = true;
+        for (int s = 0; s < p.n_src && ok; ++s) {
+          const TcSource& src = p.src[s];
+          for (int kc = 0; kc < src.n_chunks; ++kc, ++it) {
+            const int st = it % S;
+            const uint32_t ph = (uint32_t)(it / S) & 1u;
+            ok = mbar_wait(full0 + 8 * st, ph, p.err, 2);
+            if (!ok) break;
+            tc_fence_after();
+            const uint32_t a0 = smem_u32(stage0 + (size_t)st * stage_sz);
+            const uint32_t w0 = a0 + a_bytes;
+            for (int tap = 0; tap < src.taps; ++tap) {
+              const int off = (src.taps == 9) ? ((tap / 3 - 1) * Wp + (tap % 3 - 1)) : 0;
+              const uint64_t db = smem_desc(w0 + (uint32_t)tap * N * 32u, N * 16u, 128u);
+              for (int mt = 0; mt < p.MT; ++mt) {
+                const uint64_t da = smem_desc(a0 + (uint32_t)(mt * 128 + halo + off) * 16u, (uint32_t)L * 16u, 128u);
+                tc_mma(acc + (uint32_t)(mt * N), da, db, idesc, first ? 0u : 1u);
+              }
+              first = false;
+            }
+            tc_commit(empty0 + 8 * st);       // frees the stage once the MMAs that read it retire
+          }
+        }
+        tc_commit(accf0 + 8 * buf);           // this unit's accumulators are complete
+      }
+    }
+  } else {
+    // ===================================================================== epilogue (warps 0-3)
+    const int Wp2 = 2 * p.W + 2;
+    const int64_t out_plane_stride = p.upsample ? (int64_t)(2 * p.H + 2) * Wp2 * 8 : (int64_t)HpWp * 8;
+    int k = 0;
+    bool ok = true;
+    for (int u = blockIdx.x; u < p.total_units && ok; u += gridDim.x, ++k) {
+      const int buf = k & 1;
+      const int b = u / p.units_per_image;
+      const int q0 = halo + (u - b * p.units_per_image) * p.MT * 128;
+      ok = mbar_wait(accf0 + 8 * buf, ((uint32_t)k >> 1) & 1u, p.err, 3);
+      if (!ok) break;
+      tc_fence_after();
+      bf16* out_img = p.out + ((int64_t)b * p.out_planes_total + p.out_plane0) * out_plane_stride;
+      for (int mt = 0; mt < p.MT; ++mt) {
+        const int pos = q0 + mt * 128 + warp * 32 + lane;
+        const int y = pos / Wp, x = pos - y * Wp;
+        const bool interior = (y >= 1) && (y <= p.H) && (x >= 1) && (x <= p.W);
+        const bool in_tensor = pos < HpWp;
+#pragma unroll
+        for (int n0 = 0; n0 < N; n0 += 32) {
+          uint32_t v[32];
+          tc_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(buf * kAccCols + mt * N + n0), v);
+          uint4 pk[4];
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            uint32_t w[4];
+#pragma unroll
+            for (int h = 0; h < 4; ++h) {
+              float f0 = __uint_as_float(v[g * 8 + 2 * h]) + bias_s[n0 + g * 8 + 2 * h];
+              float f1 = __uint_as_float(v[g * 8 + 2 * h + 1]) + bias_s[n0 + g * 8 + 2 * h + 1];
+              if (p.relu) { f0 = fmaxf(f0, 0.f); f1 = fmaxf(f1, 0.f); }
+              if (!interior) { f0 = 0.f; f1 = 0.f; }
+              __nv_bfloat162 h2 = __floats2bfloat162_rn(f0, f1);
+              w[h] = *reinterpret_cast<uint32_t*>(&h2);
+            }
+            pk[g] = make_uint4(w[0], w[1], w[2], w[3]);
+          }
+          if (!p.upsample) {
+            if (in_tensor) {
+#pragma unroll
+              for (int g = 0; g < 4; ++g)
+                *reinterpret_cast<uint4*>(out_img + (int64_t)(n0 / 8 + g) * out_plane_stride + (int64_t)pos * 8) = pk[g];
+            }
+          } else if (interior) {
+            const int64_t up = (int64_t)(2 * y - 1) * Wp2 + (2 * x - 1);
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              bf16* o = out_img + (int64_t)(n0 / 8 + g) * out_plane_stride + up * 8;
+              *reinterpret_cast<uint4*>(o) = pk[g];
+              *reinterpret_cast<uint4*>(o + 8) = pk[g];
+              *reinterpret_cast<uint4*>(o + (int64_t)Wp2 * 8) = pk[g];
+              *reinterpret_cast<uint4*>(o + (int64_t)Wp2 * 8 + 8) = pk[g];
+            }
+          }
+        }
+      }
+      // all of this warp's TMEM reads of the buffer have completed (tcgen05.wait::ld in tc_ld32)
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acce0 + 8 * buf);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512));
+  }
+}
+
+}  // namespace tc
+}  // namespace ss

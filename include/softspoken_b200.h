@@ -151,6 +151,10 @@ SS_API int ss_silence_host(ss_ctx* ctx, float* pcm_host, int64_t n_elems, const 
 SS_API int ss_debug_activation(ss_ctx* ctx, int which, int n_windows, float* out_dev, int* C, int* H, int* W,
                                void* stream);
 
+/* Test instrumentation: choose which tcgen05 conv launch of the next SS_MODE_BF16 ss_classify call records
+ * per-CTA role timers (-1: none) and read back the previous capture ([148][8] int64 cycles; NULL to skip). */
+SS_API int ss_debug_tc_profile(ss_ctx* ctx, int select_launch, long long* out_host);
+
 #ifdef __cplusplus
 }
 #endif

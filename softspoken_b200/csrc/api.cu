@@ -580,3 +580,9 @@ extern "C" int ss_debug_activation(ss_ctx* ctx, int which, int n_windows, float*
   SS_REQUIRE(C && H && W && n_windows >= 0, SS_E_ARG, "bad ss_debug_activation arguments");
   return ss::tc_debug_dump(ctx, which, n_windows, out_dev, C, H, W, static_cast<cudaStream_t>(stream));
 }
+
+extern "C" int ss_debug_tc_profile(ss_ctx* ctx, int select_launch, long long* out_host) {
+  int rc = ss::check_ctx_public(ctx);
+  if (rc) return rc;
+  return ss::tc_debug_profile(ctx, select_launch, out_host);
+}

@@ -237,6 +237,9 @@ struct TcState {
   Tensor x0, m4, m3, m2, m1, p1, p2, p3, p4, bott, c9, spec;
   Tensor t[RB_COUNT];
   int* err = nullptr;
+  long long* prof = nullptr;   // [kNumSMs][8] role timers of the most recent conv launch (debug)
+  int prof_layer = -1;         // launch index to capture (-1: none)
+  int launch_index = 0;
   size_t bytes = 0;
 };
 
@@ -278,15 +281,13 @@ int pack_conv(TcState* st, const float* w, int taps, int cin, int cout, PackedCo
 constexpr size_t kSmemTail = (2 * kMaxStages + 4) * 8 + 128 * 4 + 16;   // barriers + bias + TMEM slot
 
 int pick_mt(int N, int H, int W) {
-  int mt = kAccCols / N;                              // one 256-column TMEM buffer per work unit
-  const int need = (H * (W + 2) - 2 + 127) / 128;     // tiles that cover one image
-  if (mt > need) mt = need;
-  while (mt > 1 && 3 * stage_bytes(N, W, mt) + kSmemTail > kSmemBudget) --mt;   // keep >= 3 stages in flight
-  return mt;
+  (void)H; (void)W;
+  return (N == 96) ? 2 : kAccCols / N;               // == TilesPerUnit<N>::value (compile-time in the kernel)
 }
 
 template <int N>
 int launch_conv_n(TcConv p, int B, cudaStream_t st) {
+  SS_REQUIRE(p.MT == TilesPerUnit<N>::value, SS_E_ARG, "tile count mismatch");
   const size_t sb = stage_bytes(N, p.W, p.MT);
   int stages = (int)((kSmemBudget - kSmemTail) / sb);
   if (stages > kMaxStages) stages = kMaxStages;
@@ -336,6 +337,7 @@ int tc_res_block(TcState* s, int which, const Tensor& x, int x_plane0, int cin, 
   p.out = t.data; p.out_planes_total = t.planes; p.out_plane0 = 0; p.upsample = 0;
   p.MT = pick_mt(N, x.H, x.W);
   p.err = s->err;
+  p.prof = (s->launch_index++ == s->prof_layer) ? s->prof : nullptr;
   int rc = launch_conv(p, N, B, st);
   if (rc) return rc;
   TcConv q{};
@@ -348,6 +350,7 @@ int tc_res_block(TcState* s, int which, const Tensor& x, int x_plane0, int cin, 
   q.out = out.data; q.out_planes_total = out.planes; q.out_plane0 = out_plane0; q.upsample = upsample;
   q.MT = p.MT;
   q.err = s->err;
+  q.prof = (s->launch_index++ == s->prof_layer) ? s->prof : nullptr;
   return launch_conv(q, N, B, st);
 }
 
@@ -398,6 +401,8 @@ static int tc_build(ss_ctx* ctx) {
   }
   SS_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&s->err), sizeof(int)));
   SS_CUDA_CHECK(cudaMemset(s->err, 0, sizeof(int)));
+  SS_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&s->prof), kNumSMs * 8 * sizeof(long long)));
+  SS_CUDA_CHECK(cudaMemset(s->prof, 0, kNumSMs * 8 * sizeof(long long)));
 #define T(t, C, H, W) do { if ((rc = alloc_tensor(s, &s->t, B, C, H, W))) return rc; } while (0)
   T(x0, 16, 128, 256);
   T(m4, 64, 128, 256);
@@ -440,6 +445,7 @@ void tc_destroy(ss_ctx* ctx) {
     if (s->rb[i].bias2) cudaFree(s->rb[i].bias2);
   }
   if (s->err) cudaFree(s->err);
+  if (s->prof) cudaFree(s->prof);
   delete s;
   ctx->tc = nullptr;
 }
@@ -448,6 +454,7 @@ int classify_bf16(ss_ctx* ctx, const float* mel, int n_windows, float* logits, f
   int rc = tc_build(ctx);
   if (rc) return rc;
   TcState* s = static_cast<TcState*>(ctx->tc);
+  s->launch_index = 0;
   for (int b0 = 0; b0 < n_windows; b0 += s->max_batch) {
     const int B = (n_windows - b0 < s->max_batch) ? (n_windows - b0) : s->max_batch;
 #define SS_TRY(e) do { if ((rc = (e))) return rc; } while (0)
@@ -510,4 +517,20 @@ int tc_debug_dump(ss_ctx* ctx, int which, int n_windows, float* out, int* C, int
   return SS_OK;
 }
 
+}  // namespace ss
+
+namespace ss {
+// Debug: select which conv launch (0-based, in issue order within one ss_classify call) records role timers,
+// and read the timers back ([148][8] int64: producer empty-wait, mma acc-empty-wait, mma full-wait, mma total,
+// epilogue acc-full-wait, epilogue total, -, units).
+int tc_debug_profile(ss_ctx* ctx, int select_launch, long long* out_host) {
+  TcState* s = static_cast<TcState*>(ctx->tc);
+  SS_REQUIRE(s, SS_E_ARG, "bf16 path not initialised");
+  if (out_host) {
+    SS_CUDA_CHECK(cudaDeviceSynchronize());
+    SS_CUDA_CHECK(cudaMemcpy(out_host, s->prof, kNumSMs * 8 * sizeof(long long), cudaMemcpyDeviceToHost));
+  }
+  s->prof_layer = select_launch;
+  return SS_OK;
+}
 }  // namespace ss

@@ -53,6 +53,12 @@ __device__ __noinline__ bool mbar_wait(uint32_t bar, uint32_t parity, int* err, 
   atomicExch(err, code);
   return false;
 }
+__device__ __forceinline__ bool mbar_wait_t(uint32_t bar, uint32_t parity, int* err, int code, long long& acc) {
+  const long long t0 = clock64();
+  const bool ok = mbar_wait(bar, parity, err, code);
+  acc += clock64() - t0;
+  return ok;
+}
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
                "l"(src), "r"(bytes), "r"(bar)
@@ -82,6 +88,21 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
         "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
       : "r"(taddr));
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// One lane of a converged warp (the CUTLASS elect_one_sync idiom).  Keeping the role loops warp-uniform and
+// predicating only the issuing instruction lets the compiler hold descriptors in uniform registers, which
+// tcgen05.mma / cp.async.bulk consume directly (no per-issue R2UR waterfall).
+__device__ __forceinline__ uint32_t elect_one() {
+  uint32_t pred = 0, lane_out = 0;
+  asm volatile(
+      "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+      "elect.sync rx|px, %2;\n\t"
+      "@px mov.s32 %1, 1;\n\t"
+      "mov.s32 %0, rx;\n\t}"
+      : "+r"(lane_out), "+r"(pred)
+      : "r"(0xFFFFFFFFu));
+  return pred;
 }
 
 // K-major, un-swizzled shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, version 1):
@@ -118,20 +139,28 @@ struct TcConv {
   int units_per_image, total_units;
   int stages;          // smem ring depth (<= kMaxStages)
   int* err;
+  long long* prof;     // optional [gridDim.x][8] cycle counters (role wait/busy times), may be null
 };
 
 __host__ __device__ inline size_t stage_bytes(int N, int W, int MT) {
   return ((size_t)MT * 128 + 2 * (size_t)(W + 3)) * 32 + 9 * (size_t)N * 32;
 }
 
+// 128-position tiles per work unit: one 256-column TMEM accumulator buffer holds MT tiles of N columns.
+template <int N>
+struct TilesPerUnit {
+  static constexpr int value = (N == 96) ? 2 : kAccCols / N;
+};
+
 template <int N>
 __global__ void __launch_bounds__(kTcThreads, 1)
 conv_tc_kernel(const TcConv p) {
   extern __shared__ __align__(128) unsigned char smem[];
+  constexpr int MT = TilesPerUnit<N>::value;
   const int Wp = p.W + 2, Hp = p.H + 2;
   const int HpWp = Hp * Wp;
   const int halo = Wp + 1;
-  const int L = p.MT * 128 + 2 * halo;                  // positions staged per plane
+  const int L = MT * 128 + 2 * halo;                  // positions staged per plane
   const uint32_t a_bytes = (uint32_t)L * 32u;           // two planes
   const uint32_t stage_sz = a_bytes + 9u * N * 32u;
   const int S = p.stages;
@@ -168,68 +197,104 @@ conv_tc_kernel(const TcConv p) {
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 4) {
-    // ===================================================================== producer
-    if (lane == 0) {
-      int it = 0;
-      bool ok = true;
-      for (int u = blockIdx.x; u < p.total_units && ok; u += gridDim.x) {
-        const int b = u / p.units_per_image;
-        const int lo = (u - b * p.units_per_image) * p.MT * 128;   // first staged position (= q0 - halo)
-        for (int s = 0; s < p.n_src && ok; ++s) {
-          const TcSource& src = p.src[s];
-          const uint32_t w_bytes = (uint32_t)src.taps * N * 32u;
-          for (int kc = 0; kc < src.n_chunks; ++kc, ++it) {
-            const int st = it % S;
-            const uint32_t ph = (uint32_t)(it / S) & 1u;
-            ok = mbar_wait(empty0 + 8 * st, ph ^ 1u, p.err, 1);
-            if (!ok) break;
-            const uint32_t dst = smem_u32(stage0 + (size_t)st * stage_sz);
+    // ===================================================================== producer (warp-uniform)
+    int it = 0;
+    bool ok = true;
+    long long w_empty = 0;
+    for (int u = blockIdx.x; u < p.total_units && ok; u += gridDim.x) {
+      const int b = u / p.units_per_image;
+      const int lo = (u - b * p.units_per_image) * MT * 128;   // first staged position (= q0 - halo)
+      for (int s = 0; s < p.n_src && ok; ++s) {
+        const TcSource& src = p.src[s];
+        const uint32_t w_bytes = (uint32_t)src.taps * N * 32u;
+        for (int kc = 0; kc < src.n_chunks; ++kc, ++it) {
+          const int st = it % S;
+          const uint32_t ph = (uint32_t)(it / S) & 1u;
+          ok = mbar_wait_t(empty0 + 8 * st, ph ^ 1u, p.err, 1, w_empty);
+          if (!ok) break;
+          const uint32_t dst = smem_u32(stage0 + (size_t)st * stage_sz);
+          const bf16* plane = src.in + (((int64_t)b * src.planes_total + src.plane0 + 2 * kc) * HpWp + lo) * 8;
+          if (elect_one()) {
             mbar_expect_tx(full0 + 8 * st, a_bytes + w_bytes);
-            const bf16* plane = src.in + (((int64_t)b * src.planes_total + src.plane0 + 2 * kc) * HpWp + lo) * 8;
             bulk_g2s(dst, plane, (uint32_t)L * 16u, full0 + 8 * st);
             bulk_g2s(dst + (uint32_t)L * 16u, plane + (int64_t)HpWp * 8, (uint32_t)L * 16u, full0 + 8 * st);
             bulk_g2s(dst + a_bytes, src.w + (int64_t)kc * src.taps * N * 16, w_bytes, full0 + 8 * st);
           }
+          __syncwarp();
         }
       }
     }
+    if (p.prof && lane == 0) p.prof[blockIdx.x * 8 + 0] = w_empty;
   } else if (warp == 5) {
-    // ===================================================================== MMA issuer
-    if (lane == 0) {
-      constexpr uint32_t idesc = instr_desc(N);
-      int it = 0, k = 0;
-      bool ok = true;
-      for (int u = blockIdx.x; u < p.total_units && ok; u += gridDim.x, ++k) {
-        const int buf = k & 1;
-        ok = mbar_wait(acce0 + 8 * buf, (((uint32_t)k >> 1) & 1u) ^ 1u, p.err, 4);   // epilogue drained this buffer
-        if (!ok) break;
-        tc_fence_after();
-        const uint32_t acc = tmem_base + (uint32_t)(buf * kAccCols);
-        bool first = true;
-        for (int s = 0; s < p.n_src && ok; ++s) {
-          const TcSource& src = p.src[s];
-          for (int kc = 0; kc < src.n_chunks; ++kc, ++it) {
-            const int st = it % S;
-            const uint32_t ph = (uint32_t)(it / S) & 1u;
-            ok = mbar_wait(full0 + 8 * st, ph, p.err, 2);
-            if (!ok) break;
-            tc_fence_after();
-            const uint32_t a0 = smem_u32(stage0 + (size_t)st * stage_sz);
-            const uint32_t w0 = a0 + a_bytes;
-            for (int tap = 0; tap < src.taps; ++tap) {
-              const int off = (src.taps == 9) ? ((tap / 3 - 1) * Wp + (tap % 3 - 1)) : 0;
-              const uint64_t db = smem_desc(w0 + (uint32_t)tap * N * 32u, N * 16u, 128u);
-              for (int mt = 0; mt < p.MT; ++mt) {
-                const uint64_t da = smem_desc(a0 + (uint32_t)(mt * 128 + halo + off) * 16u, (uint32_t)L * 16u, 128u);
-                tc_mma(acc + (uint32_t)(mt * N), da, db, idesc, first ? 0u : 1u);
+    // ===================================================================== MMA issuer (warp-uniform)
+    constexpr uint32_t idesc = instr_desc(N);
+    int tap_off[9];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) tap_off[t] = (t / 3 - 1) * Wp + (t % 3 - 1);
+    // descriptor high words are loop-invariant; the low word is (LBO >> 4) << 16 | (address >> 4)
+    const uint32_t a_hi = (128u >> 4) | (1u << 14), b_hi = a_hi;
+    const uint32_t a_lo_base = ((uint32_t)L & 0x3FFFu) << 16;            // LBO = L * 16 bytes
+    const uint32_t b_lo_base = ((uint32_t)N & 0x3FFFu) << 16;            // LBO = N * 16 bytes
+    int it = 0, k = 0;
+    bool ok = true;
+    long long w_acce = 0, w_full = 0;
+    const long long t_begin = clock64();
+    for (int u = blockIdx.x; u < p.total_units && ok; u += gridDim.x, ++k) {
+      const int buf = k & 1;
+      ok = mbar_wait_t(acce0 + 8 * buf, (((uint32_t)k >> 1) & 1u) ^ 1u, p.err, 4, w_acce);   // epilogue drained this buffer
+      if (!ok) break;
+      tc_fence_after();
+      const uint32_t acc = tmem_base + (uint32_t)(buf * kAccCols);
+      uint32_t accumulate = 0;
+      for (int s = 0; s < p.n_src && ok; ++s) {
+        const TcSource& src = p.src[s];
+        for (int kc = 0; kc < src.n_chunks; ++kc, ++it) {
+          const int st = it % S;
+          const uint32_t ph = (uint32_t)(it / S) & 1u;
+          ok = mbar_wait_t(full0 + 8 * st, ph, p.err, 2, w_full);
+          if (!ok) break;
+          tc_fence_after();
+          const uint32_t a0 = smem_u32(stage0 + (size_t)st * stage_sz);
+          const uint32_t a_lo0 = a_lo_base | ((a0 >> 4) + (uint32_t)halo);          // centre tap, tile 0
+          const uint32_t b_lo0 = b_lo_base | ((a0 + a_bytes) >> 4);
+          // Straight-line issue: every descriptor is (loop-invariant high word, base + compile-time step), so the
+          // MMAs go out back to back from uniform registers (a dependent uniform-ALU chain per MMA costs ~90
+          // cycles, twice the 32 + N/4 cycles the shared-memory operand fetch allows; tools/umma_bench.cu).
+          if (elect_one()) {
+            if (src.taps == 9) {
+#pragma unroll
+              for (int tap = 0; tap < 9; ++tap) {
+                const uint64_t db = ((uint64_t)b_hi << 32) | (uint64_t)(b_lo0 + (uint32_t)(tap * N * 2));
+                const uint32_t a_lo_tap = a_lo0 + (uint32_t)tap_off[tap];
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt) {
+                  const uint64_t da = ((uint64_t)a_hi << 32) | (uint64_t)(a_lo_tap + (uint32_t)(mt * 128));
+                  tc_mma(acc + (uint32_t)(mt * N), da, db, idesc, tap == 0 ? accumulate : 1u);
+                }
               }
-              first = false;
+            } else {
+              const uint64_t db = ((uint64_t)b_hi << 32) | (uint64_t)b_lo0;
+#pragma unroll
+              for (int mt = 0; mt < MT; ++mt) {
+                const uint64_t da = ((uint64_t)a_hi << 32) | (uint64_t)(a_lo0 + (uint32_t)(mt * 128));
+                tc_mma(acc + (uint32_t)(mt * N), da, db, idesc, accumulate);
+              }
             }
-            tc_commit(empty0 + 8 * st);       // frees the stage once the MMAs that read it retire
           }
+          __syncwarp();
+          accumulate = 1;
+          if (elect_one()) tc_commit(empty0 + 8 * st);     // frees the stage once the MMAs that read it retire
+          __syncwarp();
         }
-        tc_commit(accf0 + 8 * buf);           // this unit's accumulators are complete
       }
+      if (elect_one()) tc_commit(accf0 + 8 * buf);         // this unit's accumulators are complete
+      __syncwarp();
+    }
+    if (p.prof && lane == 0) {
+      p.prof[blockIdx.x * 8 + 1] = w_acce;
+      p.prof[blockIdx.x * 8 + 2] = w_full;
+      p.prof[blockIdx.x * 8 + 3] = clock64() - t_begin;
+      p.prof[blockIdx.x * 8 + 7] = k;
     }
   } else {
     // ===================================================================== epilogue (warps 0-3)
@@ -237,15 +302,17 @@ conv_tc_kernel(const TcConv p) {
     const int64_t out_plane_stride = p.upsample ? (int64_t)(2 * p.H + 2) * Wp2 * 8 : (int64_t)HpWp * 8;
     int k = 0;
     bool ok = true;
+    long long w_accf = 0;
+    const long long t_begin = clock64();
     for (int u = blockIdx.x; u < p.total_units && ok; u += gridDim.x, ++k) {
       const int buf = k & 1;
       const int b = u / p.units_per_image;
-      const int q0 = halo + (u - b * p.units_per_image) * p.MT * 128;
-      ok = mbar_wait(accf0 + 8 * buf, ((uint32_t)k >> 1) & 1u, p.err, 3);
+      const int q0 = halo + (u - b * p.units_per_image) * MT * 128;
+      ok = mbar_wait_t(accf0 + 8 * buf, ((uint32_t)k >> 1) & 1u, p.err, 3, w_accf);
       if (!ok) break;
       tc_fence_after();
       bf16* out_img = p.out + ((int64_t)b * p.out_planes_total + p.out_plane0) * out_plane_stride;
-      for (int mt = 0; mt < p.MT; ++mt) {
+      for (int mt = 0; mt < MT; ++mt) {
         const int pos = q0 + mt * 128 + warp * 32 + lane;
         const int y = pos / Wp, x = pos - y * Wp;
         const bool interior = (y >= 1) && (y <= p.H) && (x >= 1) && (x <= p.W);
@@ -292,6 +359,10 @@ conv_tc_kernel(const TcConv p) {
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(acce0 + 8 * buf);
+    }
+    if (p.prof && threadIdx.x == 0) {
+      p.prof[blockIdx.x * 8 + 4] = w_accf;
+      p.prof[blockIdx.x * 8 + 5] = clock64() - t_begin;
     }
   }
   tc_fence_before();

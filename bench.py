@@ -300,7 +300,8 @@ def run_b200(args):
             "metric": "audio_hours_per_sec", "value": value, "unit": "audio-hours/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_dev / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32" if args.mode == "fp32" else "bf16", "data": "synthetic",
+            "dtype": {"fp32": "f32", "bf16": "bf16", "f16": "f16", "f16x3": "f16x3 (fp16 hi/lo split operands, fp32 accumulate)"}[args.mode],
+            "data": "synthetic",
             "config": {"workload": f"config2: 1000x10-min mono 22.05 kHz corpus, step = {C} clip(s)/GPU "
                                    f"({C * WINDOWS_PER_CLIP} windows) through pad+features+classifier+average+regions",
                        "classifier_mode": args.mode, "clips_per_step_per_gpu": C, "pool_clips": len(pool),
@@ -340,7 +341,7 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--mode", default=os.environ.get("SS_BENCH_MODE", "fp32"), choices=["fp32", "bf16"])
+    ap.add_argument("--mode", default=os.environ.get("SS_BENCH_MODE", "f16x3"), choices=["fp32", "bf16", "f16", "f16x3"])
     ap.add_argument("--clips-per-step", type=int, default=1)
     ap.add_argument("--pool", type=int, default=4)
     ap.add_argument("--max-batch", type=int, default=32)

@@ -48,8 +48,11 @@ extern "C" {
 #define SS_E_NODEVICE (-5) /* no usable CUDA device */
 
 /* classifier arithmetic (ss_classify `mode`) */
-#define SS_MODE_FP32 0 /* CUDA-core float32 direct convolution: parity mode */
-#define SS_MODE_BF16 1 /* tcgen05 / TMEM implicit GEMM, bf16 operands, fp32 accumulate */
+#define SS_MODE_FP32 0  /* CUDA-core float32 direct convolution (reference arithmetic, slow) */
+#define SS_MODE_BF16 1  /* tcgen05 / TMEM implicit GEMM, bf16 operands, fp32 accumulate: throughput mode */
+#define SS_MODE_F16 2   /* same kernel, fp16 operands (weights pre-scaled per layer): 8x finer than bf16 */
+#define SS_MODE_F16X3 3 /* same kernel, fp16 hi/lo split operands, 3 MMAs per product: fp32-grade logits on
+                           tensor cores; the default (parity) mode of the drop-in path */
 
 typedef struct ss_ctx ss_ctx;
 
@@ -146,12 +149,12 @@ SS_API int ss_silence_host(ss_ctx* ctx, float* pcm_host, int64_t n_elems, const 
                     int n_intervals);
 
 /* Test instrumentation (parity localisation, not part of the drop-in surface): copy internal activation
- * `which` of the last SS_MODE_BF16 ss_classify call to out_dev as NCHW float32 and report its shape.
+ * `which` of the last tensor-core ss_classify call to out_dev as NCHW float32 and report its shape.
  * Also surfaces a tcgen05 pipeline time-out of that call as SS_E_CUDA. */
 SS_API int ss_debug_activation(ss_ctx* ctx, int which, int n_windows, float* out_dev, int* C, int* H, int* W,
                                void* stream);
 
-/* Test instrumentation: choose which tcgen05 conv launch of the next SS_MODE_BF16 ss_classify call records
+/* Test instrumentation: choose which tcgen05 conv launch of the next tensor-core ss_classify call (same mode as the last one) records
  * per-CTA role timers (-1: none) and read back the previous capture ([148][8] int64 cycles; NULL to skip). */
 SS_API int ss_debug_tc_profile(ss_ctx* ctx, int select_launch, long long* out_host);
 

@@ -13,8 +13,9 @@ LIB_PATH = os.path.join(_HERE, "libsoftspoken_b200.so")
 
 SS_OK = 0
 SS_E_ARG, SS_E_CUDA, SS_E_BLOB, SS_E_CAPACITY, SS_E_NODEVICE = -1, -2, -3, -4, -5
-MODE_FP32, MODE_BF16 = 0, 1
-MODES = {"fp32": MODE_FP32, "bf16": MODE_BF16}
+MODE_FP32, MODE_BF16, MODE_F16, MODE_F16X3 = 0, 1, 2, 3
+MODES = {"fp32": MODE_FP32, "bf16": MODE_BF16, "f16": MODE_F16, "f16x3": MODE_F16X3}
+DEFAULT_MODE = "f16x3"   # fp32-grade logits on tensor cores: the mode detections are bit-exact in
 ABI_VERSION = 1
 
 

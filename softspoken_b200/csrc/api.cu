@@ -145,6 +145,8 @@ int alloc_workspace(ss_ctx* ctx) {
   return SS_OK;
 }
 
+bool valid_mode(int mode) { return mode >= SS_MODE_FP32 && mode <= SS_MODE_F16X3; }
+
 int check_ctx(ss_ctx* ctx) {
   SS_REQUIRE(ctx != nullptr, SS_E_ARG, "null context");
   SS_CUDA_CHECK(cudaSetDevice(ctx->device));
@@ -177,7 +179,7 @@ int run_windows(ss_ctx* ctx, const float* pcm, int64_t valid_begin, int64_t vali
     if (rc) return rc;
     float* lg = logits_all + c0 * kFrames;
     if (mode == SS_MODE_FP32) rc = classify_fp32(ctx, ctx->file_mel, n, lg, nullptr, st);
-    else rc = classify_bf16(ctx, ctx->file_mel, n, lg, nullptr, st);
+    else rc = classify_tc(ctx, mode, ctx->file_mel, n, lg, nullptr, st);
     if (rc) return rc;
   }
   return SS_OK;
@@ -311,7 +313,6 @@ int ss_ctx_create(int device, const void* blob, size_t blob_bytes, int max_batch
   FAIL_IF(find(v, d, "spec_output_conv.1.b", 2, &h.spec_b));
   FAIL_IF(alloc_workspace(ctx));
   FAIL_IF(features_init());
-  FAIL_IF(tc_create(ctx, v.payload));
   {
     cudaError_t e = cudaStreamCreateWithFlags(&ctx->compute_stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
@@ -422,10 +423,9 @@ int ss_classify(ss_ctx* ctx, const float* mel_dev, int n_windows, float* logits_
   if (n_windows == 0) return SS_OK;
   SS_REQUIRE(mel_dev && logits_dev, SS_E_ARG, "null device pointer");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  SS_REQUIRE(valid_mode(mode), SS_E_ARG, "unknown classifier mode %d", mode);
   if (mode == SS_MODE_FP32) return classify_fp32(ctx, mel_dev, n_windows, logits_dev, spec_out_dev, st);
-  if (mode == SS_MODE_BF16) return classify_bf16(ctx, mel_dev, n_windows, logits_dev, spec_out_dev, st);
-  set_error("unknown classifier mode %d", mode);
-  return SS_E_ARG;
+  return classify_tc(ctx, mode, mel_dev, n_windows, logits_dev, spec_out_dev, st);
 }
 
 int ss_average(ss_ctx* ctx, const float* logits_dev, int n_windows, int64_t out_len, double* avg_dev,
@@ -482,7 +482,7 @@ int ss_detect_device(ss_ctx* ctx, const float* pcm_dev, int64_t n_samples, int m
   SS_REQUIRE(ctx->file_logits && n_samples <= ctx->file_cap_samples, SS_E_CAPACITY,
              "clip of %lld samples exceeds the reservation of %lld: call ss_ctx_reserve", (long long)n_samples,
              (long long)ctx->file_cap_samples);
-  SS_REQUIRE(mode == SS_MODE_FP32 || mode == SS_MODE_BF16, SS_E_ARG, "unknown classifier mode %d", mode);
+  SS_REQUIRE(valid_mode(mode), SS_E_ARG, "unknown classifier mode %d", mode);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int64_t W = plan_windows(n_samples);
   // virtual padding (worker.py:58-62): padded index [66150, 66150 + n) -> pcm[idx - 66150], zeros elsewhere
@@ -506,7 +506,7 @@ int ss_detect_host(ss_ctx* ctx, const float* pcm_host, int64_t n_samples, int mo
   SS_REQUIRE(ctx->file_logits && n_samples <= ctx->file_cap_samples && cap <= ctx->file_region_cap, SS_E_CAPACITY,
              "clip of %lld samples / %d regions exceeds the reservation (%lld / %d): call ss_ctx_reserve",
              (long long)n_samples, cap, (long long)ctx->file_cap_samples, ctx->file_region_cap);
-  SS_REQUIRE(mode == SS_MODE_FP32 || mode == SS_MODE_BF16, SS_E_ARG, "unknown classifier mode %d", mode);
+  SS_REQUIRE(valid_mode(mode), SS_E_ARG, "unknown classifier mode %d", mode);
   cudaStream_t cs = ctx->compute_stream, xs = ctx->copy_stream;
   const int64_t W = plan_windows(n_samples);
   int buf = 0;
@@ -534,6 +534,11 @@ int ss_detect_host(ss_ctx* ctx, const float* pcm_host, int64_t n_samples, int mo
   int32_t nreg = 0;
   SS_CUDA_CHECK(cudaMemcpyAsync(&nreg, ctx->file_nreg, sizeof(int32_t), cudaMemcpyDeviceToHost, cs));
   SS_CUDA_CHECK(cudaStreamSynchronize(cs));
+  if (mode != SS_MODE_FP32) {
+    int flag = 0;
+    if ((rc = tc_error_flag(ctx, &flag, cs))) return rc;
+    SS_REQUIRE(flag == 0, SS_E_CUDA, "tcgen05 pipeline timed out (role code %d)", flag);
+  }
   *n_regions = nreg;
   const int ncopy = nreg < cap ? nreg : cap;
   if (ncopy > 0)

@@ -1,32 +1,35 @@
-// K2 (throughput mode) — tcgen05 / TMEM implicit-GEMM implementation of the residual U-Net trunk.
+// K2 — tcgen05 / TMEM implicit-GEMM implementation of the residual U-Net trunk (tensor-core modes).
 //
 // Replaces the same reference ops as conv_fp32.cu (ResBlock x11, MaxPool2d x4, Upsample x4, torch.cat x4;
-// root/code/backend/pytorch_neural_nets.py:7-41,102-123,156-185) with bf16 operands and fp32 accumulation
-// on the 5th-generation tensor cores.
+// root/code/backend/pytorch_neural_nets.py:7-41,102-123,156-185) with 16-bit operands and fp32 accumulation
+// on the 5th-generation tensor cores.  Three operand precisions share the kernel (conv_tc_kernel.cuh):
+//   SS_MODE_BF16   bf16, one pass           — throughput mode, documented tolerance;
+//   SS_MODE_F16    fp16, one pass           — same cost, 8x finer mantissa (weights pre-scaled by 2^k per layer);
+//   SS_MODE_F16X3  fp16 hi/lo split, 3 MMAs — fp32-grade logits on tensor cores (the parity mode of the bench).
 //
-// Layout.  Every activation tensor is "planar-8, zero-padded": [B][C/8][H+2][W+2][8] bf16 — one 16-byte
+// Layout.  Every activation tensor is "planar-8, zero-padded": [B][C/8][H+2][W+2][8] 16-bit — one 16-byte
 // vector of 8 channels per padded pixel, one plane per 8 channels, a one-pixel zero border around each
-// image.  With q = y (W+2) + x the flattened padded position, a 3x3 convolution is a sum of nine shifted
-// GEMMs:  out[q, :] = sum_tap  in[q + dy (W+2) + dx, :] . w[tap]   — no im2col, no boundary logic.
+// image (split precision keeps a second tensor of the same shape with the fp16 residuals).  With
+// q = y (W+2) + x the flattened padded position, a 3x3 convolution is a sum of nine shifted GEMMs:
+//   out[q, :] = sum_tap  in[q + dy (W+2) + dx, :] . w[tap]   — no im2col, no boundary logic.
 //
-// Kernel.  One CTA owns MT*128 consecutive positions of one image and all N = C_out channels:
+// Kernel.  One CTA per SM, persistent over work units of MT*128 consecutive positions x all N = C_out:
 //   * producer warp: per 16-channel K-chunk, two 1-D bulk copies (cp.async.bulk, one per 8-channel plane)
 //     bring the run of positions plus a (W+3)-position halo on each side into shared memory, a third brings
-//     the chunk's packed weights; an mbarrier ring (full/empty) double-buffers the stages;
-//   * MMA warp: one thread issues tcgen05.mma (M=128, N, K=16, kind::f16, bf16 x bf16 -> fp32 in TMEM).
-//     Shared memory holds K-major, un-swizzled core matrices (8 positions x 16 bytes), so the A operand of
-//     tap (dy, dx) is simply the same buffer with the descriptor start address advanced by
-//     (dy (W+2) + dx) * 16 bytes: the halo tile is loaded once and used nine times;
-//   * a second source (the ResBlock's 1x1 residual branch on the block input) accumulates into the same
-//     TMEM tile, so `out = relu(conv2(t) + residual(x))` is one launch;
-//   * 4 epilogue warps: tcgen05.ld the fp32 accumulators, add the folded-BN bias, ReLU, force the border
-//     positions to zero, pack to bf16 and store 16-byte vectors (512 contiguous bytes per warp and plane).
-//     With `upsample` set each value is stored to the 2x2 block of the next level's tensor at a plane
-//     offset, which is how nearest-Upsample and torch.cat([skip, up]) are realised without a pass of
-//     their own.
-// Two CTAs are resident per SM (<= 113 KB shared memory, 256 TMEM columns each), so one CTA's epilogue
-// overlaps the other's MMA stream.
+//     the chunk's packed weights; an mbarrier ring (full/empty) pipelines the stages;
+//   * MMA warp: one thread issues tcgen05.mma (M=128, N, K=16, kind::f16 -> fp32 in TMEM).  Shared memory
+//     holds K-major, un-swizzled core matrices (8 positions x 16 bytes), so the A operand of tap (dy, dx) is
+//     the same buffer with the descriptor start address advanced by (dy (W+2) + dx) * 16 bytes: the halo
+//     tile is loaded once and used nine times;
+//   * further sources (the ResBlock's 1x1 residual branch on the block input; the lo tensors of the split
+//     precision) accumulate into the same TMEM tile, so `out = relu(conv2(t) + residual(x))` is one launch;
+//   * 4 epilogue warps: tcgen05.ld the fp32 accumulators, undo the weight scale, add the folded-BN bias,
+//     ReLU, force the border positions to zero, pack to 16 bits and store 16-byte vectors.  With `upsample`
+//     set each value is stored to the 2x2 block of the next level's tensor at a plane offset, which is how
+//     nearest-Upsample and torch.cat([skip, up]) are realised without a pass of their own.
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <math.h>
 
 #include <vector>
 
@@ -42,33 +45,65 @@ using namespace ss::tc;
 constexpr int kGuardBytes = 1 << 17;      // slack before/after every activation allocation (halo over-reads)
 constexpr size_t kSmemBudget = 200 * 1024; // dynamic shared memory of the persistent conv kernel
 
+// ------------------------------------------------------------------------------------ operand helpers
+// 8 channels of one padded pixel as floats: hi (+ lo for the split format).
+template <Prec P>
+__device__ __forceinline__ void load8(const uint16_t* __restrict__ hi, const uint16_t* __restrict__ lo, int64_t pix,
+                                      float (&f)[8]) {
+  const uint4 v = __ldg(reinterpret_cast<const uint4*>(hi) + pix);
+  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+  for (int h = 0; h < 4; ++h) {
+    const float2 t = unpack2<P>(w[h]);
+    f[2 * h] = t.x;
+    f[2 * h + 1] = t.y;
+  }
+  if constexpr (PrecTraits<P>::split) {
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(lo) + pix);
+    const uint32_t x[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int h = 0; h < 4; ++h) {
+      const float2 t = unpack2<P>(x[h]);
+      f[2 * h] += t.x;            // exact: hi and lo together span <= 24 significant bits
+      f[2 * h + 1] += t.y;
+    }
+  }
+}
+
+template <Prec P>
+__device__ __forceinline__ void store8(uint16_t* __restrict__ hi, uint16_t* __restrict__ lo, int64_t pix,
+                                       const float (&f)[8]) {
+  uint32_t hw[4], lw[4];
+#pragma unroll
+  for (int h = 0; h < 4; ++h) {
+    hw[h] = pack_hi<P>(f[2 * h], f[2 * h + 1]);
+    if constexpr (PrecTraits<P>::split) lw[h] = pack_lo_f16(f[2 * h], f[2 * h + 1], hw[h]);
+  }
+  reinterpret_cast<uint4*>(hi)[pix] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+  if constexpr (PrecTraits<P>::split) reinterpret_cast<uint4*>(lo)[pix] = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+}
+
 // ------------------------------------------------------------------------------------------ small kernels
 // mel f32 [B][128][256] -> channel 0 of plane 0 of a 16-channel planar tensor (planes 0,1; rest stays zero)
-__global__ void mel_to_planar(const float* __restrict__ mel, bf16* __restrict__ out, int64_t n_pix) {
+template <Prec P>
+__global__ void mel_to_planar(const float* __restrict__ mel, uint16_t* __restrict__ out, uint16_t* __restrict__ out_lo,
+                              int64_t n_pix) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_pix) return;
   const int x = (int)(i % kFrames);
   const int y = (int)((i / kFrames) % kMels);
   const int64_t b = i / ((int64_t)kFrames * kMels);
   const int Wp = kFrames + 2, Hp = kMels + 2;
-  const float m = __ldg(mel + i);
-  __nv_bfloat162 h2 = __floats2bfloat162_rn(m, 0.f);
-  uint4 v = make_uint4(*reinterpret_cast<uint32_t*>(&h2), 0u, 0u, 0u);
-  *reinterpret_cast<uint4*>(out + ((b * 2) * Hp * Wp + (int64_t)(y + 1) * Wp + (x + 1)) * 8) = v;
-}
-
-__device__ __forceinline__ uint32_t bmax2(uint32_t a, uint32_t b) {
-  __nv_bfloat162 r = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&a), *reinterpret_cast<__nv_bfloat162*>(&b));
-  return *reinterpret_cast<uint32_t*>(&r);
-}
-__device__ __forceinline__ uint4 bmax8(uint4 a, uint4 b) {
-  return make_uint4(bmax2(a.x, b.x), bmax2(a.y, b.y), bmax2(a.z, b.z), bmax2(a.w, b.w));
+  const float f[8] = {__ldg(mel + i), 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  store8<P>(out, out_lo, (b * 2) * Hp * Wp + (int64_t)(y + 1) * Wp + (x + 1), f);
 }
 
 // MaxPool2d(2) on planar tensors: in planes [plane0, plane0+planes) of a tensor with in_planes_total planes at
-// H x W  ->  out [B][planes][H/2+2][W/2+2][8].
-__global__ void pool_planar(const bf16* __restrict__ in, int in_planes_total, int plane0, int planes, int H, int W,
-                            bf16* __restrict__ out, int64_t total) {
+// H x W  ->  out [B][planes][H/2+2][W/2+2][8].  The max is taken on the reconstructed fp32 values.
+template <Prec P>
+__global__ void pool_planar(const uint16_t* __restrict__ in, const uint16_t* __restrict__ in_lo, int in_planes_total,
+                            int plane0, int planes, int H, int W, uint16_t* __restrict__ out,
+                            uint16_t* __restrict__ out_lo, int64_t total) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const int W2 = W >> 1, H2 = H >> 1;
@@ -78,29 +113,31 @@ __global__ void pool_planar(const bf16* __restrict__ in, int in_planes_total, in
   const int pl = (int)(r % planes);
   const int64_t b = r / planes;
   const int Wp = W + 2, Hp = H + 2, Wq = W2 + 2, Hq = H2 + 2;
-  const uint4* src = reinterpret_cast<const uint4*>(in) + ((b * in_planes_total + plane0 + pl) * Hp + (2 * y + 1)) * (int64_t)Wp + (2 * x + 1);
-  const uint4 m = bmax8(bmax8(__ldg(src), __ldg(src + 1)), bmax8(__ldg(src + Wp), __ldg(src + Wp + 1)));
-  reinterpret_cast<uint4*>(out)[((b * planes + pl) * Hq + (y + 1)) * (int64_t)Wq + (x + 1)] = m;
-}
-
-__device__ __forceinline__ void unpack8(uint4 v, float (&f)[8]) {
-  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+  const int64_t src = ((b * in_planes_total + plane0 + pl) * Hp + (2 * y + 1)) * (int64_t)Wp + (2 * x + 1);
+  float a[8], c[8];
+  load8<P>(in, in_lo, src, a);
+  load8<P>(in, in_lo, src + 1, c);
 #pragma unroll
-  for (int h = 0; h < 4; ++h) {
-    const float2 t = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[h]));
-    f[2 * h] = t.x;
-    f[2 * h + 1] = t.y;
-  }
+  for (int k = 0; k < 8; ++k) a[k] = fmaxf(a[k], c[k]);
+  load8<P>(in, in_lo, src + Wp, c);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) a[k] = fmaxf(a[k], c[k]);
+  load8<P>(in, in_lo, src + Wp + 1, c);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) a[k] = fmaxf(a[k], c[k]);
+  store8<P>(out, out_lo, ((b * planes + pl) * Hq + (y + 1)) * (int64_t)Wq + (x + 1), a);
 }
 
-// Mask head on planar bf16 conv9 [B][4][130][258][8] (same arithmetic as head.cu:mask_head_f32, fp32 math).
+// Mask head on planar conv9 [B][4][130][258][8] (same arithmetic as head.cu:mask_head_f32, fp32 math).
 // grid (8 frame chunks, B): a CTA produces 32 logits; its 288 threads are 8 mel-row groups x 36 frames
 // (32 + a 2-frame halo each side for the two k=3 1-D convolutions), so the K = 4096 reduction of
 // conv_flatten is spread over 8 x more threads than one-thread-per-frame and the loads stay coalesced.
 constexpr int kHeadFrames = 32, kHeadHalo = 2, kHeadCols = kHeadFrames + 2 * kHeadHalo, kHeadGroups = 8;
 
+template <Prec P>
 __global__ void __launch_bounds__(kHeadCols * kHeadGroups)
-mask_head_planar(const bf16* __restrict__ conv9, HeadW hw, float* __restrict__ logits) {
+mask_head_planar(const uint16_t* __restrict__ conv9, const uint16_t* __restrict__ conv9_lo, HeadW hw,
+                 float* __restrict__ logits) {
   __shared__ float part[kHeadGroups][4][kHeadCols];
   __shared__ float xf[4][kHeadCols];
   __shared__ float c1[4][kHeadCols];
@@ -109,7 +146,7 @@ mask_head_planar(const bf16* __restrict__ conv9, HeadW hw, float* __restrict__ l
   const int t = blockIdx.x * kHeadFrames - kHeadHalo + f;          // frame of this column
   const bool valid = (t >= 0) && (t < kFrames);
   const int Wp = kFrames + 2, Hp = kMels + 2;
-  const uint4* base = reinterpret_cast<const uint4*>(conv9) + (int64_t)b * 4 * Hp * Wp;
+  const int64_t base = (int64_t)b * 4 * Hp * Wp;
   float acc[4] = {0.f, 0.f, 0.f, 0.f};
   if (valid) {
     const int rows = kMels / kHeadGroups;
@@ -118,7 +155,7 @@ mask_head_planar(const bf16* __restrict__ conv9, HeadW hw, float* __restrict__ l
 #pragma unroll
       for (int pl = 0; pl < 4; ++pl) {
         float a[8];
-        unpack8(__ldg(base + ((int64_t)pl * Hp + (h + 1)) * Wp + (t + 1)), a);
+        load8<P>(conv9, conv9_lo, base + ((int64_t)pl * Hp + (h + 1)) * Wp + (t + 1), a);
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
           const float4 w = __ldg(wrow + pl * 8 + k);
@@ -173,20 +210,22 @@ mask_head_planar(const bf16* __restrict__ conv9, HeadW hw, float* __restrict__ l
   }
 }
 
-// spec head tail on planar bf16 [B][4][130][258][8] -> NCHW f32 [B][2][128][256]
-__global__ void spec_out_planar(const bf16* __restrict__ x, HeadW hw, float* __restrict__ out, int64_t n_pixels) {
+// spec head tail on planar [B][4][130][258][8] -> NCHW f32 [B][2][128][256]
+template <Prec P>
+__global__ void spec_out_planar(const uint16_t* __restrict__ x, const uint16_t* __restrict__ x_lo, HeadW hw,
+                                float* __restrict__ out, int64_t n_pixels) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_pixels) return;
   const int xx = (int)(i % kFrames);
   const int yy = (int)((i / kFrames) % kMels);
   const int64_t b = i / ((int64_t)kFrames * kMels);
   const int Wp = kFrames + 2, Hp = kMels + 2;
-  const uint4* base = reinterpret_cast<const uint4*>(x) + (int64_t)b * 4 * Hp * Wp + (int64_t)(yy + 1) * Wp + (xx + 1);
+  const int64_t base = (int64_t)b * 4 * Hp * Wp + (int64_t)(yy + 1) * Wp + (xx + 1);
   float a0 = __ldg(hw.spec_b), a1 = __ldg(hw.spec_b + 1);
 #pragma unroll
   for (int pl = 0; pl < 4; ++pl) {
     float a[8];
-    unpack8(__ldg(base + (int64_t)pl * Hp * Wp), a);
+    load8<P>(x, x_lo, base + (int64_t)pl * Hp * Wp, a);
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       a0 = fmaf(a[k], __ldg(hw.spec_w + (pl * 8 + k) * 2), a0);
@@ -198,9 +237,10 @@ __global__ void spec_out_planar(const bf16* __restrict__ x, HeadW hw, float* __r
   out[(b * 2 + 1) * plane + pix] = fmaxf(a1, 0.f);
 }
 
-// planar bf16 -> NCHW f32 (debug / parity localisation only)
-__global__ void planar_to_nchw(const bf16* __restrict__ in, int planes_total, int plane0, int C, int H, int W,
-                               float* __restrict__ out, int64_t total) {
+// planar -> NCHW f32 (debug / parity localisation only)
+template <Prec P>
+__global__ void planar_to_nchw(const uint16_t* __restrict__ in, const uint16_t* __restrict__ in_lo, int planes_total,
+                               int plane0, int C, int H, int W, float* __restrict__ out, int64_t total) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const int x = (int)(i % W);
@@ -209,86 +249,127 @@ __global__ void planar_to_nchw(const bf16* __restrict__ in, int planes_total, in
   const int c = (int)(r % C);
   const int64_t b = r / C;
   const int Wp = W + 2, Hp = H + 2;
-  out[i] = __bfloat162float(in[(((b * planes_total + plane0 + c / 8) * Hp + (y + 1)) * (int64_t)Wp + (x + 1)) * 8 + (c & 7)]);
+  float a[8];
+  load8<P>(in, in_lo, ((b * planes_total + plane0 + c / 8) * Hp + (y + 1)) * (int64_t)Wp + (x + 1), a);
+  out[i] = a[c & 7];
 }
 
 // ------------------------------------------------------------------------------------------- host state
 struct Tensor {
-  bf16* alloc = nullptr;   // includes guards
-  bf16* data = nullptr;
+  uint16_t* alloc = nullptr;      // includes guards
+  uint16_t* data = nullptr;
+  uint16_t* alloc_lo = nullptr;   // split precision only
+  uint16_t* lo = nullptr;
   int planes = 0, H = 0, W = 0;
-  size_t bytes = 0;
 };
 
 struct PackedConv {
-  bf16* w = nullptr;
-  int n_chunks = 0, taps = 0, n = 0;
+  uint16_t* w = nullptr;   // [n_chunks][parts][taps][2][n][8]
+  int n_chunks = 0, taps = 0, n = 0, parts = 1;
 };
 
 struct TcBlock {
   PackedConv res, c1, c2;
-  float* bias2 = nullptr;   // b2 + b_res (the fused second launch)
+  float* bias2 = nullptr;       // b2 + b_res (the fused second launch)
   const float* bias1 = nullptr;
+  float inv_scale1 = 1.f, inv_scale2 = 1.f;
 };
 
+}  // namespace
+
 struct TcState {
+  Prec prec = Prec::Bf16;
   int max_batch = 0;
   TcBlock rb[RB_COUNT];
   Tensor x0, m4, m3, m2, m1, p1, p2, p3, p4, bott, c9, spec;
   Tensor t[RB_COUNT];
   int* err = nullptr;
-  long long* prof = nullptr;   // [kNumSMs][8] role timers of the most recent conv launch (debug)
+  long long* prof = nullptr;   // [kNumSMs][8] role timers of the selected conv launch (debug)
   int prof_layer = -1;         // launch index to capture (-1: none)
   int launch_index = 0;
   size_t bytes = 0;
 };
 
+namespace {
+
+bool is_split(Prec p) { return p == Prec::F16x3; }
+
 int alloc_tensor(TcState* st, Tensor* t, int B, int C, int H, int W) {
   t->planes = C / 8;
   t->H = H;
   t->W = W;
-  const size_t body = (size_t)B * t->planes * (H + 2) * (W + 2) * 8 * sizeof(bf16);
-  t->bytes = body + 2 * (size_t)kGuardBytes;
-  SS_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&t->alloc), t->bytes));
-  SS_CUDA_CHECK(cudaMemset(t->alloc, 0, t->bytes));     // zero borders + guards, never overwritten with non-zero
-  t->data = reinterpret_cast<bf16*>(reinterpret_cast<unsigned char*>(t->alloc) + kGuardBytes);
-  st->bytes += t->bytes;
+  const size_t body = (size_t)B * t->planes * (H + 2) * (W + 2) * 8 * sizeof(uint16_t);
+  const size_t bytes = body + 2 * (size_t)kGuardBytes;
+  // zero borders + guards: never overwritten with non-zero values afterwards
+  SS_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&t->alloc), bytes));
+  SS_CUDA_CHECK(cudaMemset(t->alloc, 0, bytes));
+  t->data = reinterpret_cast<uint16_t*>(reinterpret_cast<unsigned char*>(t->alloc) + kGuardBytes);
+  st->bytes += bytes;
+  if (is_split(st->prec)) {
+    SS_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&t->alloc_lo), bytes));
+    SS_CUDA_CHECK(cudaMemset(t->alloc_lo, 0, bytes));
+    t->lo = reinterpret_cast<uint16_t*>(reinterpret_cast<unsigned char*>(t->alloc_lo) + kGuardBytes);
+    st->bytes += bytes;
+  }
   return SS_OK;
 }
 
-// w: [taps][cin][cout] f32 (host) -> packed bf16 [chunk][tap][2][cout][8] on the device
-int pack_conv(TcState* st, const float* w, int taps, int cin, int cout, PackedConv* out) {
+uint16_t to_bits_bf16(float v) { __nv_bfloat16 h = __float2bfloat16(v); uint16_t b; memcpy(&b, &h, 2); return b; }
+uint16_t to_bits_f16(float v) { __half h = __float2half_rn(v); uint16_t b; memcpy(&b, &h, 2); return b; }
+float from_bits_f16(uint16_t b) { __half h; memcpy(&h, &b, 2); return __half2float(h); }
+
+// Power-of-two scale that lifts the largest |w| of a group of fp16 weight tensors into [1024, 2048): the hi/lo
+// split then keeps the residuals of all but the tiniest weights out of the fp16 subnormal range, and fp16
+// single-pass weights keep their full 11-bit mantissa.  bf16 needs none (fp32 exponent range).
+float weight_scale(Prec p, std::initializer_list<const std::vector<float>*> ws) {
+  if (p == Prec::Bf16) return 1.f;
+  float m = 0.f;
+  for (const std::vector<float>* w : ws)
+    for (float v : *w) m = fmaxf(m, fabsf(v));
+  if (!(m > 0.f) || !isfinite(m)) return 1.f;
+  int e;
+  frexpf(m, &e);                         // m = f * 2^e, f in [0.5, 1)
+  return ldexpf(1.f, 11 - e);            // m * scale in [1024, 2048)
+}
+
+// w: [taps][cin][cout] f32 (host) * scale -> packed 16-bit [chunk][part][tap][2][cout][8] on the device
+int pack_conv(TcState* st, const float* w, int taps, int cin, int cout, float scale, PackedConv* out) {
   const int n_chunks = (cin + 15) / 16;
-  std::vector<bf16> h((size_t)n_chunks * taps * 2 * cout * 8);
+  const int parts = is_split(st->prec) ? 2 : 1;
+  std::vector<uint16_t> h((size_t)n_chunks * parts * taps * 2 * cout * 8);
   for (int kc = 0; kc < n_chunks; ++kc)
     for (int t = 0; t < taps; ++t)
       for (int hh = 0; hh < 2; ++hh)
         for (int n = 0; n < cout; ++n)
           for (int j = 0; j < 8; ++j) {
             const int c = kc * 16 + hh * 8 + j;
-            const float v = (c < cin) ? w[((size_t)t * cin + c) * cout + n] : 0.f;
-            h[((((size_t)kc * taps + t) * 2 + hh) * cout + n) * 8 + j] = __float2bfloat16(v);
+            const float v = (c < cin) ? w[((size_t)t * cin + c) * cout + n] * scale : 0.f;
+            const size_t at = (((((size_t)kc * parts + 0) * taps + t) * 2 + hh) * cout + n) * 8 + j;
+            if (st->prec == Prec::Bf16) {
+              h[at] = to_bits_bf16(v);
+            } else {
+              const uint16_t hi = to_bits_f16(v);
+              h[at] = hi;
+              if (parts == 2)
+                h[(((((size_t)kc * parts + 1) * taps + t) * 2 + hh) * cout + n) * 8 + j] = to_bits_f16(v - from_bits_f16(hi));
+            }
           }
-  SS_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&out->w), h.size() * sizeof(bf16)));
-  SS_CUDA_CHECK(cudaMemcpy(out->w, h.data(), h.size() * sizeof(bf16), cudaMemcpyHostToDevice));
-  st->bytes += h.size() * sizeof(bf16);
+  SS_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&out->w), h.size() * sizeof(uint16_t)));
+  SS_CUDA_CHECK(cudaMemcpy(out->w, h.data(), h.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+  st->bytes += h.size() * sizeof(uint16_t);
   out->n_chunks = n_chunks;
   out->taps = taps;
   out->n = cout;
+  out->parts = parts;
   return SS_OK;
 }
 
 constexpr size_t kSmemTail = (2 * kMaxStages + 4) * 8 + 128 * 4 + 16;   // barriers + bias + TMEM slot
 
-int pick_mt(int N, int H, int W) {
-  (void)H; (void)W;
-  return (N == 96) ? 2 : kAccCols / N;               // == TilesPerUnit<N>::value (compile-time in the kernel)
-}
-
-template <int N>
-int launch_conv_n(TcConv p, int B, cudaStream_t st) {
-  SS_REQUIRE(p.MT == TilesPerUnit<N>::value, SS_E_ARG, "tile count mismatch");
-  const size_t sb = stage_bytes(N, p.W, p.MT);
+template <int N, Prec P>
+int launch_conv_np(TcConv p, int B, cudaStream_t st) {
+  constexpr int MT = TilesPerUnit<N, P>::value;
+  const size_t sb = stage_bytes(N, p.W, MT, 1);
   int stages = (int)((kSmemBudget - kSmemTail) / sb);
   if (stages > kMaxStages) stages = kMaxStages;
   SS_REQUIRE(stages >= 2, SS_E_ARG, "conv stage of %zu bytes does not fit twice in shared memory", sb);
@@ -296,84 +377,114 @@ int launch_conv_n(TcConv p, int B, cudaStream_t st) {
   const size_t smem = (size_t)stages * sb + kSmemTail;
   static bool configured = false;
   if (!configured) {
-    SS_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    SS_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<N, P>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)kSmemBudget));
     configured = true;
   }
   const int positions = p.H * (p.W + 2) - 2;          // (1,1) .. (H,W) in flattened padded coordinates
-  p.units_per_image = (positions + p.MT * 128 - 1) / (p.MT * 128);
+  p.units_per_image = (positions + MT * 128 - 1) / (MT * 128);
   p.total_units = p.units_per_image * B;
   const int grid = p.total_units < kNumSMs ? p.total_units : kNumSMs;
-  conv_tc_kernel<N><<<grid, kTcThreads, smem, st>>>(p);
+  conv_tc_kernel<N, P><<<grid, kTcThreads, smem, st>>>(p);
   SS_CUDA_CHECK(cudaGetLastError());
   count_launch();
   return SS_OK;
 }
 
-int launch_conv(const TcConv& p, int N, int B, cudaStream_t st) {
+template <Prec P>
+int launch_conv_p(const TcConv& p, int N, int B, cudaStream_t st) {
   switch (N) {
-    case 32: return launch_conv_n<32>(p, B, st);
-    case 64: return launch_conv_n<64>(p, B, st);
-    case 96: return launch_conv_n<96>(p, B, st);
-    case 128: return launch_conv_n<128>(p, B, st);
+    case 32: return launch_conv_np<32, P>(p, B, st);
+    case 64: return launch_conv_np<64, P>(p, B, st);
+    case 96: return launch_conv_np<96, P>(p, B, st);
+    case 128: return launch_conv_np<128, P>(p, B, st);
   }
   set_error("unsupported C_out %d", N);
   return SS_E_ARG;
 }
 
+int launch_conv(Prec prec, const TcConv& p, int N, int B, cudaStream_t st) {
+  switch (prec) {
+    case Prec::Bf16: return launch_conv_p<Prec::Bf16>(p, N, B, st);
+    case Prec::F16: return launch_conv_p<Prec::F16>(p, N, B, st);
+    case Prec::F16x3: return launch_conv_p<Prec::F16x3>(p, N, B, st);
+  }
+  return SS_E_ARG;
+}
+
+// Sources of one convolution of tensor `x` (planes from plane0) with packed weights `w`.  Single precision is
+// one source.  The split precision is three — x_lo . w_hi, x_hi . w_lo (the corrections) and x_hi . w_hi (the
+// main term) — and a launch issues every correction before any main term: the tensor core truncates the fp32
+// accumulator after every MMA, so the small terms are summed while the accumulator (and its ulp) is still small
+// (Ootomo & Yokota 2022 observe the same for mma.sync; tools/precision_study.py measures it here).
+enum class Terms { All, Corrections, Main };
+
+void add_sources(TcConv* p, const TcState* s, const Tensor& x, int plane0, const PackedConv& w, Terms terms) {
+  const int part_elems = w.taps * w.n * 16;
+  const int chunk_elems = w.parts * part_elems;
+  if (!is_split(s->prec)) {
+    if (terms != Terms::Corrections)
+      p->src[p->n_src++] = TcSource{x.data, x.planes, plane0, w.n_chunks, w.taps, 1, chunk_elems, w.w};
+    return;
+  }
+  if (terms != Terms::Main) {
+    p->src[p->n_src++] = TcSource{x.lo, x.planes, plane0, w.n_chunks, w.taps, 1, chunk_elems, w.w};
+    p->src[p->n_src++] = TcSource{x.data, x.planes, plane0, w.n_chunks, w.taps, 1, chunk_elems, w.w + part_elems};
+  }
+  if (terms != Terms::Corrections)
+    p->src[p->n_src++] = TcSource{x.data, x.planes, plane0, w.n_chunks, w.taps, 1, chunk_elems, w.w};
+}
+
 // One ResBlock: t = relu(conv3x3(x) + b1);  out = relu(conv3x3(t) + conv1x1(x) + b2 + b_res).
-int tc_res_block(TcState* s, int which, const Tensor& x, int x_plane0, int cin, Tensor& out, int out_plane0,
-                 int upsample, int B, cudaStream_t st) {
+int tc_res_block(TcState* s, int which, const Tensor& x, int x_plane0, Tensor& out, int out_plane0, int upsample,
+                 int B, cudaStream_t st) {
   const TcBlock& rb = s->rb[which];
   Tensor& t = s->t[which];
   const int N = rb.c1.n;
   TcConv p{};
-  p.n_src = 1;
-  (void)cin;
-  p.src[0] = TcSource{x.data, x.planes, x_plane0, rb.c1.n_chunks, 9, rb.c1.w};
+  add_sources(&p, s, x, x_plane0, rb.c1, Terms::Corrections);
+  add_sources(&p, s, x, x_plane0, rb.c1, Terms::Main);
   p.H = x.H; p.W = x.W;
   p.bias = rb.bias1;
+  p.inv_scale = rb.inv_scale1;
   p.relu = 1;
-  p.out = t.data; p.out_planes_total = t.planes; p.out_plane0 = 0; p.upsample = 0;
-  p.MT = pick_mt(N, x.H, x.W);
+  p.out = t.data; p.out_lo = t.lo; p.out_planes_total = t.planes; p.out_plane0 = 0; p.upsample = 0;
   p.err = s->err;
   p.prof = (s->launch_index++ == s->prof_layer) ? s->prof : nullptr;
-  int rc = launch_conv(p, N, B, st);
+  int rc = launch_conv(s->prec, p, N, B, st);
   if (rc) return rc;
   TcConv q{};
-  q.n_src = 2;
-  q.src[0] = TcSource{t.data, t.planes, 0, rb.c2.n_chunks, 9, rb.c2.w};
-  q.src[1] = TcSource{x.data, x.planes, x_plane0, rb.res.n_chunks, 1, rb.res.w};
+  add_sources(&q, s, t, 0, rb.c2, Terms::Corrections);
+  add_sources(&q, s, x, x_plane0, rb.res, Terms::Corrections);
+  add_sources(&q, s, x, x_plane0, rb.res, Terms::Main);
+  add_sources(&q, s, t, 0, rb.c2, Terms::Main);
   q.H = x.H; q.W = x.W;
   q.bias = rb.bias2;
+  q.inv_scale = rb.inv_scale2;
   q.relu = 1;
-  q.out = out.data; q.out_planes_total = out.planes; q.out_plane0 = out_plane0; q.upsample = upsample;
-  q.MT = p.MT;
+  q.out = out.data; q.out_lo = out.lo; q.out_planes_total = out.planes; q.out_plane0 = out_plane0; q.upsample = upsample;
   q.err = s->err;
   q.prof = (s->launch_index++ == s->prof_layer) ? s->prof : nullptr;
-  return launch_conv(q, N, B, st);
+  return launch_conv(s->prec, q, N, B, st);
 }
 
-int tc_pool(const Tensor& in, int plane0, int planes, Tensor& out, int B, cudaStream_t st) {
+template <Prec P>
+int tc_pool_p(const Tensor& in, int plane0, int planes, Tensor& out, int B, cudaStream_t st) {
   const int64_t total = (int64_t)B * planes * (in.H / 2) * (in.W / 2);
-  pool_planar<<<(int)((total + 255) / 256), 256, 0, st>>>(in.data, in.planes, plane0, planes, in.H, in.W, out.data, total);
+  pool_planar<P><<<(int)((total + 255) / 256), 256, 0, st>>>(in.data, in.lo, in.planes, plane0, planes, in.H, in.W,
+                                                             out.data, out.lo, total);
   SS_CUDA_CHECK(cudaGetLastError());
   count_launch();
   return SS_OK;
 }
 
-}  // namespace
-
-int tc_create(ss_ctx* ctx, const float* hp) {
-  (void)hp;
-  return SS_OK;
-}
-
-// Built lazily on the first bf16 call so that fp32-only users do not pay for the second workspace.
-static int tc_build(ss_ctx* ctx) {
-  if (ctx->tc) return SS_OK;
+// Built lazily on the first call of a mode, so that nobody pays for a workspace they do not use.
+int tc_build(ss_ctx* ctx, Prec prec, TcState** out) {
+  const int slot = (int)prec;
+  if (ctx->tc[slot]) { *out = static_cast<TcState*>(ctx->tc[slot]); return SS_OK; }
   TcState* s = new TcState();
-  ctx->tc = s;
+  ctx->tc[slot] = s;
+  s->prec = prec;
   s->max_batch = ctx->max_batch;
   const int B = ctx->max_batch;
   int rc;
@@ -387,13 +498,17 @@ static int tc_build(ss_ctx* ctx) {
       SS_CUDA_CHECK(cudaMemcpy(bias->data(), c.b, bias->size() * 4, cudaMemcpyDeviceToHost));
       return SS_OK;
     };
-    std::vector<float> w, b1, b2, br;
-    if ((rc = fetch(rb.c1, &w, &b1))) return rc;
-    if ((rc = pack_conv(s, w.data(), 9, rb.c1.cin, rb.c1.cout, &s->rb[i].c1))) return rc;
-    if ((rc = fetch(rb.c2, &w, &b2))) return rc;
-    if ((rc = pack_conv(s, w.data(), 9, rb.c2.cin, rb.c2.cout, &s->rb[i].c2))) return rc;
-    if ((rc = fetch(rb.res, &w, &br))) return rc;
-    if ((rc = pack_conv(s, w.data(), 1, rb.res.cin, rb.res.cout, &s->rb[i].res))) return rc;
+    std::vector<float> w1, w2, wr, b1, b2, br;
+    if ((rc = fetch(rb.c1, &w1, &b1))) return rc;
+    if ((rc = fetch(rb.c2, &w2, &b2))) return rc;
+    if ((rc = fetch(rb.res, &wr, &br))) return rc;
+    const float s1 = weight_scale(prec, {&w1});
+    const float s2 = weight_scale(prec, {&w2, &wr});       // conv2 and the residual share one accumulator
+    if ((rc = pack_conv(s, w1.data(), 9, rb.c1.cin, rb.c1.cout, s1, &s->rb[i].c1))) return rc;
+    if ((rc = pack_conv(s, w2.data(), 9, rb.c2.cin, rb.c2.cout, s2, &s->rb[i].c2))) return rc;
+    if ((rc = pack_conv(s, wr.data(), 1, rb.res.cin, rb.res.cout, s2, &s->rb[i].res))) return rc;
+    s->rb[i].inv_scale1 = 1.f / s1;
+    s->rb[i].inv_scale2 = 1.f / s2;
     for (size_t k = 0; k < b2.size(); ++k) b2[k] += br[k];
     SS_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&s->rb[i].bias2), b2.size() * 4));
     SS_CUDA_CHECK(cudaMemcpy(s->rb[i].bias2, b2.data(), b2.size() * 4, cudaMemcpyHostToDevice));
@@ -429,61 +544,45 @@ static int tc_build(ss_ctx* ctx) {
   T(t[RB_SPEC], 32, 128, 256);
 #undef T
   ctx->device_bytes += s->bytes;
+  *out = s;
   return SS_OK;
 }
 
-void tc_destroy(ss_ctx* ctx) {
-  TcState* s = static_cast<TcState*>(ctx->tc);
-  if (!s) return;
-  Tensor* ts[] = {&s->x0, &s->m4, &s->m3, &s->m2, &s->m1, &s->p1, &s->p2, &s->p3, &s->p4, &s->bott, &s->c9, &s->spec};
-  for (Tensor* t : ts) if (t->alloc) cudaFree(t->alloc);
-  for (int i = 0; i < RB_COUNT; ++i) {
-    if (s->t[i].alloc) cudaFree(s->t[i].alloc);
-    if (s->rb[i].c1.w) cudaFree(s->rb[i].c1.w);
-    if (s->rb[i].c2.w) cudaFree(s->rb[i].c2.w);
-    if (s->rb[i].res.w) cudaFree(s->rb[i].res.w);
-    if (s->rb[i].bias2) cudaFree(s->rb[i].bias2);
-  }
-  if (s->err) cudaFree(s->err);
-  if (s->prof) cudaFree(s->prof);
-  delete s;
-  ctx->tc = nullptr;
-}
-
-int classify_bf16(ss_ctx* ctx, const float* mel, int n_windows, float* logits, float* spec_out, cudaStream_t st) {
-  int rc = tc_build(ctx);
-  if (rc) return rc;
-  TcState* s = static_cast<TcState*>(ctx->tc);
+template <Prec P>
+int classify_tc_p(ss_ctx* ctx, TcState* s, const float* mel, int n_windows, float* logits, float* spec_out,
+                  cudaStream_t st) {
+  int rc;
   s->launch_index = 0;
   for (int b0 = 0; b0 < n_windows; b0 += s->max_batch) {
     const int B = (n_windows - b0 < s->max_batch) ? (n_windows - b0) : s->max_batch;
 #define SS_TRY(e) do { if ((rc = (e))) return rc; } while (0)
     const int64_t n_pix = (int64_t)B * kMels * kFrames;
-    mel_to_planar<<<(int)((n_pix + 255) / 256), 256, 0, st>>>(mel + (int64_t)b0 * kMels * kFrames, s->x0.data, n_pix);
+    mel_to_planar<P><<<(int)((n_pix + 255) / 256), 256, 0, st>>>(mel + (int64_t)b0 * kMels * kFrames, s->x0.data,
+                                                                 s->x0.lo, n_pix);
     SS_CUDA_CHECK(cudaGetLastError());
     count_launch();
-    SS_TRY(tc_res_block(s, RB_CONV1, s->x0, 0, 16, s->m4, 0, 0, B, st));
-    SS_TRY(tc_pool(s->m4, 0, 4, s->p1, B, st));
-    SS_TRY(tc_res_block(s, RB_CONV2, s->p1, 0, 32, s->m3, 0, 0, B, st));
-    SS_TRY(tc_pool(s->m3, 0, 8, s->p2, B, st));
-    SS_TRY(tc_res_block(s, RB_CONV3, s->p2, 0, 64, s->m2, 0, 0, B, st));
-    SS_TRY(tc_pool(s->m2, 0, 12, s->p3, B, st));
-    SS_TRY(tc_res_block(s, RB_CONV4, s->p3, 0, 96, s->m1, 0, 0, B, st));
-    SS_TRY(tc_pool(s->m1, 0, 16, s->p4, B, st));
-    SS_TRY(tc_res_block(s, RB_BOTTLENECK, s->p4, 0, 128, s->bott, 0, 0, B, st));
-    SS_TRY(tc_res_block(s, RB_ENCODER_OUT, s->bott, 0, 128, s->m1, 16, 1, B, st));   // -> up, cat after conv4
-    SS_TRY(tc_res_block(s, RB_CONV6, s->m1, 0, 256, s->m2, 12, 1, B, st));
-    SS_TRY(tc_res_block(s, RB_CONV7, s->m2, 0, 192, s->m3, 8, 1, B, st));
-    SS_TRY(tc_res_block(s, RB_CONV8, s->m3, 0, 128, s->m4, 4, 1, B, st));
-    SS_TRY(tc_res_block(s, RB_CONV9, s->m4, 0, 64, s->c9, 0, 0, B, st));
-    mask_head_planar<<<dim3(kFrames / kHeadFrames, B), kHeadCols * kHeadGroups, 0, st>>>(s->c9.data, ctx->head,
-                                                                                          logits + (int64_t)b0 * kFrames);
+    SS_TRY(tc_res_block(s, RB_CONV1, s->x0, 0, s->m4, 0, 0, B, st));
+    SS_TRY(tc_pool_p<P>(s->m4, 0, 4, s->p1, B, st));
+    SS_TRY(tc_res_block(s, RB_CONV2, s->p1, 0, s->m3, 0, 0, B, st));
+    SS_TRY(tc_pool_p<P>(s->m3, 0, 8, s->p2, B, st));
+    SS_TRY(tc_res_block(s, RB_CONV3, s->p2, 0, s->m2, 0, 0, B, st));
+    SS_TRY(tc_pool_p<P>(s->m2, 0, 12, s->p3, B, st));
+    SS_TRY(tc_res_block(s, RB_CONV4, s->p3, 0, s->m1, 0, 0, B, st));
+    SS_TRY(tc_pool_p<P>(s->m1, 0, 16, s->p4, B, st));
+    SS_TRY(tc_res_block(s, RB_BOTTLENECK, s->p4, 0, s->bott, 0, 0, B, st));
+    SS_TRY(tc_res_block(s, RB_ENCODER_OUT, s->bott, 0, s->m1, 16, 1, B, st));   // -> up, cat after conv4
+    SS_TRY(tc_res_block(s, RB_CONV6, s->m1, 0, s->m2, 12, 1, B, st));
+    SS_TRY(tc_res_block(s, RB_CONV7, s->m2, 0, s->m3, 8, 1, B, st));
+    SS_TRY(tc_res_block(s, RB_CONV8, s->m3, 0, s->m4, 4, 1, B, st));
+    SS_TRY(tc_res_block(s, RB_CONV9, s->m4, 0, s->c9, 0, 0, B, st));
+    mask_head_planar<P><<<dim3(kFrames / kHeadFrames, B), kHeadCols * kHeadGroups, 0, st>>>(
+        s->c9.data, s->c9.lo, ctx->head, logits + (int64_t)b0 * kFrames);
     SS_CUDA_CHECK(cudaGetLastError());
     count_launch();
     if (spec_out) {
-      SS_TRY(tc_res_block(s, RB_SPEC, s->c9, 0, 32, s->spec, 0, 0, B, st));
-      spec_out_planar<<<(int)((n_pix + 255) / 256), 256, 0, st>>>(s->spec.data, ctx->head,
-                                                                 spec_out + (int64_t)b0 * 2 * kMels * kFrames, n_pix);
+      SS_TRY(tc_res_block(s, RB_SPEC, s->c9, 0, s->spec, 0, 0, B, st));
+      spec_out_planar<P><<<(int)((n_pix + 255) / 256), 256, 0, st>>>(s->spec.data, s->spec.lo, ctx->head,
+                                                                    spec_out + (int64_t)b0 * 2 * kMels * kFrames, n_pix);
       SS_CUDA_CHECK(cudaGetLastError());
       count_launch();
     }
@@ -492,12 +591,60 @@ int classify_bf16(ss_ctx* ctx, const float* mel, int n_windows, float* logits, f
   return SS_OK;
 }
 
-// Debug / parity localisation: copy one internal activation of the last bf16 classify call to NCHW f32.
+bool prec_of_mode(int mode, Prec* p) {
+  switch (mode) {
+    case SS_MODE_BF16: *p = Prec::Bf16; return true;
+    case SS_MODE_F16: *p = Prec::F16; return true;
+    case SS_MODE_F16X3: *p = Prec::F16x3; return true;
+  }
+  return false;
+}
+
+}  // namespace
+
+void tc_destroy(ss_ctx* ctx) {
+  for (int slot = 0; slot < 3; ++slot) {
+    TcState* s = static_cast<TcState*>(ctx->tc[slot]);
+    if (!s) continue;
+    Tensor* ts[] = {&s->x0, &s->m4, &s->m3, &s->m2, &s->m1, &s->p1, &s->p2, &s->p3, &s->p4, &s->bott, &s->c9, &s->spec};
+    for (Tensor* t : ts) { if (t->alloc) cudaFree(t->alloc); if (t->alloc_lo) cudaFree(t->alloc_lo); }
+    for (int i = 0; i < RB_COUNT; ++i) {
+      if (s->t[i].alloc) cudaFree(s->t[i].alloc);
+      if (s->t[i].alloc_lo) cudaFree(s->t[i].alloc_lo);
+      if (s->rb[i].c1.w) cudaFree(s->rb[i].c1.w);
+      if (s->rb[i].c2.w) cudaFree(s->rb[i].c2.w);
+      if (s->rb[i].res.w) cudaFree(s->rb[i].res.w);
+      if (s->rb[i].bias2) cudaFree(s->rb[i].bias2);
+    }
+    if (s->err) cudaFree(s->err);
+    if (s->prof) cudaFree(s->prof);
+    delete s;
+    ctx->tc[slot] = nullptr;
+  }
+}
+
+int classify_tc(ss_ctx* ctx, int mode, const float* mel, int n_windows, float* logits, float* spec_out,
+                cudaStream_t st) {
+  Prec prec;
+  SS_REQUIRE(prec_of_mode(mode, &prec), SS_E_ARG, "mode %d is not a tensor-core mode", mode);
+  TcState* s = nullptr;
+  int rc = tc_build(ctx, prec, &s);
+  if (rc) return rc;
+  ctx->tc_last = (int)prec;
+  switch (prec) {
+    case Prec::Bf16: return classify_tc_p<Prec::Bf16>(ctx, s, mel, n_windows, logits, spec_out, st);
+    case Prec::F16: return classify_tc_p<Prec::F16>(ctx, s, mel, n_windows, logits, spec_out, st);
+    case Prec::F16x3: return classify_tc_p<Prec::F16x3>(ctx, s, mel, n_windows, logits, spec_out, st);
+  }
+  return SS_E_ARG;
+}
+
+// Debug / parity localisation: copy one internal activation of the last tensor-core classify call to NCHW f32.
 // which: 0 conv1, 1 conv2, 2 conv3, 3 conv4, 4 bottleneck, 5 up(encoder_out), 6 up(conv6), 7 up(conv7),
 //        8 up(conv8), 9 conv9, 10 t(conv1_1.conv1), 11 x0 (16 ch).
 int tc_debug_dump(ss_ctx* ctx, int which, int n_windows, float* out, int* C, int* H, int* W, cudaStream_t st) {
-  TcState* s = static_cast<TcState*>(ctx->tc);
-  SS_REQUIRE(s, SS_E_ARG, "bf16 path not initialised");
+  TcState* s = ctx->tc_last >= 0 ? static_cast<TcState*>(ctx->tc[ctx->tc_last]) : nullptr;
+  SS_REQUIRE(s, SS_E_ARG, "tensor-core path not initialised");
   struct Sel { const Tensor* t; int plane0, c; };
   const Sel table[] = {{&s->m4, 0, 32}, {&s->m3, 0, 64}, {&s->m2, 0, 96}, {&s->m1, 0, 128}, {&s->bott, 0, 128},
                        {&s->m1, 16, 128}, {&s->m2, 12, 96}, {&s->m3, 8, 64}, {&s->m4, 4, 32}, {&s->c9, 0, 32},
@@ -507,7 +654,12 @@ int tc_debug_dump(ss_ctx* ctx, int which, int n_windows, float* out, int* C, int
   *C = e.c; *H = e.t->H; *W = e.t->W;
   if (out) {
     const int64_t total = (int64_t)n_windows * e.c * e.t->H * e.t->W;
-    planar_to_nchw<<<(int)((total + 255) / 256), 256, 0, st>>>(e.t->data, e.t->planes, e.plane0, e.c, e.t->H, e.t->W, out, total);
+    const int grid = (int)((total + 255) / 256);
+    switch (s->prec) {
+      case Prec::Bf16: planar_to_nchw<Prec::Bf16><<<grid, 256, 0, st>>>(e.t->data, e.t->lo, e.t->planes, e.plane0, e.c, e.t->H, e.t->W, out, total); break;
+      case Prec::F16: planar_to_nchw<Prec::F16><<<grid, 256, 0, st>>>(e.t->data, e.t->lo, e.t->planes, e.plane0, e.c, e.t->H, e.t->W, out, total); break;
+      case Prec::F16x3: planar_to_nchw<Prec::F16x3><<<grid, 256, 0, st>>>(e.t->data, e.t->lo, e.t->planes, e.plane0, e.c, e.t->H, e.t->W, out, total); break;
+    }
     SS_CUDA_CHECK(cudaGetLastError());
   }
   int herr = 0;
@@ -517,15 +669,12 @@ int tc_debug_dump(ss_ctx* ctx, int which, int n_windows, float* out, int* C, int
   return SS_OK;
 }
 
-}  // namespace ss
-
-namespace ss {
-// Debug: select which conv launch (0-based, in issue order within one ss_classify call) records role timers,
-// and read the timers back ([148][8] int64: producer empty-wait, mma acc-empty-wait, mma full-wait, mma total,
-// epilogue acc-full-wait, epilogue total, -, units).
+// Debug: select which conv launch (0-based, in issue order within one ss_classify call) of the most recently used
+// tensor-core mode records role timers, and read the timers back ([148][8] int64: producer empty-wait, mma
+// acc-empty-wait, mma full-wait, mma total, epilogue acc-full-wait, epilogue total, -, units).
 int tc_debug_profile(ss_ctx* ctx, int select_launch, long long* out_host) {
-  TcState* s = static_cast<TcState*>(ctx->tc);
-  SS_REQUIRE(s, SS_E_ARG, "bf16 path not initialised");
+  TcState* s = ctx->tc_last >= 0 ? static_cast<TcState*>(ctx->tc[ctx->tc_last]) : nullptr;
+  SS_REQUIRE(s, SS_E_ARG, "tensor-core path not initialised");
   if (out_host) {
     SS_CUDA_CHECK(cudaDeviceSynchronize());
     SS_CUDA_CHECK(cudaMemcpy(out_host, s->prof, kNumSMs * 8 * sizeof(long long), cudaMemcpyDeviceToHost));
@@ -533,4 +682,19 @@ int tc_debug_profile(ss_ctx* ctx, int select_launch, long long* out_host) {
   s->prof_layer = select_launch;
   return SS_OK;
 }
+
+// The pipeline's bounded waits flag a time-out in device memory; surface it (0 = healthy).
+int tc_error_flag(ss_ctx* ctx, int* flag, cudaStream_t st) {
+  *flag = 0;
+  for (int slot = 0; slot < 3; ++slot) {
+    TcState* s = static_cast<TcState*>(ctx->tc[slot]);
+    if (!s) continue;
+    int h = 0;
+    SS_CUDA_CHECK(cudaMemcpyAsync(&h, s->err, sizeof(int), cudaMemcpyDeviceToHost, st));
+    SS_CUDA_CHECK(cudaStreamSynchronize(st));
+    if (h) *flag = h;
+  }
+  return SS_OK;
+}
+
 }  // namespace ss

@@ -2,25 +2,64 @@
 //
 // Persistent, warp-specialised, one CTA per SM:
 //   warp 4     producer  — cp.async.bulk (1-D TMA) of activation runs + packed weights into an smem ring
-//   warp 5     MMA       — one thread issues tcgen05.mma into one of two 256-column TMEM accumulator buffers
-//   warps 0-3  epilogue  — tcgen05.ld -> bias / ReLU / border mask -> bf16 -> 16-byte global stores
+//   warp 5     MMA       — one elected thread issues tcgen05.mma into one of two 256-column TMEM buffers
+//   warps 0-3  epilogue  — tcgen05.ld -> bias / ReLU / border mask -> 16-bit pack -> 16-byte global stores
 // The three roles are decoupled by mbarriers (full/empty per smem stage, acc_full/acc_empty per TMEM
 // buffer), so the loads of unit k+1, the MMAs of unit k and the epilogue of unit k-1 overlap.
+//
+// Operand precision is a template parameter:
+//   Bf16   — bf16 operands, one pass (throughput mode; ~4e-2 relative logit error over the 25-layer stack);
+//   F16    — fp16 operands, one pass (8x finer mantissa at the same cost);
+//   F16x3  — every fp32 value v is carried as hi = fp16(v), lo = fp16(v - hi) in two tensors and every product
+//            as hi*hi + hi*lo + lo*hi, all accumulated in the same fp32 TMEM tile: 3x the MMAs, ~2^-22
+//            relative operand error, which is what lets tensor-core logits meet the 1e-4 parity budget.
+//            The kernel sees the split as extra "sources" (x_hi with weight parts {w_hi, w_lo}, then x_lo with
+//            {w_hi}); accumulation order is irrelevant, so no special casing is needed in the pipeline.
 #pragma once
 
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include "ss_common.cuh"
 
 namespace ss {
 namespace tc {
 
-using bf16 = __nv_bfloat16;
-
 constexpr int kMaxStages = 8;
+constexpr int kMaxSources = 6;
 constexpr int kTcThreads = 192;
 constexpr int kAccCols = 256;             // TMEM columns per accumulator buffer (two buffers = all 512)
 constexpr uint32_t kSpinLimit = 1u << 22;
+
+enum class Prec : int { Bf16 = 0, F16 = 1, F16x3 = 2 };
+
+template <Prec P> struct PrecTraits;
+template <> struct PrecTraits<Prec::Bf16> { static constexpr bool split = false; static constexpr uint32_t fmt = 1; };
+template <> struct PrecTraits<Prec::F16> { static constexpr bool split = false; static constexpr uint32_t fmt = 0; };
+template <> struct PrecTraits<Prec::F16x3> { static constexpr bool split = true; static constexpr uint32_t fmt = 0; };
+
+// two floats -> one packed pair of 16-bit operands (and the packed residuals for the split format)
+template <Prec P>
+__device__ __forceinline__ uint32_t pack_hi(float a, float b) {
+  if constexpr (PrecTraits<P>::fmt == 1) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+  } else {
+    // fp16 saturates instead of overflowing to inf (activations beyond +-65504 are outside what this mode carries)
+    __half2 h = __floats2half2_rn(fminf(fmaxf(a, -65504.f), 65504.f), fminf(fmaxf(b, -65504.f), 65504.f));
+    return *reinterpret_cast<uint32_t*>(&h);
+  }
+}
+__device__ __forceinline__ uint32_t pack_lo_f16(float a, float b, uint32_t hi) {
+  const float2 h = __half22float2(*reinterpret_cast<const __half2*>(&hi));
+  __half2 l = __floats2half2_rn(a - h.x, b - h.y);
+  return *reinterpret_cast<uint32_t*>(&l);
+}
+template <Prec P>
+__device__ __forceinline__ float2 unpack2(uint32_t w) {
+  if constexpr (PrecTraits<P>::fmt == 1) return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w));
+  else return __half22float2(*reinterpret_cast<const __half2*>(&w));
+}
 
 // ------------------------------------------------------------------------------------------- PTX helpers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -108,61 +147,62 @@ __device__ __forceinline__ uint32_t elect_one() {
 // K-major, un-swizzled shared-memory matrix descriptor (cute::UMMA::SmemDescriptor, version 1):
 //   [0,14) start >> 4 | [16,30) LBO >> 4 (stride between the two 16-byte K chunks) |
 //   [32,46) SBO >> 4 (stride between 8-row core matrices) | [46,48) version = 1 | [61,64) layout = 0.
-__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-  return (uint64_t)((addr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
-         ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | ((uint64_t)1 << 46);
-}
-// Instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = BF16, both K-major, M = 128.
-__host__ __device__ constexpr uint32_t instr_desc(int n) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+// Instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = fmt (0 F16, 1 BF16), K-major, M = 128.
+__host__ __device__ constexpr uint32_t instr_desc(int n, uint32_t fmt) {
+  return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 }
 
 // --------------------------------------------------------------------------------------------- parameters
 struct TcSource {
-  const bf16* in;      // planar-8 padded tensor at the layer's resolution
+  const uint16_t* in;  // planar-8 padded tensor of 16-bit operands at the layer's resolution
   int planes_total;    // C/8 of that tensor
   int plane0;          // first plane this convolution reads
   int n_chunks;        // C_in / 16
   int taps;            // 9 (3x3) or 1 (1x1, centre)
-  const bf16* w;       // packed [n_chunks][taps][2][N][8]
+  int wparts;          // weight parts multiplied with this activation tensor (1, or 2 = {w_hi, w_lo})
+  int w_stride;        // 16-bit elements between consecutive chunks of `w` (>= wparts * taps * N * 16)
+  const uint16_t* w;   // packed [n_chunks][parts][taps][2][N][8]; the first `wparts` parts of a chunk are used
 };
 
 struct TcConv {
-  TcSource src[2];
+  TcSource src[kMaxSources];
   int n_src;
   int H, W;            // resolution of the inputs (and of the accumulator grid)
   const float* bias;   // [N]
+  float inv_scale;     // accumulators are multiplied by this (weights are pre-scaled by a power of two) before the bias
   int relu;
-  bf16* out;
+  uint16_t* out;       // hi (or only) output tensor
+  uint16_t* out_lo;    // residual output tensor (split precision), else null
   int out_planes_total, out_plane0, upsample;
-  int MT;              // 128-position tiles per work unit
   int units_per_image, total_units;
   int stages;          // smem ring depth (<= kMaxStages)
   int* err;
   long long* prof;     // optional [gridDim.x][8] cycle counters (role wait/busy times), may be null
 };
 
-__host__ __device__ inline size_t stage_bytes(int N, int W, int MT) {
-  return ((size_t)MT * 128 + 2 * (size_t)(W + 3)) * 32 + 9 * (size_t)N * 32;
-}
-
 // 128-position tiles per work unit: one 256-column TMEM accumulator buffer holds MT tiles of N columns.
-template <int N>
+template <int N, Prec P>
 struct TilesPerUnit {
   static constexpr int value = (N == 96) ? 2 : kAccCols / N;
 };
 
-template <int N>
+__host__ __device__ inline size_t stage_bytes(int N, int W, int MT, int wparts_max) {
+  return ((size_t)MT * 128 + 2 * (size_t)(W + 3)) * 32 + (size_t)wparts_max * 9 * (size_t)N * 32;
+}
+
+template <int N, Prec P>
 __global__ void __launch_bounds__(kTcThreads, 1)
 conv_tc_kernel(const TcConv p) {
   extern __shared__ __align__(128) unsigned char smem[];
-  constexpr int MT = TilesPerUnit<N>::value;
+  constexpr int MT = TilesPerUnit<N, P>::value;
+  constexpr bool kSplit = PrecTraits<P>::split;
+  constexpr int kWpartsMax = 1;          // every source brings one weight part per stage
   const int Wp = p.W + 2, Hp = p.H + 2;
   const int HpWp = Hp * Wp;
   const int halo = Wp + 1;
-  const int L = MT * 128 + 2 * halo;                  // positions staged per plane
+  const int L = MT * 128 + 2 * halo;                    // positions staged per plane
   const uint32_t a_bytes = (uint32_t)L * 32u;           // two planes
-  const uint32_t stage_sz = a_bytes + 9u * N * 32u;
+  const uint32_t stage_sz = a_bytes + (uint32_t)kWpartsMax * 9u * N * 32u;
   const int S = p.stages;
   unsigned char* stage0 = smem;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)S * stage_sz);
@@ -206,19 +246,19 @@ conv_tc_kernel(const TcConv p) {
       const int lo = (u - b * p.units_per_image) * MT * 128;   // first staged position (= q0 - halo)
       for (int s = 0; s < p.n_src && ok; ++s) {
         const TcSource& src = p.src[s];
-        const uint32_t w_bytes = (uint32_t)src.taps * N * 32u;
+        const uint32_t w_bytes = (uint32_t)(src.wparts * src.taps) * N * 32u;
         for (int kc = 0; kc < src.n_chunks; ++kc, ++it) {
           const int st = it % S;
           const uint32_t ph = (uint32_t)(it / S) & 1u;
           ok = mbar_wait_t(empty0 + 8 * st, ph ^ 1u, p.err, 1, w_empty);
           if (!ok) break;
           const uint32_t dst = smem_u32(stage0 + (size_t)st * stage_sz);
-          const bf16* plane = src.in + (((int64_t)b * src.planes_total + src.plane0 + 2 * kc) * HpWp + lo) * 8;
+          const uint16_t* plane = src.in + (((int64_t)b * src.planes_total + src.plane0 + 2 * kc) * HpWp + lo) * 8;
           if (elect_one()) {
             mbar_expect_tx(full0 + 8 * st, a_bytes + w_bytes);
             bulk_g2s(dst, plane, (uint32_t)L * 16u, full0 + 8 * st);
             bulk_g2s(dst + (uint32_t)L * 16u, plane + (int64_t)HpWp * 8, (uint32_t)L * 16u, full0 + 8 * st);
-            bulk_g2s(dst + a_bytes, src.w + (int64_t)kc * src.taps * N * 16, w_bytes, full0 + 8 * st);
+            bulk_g2s(dst + a_bytes, src.w + (int64_t)kc * src.w_stride, w_bytes, full0 + 8 * st);
           }
           __syncwarp();
         }
@@ -227,7 +267,7 @@ conv_tc_kernel(const TcConv p) {
     if (p.prof && lane == 0) p.prof[blockIdx.x * 8 + 0] = w_empty;
   } else if (warp == 5) {
     // ===================================================================== MMA issuer (warp-uniform)
-    constexpr uint32_t idesc = instr_desc(N);
+    constexpr uint32_t idesc = instr_desc(N, PrecTraits<P>::fmt);
     int tap_off[9];
 #pragma unroll
     for (int t = 0; t < 9; ++t) tap_off[t] = (t / 3 - 1) * Wp + (t % 3 - 1);
@@ -241,7 +281,7 @@ conv_tc_kernel(const TcConv p) {
     const long long t_begin = clock64();
     for (int u = blockIdx.x; u < p.total_units && ok; u += gridDim.x, ++k) {
       const int buf = k & 1;
-      ok = mbar_wait_t(acce0 + 8 * buf, (((uint32_t)k >> 1) & 1u) ^ 1u, p.err, 4, w_acce);   // epilogue drained this buffer
+      ok = mbar_wait_t(acce0 + 8 * buf, (((uint32_t)k >> 1) & 1u) ^ 1u, p.err, 4, w_acce);   // buffer drained
       if (!ok) break;
       tc_fence_after();
       const uint32_t acc = tmem_base + (uint32_t)(buf * kAccCols);
@@ -262,22 +302,31 @@ conv_tc_kernel(const TcConv p) {
           // cycles, twice the 32 + N/4 cycles the shared-memory operand fetch allows; tools/umma_bench.cu).
           if (elect_one()) {
             if (src.taps == 9) {
+#pragma unroll 1
+              for (int part = 0; part < src.wparts; ++part) {
+                const uint32_t b_lo_part = b_lo0 + (uint32_t)(part * 9 * N * 2);
 #pragma unroll
-              for (int tap = 0; tap < 9; ++tap) {
-                const uint64_t db = ((uint64_t)b_hi << 32) | (uint64_t)(b_lo0 + (uint32_t)(tap * N * 2));
-                const uint32_t a_lo_tap = a_lo0 + (uint32_t)tap_off[tap];
+                for (int tap = 0; tap < 9; ++tap) {
+                  const uint64_t db = ((uint64_t)b_hi << 32) | (uint64_t)(b_lo_part + (uint32_t)(tap * N * 2));
+                  const uint32_t a_lo_tap = a_lo0 + (uint32_t)tap_off[tap];
 #pragma unroll
-                for (int mt = 0; mt < MT; ++mt) {
-                  const uint64_t da = ((uint64_t)a_hi << 32) | (uint64_t)(a_lo_tap + (uint32_t)(mt * 128));
-                  tc_mma(acc + (uint32_t)(mt * N), da, db, idesc, tap == 0 ? accumulate : 1u);
+                  for (int mt = 0; mt < MT; ++mt) {
+                    const uint64_t da = ((uint64_t)a_hi << 32) | (uint64_t)(a_lo_tap + (uint32_t)(mt * 128));
+                    tc_mma(acc + (uint32_t)(mt * N), da, db, idesc, tap == 0 ? accumulate : 1u);
+                  }
                 }
+                accumulate = 1;
               }
             } else {
-              const uint64_t db = ((uint64_t)b_hi << 32) | (uint64_t)b_lo0;
+#pragma unroll 1
+              for (int part = 0; part < src.wparts; ++part) {
+                const uint64_t db = ((uint64_t)b_hi << 32) | (uint64_t)(b_lo0 + (uint32_t)(part * N * 2));
 #pragma unroll
-              for (int mt = 0; mt < MT; ++mt) {
-                const uint64_t da = ((uint64_t)a_hi << 32) | (uint64_t)(a_lo0 + (uint32_t)(mt * 128));
-                tc_mma(acc + (uint32_t)(mt * N), da, db, idesc, accumulate);
+                for (int mt = 0; mt < MT; ++mt) {
+                  const uint64_t da = ((uint64_t)a_hi << 32) | (uint64_t)(a_lo0 + (uint32_t)(mt * 128));
+                  tc_mma(acc + (uint32_t)(mt * N), da, db, idesc, accumulate);
+                }
+                accumulate = 1;
               }
             }
           }
@@ -299,6 +348,7 @@ conv_tc_kernel(const TcConv p) {
   } else {
     // ===================================================================== epilogue (warps 0-3)
     const int Wp2 = 2 * p.W + 2;
+    const float inv_scale = p.inv_scale;
     const int64_t out_plane_stride = p.upsample ? (int64_t)(2 * p.H + 2) * Wp2 * 8 : (int64_t)HpWp * 8;
     int k = 0;
     bool ok = true;
@@ -311,46 +361,52 @@ conv_tc_kernel(const TcConv p) {
       ok = mbar_wait_t(accf0 + 8 * buf, ((uint32_t)k >> 1) & 1u, p.err, 3, w_accf);
       if (!ok) break;
       tc_fence_after();
-      bf16* out_img = p.out + ((int64_t)b * p.out_planes_total + p.out_plane0) * out_plane_stride;
+      const int64_t img_off = ((int64_t)b * p.out_planes_total + p.out_plane0) * out_plane_stride;
       for (int mt = 0; mt < MT; ++mt) {
         const int pos = q0 + mt * 128 + warp * 32 + lane;
         const int y = pos / Wp, x = pos - y * Wp;
         const bool interior = (y >= 1) && (y <= p.H) && (x >= 1) && (x <= p.W);
         const bool in_tensor = pos < HpWp;
+        const int64_t up = (int64_t)(2 * y - 1) * Wp2 + (2 * x - 1);
 #pragma unroll
         for (int n0 = 0; n0 < N; n0 += 32) {
           uint32_t v[32];
           tc_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(buf * kAccCols + mt * N + n0), v);
-          uint4 pk[4];
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
-            uint32_t w[4];
+            uint32_t hw[4], lw[4];
 #pragma unroll
             for (int h = 0; h < 4; ++h) {
-              float f0 = __uint_as_float(v[g * 8 + 2 * h]) + bias_s[n0 + g * 8 + 2 * h];
-              float f1 = __uint_as_float(v[g * 8 + 2 * h + 1]) + bias_s[n0 + g * 8 + 2 * h + 1];
+              float f0 = fmaf(__uint_as_float(v[g * 8 + 2 * h]), inv_scale, bias_s[n0 + g * 8 + 2 * h]);
+              float f1 = fmaf(__uint_as_float(v[g * 8 + 2 * h + 1]), inv_scale, bias_s[n0 + g * 8 + 2 * h + 1]);
               if (p.relu) { f0 = fmaxf(f0, 0.f); f1 = fmaxf(f1, 0.f); }
               if (!interior) { f0 = 0.f; f1 = 0.f; }
-              __nv_bfloat162 h2 = __floats2bfloat162_rn(f0, f1);
-              w[h] = *reinterpret_cast<uint32_t*>(&h2);
+              hw[h] = pack_hi<P>(f0, f1);
+              if constexpr (kSplit) lw[h] = pack_lo_f16(f0, f1, hw[h]);
+              else lw[h] = 0u;
             }
-            pk[g] = make_uint4(w[0], w[1], w[2], w[3]);
-          }
-          if (!p.upsample) {
-            if (in_tensor) {
-#pragma unroll
-              for (int g = 0; g < 4; ++g)
-                *reinterpret_cast<uint4*>(out_img + (int64_t)(n0 / 8 + g) * out_plane_stride + (int64_t)pos * 8) = pk[g];
-            }
-          } else if (interior) {
-            const int64_t up = (int64_t)(2 * y - 1) * Wp2 + (2 * x - 1);
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-              bf16* o = out_img + (int64_t)(n0 / 8 + g) * out_plane_stride + up * 8;
-              *reinterpret_cast<uint4*>(o) = pk[g];
-              *reinterpret_cast<uint4*>(o + 8) = pk[g];
-              *reinterpret_cast<uint4*>(o + (int64_t)Wp2 * 8) = pk[g];
-              *reinterpret_cast<uint4*>(o + (int64_t)Wp2 * 8 + 8) = pk[g];
+            const uint4 ph = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+            const int64_t plane_off = img_off + (int64_t)(n0 / 8 + g) * out_plane_stride;
+            if (!p.upsample) {
+              if (in_tensor) {
+                *reinterpret_cast<uint4*>(p.out + plane_off + (int64_t)pos * 8) = ph;
+                if constexpr (kSplit)
+                  *reinterpret_cast<uint4*>(p.out_lo + plane_off + (int64_t)pos * 8) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+              }
+            } else if (interior) {
+              uint16_t* o = p.out + plane_off + up * 8;
+              *reinterpret_cast<uint4*>(o) = ph;
+              *reinterpret_cast<uint4*>(o + 8) = ph;
+              *reinterpret_cast<uint4*>(o + (int64_t)Wp2 * 8) = ph;
+              *reinterpret_cast<uint4*>(o + (int64_t)Wp2 * 8 + 8) = ph;
+              if constexpr (kSplit) {
+                const uint4 pl = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+                uint16_t* ol = p.out_lo + plane_off + up * 8;
+                *reinterpret_cast<uint4*>(ol) = pl;
+                *reinterpret_cast<uint4*>(ol + 8) = pl;
+                *reinterpret_cast<uint4*>(ol + (int64_t)Wp2 * 8) = pl;
+                *reinterpret_cast<uint4*>(ol + (int64_t)Wp2 * 8 + 8) = pl;
+              }
             }
           }
         }

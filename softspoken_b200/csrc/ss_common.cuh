@@ -123,7 +123,8 @@ struct ss_ctx {
   ss::ResBlockW rb[ss::RB_COUNT];
   ss::HeadW head;
   ss::WorkspaceF32 ws;
-  void* tc = nullptr;                 // tensor-core (bf16) state, see conv_tc.cu
+  void* tc[3] = {nullptr, nullptr, nullptr};   // tensor-core state per operand precision, see conv_tc.cu
+  int tc_last = -1;                   // precision slot of the most recent tensor-core classify call
   // file-level scratch (ss_detect_*): grown only inside ss_ctx_reserve_file
   int64_t file_cap_samples = 0;
   float* file_mel = nullptr;
@@ -174,9 +175,10 @@ int64_t regions_scan_tmp_len(int64_t out_len);
 // zero [begin - shift, end - shift) ∩ [0, n_elems) of pcm for every interval
 int launch_silence(float* pcm, int64_t n_elems, int64_t shift, const ss_interval* iv, int n_intervals, cudaStream_t st);
 // conv_tc.cu
-int tc_create(ss_ctx* ctx, const float* blob_host_payload);
 void tc_destroy(ss_ctx* ctx);
-int classify_bf16(ss_ctx* ctx, const float* mel, int n_windows, float* logits, float* spec_out, cudaStream_t st);
+int classify_tc(ss_ctx* ctx, int mode, const float* mel, int n_windows, float* logits, float* spec_out,
+                cudaStream_t st);
+int tc_error_flag(ss_ctx* ctx, int* flag, cudaStream_t st);
 int tc_debug_profile(ss_ctx* ctx, int select_launch, long long* out_host);
 int tc_debug_dump(ss_ctx* ctx, int which, int n_windows, float* out, int* C, int* H, int* W, cudaStream_t st);
 

@@ -22,6 +22,7 @@ import numpy as np
 import torch
 
 from . import checkpoint, settings, spec, wavio
+from ._lib import DEFAULT_MODE
 from .model import SpecUNet_2D
 
 
@@ -43,7 +44,7 @@ def bin_time_str(idx: int) -> str:
 
 
 class NNDetector:
-    def __init__(self, project_manager, mode: str = "fp32", device=None, max_batch: int = 32):
+    def __init__(self, project_manager, mode: str = DEFAULT_MODE, device=None, max_batch: int = 32):
         if not torch.cuda.is_available():
             raise RuntimeError("softspoken_b200.NNDetector needs a CUDA device (there is no CPU fallback)")
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)

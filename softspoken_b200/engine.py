@@ -21,7 +21,7 @@ def _ptr(t: Optional[torch.Tensor]):
 
 
 class Engine:
-    def __init__(self, state_dict, device: int | torch.device = 0, max_batch: int = 32, mode: str = "fp32"):
+    def __init__(self, state_dict, device: int | torch.device = 0, max_batch: int = 32, mode: str = _lib.DEFAULT_MODE):
         if not torch.cuda.is_available() or _lib.device_count() == 0:
             raise _lib.SoftspokenError(_lib.SS_E_NODEVICE,
                                        "no CUDA device: softspoken_b200 has no CPU fallback")

@@ -14,6 +14,7 @@ from typing import Optional
 import torch
 
 from . import checkpoint, spec
+from ._lib import DEFAULT_MODE
 from .engine import Engine
 
 
@@ -22,7 +23,7 @@ class SpecUNet_2D:
     output_shape = (2, 128, 256)
     n_mels = 128
 
-    def __init__(self, mode: str = "fp32", max_batch: int = 32):
+    def __init__(self, mode: str = DEFAULT_MODE, max_batch: int = 32):
         # The reference initialises randomly (torch defaults); a fixed seeded init keeps runs repeatable.
         self._sd = checkpoint.synthetic_state_dict(0)
         self._device: Optional[torch.device] = None

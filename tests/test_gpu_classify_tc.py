@@ -1,7 +1,10 @@
-"""Throughput mode (tcgen05, bf16 operands): layer-by-layer agreement with the fp32 oracle, within bf16 tolerance.
+"""Tensor-core classifier modes (tcgen05, 16-bit operands): layer-by-layer agreement with the fp32 oracle.
 
-north_star allows a documented tolerance for a bf16 GEMM path; the numbers asserted here are the ones
-DESIGN.md quotes.  Bit-exact detections are a property of the fp32 parity mode (test_gpu_detect.py)."""
+  f16x3  fp16 hi/lo split, three MMAs per product: the parity mode.  Logits must meet north_star's 1e-4
+         relative budget and the averaged-bin decisions of the 60 s clip must be identical to the reference's.
+  f16    fp16 single pass, bf16 single pass: throughput modes with the documented tolerances asserted here
+  bf16   (north_star allows a documented tolerance for a 16-bit GEMM path); DESIGN.md quotes these numbers.
+"""
 import ctypes as C
 
 import numpy as np
@@ -9,18 +12,23 @@ import pytest
 import torch
 
 from conftest import load_golden
-from softspoken_b200 import spec
 
 pytestmark = pytest.mark.gpu
 
-ACT_TOL = 4e-2        # max |delta| / max |ref| per activation tensor (bf16 storage between 25 conv layers)
-LOGIT_TOL = 6e-2      # logits: max |delta| / max |ref| (measured 3.4e-2..4.3e-2 on the seed-0 checkpoint)
+# mode -> (activation tol, logit tol): max |delta| / max |ref| over the tensor
+TOL = {
+    "f16x3": (5e-5, 1e-4),
+    "f16": (8e-3, 1.2e-2),
+    "bf16": (5e-2, 6e-2),
+}
+# allowed fraction of averaged timeline bins of the 60 s clip whose `> 0.1` decision differs from the reference
+FLIP_FRAC = {"f16x3": 0.0, "f16": 0.005, "bf16": 0.02}
 
 
-@pytest.fixture(scope="module")
-def engine(sd_seed0):
+@pytest.fixture(scope="module", params=["f16x3", "f16", "bf16"])
+def engine(request, sd_seed0):
     from softspoken_b200.engine import Engine
-    eng = Engine(sd_seed0, 0, max_batch=4, mode="bf16")
+    eng = Engine(sd_seed0, 0, max_batch=4, mode=request.param)
     yield eng
     eng.close()
 
@@ -38,64 +46,68 @@ def _dump(engine, which, n):
 def test_layerwise_against_oracle(engine, sd_seed0, clip60):
     from oracle import model as om
     from oracle import postproc as pp
+    act_tol, logit_tol = TOL[engine.mode]
     g = load_golden("model_seed0.npz")
     sel = g["starts"][[0, 41, 77]]
     padded = torch.from_numpy(pp.pad_audio(clip60)).cuda()
     mel = engine.features(padded, torch.from_numpy(sel))
-    logits = engine.classify(mel, mode="bf16")
+    logits = engine.classify(mel)
     torch.cuda.synchronize()
     taps = {}
     _, mk = om.forward_from_mel(sd_seed0, mel.cpu().unsqueeze(1), want_spec=False, taps=taps)
     up = lambda t: torch.nn.functional.interpolate(t, scale_factor=2, mode="nearest")
-    ref = {11: None, 10: None, 0: taps["conv1"], 1: taps["conv2"], 2: taps["conv3"], 3: taps["conv4"],
+    ref = {0: taps["conv1"], 1: taps["conv2"], 2: taps["conv3"], 3: taps["conv4"],
            4: taps["bottleneck"], 5: up(taps["encoder_out"]), 6: up(taps["conv6"]), 7: up(taps["conv7"]),
            8: up(taps["conv8"]), 9: taps["conv9"]}
     x0 = _dump(engine, 11, 3)
     e0 = float((x0[:, 0] - mel.cpu()).abs().max() / mel.cpu().abs().max())
-    print(f"x0 (mel as bf16): rel err {e0:.3e}; other channels max {float(x0[:, 1:].abs().max()):.1e}")
-    assert e0 < 1e-2 and float(x0[:, 1:].abs().max()) == 0.0
+    print(f"[{engine.mode}] x0 (mel as operand): rel err {e0:.3e}; other channels max {float(x0[:, 1:].abs().max()):.1e}")
+    assert e0 <= act_tol and float(x0[:, 1:].abs().max()) == 0.0
     worst = 0.0
-    for which in [0, 1, 2, 3, 4, 5, 6, 7, 8, 9]:
+    for which in range(10):
         got = _dump(engine, which, 3)
         want = ref[which]
         assert got.shape == want.shape, (which, got.shape, want.shape)
         err = float((got - want).abs().max() / want.abs().max())
-        print(f"activation {which}: shape {tuple(got.shape)} rel err {err:.3e}")
+        print(f"[{engine.mode}] activation {which}: shape {tuple(got.shape)} rel err {err:.3e}")
         worst = max(worst, err)
     lerr = float((logits.cpu() - mk[:, 0]).abs().max() / mk.abs().max())
-    print(f"logits rel err {lerr:.3e} (abs {float((logits.cpu() - mk[:, 0]).abs().max()):.3e})")
-    assert worst <= ACT_TOL
-    assert lerr <= LOGIT_TOL
+    print(f"[{engine.mode}] logits rel err {lerr:.3e} (abs {float((logits.cpu() - mk[:, 0]).abs().max()):.3e})")
+    assert worst <= act_tol
+    assert lerr <= logit_tol
 
 
-def test_bf16_logits_vs_reference_golden_and_interval_agreement(engine, clip60):
+def test_logits_vs_reference_golden_and_interval_agreement(engine, clip60):
     """Whole 60 s clip: logit error against the reference golden, and how many timeline bins change side."""
     from oracle import postproc as pp
+    _, logit_tol = TOL[engine.mode]
     g = load_golden("model_seed0.npz")
     padded = torch.from_numpy(pp.pad_audio(clip60)).cuda()
-    lg = engine.classify(engine.features(padded, torch.from_numpy(g["starts"])), mode="bf16").cpu().numpy()
+    lg = engine.classify(engine.features(padded, torch.from_numpy(g["starts"]))).cpu().numpy()
     ref = g["logits"][:, 0]
     err = np.max(np.abs(lg - ref))
     a_ref, c_ref = pp.average_idx(ref.reshape(-1, 1, 256), len(padded) / 22050)
     a_got, _ = pp.average_idx(lg.reshape(-1, 1, 256), len(padded) / 22050)
     cov = c_ref > 0
     flips = int(np.sum((a_ref[cov] > 0.1) != (a_got[cov] > 0.1)))
-    print(f"bf16 logits vs golden: max abs {err:.3e} (max |ref| {np.abs(ref).max():.3f}); averaged-bin decision flips "
-          f"{flips}/{int(cov.sum())}")
-    assert err <= LOGIT_TOL * np.abs(ref).max()
-    assert flips <= 0.02 * cov.sum()
+    print(f"[{engine.mode}] logits vs golden: max abs {err:.3e} (max |ref| {np.abs(ref).max():.3f}); averaged-bin "
+          f"decision flips {flips}/{int(cov.sum())}")
+    assert err <= logit_tol * np.abs(ref).max()
+    assert flips <= FLIP_FRAC[engine.mode] * cov.sum()
+    if engine.mode == "f16x3":
+        assert np.array_equal(pp.find_speech_regions_idx(a_got, c_ref), pp.find_speech_regions_idx(a_ref, c_ref))
 
 
-def test_bf16_batch_invariance_and_spec_head(engine, clip60):
+def test_batch_invariance_and_spec_head(engine, clip60):
     from oracle import postproc as pp
+    act_tol, _ = TOL[engine.mode]
     g = load_golden("model_seed0.npz")
     padded = torch.from_numpy(pp.pad_audio(clip60)).cuda()
     mel = engine.features(padded, torch.from_numpy(g["starts"][38:47]))
-    full, sp = engine.classify(mel, want_spec=True, mode="bf16")
-    parts = torch.cat([engine.classify(mel[:1], mode="bf16"), engine.classify(mel[1:6], mode="bf16"),
-                       engine.classify(mel[6:], mode="bf16")])
+    full, sp = engine.classify(mel, want_spec=True)
+    parts = torch.cat([engine.classify(mel[:1]), engine.classify(mel[1:6]), engine.classify(mel[6:])])
     assert torch.equal(full, parts)
     ref = torch.from_numpy(g["spec_w41"])
     err = float((sp[3].cpu() - ref).abs().max() / ref.abs().max())
-    print(f"bf16 spec head rel err {err:.3e}")
-    assert err <= ACT_TOL
+    print(f"[{engine.mode}] spec head rel err {err:.3e}")
+    assert err <= act_tol

@@ -1,4 +1,5 @@
-"""End-to-end on the GPU: synthetic wav -> regions -> CSV rows, bit-exact vs the reference goldens."""
+"""End-to-end on the GPU: synthetic wav -> regions -> CSV rows, bit-exact vs the reference goldens, in both
+parity-grade classifier modes (f16x3 = tensor cores with split fp16 operands, the default; fp32 = CUDA cores)."""
 import os
 import types
 
@@ -20,8 +21,8 @@ class _PM:
         return list(self.files)
 
 
-@pytest.fixture(scope="module")
-def detector(sd_seed0, tmp_path_factory):
+@pytest.fixture(scope="module", params=["f16x3", "fp32"])
+def detector(request, sd_seed0, tmp_path_factory):
     from softspoken_b200 import checkpoint, settings
     from softspoken_b200.detector import NNDetector
     d = tmp_path_factory.mktemp("ckpt")
@@ -29,7 +30,7 @@ def detector(sd_seed0, tmp_path_factory):
     checkpoint.save_checkpoint(sd_seed0, path, epoch=7)
     old = settings.model_dir, settings.model_name
     settings.model_dir, settings.model_name = str(d), "model_checkpoint.pth"
-    det = NNDetector(_PM([]), mode="fp32")
+    det = NNDetector(_PM([]), mode=request.param)
     settings.model_dir, settings.model_name = old
     assert det.load_checkpoint(det.model, path) == 8          # epoch + 1 (NNDetector.py:49-50)
     yield det

@@ -12,7 +12,7 @@ def main(path, top=40):
     n = 0
     for row in csv.DictReader(lines):
         name = row["Kernel Name"]
-        m = re.search(r"(conv_tc_kernel<\d+>|conv_nhwc_f32<[\d, ]+>|[A-Za-z_0-9]+)(?=\(|<|$)", name.split("::")[-1])
+        m = re.search(r"(conv_tc_kernel<[^>]*>|conv_nhwc_f32<[\d, ]+>|[A-Za-z_0-9]+)(?=\(|<|$)", name.split("::")[-1])
         name = m.group(1) if m else name[:50]
         t = float(row["Metric Value"]) / 1e3
         key = (name, row.get("Grid Size", ""), row.get("Block Size", ""))

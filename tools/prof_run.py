@@ -12,7 +12,7 @@ from softspoken_b200 import checkpoint, synth  # noqa: E402
 from softspoken_b200.engine import Engine  # noqa: E402
 
 ap = argparse.ArgumentParser()
-ap.add_argument("--mode", default="bf16")
+ap.add_argument("--mode", default="f16x3")
 ap.add_argument("--windows", type=int, default=128)
 ap.add_argument("--max-batch", type=int, default=64)
 ap.add_argument("--reps", type=int, default=1)

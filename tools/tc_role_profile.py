@@ -16,7 +16,8 @@ from softspoken_b200.engine import Engine  # noqa: E402
 with open(os.path.join(ROOT, "tests", "golden", "head_seed0.json")) as f:
     head = json.load(f)
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 64
-eng = Engine(checkpoint.synthetic_state_dict(0, head), 0, max_batch=B, mode="bf16")
+MODE = sys.argv[2] if len(sys.argv) > 2 else "f16x3"
+eng = Engine(checkpoint.synthetic_state_dict(0, head), 0, max_batch=B, mode=MODE)
 mel = torch.rand(B, 128, 256, device="cuda")
 eng.classify(mel)
 torch.cuda.synchronize()

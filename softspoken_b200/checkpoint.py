@@ -261,7 +261,7 @@ def sparse_filterbank(fb: torch.Tensor):
 
 BLOB_MAGIC = 0x53534232  # 'SSB2'
 BLOB_VERSION = 2
-MAX_MEL_TAPS = 64
+MAX_MEL_TAPS = 32
 
 
 def _conv2d_to_kernel_layout(w: torch.Tensor) -> np.ndarray:

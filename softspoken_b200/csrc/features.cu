@@ -5,65 +5,97 @@
 // 512-tap Hann frames at hop 256, |.|^2, 128-band HTK mel; root/code/backend/pytorch_neural_nets.py:92-99,144),
 // sqrt(log10(x + 1)) (:147) and the trim to 256 frames (:150).
 //
-// Data flow: PCM is read in place from the (optionally virtual) padded clip — no [W, 66150] window
-// matrix is ever materialised.  One CTA owns 32 consecutive frames of one window.  Per frame the 2048-point
-// spectrum of the 512 real taps is obtained from two 512-point complex FFTs (64 threads x 8 registers,
-// three radix-8 passes, two shared-memory exchanges):
+// Data flow: PCM is read in place from the (optionally virtual) padded clip — no [W, 66150] window matrix is
+// ever materialised.  The kernel is persistent (one 512-thread CTA per SM, tables loaded once); a work tile is
+// 32 consecutive frames of one window.  Phase 1: each of the 16 warps takes 2 of the frames and works alone (no
+// block barrier, __syncwarp only).  Per frame the 2048-point spectrum of the 512 real taps comes from two
+// 512-point complex FFTs, 16 points per lane (two radix-8 butterflies per pass, three passes, two exchanges
+// through a private 4.6 KB shared-memory buffer with conflict-free strides):
 //   FFT_A of a[n] = x[n] w[n] e^{-2 pi i n / 2048}         -> bins 4q+1 (A[q]) and 4q+3 (conj A[511-q])
 //   FFT_B of c[n] = x[2n] w[2n] + i x[2n+1] w[2n+1], n<256 -> even bins 2m by the real-FFT split
-// Only bins 1..743 are formed (the filterbank is zero elsewhere).  The mel reduction walks each band's
-// contiguous taps with 4 lanes per band and a warp-shuffle sum; the 128 x 32 output tile is staged in
-// shared memory and stored as full 128-byte rows of the [W][128][256] feature tensor.
+// Only bins 1..743 are formed (the filterbank is zero elsewhere); their powers go to a [bin][frame] tile in
+// shared memory (row stride 33, rows ordered so that every store is conflict-free).  Phase 2 (after one block
+// barrier): lane = frame; each warp walks the sparse triangular taps of 8 bands with one broadcast weight load
+// and one conflict-free power load per tap, and stores sqrt(log10(1 + mel)) as full 128-byte rows of the
+// [W][128][256] feature tensor.
 #include "ss_common.cuh"
 
 namespace ss {
 
 namespace {
 
-constexpr int kThreads = 128;
-constexpr int kFramesPerCta = 32;
-constexpr int kExA = 8 * 72;   // exchange A: [k1][t] with row stride 72 (bank-conflict-free both ways)
-constexpr int kExB = 64 * 9;   // exchange B: [k2a*8+k1][u] with row stride 9
-constexpr int kEvenBins = 372; // even bins 2m, m <= 371  (k <= 742)
-constexpr int kOddBins = 372;  // odd bins 2j+1, j <= 371 (k <= 743)
-constexpr int kMaxTapsSmem = 2048;
+constexpr int kWarps = 16;
+constexpr int kThreads = kWarps * 32;
+constexpr int kFramesPerTile = 32;
+constexpr int kFramesPerWarp = kFramesPerTile / kWarps;
+constexpr int kBandsPerWarp = kMels / kWarps;
+constexpr int kEx = 8 * 72;     // exchange A: [k1][t] with row stride 72; exchange B: [k2a*8+k1][u] with row stride 9
+constexpr int kEvenBins = 372;  // even bins 2m, m <= 371  (k <= 742)
+constexpr int kOddQ = 186;      // bins 4q+1 and 4q+3, q <= 185 (k <= 743)
+constexpr int kRows = 2 * kOddQ + kEvenBins;   // power rows: [4q+1 | 4q+3 | 2m]
+constexpr int kRowStride = kFramesPerTile + 1;
+constexpr int kMaxTaps = 2048;
 
-struct Smem {
-  float exA[2][2][kExA];
-  float exB[2][2][kExB];
-  float evenP[kEvenBins];
-  float oddP[kOddBins];
-  float2 tw[512];
-  float taps[kMaxTapsSmem];
-  int mstart[kMels], mcount[kMels], moffs[kMels];
-  float tile[kMels][kFramesPerCta + 1];
+struct WarpSmem {
+  float re[kEx];
+  float im[kEx];
 };
 
-// In-place forward 8-point DFT: y[k] = sum_j v[j] exp(-2 pi i j k / 8).
+struct Smem {
+  float2 tw1[7][64];            // W512^(t k1), k1 = 1..7
+  float2 tw2[7][64];            // W64^(u k2a), k2a = 1..7, u = t & 7
+  float tw_a_re[512], tw_a_im[512], win[512];
+  float2 tw1024[kEvenBins];
+  float taps[kMaxTaps];
+  int tap_row[kMaxTaps];         // row offset (row * kRowStride) of each tap's bin in the power tile
+  int mcount[kMels], moffs[kMels];
+  float P[kRows * kRowStride];  // power spectrum tile [row(bin)][frame]
+  WarpSmem w[kWarps];
+};
+
+// Row of bin k (1 <= k <= 743) in the power tile.
+__device__ __forceinline__ int row_of_bin(int k) {
+  return (k & 1) ? (((k & 2) ? kOddQ : 0) + (k >> 2)) : (2 * kOddQ + (k >> 1));
+}
+
+// In-place forward 8-point DFT: y[k] = sum_j v[j] exp(-2 pi i j k / 8).  kLow4: v[4..7] are zero (not read).
+template <bool kLow4>
 __device__ __forceinline__ void dft8(float (&re)[8], float (&im)[8]) {
   const float c = 0.70710678118654752440f;
-  // even half: v0 v2 v4 v6
-  float s0r = re[0] + re[4], s0i = im[0] + im[4];
-  float s1r = re[0] - re[4], s1i = im[0] - im[4];
-  float s2r = re[2] + re[6], s2i = im[2] + im[6];
-  float s3r = re[2] - re[6], s3i = im[2] - im[6];
-  float e0r = s0r + s2r, e0i = s0i + s2i;
-  float e2r = s0r - s2r, e2i = s0i - s2i;
-  float e1r = s1r + s3i, e1i = s1i - s3r;
-  float e3r = s1r - s3i, e3i = s1i + s3r;
-  // odd half: v1 v3 v5 v7
-  float t0r = re[1] + re[5], t0i = im[1] + im[5];
-  float t1r = re[1] - re[5], t1i = im[1] - im[5];
-  float t2r = re[3] + re[7], t2i = im[3] + im[7];
-  float t3r = re[3] - re[7], t3i = im[3] - im[7];
-  float o0r = t0r + t2r, o0i = t0i + t2i;
-  float o2r = t0r - t2r, o2i = t0i - t2i;
-  float o1r = t1r + t3i, o1i = t1i - t3r;
-  float o3r = t1r - t3i, o3i = t1i + t3r;
+  float e0r, e0i, e1r, e1i, e2r, e2i, e3r, e3i, o0r, o0i, o1r, o1i, o2r, o2i, o3r, o3i;
+  if constexpr (kLow4) {
+    e0r = re[0] + re[2]; e0i = im[0] + im[2];
+    e2r = re[0] - re[2]; e2i = im[0] - im[2];
+    e1r = re[0] + im[2]; e1i = im[0] - re[2];
+    e3r = re[0] - im[2]; e3i = im[0] + re[2];
+    o0r = re[1] + re[3]; o0i = im[1] + im[3];
+    o2r = re[1] - re[3]; o2i = im[1] - im[3];
+    o1r = re[1] + im[3]; o1i = im[1] - re[3];
+    o3r = re[1] - im[3]; o3i = im[1] + re[3];
+  } else {
+    // even half: v0 v2 v4 v6
+    const float s0r = re[0] + re[4], s0i = im[0] + im[4];
+    const float s1r = re[0] - re[4], s1i = im[0] - im[4];
+    const float s2r = re[2] + re[6], s2i = im[2] + im[6];
+    const float s3r = re[2] - re[6], s3i = im[2] - im[6];
+    e0r = s0r + s2r; e0i = s0i + s2i;
+    e2r = s0r - s2r; e2i = s0i - s2i;
+    e1r = s1r + s3i; e1i = s1i - s3r;
+    e3r = s1r - s3i; e3i = s1i + s3r;
+    // odd half: v1 v3 v5 v7
+    const float t0r = re[1] + re[5], t0i = im[1] + im[5];
+    const float t1r = re[1] - re[5], t1i = im[1] - im[5];
+    const float t2r = re[3] + re[7], t2i = im[3] + im[7];
+    const float t3r = re[3] - re[7], t3i = im[3] - im[7];
+    o0r = t0r + t2r; o0i = t0i + t2i;
+    o2r = t0r - t2r; o2i = t0i - t2i;
+    o1r = t1r + t3i; o1i = t1i - t3r;
+    o3r = t1r - t3i; o3i = t1i + t3r;
+  }
   // twiddles W8^k
-  float p1r = (o1r + o1i) * c, p1i = (o1i - o1r) * c;   // (1 - i)/sqrt2
-  float p2r = o2i, p2i = -o2r;                          // -i
-  float p3r = (o3i - o3r) * c, p3i = -(o3r + o3i) * c;  // (-1 - i)/sqrt2
+  const float p1r = (o1r + o1i) * c, p1i = (o1i - o1r) * c;   // (1 - i)/sqrt2
+  const float p2r = o2i, p2i = -o2r;                          // -i
+  const float p3r = (o3i - o3r) * c, p3i = -(o3r + o3i) * c;  // (-1 - i)/sqrt2
   re[0] = e0r + o0r; im[0] = e0i + o0i;
   re[4] = e0r - o0r; im[4] = e0i - o0i;
   re[1] = e1r + p1r; im[1] = e1i + p1i;
@@ -75,8 +107,8 @@ __device__ __forceinline__ void dft8(float (&re)[8], float (&im)[8]) {
 }
 
 __device__ __forceinline__ void cmul(float& r, float& i, float2 w) {
-  float nr = r * w.x - i * w.y;
-  float ni = r * w.y + i * w.x;
+  const float nr = r * w.x - i * w.y;
+  const float ni = r * w.y + i * w.x;
   r = nr;
   i = ni;
 }
@@ -85,154 +117,222 @@ __device__ __forceinline__ void cmul(float& r, float& i, float2 w) {
 // virtual padded clip: indices inside [valid_begin, valid_end) map to pcm[idx - offset], the rest are 0.
 __device__ __forceinline__ float load_sample(const float* __restrict__ pcm, int64_t wstart, int l,
                                              int64_t valid_begin, int64_t valid_end, int64_t offset) {
-  int64_t idx = wstart + (l < 0 ? -l : l);
+  const int64_t idx = wstart + (l < 0 ? -l : l);
   return (idx >= valid_begin && idx < valid_end) ? __ldg(pcm + (idx - offset)) : 0.0f;
 }
 
-__global__ void __launch_bounds__(kThreads)
+// Passes 2 and 3 of the 512-point FFT whose pass-1 results sit in the warp's exchange buffer (A layout).
+// On return (re, im)[h][k2b] = X[t + 64 k2b] with t = lane + 32 h.
+__device__ __forceinline__ void fft512_tail(WarpSmem& ws, const Smem& s, int lane, float (&re)[2][8], float (&im)[2][8]) {
+  __syncwarp();
+  // ---- pass 2: butterfly (k1, u) = (t >> 3, t & 7) transforms over v, twiddle W64^(u k2a)
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int t = lane + 32 * h, k1 = t >> 3, u = t & 7;
+#pragma unroll
+    for (int v = 0; v < 8; ++v) {
+      re[h][v] = ws.re[k1 * 72 + u + 8 * v];
+      im[h][v] = ws.im[k1 * 72 + u + 8 * v];
+    }
+  }
+  __syncwarp();
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int t = lane + 32 * h, k1 = t >> 3, u = t & 7;
+    dft8<false>(re[h], im[h]);
+#pragma unroll
+    for (int k2a = 0; k2a < 8; ++k2a) {
+      if (k2a) cmul(re[h][k2a], im[h][k2a], s.tw2[k2a - 1][t]);
+      ws.re[(k2a * 8 + k1) * 9 + u] = re[h][k2a];
+      ws.im[(k2a * 8 + k1) * 9 + u] = im[h][k2a];
+    }
+  }
+  __syncwarp();
+  // ---- pass 3: butterfly q0 = t = k1 + 8 k2a transforms over u -> X[q0 + 64 k2b]
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int t = lane + 32 * h;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      re[h][u] = ws.re[t * 9 + u];
+      im[h][u] = ws.im[t * 9 + u];
+    }
+  }
+  __syncwarp();                 // the buffer is free again once every lane has read
+#pragma unroll
+  for (int h = 0; h < 2; ++h) dft8<false>(re[h], im[h]);
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
 features_kernel(const float* __restrict__ pcm, int64_t valid_begin, int64_t valid_end, int64_t offset,
-                const int64_t* __restrict__ starts, int64_t w_base, FrontEnd fe, float* __restrict__ mel) {
+                const int64_t* __restrict__ starts, int64_t w_base, int n_tiles, FrontEnd fe, float* __restrict__ mel) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Smem& s = *reinterpret_cast<Smem*>(smem_raw);
 
   const int tid = threadIdx.x;
-  const int half = tid >> 6;      // 0: FFT_A, 1: FFT_B
-  const int t64 = tid & 63;
-  const int w = blockIdx.x;
-  const int frame0 = blockIdx.y * kFramesPerCta;
-  const int64_t wstart = starts ? starts[w] : (w_base + w) * (int64_t)kStepSamples;
+  const int warp = tid >> 5, lane = tid & 31;
 
-  for (int i = tid; i < 512; i += kThreads) s.tw[i] = fe.tw512[i];
+  // ---- CTA-resident tables
+  for (int i = tid; i < 7 * 64; i += kThreads) {
+    const int k = i / 64 + 1, t = i % 64;
+    s.tw1[k - 1][t] = fe.tw512[(t * k) & 511];
+    s.tw2[k - 1][t] = fe.tw512[(8 * (t & 7) * k) & 511];
+  }
+  for (int i = tid; i < 512; i += kThreads) {
+    s.tw_a_re[i] = fe.tw_a_re[i];
+    s.tw_a_im[i] = fe.tw_a_im[i];
+    s.win[i] = fe.window[i];
+  }
+  for (int i = tid; i < kEvenBins; i += kThreads) s.tw1024[i] = fe.tw1024[i];
   for (int i = tid; i < fe.n_taps; i += kThreads) s.taps[i] = fe.mel_taps[i];
   if (tid < kMels) {
-    s.mstart[tid] = fe.mel_start[tid];
-    s.mcount[tid] = fe.mel_count[tid];
-    s.moffs[tid] = fe.mel_offs[tid];
+    const int k0 = fe.mel_start[tid], cnt = fe.mel_count[tid], off = fe.mel_offs[tid];
+    s.mcount[tid] = cnt;
+    s.moffs[tid] = off;
+    for (int i = 0; i < cnt; ++i) s.tap_row[off + i] = row_of_bin(k0 + i) * kRowStride;
   }
   __syncthreads();
 
-  float* exAr = s.exA[half][0];
-  float* exAi = s.exA[half][1];
-  float* exBr = s.exB[half][0];
-  float* exBi = s.exB[half][1];
+  WarpSmem& ws = s.w[warp];
+  float re[2][8], im[2][8];
 
-  for (int f = 0; f < kFramesPerCta; ++f) {
-    const int l0 = (frame0 + f) * kHop - kHop;   // first sample of the frame relative to the window
-    float re[8], im[8];
+#pragma unroll 1
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int w = tile >> 3;                             // 8 tiles of 32 frames per window
+    const int frame0 = (tile & 7) * kFramesPerTile;
+    const int64_t wstart = starts ? starts[w] : (w_base + w) * (int64_t)kStepSamples;
 
-    // ---- stage 1: load, window, (pre-twiddle,) radix-8 over j, twiddle W512^(t k1)
-    if (half == 0) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int n = t64 + 64 * j;
-        const float x = load_sample(pcm, wstart, l0 + n, valid_begin, valid_end, offset);
-        re[j] = x * __ldg(fe.tw_a_re + n);
-        im[j] = x * __ldg(fe.tw_a_im + n);
+    // ======================================================================= phase 1: spectra (per warp)
+#pragma unroll 1
+    for (int fi = 0; fi < kFramesPerWarp; ++fi) {
+      const int f = warp * kFramesPerWarp + fi;
+      const int l0 = (frame0 + f) * kHop - kHop;   // first sample of the frame relative to the window
+      const int64_t g0 = wstart + l0;
+      const bool fast = (l0 >= 0) && (g0 >= valid_begin) && (g0 + kWin <= valid_end);   // warp-uniform
+      const float* __restrict__ src = pcm + (g0 - offset);
+      const bool fast2 = fast && (reinterpret_cast<uintptr_t>(src) & 7) == 0;            // 8-byte aligned frame
+      float* __restrict__ Pf = s.P + f;
+      {
+        // pull the samples of the next frame this warp will transform into L1 while this frame computes
+        const int ntile = (fi + 1 < kFramesPerWarp) ? tile : tile + (int)gridDim.x;
+        if (ntile < n_tiles && lane < 17) {
+          const int nw = ntile >> 3;
+          const int nf = (ntile & 7) * kFramesPerTile + warp * kFramesPerWarp + ((fi + 1) % kFramesPerWarp);
+          const int64_t nws = starts ? starts[nw] : (w_base + nw) * (int64_t)kStepSamples;
+          const int64_t ng = nws + (int64_t)nf * kHop - kHop + 32 * lane;
+          if (ng >= valid_begin && ng < valid_end) asm volatile("prefetch.global.L1 [%0];" ::"l"(pcm + (ng - offset)));
+        }
       }
-    } else {
+
+      // ------------------------------- FFT_A: a[n] = x[n] w[n] e^{-2 pi i n / 2048}
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int n = t64 + 64 * j;
-        const float x0 = load_sample(pcm, wstart, l0 + 2 * n, valid_begin, valid_end, offset);
-        const float x1 = load_sample(pcm, wstart, l0 + 2 * n + 1, valid_begin, valid_end, offset);
-        re[j] = x0 * __ldg(fe.window + 2 * n);
-        im[j] = x1 * __ldg(fe.window + 2 * n + 1);
+      for (int h = 0; h < 2; ++h) {
+        const int t = lane + 32 * h;
+        float x[8];
+        if (fast) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) x[j] = __ldg(src + t + 64 * j);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) x[j] = load_sample(pcm, wstart, l0 + t + 64 * j, valid_begin, valid_end, offset);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int n = t + 64 * j;
+          re[h][j] = x[j] * s.tw_a_re[n];
+          im[h][j] = x[j] * s.tw_a_im[n];
+        }
+        dft8<false>(re[h], im[h]);
+#pragma unroll
+        for (int k1 = 0; k1 < 8; ++k1) {
+          if (k1) cmul(re[h][k1], im[h][k1], s.tw1[k1 - 1][t]);
+          ws.re[k1 * 72 + t] = re[h][k1];
+          ws.im[k1 * 72 + t] = im[h][k1];
+        }
       }
+      fft512_tail(ws, s, lane, re, im);
 #pragma unroll
-      for (int j = 4; j < 8; ++j) { re[j] = 0.f; im[j] = 0.f; }
-    }
-    dft8(re, im);
+      for (int h = 0; h < 2; ++h) {
 #pragma unroll
-    for (int k1 = 0; k1 < 8; ++k1) {
-      if (k1) cmul(re[k1], im[k1], s.tw[t64 * k1]);
-      exAr[k1 * 72 + t64] = re[k1];
-      exAi[k1 * 72 + t64] = im[k1];
+        for (int k2b = 0; k2b < 8; ++k2b) {
+          const int q = lane + 32 * h + 64 * k2b;
+          const float pw = re[h][k2b] * re[h][k2b] + im[h][k2b] * im[h][k2b];
+          if (q < kOddQ) Pf[q * kRowStride] = pw;                              // bin 4q+1
+          if (q > 511 - kOddQ) Pf[(kOddQ + 511 - q) * kRowStride] = pw;        // bin 4(511-q)+3 (conjugate symmetry)
+        }
+      }
+
+      // ------------------------------- FFT_B: c[n] = x[2n] w[2n] + i x[2n+1] w[2n+1], n < 256 (rest zero)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int t = lane + 32 * h;
+        float2 x[4];
+        if (fast2) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) x[j] = __ldg(reinterpret_cast<const float2*>(src) + t + 64 * j);
+        } else if (fast) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) x[j] = make_float2(__ldg(src + 2 * (t + 64 * j)), __ldg(src + 2 * (t + 64 * j) + 1));
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            x[j] = make_float2(load_sample(pcm, wstart, l0 + 2 * (t + 64 * j), valid_begin, valid_end, offset),
+                               load_sample(pcm, wstart, l0 + 2 * (t + 64 * j) + 1, valid_begin, valid_end, offset));
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 wv = *reinterpret_cast<const float2*>(&s.win[2 * (t + 64 * j)]);
+          re[h][j] = x[j].x * wv.x;
+          im[h][j] = x[j].y * wv.y;
+        }
+        dft8<true>(re[h], im[h]);
+#pragma unroll
+        for (int k1 = 0; k1 < 8; ++k1) {
+          if (k1) cmul(re[h][k1], im[h][k1], s.tw1[k1 - 1][t]);
+          ws.re[k1 * 72 + t] = re[h][k1];
+          ws.im[k1 * 72 + t] = im[h][k1];
+        }
+      }
+      fft512_tail(ws, s, lane, re, im);
+      // C[q] parked in the exchange buffer, plain layout
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+#pragma unroll
+        for (int k2b = 0; k2b < 8; ++k2b) {
+          const int q = lane + 32 * h + 64 * k2b;
+          ws.re[q] = re[h][k2b];
+          ws.im[q] = im[h][k2b];
+        }
+      }
+      __syncwarp();
+      // ---- even bins: U[m] = (C[m] + conj C[512-m])/2 + W1024^m (C[m] - conj C[512-m])/(2i)
+      for (int m = lane; m < kEvenBins; m += 32) {
+        const int mm = (512 - m) & 511;
+        const float cr = ws.re[m], ci = ws.im[m];
+        const float nr = ws.re[mm], ni = -ws.im[mm];
+        const float er = 0.5f * (cr + nr), ei = 0.5f * (ci + ni);
+        const float dr = cr - nr, di = ci - ni;
+        float orr = 0.5f * di, oi = -0.5f * dr;
+        cmul(orr, oi, s.tw1024[m]);
+        const float ur = er + orr, ui = ei + oi;
+        Pf[(2 * kOddQ + m) * kRowStride] = ur * ur + ui * ui;
+      }
+      __syncwarp();   // the exchange buffer is reused by the next frame
     }
     __syncthreads();
 
-    // ---- stage 2: thread (k1, u) transforms over v, twiddle W64^(u k2a)
-    {
-      const int k1 = t64 >> 3, u = t64 & 7;
-#pragma unroll
-      for (int v = 0; v < 8; ++v) {
-        re[v] = exAr[k1 * 72 + u + 8 * v];
-        im[v] = exAi[k1 * 72 + u + 8 * v];
-      }
-      dft8(re, im);
-#pragma unroll
-      for (int k2a = 0; k2a < 8; ++k2a) {
-        if (k2a) cmul(re[k2a], im[k2a], s.tw[8 * u * k2a]);
-        exBr[(k2a * 8 + k1) * 9 + u] = re[k2a];
-        exBi[(k2a * 8 + k1) * 9 + u] = im[k2a];
-      }
-    }
-    __syncthreads();
-
-    // ---- stage 3: thread q0 = k1 + 8 k2a transforms over u -> X[q0 + 64 k2b]
-#pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      re[u] = exBr[t64 * 9 + u];
-      im[u] = exBi[t64 * 9 + u];
-    }
-    dft8(re, im);
-    if (half == 0) {
-#pragma unroll
-      for (int k2b = 0; k2b < 8; ++k2b) {
-        const int q = t64 + 64 * k2b;
-        const float pw = re[k2b] * re[k2b] + im[k2b] * im[k2b];
-        if (q <= 185) s.oddP[2 * q] = pw;                    // bin 4q+1
-        if (q >= 326) s.oddP[2 * (511 - q) + 1] = pw;        // bin 4(511-q)+3 = conj symmetry
-      }
-    } else {
-      // C[q] parked in FFT_B's (now free) exchange-A buffers, plain layout
-#pragma unroll
-      for (int k2b = 0; k2b < 8; ++k2b) {
-        const int q = t64 + 64 * k2b;
-        s.exA[1][0][q] = re[k2b];
-        s.exA[1][1][q] = im[k2b];
-      }
-    }
-    __syncthreads();
-
-    // ---- even bins: U[m] = (C[m] + conj C[512-m])/2 + W1024^m (C[m] - conj C[512-m])/(2i)
-    for (int m = tid; m < kEvenBins; m += kThreads) {
-      const int mm = (512 - m) & 511;
-      const float cr = s.exA[1][0][m], ci = s.exA[1][1][m];
-      const float nr = s.exA[1][0][mm], ni = -s.exA[1][1][mm];
-      const float er = 0.5f * (cr + nr), ei = 0.5f * (ci + ni);
-      const float dr = cr - nr, di = ci - ni;
-      float orr = 0.5f * di, oi = -0.5f * dr;
-      cmul(orr, oi, __ldg(fe.tw1024 + m));
-      const float ur = er + orr, ui = ei + oi;
-      s.evenP[m] = ur * ur + ui * ui;
-    }
-    __syncthreads();
-
-    // ---- mel: 4 lanes per band, 32 bands per round, warp-shuffle reduction
-#pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      const int band = r * 32 + (tid >> 2);
-      const int lane4 = tid & 3;
-      const int k0 = s.mstart[band], cnt = s.mcount[band], off = s.moffs[band];
+    // ======================================================================= phase 2: mel (lane = frame)
+    float* __restrict__ out = mel + ((int64_t)w * kMels) * kFrames + frame0 + lane;
+#pragma unroll 1
+    for (int j = 0; j < kBandsPerWarp; ++j) {
+      const int band = warp + kWarps * j;              // interleaved: narrow and wide bands mix in every warp
+      const int cnt = s.mcount[band], off = s.moffs[band];
+      const float* __restrict__ Pl = s.P + lane;
       float acc = 0.f;
-      for (int i = lane4; i < cnt; i += 4) {
-        const int k = k0 + i;
-        const float p = (k & 1) ? s.oddP[k >> 1] : s.evenP[k >> 1];
-        acc = fmaf(s.taps[off + i], p, acc);
-      }
-      acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-      acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-      if (lane4 == 0) s.tile[band][f] = sqrtf(log10f(acc + 1.0f));
+      for (int i = off; i < off + cnt; ++i) acc = fmaf(s.taps[i], Pl[s.tap_row[i]], acc);
+      out[(int64_t)band * kFrames] = sqrtf(log10f(acc + 1.0f));
     }
-    // the next frame's stage-1 writes touch exA only; its first barrier orders them after this
-    // frame's evenP/oddP reads, and the barrier above ordered the C reads before them.
-  }
-  __syncthreads();
-
-  float* out = mel + ((int64_t)w * kMels) * kFrames + frame0;
-  for (int idx = tid; idx < kMels * kFramesPerCta; idx += kThreads) {
-    const int m = idx >> 5, f = idx & 31;
-    out[(int64_t)m * kFrames + f] = s.tile[m][f];
+    __syncthreads();   // the power tile is rewritten by the next work tile
   }
 }
 
@@ -261,10 +361,10 @@ int launch_features_virtual(const ss_ctx* ctx, const float* pcm, int64_t valid_b
                             int64_t offset, const int64_t* starts, int64_t w_base, int n_windows, float* mel,
                             cudaStream_t st) {
   if (n_windows <= 0) return SS_OK;
-  SS_REQUIRE(ctx->fe.n_taps <= kMaxTapsSmem, SS_E_BLOB, "mel filterbank has %d taps (> %d)", ctx->fe.n_taps,
-             kMaxTapsSmem);
-  dim3 grid(n_windows, kFrames / kFramesPerCta);
-  features_kernel<<<grid, kThreads, sizeof(Smem), st>>>(pcm, valid_begin, valid_end, offset, starts, w_base,
+  SS_REQUIRE(ctx->fe.n_taps <= kMaxTaps, SS_E_BLOB, "mel filterbank has %d taps (> %d)", ctx->fe.n_taps, kMaxTaps);
+  const int n_tiles = n_windows * (kFrames / kFramesPerTile);
+  const int grid = n_tiles < kNumSMs ? n_tiles : kNumSMs;
+  features_kernel<<<grid, kThreads, sizeof(Smem), st>>>(pcm, valid_begin, valid_end, offset, starts, w_base, n_tiles,
                                                         ctx->fe, mel);
   SS_CUDA_CHECK(cudaGetLastError());
   count_launch();

@@ -23,7 +23,7 @@ constexpr int kNfft = 2048;                        // pytorch_neural_nets.py:94
 constexpr int kFrames = 256;                       // pytorch_neural_nets.py:150
 constexpr int kMels = 128;                         // pytorch_neural_nets.py:87
 constexpr int kFreqs = 1025;
-constexpr int kMaxMelTaps = 64;
+constexpr int kMaxMelTaps = 32;    // rows of the feature kernel's transposed tap table
 constexpr int kGapBins = 42;                       // 0.5 s break (worker.py:97) on the 256/3 Hz timeline
 constexpr int kNumSMs = 148;
 

@@ -84,7 +84,10 @@ __device__ __forceinline__ void store8(uint16_t* __restrict__ hi, uint16_t* __re
 }
 
 // ------------------------------------------------------------------------------------------ small kernels
-// mel f32 [B][128][256] -> channel 0 of plane 0 of a 16-channel planar tensor (planes 0,1; rest stays zero)
+// mel f32 [B][128][256] -> the first layer's operand tensor: a 16-channel planar tensor whose channel c < 9 is
+// the mel image shifted by tap c = (dy+1)*3 + (dx+1) (zero outside the image), channels 9..15 zero.  The single
+// input channel of conv1_1 is thereby unrolled into the GEMM K dimension (im2col in K): its 3x3 convolution is
+// one K=16 MMA per tile instead of nine MMAs with 15/16 of K empty, and its 1x1 residual reads channel 4.
 template <Prec P>
 __global__ void mel_to_planar(const float* __restrict__ mel, uint16_t* __restrict__ out, uint16_t* __restrict__ out_lo,
                               int64_t n_pix) {
@@ -94,8 +97,18 @@ __global__ void mel_to_planar(const float* __restrict__ mel, uint16_t* __restric
   const int y = (int)((i / kFrames) % kMels);
   const int64_t b = i / ((int64_t)kFrames * kMels);
   const int Wp = kFrames + 2, Hp = kMels + 2;
-  const float f[8] = {__ldg(mel + i), 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  store8<P>(out, out_lo, (b * 2) * Hp * Wp + (int64_t)(y + 1) * Wp + (x + 1), f);
+  const float* img = mel + b * (int64_t)kFrames * kMels;
+  float f[16];
+#pragma unroll
+  for (int c = 0; c < 16; ++c) {
+    const int yy = y + c / 3 - 1, xx = x + c % 3 - 1;
+    f[c] = (c < 9 && yy >= 0 && yy < kMels && xx >= 0 && xx < kFrames) ? __ldg(img + yy * kFrames + xx) : 0.f;
+  }
+  const int64_t pix = (b * 2) * Hp * Wp + (int64_t)(y + 1) * Wp + (x + 1);
+  const float lo8[8] = {f[0], f[1], f[2], f[3], f[4], f[5], f[6], f[7]};
+  const float hi8[8] = {f[8], f[9], f[10], f[11], f[12], f[13], f[14], f[15]};
+  store8<P>(out, out_lo, pix, lo8);
+  store8<P>(out, out_lo, pix + (int64_t)Hp * Wp, hi8);
 }
 
 // MaxPool2d(2) on planar tensors: in planes [plane0, plane0+planes) of a tensor with in_planes_total planes at
@@ -264,8 +277,9 @@ struct Tensor {
 };
 
 struct PackedConv {
-  uint16_t* w = nullptr;   // [n_chunks][parts][taps][2][n][8]
+  uint16_t* w = nullptr;   // plain: [n_chunks][parts][taps][2][n][8];  dual: [n_chunks][taps][2][2n][8] (hi rows, lo rows)
   int n_chunks = 0, taps = 0, n = 0, parts = 1;
+  bool dual = false;
 };
 
 struct TcBlock {
@@ -293,6 +307,8 @@ struct TcState {
 namespace {
 
 bool is_split(Prec p) { return p == Prec::F16x3; }
+// Layers whose doubled C_out still fits one MMA cheaply use the dual layout (see conv_tc_kernel.cuh).
+bool is_dual(Prec p, int n) { return is_split(p) && n <= 64; }
 
 int alloc_tensor(TcState* st, Tensor* t, int B, int C, int H, int W) {
   t->planes = C / 8;
@@ -336,7 +352,13 @@ float weight_scale(Prec p, std::initializer_list<const std::vector<float>*> ws) 
 int pack_conv(TcState* st, const float* w, int taps, int cin, int cout, float scale, PackedConv* out) {
   const int n_chunks = (cin + 15) / 16;
   const int parts = is_split(st->prec) ? 2 : 1;
+  const bool dual = is_dual(st->prec, cout);
   std::vector<uint16_t> h((size_t)n_chunks * parts * taps * 2 * cout * 8);
+  // element index of (chunk, part, tap, K-half, row, j) in the plain or the dual layout
+  auto at = [&](int kc, int part, int t, int hh, int n, int j) -> size_t {
+    if (dual) return (((((size_t)kc * taps + t) * 2 + hh) * 2 + part) * cout + n) * 8 + j;
+    return (((((size_t)kc * parts + part) * taps + t) * 2 + hh) * cout + n) * 8 + j;
+  };
   for (int kc = 0; kc < n_chunks; ++kc)
     for (int t = 0; t < taps; ++t)
       for (int hh = 0; hh < 2; ++hh)
@@ -344,14 +366,12 @@ int pack_conv(TcState* st, const float* w, int taps, int cin, int cout, float sc
           for (int j = 0; j < 8; ++j) {
             const int c = kc * 16 + hh * 8 + j;
             const float v = (c < cin) ? w[((size_t)t * cin + c) * cout + n] * scale : 0.f;
-            const size_t at = (((((size_t)kc * parts + 0) * taps + t) * 2 + hh) * cout + n) * 8 + j;
             if (st->prec == Prec::Bf16) {
-              h[at] = to_bits_bf16(v);
+              h[at(kc, 0, t, hh, n, j)] = to_bits_bf16(v);
             } else {
               const uint16_t hi = to_bits_f16(v);
-              h[at] = hi;
-              if (parts == 2)
-                h[(((((size_t)kc * parts + 1) * taps + t) * 2 + hh) * cout + n) * 8 + j] = to_bits_f16(v - from_bits_f16(hi));
+              h[at(kc, 0, t, hh, n, j)] = hi;
+              if (parts == 2) h[at(kc, 1, t, hh, n, j)] = to_bits_f16(v - from_bits_f16(hi));
             }
           }
   SS_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&out->w), h.size() * sizeof(uint16_t)));
@@ -361,15 +381,16 @@ int pack_conv(TcState* st, const float* w, int taps, int cin, int cout, float sc
   out->taps = taps;
   out->n = cout;
   out->parts = parts;
+  out->dual = dual;
   return SS_OK;
 }
 
 constexpr size_t kSmemTail = (2 * kMaxStages + 4) * 8 + 128 * 4 + 16;   // barriers + bias + TMEM slot
 
-template <int N, Prec P>
+template <int N, Prec P, bool Dual>
 int launch_conv_np(TcConv p, int B, cudaStream_t st) {
-  constexpr int MT = TilesPerUnit<N, P>::value;
-  const size_t sb = stage_bytes(N, p.W, MT, 1);
+  constexpr int MT = TilesPerUnit<N, Dual>::value;
+  const size_t sb = stage_bytes(N, p.W, MT, Dual);
   int stages = (int)((kSmemBudget - kSmemTail) / sb);
   if (stages > kMaxStages) stages = kMaxStages;
   SS_REQUIRE(stages >= 2, SS_E_ARG, "conv stage of %zu bytes does not fit twice in shared memory", sb);
@@ -377,7 +398,7 @@ int launch_conv_np(TcConv p, int B, cudaStream_t st) {
   const size_t smem = (size_t)stages * sb + kSmemTail;
   static bool configured = false;
   if (!configured) {
-    SS_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<N, P>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    SS_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<N, P, Dual>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)kSmemBudget));
     configured = true;
   }
@@ -385,7 +406,7 @@ int launch_conv_np(TcConv p, int B, cudaStream_t st) {
   p.units_per_image = (positions + MT * 128 - 1) / (MT * 128);
   p.total_units = p.units_per_image * B;
   const int grid = p.total_units < kNumSMs ? p.total_units : kNumSMs;
-  conv_tc_kernel<N, P><<<grid, kTcThreads, smem, st>>>(p);
+  conv_tc_kernel<N, P, Dual><<<grid, kTcThreads, smem, st>>>(p);
   SS_CUDA_CHECK(cudaGetLastError());
   count_launch();
   return SS_OK;
@@ -393,11 +414,12 @@ int launch_conv_np(TcConv p, int B, cudaStream_t st) {
 
 template <Prec P>
 int launch_conv_p(const TcConv& p, int N, int B, cudaStream_t st) {
+  constexpr bool kDualSmall = PrecTraits<P>::split;      // == is_dual(P, N) for N <= 64
   switch (N) {
-    case 32: return launch_conv_np<32, P>(p, B, st);
-    case 64: return launch_conv_np<64, P>(p, B, st);
-    case 96: return launch_conv_np<96, P>(p, B, st);
-    case 128: return launch_conv_np<128, P>(p, B, st);
+    case 32: return launch_conv_np<32, P, kDualSmall>(p, B, st);
+    case 64: return launch_conv_np<64, P, kDualSmall>(p, B, st);
+    case 96: return launch_conv_np<96, P, false>(p, B, st);
+    case 128: return launch_conv_np<128, P, false>(p, B, st);
   }
   set_error("unsupported C_out %d", N);
   return SS_E_ARG;
@@ -412,11 +434,14 @@ int launch_conv(Prec prec, const TcConv& p, int N, int B, cudaStream_t st) {
   return SS_E_ARG;
 }
 
-// Sources of one convolution of tensor `x` (planes from plane0) with packed weights `w`.  Single precision is
-// one source.  The split precision is three — x_lo . w_hi, x_hi . w_lo (the corrections) and x_hi . w_hi (the
-// main term) — and a launch issues every correction before any main term: the tensor core truncates the fp32
-// accumulator after every MMA, so the small terms are summed while the accumulator (and its ulp) is still small
-// (Ootomo & Yokota 2022 observe the same for mma.sync; tools/precision_study.py measures it here).
+// Sources of one convolution of tensor `x` (planes from plane0) with packed weights `w`.
+//  * single precision: one source;
+//  * split, dual layout (C_out <= 64): x_hi . [w_hi | w_lo] as one 2N-column source, then x_lo . w_hi into the
+//    correction columns; the first source of a launch must be a dual one (its first MMA zeroes both groups);
+//  * split, C_out >= 96: three sources — x_lo . w_hi, x_hi . w_lo (the corrections) and x_hi . w_hi (the main
+//    term) — and a launch issues every correction before any main term: the tensor core truncates the fp32
+//    accumulator after every MMA, so the small terms are summed while the accumulator (and its ulp) is still
+//    small (Ootomo & Yokota 2022 observe the same for mma.sync; tools/precision_study.py measures it here).
 enum class Terms { All, Corrections, Main };
 
 void add_sources(TcConv* p, const TcState* s, const Tensor& x, int plane0, const PackedConv& w, Terms terms) {
@@ -424,15 +449,22 @@ void add_sources(TcConv* p, const TcState* s, const Tensor& x, int plane0, const
   const int chunk_elems = w.parts * part_elems;
   if (!is_split(s->prec)) {
     if (terms != Terms::Corrections)
+      p->src[p->n_src++] = TcSource{x.data, x.planes, plane0, w.n_chunks, w.taps, 0, chunk_elems, w.w};
+    return;
+  }
+  if (w.dual) {
+    if (terms != Terms::Corrections) {
       p->src[p->n_src++] = TcSource{x.data, x.planes, plane0, w.n_chunks, w.taps, 1, chunk_elems, w.w};
+      p->src[p->n_src++] = TcSource{x.lo, x.planes, plane0, w.n_chunks, w.taps, 2, chunk_elems, w.w};
+    }
     return;
   }
   if (terms != Terms::Main) {
-    p->src[p->n_src++] = TcSource{x.lo, x.planes, plane0, w.n_chunks, w.taps, 1, chunk_elems, w.w};
-    p->src[p->n_src++] = TcSource{x.data, x.planes, plane0, w.n_chunks, w.taps, 1, chunk_elems, w.w + part_elems};
+    p->src[p->n_src++] = TcSource{x.lo, x.planes, plane0, w.n_chunks, w.taps, 0, chunk_elems, w.w};
+    p->src[p->n_src++] = TcSource{x.data, x.planes, plane0, w.n_chunks, w.taps, 0, chunk_elems, w.w + part_elems};
   }
   if (terms != Terms::Corrections)
-    p->src[p->n_src++] = TcSource{x.data, x.planes, plane0, w.n_chunks, w.taps, 1, chunk_elems, w.w};
+    p->src[p->n_src++] = TcSource{x.data, x.planes, plane0, w.n_chunks, w.taps, 0, chunk_elems, w.w};
 }
 
 // One ResBlock: t = relu(conv3x3(x) + b1);  out = relu(conv3x3(t) + conv1x1(x) + b2 + b_res).
@@ -504,9 +536,21 @@ int tc_build(ss_ctx* ctx, Prec prec, TcState** out) {
     if ((rc = fetch(rb.res, &wr, &br))) return rc;
     const float s1 = weight_scale(prec, {&w1});
     const float s2 = weight_scale(prec, {&w2, &wr});       // conv2 and the residual share one accumulator
-    if ((rc = pack_conv(s, w1.data(), 9, rb.c1.cin, rb.c1.cout, s1, &s->rb[i].c1))) return rc;
+    if (i == RB_CONV1) {
+      // C_in = 1: the nine taps become input channels 0..8 of a 1x1 convolution over the im2col'd operand
+      // tensor written by mel_to_planar; the residual 1x1 reads the centre tap (channel 4).
+      const int co = rb.c1.cout;
+      std::vector<float> w1k((size_t)16 * co, 0.f), wrk((size_t)16 * co, 0.f);
+      for (int t = 0; t < 9; ++t)
+        for (int n = 0; n < co; ++n) w1k[(size_t)t * co + n] = w1[(size_t)t * co + n];
+      for (int n = 0; n < co; ++n) wrk[(size_t)4 * co + n] = wr[n];
+      if ((rc = pack_conv(s, w1k.data(), 1, 16, co, s1, &s->rb[i].c1))) return rc;
+      if ((rc = pack_conv(s, wrk.data(), 1, 16, co, s2, &s->rb[i].res))) return rc;
+    } else {
+      if ((rc = pack_conv(s, w1.data(), 9, rb.c1.cin, rb.c1.cout, s1, &s->rb[i].c1))) return rc;
+      if ((rc = pack_conv(s, wr.data(), 1, rb.res.cin, rb.res.cout, s2, &s->rb[i].res))) return rc;
+    }
     if ((rc = pack_conv(s, w2.data(), 9, rb.c2.cin, rb.c2.cout, s2, &s->rb[i].c2))) return rc;
-    if ((rc = pack_conv(s, wr.data(), 1, rb.res.cin, rb.res.cout, s2, &s->rb[i].res))) return rc;
     s->rb[i].inv_scale1 = 1.f / s1;
     s->rb[i].inv_scale2 = 1.f / s2;
     for (size_t k = 0; k < b2.size(); ++k) b2[k] += br[k];

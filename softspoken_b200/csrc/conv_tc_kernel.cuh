@@ -13,8 +13,13 @@
 //   F16x3  — every fp32 value v is carried as hi = fp16(v), lo = fp16(v - hi) in two tensors and every product
 //            as hi*hi + hi*lo + lo*hi, all accumulated in the same fp32 TMEM tile: 3x the MMAs, ~2^-22
 //            relative operand error, which is what lets tensor-core logits meet the 1e-4 parity budget.
-//            The kernel sees the split as extra "sources" (x_hi with weight parts {w_hi, w_lo}, then x_lo with
-//            {w_hi}); accumulation order is irrelevant, so no special casing is needed in the pipeline.
+//            The kernel sees the split as extra "sources".  For C_out <= 64 ("dual" layout) x_hi is multiplied
+//            with [w_hi | w_lo] in ONE MMA of 2 C_out columns (the A tile — the shared-memory bottleneck of
+//            small-N MMAs — is fetched once instead of twice), main and correction terms land in separate
+//            TMEM column groups, x_lo . w_hi accumulates into the correction group and the epilogue adds the
+//            two.  For C_out >= 96 the three products are separate sources into one accumulator, corrections
+//            first (the tensor core truncates the fp32 accumulator after every MMA, so small terms are summed
+//            while the accumulator is still small).
 #pragma once
 
 #include <cuda_bf16.h>
@@ -159,9 +164,11 @@ struct TcSource {
   int plane0;          // first plane this convolution reads
   int n_chunks;        // C_in / 16
   int taps;            // 9 (3x3) or 1 (1x1, centre)
-  int wparts;          // weight parts multiplied with this activation tensor (1, or 2 = {w_hi, w_lo})
-  int w_stride;        // 16-bit elements between consecutive chunks of `w` (>= wparts * taps * N * 16)
-  const uint16_t* w;   // packed [n_chunks][parts][taps][2][N][8]; the first `wparts` parts of a chunk are used
+  int kind;            // 0: N columns into the main group; 1: 2N columns (main | correction), dual weights;
+                       // 2: N columns into the correction group, dual weights (only their first N rows are used)
+  int w_stride;        // 16-bit elements between consecutive chunks of `w`
+  const uint16_t* w;   // plain: [n_chunks][parts][taps][2][N][8] (pointing at the part to use);
+                       // dual:  [n_chunks][taps][2][2N][8] (rows 0..N-1 = w_hi, N..2N-1 = w_lo)
 };
 
 struct TcConv {
@@ -181,22 +188,26 @@ struct TcConv {
 };
 
 // 128-position tiles per work unit: one 256-column TMEM accumulator buffer holds MT tiles of N columns.
-template <int N, Prec P>
+// (TS = TMEM columns per tile: N, or 2N in the dual layout).
+template <int N, bool Dual>
 struct TilesPerUnit {
-  static constexpr int value = (N == 96) ? 2 : kAccCols / N;
+  static constexpr int TS = Dual ? 2 * N : N;
+  static constexpr int value = (TS == 96) ? 2 : kAccCols / TS;
 };
 
-__host__ __device__ inline size_t stage_bytes(int N, int W, int MT, int wparts_max) {
-  return ((size_t)MT * 128 + 2 * (size_t)(W + 3)) * 32 + (size_t)wparts_max * 9 * (size_t)N * 32;
+__host__ __device__ inline size_t stage_bytes(int N, int W, int MT, bool dual) {
+  return ((size_t)MT * 128 + 2 * (size_t)(W + 3)) * 32 + (dual ? 2 : 1) * 9 * (size_t)N * 32;
 }
 
-template <int N, Prec P>
+template <int N, Prec P, bool Dual>
 __global__ void __launch_bounds__(kTcThreads, 1)
 conv_tc_kernel(const TcConv p) {
   extern __shared__ __align__(128) unsigned char smem[];
-  constexpr int MT = TilesPerUnit<N, P>::value;
+  static_assert(!Dual || PrecTraits<P>::split, "the dual layout belongs to the split precision");
+  constexpr int MT = TilesPerUnit<N, Dual>::value;
+  constexpr int TS = TilesPerUnit<N, Dual>::TS;
   constexpr bool kSplit = PrecTraits<P>::split;
-  constexpr int kWpartsMax = 1;          // every source brings one weight part per stage
+  constexpr int kWpartsMax = Dual ? 2 : 1;   // weight rows per tap and K-half staged per chunk, in units of N
   const int Wp = p.W + 2, Hp = p.H + 2;
   const int HpWp = Hp * Wp;
   const int halo = Wp + 1;
@@ -246,7 +257,7 @@ conv_tc_kernel(const TcConv p) {
       const int lo = (u - b * p.units_per_image) * MT * 128;   // first staged position (= q0 - halo)
       for (int s = 0; s < p.n_src && ok; ++s) {
         const TcSource& src = p.src[s];
-        const uint32_t w_bytes = (uint32_t)(src.wparts * src.taps) * N * 32u;
+        const uint32_t w_bytes = (uint32_t)(kWpartsMax * src.taps) * N * 32u;
         for (int kc = 0; kc < src.n_chunks; ++kc, ++it) {
           const int st = it % S;
           const uint32_t ph = (uint32_t)(it / S) & 1u;
@@ -267,14 +278,16 @@ conv_tc_kernel(const TcConv p) {
     if (p.prof && lane == 0) p.prof[blockIdx.x * 8 + 0] = w_empty;
   } else if (warp == 5) {
     // ===================================================================== MMA issuer (warp-uniform)
-    constexpr uint32_t idesc = instr_desc(N, PrecTraits<P>::fmt);
+    constexpr uint32_t idesc_n = instr_desc(N, PrecTraits<P>::fmt);
+    constexpr uint32_t idesc_2n = instr_desc(2 * N, PrecTraits<P>::fmt);
+    constexpr int BN = Dual ? 2 * N : N;                 // weight rows per tap and K-half in a stage
     int tap_off[9];
 #pragma unroll
     for (int t = 0; t < 9; ++t) tap_off[t] = (t / 3 - 1) * Wp + (t % 3 - 1);
     // descriptor high words are loop-invariant; the low word is (LBO >> 4) << 16 | (address >> 4)
     const uint32_t a_hi = (128u >> 4) | (1u << 14), b_hi = a_hi;
     const uint32_t a_lo_base = ((uint32_t)L & 0x3FFFu) << 16;            // LBO = L * 16 bytes
-    const uint32_t b_lo_base = ((uint32_t)N & 0x3FFFu) << 16;            // LBO = N * 16 bytes
+    const uint32_t b_lo_base = ((uint32_t)BN & 0x3FFFu) << 16;           // LBO = BN * 16 bytes
     int it = 0, k = 0;
     bool ok = true;
     long long w_acce = 0, w_full = 0;
@@ -288,6 +301,9 @@ conv_tc_kernel(const TcConv p) {
       uint32_t accumulate = 0;
       for (int s = 0; s < p.n_src && ok; ++s) {
         const TcSource& src = p.src[s];
+        // per-source MMA shape: the dual product writes 2N columns, a correction-only source the upper N
+        const uint32_t idesc = (Dual && src.kind == 1) ? idesc_2n : idesc_n;
+        const uint32_t col0 = (Dual && src.kind == 2) ? (uint32_t)N : 0u;
         for (int kc = 0; kc < src.n_chunks; ++kc, ++it) {
           const int st = it % S;
           const uint32_t ph = (uint32_t)(it / S) & 1u;
@@ -297,36 +313,28 @@ conv_tc_kernel(const TcConv p) {
           const uint32_t a0 = smem_u32(stage0 + (size_t)st * stage_sz);
           const uint32_t a_lo0 = a_lo_base | ((a0 >> 4) + (uint32_t)halo);          // centre tap, tile 0
           const uint32_t b_lo0 = b_lo_base | ((a0 + a_bytes) >> 4);
+          const uint32_t d0 = acc + col0;
           // Straight-line issue: every descriptor is (loop-invariant high word, base + compile-time step), so the
           // MMAs go out back to back from uniform registers (a dependent uniform-ALU chain per MMA costs ~90
           // cycles, twice the 32 + N/4 cycles the shared-memory operand fetch allows; tools/umma_bench.cu).
           if (elect_one()) {
             if (src.taps == 9) {
-#pragma unroll 1
-              for (int part = 0; part < src.wparts; ++part) {
-                const uint32_t b_lo_part = b_lo0 + (uint32_t)(part * 9 * N * 2);
 #pragma unroll
-                for (int tap = 0; tap < 9; ++tap) {
-                  const uint64_t db = ((uint64_t)b_hi << 32) | (uint64_t)(b_lo_part + (uint32_t)(tap * N * 2));
-                  const uint32_t a_lo_tap = a_lo0 + (uint32_t)tap_off[tap];
-#pragma unroll
-                  for (int mt = 0; mt < MT; ++mt) {
-                    const uint64_t da = ((uint64_t)a_hi << 32) | (uint64_t)(a_lo_tap + (uint32_t)(mt * 128));
-                    tc_mma(acc + (uint32_t)(mt * N), da, db, idesc, tap == 0 ? accumulate : 1u);
-                  }
-                }
-                accumulate = 1;
-              }
-            } else {
-#pragma unroll 1
-              for (int part = 0; part < src.wparts; ++part) {
-                const uint64_t db = ((uint64_t)b_hi << 32) | (uint64_t)(b_lo0 + (uint32_t)(part * N * 2));
+              for (int tap = 0; tap < 9; ++tap) {
+                const uint64_t db = ((uint64_t)b_hi << 32) | (uint64_t)(b_lo0 + (uint32_t)(tap * BN * 2));
+                const uint32_t a_lo_tap = a_lo0 + (uint32_t)tap_off[tap];
 #pragma unroll
                 for (int mt = 0; mt < MT; ++mt) {
-                  const uint64_t da = ((uint64_t)a_hi << 32) | (uint64_t)(a_lo0 + (uint32_t)(mt * 128));
-                  tc_mma(acc + (uint32_t)(mt * N), da, db, idesc, accumulate);
+                  const uint64_t da = ((uint64_t)a_hi << 32) | (uint64_t)(a_lo_tap + (uint32_t)(mt * 128));
+                  tc_mma(d0 + (uint32_t)(mt * TS), da, db, idesc, tap == 0 ? accumulate : 1u);
                 }
-                accumulate = 1;
+              }
+            } else {
+              const uint64_t db = ((uint64_t)b_hi << 32) | (uint64_t)b_lo0;
+#pragma unroll
+              for (int mt = 0; mt < MT; ++mt) {
+                const uint64_t da = ((uint64_t)a_hi << 32) | (uint64_t)(a_lo0 + (uint32_t)(mt * 128));
+                tc_mma(d0 + (uint32_t)(mt * TS), da, db, idesc, accumulate);
               }
             }
           }
@@ -371,7 +379,13 @@ conv_tc_kernel(const TcConv p) {
 #pragma unroll
         for (int n0 = 0; n0 < N; n0 += 32) {
           uint32_t v[32];
-          tc_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(buf * kAccCols + mt * N + n0), v);
+          tc_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(buf * kAccCols + mt * TS + n0), v);
+          if constexpr (Dual) {
+            uint32_t c[32];
+            tc_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(buf * kAccCols + mt * TS + N + n0), c);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(c[i]));
+          }
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
             uint32_t hw[4], lw[4];

@@ -30,6 +30,7 @@
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <math.h>
+#include <stdlib.h>
 
 #include <vector>
 
@@ -43,7 +44,7 @@ namespace {
 using namespace ss::tc;
 
 constexpr int kGuardBytes = 1 << 17;      // slack before/after every activation allocation (halo over-reads)
-constexpr size_t kSmemBudget = 200 * 1024; // dynamic shared memory of the persistent conv kernel
+constexpr size_t kSmemBudget = 224 * 1024; // dynamic shared memory of the persistent conv kernel (one CTA per SM)
 
 // ------------------------------------------------------------------------------------ operand helpers
 // 8 channels of one padded pixel as floats: hi (+ lo for the split format).
@@ -278,6 +279,7 @@ struct Tensor {
 
 struct PackedConv {
   uint16_t* w = nullptr;   // plain: [n_chunks][parts][taps][2][n][8];  dual: [n_chunks][taps][2][2n][8] (hi rows, lo rows)
+  uint16_t* w_hi = nullptr;   // dual only: the hi parts alone, [n_chunks][taps][2][n][8] (for x_lo . w_hi)
   int n_chunks = 0, taps = 0, n = 0, parts = 1;
   bool dual = false;
 };
@@ -377,6 +379,18 @@ int pack_conv(TcState* st, const float* w, int taps, int cin, int cout, float sc
   SS_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&out->w), h.size() * sizeof(uint16_t)));
   SS_CUDA_CHECK(cudaMemcpy(out->w, h.data(), h.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
   st->bytes += h.size() * sizeof(uint16_t);
+  if (dual) {
+    std::vector<uint16_t> hh_only((size_t)n_chunks * taps * 2 * cout * 8);
+    for (int kc = 0; kc < n_chunks; ++kc)
+      for (int t = 0; t < taps; ++t)
+        for (int hh = 0; hh < 2; ++hh)
+          for (int n = 0; n < cout; ++n)
+            for (int j = 0; j < 8; ++j)
+              hh_only[((((size_t)kc * taps + t) * 2 + hh) * cout + n) * 8 + j] = h[at(kc, 0, t, hh, n, j)];
+    SS_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&out->w_hi), hh_only.size() * sizeof(uint16_t)));
+    SS_CUDA_CHECK(cudaMemcpy(out->w_hi, hh_only.data(), hh_only.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+    st->bytes += hh_only.size() * sizeof(uint16_t);
+  }
   out->n_chunks = n_chunks;
   out->taps = taps;
   out->n = cout;
@@ -387,10 +401,12 @@ int pack_conv(TcState* st, const float* w, int taps, int cin, int cout, float sc
 
 constexpr size_t kSmemTail = (2 * kMaxStages + 4) * 8 + 128 * 4 + 16;   // barriers + bias + TMEM slot
 
-template <int N, Prec P, bool Dual>
-int launch_conv_np(TcConv p, int B, cudaStream_t st) {
+constexpr int kMinUnitsForPairs = 4 * kNumSMs;   // use two-group units only while >= 4 waves of them remain
+
+template <int N, Prec P, bool Dual, int G>
+int launch_conv_npg(TcConv p, int B, cudaStream_t st) {
   constexpr int MT = TilesPerUnit<N, Dual>::value;
-  const size_t sb = stage_bytes(N, p.W, MT, Dual);
+  const size_t sb = stage_bytes(N, p.W, G * MT, Dual);
   int stages = (int)((kSmemBudget - kSmemTail) / sb);
   if (stages > kMaxStages) stages = kMaxStages;
   SS_REQUIRE(stages >= 2, SS_E_ARG, "conv stage of %zu bytes does not fit twice in shared memory", sb);
@@ -398,18 +414,32 @@ int launch_conv_np(TcConv p, int B, cudaStream_t st) {
   const size_t smem = (size_t)stages * sb + kSmemTail;
   static bool configured = false;
   if (!configured) {
-    SS_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<N, P, Dual>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    SS_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<N, P, Dual, G>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)kSmemBudget));
     configured = true;
   }
   const int positions = p.H * (p.W + 2) - 2;          // (1,1) .. (H,W) in flattened padded coordinates
-  p.units_per_image = (positions + MT * 128 - 1) / (MT * 128);
+  p.units_per_image = (positions + G * MT * 128 - 1) / (G * MT * 128);
   p.total_units = p.units_per_image * B;
   const int grid = p.total_units < kNumSMs ? p.total_units : kNumSMs;
-  conv_tc_kernel<N, P, Dual><<<grid, kTcThreads, smem, st>>>(p);
+  conv_tc_kernel<N, P, Dual, G><<<grid, kTcThreads, smem, st>>>(p);
   SS_CUDA_CHECK(cudaGetLastError());
   count_launch();
   return SS_OK;
+}
+
+template <int N, Prec P, bool Dual>
+int launch_conv_np(const TcConv& p, int B, cudaStream_t st) {
+  constexpr int MT = TilesPerUnit<N, Dual>::value;
+  const int positions = p.H * (p.W + 2) - 2;
+  const int64_t pair_units = (int64_t)((positions + 2 * MT * 128 - 1) / (2 * MT * 128)) * B;
+  const bool fits = stage_bytes(N, p.W, 2 * MT, Dual) * 2 + kSmemTail <= kSmemBudget;
+  // Measured (B200, batch 64): two-group units pay off where the stage traffic is heaviest — the dual layout of the
+  // split precision (-1.4 % step time) — and cost 6 % in the single-pass modes, whose epilogue overlap they reduce.
+  static const int policy = [] { const char* e = getenv("SS_TC_PAIRS"); return e ? atoi(e) : -1; }();   // tuning override
+  const bool want = policy < 0 ? Dual : policy != 0;
+  if (want && pair_units >= kMinUnitsForPairs && fits) return launch_conv_npg<N, P, Dual, 2>(p, B, st);
+  return launch_conv_npg<N, P, Dual, 1>(p, B, st);
 }
 
 template <Prec P>
@@ -455,7 +485,7 @@ void add_sources(TcConv* p, const TcState* s, const Tensor& x, int plane0, const
   if (w.dual) {
     if (terms != Terms::Corrections) {
       p->src[p->n_src++] = TcSource{x.data, x.planes, plane0, w.n_chunks, w.taps, 1, chunk_elems, w.w};
-      p->src[p->n_src++] = TcSource{x.lo, x.planes, plane0, w.n_chunks, w.taps, 2, chunk_elems, w.w};
+      p->src[p->n_src++] = TcSource{x.lo, x.planes, plane0, w.n_chunks, w.taps, 2, part_elems, w.w_hi};
     }
     return;
   }
@@ -655,9 +685,10 @@ void tc_destroy(ss_ctx* ctx) {
     for (int i = 0; i < RB_COUNT; ++i) {
       if (s->t[i].alloc) cudaFree(s->t[i].alloc);
       if (s->t[i].alloc_lo) cudaFree(s->t[i].alloc_lo);
-      if (s->rb[i].c1.w) cudaFree(s->rb[i].c1.w);
-      if (s->rb[i].c2.w) cudaFree(s->rb[i].c2.w);
-      if (s->rb[i].res.w) cudaFree(s->rb[i].res.w);
+      for (PackedConv* pc : {&s->rb[i].c1, &s->rb[i].c2, &s->rb[i].res}) {
+        if (pc->w) cudaFree(pc->w);
+        if (pc->w_hi) cudaFree(pc->w_hi);
+      }
       if (s->rb[i].bias2) cudaFree(s->rb[i].bias2);
     }
     if (s->err) cudaFree(s->err);

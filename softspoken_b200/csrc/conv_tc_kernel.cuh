@@ -3,9 +3,17 @@
 // Persistent, warp-specialised, one CTA per SM:
 //   warp 4     producer  — cp.async.bulk (1-D TMA) of activation runs + packed weights into an smem ring
 //   warp 5     MMA       — one elected thread issues tcgen05.mma into one of two 256-column TMEM buffers
-//   warps 0-3  epilogue  — tcgen05.ld -> bias / ReLU / border mask -> 16-bit pack -> 16-byte global stores
+//   warps 0-3, 6-9  epilogue — tcgen05.ld -> bias / ReLU / border mask -> 16-bit pack -> 16-byte global stores
+//              (a warp reads the TMEM lane quadrant warp % 4; the two warps of a quadrant take alternate tiles)
 // The three roles are decoupled by mbarriers (full/empty per smem stage, acc_full/acc_empty per TMEM
 // buffer), so the loads of unit k+1, the MMAs of unit k and the epilogue of unit k-1 overlap.
+//
+// A work unit is G groups of MT 128-position tiles.  G = 1: one group per unit, the two TMEM buffers alternate
+// between consecutive units.  G = 2 (large images): a unit spans both buffers — one staged run of 2*MT*128
+// positions and one copy of the chunk's weights feed both groups, which cuts the L2 -> shared-memory traffic
+// per output position (halo and weights amortised over twice the positions; the N=32 layers are otherwise
+// bound by exactly that traffic).  The groups still complete one after the other (group 0's MMAs of the last
+// chunk are issued, and committed, before group 1's), so the epilogue of a group overlaps the MMAs of the next.
 //
 // Operand precision is a template parameter:
 //   Bf16   — bf16 operands, one pass (throughput mode; ~4e-2 relative logit error over the 25-layer stack);
@@ -32,7 +40,7 @@ namespace tc {
 
 constexpr int kMaxStages = 8;
 constexpr int kMaxSources = 6;
-constexpr int kTcThreads = 192;
+constexpr int kTcThreads = 320;          // warps 0-3 and 6-9: epilogue; warp 4: producer; warp 5: MMA issuer
 constexpr int kAccCols = 256;             // TMEM columns per accumulator buffer (two buffers = all 512)
 constexpr uint32_t kSpinLimit = 1u << 22;
 
@@ -164,8 +172,8 @@ struct TcSource {
   int plane0;          // first plane this convolution reads
   int n_chunks;        // C_in / 16
   int taps;            // 9 (3x3) or 1 (1x1, centre)
-  int kind;            // 0: N columns into the main group; 1: 2N columns (main | correction), dual weights;
-                       // 2: N columns into the correction group, dual weights (only their first N rows are used)
+  int kind;            // 0: N columns into the main columns; 1: 2N columns (main | correction), dual weights;
+                       // 2: N columns into the correction columns
   int w_stride;        // 16-bit elements between consecutive chunks of `w`
   const uint16_t* w;   // plain: [n_chunks][parts][taps][2][N][8] (pointing at the part to use);
                        // dual:  [n_chunks][taps][2][2N][8] (rows 0..N-1 = w_hi, N..2N-1 = w_lo)
@@ -195,11 +203,40 @@ struct TilesPerUnit {
   static constexpr int value = (TS == 96) ? 2 : kAccCols / TS;
 };
 
-__host__ __device__ inline size_t stage_bytes(int N, int W, int MT, bool dual) {
-  return ((size_t)MT * 128 + 2 * (size_t)(W + 3)) * 32 + (dual ? 2 : 1) * 9 * (size_t)N * 32;
+__host__ __device__ inline size_t stage_bytes(int N, int W, int tiles, bool dual) {
+  return ((size_t)tiles * 128 + 2 * (size_t)(W + 3)) * 32 + (dual ? 2 : 1) * 9 * (size_t)N * 32;
 }
 
-template <int N, Prec P, bool Dual>
+// The MMAs of one K-chunk for one group of MT tiles: straight-line, every descriptor is (loop-invariant high
+// word, base + compile-time step), so the MMAs go out back to back from uniform registers (a dependent
+// uniform-ALU chain per MMA costs ~90 cycles, twice the 32 + N/4 cycles the shared-memory operand fetch allows;
+// tools/umma_bench.cu).  BN = weight rows per tap and K-half in the stage (N, or 2N for dual weights).
+template <int MT, int TS, int BN>
+__device__ __forceinline__ void issue_group(uint32_t d0, uint32_t a_lo0, uint32_t b_lo0, uint32_t idesc, int taps,
+                                            const int (&tap_off)[9], uint32_t accumulate) {
+  const uint32_t a_hi = (128u >> 4) | (1u << 14), b_hi = a_hi;
+  if (taps == 9) {
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+      const uint64_t db = ((uint64_t)b_hi << 32) | (uint64_t)(b_lo0 + (uint32_t)(tap * BN * 2));
+      const uint32_t a_lo_tap = a_lo0 + (uint32_t)tap_off[tap];
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt) {
+        const uint64_t da = ((uint64_t)a_hi << 32) | (uint64_t)(a_lo_tap + (uint32_t)(mt * 128));
+        tc_mma(d0 + (uint32_t)(mt * TS), da, db, idesc, tap == 0 ? accumulate : 1u);
+      }
+    }
+  } else {
+    const uint64_t db = ((uint64_t)b_hi << 32) | (uint64_t)b_lo0;
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) {
+      const uint64_t da = ((uint64_t)a_hi << 32) | (uint64_t)(a_lo0 + (uint32_t)(mt * 128));
+      tc_mma(d0 + (uint32_t)(mt * TS), da, db, idesc, accumulate);
+    }
+  }
+}
+
+template <int N, Prec P, bool Dual, int G>
 __global__ void __launch_bounds__(kTcThreads, 1)
 conv_tc_kernel(const TcConv p) {
   extern __shared__ __align__(128) unsigned char smem[];
@@ -211,7 +248,7 @@ conv_tc_kernel(const TcConv p) {
   const int Wp = p.W + 2, Hp = p.H + 2;
   const int HpWp = Hp * Wp;
   const int halo = Wp + 1;
-  const int L = MT * 128 + 2 * halo;                    // positions staged per plane
+  const int L = G * MT * 128 + 2 * halo;                // positions staged per plane
   const uint32_t a_bytes = (uint32_t)L * 32u;           // two planes
   const uint32_t stage_sz = a_bytes + (uint32_t)kWpartsMax * 9u * N * 32u;
   const int S = p.stages;
@@ -232,7 +269,7 @@ conv_tc_kernel(const TcConv p) {
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(accf0 + 8 * i, 1);
-      mbar_init(acce0 + 8 * i, 4);       // one arrival per epilogue warp
+      mbar_init(acce0 + 8 * i, 8);       // one arrival per epilogue warp
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -254,10 +291,10 @@ conv_tc_kernel(const TcConv p) {
     long long w_empty = 0;
     for (int u = blockIdx.x; u < p.total_units && ok; u += gridDim.x) {
       const int b = u / p.units_per_image;
-      const int lo = (u - b * p.units_per_image) * MT * 128;   // first staged position (= q0 - halo)
+      const int lo = (u - b * p.units_per_image) * G * MT * 128;   // first staged position (= q0 - halo)
       for (int s = 0; s < p.n_src && ok; ++s) {
         const TcSource& src = p.src[s];
-        const uint32_t w_bytes = (uint32_t)(kWpartsMax * src.taps) * N * 32u;
+        const uint32_t w_bytes = (uint32_t)((Dual && src.kind == 1 ? 2 : 1) * src.taps) * N * 32u;
         for (int kc = 0; kc < src.n_chunks; ++kc, ++it) {
           const int st = it % S;
           const uint32_t ph = (uint32_t)(it / S) & 1u;
@@ -280,31 +317,31 @@ conv_tc_kernel(const TcConv p) {
     // ===================================================================== MMA issuer (warp-uniform)
     constexpr uint32_t idesc_n = instr_desc(N, PrecTraits<P>::fmt);
     constexpr uint32_t idesc_2n = instr_desc(2 * N, PrecTraits<P>::fmt);
-    constexpr int BN = Dual ? 2 * N : N;                 // weight rows per tap and K-half in a stage
     int tap_off[9];
 #pragma unroll
     for (int t = 0; t < 9; ++t) tap_off[t] = (t / 3 - 1) * Wp + (t % 3 - 1);
-    // descriptor high words are loop-invariant; the low word is (LBO >> 4) << 16 | (address >> 4)
-    const uint32_t a_hi = (128u >> 4) | (1u << 14), b_hi = a_hi;
+    // descriptor low word = (LBO >> 4) << 16 | (address >> 4)
     const uint32_t a_lo_base = ((uint32_t)L & 0x3FFFu) << 16;            // LBO = L * 16 bytes
-    const uint32_t b_lo_base = ((uint32_t)BN & 0x3FFFu) << 16;           // LBO = BN * 16 bytes
     int it = 0, k = 0;
     bool ok = true;
     long long w_acce = 0, w_full = 0;
     const long long t_begin = clock64();
+    // total K-chunks of a unit, to recognise the last one
+    int chunks_per_unit = 0;
+    for (int s = 0; s < p.n_src; ++s) chunks_per_unit += p.src[s].n_chunks;
     for (int u = blockIdx.x; u < p.total_units && ok; u += gridDim.x, ++k) {
-      const int buf = k & 1;
-      ok = mbar_wait_t(acce0 + 8 * buf, (((uint32_t)k >> 1) & 1u) ^ 1u, p.err, 4, w_acce);   // buffer drained
-      if (!ok) break;
-      tc_fence_after();
-      const uint32_t acc = tmem_base + (uint32_t)(buf * kAccCols);
+      // G = 1: this unit owns buffer k & 1; G = 2: group g owns buffer g in every unit
+      const uint32_t e_parity = (G == 1) ? ((((uint32_t)k >> 1) & 1u) ^ 1u) : (((uint32_t)k & 1u) ^ 1u);
       uint32_t accumulate = 0;
+      int c_in_unit = 0;
       for (int s = 0; s < p.n_src && ok; ++s) {
         const TcSource& src = p.src[s];
         // per-source MMA shape: the dual product writes 2N columns, a correction-only source the upper N
-        const uint32_t idesc = (Dual && src.kind == 1) ? idesc_2n : idesc_n;
+        const bool dual_src = Dual && src.kind == 1;
+        const uint32_t idesc = dual_src ? idesc_2n : idesc_n;
         const uint32_t col0 = (Dual && src.kind == 2) ? (uint32_t)N : 0u;
-        for (int kc = 0; kc < src.n_chunks; ++kc, ++it) {
+        const uint32_t b_lo_base = ((uint32_t)(dual_src ? 2 * N : N) & 0x3FFFu) << 16;   // LBO = rows * 16 bytes
+        for (int kc = 0; kc < src.n_chunks && ok; ++kc, ++it, ++c_in_unit) {
           const int st = it % S;
           const uint32_t ph = (uint32_t)(it / S) & 1u;
           ok = mbar_wait_t(full0 + 8 * st, ph, p.err, 2, w_full);
@@ -313,39 +350,30 @@ conv_tc_kernel(const TcConv p) {
           const uint32_t a0 = smem_u32(stage0 + (size_t)st * stage_sz);
           const uint32_t a_lo0 = a_lo_base | ((a0 >> 4) + (uint32_t)halo);          // centre tap, tile 0
           const uint32_t b_lo0 = b_lo_base | ((a0 + a_bytes) >> 4);
-          const uint32_t d0 = acc + col0;
-          // Straight-line issue: every descriptor is (loop-invariant high word, base + compile-time step), so the
-          // MMAs go out back to back from uniform registers (a dependent uniform-ALU chain per MMA costs ~90
-          // cycles, twice the 32 + N/4 cycles the shared-memory operand fetch allows; tools/umma_bench.cu).
-          if (elect_one()) {
-            if (src.taps == 9) {
+          const bool last = (c_in_unit == chunks_per_unit - 1);
 #pragma unroll
-              for (int tap = 0; tap < 9; ++tap) {
-                const uint64_t db = ((uint64_t)b_hi << 32) | (uint64_t)(b_lo0 + (uint32_t)(tap * BN * 2));
-                const uint32_t a_lo_tap = a_lo0 + (uint32_t)tap_off[tap];
-#pragma unroll
-                for (int mt = 0; mt < MT; ++mt) {
-                  const uint64_t da = ((uint64_t)a_hi << 32) | (uint64_t)(a_lo_tap + (uint32_t)(mt * 128));
-                  tc_mma(d0 + (uint32_t)(mt * TS), da, db, idesc, tap == 0 ? accumulate : 1u);
-                }
-              }
-            } else {
-              const uint64_t db = ((uint64_t)b_hi << 32) | (uint64_t)b_lo0;
-#pragma unroll
-              for (int mt = 0; mt < MT; ++mt) {
-                const uint64_t da = ((uint64_t)a_hi << 32) | (uint64_t)(a_lo0 + (uint32_t)(mt * 128));
-                tc_mma(d0 + (uint32_t)(mt * TS), da, db, idesc, accumulate);
-              }
+          for (int g = 0; g < G; ++g) {
+            const int buf = (G == 1) ? (k & 1) : g;
+            if (c_in_unit == 0) {                          // the epilogue must have drained this buffer
+              ok = mbar_wait_t(acce0 + 8 * buf, e_parity, p.err, 4, w_acce);
+              if (!ok) break;
+              tc_fence_after();
             }
+            const uint32_t d0 = tmem_base + (uint32_t)(buf * kAccCols) + col0;
+            const uint32_t a_g = a_lo0 + (uint32_t)(g * MT * 128);
+            if (elect_one()) {
+              if (dual_src) issue_group<MT, TS, 2 * N>(d0, a_g, b_lo0, idesc, src.taps, tap_off, accumulate);
+              else issue_group<MT, TS, N>(d0, a_g, b_lo0, idesc, src.taps, tap_off, accumulate);
+              if (last) tc_commit(accf0 + 8 * buf);        // this group's accumulators are complete
+            }
+            __syncwarp();
           }
-          __syncwarp();
+          if (!ok) break;
           accumulate = 1;
           if (elect_one()) tc_commit(empty0 + 8 * st);     // frees the stage once the MMAs that read it retire
           __syncwarp();
         }
       }
-      if (elect_one()) tc_commit(accf0 + 8 * buf);         // this unit's accumulators are complete
-      __syncwarp();
     }
     if (p.prof && lane == 0) {
       p.prof[blockIdx.x * 8 + 1] = w_acce;
@@ -354,7 +382,9 @@ conv_tc_kernel(const TcConv p) {
       p.prof[blockIdx.x * 8 + 7] = k;
     }
   } else {
-    // ===================================================================== epilogue (warps 0-3)
+    // ===================================================================== epilogue (warps 0-3 and 6-9)
+    const int quad = warp & 3;                 // TMEM lane quadrant this warp may read
+    const int tile_par = warp >= 6 ? 1 : 0;    // the two warps of a quadrant take alternate tiles
     const int Wp2 = 2 * p.W + 2;
     const float inv_scale = p.inv_scale;
     const int64_t out_plane_stride = p.upsample ? (int64_t)(2 * p.H + 2) * Wp2 * 8 : (int64_t)HpWp * 8;
@@ -363,15 +393,17 @@ conv_tc_kernel(const TcConv p) {
     long long w_accf = 0;
     const long long t_begin = clock64();
     for (int u = blockIdx.x; u < p.total_units && ok; u += gridDim.x, ++k) {
-      const int buf = k & 1;
       const int b = u / p.units_per_image;
-      const int q0 = halo + (u - b * p.units_per_image) * MT * 128;
-      ok = mbar_wait_t(accf0 + 8 * buf, ((uint32_t)k >> 1) & 1u, p.err, 3, w_accf);
+      const int64_t img_off = ((int64_t)b * p.out_planes_total + p.out_plane0) * out_plane_stride;
+     for (int g = 0; g < G && ok; ++g) {
+      const int buf = (G == 1) ? (k & 1) : g;
+      const uint32_t f_parity = (G == 1) ? (((uint32_t)k >> 1) & 1u) : ((uint32_t)k & 1u);
+      const int q0 = halo + ((u - b * p.units_per_image) * G + g) * MT * 128;
+      ok = mbar_wait_t(accf0 + 8 * buf, f_parity, p.err, 3, w_accf);
       if (!ok) break;
       tc_fence_after();
-      const int64_t img_off = ((int64_t)b * p.out_planes_total + p.out_plane0) * out_plane_stride;
-      for (int mt = 0; mt < MT; ++mt) {
-        const int pos = q0 + mt * 128 + warp * 32 + lane;
+      for (int mt = tile_par; mt < MT; mt += 2) {
+        const int pos = q0 + mt * 128 + quad * 32 + lane;
         const int y = pos / Wp, x = pos - y * Wp;
         const bool interior = (y >= 1) && (y <= p.H) && (x >= 1) && (x <= p.W);
         const bool in_tensor = pos < HpWp;
@@ -379,10 +411,10 @@ conv_tc_kernel(const TcConv p) {
 #pragma unroll
         for (int n0 = 0; n0 < N; n0 += 32) {
           uint32_t v[32];
-          tc_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(buf * kAccCols + mt * TS + n0), v);
+          tc_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * kAccCols + mt * TS + n0), v);
           if constexpr (Dual) {
             uint32_t c[32];
-            tc_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(buf * kAccCols + mt * TS + N + n0), c);
+            tc_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * kAccCols + mt * TS + N + n0), c);
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(c[i]));
           }
@@ -429,6 +461,7 @@ conv_tc_kernel(const TcConv p) {
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(acce0 + 8 * buf);
+     }
     }
     if (p.prof && threadIdx.x == 0) {
       p.prof[blockIdx.x * 8 + 4] = w_accf;

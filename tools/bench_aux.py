@@ -1,0 +1,164 @@
+"""BASELINE.json configs 4 and 5 on one B200: one JSON line each (same vocabulary as bench.py).
+
+    python tools/bench_aux.py long    [--hours 24]     # config 4: one long recording streamed in chunks
+    python tools/bench_aux.py silence [--files 1000]   # config 5: 10k flagged intervals masked across the corpus
+
+config 4 — a synthetic 24 h mono 22,050 Hz recording (a seeded 10-minute clip tiled with a different gain per
+tile, so neighbouring hours differ) is handed to `ss_detect_host` as ONE host buffer; the library streams it in
+chunks of 1,024 windows with overlapping analysis windows.  Checked here: the logits of the first 30 minutes are
+bitwise those of a separate run on that prefix alone (windows are independent of chunking), and the regions of
+the prefix run are a prefix of the long run's regions.
+config 5 — 10,000 `erase = 1` intervals (SURVEY §8d recipe) over a 1,000-clip corpus resident in HBM as one
+packed float32 buffer, one `ss_silence` launch; a sample of files is compared bit-for-bit with the oracle's
+`audio[:, s:e] = 0.0` (oracle/silence.py is used as the checker only).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+SR = 22050
+
+
+def load_engine(max_batch=64, mode="f16x3"):
+    from softspoken_b200 import checkpoint
+    from softspoken_b200.engine import Engine
+    with open(os.path.join(ROOT, "tests", "golden", "head_seed0.json")) as f:
+        head = json.load(f)
+    return Engine(checkpoint.synthetic_state_dict(0, head), 0, max_batch=max_batch, mode=mode)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f)["hbm_gbs"], "measured"
+    return 6650.0, "fallback"
+
+
+def run_long(args):
+    from softspoken_b200 import synth
+    eng = load_engine(args.max_batch, args.mode)
+    clip = synth.synth_audio(600.0, 0)
+    tiles = int(round(args.hours * 6))
+    n = tiles * clip.size
+    t0 = time.perf_counter()
+    audio = torch.empty(n, dtype=torch.float32).pin_memory()
+    view = audio.numpy()
+    rng = np.random.default_rng(7)
+    for i in range(tiles):
+        view[i * clip.size:(i + 1) * clip.size] = clip * np.float32(rng.uniform(0.5, 1.0))
+    gen_s = time.perf_counter() - t0
+    W = (n + 66150 + 13229) // 13230
+    eng.reserve(n, 1 << 20)
+    # warm-up on the first 30 minutes, which is also the prefix reference
+    n_pre = 3 * clip.size
+    reg_pre, lg_pre = eng.detect_host(audio[:n_pre], want_logits=True, cap=1 << 20)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    reg, lg = eng.detect_host(audio, want_logits=True, cap=1 << 20)
+    dt = time.perf_counter() - t0
+    # windows that lie entirely inside the prefix (and its leading pad) see identical samples in both runs
+    w_same = (n_pre + 66150 - 65536) // 13230
+    same_logits = bool(np.array_equal(lg[:w_same], lg_pre[:w_same]))
+    safe_bin = int((w_same - 5) * 51.2)
+    a = reg[reg[:, 1] < safe_bin]
+    b = reg_pre[reg_pre[:, 1] < safe_bin]
+    same_regions = bool(np.array_equal(a, b))
+    hours = n / SR / 3600.0
+    line = {
+        "metric": "audio_hours_per_sec", "value": hours / dt, "unit": "audio-hours/s", "n_gpus": 1,
+        "higher_is_better": True, "dtype": args.mode, "data": "synthetic",
+        "config": {"workload": f"config4: one {hours:.1f} h mono 22.05 kHz recording, host buffer streamed in chunks of "
+                               "1024 windows (52,920-sample overlap), K5/K6 once over the whole timeline",
+                   "windows": int(lg.shape[0]), "timeline_bins": int(lg.shape[0] * 51.2) + 256, "regions": int(len(reg)),
+                   "planned_windows": int(W), "host_generation_s": round(gen_s, 1)},
+        "x_realtime": hours * 3600.0 / dt, "seconds": dt,
+        "e2e": {"value": hours / dt, "unit": "audio-hours/s", "h2d_bytes_per_step": int(n * 4),
+                "d2h_bytes_per_step": int(lg.nbytes + reg.nbytes)},
+        "checks": {"prefix_logits_bitwise_equal": same_logits, "prefix_regions_equal": same_regions,
+                   "prefix_windows_compared": int(w_same)},
+    }
+    print(json.dumps(line), flush=True)
+    assert same_logits and same_regions
+    eng.close()
+
+
+def run_silence(args):
+    from oracle import silence as osil          # checker only
+    from softspoken_b200 import synth
+    from softspoken_b200.silencer import interval_table
+    eng = load_engine(4, "bf16")
+    n = 600 * SR
+    files, start, end = synth.synth_review_rows(args.intervals, args.files, 600.0, 0)
+    dev = torch.device("cuda", 0)
+    corpus = torch.empty(args.files * n, dtype=torch.float32, device=dev)
+    # cheap deterministic non-zero content: every sample is a function of its flat index
+    idx = torch.arange(n, device=dev, dtype=torch.float32)
+    for f in range(args.files):
+        corpus[f * n:(f + 1) * n] = torch.sin(idx * (0.001 + 1e-6 * f)) * 0.5 + 0.25
+    tabs = []
+    for f in range(args.files):
+        sel = np.nonzero(files == f)[0]
+        if len(sel):
+            tabs.append(interval_table(list(zip(start[sel], end[sel])), SR, 1, n, base=f * n))
+    table = np.concatenate(tabs).astype(np.int64)
+    masked_elems = int(np.sum(table[:, 1] - table[:, 0]))           # overlaps counted twice, as the kernel writes them
+    iv = torch.from_numpy(table).to(dev)
+    before = {f: corpus[f * n:(f + 1) * n].cpu().numpy() for f in range(0, args.files, max(1, args.files // 16))}
+    stream = torch.cuda.current_stream()
+    eng.silence(corpus[:n].clone(), iv[:1] * 0)                       # warm-up launch on a scratch copy
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    eng.silence(corpus, iv)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    dt = e0.elapsed_time(e1) / 1e3
+    ok = True
+    for f, orig in before.items():
+        sel = np.nonzero(files == f)[0]
+        want = osil.silence_buffer(orig.reshape(1, -1).copy(), SR, list(zip(start[sel], end[sel])))
+        got = corpus[f * n:(f + 1) * n].cpu().numpy()
+        ok = ok and np.array_equal(got, want.reshape(-1))
+    peak, src = peaks()
+    gbs = masked_elems * 4 / dt / 1e9
+    line = {
+        "metric": "silence_GBps", "value": gbs, "unit": "GB/s", "n_gpus": 1, "higher_is_better": True, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": f"config5: {len(table)} erase=1 intervals over {args.files} x 10-min clips resident in HBM "
+                               f"({args.files * n * 4 / 1e9:.1f} GB packed float32), one ss_silence launch",
+                   "masked_bytes": masked_elems * 4},
+        "ms": dt * 1e3,
+        "roofline": {"bound": "hbm", "kernel": "silence_kernel (K7)", "achieved": gbs, "peak": peak, "unit": "GB/s",
+                     "frac": gbs / peak, "traffic": None, "peak_source": src,
+                     "note": "write-only: algorithmic bytes = sum(e - s) * 4"},
+        "checks": {"files_compared_bitwise_with_oracle": len(before), "bit_exact": bool(ok)},
+    }
+    print(json.dumps(line), flush=True)
+    assert ok
+    eng.close()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("what", choices=["long", "silence"])
+    ap.add_argument("--hours", type=float, default=24.0)
+    ap.add_argument("--files", type=int, default=1000)
+    ap.add_argument("--intervals", type=int, default=10000)
+    ap.add_argument("--max-batch", type=int, default=64)
+    ap.add_argument("--mode", default="f16x3")
+    args = ap.parse_args()
+    (run_long if args.what == "long" else run_silence)(args)
+
+
+if __name__ == "__main__":
+    main()

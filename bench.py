@@ -40,6 +40,8 @@ SR = 22050
 WINDOWS_PER_CLIP = 1005
 FLOP_PER_WINDOW_MASK = 6_359_672_832          # convs on the mask path, 2 x MAC, BN folded
 FEATURE_BYTES_PER_CLIP = 4 * (13_230_000 + 132_300) + WINDOWS_PER_CLIP * 128 * 256 * 4   # PCM once + mel once
+# DRAM bytes the classifier launches move per window (ncu, profiles/r1_launches_f16x3_metrics.csv: 11.8 GB / 133 windows)
+CLASSIFIER_DRAM_BYTES_PER_WINDOW = {"f16x3": 88_900_000}
 
 
 def peaks():
@@ -219,9 +221,8 @@ def run_b200(args):
     def step_host(s):
         total_regions = 0
         trip = []
-        for j in range(C):
-            clip = pinned[(s * C + j) % len(pinned)]
-            bins = eng.detect_host(clip, cap=cap)
+        clips = [pinned[(s * C + j) % len(pinned)] for j in range(C)]
+        for j, bins in enumerate(eng.detect_host_batch(clips, cap=cap)):   # one C-ABI call per step
             total_regions += len(bins)
             if world > 1:
                 trip.append(np.concatenate([np.full((len(bins), 1), (s * C + j) * world + rank, np.int32), bins], 1))
@@ -293,6 +294,13 @@ def run_b200(args):
     t_cls = ev_time(lambda: eng.classify(mel, mode=args.mode), 2)
     achieved_tf = FLOP_PER_WINDOW_MASK * WINDOWS_PER_CLIP / t_cls / 1e12
     achieved_gbs = FEATURE_BYTES_PER_CLIP / t_feat / 1e9
+    other_modes = {}
+    if world == 1 and not args.no_other_modes:
+        for m in ("f16", "bf16"):
+            if m != args.mode:
+                t_m = ev_time(lambda: eng.classify(mel, mode=m), 2)
+                other_modes[m] = {"ms_per_clip": 1e3 * t_m, "tflops": FLOP_PER_WINDOW_MASK * WINDOWS_PER_CLIP / t_m / 1e12,
+                                  "frac": FLOP_PER_WINDOW_MASK * WINDOWS_PER_CLIP / t_m / 1e12 / pk["tflops_sustained"]}
 
     line = None
     if rank == 0:
@@ -315,8 +323,13 @@ def run_b200(args):
             "clocks": clocks,
             "roofline": {"bound": "tensor", "kernel": "classifier (conv stack, ss_classify)", "achieved": achieved_tf,
                          "peak": pk["tflops_sustained"], "unit": "TFLOP/s", "frac": achieved_tf / pk["tflops_sustained"],
-                         "frac_of_burst_peak": achieved_tf / pk["tflops_burst"], "traffic": None,
+                         "frac_of_burst_peak": achieved_tf / pk["tflops_burst"],
+                         "traffic": CLASSIFIER_DRAM_BYTES_PER_WINDOW.get(args.mode, 0) * WINDOWS_PER_CLIP or None,
+                         "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum over the classifier launches of "
+                                           "profiles/r1_launches_f16x3_metrics.csv, per window x 1005",
                          "peak_source": pk["source"], "ms_per_clip": 1e3 * t_cls,
+                         "executed_mma_flops_factor": 3 if args.mode == "f16x3" else 1,
+                         "single_pass_modes": other_modes,
                          "algorithmic_flops_per_launch_group": FLOP_PER_WINDOW_MASK * WINDOWS_PER_CLIP},
             "roofline_features": {"bound": "hbm", "kernel": "features_kernel (K1)", "achieved": achieved_gbs,
                                   "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": achieved_gbs / pk["hbm_gbs"],
@@ -342,12 +355,13 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--mode", default=os.environ.get("SS_BENCH_MODE", "f16x3"), choices=["fp32", "bf16", "f16", "f16x3"])
-    ap.add_argument("--clips-per-step", type=int, default=1)
+    ap.add_argument("--clips-per-step", type=int, default=2)
     ap.add_argument("--pool", type=int, default=4)
-    ap.add_argument("--max-batch", type=int, default=32)
+    ap.add_argument("--max-batch", type=int, default=256)
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--ref-step-seconds", type=float, default=10.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-other-modes", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -143,6 +143,13 @@ SS_API int ss_detect_device(ss_ctx* ctx, const float* pcm_dev, int64_t n_samples
 SS_API int ss_detect_host(ss_ctx* ctx, const float* pcm_host, int64_t n_samples, int mode,
                    int32_t* regions_host, int cap, int* n_regions, float* logits_host);
 
+/* The file loop of ProcessWorker.run (worker.py:49-136) for `n_clips` host clips in one call: clip k+1 is uploaded
+ * while clip k computes, region lists come back through pinned staging, and the host synchronises once per group of
+ * 8 clips instead of once per clip.  regions_host: [n_clips][cap][2]; n_regions: [n_clips] (numbers found; at most
+ * cap pairs per clip are written).  Results are identical to n_clips calls of ss_detect_host. */
+SS_API int ss_detect_host_batch(ss_ctx* ctx, int n_clips, const float* const* pcm_host, const int64_t* n_samples,
+                                int mode, int32_t* regions_host, int cap, int* n_regions);
+
 /* SilenceWorker.run on one HOST buffer `(channels, n)` float32: zero [begin, end) of every
  * interval (element offsets into the flattened buffer) on the device and copy the result back. */
 SS_API int ss_silence_host(ss_ctx* ctx, float* pcm_host, int64_t n_elems, const ss_interval* intervals_host,

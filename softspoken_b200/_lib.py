@@ -60,6 +60,7 @@ _SIGNATURES = {
     "ss_silence": (_int, [_p, _p, _i64, _p, _int, _p]),
     "ss_detect_device": (_int, [_p, _p, _i64, _int, _p, _p, _int, _p, _p]),
     "ss_detect_host": (_int, [_p, _p, _i64, _int, _p, _int, C.POINTER(_int), _p]),
+    "ss_detect_host_batch": (_int, [_p, _int, _p, _p, _int, _p, _int, _p]),
     "ss_silence_host": (_int, [_p, _p, _i64, _p, _int]),
     "ss_debug_tc_profile": (_int, [_p, _int, _p]),
     "ss_debug_activation": (_int, [_p, _int, _int, _p, C.POINTER(_int), C.POINTER(_int), C.POINTER(_int), _p]),

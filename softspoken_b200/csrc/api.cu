@@ -28,6 +28,7 @@ constexpr uint32_t kBlobMagic = 0x53534232u;   // 'SSB2' (softspoken_b200/checkp
 constexpr uint32_t kBlobVersion = 2;
 constexpr int64_t kChunkWindows = 1024;        // windows per streamed chunk in ss_detect_*
 constexpr int kIntervalCap = 1 << 20;
+constexpr int kBatchSlots = 8;                 // clips in flight inside ss_detect_host_batch
 
 struct BlobEntry {
   uint64_t off, count;
@@ -341,6 +342,8 @@ int ss_ctx_destroy(ss_ctx* ctx) {
   if (ctx->file_cnt) cudaFree(ctx->file_cnt);
   if (ctx->file_regions) cudaFree(ctx->file_regions);
   if (ctx->file_nreg) cudaFree(ctx->file_nreg);
+  if (ctx->slot_nreg) cudaFree(ctx->slot_nreg);
+  if (ctx->slot_host) cudaFreeHost(ctx->slot_host);
   if (ctx->scan_tmp) cudaFree(ctx->scan_tmp);
   if (ctx->intervals) cudaFree(ctx->intervals);
   for (int i = 0; i < 2; ++i) {
@@ -390,8 +393,14 @@ int ss_ctx_reserve(ss_ctx* ctx, int64_t max_samples, int region_cap) {
   if (region_cap > ctx->file_region_cap) {
     SS_CUDA_CHECK(cudaDeviceSynchronize());
     if (ctx->file_regions) cudaFree(ctx->file_regions);
-    ctx->file_regions = nullptr;
-    if ((rc = dev_alloc(ctx, &ctx->file_regions, (size_t)region_cap * 2))) return rc;
+    if (ctx->slot_nreg) cudaFree(ctx->slot_nreg);
+    if (ctx->slot_host) cudaFreeHost(ctx->slot_host);
+    ctx->file_regions = nullptr; ctx->slot_nreg = nullptr; ctx->slot_host = nullptr;
+    // kBatchSlots region buffers (slot 0 doubles as the single-clip buffer) + counters + a pinned host mirror
+    if ((rc = dev_alloc(ctx, &ctx->file_regions, (size_t)kBatchSlots * region_cap * 2))) return rc;
+    if ((rc = dev_alloc(ctx, &ctx->slot_nreg, (size_t)kBatchSlots))) return rc;
+    SS_CUDA_CHECK(cudaMallocHost(reinterpret_cast<void**>(&ctx->slot_host),
+                                 (size_t)kBatchSlots * ((size_t)region_cap * 2 + 1) * sizeof(int32_t)));
     ctx->file_region_cap = region_cap;
   }
   return SS_OK;
@@ -496,21 +505,16 @@ int ss_detect_device(ss_ctx* ctx, const float* pcm_dev, int64_t n_samples, int m
   return SS_OK;
 }
 
-int ss_detect_host(ss_ctx* ctx, const float* pcm_host, int64_t n_samples, int mode, int32_t* regions_host, int cap,
-                   int* n_regions, float* logits_host) {
-  int rc = check_ctx(ctx);
-  if (rc) return rc;
-  SS_REQUIRE(n_samples >= 0 && cap >= 0 && n_regions && (regions_host || cap == 0), SS_E_ARG,
-             "bad ss_detect_host arguments");
-  SS_REQUIRE(pcm_host || n_samples == 0, SS_E_ARG, "null pcm");
-  SS_REQUIRE(ctx->file_logits && n_samples <= ctx->file_cap_samples && cap <= ctx->file_region_cap, SS_E_CAPACITY,
-             "clip of %lld samples / %d regions exceeds the reservation (%lld / %d): call ss_ctx_reserve",
-             (long long)n_samples, cap, (long long)ctx->file_cap_samples, ctx->file_region_cap);
-  SS_REQUIRE(valid_mode(mode), SS_E_ARG, "unknown classifier mode %d", mode);
+// Enqueue one host clip: chunked H2D on the copy stream (double-buffered staging), K1-K3 per chunk and K5/K6 on the
+// compute stream, regions left in `regions_dev` / `nreg_dev`.  Does not synchronise.
+static int enqueue_detect_host(ss_ctx* ctx, const float* pcm_host, int64_t n_samples, int mode, int32_t* regions_dev,
+                               int32_t* nreg_dev, int cap) {
   cudaStream_t cs = ctx->compute_stream, xs = ctx->copy_stream;
   const int64_t W = plan_windows(n_samples);
-  int buf = 0;
-  for (int64_t w0 = 0; w0 < W; w0 += ctx->chunk_windows, buf ^= 1) {
+  int rc;
+  for (int64_t w0 = 0; w0 < W; w0 += ctx->chunk_windows) {
+    const int buf = ctx->stage_next;
+    ctx->stage_next ^= 1;
     const int64_t w1 = (w0 + ctx->chunk_windows < W) ? w0 + ctx->chunk_windows : W;
     // padded sample range the chunk's kept frames touch: [w0*step - 256 (reflection stays >= w0*step), ...)
     const int64_t plo = w0 * kStepSamples, phi = (w1 - 1) * kStepSamples + kWindowSamplesUsed;
@@ -529,16 +533,37 @@ int ss_detect_host(ss_ctx* ctx, const float* pcm_host, int64_t n_samples, int mo
     if (rc) return rc;
     SS_CUDA_CHECK(cudaEventRecord(ctx->ev_consumed[buf], cs));
   }
-  rc = detect_tail(ctx, n_samples, W, ctx->file_regions, ctx->file_nreg, cap, cs);
+  return detect_tail(ctx, n_samples, W, regions_dev, nreg_dev, cap, cs);
+}
+
+static int check_tc_health(ss_ctx* ctx, int mode, cudaStream_t cs) {
+  if (mode == SS_MODE_FP32) return SS_OK;
+  int flag = 0;
+  int rc = tc_error_flag(ctx, &flag, cs);
+  if (rc) return rc;
+  SS_REQUIRE(flag == 0, SS_E_CUDA, "tcgen05 pipeline timed out (role code %d)", flag);
+  return SS_OK;
+}
+
+int ss_detect_host(ss_ctx* ctx, const float* pcm_host, int64_t n_samples, int mode, int32_t* regions_host, int cap,
+                   int* n_regions, float* logits_host) {
+  int rc = check_ctx(ctx);
+  if (rc) return rc;
+  SS_REQUIRE(n_samples >= 0 && cap >= 0 && n_regions && (regions_host || cap == 0), SS_E_ARG,
+             "bad ss_detect_host arguments");
+  SS_REQUIRE(pcm_host || n_samples == 0, SS_E_ARG, "null pcm");
+  SS_REQUIRE(ctx->file_logits && n_samples <= ctx->file_cap_samples && cap <= ctx->file_region_cap, SS_E_CAPACITY,
+             "clip of %lld samples / %d regions exceeds the reservation (%lld / %d): call ss_ctx_reserve",
+             (long long)n_samples, cap, (long long)ctx->file_cap_samples, ctx->file_region_cap);
+  SS_REQUIRE(valid_mode(mode), SS_E_ARG, "unknown classifier mode %d", mode);
+  cudaStream_t cs = ctx->compute_stream;
+  const int64_t W = plan_windows(n_samples);
+  rc = enqueue_detect_host(ctx, pcm_host, n_samples, mode, ctx->file_regions, ctx->file_nreg, cap);
   if (rc) return rc;
   int32_t nreg = 0;
   SS_CUDA_CHECK(cudaMemcpyAsync(&nreg, ctx->file_nreg, sizeof(int32_t), cudaMemcpyDeviceToHost, cs));
   SS_CUDA_CHECK(cudaStreamSynchronize(cs));
-  if (mode != SS_MODE_FP32) {
-    int flag = 0;
-    if ((rc = tc_error_flag(ctx, &flag, cs))) return rc;
-    SS_REQUIRE(flag == 0, SS_E_CUDA, "tcgen05 pipeline timed out (role code %d)", flag);
-  }
+  if ((rc = check_tc_health(ctx, mode, cs))) return rc;
   *n_regions = nreg;
   const int ncopy = nreg < cap ? nreg : cap;
   if (ncopy > 0)
@@ -548,6 +573,48 @@ int ss_detect_host(ss_ctx* ctx, const float* pcm_host, int64_t n_samples, int mo
     SS_CUDA_CHECK(cudaMemcpyAsync(logits_host, ctx->file_logits, (size_t)W * kFrames * sizeof(float),
                                   cudaMemcpyDeviceToHost, cs));
   SS_CUDA_CHECK(cudaStreamSynchronize(cs));
+  return SS_OK;
+}
+
+int ss_detect_host_batch(ss_ctx* ctx, int n_clips, const float* const* pcm_host, const int64_t* n_samples, int mode,
+                         int32_t* regions_host, int cap, int* n_regions) {
+  int rc = check_ctx(ctx);
+  if (rc) return rc;
+  SS_REQUIRE(n_clips >= 0 && cap >= 0 && (n_clips == 0 || (pcm_host && n_samples && n_regions)) &&
+                 (regions_host || cap == 0 || n_clips == 0),
+             SS_E_ARG, "bad ss_detect_host_batch arguments");
+  SS_REQUIRE(valid_mode(mode), SS_E_ARG, "unknown classifier mode %d", mode);
+  for (int i = 0; i < n_clips; ++i) {
+    SS_REQUIRE(n_samples[i] >= 0 && (pcm_host[i] || n_samples[i] == 0), SS_E_ARG, "clip %d: bad buffer", i);
+    SS_REQUIRE(ctx->file_logits && n_samples[i] <= ctx->file_cap_samples && cap <= ctx->file_region_cap, SS_E_CAPACITY,
+               "clip %d of %lld samples / %d regions exceeds the reservation (%lld / %d): call ss_ctx_reserve", i,
+               (long long)n_samples[i], cap, (long long)ctx->file_cap_samples, ctx->file_region_cap);
+  }
+  cudaStream_t cs = ctx->compute_stream;
+  const size_t slot_ints = (size_t)ctx->file_region_cap * 2;
+  for (int g0 = 0; g0 < n_clips; g0 += kBatchSlots) {
+    const int g1 = (g0 + kBatchSlots < n_clips) ? g0 + kBatchSlots : n_clips;
+    // enqueue the whole group: clip k+1's upload overlaps clip k's compute; results land in pinned host slots
+    for (int i = g0; i < g1; ++i) {
+      const int slot = i - g0;
+      int32_t* reg_dev = ctx->file_regions + (size_t)slot * slot_ints;
+      int32_t* host_slot = ctx->slot_host + (size_t)slot * (slot_ints + 1);
+      rc = enqueue_detect_host(ctx, pcm_host[i], n_samples[i], mode, reg_dev, ctx->slot_nreg + slot, cap);
+      if (rc) return rc;
+      SS_CUDA_CHECK(cudaMemcpyAsync(host_slot, ctx->slot_nreg + slot, sizeof(int32_t), cudaMemcpyDeviceToHost, cs));
+      if (cap > 0)
+        SS_CUDA_CHECK(cudaMemcpyAsync(host_slot + 1, reg_dev, (size_t)cap * 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, cs));
+    }
+    SS_CUDA_CHECK(cudaStreamSynchronize(cs));
+    if ((rc = check_tc_health(ctx, mode, cs))) return rc;
+    for (int i = g0; i < g1; ++i) {
+      const int32_t* host_slot = ctx->slot_host + (size_t)(i - g0) * (slot_ints + 1);
+      const int nreg = host_slot[0];
+      n_regions[i] = nreg;
+      const int ncopy = nreg < cap ? nreg : cap;
+      if (ncopy > 0) memcpy(regions_host + (size_t)i * cap * 2, host_slot + 1, (size_t)ncopy * 2 * sizeof(int32_t));
+    }
+  }
   return SS_OK;
 }
 

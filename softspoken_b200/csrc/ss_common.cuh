@@ -133,6 +133,9 @@ struct ss_ctx {
   int32_t* file_cnt = nullptr;
   int32_t* file_regions = nullptr;
   int32_t* file_nreg = nullptr;
+  int32_t* slot_nreg = nullptr;       // region counters of the clips in flight in ss_detect_host_batch
+  int32_t* slot_host = nullptr;       // pinned host mirror of the batch slots: per slot {count, cap * 2 ints}
+  int stage_next = 0;                 // staging buffer the next streamed chunk uses
   int32_t* scan_tmp = nullptr;        // K6 per-block counts
   int64_t scan_tmp_len = 0;
   int file_region_cap = 0;

@@ -170,6 +170,33 @@ class Engine:
         out = reg[:k.value].copy()
         return (out, lg) if want_logits else out
 
+    def detect_host_batch(self, clips, mode: Optional[str] = None, cap: int = 4096):
+        """Several host float32 mono clips (numpy arrays or CPU tensors, ideally pinned) -> list of int32 `[R,2]`
+        region-bin arrays.  One library call: uploads overlap compute across clips."""
+        ptrs, sizes, keep = [], [], []
+        for a in clips:
+            if isinstance(a, torch.Tensor):
+                assert a.device.type == "cpu" and a.dtype == torch.float32 and a.is_contiguous()
+                ptrs.append(a.data_ptr()); sizes.append(a.numel())
+            else:
+                a = np.ascontiguousarray(a, dtype=np.float32)
+                ptrs.append(a.ctypes.data); sizes.append(a.size)
+            keep.append(a)
+        n = len(keep)
+        if n == 0:
+            return []
+        self.reserve(max(sizes), cap)
+        reg = np.empty((n, cap, 2), dtype=np.int32)
+        cnt = (C.c_int * n)()
+        check(lib.ss_detect_host_batch(self._ctx, n, (C.c_void_p * n)(*ptrs), (C.c_int64 * n)(*sizes), self._mode(mode),
+                                       C.c_void_p(reg.ctypes.data), cap, cnt))
+        out = []
+        for i in range(n):
+            if cnt[i] > cap:
+                raise _lib.SoftspokenError(_lib.SS_E_CAPACITY, f"clip {i}: {cnt[i]} regions exceed capacity {cap}")
+            out.append(reg[i, :cnt[i]].copy())
+        return out
+
     def silence_host(self, audio: np.ndarray, intervals: np.ndarray) -> None:
         """In place on a host float32 buffer (any shape, C-contiguous); `intervals` int64 `[K,2]` flat offsets."""
         assert audio.dtype == np.float32 and audio.flags.c_contiguous and audio.flags.writeable

@@ -115,3 +115,21 @@ def test_batch_invariance_and_spec_head(engine, clip60):
     err = float((sp[3].cpu() - ref).abs().max() / ref.abs().max())
     print(f"[{engine.mode}] spec head rel err {err:.3e}")
     assert err <= act_tol
+
+
+def test_large_batch_paths_equal_small_batch(sd_seed0, clip60):
+    """Batches large enough to switch the conv kernel to two-group work units (and several units per CTA) must give
+    bitwise the logits of the small-batch engine: the MMA order per output element does not depend on the batch."""
+    from oracle import postproc as pp
+    from softspoken_b200.engine import Engine
+    g = load_golden("model_seed0.npz")
+    padded = torch.from_numpy(pp.pad_audio(clip60)).cuda()
+    for mode in ("f16x3", "bf16"):
+        big = Engine(sd_seed0, 0, max_batch=48, mode=mode)
+        small = Engine(sd_seed0, 0, max_batch=4, mode=mode)
+        mel = big.features(padded, torch.from_numpy(g["starts"][:48]))
+        a = big.classify(mel)
+        b = small.classify(mel)
+        assert torch.equal(a, b), mode
+        big.close()
+        small.close()

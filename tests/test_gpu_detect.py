@@ -122,3 +122,15 @@ def test_short_and_empty_clips(detector):
         reg, lg = eng.detect_host(audio, want_logits=True)
         assert lg.shape[0] == max(5, int(np.ceil((n + 66150) / 13230)))
         assert reg.ndim == 2 and reg.shape[1] == 2
+
+
+def test_detect_host_batch_equals_per_clip(detector):
+    """ss_detect_host_batch (cross-clip overlap of upload and compute) == one ss_detect_host per clip, for more
+    clips than the 8 in-flight slots and for ragged / empty clips."""
+    eng = detector.model.engine
+    clips = [synth.synth_audio(d, 10 + i) for i, d in enumerate([20.0, 0.7, 33.1, 5.0, 12.4, 20.0, 1.0, 8.8, 15.5, 3.3])]
+    clips.insert(3, np.zeros(0, np.float32))
+    got = eng.detect_host_batch(clips, cap=512)
+    assert len(got) == len(clips)
+    for c, g in zip(clips, got):
+        assert np.array_equal(g, eng.detect_host(c, cap=512))

@@ -401,7 +401,8 @@ int pack_conv(TcState* st, const float* w, int taps, int cin, int cout, float sc
 
 constexpr size_t kSmemTail = (2 * kMaxStages + 4) * 8 + 128 * 4 + 16;   // barriers + bias + TMEM slot
 
-constexpr int kMinUnitsForPairs = 4 * kNumSMs;   // use two-group units only while >= 4 waves of them remain
+constexpr int kMinUnitsForPairs = 4 * kNumSMs;
+constexpr int kDefaultPairPolicy = 1;   // use two-group units only while >= 4 waves of them remain
 
 template <int N, Prec P, bool Dual, int G>
 int launch_conv_npg(TcConv p, int B, cudaStream_t st) {
@@ -411,6 +412,8 @@ int launch_conv_npg(TcConv p, int B, cudaStream_t st) {
   if (stages > kMaxStages) stages = kMaxStages;
   SS_REQUIRE(stages >= 2, SS_E_ARG, "conv stage of %zu bytes does not fit twice in shared memory", sb);
   p.stages = stages;
+  static const int debug = [] { const char* e = getenv("SS_TC_DEBUG"); return e ? atoi(e) : 0; }();
+  p.debug = debug;
   const size_t smem = (size_t)stages * sb + kSmemTail;
   static bool configured = false;
   if (!configured) {
@@ -434,10 +437,11 @@ int launch_conv_np(const TcConv& p, int B, cudaStream_t st) {
   const int positions = p.H * (p.W + 2) - 2;
   const int64_t pair_units = (int64_t)((positions + 2 * MT * 128 - 1) / (2 * MT * 128)) * B;
   const bool fits = stage_bytes(N, p.W, 2 * MT, Dual) * 2 + kSmemTail <= kSmemBudget;
-  // Measured (B200, batch 64): two-group units pay off where the stage traffic is heaviest — the dual layout of the
-  // split precision (-1.4 % step time) — and cost 6 % in the single-pass modes, whose epilogue overlap they reduce.
-  static const int policy = [] { const char* e = getenv("SS_TC_PAIRS"); return e ? atoi(e) : -1; }();   // tuning override
-  const bool want = policy < 0 ? Dual : policy != 0;
+  // Policy bits (SS_TC_PAIRS, tuning): 1 dual layout, 2 other split-precision layers, 4 single-pass C_out >= 96,
+  // 8 single-pass C_out <= 64.  Default: see kDefaultPairPolicy.
+  static const int policy = [] { const char* e = getenv("SS_TC_PAIRS"); return e ? atoi(e) : kDefaultPairPolicy; }();
+  const int cls = Dual ? 1 : (PrecTraits<P>::split ? 2 : (N >= 96 ? 4 : 8));
+  const bool want = (policy & cls) != 0;
   if (want && pair_units >= kMinUnitsForPairs && fits) return launch_conv_npg<N, P, Dual, 2>(p, B, st);
   return launch_conv_npg<N, P, Dual, 1>(p, B, st);
 }
@@ -588,8 +592,8 @@ int tc_build(ss_ctx* ctx, Prec prec, TcState** out) {
     SS_CUDA_CHECK(cudaMemcpy(s->rb[i].bias2, b2.data(), b2.size() * 4, cudaMemcpyHostToDevice));
     s->rb[i].bias1 = rb.c1.b;
   }
-  SS_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&s->err), sizeof(int)));
-  SS_CUDA_CHECK(cudaMemset(s->err, 0, sizeof(int)));
+  SS_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&s->err), 2 * sizeof(int)));
+  SS_CUDA_CHECK(cudaMemset(s->err, 0, 2 * sizeof(int)));
   SS_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&s->prof), kNumSMs * 8 * sizeof(long long)));
   SS_CUDA_CHECK(cudaMemset(s->prof, 0, kNumSMs * 8 * sizeof(long long)));
 #define T(t, C, H, W) do { if ((rc = alloc_tensor(s, &s->t, B, C, H, W))) return rc; } while (0)

@@ -2,7 +2,10 @@
 //
 // Persistent, warp-specialised, one CTA per SM:
 //   warp 4     producer  — cp.async.bulk (1-D TMA) of activation runs + packed weights into an smem ring
-//   warp 5     MMA       — one elected thread issues tcgen05.mma into one of two 256-column TMEM buffers
+//   warps 5,10 MMA       — one elected thread per warp issues tcgen05.mma into the two 256-column TMEM buffers; the
+//              two warps take alternate K-chunk stages and hand the issue order over through a shared-memory turn
+//              counter, so one warp's per-stage bookkeeping (barrier probes, descriptor set-up: ~500 cycles, which
+//              the shallow tensor-pipe queue would otherwise expose as a bubble) runs under the other's MMAs
 //   warps 0-3, 6-9  epilogue — tcgen05.ld -> bias / ReLU / border mask -> 16-bit pack -> 16-byte global stores
 //              (a warp reads the TMEM lane quadrant warp % 4; the two warps of a quadrant take alternate tiles)
 // The three roles are decoupled by mbarriers (full/empty per smem stage, acc_full/acc_empty per TMEM
@@ -40,7 +43,7 @@ namespace tc {
 
 constexpr int kMaxStages = 8;
 constexpr int kMaxSources = 6;
-constexpr int kTcThreads = 320;          // warps 0-3 and 6-9: epilogue; warp 4: producer; warp 5: MMA issuer
+constexpr int kTcThreads = 352;          // warps 0-3 and 6-9: epilogue; warp 4: producer; warps 5 and 10: MMA issuers
 constexpr int kAccCols = 256;             // TMEM columns per accumulator buffer (two buffers = all 512)
 constexpr uint32_t kSpinLimit = 1u << 22;
 
@@ -110,6 +113,14 @@ __device__ __forceinline__ bool mbar_wait_t(uint32_t bar, uint32_t parity, int* 
   const bool ok = mbar_wait(bar, parity, err, code);
   acc += clock64() - t0;
   return ok;
+}
+// Hot-path wait: one inline probe (the common case on the MMA warp: the barrier completed long ago), the bounded
+// loop only when it has not; cycle accounting only when a profile was requested.
+__device__ __forceinline__ bool mbar_wait_fast(uint32_t bar, uint32_t parity, int* err, int code, bool timing,
+                                               long long& acc) {
+  if (mbar_try_wait(bar, parity)) return true;
+  if (timing) return mbar_wait_t(bar, parity, err, code, acc);
+  return mbar_wait(bar, parity, err, code);
 }
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
@@ -193,6 +204,7 @@ struct TcConv {
   int stages;          // smem ring depth (<= kMaxStages)
   int* err;
   long long* prof;     // optional [gridDim.x][8] cycle counters (role wait/busy times), may be null
+  int debug;           // tuning experiments only: 1 = producer skips the copies, 2 = epilogue skips the stores
 };
 
 // 128-position tiles per work unit: one 256-column TMEM accumulator buffer holds MT tiles of N columns.
@@ -257,12 +269,14 @@ conv_tc_kernel(const TcConv p) {
   // bars: full[kMaxStages] | empty[kMaxStages] | acc_full[2] | acc_empty[2]
   float* bias_s = reinterpret_cast<float*>(bars + 2 * kMaxStages + 4);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bias_s + N);
+  volatile uint32_t* turn = tmem_slot + 1;    // number of stages whose MMAs have been issued (MMA warp hand-over)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + kMaxStages);
   const uint32_t accf0 = smem_u32(bars + 2 * kMaxStages), acce0 = smem_u32(bars + 2 * kMaxStages + 2);
 
   if (threadIdx.x == 0) {
+    *turn = 0;
     for (int s = 0; s < S; ++s) {
       mbar_init(full0 + 8 * s, 1);
       mbar_init(empty0 + 8 * s, 1);
@@ -289,7 +303,7 @@ conv_tc_kernel(const TcConv p) {
     int it = 0;
     bool ok = true;
     long long w_empty = 0;
-    for (int u = blockIdx.x; u < p.total_units && ok; u += gridDim.x) {
+    for (int u = blockIdx.x; u < p.total_units && ok && !(p.debug & 4); u += gridDim.x) {
       const int b = u / p.units_per_image;
       const int lo = (u - b * p.units_per_image) * G * MT * 128;   // first staged position (= q0 - halo)
       for (int s = 0; s < p.n_src && ok; ++s) {
@@ -302,10 +316,15 @@ conv_tc_kernel(const TcConv p) {
           if (!ok) break;
           const uint32_t dst = smem_u32(stage0 + (size_t)st * stage_sz);
           const uint16_t* plane = src.in + (((int64_t)b * src.planes_total + src.plane0 + 2 * kc) * HpWp + lo) * 8;
-          if (elect_one()) {
-            mbar_expect_tx(full0 + 8 * st, a_bytes + w_bytes);
-            bulk_g2s(dst, plane, (uint32_t)L * 16u, full0 + 8 * st);
-            bulk_g2s(dst + (uint32_t)L * 16u, plane + (int64_t)HpWp * 8, (uint32_t)L * 16u, full0 + 8 * st);
+          // a 1x1 source reads only the centre tap: its stage skips the halo on both sides
+          const uint32_t skip = (src.taps == 1) ? (uint32_t)halo * 16u : 0u;
+          const uint32_t run = (uint32_t)L * 16u - 2u * skip;
+          if (p.debug & 1) {
+            if (elect_one()) mbar_arrive(full0 + 8 * st);
+          } else if (elect_one()) {
+            mbar_expect_tx(full0 + 8 * st, 2u * run + w_bytes);
+            bulk_g2s(dst + skip, plane + skip / 2, run, full0 + 8 * st);
+            bulk_g2s(dst + (uint32_t)L * 16u + skip, plane + (int64_t)HpWp * 8 + skip / 2, run, full0 + 8 * st);
             bulk_g2s(dst + a_bytes, src.w + (int64_t)kc * src.w_stride, w_bytes, full0 + 8 * st);
           }
           __syncwarp();
@@ -313,8 +332,9 @@ conv_tc_kernel(const TcConv p) {
       }
     }
     if (p.prof && lane == 0) p.prof[blockIdx.x * 8 + 0] = w_empty;
-  } else if (warp == 5) {
-    // ===================================================================== MMA issuer (warp-uniform)
+  } else if (warp == 5 || warp == 10) {
+    // ===================================================================== MMA issuers (warp-uniform)
+    const uint32_t me = (warp == 5) ? 0u : 1u;      // this warp issues the stages with (stage index & 1) == me
     constexpr uint32_t idesc_n = instr_desc(N, PrecTraits<P>::fmt);
     constexpr uint32_t idesc_2n = instr_desc(2 * N, PrecTraits<P>::fmt);
     int tap_off[9];
@@ -322,17 +342,24 @@ conv_tc_kernel(const TcConv p) {
     for (int t = 0; t < 9; ++t) tap_off[t] = (t / 3 - 1) * Wp + (t % 3 - 1);
     // descriptor low word = (LBO >> 4) << 16 | (address >> 4)
     const uint32_t a_lo_base = ((uint32_t)L & 0x3FFFu) << 16;            // LBO = L * 16 bytes
-    int it = 0, k = 0;
+    int k = 0;
     bool ok = true;
     long long w_acce = 0, w_full = 0;
+    const bool timing = p.prof != nullptr;
     const long long t_begin = clock64();
     // total K-chunks of a unit, to recognise the last one
     int chunks_per_unit = 0;
     for (int s = 0; s < p.n_src; ++s) chunks_per_unit += p.src[s].n_chunks;
+    // The tensor pipe accepts only a couple of MMAs ahead of execution, so every cycle this loop spends between two
+    // bursts of MMAs is a pipe bubble: the ring position is carried incrementally (no division), the leader lane is
+    // elected once, waits probe inline, and a stage costs one commit.
+    const uint32_t leader = elect_one();
+    const uint32_t stage_base = smem_u32(stage0);
+    int st = 0;
+    uint32_t ph = 0, a0 = stage_base, si = 0;      // si: stage index within this CTA's whole run
     for (int u = blockIdx.x; u < p.total_units && ok; u += gridDim.x, ++k) {
       // G = 1: this unit owns buffer k & 1; G = 2: group g owns buffer g in every unit
       const uint32_t e_parity = (G == 1) ? ((((uint32_t)k >> 1) & 1u) ^ 1u) : (((uint32_t)k & 1u) ^ 1u);
-      uint32_t accumulate = 0;
       int c_in_unit = 0;
       for (int s = 0; s < p.n_src && ok; ++s) {
         const TcSource& src = p.src[s];
@@ -341,41 +368,60 @@ conv_tc_kernel(const TcConv p) {
         const uint32_t idesc = dual_src ? idesc_2n : idesc_n;
         const uint32_t col0 = (Dual && src.kind == 2) ? (uint32_t)N : 0u;
         const uint32_t b_lo_base = ((uint32_t)(dual_src ? 2 * N : N) & 0x3FFFu) << 16;   // LBO = rows * 16 bytes
-        for (int kc = 0; kc < src.n_chunks && ok; ++kc, ++it, ++c_in_unit) {
-          const int st = it % S;
-          const uint32_t ph = (uint32_t)(it / S) & 1u;
-          ok = mbar_wait_t(full0 + 8 * st, ph, p.err, 2, w_full);
-          if (!ok) break;
-          tc_fence_after();
-          const uint32_t a0 = smem_u32(stage0 + (size_t)st * stage_sz);
-          const uint32_t a_lo0 = a_lo_base | ((a0 >> 4) + (uint32_t)halo);          // centre tap, tile 0
-          const uint32_t b_lo0 = b_lo_base | ((a0 + a_bytes) >> 4);
-          const bool last = (c_in_unit == chunks_per_unit - 1);
+        const int taps = src.taps, n_chunks = src.n_chunks;
+        for (int kc = 0; kc < n_chunks && ok; ++kc, ++c_in_unit, ++si) {
+          if ((si & 1u) == me) {
+            // ---- bookkeeping (overlaps the other warp's MMAs)
+            if (!(p.debug & 4)) ok = mbar_wait_fast(full0 + 8 * st, ph, p.err, 2, timing, w_full);
+            if (!ok) break;
+            if (c_in_unit == 0) {                          // the epilogue must have drained the buffer(s)
 #pragma unroll
-          for (int g = 0; g < G; ++g) {
-            const int buf = (G == 1) ? (k & 1) : g;
-            if (c_in_unit == 0) {                          // the epilogue must have drained this buffer
-              ok = mbar_wait_t(acce0 + 8 * buf, e_parity, p.err, 4, w_acce);
+              for (int g = 0; g < G; ++g) {
+                const int buf = (G == 1) ? (k & 1) : g;
+                ok = ok && mbar_wait_fast(acce0 + 8 * buf, e_parity, p.err, 4, timing, w_acce);
+              }
               if (!ok) break;
-              tc_fence_after();
             }
-            const uint32_t d0 = tmem_base + (uint32_t)(buf * kAccCols) + col0;
-            const uint32_t a_g = a_lo0 + (uint32_t)(g * MT * 128);
-            if (elect_one()) {
-              if (dual_src) issue_group<MT, TS, 2 * N>(d0, a_g, b_lo0, idesc, src.taps, tap_off, accumulate);
-              else issue_group<MT, TS, N>(d0, a_g, b_lo0, idesc, src.taps, tap_off, accumulate);
-              if (last) tc_commit(accf0 + 8 * buf);        // this group's accumulators are complete
+            const uint32_t a_lo0 = a_lo_base | ((a0 >> 4) + (uint32_t)halo);          // centre tap, tile 0
+            const uint32_t b_lo0 = b_lo_base | ((a0 + a_bytes) >> 4);
+            const bool last = (c_in_unit == chunks_per_unit - 1);
+            const uint32_t accumulate = c_in_unit > 0 ? 1u : 0u;
+            // ---- my turn: every earlier stage's MMAs have been handed to the tensor pipe
+            {
+              uint32_t spins = 0;
+              while (*turn != si) {
+                if (++spins > kSpinLimit) { atomicExch(p.err, 5); ok = false; break; }
+              }
+              if (!ok) break;
+            }
+            tc_fence_after();
+            if (leader) {
+#pragma unroll
+              for (int g = 0; g < G; ++g) {
+                const int buf = (G == 1) ? (k & 1) : g;
+                const uint32_t d0 = tmem_base + (uint32_t)(buf * kAccCols) + col0;
+                const uint32_t a_g = a_lo0 + (uint32_t)(g * MT * 128);
+                if (p.debug & 8) { if (a_g == 0xdeadbeefu) p.err[1] = (int)(d0 + b_lo0 + idesc); }   // issue nothing
+                else if (dual_src) issue_group<MT, TS, 2 * N>(d0, a_g, b_lo0, idesc, taps, tap_off, accumulate);
+                else issue_group<MT, TS, N>(d0, a_g, b_lo0, idesc, taps, tap_off, accumulate);
+                // The tensor pipe retires MMAs in issue order, and the turn counter orders the two warps' issues, so
+                // the commit of the unit's last stage covers the other warp's earlier stages as well.
+                if (last) tc_commit(accf0 + 8 * buf);      // this group's accumulators are complete
+              }
+              // frees the stage once the MMAs that read it retire
+              if (!(p.debug & 4)) tc_commit(empty0 + 8 * st);
+              tc_fence_before();
+              *turn = si + 1u;
             }
             __syncwarp();
           }
-          if (!ok) break;
-          accumulate = 1;
-          if (elect_one()) tc_commit(empty0 + 8 * st);     // frees the stage once the MMAs that read it retire
-          __syncwarp();
+          a0 += stage_sz;
+          if (++st == S) { st = 0; ph ^= 1u; a0 = stage_base; }
         }
       }
     }
-    if (p.prof && lane == 0) {
+    __syncwarp();
+    if (p.prof && lane == 0 && me == 0) {
       p.prof[blockIdx.x * 8 + 1] = w_acce;
       p.prof[blockIdx.x * 8 + 2] = w_full;
       p.prof[blockIdx.x * 8 + 3] = clock64() - t_begin;
@@ -433,7 +479,9 @@ conv_tc_kernel(const TcConv p) {
             }
             const uint4 ph = make_uint4(hw[0], hw[1], hw[2], hw[3]);
             const int64_t plane_off = img_off + (int64_t)(n0 / 8 + g) * out_plane_stride;
-            if (!p.upsample) {
+            if (p.debug & 2) {
+              if (ph.x == 0x12345678u && lw[0] == 0x9abcdef0u) p.err[1] = 1;      // keep the values alive
+            } else if (!p.upsample) {
               if (in_tensor) {
                 *reinterpret_cast<uint4*>(p.out + plane_off + (int64_t)pos * 8) = ph;
                 if constexpr (kSplit)

@@ -2,10 +2,12 @@
 //
 // Persistent, warp-specialised, one CTA per SM:
 //   warp 4     producer  — cp.async.bulk (1-D TMA) of activation runs + packed weights into an smem ring
-//   warps 5,10 MMA       — one elected thread per warp issues tcgen05.mma into the two 256-column TMEM buffers; the
-//              two warps take alternate K-chunk stages and hand the issue order over through a shared-memory turn
-//              counter, so one warp's per-stage bookkeeping (barrier probes, descriptor set-up: ~500 cycles, which
-//              the shallow tensor-pipe queue would otherwise expose as a bubble) runs under the other's MMAs
+//   warps 5,10 MMA       — one elected thread per warp issues tcgen05.mma into the two 256-column TMEM buffers.
+//              Each warp owns half of every unit's accumulator tiles (G = 2: one group each; G = 1: half the tiles)
+//              and walks every stage for them.  The tensor pipe queues only a couple of MMAs, so whatever an issuer
+//              does between two MMAs (barrier probes, descriptor set-up: ~500 cycles per stage) would be a pipe
+//              bubble; with two independent issuers one warp's bookkeeping runs under the other's MMAs.  Every
+//              accumulator tile still has a single issuing thread and a fixed order, so results are deterministic.
 //   warps 0-3, 6-9  epilogue — tcgen05.ld -> bias / ReLU / border mask -> 16-bit pack -> 16-byte global stores
 //              (a warp reads the TMEM lane quadrant warp % 4; the two warps of a quadrant take alternate tiles)
 // The three roles are decoupled by mbarriers (full/empty per smem stage, acc_full/acc_empty per TMEM
@@ -269,20 +271,18 @@ conv_tc_kernel(const TcConv p) {
   // bars: full[kMaxStages] | empty[kMaxStages] | acc_full[2] | acc_empty[2]
   float* bias_s = reinterpret_cast<float*>(bars + 2 * kMaxStages + 4);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bias_s + N);
-  volatile uint32_t* turn = tmem_slot + 1;    // number of stages whose MMAs have been issued (MMA warp hand-over)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + kMaxStages);
   const uint32_t accf0 = smem_u32(bars + 2 * kMaxStages), acce0 = smem_u32(bars + 2 * kMaxStages + 2);
 
   if (threadIdx.x == 0) {
-    *turn = 0;
     for (int s = 0; s < S; ++s) {
       mbar_init(full0 + 8 * s, 1);
-      mbar_init(empty0 + 8 * s, 1);
+      mbar_init(empty0 + 8 * s, 2);      // both MMA warps commit their share of the stage
     }
     for (int i = 0; i < 2; ++i) {
-      mbar_init(accf0 + 8 * i, 1);
+      mbar_init(accf0 + 8 * i, G == 2 ? 1 : 2);   // G = 2: the buffer's owner; G = 1: both MMA warps
       mbar_init(acce0 + 8 * i, 8);       // one arrival per epilogue warp
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -334,7 +334,9 @@ conv_tc_kernel(const TcConv p) {
     if (p.prof && lane == 0) p.prof[blockIdx.x * 8 + 0] = w_empty;
   } else if (warp == 5 || warp == 10) {
     // ===================================================================== MMA issuers (warp-uniform)
-    const uint32_t me = (warp == 5) ? 0u : 1u;      // this warp issues the stages with (stage index & 1) == me
+    const int me = (warp == 5) ? 0 : 1;             // which half of the accumulator tiles this warp issues for
+    constexpr int MTW = (G == 2) ? MT : MT / 2;     // tiles per warp and stage
+    static_assert(G == 2 || MT % 2 == 0, "tiles must split evenly between the two MMA warps");
     constexpr uint32_t idesc_n = instr_desc(N, PrecTraits<P>::fmt);
     constexpr uint32_t idesc_2n = instr_desc(2 * N, PrecTraits<P>::fmt);
     int tap_off[9];
@@ -356,10 +358,13 @@ conv_tc_kernel(const TcConv p) {
     const uint32_t leader = elect_one();
     const uint32_t stage_base = smem_u32(stage0);
     int st = 0;
-    uint32_t ph = 0, a0 = stage_base, si = 0;      // si: stage index within this CTA's whole run
+    uint32_t ph = 0, a0 = stage_base;
     for (int u = blockIdx.x; u < p.total_units && ok; u += gridDim.x, ++k) {
-      // G = 1: this unit owns buffer k & 1; G = 2: group g owns buffer g in every unit
+      // G = 1: this unit owns buffer k & 1 (tiles split between the warps); G = 2: warp `me` owns buffer `me`
+      const int buf = (G == 1) ? (k & 1) : me;
       const uint32_t e_parity = (G == 1) ? ((((uint32_t)k >> 1) & 1u) ^ 1u) : (((uint32_t)k & 1u) ^ 1u);
+      const uint32_t d_unit = tmem_base + (uint32_t)(buf * kAccCols) + (G == 1 ? (uint32_t)(me * MTW * TS) : 0u);
+      const uint32_t a_tile0 = (uint32_t)((G == 1 ? me * MTW : me * MT) * 128);     // first position of my tiles
       int c_in_unit = 0;
       for (int s = 0; s < p.n_src && ok; ++s) {
         const TcSource& src = p.src[s];
@@ -369,52 +374,25 @@ conv_tc_kernel(const TcConv p) {
         const uint32_t col0 = (Dual && src.kind == 2) ? (uint32_t)N : 0u;
         const uint32_t b_lo_base = ((uint32_t)(dual_src ? 2 * N : N) & 0x3FFFu) << 16;   // LBO = rows * 16 bytes
         const int taps = src.taps, n_chunks = src.n_chunks;
-        for (int kc = 0; kc < n_chunks && ok; ++kc, ++c_in_unit, ++si) {
-          if ((si & 1u) == me) {
-            // ---- bookkeeping (overlaps the other warp's MMAs)
-            if (!(p.debug & 4)) ok = mbar_wait_fast(full0 + 8 * st, ph, p.err, 2, timing, w_full);
+        for (int kc = 0; kc < n_chunks && ok; ++kc, ++c_in_unit) {
+          if (!(p.debug & 4)) ok = mbar_wait_fast(full0 + 8 * st, ph, p.err, 2, timing, w_full);
+          if (!ok) break;
+          if (c_in_unit == 0) {                            // the epilogue must have drained the buffer
+            ok = mbar_wait_fast(acce0 + 8 * buf, e_parity, p.err, 4, timing, w_acce);
             if (!ok) break;
-            if (c_in_unit == 0) {                          // the epilogue must have drained the buffer(s)
-#pragma unroll
-              for (int g = 0; g < G; ++g) {
-                const int buf = (G == 1) ? (k & 1) : g;
-                ok = ok && mbar_wait_fast(acce0 + 8 * buf, e_parity, p.err, 4, timing, w_acce);
-              }
-              if (!ok) break;
-            }
-            const uint32_t a_lo0 = a_lo_base | ((a0 >> 4) + (uint32_t)halo);          // centre tap, tile 0
-            const uint32_t b_lo0 = b_lo_base | ((a0 + a_bytes) >> 4);
-            const bool last = (c_in_unit == chunks_per_unit - 1);
-            const uint32_t accumulate = c_in_unit > 0 ? 1u : 0u;
-            // ---- my turn: every earlier stage's MMAs have been handed to the tensor pipe
-            {
-              uint32_t spins = 0;
-              while (*turn != si) {
-                if (++spins > kSpinLimit) { atomicExch(p.err, 5); ok = false; break; }
-              }
-              if (!ok) break;
-            }
-            tc_fence_after();
-            if (leader) {
-#pragma unroll
-              for (int g = 0; g < G; ++g) {
-                const int buf = (G == 1) ? (k & 1) : g;
-                const uint32_t d0 = tmem_base + (uint32_t)(buf * kAccCols) + col0;
-                const uint32_t a_g = a_lo0 + (uint32_t)(g * MT * 128);
-                if (p.debug & 8) { if (a_g == 0xdeadbeefu) p.err[1] = (int)(d0 + b_lo0 + idesc); }   // issue nothing
-                else if (dual_src) issue_group<MT, TS, 2 * N>(d0, a_g, b_lo0, idesc, taps, tap_off, accumulate);
-                else issue_group<MT, TS, N>(d0, a_g, b_lo0, idesc, taps, tap_off, accumulate);
-                // The tensor pipe retires MMAs in issue order, and the turn counter orders the two warps' issues, so
-                // the commit of the unit's last stage covers the other warp's earlier stages as well.
-                if (last) tc_commit(accf0 + 8 * buf);      // this group's accumulators are complete
-              }
-              // frees the stage once the MMAs that read it retire
-              if (!(p.debug & 4)) tc_commit(empty0 + 8 * st);
-              tc_fence_before();
-              *turn = si + 1u;
-            }
-            __syncwarp();
           }
+          tc_fence_after();
+          const uint32_t a_lo0 = (a_lo_base | ((a0 >> 4) + (uint32_t)halo)) + a_tile0;   // centre tap, my first tile
+          const uint32_t b_lo0 = b_lo_base | ((a0 + a_bytes) >> 4);
+          if (leader) {
+            const uint32_t accumulate = c_in_unit > 0 ? 1u : 0u;
+            if (p.debug & 8) { if (a_lo0 == 0xdeadbeefu) p.err[1] = (int)(d_unit + b_lo0 + idesc); }   // issue nothing
+            else if (dual_src) issue_group<MTW, TS, 2 * N>(d_unit + col0, a_lo0, b_lo0, idesc, taps, tap_off, accumulate);
+            else issue_group<MTW, TS, N>(d_unit + col0, a_lo0, b_lo0, idesc, taps, tap_off, accumulate);
+            if (c_in_unit == chunks_per_unit - 1) tc_commit(accf0 + 8 * buf);   // my tiles of this unit are complete
+            if (!(p.debug & 4)) tc_commit(empty0 + 8 * st);   // my reads of the stage retire with these MMAs
+          }
+          __syncwarp();
           a0 += stage_sz;
           if (++st == S) { st = 0; ph ^= 1u; a0 = stage_base; }
         }

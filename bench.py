@@ -62,33 +62,47 @@ def load_state_dict():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    """nvidia-smi clocks / throttle reasons sampled every 50 ms.  Started before the warm-up (nvidia-smi itself takes
+    a few hundred ms to come up); `mark()` brackets the timed region and `stop()` summarises the samples inside it
+    (falling back to all samples under load if the region was shorter than a sampling period)."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int):
         super().__init__(daemon=True)
         self.index, self.rows, self.proc = index, [], None
+        self.t0 = self.t1 = None
 
     def run(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             for line in self.proc.stdout:
-                self.rows.append([c.strip() for c in line.split(",")])
+                self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
         except Exception:
             pass
 
+    def mark(self, begin: bool):
+        if begin:
+            self.t0 = time.time()
+        else:
+            self.t1 = time.time()
+
     def stop(self):
+        time.sleep(0.06)                    # let the sample that covers the end of the region arrive
         if self.proc:
             self.proc.terminate()
-        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        rows = [r for t, r in self.rows if len(r) >= 6 and self.t0 is not None and self.t0 <= t <= (self.t1 or t) + 0.06]
+        where = "timed region"
+        if not rows:
+            rows, where = [r for _, r in self.rows if len(r) >= 6], "warm-up + timed region"
+        sm = [float(r[0]) for r in rows if r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in rows if r[1].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for r in self.rows if len(r) >= 6 for n, v in zip(names, r[2:6]) if v == "Active"})
+        reasons = sorted({n for r in rows for n, v in zip(names, r[2:6]) if v == "Active"})
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+                "reasons": reasons, "samples": len(sm), "window": where}
 
 
 # ------------------------------------------------------------------------------------------------ CPU arm
@@ -231,12 +245,14 @@ def run_b200(args):
         return total_regions
 
     def timed(fn, steps, warmup):
-        for s in range(warmup):
-            fn(s)
-        sync_all()
         sampler = ClockSampler(local) if rank == 0 else None
         if sampler:
             sampler.start()
+        for s in range(warmup):
+            fn(s)
+        sync_all()
+        if sampler:
+            sampler.mark(True)
         l0 = _lib.launch_count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.perf_counter()
@@ -247,6 +263,8 @@ def run_b200(args):
         e1.record(stream)
         sync_all()
         wall = time.perf_counter() - t0
+        if sampler:
+            sampler.mark(False)
         dev_s = e0.elapsed_time(e1) / 1e3
         launches = _lib.launch_count() - l0
         clocks = sampler.stop() if sampler else None

@@ -164,19 +164,27 @@ mask_head_planar(const uint16_t* __restrict__ conv9, const uint16_t* __restrict_
   float acc[4] = {0.f, 0.f, 0.f, 0.f};
   if (valid) {
     const int rows = kMels / kHeadGroups;
-    for (int h = hg * rows; h < (hg + 1) * rows; ++h) {
-      const float4* wrow = reinterpret_cast<const float4*>(hw.flat_w + (int64_t)h * 32 * 4);
+    // two mel rows per iteration, all eight 16-byte loads of both rows issued before their FMAs (latency-bound otherwise)
+    for (int h = hg * rows; h < (hg + 1) * rows; h += 2) {
+      float a[2][4][8];
 #pragma unroll
-      for (int pl = 0; pl < 4; ++pl) {
-        float a[8];
-        load8<P>(conv9, conv9_lo, base + ((int64_t)pl * Hp + (h + 1)) * Wp + (t + 1), a);
+      for (int r = 0; r < 2; ++r)
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const float4 w = __ldg(wrow + pl * 8 + k);
-          acc[0] = fmaf(a[k], w.x, acc[0]);
-          acc[1] = fmaf(a[k], w.y, acc[1]);
-          acc[2] = fmaf(a[k], w.z, acc[2]);
-          acc[3] = fmaf(a[k], w.w, acc[3]);
+        for (int pl = 0; pl < 4; ++pl)
+          load8<P>(conv9, conv9_lo, base + ((int64_t)pl * Hp + (h + r + 1)) * Wp + (t + 1), a[r][pl]);
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const float4* wrow = reinterpret_cast<const float4*>(hw.flat_w + (int64_t)(h + r) * 32 * 4);
+#pragma unroll
+        for (int pl = 0; pl < 4; ++pl) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const float4 w = __ldg(wrow + pl * 8 + k);
+            acc[0] = fmaf(a[r][pl][k], w.x, acc[0]);
+            acc[1] = fmaf(a[r][pl][k], w.y, acc[1]);
+            acc[2] = fmaf(a[r][pl][k], w.z, acc[2]);
+            acc[3] = fmaf(a[r][pl][k], w.w, acc[3]);
+          }
         }
       }
     }

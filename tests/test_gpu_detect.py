@@ -134,3 +134,26 @@ def test_detect_host_batch_equals_per_clip(detector):
     assert len(got) == len(clips)
     for c, g in zip(clips, got):
         assert np.array_equal(g, eng.detect_host(c, cap=512))
+
+
+def test_config2_clip_device_vs_host_paths(detector):
+    """A full BASELINE config-2 unit (10-minute clip, 1,005 windows, 51,712 timeline bins): the device-resident path,
+    the streamed host path and the batched host path give bitwise the same regions, and the regions are sorted,
+    disjoint and separated by more than the 0.5 s merge gap (size-independent properties of NNDetector.py:109-141)."""
+    eng = detector.model.engine
+    audio = synth.synth_audio(600.0, 42)
+    reg_d, n_d = eng.detect_device(torch.from_numpy(audio).cuda())
+    reg_d = reg_d[: int(n_d.item())].cpu().numpy()
+    reg_h = eng.detect_host(audio)
+    reg_b = eng.detect_host_batch([audio, audio[: 22050 * 30]])[0]
+    assert lib_windows(len(audio)) == 1005
+    assert np.array_equal(reg_d, reg_h) and np.array_equal(reg_d, reg_b)
+    assert len(reg_d) > 0
+    assert (reg_d[:, 0] <= reg_d[:, 1]).all()
+    assert (reg_d[1:, 0] - reg_d[:-1, 1] > spec.GAP_BINS).all()
+    assert reg_d.min() >= 0 and reg_d.max() < 51712
+
+
+def lib_windows(n):
+    from softspoken_b200.engine import plan_windows
+    return plan_windows(n)

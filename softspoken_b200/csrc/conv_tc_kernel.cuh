@@ -48,6 +48,12 @@ constexpr int kMaxSources = 6;
 constexpr int kTcThreads = 352;          // warps 0-3 and 6-9: epilogue; warp 4: producer; warps 5 and 10: MMA issuers
 constexpr int kAccCols = 256;             // TMEM columns per accumulator buffer (two buffers = all 512)
 constexpr uint32_t kSpinLimit = 1u << 22;
+// Tuning experiments (SS_TC_DEBUG: 1 skip the copies, 2 skip the stores, 4 skip the stage barriers, 8 skip the MMAs)
+// are compiled in only with -DSS_TC_DEBUG_HOOKS=1; the production kernel carries none of their tests.
+#ifndef SS_TC_DEBUG_HOOKS
+#define SS_TC_DEBUG_HOOKS 0
+#endif
+constexpr bool kDebugHooks = SS_TC_DEBUG_HOOKS != 0;
 
 enum class Prec : int { Bf16 = 0, F16 = 1, F16x3 = 2 };
 
@@ -259,6 +265,7 @@ conv_tc_kernel(const TcConv p) {
   constexpr int TS = TilesPerUnit<N, Dual>::TS;
   constexpr bool kSplit = PrecTraits<P>::split;
   constexpr int kWpartsMax = Dual ? 2 : 1;   // weight rows per tap and K-half staged per chunk, in units of N
+  const int dbg = kDebugHooks ? p.debug : 0;
   const int Wp = p.W + 2, Hp = p.H + 2;
   const int HpWp = Hp * Wp;
   const int halo = Wp + 1;
@@ -303,7 +310,7 @@ conv_tc_kernel(const TcConv p) {
     int it = 0;
     bool ok = true;
     long long w_empty = 0;
-    for (int u = blockIdx.x; u < p.total_units && ok && !(p.debug & 4); u += gridDim.x) {
+    for (int u = blockIdx.x; u < p.total_units && ok && !(dbg & 4); u += gridDim.x) {
       const int b = u / p.units_per_image;
       const int lo = (u - b * p.units_per_image) * G * MT * 128;   // first staged position (= q0 - halo)
       for (int s = 0; s < p.n_src && ok; ++s) {
@@ -319,7 +326,7 @@ conv_tc_kernel(const TcConv p) {
           // a 1x1 source reads only the centre tap: its stage skips the halo on both sides
           const uint32_t skip = (src.taps == 1) ? (uint32_t)halo * 16u : 0u;
           const uint32_t run = (uint32_t)L * 16u - 2u * skip;
-          if (p.debug & 1) {
+          if (dbg & 1) {
             if (elect_one()) mbar_arrive(full0 + 8 * st);
           } else if (elect_one()) {
             mbar_expect_tx(full0 + 8 * st, 2u * run + w_bytes);
@@ -375,7 +382,7 @@ conv_tc_kernel(const TcConv p) {
         const uint32_t b_lo_base = ((uint32_t)(dual_src ? 2 * N : N) & 0x3FFFu) << 16;   // LBO = rows * 16 bytes
         const int taps = src.taps, n_chunks = src.n_chunks;
         for (int kc = 0; kc < n_chunks && ok; ++kc, ++c_in_unit) {
-          if (!(p.debug & 4)) ok = mbar_wait_fast(full0 + 8 * st, ph, p.err, 2, timing, w_full);
+          if (!(dbg & 4)) ok = mbar_wait_fast(full0 + 8 * st, ph, p.err, 2, timing, w_full);
           if (!ok) break;
           if (c_in_unit == 0) {                            // the epilogue must have drained the buffer
             ok = mbar_wait_fast(acce0 + 8 * buf, e_parity, p.err, 4, timing, w_acce);
@@ -386,11 +393,11 @@ conv_tc_kernel(const TcConv p) {
           const uint32_t b_lo0 = b_lo_base | ((a0 + a_bytes) >> 4);
           if (leader) {
             const uint32_t accumulate = c_in_unit > 0 ? 1u : 0u;
-            if (p.debug & 8) { if (a_lo0 == 0xdeadbeefu) p.err[1] = (int)(d_unit + b_lo0 + idesc); }   // issue nothing
+            if (dbg & 8) { if (a_lo0 == 0xdeadbeefu) p.err[1] = (int)(d_unit + b_lo0 + idesc); }   // issue nothing
             else if (dual_src) issue_group<MTW, TS, 2 * N>(d_unit + col0, a_lo0, b_lo0, idesc, taps, tap_off, accumulate);
             else issue_group<MTW, TS, N>(d_unit + col0, a_lo0, b_lo0, idesc, taps, tap_off, accumulate);
             if (c_in_unit == chunks_per_unit - 1) tc_commit(accf0 + 8 * buf);   // my tiles of this unit are complete
-            if (!(p.debug & 4)) tc_commit(empty0 + 8 * st);   // my reads of the stage retire with these MMAs
+            if (!(dbg & 4)) tc_commit(empty0 + 8 * st);   // my reads of the stage retire with these MMAs
           }
           __syncwarp();
           a0 += stage_sz;
@@ -457,7 +464,7 @@ conv_tc_kernel(const TcConv p) {
             }
             const uint4 ph = make_uint4(hw[0], hw[1], hw[2], hw[3]);
             const int64_t plane_off = img_off + (int64_t)(n0 / 8 + g) * out_plane_stride;
-            if (p.debug & 2) {
+            if (dbg & 2) {
               if (ph.x == 0x12345678u && lw[0] == 0x9abcdef0u) p.err[1] = 1;      // keep the values alive
             } else if (!p.upsample) {
               if (in_tensor) {

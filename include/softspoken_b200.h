@@ -46,6 +46,7 @@ extern "C" {
 #define SS_E_BLOB (-3)     /* malformed / incompatible weight blob */
 #define SS_E_CAPACITY (-4) /* output capacity or context limit exceeded */
 #define SS_E_NODEVICE (-5) /* no usable CUDA device */
+#define SS_E_RANGE (-6)    /* an activation left the fp16 range in an fp16-operand mode: result invalid */
 
 /* classifier arithmetic (ss_classify `mode`) */
 #define SS_MODE_FP32 0  /* CUDA-core float32 direct convolution (reference arithmetic, slow) */
@@ -149,6 +150,12 @@ SS_API int ss_detect_host(ss_ctx* ctx, const float* pcm_host, int64_t n_samples,
  * cap pairs per clip are written).  Results are identical to n_clips calls of ss_detect_host. */
 SS_API int ss_detect_host_batch(ss_ctx* ctx, int n_clips, const float* const* pcm_host, const int64_t* n_samples,
                                 int mode, int32_t* regions_host, int cap, int* n_regions);
+
+/* Device-level entry points (ss_classify, ss_detect_device) only enqueue work, so they cannot report what the
+ * kernels found: this call synchronises `stream` and returns SS_E_CUDA if a tcgen05 pipeline wait timed out or
+ * SS_E_RANGE if an fp16-operand mode saturated an activation since the last check (the host-level calls
+ * ss_detect_host / ss_detect_host_batch check by themselves). */
+SS_API int ss_check_health(ss_ctx* ctx, void* stream);
 
 /* SilenceWorker.run on one HOST buffer `(channels, n)` float32: zero [begin, end) of every
  * interval (element offsets into the flattened buffer) on the device and copy the result back. */

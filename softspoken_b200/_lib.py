@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libsoftspoken_b200.so")
 
 SS_OK = 0
-SS_E_ARG, SS_E_CUDA, SS_E_BLOB, SS_E_CAPACITY, SS_E_NODEVICE = -1, -2, -3, -4, -5
+SS_E_ARG, SS_E_CUDA, SS_E_BLOB, SS_E_CAPACITY, SS_E_NODEVICE, SS_E_RANGE = -1, -2, -3, -4, -5, -6
 MODE_FP32, MODE_BF16, MODE_F16, MODE_F16X3 = 0, 1, 2, 3
 MODES = {"fp32": MODE_FP32, "bf16": MODE_BF16, "f16": MODE_F16, "f16x3": MODE_F16X3}
 DEFAULT_MODE = "f16x3"   # fp32-grade logits on tensor cores: the mode detections are bit-exact in
@@ -61,6 +61,7 @@ _SIGNATURES = {
     "ss_detect_device": (_int, [_p, _p, _i64, _int, _p, _p, _int, _p, _p]),
     "ss_detect_host": (_int, [_p, _p, _i64, _int, _p, _int, C.POINTER(_int), _p]),
     "ss_detect_host_batch": (_int, [_p, _int, _p, _p, _int, _p, _int, _p]),
+    "ss_check_health": (_int, [_p, _p]),
     "ss_silence_host": (_int, [_p, _p, _i64, _p, _int]),
     "ss_debug_tc_profile": (_int, [_p, _int, _p]),
     "ss_debug_activation": (_int, [_p, _int, _int, _p, C.POINTER(_int), C.POINTER(_int), C.POINTER(_int), _p]),

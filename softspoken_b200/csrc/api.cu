@@ -538,10 +538,13 @@ static int enqueue_detect_host(ss_ctx* ctx, const float* pcm_host, int64_t n_sam
 
 static int check_tc_health(ss_ctx* ctx, int mode, cudaStream_t cs) {
   if (mode == SS_MODE_FP32) return SS_OK;
-  int flag = 0;
-  int rc = tc_error_flag(ctx, &flag, cs);
+  int flag = 0, range = 0;
+  int rc = tc_error_flag(ctx, &flag, &range, cs);
   if (rc) return rc;
   SS_REQUIRE(flag == 0, SS_E_CUDA, "tcgen05 pipeline timed out (role code %d)", flag);
+  SS_REQUIRE(range == 0, SS_E_RANGE,
+             "an activation exceeded the fp16 range (65504) in an fp16-operand classifier mode: the result is not "
+             "valid; use SS_MODE_BF16 or SS_MODE_FP32 for this checkpoint");
   return SS_OK;
 }
 
@@ -616,6 +619,12 @@ int ss_detect_host_batch(ss_ctx* ctx, int n_clips, const float* const* pcm_host,
     }
   }
   return SS_OK;
+}
+
+int ss_check_health(ss_ctx* ctx, void* stream) {
+  int rc = check_ctx(ctx);
+  if (rc) return rc;
+  return check_tc_health(ctx, SS_MODE_F16X3, static_cast<cudaStream_t>(stream));
 }
 
 int ss_silence_host(ss_ctx* ctx, float* pcm_host, int64_t n_elems, const ss_interval* intervals_host,

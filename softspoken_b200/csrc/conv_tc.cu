@@ -600,8 +600,8 @@ int tc_build(ss_ctx* ctx, Prec prec, TcState** out) {
     SS_CUDA_CHECK(cudaMemcpy(s->rb[i].bias2, b2.data(), b2.size() * 4, cudaMemcpyHostToDevice));
     s->rb[i].bias1 = rb.c1.b;
   }
-  SS_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&s->err), 2 * sizeof(int)));
-  SS_CUDA_CHECK(cudaMemset(s->err, 0, 2 * sizeof(int)));
+  SS_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&s->err), 4 * sizeof(int)));
+  SS_CUDA_CHECK(cudaMemset(s->err, 0, 4 * sizeof(int)));
   SS_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&s->prof), kNumSMs * 8 * sizeof(long long)));
   SS_CUDA_CHECK(cudaMemset(s->prof, 0, kNumSMs * 8 * sizeof(long long)));
 #define T(t, C, H, W) do { if ((rc = alloc_tensor(s, &s->t, B, C, H, W))) return rc; } while (0)
@@ -770,16 +770,22 @@ int tc_debug_profile(ss_ctx* ctx, int select_launch, long long* out_host) {
   return SS_OK;
 }
 
-// The pipeline's bounded waits flag a time-out in device memory; surface it (0 = healthy).
-int tc_error_flag(ss_ctx* ctx, int* flag, cudaStream_t st) {
+// The pipeline's bounded waits flag a time-out in device memory and the fp16-operand epilogues flag activations that
+// left the fp16 range; surface both (0 = healthy) and clear the range flag so that the next call starts clean.
+int tc_error_flag(ss_ctx* ctx, int* flag, int* range_flag, cudaStream_t st) {
   *flag = 0;
+  *range_flag = 0;
   for (int slot = 0; slot < 3; ++slot) {
     TcState* s = static_cast<TcState*>(ctx->tc[slot]);
     if (!s) continue;
-    int h = 0;
-    SS_CUDA_CHECK(cudaMemcpyAsync(&h, s->err, sizeof(int), cudaMemcpyDeviceToHost, st));
+    int h[4] = {0, 0, 0, 0};
+    SS_CUDA_CHECK(cudaMemcpyAsync(h, s->err, sizeof(h), cudaMemcpyDeviceToHost, st));
     SS_CUDA_CHECK(cudaStreamSynchronize(st));
-    if (h) *flag = h;
+    if (h[0]) *flag = h[0];
+    if (h[2]) {
+      *range_flag = 1;
+      SS_CUDA_CHECK(cudaMemsetAsync(s->err + 2, 0, sizeof(int), st));
+    }
   }
   return SS_OK;
 }

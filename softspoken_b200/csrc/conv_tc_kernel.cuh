@@ -210,7 +210,7 @@ struct TcConv {
   int out_planes_total, out_plane0, upsample;
   int units_per_image, total_units;
   int stages;          // smem ring depth (<= kMaxStages)
-  int* err;
+  int* err;            // [0] pipeline time-out code, [1] scratch of the tuning hooks, [2] fp16 range overflow seen
   long long* prof;     // optional [gridDim.x][8] cycle counters (role wait/busy times), may be null
   int debug;           // tuning experiments only: 1 = producer skips the copies, 2 = epilogue skips the stores
 };
@@ -421,6 +421,7 @@ conv_tc_kernel(const TcConv p) {
     const int64_t out_plane_stride = p.upsample ? (int64_t)(2 * p.H + 2) * Wp2 * 8 : (int64_t)HpWp * 8;
     int k = 0;
     bool ok = true;
+    bool out_of_range = false;     // fp16 operand modes: an activation left the fp16 range (it was saturated)
     long long w_accf = 0;
     const long long t_begin = clock64();
     for (int u = blockIdx.x; u < p.total_units && ok; u += gridDim.x, ++k) {
@@ -458,6 +459,7 @@ conv_tc_kernel(const TcConv p) {
               float f1 = fmaf(__uint_as_float(v[g * 8 + 2 * h + 1]), inv_scale, bias_s[n0 + g * 8 + 2 * h + 1]);
               if (p.relu) { f0 = fmaxf(f0, 0.f); f1 = fmaxf(f1, 0.f); }
               if (!interior) { f0 = 0.f; f1 = 0.f; }
+              if constexpr (PrecTraits<P>::fmt == 0) out_of_range |= (fmaxf(fabsf(f0), fabsf(f1)) > 65504.f);
               hw[h] = pack_hi<P>(f0, f1);
               if constexpr (kSplit) lw[h] = pack_lo_f16(f0, f1, hw[h]);
               else lw[h] = 0u;
@@ -496,6 +498,7 @@ conv_tc_kernel(const TcConv p) {
       if (lane == 0) mbar_arrive(acce0 + 8 * buf);
      }
     }
+    if (out_of_range) p.err[2] = 1;
     if (p.prof && threadIdx.x == 0) {
       p.prof[blockIdx.x * 8 + 4] = w_accf;
       p.prof[blockIdx.x * 8 + 5] = clock64() - t_begin;

@@ -181,7 +181,7 @@ int launch_silence(float* pcm, int64_t n_elems, int64_t shift, const ss_interval
 void tc_destroy(ss_ctx* ctx);
 int classify_tc(ss_ctx* ctx, int mode, const float* mel, int n_windows, float* logits, float* spec_out,
                 cudaStream_t st);
-int tc_error_flag(ss_ctx* ctx, int* flag, cudaStream_t st);
+int tc_error_flag(ss_ctx* ctx, int* flag, int* range_flag, cudaStream_t st);
 int tc_debug_profile(ss_ctx* ctx, int select_launch, long long* out_host);
 int tc_debug_dump(ss_ctx* ctx, int which, int n_windows, float* out, int* C, int* H, int* W, cudaStream_t st);
 

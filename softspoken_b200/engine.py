@@ -197,6 +197,11 @@ class Engine:
             out.append(reg[i, :cnt[i]].copy())
         return out
 
+    def check_health(self) -> None:
+        """Synchronise and raise if a kernel flagged a pipeline time-out or an fp16 range overflow (device-level
+        calls only enqueue work; the host-level detect calls check by themselves)."""
+        check(lib.ss_check_health(self._ctx, self._stream()))
+
     def silence_host(self, audio: np.ndarray, intervals: np.ndarray) -> None:
         """In place on a host float32 buffer (any shape, C-contiguous); `intervals` int64 `[K,2]` flat offsets."""
         assert audio.dtype == np.float32 and audio.flags.c_contiguous and audio.flags.writeable

@@ -133,3 +133,22 @@ def test_large_batch_paths_equal_small_batch(sd_seed0, clip60):
         assert torch.equal(a, b), mode
         big.close()
         small.close()
+
+
+def test_fp16_range_overflow_is_reported(sd_seed0, clip60):
+    """fp16-operand modes saturate activations beyond 65504; the library must say so (SS_E_RANGE) instead of
+    returning silently wrong detections, and the bf16 mode must still run on the same checkpoint."""
+    from collections import OrderedDict
+    from softspoken_b200 import _lib
+    from softspoken_b200.engine import Engine
+    sd = OrderedDict((k, v.clone()) for k, v in sd_seed0.items())
+    sd["conv1_1.conv1.0.weight"] *= 1e7
+    audio = clip60[: 22050 * 5]
+    eng = Engine(sd, 0, max_batch=8, mode="f16x3")
+    with pytest.raises(_lib.SoftspokenError) as e:
+        eng.detect_host(audio)
+    assert e.value.code == _lib.SS_E_RANGE
+    reg, lg = eng.detect_host(audio, mode="bf16", want_logits=True)      # the flag was cleared; bf16 has the range
+    assert np.isfinite(lg).all()
+    eng.check_health()
+    eng.close()

@@ -1,0 +1,120 @@
+"""Headless corpus driver: "Run Voice Detector" over a file list on 1..N GPUs of one box (BASELINE config 3).
+
+The reference processes its file list in one loop on one device (root/code/backend/worker.py:49-136) and saves
+the detections CSV after every file.  Here the list is sharded per file across ranks (one process per GPU,
+`torchrun`), every rank streams its files through `ss_detect_host_batch` in groups, and the
+`(file_index, start_bin, end_bin)` triplets are gathered to rank 0 once at the end (softspoken_b200/dist.py) —
+the only collective of the path.  Rank 0 assigns `ID = 1..` in file-list order and writes the same CSV text the
+reference's `DetectionProject.save_detections` would (silencer_ui.py:816-817), so the output is byte-identical
+for any number of ranks.
+
+    torchrun --nproc-per-node 8 -m softspoken_b200.corpus files.txt detections.csv [--checkpoint model.pth]
+"""
+from __future__ import annotations
+
+import argparse
+import os
+import sys
+from typing import Callable, List, Optional, Sequence
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import dist as ssdist
+from . import spec, wavio
+
+
+def load_mono_22050(path: str) -> np.ndarray:
+    """`voice_activity.load_audio` for what the configs use: wav -> float32 mono at 22,050 Hz.  Multi-channel
+    files are averaged as `librosa.to_mono` does (voice_activity.py:61-63); other rates are refused (the
+    reference resamples with soxr, which this path does not restate — SURVEY §8c)."""
+    x, sr = wavio.read_wav(path)
+    if x.ndim > 1:
+        x = np.mean(x, axis=0).astype(np.float32)
+    if sr != spec.SAMPLE_RATE:
+        raise ValueError(f"{path}: sample rate {sr} != {spec.SAMPLE_RATE} (resampling is outside this path)")
+    return np.ascontiguousarray(x, dtype=np.float32)
+
+
+def detect_corpus(files: Sequence[str], detect_batch: Callable[[List[np.ndarray]], List[np.ndarray]],
+                  load: Callable[[str], np.ndarray] = load_mono_22050, durations: Optional[Sequence[float]] = None,
+                  group_size: int = 8, device: Optional[torch.device] = None, next_id: int = 1):
+    """-> list of CSV row dicts on rank 0 (None on the other ranks).
+
+    `detect_batch(clips) -> [int32 [R,2] region bins per clip]` is `Engine.detect_host_batch` (or any stand-in
+    with that contract: the CPU tests drive this function with the oracle)."""
+    world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+    rank = dist.get_rank() if world > 1 else 0
+    if durations is None:
+        durations = [wavio.duration_and_rate(f)[0] for f in files]
+    mine = ssdist.shard_files(durations, world)[rank]
+    parts = []
+    for g0 in range(0, len(mine), group_size):
+        idx = mine[g0:g0 + group_size]
+        clips = [load(files[i]) for i in idx]
+        for i, bins in zip(idx, detect_batch(clips)):
+            b = np.asarray(bins, dtype=np.int32).reshape(-1, 2)
+            parts.append(np.concatenate([np.full((len(b), 1), i, np.int32), b], axis=1))
+    local = np.concatenate(parts) if parts else np.zeros((0, 3), np.int32)
+    allrows = ssdist.gather_detections(local, device)
+    if rank != 0:
+        return None
+    return ssdist.rows_from_triplets(list(files), allrows, next_id)
+
+
+def csv_text(rows) -> str:
+    """The text `DetectionProject.save_detections` writes for these rows (silencer_ui.py:779-788,816-817):
+    `DataFrame.to_csv(index=False)` prints ints as ints, floats with the shortest repr, empty strings as empty
+    fields and quotes a field only when it must (csv.QUOTE_MINIMAL).  Written directly because appending ten
+    thousand rows one `df.loc[len(df)] = row` at a time, as the reference does per file, is quadratic."""
+    import csv
+    import io
+    from .worker import COLUMN_TYPES
+    cols = list(COLUMN_TYPES.keys())
+    buf = io.StringIO()
+    w = csv.writer(buf, quoting=csv.QUOTE_MINIMAL, lineterminator="\n")
+    w.writerow(cols)
+    for r in rows:
+        w.writerow([repr(float(r[c])) if c in ("start_time", "end_time") else r[c] for c in cols])
+    return buf.getvalue()
+
+
+def main(argv=None) -> int:
+    ap = argparse.ArgumentParser(description=__doc__.split("\n\n")[0])
+    ap.add_argument("file_list", help="text file with one wav path per line (the reference's <project>_files.txt)")
+    ap.add_argument("out_csv")
+    ap.add_argument("--checkpoint", default=None, help="reference checkpoint (.pth); seeded init if absent, as the reference")
+    ap.add_argument("--mode", default=None)
+    ap.add_argument("--max-batch", type=int, default=256)
+    args = ap.parse_args(argv)
+    from . import checkpoint
+    from .engine import Engine
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=device)
+    with open(args.file_list) as f:
+        files = [ln.strip() for ln in f if ln.strip()]
+    if args.checkpoint and os.path.exists(checkpoint.normalise_model_path(args.checkpoint)):
+        sd = torch.load(checkpoint.normalise_model_path(args.checkpoint), map_location="cpu", weights_only=True)["model_state_dict"]
+    else:
+        print("No checkpoint found. Starting training from scratch.")     # NNDetector.py:52
+        sd = checkpoint.synthetic_state_dict(0)
+    eng = Engine(sd, local, max_batch=args.max_batch, **({"mode": args.mode} if args.mode else {}))
+    rows = detect_corpus(files, eng.detect_host_batch, device=device)
+    if rows is not None:
+        with open(args.out_csv, "w", newline="") as f:
+            f.write(csv_text(rows))
+        print(f"{len(rows)} detections in {len(files)} files -> {args.out_csv}")
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

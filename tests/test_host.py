@@ -171,3 +171,65 @@ def test_rows_from_triplets_assigns_ids_in_file_order():
     assert [r["ID"] for r in rows] == [1, 2, 3]
     assert [r["file_name"] for r in rows] == ["a.wav", "c.wav", "c.wav"]
     assert rows[0]["start_time"] == float("0.1172") - 3
+
+
+def _corpus_worker(rank, world, port, q, files, durations):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    if world > 1:
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+    from softspoken_b200 import corpus
+
+    def fake_load(path):                      # "audio" = the file's index, so that detections depend on the file
+        return np.full(4, float(files.index(path)), np.float32)
+
+    def fake_detect(clips):                   # deterministic regions per file, some files without any
+        out = []
+        for c in clips:
+            i = int(c[0])
+            rng = np.random.default_rng(i)
+            out.append(np.sort(rng.integers(0, 51000, (i % 5, 2)), axis=1).astype(np.int32))
+        return out
+
+    rows = corpus.detect_corpus(files, fake_detect, load=fake_load, durations=durations, group_size=3)
+    q.put(corpus.csv_text(rows) if rank == 0 else (rows is None))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def test_corpus_driver_same_csv_for_one_and_two_ranks():
+    """BASELINE config 3 host logic: per-file sharding + gather + ID assignment give byte-identical CSV text for
+    world sizes 1 and 2, and the direct CSV writer prints what DetectionProject's DataFrame prints."""
+    import types
+    import torch.multiprocessing as mp
+    from softspoken_b200 import corpus
+    from softspoken_b200.worker import DetectionProject, append_rows
+    files = [f"/data/dir{i % 3}/clip, {i}.wav" if i == 4 else f"/data/dir{i % 3}/clip{i}.wav" for i in range(11)]
+    durations = [600.0 - 7 * (i % 4) for i in range(11)]
+    ctx = mp.get_context("spawn")
+    texts = {}
+    for world in (1, 2):
+        q = ctx.Queue()
+        port = 29500 + (os.getpid() + 17 * world) % 2000
+        procs = [ctx.Process(target=_corpus_worker, args=(r, world, port, q, files, durations)) for r in range(world)]
+        for p in procs:
+            p.start()
+        res = [q.get(timeout=120) for _ in procs]
+        for p in procs:
+            p.join(60)
+        texts[world] = [r for r in res if isinstance(r, str)][0]
+        assert all(r is True for r in res if not isinstance(r, str))
+    assert texts[1] == texts[2]
+    assert texts[1].splitlines()[0] == "ID,file_path,file_name,start_time,end_time,erase,user_comment,review_datetime"
+    # the DataFrame route of the reference prints the same text
+    import tempfile
+    from softspoken_b200.detector import region_bins_to_times
+    with tempfile.TemporaryDirectory() as d:
+        proj = DetectionProject(types.SimpleNamespace(current_project={"detections_file": os.path.join(d, "x.csv")}))
+        for i, f in enumerate(files):
+            rng = np.random.default_rng(i)
+            bins = np.sort(rng.integers(0, 51000, (i % 5, 2)), axis=1).astype(np.int32)
+            append_rows(proj, f, region_bins_to_times(bins))
+        proj.save_detections()
+        assert open(os.path.join(d, "x.csv")).read() == texts[1]

@@ -410,7 +410,7 @@ int pack_conv(TcState* st, const float* w, int taps, int cin, int cout, float sc
 constexpr size_t kSmemTail = (2 * kMaxStages + 4) * 8 + 128 * 4 + 16;   // barriers + bias + TMEM slot
 
 constexpr int kMinUnitsForPairs = 4 * kNumSMs;
-constexpr int kDefaultPairPolicy = 1;   // use two-group units only while >= 4 waves of them remain
+constexpr int kDefaultPairPolicy = 0;   // measured with the two-issuer kernel (batch 256): G = 1 everywhere is 2 % faster   // use two-group units only while >= 4 waves of them remain
 
 template <int N, Prec P, bool Dual, int G>
 int launch_conv_npg(TcConv p, int B, cudaStream_t st) {

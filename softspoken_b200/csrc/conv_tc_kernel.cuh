@@ -366,6 +366,7 @@ conv_tc_kernel(const TcConv p) {
     const uint32_t stage_base = smem_u32(stage0);
     int st = 0;
     uint32_t ph = 0, a0 = stage_base;
+    bool ready = false;            // the full barrier of the stage about to be consumed was already seen complete
     for (int u = blockIdx.x; u < p.total_units && ok; u += gridDim.x, ++k) {
       // G = 1: this unit owns buffer k & 1 (tiles split between the warps); G = 2: warp `me` owns buffer `me`
       const int buf = (G == 1) ? (k & 1) : me;
@@ -382,7 +383,7 @@ conv_tc_kernel(const TcConv p) {
         const uint32_t b_lo_base = ((uint32_t)(dual_src ? 2 * N : N) & 0x3FFFu) << 16;   // LBO = rows * 16 bytes
         const int taps = src.taps, n_chunks = src.n_chunks;
         for (int kc = 0; kc < n_chunks && ok; ++kc, ++c_in_unit) {
-          if (!(dbg & 4)) ok = mbar_wait_fast(full0 + 8 * st, ph, p.err, 2, timing, w_full);
+          if (!ready && !(dbg & 4)) ok = mbar_wait_fast(full0 + 8 * st, ph, p.err, 2, timing, w_full);
           if (!ok) break;
           if (c_in_unit == 0) {                            // the epilogue must have drained the buffer
             ok = mbar_wait_fast(acce0 + 8 * buf, e_parity, p.err, 4, timing, w_acce);
@@ -402,6 +403,8 @@ conv_tc_kernel(const TcConv p) {
           __syncwarp();
           a0 += stage_sz;
           if (++st == S) { st = 0; ph ^= 1u; a0 = stage_base; }
+          // probe the next stage now: the answer travels while this iteration winds down
+          ready = !(dbg & 4) && mbar_try_wait(full0 + 8 * st, ph);
         }
       }
     }

@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsoftspoken_b200.so")
+LIB_PATH = os.environ.get("SOFTSPOKEN_B200_LIB") or os.path.join(_HERE, "libsoftspoken_b200.so")   # override: A/B tuning builds
 
 SS_OK = 0
 SS_E_ARG, SS_E_CUDA, SS_E_BLOB, SS_E_CAPACITY, SS_E_NODEVICE, SS_E_RANGE = -1, -2, -3, -4, -5, -6

@@ -308,6 +308,8 @@ struct TcState {
   Tensor x0, m4, m3, m2, m1, p1, p2, p3, p4, bott, c9, spec;
   Tensor t[RB_COUNT];
   int* err = nullptr;
+  int* flags = nullptr;        // per-unit completion counts of a fused ResBlock launch (TcJob)
+  int flags_cap = 0;
   long long* prof = nullptr;   // [kNumSMs][8] role timers of the selected conv launch (debug)
   int prof_layer = -1;         // launch index to capture (-1: none)
   int launch_index = 0;
@@ -407,19 +409,30 @@ int pack_conv(TcState* st, const float* w, int taps, int cin, int cout, float sc
   return SS_OK;
 }
 
-constexpr size_t kSmemTail = (2 * kMaxStages + 4) * 8 + 128 * 4 + 16;   // barriers + bias + TMEM slot
+constexpr size_t kSmemTail = (2 * kMaxStages + 4) * 8 + 2 * 128 * 4 + 16;   // barriers + bias of both phases + TMEM slot
 
+constexpr int kDefaultLag = 160;   // units by which conv2 trails conv1 in a fused ResBlock launch (> one round of 148 CTAs)
 constexpr int kMinUnitsForPairs = 4 * kNumSMs;
 constexpr int kDefaultPairPolicy = 0;   // measured with the two-issuer kernel (batch 256): G = 1 everywhere is 2 % faster   // use two-group units only while >= 4 waves of them remain
 
 template <int N, Prec P, bool Dual, int G>
-int launch_conv_npg(TcConv p, int B, cudaStream_t st) {
+int launch_conv_npg(TcJob job, int B, cudaStream_t st) {
+  TcConv& p = job.c[0];
   constexpr int MT = TilesPerUnit<N, Dual>::value;
   const size_t sb = stage_bytes(N, p.W, G * MT, Dual);
   int stages = (int)((kSmemBudget - kSmemTail) / sb);
   if (stages > kMaxStages) stages = kMaxStages;
   SS_REQUIRE(stages >= 2, SS_E_ARG, "conv stage of %zu bytes does not fit twice in shared memory", sb);
   p.stages = stages;
+  {
+    // K-chunks of a 1x1 source per stage-sized slot (SS_TC_CPS caps it; 1 = one chunk per stage as for 3x3 sources)
+    const char* ce = getenv("SS_TC_CPS");
+    const int cap = ce ? atoi(ce) : 4;
+    const size_t chunk1 = (size_t)G * MT * 128 * 32 + (Dual ? 2 : 1) * (size_t)N * 32;
+    int cps = (int)(sb / chunk1);
+    if (cps > cap) cps = cap;
+    p.cps = cps < 1 ? 1 : cps;
+  }
   static const int debug = [] { const char* e = getenv("SS_TC_DEBUG"); return e ? atoi(e) : 0; }();
   p.debug = debug;
   const size_t smem = (size_t)stages * sb + kSmemTail;
@@ -432,15 +445,23 @@ int launch_conv_npg(TcConv p, int B, cudaStream_t st) {
   const int positions = p.H * (p.W + 2) - 2;          // (1,1) .. (H,W) in flattened padded coordinates
   p.units_per_image = (positions + G * MT * 128 - 1) / (G * MT * 128);
   p.total_units = p.units_per_image * B;
-  const int grid = p.total_units < kNumSMs ? p.total_units : kNumSMs;
-  conv_tc_kernel<N, P, Dual, G><<<grid, kTcThreads, smem, st>>>(p);
+  const int items = p.total_units * job.n_phase;
+  const int grid = items < kNumSMs ? items : kNumSMs;
+  if (job.n_phase == 2) {
+    SS_REQUIRE(p.W + 3 <= G * MT * 128, SS_E_ARG, "fused ResBlock launch: halo %d exceeds the unit", p.W + 3);
+    SS_REQUIRE(p.total_units <= job.flags_cap, SS_E_ARG, "fused ResBlock launch: %d units exceed the flag array",
+               p.total_units);
+    SS_CUDA_CHECK(cudaMemsetAsync(job.flags, 0, (size_t)p.total_units * sizeof(int), st));
+  }
+  conv_tc_kernel<N, P, Dual, G><<<grid, kTcThreads, smem, st>>>(job);
   SS_CUDA_CHECK(cudaGetLastError());
   count_launch();
   return SS_OK;
 }
 
 template <int N, Prec P, bool Dual>
-int launch_conv_np(const TcConv& p, int B, cudaStream_t st) {
+int launch_conv_np(const TcJob& job, int B, cudaStream_t st) {
+  const TcConv& p = job.c[0];
   constexpr int MT = TilesPerUnit<N, Dual>::value;
   const int positions = p.H * (p.W + 2) - 2;
   const int64_t pair_units = (int64_t)((positions + 2 * MT * 128 - 1) / (2 * MT * 128)) * B;
@@ -450,12 +471,12 @@ int launch_conv_np(const TcConv& p, int B, cudaStream_t st) {
   static const int policy = [] { const char* e = getenv("SS_TC_PAIRS"); return e ? atoi(e) : kDefaultPairPolicy; }();
   const int cls = Dual ? 1 : (PrecTraits<P>::split ? 2 : (N >= 96 ? 4 : 8));
   const bool want = (policy & cls) != 0;
-  if (want && pair_units >= kMinUnitsForPairs && fits) return launch_conv_npg<N, P, Dual, 2>(p, B, st);
-  return launch_conv_npg<N, P, Dual, 1>(p, B, st);
+  if (want && pair_units >= kMinUnitsForPairs && fits) return launch_conv_npg<N, P, Dual, 2>(job, B, st);
+  return launch_conv_npg<N, P, Dual, 1>(job, B, st);
 }
 
 template <Prec P>
-int launch_conv_p(const TcConv& p, int N, int B, cudaStream_t st) {
+int launch_conv_p(const TcJob& p, int N, int B, cudaStream_t st) {
   constexpr bool kDualSmall = PrecTraits<P>::split;      // == is_dual(P, N) for N <= 64
   switch (N) {
     case 32: return launch_conv_np<32, P, kDualSmall>(p, B, st);
@@ -467,7 +488,7 @@ int launch_conv_p(const TcConv& p, int N, int B, cudaStream_t st) {
   return SS_E_ARG;
 }
 
-int launch_conv(Prec prec, const TcConv& p, int N, int B, cudaStream_t st) {
+int launch_conv(Prec prec, const TcJob& p, int N, int B, cudaStream_t st) {
   switch (prec) {
     case Prec::Bf16: return launch_conv_p<Prec::Bf16>(p, N, B, st);
     case Prec::F16: return launch_conv_p<Prec::F16>(p, N, B, st);
@@ -524,9 +545,6 @@ int tc_res_block(TcState* s, int which, const Tensor& x, int x_plane0, Tensor& o
   p.relu = 1;
   p.out = t.data; p.out_lo = t.lo; p.out_planes_total = t.planes; p.out_plane0 = 0; p.upsample = 0;
   p.err = s->err;
-  p.prof = (s->launch_index++ == s->prof_layer) ? s->prof : nullptr;
-  int rc = launch_conv(s->prec, p, N, B, st);
-  if (rc) return rc;
   TcConv q{};
   add_sources(&q, s, t, 0, rb.c2, Terms::Corrections);
   add_sources(&q, s, x, x_plane0, rb.res, Terms::Corrections);
@@ -538,8 +556,31 @@ int tc_res_block(TcState* s, int which, const Tensor& x, int x_plane0, Tensor& o
   q.relu = 1;
   q.out = out.data; q.out_lo = out.lo; q.out_planes_total = out.planes; q.out_plane0 = out_plane0; q.upsample = upsample;
   q.err = s->err;
+  // SS_TC_FUSE=1: both convolutions of the block in ONE persistent launch, conv2 trailing conv1 by SS_TC_LAG units
+  // behind per-unit completion flags (TcJob).  Bit-identical results, t is read back from L2 instead of HBM and the
+  // launch has one tail; measured equal in time to two launches (29.77 vs 29.74 ms per 10-min clip, f16x3, batch
+  // 256: the c2 launches are bound by MMA issue and stores, not by DRAM reads), so the simpler schedule is the
+  // default.  Read per call so that tests can compare the two in one process.
+  const char* fe = getenv("SS_TC_FUSE");
+  const char* le = getenv("SS_TC_LAG");
+  const int fuse = fe ? atoi(fe) : 0;
+  const int lag = le ? atoi(le) : kDefaultLag;
+  TcJob job{};
+  job.flags = s->flags;
+  job.flags_cap = s->flags_cap;
+  job.lag = lag;
+  if (fuse) {
+    p.prof = (s->launch_index++ == s->prof_layer) ? s->prof : nullptr;
+    job.c[0] = p; job.c[1] = q; job.n_phase = 2;
+    return launch_conv(s->prec, job, N, B, st);
+  }
+  p.prof = (s->launch_index++ == s->prof_layer) ? s->prof : nullptr;
+  job.c[0] = p; job.n_phase = 1;
+  int rc = launch_conv(s->prec, job, N, B, st);
+  if (rc) return rc;
   q.prof = (s->launch_index++ == s->prof_layer) ? s->prof : nullptr;
-  return launch_conv(s->prec, q, N, B, st);
+  job.c[0] = q;
+  return launch_conv(s->prec, job, N, B, st);
 }
 
 template <Prec P>
@@ -602,6 +643,8 @@ int tc_build(ss_ctx* ctx, Prec prec, TcState** out) {
   }
   SS_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&s->err), 4 * sizeof(int)));
   SS_CUDA_CHECK(cudaMemset(s->err, 0, 4 * sizeof(int)));
+  s->flags_cap = B * (((kMels + 2) * (kFrames + 2) + 255) / 256);      // smallest unit: 256 positions
+  SS_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&s->flags), (size_t)s->flags_cap * sizeof(int)));
   SS_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&s->prof), kNumSMs * 8 * sizeof(long long)));
   SS_CUDA_CHECK(cudaMemset(s->prof, 0, kNumSMs * 8 * sizeof(long long)));
 #define T(t, C, H, W) do { if ((rc = alloc_tensor(s, &s->t, B, C, H, W))) return rc; } while (0)
@@ -704,6 +747,7 @@ void tc_destroy(ss_ctx* ctx) {
       if (s->rb[i].bias2) cudaFree(s->rb[i].bias2);
     }
     if (s->err) cudaFree(s->err);
+    if (s->flags) cudaFree(s->flags);
     if (s->prof) cudaFree(s->prof);
     delete s;
     ctx->tc[slot] = nullptr;

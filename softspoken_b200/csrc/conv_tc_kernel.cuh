@@ -210,10 +210,57 @@ struct TcConv {
   int out_planes_total, out_plane0, upsample;
   int units_per_image, total_units;
   int stages;          // smem ring depth (<= kMaxStages)
+  int cps;             // K-chunks a stage of a 1x1 source carries (>= 1; see the producer)
   int* err;            // [0] pipeline time-out code, [1] scratch of the tuning hooks, [2] fp16 range overflow seen
   long long* prof;     // optional [gridDim.x][8] cycle counters (role wait/busy times), may be null
   int debug;           // tuning experiments only: 1 = producer skips the copies, 2 = epilogue skips the stores
 };
+
+// One launch: a single convolution (n_phase = 1) or both convolutions of a ResBlock (n_phase = 2), c[1] reading the
+// tensor c[0] writes.  Geometry (H, W, units, stages, err, prof, debug) is shared and taken from c[0].
+//
+// Fused schedule.  The work items of the launch are the units of c[0] and c[1] interleaved one to one, c[1] running
+// `lag` units behind:   c0:0 .. c0:lag-1 | c0:lag c1:0 | c0:lag+1 c1:1 | ... | c1:T-lag .. c1:T-1,   handed to the
+// persistent CTAs round-robin.  A c[1] unit reads positions produced by the c[0] units v-1, v, v+1 of its image
+// (the halo is shorter than a unit); every epilogue warp of a c[0] unit bumps flags[unit] after its stores, and the
+// producer of the c[1] unit waits for 8 arrivals on each of the (up to) three flags before its first copy.  With
+// lag > 148 the flags it needs were raised about two rounds earlier, so the wait is a formality, the intermediate
+// tensor is read back from L2 a few microseconds after it was written instead of from HBM a whole batch later, and
+// the launch has one tail instead of two.  Every item depends only on items with a smaller index and CTAs take
+// their items in increasing order, so the lowest unfinished item can always run: no deadlock while all CTAs are
+// resident (grid <= SM count, one CTA per SM); all waits are bounded and flag p.err instead of hanging.
+struct TcJob {
+  TcConv c[2];
+  int n_phase;
+  int lag;             // units by which c[1] trails c[0]
+  int* flags;          // [total_units], zeroed before the launch (fused launches only)
+  int flags_cap;
+};
+
+// item -> (phase, unit) of the interleaved schedule above (T units per phase, D = min(lag, T))
+__device__ __forceinline__ void decode_item(int i, int T, int D, int n_phase, int& phase, int& unit) {
+  if (n_phase == 1 || i < D) { phase = 0; unit = i; return; }
+  const int j = i - D;
+  if (j < 2 * (T - D)) { phase = j & 1; unit = (j >> 1) + (phase ? 0 : D); return; }
+  phase = 1;
+  unit = (T - D) + (j - 2 * (T - D));
+}
+
+__device__ __forceinline__ int ld_acquire(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+// Bounded wait for `want` arrivals on a unit flag (all lanes probe the same word: one transaction).
+__device__ __noinline__ bool flag_wait(const int* f, int want, int* err, int code) {
+#pragma unroll 1
+  for (uint32_t i = 0; i < kSpinLimit; ++i) {
+    if (ld_acquire(f) >= want) return true;
+    __nanosleep(64);
+  }
+  atomicExch(err, code);
+  return false;
+}
 
 // 128-position tiles per work unit: one 256-column TMEM accumulator buffer holds MT tiles of N columns.
 // (TS = TMEM columns per tile: N, or 2N in the dual layout).
@@ -258,8 +305,16 @@ __device__ __forceinline__ void issue_group(uint32_t d0, uint32_t a_lo0, uint32_
 
 template <int N, Prec P, bool Dual, int G>
 __global__ void __launch_bounds__(kTcThreads, 1)
-conv_tc_kernel(const TcConv p) {
+conv_tc_kernel(const TcJob job) {
   extern __shared__ __align__(128) unsigned char smem[];
+  const TcConv& p = job.c[0];                 // shared geometry; per-item parameters are job.c[phase]
+  const int n_phase = job.n_phase;
+  const int T = p.total_units, D = job.lag < T ? job.lag : T;
+  const int n_items = n_phase * T;
+  // Round r of the persistent loop: CTA j takes item r * grid + (j + r) % grid.  The rotation matters for fused
+  // launches: items alternate c[0] / c[1], the grid is even, and without it a CTA would see one phase only (the two
+  // phases cost differently, so half the SMs would finish early).  Items still increase with r for every CTA.
+  auto item_of = [](int r) { return r * (int)gridDim.x + (int)((blockIdx.x + (unsigned)r) % gridDim.x); };
   static_assert(!Dual || PrecTraits<P>::split, "the dual layout belongs to the split precision");
   constexpr int MT = TilesPerUnit<N, Dual>::value;
   constexpr int TS = TilesPerUnit<N, Dual>::TS;
@@ -273,11 +328,14 @@ conv_tc_kernel(const TcConv p) {
   const uint32_t a_bytes = (uint32_t)L * 32u;           // two planes
   const uint32_t stage_sz = a_bytes + (uint32_t)kWpartsMax * 9u * N * 32u;
   const int S = p.stages;
+  const int cps = p.cps;
+  const uint32_t run1 = (uint32_t)(G * MT * 128) * 16u;      // one plane of a 1x1 source's chunk (no halo)
+  const uint32_t w1_off = (uint32_t)cps * 2u * run1;          // weights of a 1x1 stage follow its cps chunk slots
   unsigned char* stage0 = smem;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)S * stage_sz);
   // bars: full[kMaxStages] | empty[kMaxStages] | acc_full[2] | acc_empty[2]
-  float* bias_s = reinterpret_cast<float*>(bars + 2 * kMaxStages + 4);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bias_s + N);
+  float* bias_s = reinterpret_cast<float*>(bars + 2 * kMaxStages + 4);       // [2][N]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bias_s + 2 * N);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + kMaxStages);
@@ -294,7 +352,7 @@ conv_tc_kernel(const TcConv p) {
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  for (int i = threadIdx.x; i < N; i += kTcThreads) bias_s[i] = p.bias[i];
+  for (int i = threadIdx.x; i < n_phase * N; i += kTcThreads) bias_s[i] = job.c[i / N].bias[i % N];
   if (warp == 4) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
                  "n"(512));
@@ -310,28 +368,55 @@ conv_tc_kernel(const TcConv p) {
     int it = 0;
     bool ok = true;
     long long w_empty = 0;
-    for (int u = blockIdx.x; u < p.total_units && ok && !(dbg & 4); u += gridDim.x) {
+    for (int r = 0, item; (item = item_of(r)) < n_items && ok && !(dbg & 4); ++r) {
+      int phase, u;
+      decode_item(item, T, D, n_phase, phase, u);
+      const TcConv& c = job.c[phase];
       const int b = u / p.units_per_image;
-      const int lo = (u - b * p.units_per_image) * G * MT * 128;   // first staged position (= q0 - halo)
-      for (int s = 0; s < p.n_src && ok; ++s) {
-        const TcSource& src = p.src[s];
+      const int lu = u - b * p.units_per_image;
+      const int lo = lu * G * MT * 128;   // first staged position (= q0 - halo)
+      if (phase == 1) {
+        // the units of c[0] whose output this unit reads must be complete (see TcJob), and their generic-proxy
+        // stores visible to the async proxy that performs the bulk copies
+        ok = flag_wait(job.flags + u, 8, p.err, 5);
+        if (ok && lu > 0) ok = flag_wait(job.flags + u - 1, 8, p.err, 5);
+        if (ok && lu < p.units_per_image - 1) ok = flag_wait(job.flags + u + 1, 8, p.err, 5);
+        if (!ok) break;
+        asm volatile("fence.proxy.async.global;" ::: "memory");
+      }
+      for (int s = 0; s < c.n_src && ok; ++s) {
+        const TcSource& src = c.src[s];
         const uint32_t w_bytes = (uint32_t)((Dual && src.kind == 1 ? 2 : 1) * src.taps) * N * 32u;
-        for (int kc = 0; kc < src.n_chunks; ++kc, ++it) {
+        // A 1x1 source has no halo and a ninth of the weights, so a stage-sized slot takes `cps` of its K-chunks:
+        // [chunk][plane][run1] activations, then [chunk] weights at w1_off.  (One chunk per stage left these
+        // sources bound by the per-stage hand-over and by load latency: 4 MMAs per 18 KB stage.)
+        const int per_stage = (src.taps == 1) ? cps : 1;
+        for (int kc = 0; kc < src.n_chunks; kc += per_stage, ++it) {
           const int st = it % S;
           const uint32_t ph = (uint32_t)(it / S) & 1u;
           ok = mbar_wait_t(empty0 + 8 * st, ph ^ 1u, p.err, 1, w_empty);
           if (!ok) break;
           const uint32_t dst = smem_u32(stage0 + (size_t)st * stage_sz);
           const uint16_t* plane = src.in + (((int64_t)b * src.planes_total + src.plane0 + 2 * kc) * HpWp + lo) * 8;
-          // a 1x1 source reads only the centre tap: its stage skips the halo on both sides
-          const uint32_t skip = (src.taps == 1) ? (uint32_t)halo * 16u : 0u;
-          const uint32_t run = (uint32_t)L * 16u - 2u * skip;
           if (dbg & 1) {
             if (elect_one()) mbar_arrive(full0 + 8 * st);
+          } else if (src.taps == 1) {
+            const int n = (src.n_chunks - kc < per_stage) ? (src.n_chunks - kc) : per_stage;
+            if (elect_one()) {
+              mbar_expect_tx(full0 + 8 * st, (uint32_t)n * (2u * run1 + w_bytes));
+              for (int j = 0; j < n; ++j) {
+                const uint16_t* pj = plane + (int64_t)2 * j * HpWp * 8 + (int64_t)halo * 8;    // centre tap only
+                bulk_g2s(dst + (uint32_t)(2 * j) * run1, pj, run1, full0 + 8 * st);
+                bulk_g2s(dst + (uint32_t)(2 * j + 1) * run1, pj + (int64_t)HpWp * 8, run1, full0 + 8 * st);
+                bulk_g2s(dst + w1_off + (uint32_t)j * w_bytes, src.w + (int64_t)(kc + j) * src.w_stride, w_bytes,
+                         full0 + 8 * st);
+              }
+            }
           } else if (elect_one()) {
+            const uint32_t run = (uint32_t)L * 16u;
             mbar_expect_tx(full0 + 8 * st, 2u * run + w_bytes);
-            bulk_g2s(dst + skip, plane + skip / 2, run, full0 + 8 * st);
-            bulk_g2s(dst + (uint32_t)L * 16u + skip, plane + (int64_t)HpWp * 8 + skip / 2, run, full0 + 8 * st);
+            bulk_g2s(dst, plane, run, full0 + 8 * st);
+            bulk_g2s(dst + run, plane + (int64_t)HpWp * 8, run, full0 + 8 * st);
             bulk_g2s(dst + a_bytes, src.w + (int64_t)kc * src.w_stride, w_bytes, full0 + 8 * st);
           }
           __syncwarp();
@@ -351,14 +436,16 @@ conv_tc_kernel(const TcConv p) {
     for (int t = 0; t < 9; ++t) tap_off[t] = (t / 3 - 1) * Wp + (t % 3 - 1);
     // descriptor low word = (LBO >> 4) << 16 | (address >> 4)
     const uint32_t a_lo_base = ((uint32_t)L & 0x3FFFu) << 16;            // LBO = L * 16 bytes
+    const uint32_t a1_lo_base = ((run1 >> 4) & 0x3FFFu) << 16;           // 1x1 stages: LBO = run1
     int k = 0;
     bool ok = true;
     long long w_acce = 0, w_full = 0;
     const bool timing = p.prof != nullptr;
     const long long t_begin = clock64();
     // total K-chunks of a unit, to recognise the last one
-    int chunks_per_unit = 0;
-    for (int s = 0; s < p.n_src; ++s) chunks_per_unit += p.src[s].n_chunks;
+    int chunks_of[2] = {0, 0};
+    for (int ph2 = 0; ph2 < n_phase; ++ph2)
+      for (int s = 0; s < job.c[ph2].n_src; ++s) chunks_of[ph2] += job.c[ph2].src[s].n_chunks;
     // The tensor pipe accepts only a couple of MMAs ahead of execution, so every cycle this loop spends between two
     // bursts of MMAs is a pipe bubble: the ring position is carried incrementally (no division), the leader lane is
     // elected once, waits probe inline, and a stage costs one commit.
@@ -367,22 +454,29 @@ conv_tc_kernel(const TcConv p) {
     int st = 0;
     uint32_t ph = 0, a0 = stage_base;
     bool ready = false;            // the full barrier of the stage about to be consumed was already seen complete
-    for (int u = blockIdx.x; u < p.total_units && ok; u += gridDim.x, ++k) {
+    for (int item; (item = item_of(k)) < n_items && ok; ++k) {
+      int phase, u;
+      decode_item(item, T, D, n_phase, phase, u);
+      const TcConv& c = job.c[phase];
+      const int chunks_per_unit = chunks_of[phase];
       // G = 1: this unit owns buffer k & 1 (tiles split between the warps); G = 2: warp `me` owns buffer `me`
       const int buf = (G == 1) ? (k & 1) : me;
       const uint32_t e_parity = (G == 1) ? ((((uint32_t)k >> 1) & 1u) ^ 1u) : (((uint32_t)k & 1u) ^ 1u);
       const uint32_t d_unit = tmem_base + (uint32_t)(buf * kAccCols) + (G == 1 ? (uint32_t)(me * MTW * TS) : 0u);
       const uint32_t a_tile0 = (uint32_t)((G == 1 ? me * MTW : me * MT) * 128);     // first position of my tiles
       int c_in_unit = 0;
-      for (int s = 0; s < p.n_src && ok; ++s) {
-        const TcSource& src = p.src[s];
+      for (int s = 0; s < c.n_src && ok; ++s) {
+        const TcSource& src = c.src[s];
         // per-source MMA shape: the dual product writes 2N columns, a correction-only source the upper N
         const bool dual_src = Dual && src.kind == 1;
         const uint32_t idesc = dual_src ? idesc_2n : idesc_n;
         const uint32_t col0 = (Dual && src.kind == 2) ? (uint32_t)N : 0u;
         const uint32_t b_lo_base = ((uint32_t)(dual_src ? 2 * N : N) & 0x3FFFu) << 16;   // LBO = rows * 16 bytes
         const int taps = src.taps, n_chunks = src.n_chunks;
-        for (int kc = 0; kc < n_chunks && ok; ++kc, ++c_in_unit) {
+        const int per_stage = (taps == 1) ? cps : 1;
+        const uint32_t w_bytes16 = (uint32_t)((dual_src ? 2 : 1) * N * 2);             // 1x1 chunk weights >> 4
+        for (int kc = 0; kc < n_chunks && ok; kc += per_stage) {
+          const int n = (n_chunks - kc < per_stage) ? (n_chunks - kc) : per_stage;
           if (!ready && !(dbg & 4)) ok = mbar_wait_fast(full0 + 8 * st, ph, p.err, 2, timing, w_full);
           if (!ok) break;
           if (c_in_unit == 0) {                            // the epilogue must have drained the buffer
@@ -390,17 +484,30 @@ conv_tc_kernel(const TcConv p) {
             if (!ok) break;
           }
           tc_fence_after();
-          const uint32_t a_lo0 = (a_lo_base | ((a0 >> 4) + (uint32_t)halo)) + a_tile0;   // centre tap, my first tile
-          const uint32_t b_lo0 = b_lo_base | ((a0 + a_bytes) >> 4);
           if (leader) {
-            const uint32_t accumulate = c_in_unit > 0 ? 1u : 0u;
-            if (dbg & 8) { if (a_lo0 == 0xdeadbeefu) p.err[1] = (int)(d_unit + b_lo0 + idesc); }   // issue nothing
-            else if (dual_src) issue_group<MTW, TS, 2 * N>(d_unit + col0, a_lo0, b_lo0, idesc, taps, tap_off, accumulate);
-            else issue_group<MTW, TS, N>(d_unit + col0, a_lo0, b_lo0, idesc, taps, tap_off, accumulate);
-            if (c_in_unit == chunks_per_unit - 1) tc_commit(accf0 + 8 * buf);   // my tiles of this unit are complete
+            if (dbg & 8) { if (a0 == 0xdeadbeefu) p.err[1] = (int)(d_unit + idesc); }   // issue nothing
+            else if (taps == 1) {
+              // compact 1x1 stage: chunk j at a0 + 2 j run1 (plane stride run1), its weights at a0 + w1_off + j w_bytes
+              const uint32_t a1 = (a1_lo_base | (a0 >> 4)) + a_tile0;
+              const uint32_t b1 = b_lo_base | ((a0 + w1_off) >> 4);
+              for (int j = 0; j < n; ++j) {
+                const uint32_t accumulate = (c_in_unit + j) > 0 ? 1u : 0u;
+                const uint32_t aj = a1 + (uint32_t)j * (2u * run1 >> 4), bj = b1 + (uint32_t)j * w_bytes16;
+                if (dual_src) issue_group<MTW, TS, 2 * N>(d_unit + col0, aj, bj, idesc, 1, tap_off, accumulate);
+                else issue_group<MTW, TS, N>(d_unit + col0, aj, bj, idesc, 1, tap_off, accumulate);
+              }
+            } else {
+              const uint32_t accumulate = c_in_unit > 0 ? 1u : 0u;
+              const uint32_t a_lo0 = (a_lo_base | ((a0 >> 4) + (uint32_t)halo)) + a_tile0;   // centre tap, my first tile
+              const uint32_t b_lo0 = b_lo_base | ((a0 + a_bytes) >> 4);
+              if (dual_src) issue_group<MTW, TS, 2 * N>(d_unit + col0, a_lo0, b_lo0, idesc, 9, tap_off, accumulate);
+              else issue_group<MTW, TS, N>(d_unit + col0, a_lo0, b_lo0, idesc, 9, tap_off, accumulate);
+            }
+            if (c_in_unit + n == chunks_per_unit) tc_commit(accf0 + 8 * buf);   // my tiles of this unit are complete
             if (!(dbg & 4)) tc_commit(empty0 + 8 * st);   // my reads of the stage retire with these MMAs
           }
           __syncwarp();
+          c_in_unit += n;
           a0 += stage_sz;
           if (++st == S) { st = 0; ph ^= 1u; a0 = stage_base; }
           // probe the next stage now: the answer travels while this iteration winds down
@@ -420,16 +527,20 @@ conv_tc_kernel(const TcConv p) {
     const int quad = warp & 3;                 // TMEM lane quadrant this warp may read
     const int tile_par = warp >= 6 ? 1 : 0;    // the two warps of a quadrant take alternate tiles
     const int Wp2 = 2 * p.W + 2;
-    const float inv_scale = p.inv_scale;
-    const int64_t out_plane_stride = p.upsample ? (int64_t)(2 * p.H + 2) * Wp2 * 8 : (int64_t)HpWp * 8;
     int k = 0;
     bool ok = true;
     bool out_of_range = false;     // fp16 operand modes: an activation left the fp16 range (it was saturated)
     long long w_accf = 0;
     const long long t_begin = clock64();
-    for (int u = blockIdx.x; u < p.total_units && ok; u += gridDim.x, ++k) {
+    for (int item; (item = item_of(k)) < n_items && ok; ++k) {
+      int phase, u;
+      decode_item(item, T, D, n_phase, phase, u);
+      const TcConv& c = job.c[phase];
+      const float inv_scale = c.inv_scale;
+      const float* bias_p = bias_s + phase * N;
+      const int64_t out_plane_stride = c.upsample ? (int64_t)(2 * p.H + 2) * Wp2 * 8 : (int64_t)HpWp * 8;
       const int b = u / p.units_per_image;
-      const int64_t img_off = ((int64_t)b * p.out_planes_total + p.out_plane0) * out_plane_stride;
+      const int64_t img_off = ((int64_t)b * c.out_planes_total + c.out_plane0) * out_plane_stride;
      for (int g = 0; g < G && ok; ++g) {
       const int buf = (G == 1) ? (k & 1) : g;
       const uint32_t f_parity = (G == 1) ? (((uint32_t)k >> 1) & 1u) : ((uint32_t)k & 1u);
@@ -458,9 +569,9 @@ conv_tc_kernel(const TcConv p) {
             uint32_t hw[4], lw[4];
 #pragma unroll
             for (int h = 0; h < 4; ++h) {
-              float f0 = fmaf(__uint_as_float(v[g * 8 + 2 * h]), inv_scale, bias_s[n0 + g * 8 + 2 * h]);
-              float f1 = fmaf(__uint_as_float(v[g * 8 + 2 * h + 1]), inv_scale, bias_s[n0 + g * 8 + 2 * h + 1]);
-              if (p.relu) { f0 = fmaxf(f0, 0.f); f1 = fmaxf(f1, 0.f); }
+              float f0 = fmaf(__uint_as_float(v[g * 8 + 2 * h]), inv_scale, bias_p[n0 + g * 8 + 2 * h]);
+              float f1 = fmaf(__uint_as_float(v[g * 8 + 2 * h + 1]), inv_scale, bias_p[n0 + g * 8 + 2 * h + 1]);
+              if (c.relu) { f0 = fmaxf(f0, 0.f); f1 = fmaxf(f1, 0.f); }
               if (!interior) { f0 = 0.f; f1 = 0.f; }
               if constexpr (PrecTraits<P>::fmt == 0) out_of_range |= (fmaxf(fabsf(f0), fabsf(f1)) > 65504.f);
               hw[h] = pack_hi<P>(f0, f1);
@@ -471,21 +582,21 @@ conv_tc_kernel(const TcConv p) {
             const int64_t plane_off = img_off + (int64_t)(n0 / 8 + g) * out_plane_stride;
             if (dbg & 2) {
               if (ph.x == 0x12345678u && lw[0] == 0x9abcdef0u) p.err[1] = 1;      // keep the values alive
-            } else if (!p.upsample) {
+            } else if (!c.upsample) {
               if (in_tensor) {
-                *reinterpret_cast<uint4*>(p.out + plane_off + (int64_t)pos * 8) = ph;
+                *reinterpret_cast<uint4*>(c.out + plane_off + (int64_t)pos * 8) = ph;
                 if constexpr (kSplit)
-                  *reinterpret_cast<uint4*>(p.out_lo + plane_off + (int64_t)pos * 8) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+                  *reinterpret_cast<uint4*>(c.out_lo + plane_off + (int64_t)pos * 8) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
               }
             } else if (interior) {
-              uint16_t* o = p.out + plane_off + up * 8;
+              uint16_t* o = c.out + plane_off + up * 8;
               *reinterpret_cast<uint4*>(o) = ph;
               *reinterpret_cast<uint4*>(o + 8) = ph;
               *reinterpret_cast<uint4*>(o + (int64_t)Wp2 * 8) = ph;
               *reinterpret_cast<uint4*>(o + (int64_t)Wp2 * 8 + 8) = ph;
               if constexpr (kSplit) {
                 const uint4 pl = make_uint4(lw[0], lw[1], lw[2], lw[3]);
-                uint16_t* ol = p.out_lo + plane_off + up * 8;
+                uint16_t* ol = c.out_lo + plane_off + up * 8;
                 *reinterpret_cast<uint4*>(ol) = pl;
                 *reinterpret_cast<uint4*>(ol + 8) = pl;
                 *reinterpret_cast<uint4*>(ol + (int64_t)Wp2 * 8) = pl;
@@ -500,6 +611,13 @@ conv_tc_kernel(const TcConv p) {
       __syncwarp();
       if (lane == 0) mbar_arrive(acce0 + 8 * buf);
      }
+      if (n_phase == 2 && phase == 0) {
+        // publish this warp's share of the unit to the c[1] producers of other CTAs (release at gpu scope)
+        asm volatile("fence.proxy.async.global;" ::: "memory");
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) atomicAdd(job.flags + u, 1);
+      }
     }
     if (out_of_range) p.err[2] = 1;
     if (p.prof && threadIdx.x == 0) {

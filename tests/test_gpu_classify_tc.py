@@ -152,3 +152,31 @@ def test_fp16_range_overflow_is_reported(sd_seed0, clip60):
     assert np.isfinite(lg).all()
     eng.check_health()
     eng.close()
+
+
+def test_fused_resblock_launch_is_bit_identical(sd_seed0, clip60, monkeypatch):
+    """SS_TC_FUSE=1 runs both convolutions of every ResBlock in one persistent launch (conv2 trailing conv1 behind
+    per-unit completion flags, conv_tc_kernel.cuh:TcJob).  The schedule must not change a bit, for lags below and
+    above the unit count (lag >= units degenerates to conv1 entirely before conv2) and for one-chunk 1x1 stages."""
+    import os
+    from oracle import postproc as pp
+    from softspoken_b200.engine import Engine
+    g = load_golden("model_seed0.npz")
+    padded = torch.from_numpy(pp.pad_audio(clip60)).cuda()
+    for mode in ("f16x3", "bf16"):
+        eng = Engine(sd_seed0, 0, max_batch=48, mode=mode)
+        mel = eng.features(padded, torch.from_numpy(g["starts"][:48]))
+        monkeypatch.delenv("SS_TC_FUSE", raising=False)
+        base = eng.classify(mel)
+        for env in ({"SS_TC_FUSE": "1"}, {"SS_TC_FUSE": "1", "SS_TC_LAG": "3"}, {"SS_TC_FUSE": "1", "SS_TC_LAG": "100000"},
+                    {"SS_TC_CPS": "1"}):
+            for k in ("SS_TC_FUSE", "SS_TC_LAG"):
+                monkeypatch.delenv(k, raising=False)
+            for k, v in env.items():
+                monkeypatch.setenv(k, v)
+            got = eng.classify(mel)
+            eng.check_health()
+            assert torch.equal(base, got), (mode, env)
+        for k in ("SS_TC_FUSE", "SS_TC_LAG", "SS_TC_CPS"):
+            monkeypatch.delenv(k, raising=False)
+        eng.close()

@@ -1,4 +1,5 @@
-"""Per-role cycle breakdown of the persistent tcgen05 conv kernel, one launch at a time (debug tool)."""
+"""Per-role cycle breakdown of the persistent tcgen05 conv kernel, one launch at a time (debug tool; the launch
+names assume one launch per convolution, i.e. SS_TC_FUSE unset or 0)."""
 import ctypes as C
 import json
 import os

@@ -151,6 +151,40 @@ SS_API int ss_detect_host(ss_ctx* ctx, const float* pcm_host, int64_t n_samples,
 SS_API int ss_detect_host_batch(ss_ctx* ctx, int n_clips, const float* const* pcm_host, const int64_t* n_samples,
                                 int mode, int32_t* regions_host, int cap, int* n_regions);
 
+/* ---- PCM_16 sample path (the decode of `voice_activity.load_audio`,
+ * voice_activity.py:32-69, and the encode of `sf.write`, silencer_ui.py:998, moved onto the device) -------------
+ * The `_pcm16` variants of the three file-level calls take the int16 samples of a mono PCM_16 file as stored and
+ * decode them inside K1 exactly as libsndfile's float read does (sample / 32768, exact in float32): results are
+ * bit-identical to the float32 calls on `pcm / 32768`, with half the bytes crossing PCIe and HBM. */
+SS_API int ss_detect_device_pcm16(ss_ctx* ctx, const int16_t* pcm_dev, int64_t n_samples, int mode,
+                                  int32_t* regions_dev, int32_t* n_regions_dev, int cap, float* logits_out_dev,
+                                  void* stream);
+SS_API int ss_detect_host_pcm16(ss_ctx* ctx, const int16_t* pcm_host, int64_t n_samples, int mode,
+                                int32_t* regions_host, int cap, int* n_regions, float* logits_host);
+SS_API int ss_detect_host_batch_pcm16(ss_ctx* ctx, int n_clips, const int16_t* const* pcm_host,
+                                      const int64_t* n_samples, int mode, int32_t* regions_host, int cap,
+                                      int* n_regions);
+
+/* `sf.read(dtype='float32')` + `librosa.to_mono` (voice_activity.py:37,61-62) for interleaved PCM_16 frames
+ * [n_frames][channels] -> float32 mono [n_frames]: sample / 32768, float32 sum over channels (exact for PCM_16),
+ * one float32 division by the channel count. */
+SS_API int ss_decode_pcm16(ss_ctx* ctx, const int16_t* interleaved_dev, int64_t n_frames, int channels,
+                           float* mono_dev, void* stream);
+
+/* `sf.write` float32 -> PCM_16 (silencer_ui.py:998): short(lrintf(x * 32767.0f)) as libsndfile's f2les_array with
+ * normalisation on; out-of-range samples saturate.  Restated from libsndfile's source, not pinned by a golden
+ * vector (the library is not in the build image).  Both buffers 16-byte aligned. */
+SS_API int ss_encode_pcm16(ss_ctx* ctx, const float* src_dev, int64_t n_elems, int16_t* dst_dev, void* stream);
+
+/* K7 on int16 samples: "Silence Voices" for a PCM_16 file that never leaves its storage format.  Zeroes the
+ * element ranges like ss_silence; with requantize != 0 every sample first goes through the reference's
+ * read -> write round trip, encode(decode(k)) (see ss_encode_pcm16), so that the buffer equals what
+ * `sf.write(librosa.load(...))` would store.  The _host variant streams a host buffer through the device. */
+SS_API int ss_silence_pcm16(ss_ctx* ctx, int16_t* pcm_dev, int64_t n_elems, const ss_interval* intervals_dev,
+                            int n_intervals, int requantize, void* stream);
+SS_API int ss_silence_pcm16_host(ss_ctx* ctx, int16_t* pcm_host, int64_t n_elems, const ss_interval* intervals_host,
+                                 int n_intervals, int requantize);
+
 /* Device-level entry points (ss_classify, ss_detect_device) only enqueue work, so they cannot report what the
  * kernels found: this call synchronises `stream` and returns SS_E_CUDA if a tcgen05 pipeline wait timed out or
  * SS_E_RANGE if an fp16-operand mode saturated an activation since the last check (the host-level calls

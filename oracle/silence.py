@@ -58,6 +58,35 @@ def group_rows(file_path: Sequence[str], file_name: Sequence[str], start: Sequen
 
 def float_to_pcm16(a: np.ndarray) -> np.ndarray:
     """float32 -> int16 as libsndfile writes a PCM_16 WAV from float input with its default
-    (non-clipping) normalisation: `lrint(x * 32767)`... UNPINNED: libsndfile is absent from this
-    image, so byte parity of the written wav is NOT claimed; float buffers are."""
-    return np.clip(np.rint(a.astype(np.float64) * 32767.0), -32768, 32767).astype(np.int16)
+    (non-clipping) normalisation, pcm.c:f2les_array: `lrintf(src[i] * normfact)` with `normfact = 1.0 * 0x7FFF`
+    held in a float (so the product is a float32 product), round-half-even.  Saturated here where C would wrap.
+    UNPINNED: libsndfile is absent from this image, so byte parity of the written wav is NOT claimed
+    (SURVEY §8c); float buffers are."""
+    y = np.rint(np.asarray(a, np.float32) * np.float32(32767.0))
+    return np.clip(y, -32768, 32767).astype(np.int16)
+
+
+def pcm16_to_float(pcm: np.ndarray) -> np.ndarray:
+    """int16 -> float32 as `sf.read(dtype='float32')` (libsndfile pcm.c:s2f_array, normfact 1/0x8000)."""
+    return pcm.astype(np.float32) / np.float32(32768.0)
+
+
+def load_audio_pcm16(frames: np.ndarray) -> np.ndarray:
+    """`voice_activity.load_audio` for PCM_16 frames `(n,)` or `(n, C)` at 22,050 Hz
+    (root/code/backend/voice_activity.py:37,61-62): float32 read, `.T`, `librosa.to_mono` = `np.mean(y, axis=0)`."""
+    f1 = pcm16_to_float(np.asarray(frames))
+    data = f1.T
+    if data.ndim > 1:
+        data = np.mean(data, axis=tuple(range(data.ndim - 1)))      # librosa.to_mono
+    return data
+
+
+def silence_pcm16(frames: np.ndarray, sr: int, rows: Sequence[Tuple[float, float]], requantize: bool = True) -> np.ndarray:
+    """PCM_16 file in, PCM_16 file out through the reference's float path (silencer_ui.py:959-998):
+    `librosa.load(sr=None, mono=False)` -> zero the rows -> `sf.write(audio.T)`.  `(n,)` or `(n, C)` int16 frames
+    -> same shape.  With `requantize=False` the untouched samples are kept as stored (identity round trip)."""
+    fr = np.asarray(frames)
+    audio = pcm16_to_float(fr).T                                   # (C, n) or (n,)
+    out = silence_buffer(audio, sr, rows)                          # (C, n)
+    enc = float_to_pcm16(out.T) if requantize else np.where(out.T == 0.0, 0, fr.reshape(out.T.shape)).astype(np.int16)
+    return enc.reshape(fr.shape)

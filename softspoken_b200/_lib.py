@@ -61,6 +61,13 @@ _SIGNATURES = {
     "ss_detect_device": (_int, [_p, _p, _i64, _int, _p, _p, _int, _p, _p]),
     "ss_detect_host": (_int, [_p, _p, _i64, _int, _p, _int, C.POINTER(_int), _p]),
     "ss_detect_host_batch": (_int, [_p, _int, _p, _p, _int, _p, _int, _p]),
+    "ss_detect_device_pcm16": (_int, [_p, _p, _i64, _int, _p, _p, _int, _p, _p]),
+    "ss_detect_host_pcm16": (_int, [_p, _p, _i64, _int, _p, _int, C.POINTER(_int), _p]),
+    "ss_detect_host_batch_pcm16": (_int, [_p, _int, _p, _p, _int, _p, _int, _p]),
+    "ss_decode_pcm16": (_int, [_p, _p, _i64, _int, _p, _p]),
+    "ss_encode_pcm16": (_int, [_p, _p, _i64, _p, _p]),
+    "ss_silence_pcm16": (_int, [_p, _p, _i64, _p, _int, _int, _p]),
+    "ss_silence_pcm16_host": (_int, [_p, _p, _i64, _p, _int, _int]),
     "ss_check_health": (_int, [_p, _p]),
     "ss_silence_host": (_int, [_p, _p, _i64, _p, _int]),
     "ss_debug_tc_profile": (_int, [_p, _int, _p]),

@@ -37,6 +37,16 @@ def load_mono_22050(path: str) -> np.ndarray:
     return np.ascontiguousarray(x, dtype=np.float32)
 
 
+def load_native_22050(path: str) -> np.ndarray:
+    """Like `load_mono_22050`, but a mono PCM_16 file is returned as its int16 samples (the library decodes them on
+    the device: `ss_detect_host_batch_pcm16`), so the host never builds the float32 copy and the upload is half the
+    size.  Detections are bit-identical to the float32 route (tests/test_gpu_pcm16.py)."""
+    got = wavio.read_wav_pcm16(path)
+    if got is not None and got[0].ndim == 1 and got[1] == spec.SAMPLE_RATE:
+        return np.ascontiguousarray(got[0])
+    return load_mono_22050(path)
+
+
 def detect_corpus(files: Sequence[str], detect_batch: Callable[[List[np.ndarray]], List[np.ndarray]],
                   load: Callable[[str], np.ndarray] = load_mono_22050, durations: Optional[Sequence[float]] = None,
                   group_size: int = 8, device: Optional[torch.device] = None, next_id: int = 1):
@@ -105,7 +115,7 @@ def main(argv=None) -> int:
         print("No checkpoint found. Starting training from scratch.")     # NNDetector.py:52
         sd = checkpoint.synthetic_state_dict(0)
     eng = Engine(sd, local, max_batch=args.max_batch, **({"mode": args.mode} if args.mode else {}))
-    rows = detect_corpus(files, eng.detect_host_batch, device=device)
+    rows = detect_corpus(files, eng.detect_host_batch, load=load_native_22050, device=device)
     if rows is not None:
         with open(args.out_csv, "w", newline="") as f:
             f.write(csv_text(rows))

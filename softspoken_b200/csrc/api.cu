@@ -172,11 +172,11 @@ int64_t timeline_bins(int64_t n_padded) {
 }
 
 // Windows [w0, w1) of the virtual padded clip -> logits[w0..w1) (features then classifier).
-int run_windows(ss_ctx* ctx, const float* pcm, int64_t valid_begin, int64_t valid_end, int64_t offset, int64_t w0,
-                int64_t w1, int mode, float* logits_all, cudaStream_t st) {
+int run_windows(ss_ctx* ctx, const void* pcm, int fmt, int64_t valid_begin, int64_t valid_end, int64_t offset,
+                int64_t w0, int64_t w1, int mode, float* logits_all, cudaStream_t st) {
   for (int64_t c0 = w0; c0 < w1; c0 += ctx->chunk_windows) {
     const int n = (int)((w1 - c0 < ctx->chunk_windows) ? (w1 - c0) : ctx->chunk_windows);
-    int rc = launch_features_virtual(ctx, pcm, valid_begin, valid_end, offset, nullptr, c0, n, ctx->file_mel, st);
+    int rc = launch_features_virtual(ctx, pcm, fmt, valid_begin, valid_end, offset, nullptr, c0, n, ctx->file_mel, st);
     if (rc) return rc;
     float* lg = logits_all + c0 * kFrames;
     if (mode == SS_MODE_FP32) rc = classify_fp32(ctx, ctx->file_mel, n, lg, nullptr, st);
@@ -482,8 +482,9 @@ static int detect_tail(ss_ctx* ctx, int64_t n_samples, int64_t W, int32_t* regio
                         ctx->scan_tmp, ctx->scan_tmp_len, st);
 }
 
-int ss_detect_device(ss_ctx* ctx, const float* pcm_dev, int64_t n_samples, int mode, int32_t* regions_dev,
-                     int32_t* n_regions_dev, int cap, float* logits_out_dev, void* stream) {
+static int detect_device_impl(ss_ctx* ctx, const void* pcm_dev, int fmt, int64_t n_samples, int mode,
+                              int32_t* regions_dev, int32_t* n_regions_dev, int cap, float* logits_out_dev,
+                              void* stream) {
   int rc = check_ctx(ctx);
   if (rc) return rc;
   SS_REQUIRE(n_samples >= 0 && cap >= 0 && regions_dev && n_regions_dev, SS_E_ARG, "bad ss_detect_device arguments");
@@ -495,7 +496,8 @@ int ss_detect_device(ss_ctx* ctx, const float* pcm_dev, int64_t n_samples, int m
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int64_t W = plan_windows(n_samples);
   // virtual padding (worker.py:58-62): padded index [66150, 66150 + n) -> pcm[idx - 66150], zeros elsewhere
-  rc = run_windows(ctx, pcm_dev, kPadSamples, kPadSamples + n_samples, kPadSamples, 0, W, mode, ctx->file_logits, st);
+  rc = run_windows(ctx, pcm_dev, fmt, kPadSamples, kPadSamples + n_samples, kPadSamples, 0, W, mode, ctx->file_logits,
+                   st);
   if (rc) return rc;
   rc = detect_tail(ctx, n_samples, W, regions_dev, n_regions_dev, cap, st);
   if (rc) return rc;
@@ -505,10 +507,23 @@ int ss_detect_device(ss_ctx* ctx, const float* pcm_dev, int64_t n_samples, int m
   return SS_OK;
 }
 
+int ss_detect_device(ss_ctx* ctx, const float* pcm_dev, int64_t n_samples, int mode, int32_t* regions_dev,
+                     int32_t* n_regions_dev, int cap, float* logits_out_dev, void* stream) {
+  return detect_device_impl(ctx, pcm_dev, kSampleF32, n_samples, mode, regions_dev, n_regions_dev, cap, logits_out_dev,
+                            stream);
+}
+
+int ss_detect_device_pcm16(ss_ctx* ctx, const int16_t* pcm_dev, int64_t n_samples, int mode, int32_t* regions_dev,
+                           int32_t* n_regions_dev, int cap, float* logits_out_dev, void* stream) {
+  return detect_device_impl(ctx, pcm_dev, kSampleS16, n_samples, mode, regions_dev, n_regions_dev, cap, logits_out_dev,
+                            stream);
+}
+
 // Enqueue one host clip: chunked H2D on the copy stream (double-buffered staging), K1-K3 per chunk and K5/K6 on the
 // compute stream, regions left in `regions_dev` / `nreg_dev`.  Does not synchronise.
-static int enqueue_detect_host(ss_ctx* ctx, const float* pcm_host, int64_t n_samples, int mode, int32_t* regions_dev,
-                               int32_t* nreg_dev, int cap) {
+static int enqueue_detect_host(ss_ctx* ctx, const void* pcm_host, int fmt, int64_t n_samples, int mode,
+                               int32_t* regions_dev, int32_t* nreg_dev, int cap) {
+  const size_t esz = (fmt == kSampleS16) ? sizeof(int16_t) : sizeof(float);   // the staging buffers hold either type
   cudaStream_t cs = ctx->compute_stream, xs = ctx->copy_stream;
   const int64_t W = plan_windows(n_samples);
   int rc;
@@ -524,11 +539,11 @@ static int enqueue_detect_host(ss_ctx* ctx, const float* pcm_host, int64_t n_sam
     if (s1 < s0) s1 = s0;
     SS_CUDA_CHECK(cudaStreamWaitEvent(xs, ctx->ev_consumed[buf], 0));   // staging buffer free again
     if (s1 > s0)
-      SS_CUDA_CHECK(cudaMemcpyAsync(ctx->stage_buf[buf], pcm_host + s0, (size_t)(s1 - s0) * sizeof(float),
-                                    cudaMemcpyHostToDevice, xs));
+      SS_CUDA_CHECK(cudaMemcpyAsync(ctx->stage_buf[buf], static_cast<const char*>(pcm_host) + (size_t)s0 * esz,
+                                    (size_t)(s1 - s0) * esz, cudaMemcpyHostToDevice, xs));
     SS_CUDA_CHECK(cudaEventRecord(ctx->ev_copied[buf], xs));
     SS_CUDA_CHECK(cudaStreamWaitEvent(cs, ctx->ev_copied[buf], 0));
-    rc = run_windows(ctx, ctx->stage_buf[buf], kPadSamples + s0, kPadSamples + s1, kPadSamples + s0, w0, w1, mode,
+    rc = run_windows(ctx, ctx->stage_buf[buf], fmt, kPadSamples + s0, kPadSamples + s1, kPadSamples + s0, w0, w1, mode,
                      ctx->file_logits, cs);
     if (rc) return rc;
     SS_CUDA_CHECK(cudaEventRecord(ctx->ev_consumed[buf], cs));
@@ -548,8 +563,8 @@ static int check_tc_health(ss_ctx* ctx, int mode, cudaStream_t cs) {
   return SS_OK;
 }
 
-int ss_detect_host(ss_ctx* ctx, const float* pcm_host, int64_t n_samples, int mode, int32_t* regions_host, int cap,
-                   int* n_regions, float* logits_host) {
+static int detect_host_impl(ss_ctx* ctx, const void* pcm_host, int fmt, int64_t n_samples, int mode,
+                            int32_t* regions_host, int cap, int* n_regions, float* logits_host) {
   int rc = check_ctx(ctx);
   if (rc) return rc;
   SS_REQUIRE(n_samples >= 0 && cap >= 0 && n_regions && (regions_host || cap == 0), SS_E_ARG,
@@ -561,7 +576,7 @@ int ss_detect_host(ss_ctx* ctx, const float* pcm_host, int64_t n_samples, int mo
   SS_REQUIRE(valid_mode(mode), SS_E_ARG, "unknown classifier mode %d", mode);
   cudaStream_t cs = ctx->compute_stream;
   const int64_t W = plan_windows(n_samples);
-  rc = enqueue_detect_host(ctx, pcm_host, n_samples, mode, ctx->file_regions, ctx->file_nreg, cap);
+  rc = enqueue_detect_host(ctx, pcm_host, fmt, n_samples, mode, ctx->file_regions, ctx->file_nreg, cap);
   if (rc) return rc;
   int32_t nreg = 0;
   SS_CUDA_CHECK(cudaMemcpyAsync(&nreg, ctx->file_nreg, sizeof(int32_t), cudaMemcpyDeviceToHost, cs));
@@ -579,8 +594,18 @@ int ss_detect_host(ss_ctx* ctx, const float* pcm_host, int64_t n_samples, int mo
   return SS_OK;
 }
 
-int ss_detect_host_batch(ss_ctx* ctx, int n_clips, const float* const* pcm_host, const int64_t* n_samples, int mode,
-                         int32_t* regions_host, int cap, int* n_regions) {
+int ss_detect_host(ss_ctx* ctx, const float* pcm_host, int64_t n_samples, int mode, int32_t* regions_host, int cap,
+                   int* n_regions, float* logits_host) {
+  return detect_host_impl(ctx, pcm_host, kSampleF32, n_samples, mode, regions_host, cap, n_regions, logits_host);
+}
+
+int ss_detect_host_pcm16(ss_ctx* ctx, const int16_t* pcm_host, int64_t n_samples, int mode, int32_t* regions_host,
+                         int cap, int* n_regions, float* logits_host) {
+  return detect_host_impl(ctx, pcm_host, kSampleS16, n_samples, mode, regions_host, cap, n_regions, logits_host);
+}
+
+static int detect_host_batch_impl(ss_ctx* ctx, int n_clips, const void* const* pcm_host, int fmt,
+                                  const int64_t* n_samples, int mode, int32_t* regions_host, int cap, int* n_regions) {
   int rc = check_ctx(ctx);
   if (rc) return rc;
   SS_REQUIRE(n_clips >= 0 && cap >= 0 && (n_clips == 0 || (pcm_host && n_samples && n_regions)) &&
@@ -602,7 +627,7 @@ int ss_detect_host_batch(ss_ctx* ctx, int n_clips, const float* const* pcm_host,
       const int slot = i - g0;
       int32_t* reg_dev = ctx->file_regions + (size_t)slot * slot_ints;
       int32_t* host_slot = ctx->slot_host + (size_t)slot * (slot_ints + 1);
-      rc = enqueue_detect_host(ctx, pcm_host[i], n_samples[i], mode, reg_dev, ctx->slot_nreg + slot, cap);
+      rc = enqueue_detect_host(ctx, pcm_host[i], fmt, n_samples[i], mode, reg_dev, ctx->slot_nreg + slot, cap);
       if (rc) return rc;
       SS_CUDA_CHECK(cudaMemcpyAsync(host_slot, ctx->slot_nreg + slot, sizeof(int32_t), cudaMemcpyDeviceToHost, cs));
       if (cap > 0)
@@ -618,6 +643,75 @@ int ss_detect_host_batch(ss_ctx* ctx, int n_clips, const float* const* pcm_host,
       if (ncopy > 0) memcpy(regions_host + (size_t)i * cap * 2, host_slot + 1, (size_t)ncopy * 2 * sizeof(int32_t));
     }
   }
+  return SS_OK;
+}
+
+int ss_detect_host_batch(ss_ctx* ctx, int n_clips, const float* const* pcm_host, const int64_t* n_samples, int mode,
+                         int32_t* regions_host, int cap, int* n_regions) {
+  return detect_host_batch_impl(ctx, n_clips, reinterpret_cast<const void* const*>(pcm_host), kSampleF32, n_samples,
+                                mode, regions_host, cap, n_regions);
+}
+
+int ss_detect_host_batch_pcm16(ss_ctx* ctx, int n_clips, const int16_t* const* pcm_host, const int64_t* n_samples,
+                               int mode, int32_t* regions_host, int cap, int* n_regions) {
+  return detect_host_batch_impl(ctx, n_clips, reinterpret_cast<const void* const*>(pcm_host), kSampleS16, n_samples,
+                                mode, regions_host, cap, n_regions);
+}
+
+int ss_decode_pcm16(ss_ctx* ctx, const int16_t* interleaved_dev, int64_t n_frames, int channels, float* mono_dev,
+                    void* stream) {
+  int rc = check_ctx(ctx);
+  if (rc) return rc;
+  SS_REQUIRE(n_frames >= 0 && channels >= 1 && channels <= 256, SS_E_ARG, "bad ss_decode_pcm16 arguments (%lld frames, %d channels)",
+             (long long)n_frames, channels);
+  SS_REQUIRE((interleaved_dev && mono_dev) || n_frames == 0, SS_E_ARG, "null pointer");
+  return launch_decode_pcm16(interleaved_dev, n_frames, channels, mono_dev, static_cast<cudaStream_t>(stream));
+}
+
+int ss_encode_pcm16(ss_ctx* ctx, const float* src_dev, int64_t n_elems, int16_t* dst_dev, void* stream) {
+  int rc = check_ctx(ctx);
+  if (rc) return rc;
+  SS_REQUIRE(n_elems >= 0 && ((src_dev && dst_dev) || n_elems == 0), SS_E_ARG, "bad ss_encode_pcm16 arguments");
+  return launch_encode_pcm16(src_dev, n_elems, dst_dev, static_cast<cudaStream_t>(stream));
+}
+
+int ss_silence_pcm16(ss_ctx* ctx, int16_t* pcm_dev, int64_t n_elems, const ss_interval* intervals_dev, int n_intervals,
+                     int requantize, void* stream) {
+  int rc = check_ctx(ctx);
+  if (rc) return rc;
+  SS_REQUIRE(n_elems >= 0 && n_intervals >= 0, SS_E_ARG, "negative size");
+  if (n_elems == 0) return SS_OK;
+  SS_REQUIRE(pcm_dev && (intervals_dev || n_intervals == 0), SS_E_ARG, "null pointer");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (requantize && (rc = launch_requant_pcm16(pcm_dev, n_elems, st))) return rc;
+  return launch_silence_s16(pcm_dev, n_elems, 0, intervals_dev, n_intervals, st);
+}
+
+int ss_silence_pcm16_host(ss_ctx* ctx, int16_t* pcm_host, int64_t n_elems, const ss_interval* intervals_host,
+                          int n_intervals, int requantize) {
+  int rc = check_ctx(ctx);
+  if (rc) return rc;
+  SS_REQUIRE(n_elems >= 0 && n_intervals >= 0, SS_E_ARG, "negative size");
+  if (n_elems == 0 || (n_intervals == 0 && !requantize)) return SS_OK;
+  SS_REQUIRE(pcm_host && (intervals_host || n_intervals == 0), SS_E_ARG, "null pointer");
+  SS_REQUIRE(ctx->intervals, SS_E_CAPACITY, "call ss_ctx_reserve before ss_silence_pcm16_host");
+  SS_REQUIRE((size_t)n_intervals * sizeof(ss_interval) <= (size_t)kIntervalCap * sizeof(float), SS_E_CAPACITY,
+             "%d intervals exceed the table capacity", n_intervals);
+  cudaStream_t cs = ctx->compute_stream;
+  ss_interval* iv = reinterpret_cast<ss_interval*>(ctx->intervals);
+  if (n_intervals > 0)
+    SS_CUDA_CHECK(cudaMemcpyAsync(iv, intervals_host, (size_t)n_intervals * sizeof(ss_interval), cudaMemcpyHostToDevice, cs));
+  // the float-sized staging buffer holds twice as many int16 samples (kept a multiple of 8 for the vector kernels)
+  const int64_t cap = (ctx->stage_cap * 2) & ~(int64_t)7;
+  int16_t* stage = reinterpret_cast<int16_t*>(ctx->stage_buf[0]);
+  for (int64_t c0 = 0; c0 < n_elems; c0 += cap) {
+    const int64_t len = (n_elems - c0 < cap) ? (n_elems - c0) : cap;
+    SS_CUDA_CHECK(cudaMemcpyAsync(stage, pcm_host + c0, (size_t)len * sizeof(int16_t), cudaMemcpyHostToDevice, cs));
+    if (requantize && (rc = launch_requant_pcm16(stage, len, cs))) return rc;
+    if ((rc = launch_silence_s16(stage, len, c0, iv, n_intervals, cs))) return rc;
+    SS_CUDA_CHECK(cudaMemcpyAsync(pcm_host + c0, stage, (size_t)len * sizeof(int16_t), cudaMemcpyDeviceToHost, cs));
+  }
+  SS_CUDA_CHECK(cudaStreamSynchronize(cs));
   return SS_OK;
 }
 

@@ -115,10 +115,22 @@ __device__ __forceinline__ void cmul(float& r, float& i, float2 w) {
 
 // Sample `l` (relative to the window start, may be negative for frame 0 -> torch 'reflect') of the
 // virtual padded clip: indices inside [valid_begin, valid_end) map to pcm[idx - offset], the rest are 0.
-__device__ __forceinline__ float load_sample(const float* __restrict__ pcm, int64_t wstart, int l,
+// Sample types: float32 (what `load_audio` returns) or the int16 of a PCM_16 file, decoded on the fly exactly as
+// libsndfile's float read does (value / 32768; voice_activity.py:37) — int16 -> float and the power-of-two scale are
+// both exact, so the two sample types give bit-identical features.
+__device__ __forceinline__ float ld1(const float* p) { return __ldg(p); }
+__device__ __forceinline__ float ld1(const int16_t* p) { return (float)__ldg(p) * (1.0f / 32768.0f); }
+__device__ __forceinline__ float2 ld2(const float* p) { return __ldg(reinterpret_cast<const float2*>(p)); }
+__device__ __forceinline__ float2 ld2(const int16_t* p) {
+  const short2 v = __ldg(reinterpret_cast<const short2*>(p));
+  return make_float2((float)v.x * (1.0f / 32768.0f), (float)v.y * (1.0f / 32768.0f));
+}
+
+template <typename T>
+__device__ __forceinline__ float load_sample(const T* __restrict__ pcm, int64_t wstart, int l,
                                              int64_t valid_begin, int64_t valid_end, int64_t offset) {
   const int64_t idx = wstart + (l < 0 ? -l : l);
-  return (idx >= valid_begin && idx < valid_end) ? __ldg(pcm + (idx - offset)) : 0.0f;
+  return (idx >= valid_begin && idx < valid_end) ? ld1(pcm + (idx - offset)) : 0.0f;
 }
 
 // Passes 2 and 3 of the 512-point FFT whose pass-1 results sit in the warp's exchange buffer (A layout).
@@ -163,8 +175,9 @@ __device__ __forceinline__ void fft512_tail(WarpSmem& ws, const Smem& s, int lan
   for (int h = 0; h < 2; ++h) dft8<false>(re[h], im[h]);
 }
 
+template <typename T>
 __global__ void __launch_bounds__(kThreads, 1)
-features_kernel(const float* __restrict__ pcm, int64_t valid_begin, int64_t valid_end, int64_t offset,
+features_kernel(const T* __restrict__ pcm, int64_t valid_begin, int64_t valid_end, int64_t offset,
                 const int64_t* __restrict__ starts, int64_t w_base, int n_tiles, FrontEnd fe, float* __restrict__ mel) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Smem& s = *reinterpret_cast<Smem*>(smem_raw);
@@ -209,17 +222,17 @@ features_kernel(const float* __restrict__ pcm, int64_t valid_begin, int64_t vali
       const int l0 = (frame0 + f) * kHop - kHop;   // first sample of the frame relative to the window
       const int64_t g0 = wstart + l0;
       const bool fast = (l0 >= 0) && (g0 >= valid_begin) && (g0 + kWin <= valid_end);   // warp-uniform
-      const float* __restrict__ src = pcm + (g0 - offset);
-      const bool fast2 = fast && (reinterpret_cast<uintptr_t>(src) & 7) == 0;            // 8-byte aligned frame
+      const T* __restrict__ src = pcm + (g0 - offset);
+      const bool fast2 = fast && (reinterpret_cast<uintptr_t>(src) & (2 * sizeof(T) - 1)) == 0;   // pair-aligned frame
       float* __restrict__ Pf = s.P + f;
       {
         // pull the samples of the next frame this warp will transform into L1 while this frame computes
         const int ntile = (fi + 1 < kFramesPerWarp) ? tile : tile + (int)gridDim.x;
-        if (ntile < n_tiles && lane < 17) {
+        if (ntile < n_tiles && lane < (int)(kWin * sizeof(T) / 128) + 1) {
           const int nw = ntile >> 3;
           const int nf = (ntile & 7) * kFramesPerTile + warp * kFramesPerWarp + ((fi + 1) % kFramesPerWarp);
           const int64_t nws = starts ? starts[nw] : (w_base + nw) * (int64_t)kStepSamples;
-          const int64_t ng = nws + (int64_t)nf * kHop - kHop + 32 * lane;
+          const int64_t ng = nws + (int64_t)nf * kHop - kHop + (int64_t)(128 / sizeof(T)) * lane;   // one 128 B line per lane
           if (ng >= valid_begin && ng < valid_end) asm volatile("prefetch.global.L1 [%0];" ::"l"(pcm + (ng - offset)));
         }
       }
@@ -231,7 +244,7 @@ features_kernel(const float* __restrict__ pcm, int64_t valid_begin, int64_t vali
         float x[8];
         if (fast) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) x[j] = __ldg(src + t + 64 * j);
+          for (int j = 0; j < 8; ++j) x[j] = ld1(src + t + 64 * j);
         } else {
 #pragma unroll
           for (int j = 0; j < 8; ++j) x[j] = load_sample(pcm, wstart, l0 + t + 64 * j, valid_begin, valid_end, offset);
@@ -269,10 +282,10 @@ features_kernel(const float* __restrict__ pcm, int64_t valid_begin, int64_t vali
         float2 x[4];
         if (fast2) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) x[j] = __ldg(reinterpret_cast<const float2*>(src) + t + 64 * j);
+          for (int j = 0; j < 4; ++j) x[j] = ld2(src + 2 * (t + 64 * j));
         } else if (fast) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) x[j] = make_float2(__ldg(src + 2 * (t + 64 * j)), __ldg(src + 2 * (t + 64 * j) + 1));
+          for (int j = 0; j < 4; ++j) x[j] = make_float2(ld1(src + 2 * (t + 64 * j)), ld1(src + 2 * (t + 64 * j) + 1));
         } else {
 #pragma unroll
           for (int j = 0; j < 4; ++j)
@@ -352,20 +365,26 @@ __global__ void window_starts_kernel(int64_t* starts, int64_t n) {
 }  // namespace
 
 int features_init() {
-  SS_CUDA_CHECK(cudaFuncSetAttribute(features_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  SS_CUDA_CHECK(cudaFuncSetAttribute(features_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)sizeof(Smem)));
+  SS_CUDA_CHECK(cudaFuncSetAttribute(features_kernel<int16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)sizeof(Smem)));
   return SS_OK;
 }
 
-int launch_features_virtual(const ss_ctx* ctx, const float* pcm, int64_t valid_begin, int64_t valid_end,
+int launch_features_virtual(const ss_ctx* ctx, const void* pcm, int sample_fmt, int64_t valid_begin, int64_t valid_end,
                             int64_t offset, const int64_t* starts, int64_t w_base, int n_windows, float* mel,
                             cudaStream_t st) {
   if (n_windows <= 0) return SS_OK;
   SS_REQUIRE(ctx->fe.n_taps <= kMaxTaps, SS_E_BLOB, "mel filterbank has %d taps (> %d)", ctx->fe.n_taps, kMaxTaps);
   const int n_tiles = n_windows * (kFrames / kFramesPerTile);
   const int grid = n_tiles < kNumSMs ? n_tiles : kNumSMs;
-  features_kernel<<<grid, kThreads, sizeof(Smem), st>>>(pcm, valid_begin, valid_end, offset, starts, w_base, n_tiles,
-                                                        ctx->fe, mel);
+  if (sample_fmt == kSampleS16)
+    features_kernel<int16_t><<<grid, kThreads, sizeof(Smem), st>>>(static_cast<const int16_t*>(pcm), valid_begin,
+                                                                   valid_end, offset, starts, w_base, n_tiles, ctx->fe, mel);
+  else
+    features_kernel<float><<<grid, kThreads, sizeof(Smem), st>>>(static_cast<const float*>(pcm), valid_begin, valid_end,
+                                                                 offset, starts, w_base, n_tiles, ctx->fe, mel);
   SS_CUDA_CHECK(cudaGetLastError());
   count_launch();
   return SS_OK;
@@ -373,7 +392,7 @@ int launch_features_virtual(const ss_ctx* ctx, const float* pcm, int64_t valid_b
 
 int launch_features(const ss_ctx* ctx, const float* pcm, int64_t n_padded, const int64_t* starts, int n_windows,
                     float* mel, cudaStream_t st) {
-  return launch_features_virtual(ctx, pcm, 0, n_padded, 0, starts, 0, n_windows, mel, st);
+  return launch_features_virtual(ctx, pcm, kSampleF32, 0, n_padded, 0, starts, 0, n_windows, mel, st);
 }
 
 int launch_pad(const float* src, int64_t n, float* dst, cudaStream_t st) {

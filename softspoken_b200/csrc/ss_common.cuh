@@ -158,7 +158,9 @@ int launch_features(const ss_ctx* ctx, const float* pcm, int64_t n_padded, const
                     float* mel, cudaStream_t st);
 // Virtual padded clip: padded index idx in [valid_begin, valid_end) reads pcm[idx - offset], the rest are 0.
 // starts == nullptr -> window w starts at (w_base + w) * 13230.
-int launch_features_virtual(const ss_ctx* ctx, const float* pcm, int64_t valid_begin, int64_t valid_end,
+// sample_fmt: kSampleF32 (float32 samples) or kSampleS16 (int16 of a PCM_16 file, decoded as value / 32768 on load).
+constexpr int kSampleF32 = 0, kSampleS16 = 1;
+int launch_features_virtual(const ss_ctx* ctx, const void* pcm, int sample_fmt, int64_t valid_begin, int64_t valid_end,
                             int64_t offset, const int64_t* starts, int64_t w_base, int n_windows, float* mel,
                             cudaStream_t st);
 int launch_pad(const float* src, int64_t n, float* dst, cudaStream_t st);
@@ -177,6 +179,12 @@ int64_t regions_scan_tmp_len(int64_t out_len);
 // silence.cu
 // zero [begin - shift, end - shift) ∩ [0, n_elems) of pcm for every interval
 int launch_silence(float* pcm, int64_t n_elems, int64_t shift, const ss_interval* iv, int n_intervals, cudaStream_t st);
+int launch_silence_s16(int16_t* pcm, int64_t n_elems, int64_t shift, const ss_interval* iv, int n_intervals,
+                       cudaStream_t st);
+// pcm16.cu
+int launch_decode_pcm16(const int16_t* interleaved, int64_t frames, int channels, float* mono, cudaStream_t st);
+int launch_encode_pcm16(const float* src, int64_t n_elems, int16_t* dst, cudaStream_t st);
+int launch_requant_pcm16(int16_t* pcm, int64_t n_elems, cudaStream_t st);
 // conv_tc.cu
 void tc_destroy(ss_ctx* ctx);
 int classify_tc(ss_ctx* ctx, int mode, const float* mel, int n_windows, float* logits, float* spec_out,

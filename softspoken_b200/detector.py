@@ -172,8 +172,8 @@ class NNDetector:
 
     # ------------------------------------------------------------------ throughput path (new)
     def detect_file(self, audio: np.ndarray, want_logits: bool = False):
-        """Unpadded float32 mono clip at 22,050 Hz -> [(start_s, end_s)] exactly as `ProcessWorker.run` derives
-        them (pad 3 s, window, classify, average, threshold, merge, subtract 3 s; worker.py:57-100)."""
+        """Unpadded mono clip at 22,050 Hz (float32, or the int16 samples of a PCM_16 file) -> [(start_s, end_s)]
+        exactly as `ProcessWorker.run` derives them (pad 3 s, window, classify, average, threshold, merge, subtract 3 s; worker.py:57-100)."""
         eng = self.model.engine
         res = eng.detect_host(audio, want_logits=want_logits)
         bins = res[0] if want_logits else res

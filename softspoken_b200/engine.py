@@ -137,59 +137,63 @@ class Engine:
     # ------------------------------------------------------------------ file-level entry points
     def detect_device(self, pcm: torch.Tensor, mode: Optional[str] = None, cap: int = 1 << 16,
                       want_logits: bool = False):
-        """Unpadded device clip -> (regions i32 `[cap,2]` device, n i32 `[1]` device[, logits])."""
-        pcm = self._f32(pcm)
+        """Unpadded device clip -> (regions i32 `[cap,2]` device, n i32 `[1]` device[, logits]).
+
+        `pcm` is float32 (what `load_audio` returns) or int16 (the samples of a mono PCM_16 file as stored; K1
+        decodes them as sample / 32768, bit-identical to the float32 route)."""
+        pcm16 = isinstance(pcm, torch.Tensor) and pcm.dtype == torch.int16
+        pcm = pcm.to(self.device).contiguous() if pcm16 else self._f32(pcm)
         n = pcm.numel()
         self.reserve(n, cap)
         reg = torch.empty((cap, 2), dtype=torch.int32, device=self.device)
         cnt = torch.zeros(1, dtype=torch.int32, device=self.device)
         W = lib.ss_plan_windows(n)
         lg = torch.empty((W, spec.N_FRAMES), dtype=torch.float32, device=self.device) if want_logits else None
-        check(lib.ss_detect_device(self._ctx, _ptr(pcm), n, self._mode(mode), _ptr(reg), _ptr(cnt), cap, _ptr(lg),
-                                   self._stream()))
+        fn = lib.ss_detect_device_pcm16 if pcm16 else lib.ss_detect_device
+        check(fn(self._ctx, _ptr(pcm), n, self._mode(mode), _ptr(reg), _ptr(cnt), cap, _ptr(lg), self._stream()))
         return (reg, cnt, lg) if want_logits else (reg, cnt)
 
     def detect_host(self, audio: np.ndarray | torch.Tensor, mode: Optional[str] = None, cap: int = 1 << 16,
                     want_logits: bool = False):
-        """Host float32 mono clip (what `load_audio` returns) -> int32 `[R,2]` region bins (host)."""
-        if isinstance(audio, torch.Tensor):
-            assert audio.device.type == "cpu" and audio.dtype == torch.float32 and audio.is_contiguous()
-            n, ptr = audio.numel(), C.c_void_p(audio.data_ptr())
-        else:
-            audio = np.ascontiguousarray(audio, dtype=np.float32)
-            n, ptr = audio.size, C.c_void_p(audio.ctypes.data)
+        """Host mono clip -> int32 `[R,2]` region bins (host).  float32 (what `load_audio` returns) or int16 (the
+        samples of a PCM_16 file as stored: half the upload, same bits out)."""
+        n, ptr, pcm16, audio = _host_clip(audio)
         self.reserve(n, cap)
         reg = np.empty((cap, 2), dtype=np.int32)
         k = C.c_int()
         W = lib.ss_plan_windows(n)
         lg = np.empty((W, spec.N_FRAMES), dtype=np.float32) if want_logits else None
-        check(lib.ss_detect_host(self._ctx, ptr, n, self._mode(mode), C.c_void_p(reg.ctypes.data), cap,
-                                 C.byref(k), C.c_void_p(lg.ctypes.data) if want_logits else None))
+        fn = lib.ss_detect_host_pcm16 if pcm16 else lib.ss_detect_host
+        check(fn(self._ctx, ptr, n, self._mode(mode), C.c_void_p(reg.ctypes.data), cap, C.byref(k),
+                 C.c_void_p(lg.ctypes.data) if want_logits else None))
         if k.value > cap:
             raise _lib.SoftspokenError(_lib.SS_E_CAPACITY, f"{k.value} regions exceed capacity {cap}")
         out = reg[:k.value].copy()
         return (out, lg) if want_logits else out
 
     def detect_host_batch(self, clips, mode: Optional[str] = None, cap: int = 4096):
-        """Several host float32 mono clips (numpy arrays or CPU tensors, ideally pinned) -> list of int32 `[R,2]`
-        region-bin arrays.  One library call: uploads overlap compute across clips."""
-        ptrs, sizes, keep = [], [], []
+        """Several host mono clips (numpy arrays or CPU tensors, ideally pinned; all float32 or all int16) -> list of
+        int32 `[R,2]` region-bin arrays.  One library call: uploads overlap compute across clips."""
+        ptrs, sizes, keep, kinds = [], [], [], set()
         for a in clips:
-            if isinstance(a, torch.Tensor):
-                assert a.device.type == "cpu" and a.dtype == torch.float32 and a.is_contiguous()
-                ptrs.append(a.data_ptr()); sizes.append(a.numel())
-            else:
-                a = np.ascontiguousarray(a, dtype=np.float32)
-                ptrs.append(a.ctypes.data); sizes.append(a.size)
-            keep.append(a)
+            k, ptr, pcm16, a = _host_clip(a)
+            ptrs.append(ptr.value or 0); sizes.append(k); keep.append(a); kinds.add(pcm16)
         n = len(keep)
         if n == 0:
             return []
+        if len(kinds) != 1:      # mixed sample types: one library call per type, results back in input order
+            out = [None] * n
+            for want in (False, True):
+                idx = [i for i, a in enumerate(keep) if _host_clip(a)[2] == want]
+                for i, r in zip(idx, self.detect_host_batch([keep[i] for i in idx], mode, cap)):
+                    out[i] = r
+            return out
+        batch_fn = lib.ss_detect_host_batch_pcm16 if kinds.pop() else lib.ss_detect_host_batch
         self.reserve(max(sizes), cap)
         reg = np.empty((n, cap, 2), dtype=np.int32)
         cnt = (C.c_int * n)()
-        check(lib.ss_detect_host_batch(self._ctx, n, (C.c_void_p * n)(*ptrs), (C.c_int64 * n)(*sizes), self._mode(mode),
-                                       C.c_void_p(reg.ctypes.data), cap, cnt))
+        check(batch_fn(self._ctx, n, (C.c_void_p * n)(*ptrs), (C.c_int64 * n)(*sizes), self._mode(mode),
+                       C.c_void_p(reg.ctypes.data), cap, cnt))
         out = []
         for i in range(n):
             if cnt[i] > cap:
@@ -210,10 +214,56 @@ class Engine:
         check(lib.ss_silence_host(self._ctx, C.c_void_p(audio.ctypes.data), audio.size,
                                   C.c_void_p(iv.ctypes.data), iv.shape[0]))
 
+    # ------------------------------------------------------------------ PCM_16 sample path
+    def decode_pcm16(self, frames: torch.Tensor) -> torch.Tensor:
+        """Interleaved int16 `[n]` or `[n, C]` (device) -> float32 mono `[n]`: `sf.read(dtype='float32')` +
+        `librosa.to_mono` (voice_activity.py:37,61-62)."""
+        assert frames.dtype == torch.int16
+        frames = frames.to(self.device).contiguous()
+        n = frames.shape[0]
+        ch = 1 if frames.dim() == 1 else frames.shape[1]
+        out = torch.empty(n, dtype=torch.float32, device=self.device)
+        check(lib.ss_decode_pcm16(self._ctx, _ptr(frames), n, ch, _ptr(out), self._stream()))
+        return out
+
+    def encode_pcm16(self, x: torch.Tensor) -> torch.Tensor:
+        """float32 (device, any shape) -> int16 of the same shape, as `sf.write(..., subtype='PCM_16')` stores it."""
+        x = self._f32(x)
+        out = torch.empty(x.shape, dtype=torch.int16, device=self.device)
+        check(lib.ss_encode_pcm16(self._ctx, _ptr(x), x.numel(), _ptr(out), self._stream()))
+        return out
+
+    def silence_pcm16(self, pcm: torch.Tensor, intervals: torch.Tensor, requantize: bool = True) -> None:
+        """In place on a device int16 buffer: optional read->write round trip of every sample, then zero the ranges."""
+        assert pcm.is_cuda and pcm.dtype == torch.int16 and pcm.is_contiguous()
+        iv = intervals.to(device=self.device, dtype=torch.int64).contiguous().reshape(-1, 2)
+        check(lib.ss_silence_pcm16(self._ctx, _ptr(pcm), pcm.numel(), _ptr(iv), iv.shape[0], int(requantize),
+                                   self._stream()))
+
+    def silence_pcm16_host(self, pcm: np.ndarray, intervals: np.ndarray, requantize: bool = True) -> None:
+        """In place on a host int16 buffer (any shape, C-contiguous); `intervals` int64 `[K,2]` flat offsets."""
+        assert pcm.dtype == np.int16 and pcm.flags.c_contiguous and pcm.flags.writeable
+        iv = np.ascontiguousarray(intervals, dtype=np.int64).reshape(-1, 2)
+        self.reserve(max(self._reserved_samples, 0), max(self._region_cap, 1))
+        check(lib.ss_silence_pcm16_host(self._ctx, C.c_void_p(pcm.ctypes.data), pcm.size,
+                                        C.c_void_p(iv.ctypes.data), iv.shape[0], int(requantize)))
+
     def _f32(self, t: torch.Tensor) -> torch.Tensor:
         if not isinstance(t, torch.Tensor):
             t = torch.as_tensor(np.asarray(t))
         return t.to(device=self.device, dtype=torch.float32).contiguous()
+
+
+def _host_clip(audio):
+    """-> (n, pointer, is_int16, keep-alive object) of a host clip given as numpy array or CPU tensor."""
+    if isinstance(audio, torch.Tensor):
+        assert audio.device.type == "cpu" and audio.dtype in (torch.float32, torch.int16) and audio.is_contiguous()
+        return audio.numel(), C.c_void_p(audio.data_ptr()), audio.dtype == torch.int16, audio
+    audio = np.asarray(audio)
+    if audio.dtype != np.int16:
+        audio = np.ascontiguousarray(audio, dtype=np.float32)
+    audio = np.ascontiguousarray(audio)
+    return audio.size, C.c_void_p(audio.ctypes.data), audio.dtype == np.int16, audio
 
 
 def plan_windows(n_samples: int) -> int:

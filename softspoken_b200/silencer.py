@@ -123,5 +123,4 @@ def _write_pcm16(path: str, data: np.ndarray, sr: int) -> None:
     """`sf.write(path, data, sr)` (silencer_ui.py:998; WAV default subtype PCM_16).  libsndfile's exact
     float->short conversion could not be pinned in this image: parity is claimed for the
     float32 buffers handed to the writer, not for the encoded bytes."""
-    pcm = np.clip(np.rint(np.asarray(data, np.float64) * 32767.0), -32768, 32767).astype(np.int16)
-    wavio.write_wav_pcm16(path, pcm, sr)
+    wavio.write_wav_pcm16(path, wavio.encode_pcm16(data), sr)

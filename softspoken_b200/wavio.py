@@ -98,6 +98,28 @@ def read_wav(path: str) -> Tuple[np.ndarray, int]:
     return x, sr
 
 
+def read_wav_pcm16(path: str):
+    """PCM_16 file -> (int16 `(n,)` mono or `(n, C)` interleaved frames as stored, sample_rate); `None` for any
+    other sample format.  The device decodes these samples itself (`ss_detect_*_pcm16`, `ss_decode_pcm16`): the
+    float32 copy that `sf.read(dtype='float32')` would build on the host is never made."""
+    raw = np.fromfile(path, dtype=np.uint8)
+    frames, sr, ch, bits, tag, off, size = _parse_header(memoryview(raw), len(raw))
+    if tag != WAVE_FORMAT_PCM or bits != 16:
+        return None
+    size = min(size, len(raw) - off)
+    frames = size // (ch * 2)
+    x = raw[off:off + frames * ch * 2].view("<i2")
+    return (x if ch == 1 else x.reshape(frames, ch)), sr
+
+
+def encode_pcm16(x: np.ndarray) -> np.ndarray:
+    """float32 -> int16 as `sf.write(..., subtype='PCM_16')` (libsndfile pcm.c:f2les_array, normalisation on):
+    lrintf(x * 32767.0f) with the product rounded to float32 first; out-of-range samples saturate (the C code
+    would wrap).  Host twin of the `ss_encode_pcm16` kernel."""
+    y = np.rint(np.asarray(x, np.float32) * np.float32(32767.0))
+    return np.clip(y, -32768, 32767).astype(np.int16)
+
+
 def write_wav_pcm16(path: str, pcm: np.ndarray, sr: int) -> None:
     """int16 `(n,)` or `(n, C)` -> PCM_16 WAVE."""
     pcm = np.ascontiguousarray(pcm, dtype="<i2")

@@ -233,3 +233,28 @@ def test_corpus_driver_same_csv_for_one_and_two_ranks():
             append_rows(proj, f, region_bins_to_times(bins))
         proj.save_detections()
         assert open(os.path.join(d, "x.csv")).read() == texts[1]
+
+
+def test_pcm16_host_helpers(tmp_path):
+    """PCM_16 sample path, host side: the raw int16 reader returns the stored samples, the float decode of the oracle
+    equals `wavio.read_wav` (+ channel mean), and the host twin of the encode kernel equals the oracle's restatement
+    of libsndfile's float -> short conversion."""
+    from oracle import silence as osil
+    from softspoken_b200 import corpus, wavio
+    rng = np.random.default_rng(1)
+    for ch in (1, 2):
+        fr = rng.integers(-32768, 32768, size=(5000, ch) if ch > 1 else 5000, dtype=np.int16)
+        p = os.path.join(tmp_path, f"c{ch}.wav")
+        wavio.write_wav_pcm16(p, fr, 22050)
+        raw, sr = wavio.read_wav_pcm16(p)
+        assert sr == 22050 and raw.dtype == np.int16 and np.array_equal(raw, fr)
+        f32, _ = wavio.read_wav(p)
+        want = f32 if ch == 1 else np.mean(f32, axis=0)
+        assert np.array_equal(osil.load_audio_pcm16(fr), want)
+        got = corpus.load_native_22050(p)
+        assert (got.dtype == np.int16) == (ch == 1)
+    pf = os.path.join(tmp_path, "f.wav")
+    wavio.write_wav_float32(pf, rng.standard_normal(100).astype(np.float32), 22050)
+    assert wavio.read_wav_pcm16(pf) is None and corpus.load_native_22050(pf).dtype == np.float32
+    x = (rng.standard_normal(10000) * 0.5).astype(np.float32)
+    assert np.array_equal(wavio.encode_pcm16(x), osil.float_to_pcm16(x))

@@ -203,6 +203,8 @@ def run_b200(args):
     C = args.clips_per_step
     pool = device_clips(args.pool, device, seed0=1000 * rank)
     pinned = [p.cpu().pin_memory() for p in pool]
+    # the same clips as the int16 samples a PCM_16 wav stores (the pool is quantised to k / 32768, so this is exact)
+    pinned16 = [(p * 32768.0).round().to(torch.int16).cpu().pin_memory() for p in pool]
     reg_bufs = [(torch.empty((cap, 2), dtype=torch.int32, device=device), torch.zeros(1, dtype=torch.int32, device=device))
                 for _ in range(C)]
     stream = torch.cuda.current_stream(device)
@@ -232,10 +234,11 @@ def run_b200(args):
                 trip.append(torch.cat([fi, reg[:k]], 1).cpu().numpy())
             ssdist.gather_detections(np.concatenate(trip) if trip else np.zeros((0, 3), np.int32), device)
 
-    def step_host(s):
+    def step_host(s, src=None):
         total_regions = 0
         trip = []
-        clips = [pinned[(s * C + j) % len(pinned)] for j in range(C)]
+        src = pinned if src is None else src
+        clips = [src[(s * C + j) % len(src)] for j in range(C)]
         for j, bins in enumerate(eng.detect_host_batch(clips, cap=cap)):   # one C-ABI call per step
             total_regions += len(bins)
             if world > 1:
@@ -275,6 +278,7 @@ def run_b200(args):
     dev_s, wall_s, launches, clocks, _ = timed(step_device, args.steps, args.warmup)
     t_dev = max(dev_s, 1e-9) if world == 1 else wall_s        # multi-rank steps include the host-side gather
     e_dev_s, e_wall_s, _, _, n_regions = timed(step_host, args.steps, max(1, args.warmup // 2))
+    _, e16_wall_s, _, _, n_regions16 = timed(lambda s: step_host(s, pinned16), args.steps, max(1, args.warmup // 2))
 
     def max_over_ranks(x):
         if world == 1:
@@ -285,9 +289,11 @@ def run_b200(args):
 
     t_dev = max_over_ranks(t_dev)
     t_e2e = max_over_ranks(e_wall_s)
+    t_e2e16 = max_over_ranks(e16_wall_s)
     hours = args.steps * C * world * CLIP_S / 3600.0
     value = hours / t_dev
     e2e = hours / t_e2e
+    e2e16 = hours / t_e2e16
 
     # ---- per-kernel-family times for the roofline: one clip's 1,005 windows, CUDA events on torch's stream
     pk = peaks()
@@ -337,6 +343,11 @@ def run_b200(args):
             "x_realtime": value * 3600.0,
             "e2e": {"value": e2e, "unit": "audio-hours/s", "h2d_bytes_per_step": C * n * 4,
                     "d2h_bytes_per_step": int(C * 4 + (n_regions or 0) * 8), "x_realtime": e2e * 3600.0},
+            # same call with the int16 samples of PCM_16 files as host buffers (ss_detect_host_batch_pcm16: decode fused
+            # into K1, bit-identical detections, half the upload)
+            "e2e_pcm16": {"value": e2e16, "unit": "audio-hours/s", "h2d_bytes_per_step": C * n * 2,
+                          "d2h_bytes_per_step": int(C * 4 + (n_regions16 or 0) * 8), "x_realtime": e2e16 * 3600.0,
+                          "same_regions_as_float32": bool(n_regions16 == n_regions)},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "tensor", "kernel": "classifier (conv stack, ss_classify)", "achieved": achieved_tf,
@@ -375,7 +386,7 @@ def main():
     ap.add_argument("--mode", default=os.environ.get("SS_BENCH_MODE", "f16x3"), choices=["fp32", "bf16", "f16", "f16x3"])
     ap.add_argument("--clips-per-step", type=int, default=2)
     ap.add_argument("--pool", type=int, default=4)
-    ap.add_argument("--max-batch", type=int, default=256)
+    ap.add_argument("--max-batch", type=int, default=1005)      # one 10-minute clip per classifier batch (36 GB of f16x3 activations)
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--ref-step-seconds", type=float, default=10.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -120,8 +120,15 @@ int upload_tables(ss_ctx* ctx, const BlobView& v) {
   return SS_OK;
 }
 
-int alloc_workspace(ss_ctx* ctx) {
-  const size_t B = (size_t)ctx->max_batch;
+}  // namespace
+
+// The fp32 (CUDA-core) classifier's activation workspace, allocated on its first use: contexts that only run the
+// tensor-core modes (the default) never pay for it.  The fp32 path is compute-bound at any batch, so its batch is
+// capped at 64 windows whatever max_batch says (a 1,005-window batch would otherwise hold 28 GB here).
+int ensure_workspace_f32(ss_ctx* ctx) {
+  if (ctx->ws.conv1) return SS_OK;
+  ctx->f32_batch = ctx->max_batch < 64 ? ctx->max_batch : 64;
+  const size_t B = (size_t)ctx->f32_batch;
   WorkspaceF32& w = ctx->ws;
   int rc;
 #define A(field, n) do { if ((rc = dev_alloc(ctx, &w.field, B * (size_t)(n)))) return rc; } while (0)
@@ -145,6 +152,8 @@ int alloc_workspace(ss_ctx* ctx) {
 #undef A
   return SS_OK;
 }
+
+namespace {
 
 bool valid_mode(int mode) { return mode >= SS_MODE_FP32 && mode <= SS_MODE_F16X3; }
 
@@ -312,7 +321,6 @@ int ss_ctx_create(int device, const void* blob, size_t blob_bytes, int max_batch
   FAIL_IF(find(v, d, "mask_output_conv.1.b", 1, &h.out_b));
   FAIL_IF(find(v, d, "spec_output_conv.1.w", 64, &h.spec_w));
   FAIL_IF(find(v, d, "spec_output_conv.1.b", 2, &h.spec_b));
-  FAIL_IF(alloc_workspace(ctx));
   FAIL_IF(features_init());
   {
     cudaError_t e = cudaStreamCreateWithFlags(&ctx->compute_stream, cudaStreamNonBlocking);

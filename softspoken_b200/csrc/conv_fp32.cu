@@ -211,9 +211,13 @@ int pool(const float* in, int B, int H, int W, int C, float* out, cudaStream_t s
 }  // namespace
 
 int classify_fp32(ss_ctx* ctx, const float* mel, int n_windows, float* logits, float* spec_out, cudaStream_t st) {
+  {
+    const int rc0 = ensure_workspace_f32(ctx);
+    if (rc0) return rc0;
+  }
   WorkspaceF32& ws = ctx->ws;
-  for (int b0 = 0; b0 < n_windows; b0 += ctx->max_batch) {
-    const int B = (n_windows - b0 < ctx->max_batch) ? (n_windows - b0) : ctx->max_batch;
+  for (int b0 = 0; b0 < n_windows; b0 += ctx->f32_batch) {
+    const int B = (n_windows - b0 < ctx->f32_batch) ? (n_windows - b0) : ctx->f32_batch;
     const float* x = mel + (int64_t)b0 * kMels * kFrames;   // [B,128,256,1]
     int rc;
 #define SS_TRY(e) do { if ((rc = (e))) return rc; } while (0)

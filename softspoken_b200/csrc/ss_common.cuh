@@ -117,6 +117,7 @@ struct WorkspaceF32 {
 struct ss_ctx {
   int device = 0;
   int max_batch = 0;
+  int f32_batch = 0;          // batch of the fp32 classifier (set with its lazily allocated workspace)
   size_t device_bytes = 0;
   float* blob_dev = nullptr;          // the whole float payload of the weight blob
   ss::FrontEnd fe;
@@ -165,6 +166,8 @@ int launch_features_virtual(const ss_ctx* ctx, const void* pcm, int sample_fmt, 
                             cudaStream_t st);
 int launch_pad(const float* src, int64_t n, float* dst, cudaStream_t st);
 int launch_window_starts(int64_t* starts, int64_t n_windows, cudaStream_t st);
+// api.cu
+int ensure_workspace_f32(ss_ctx* ctx);
 // conv_fp32.cu
 int classify_fp32(ss_ctx* ctx, const float* mel, int n_windows, float* logits, float* spec_out, cudaStream_t st);
 // head.cu

@@ -148,6 +148,51 @@ __global__ void pool_planar(const uint16_t* __restrict__ in, const uint16_t* __r
 // conv_flatten is spread over 8 x more threads than one-thread-per-frame and the loads stay coalesced.
 constexpr int kHeadFrames = 32, kHeadHalo = 2, kHeadCols = kHeadFrames + 2 * kHeadHalo, kHeadGroups = 8;
 
+// Shared tail of the two mask-head kernels: group partials -> conv_flatten bias + ReLU -> ResBlock1D(4, 4) ->
+// Conv1d(4, 1, 1) (pytorch_neural_nets.py:43-77,137-140,191-195), zero padding outside [0, 256).
+__device__ __forceinline__ void mask_head_tail(float (&part)[kHeadGroups][4][kHeadCols], float (&xf)[4][kHeadCols],
+                                               float (&c1)[4][kHeadCols], const HeadW& hw, int f, int hg, int t,
+                                               bool valid, float* __restrict__ logits_b) {
+  if (hg == 0) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      float v = 0.f;
+#pragma unroll
+      for (int g = 0; g < kHeadGroups; ++g) v += part[g][c][f];
+      xf[c][f] = valid ? fmaxf(v + __ldg(hw.flat_b + c), 0.f) : 0.f;     // zero padding outside [0, 256)
+    }
+  }
+  __syncthreads();
+  if (hg == 0 && f >= 1 && f < kHeadCols - 1) {
+#pragma unroll
+    for (int co = 0; co < 4; ++co) {
+      float v = __ldg(hw.c1_b + co);
+#pragma unroll
+      for (int k = 0; k < 3; ++k)
+#pragma unroll
+        for (int ci = 0; ci < 4; ++ci) v = fmaf(__ldg(hw.c1_w + (k * 4 + ci) * 4 + co), xf[ci][f + k - 1], v);
+      c1[co][f] = valid ? fmaxf(v, 0.f) : 0.f;
+    }
+  }
+  __syncthreads();
+  if (hg == 0 && f >= kHeadHalo && f < kHeadCols - kHeadHalo) {
+    float logit = __ldg(hw.out_b);
+#pragma unroll
+    for (int co = 0; co < 4; ++co) {
+      float v = __ldg(hw.c2_b + co);
+#pragma unroll
+      for (int k = 0; k < 3; ++k)
+#pragma unroll
+        for (int ci = 0; ci < 4; ++ci) v = fmaf(__ldg(hw.c2_w + (k * 4 + ci) * 4 + co), c1[ci][f + k - 1], v);
+      float r = __ldg(hw.res_b + co);
+#pragma unroll
+      for (int ci = 0; ci < 4; ++ci) r = fmaf(__ldg(hw.res_w + ci * 4 + co), xf[ci][f], r);
+      logit = fmaf(__ldg(hw.out_w + co), fmaxf(v + r, 0.f), logit);
+    }
+    logits_b[t] = logit;
+  }
+}
+
 template <Prec P>
 __global__ void __launch_bounds__(kHeadCols * kHeadGroups)
 mask_head_planar(const uint16_t* __restrict__ conv9, const uint16_t* __restrict__ conv9_lo, HeadW hw,
@@ -192,44 +237,34 @@ mask_head_planar(const uint16_t* __restrict__ conv9, const uint16_t* __restrict_
 #pragma unroll
   for (int c = 0; c < 4; ++c) part[hg][c][f] = acc[c];
   __syncthreads();
-  if (hg == 0) {
+  mask_head_tail(part, xf, c1, hw, f, hg, t, valid, logits + (int64_t)b * kFrames);
+}
+
+// Mask head from the conv_flatten partials the conv9_1 epilogue wrote (TcConv::head_out, [B][128][256][4]):
+// sum the 128 mel rows of each frame in a fixed order (8 groups of 16 rows, then the groups in order), then the same
+// 1-D tail as mask_head_planar.  grid (8 frame chunks, B).
+__global__ void __launch_bounds__(kHeadCols * kHeadGroups)
+mask_head_partials(const float* __restrict__ part_in, HeadW hw, float* __restrict__ logits) {
+  __shared__ float part[kHeadGroups][4][kHeadCols];
+  __shared__ float xf[4][kHeadCols];
+  __shared__ float c1[4][kHeadCols];
+  const int f = threadIdx.x % kHeadCols, hg = threadIdx.x / kHeadCols;
+  const int b = blockIdx.y;
+  const int t = blockIdx.x * kHeadFrames - kHeadHalo + f;          // frame of this column
+  const bool valid = (t >= 0) && (t < kFrames);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (valid) {
+    const int rows = kMels / kHeadGroups;
+    const float4* src = reinterpret_cast<const float4*>(part_in) + ((int64_t)b * kMels + hg * rows) * kFrames + t;
+    float4 v[16];
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      float v = 0.f;
+    for (int r = 0; r < 16; ++r) v[r] = __ldg(src + (int64_t)r * kFrames);
 #pragma unroll
-      for (int g = 0; g < kHeadGroups; ++g) v += part[g][c][f];
-      xf[c][f] = valid ? fmaxf(v + __ldg(hw.flat_b + c), 0.f) : 0.f;     // zero padding outside [0, 256)
-    }
+    for (int r = 0; r < 16; ++r) { acc.x += v[r].x; acc.y += v[r].y; acc.z += v[r].z; acc.w += v[r].w; }
   }
+  part[hg][0][f] = acc.x; part[hg][1][f] = acc.y; part[hg][2][f] = acc.z; part[hg][3][f] = acc.w;
   __syncthreads();
-  if (hg == 0 && f >= 1 && f < kHeadCols - 1) {
-#pragma unroll
-    for (int co = 0; co < 4; ++co) {
-      float v = __ldg(hw.c1_b + co);
-#pragma unroll
-      for (int k = 0; k < 3; ++k)
-#pragma unroll
-        for (int ci = 0; ci < 4; ++ci) v = fmaf(__ldg(hw.c1_w + (k * 4 + ci) * 4 + co), xf[ci][f + k - 1], v);
-      c1[co][f] = valid ? fmaxf(v, 0.f) : 0.f;
-    }
-  }
-  __syncthreads();
-  if (hg == 0 && f >= kHeadHalo && f < kHeadCols - kHeadHalo) {
-    float logit = __ldg(hw.out_b);
-#pragma unroll
-    for (int co = 0; co < 4; ++co) {
-      float v = __ldg(hw.c2_b + co);
-#pragma unroll
-      for (int k = 0; k < 3; ++k)
-#pragma unroll
-        for (int ci = 0; ci < 4; ++ci) v = fmaf(__ldg(hw.c2_w + (k * 4 + ci) * 4 + co), c1[ci][f + k - 1], v);
-      float r = __ldg(hw.res_b + co);
-#pragma unroll
-      for (int ci = 0; ci < 4; ++ci) r = fmaf(__ldg(hw.res_w + ci * 4 + co), xf[ci][f], r);
-      logit = fmaf(__ldg(hw.out_w + co), fmaxf(v + r, 0.f), logit);
-    }
-    logits[(int64_t)b * kFrames + t] = logit;
-  }
+  mask_head_tail(part, xf, c1, hw, f, hg, t, valid, logits + (int64_t)b * kFrames);
 }
 
 // spec head tail on planar [B][4][130][258][8] -> NCHW f32 [B][2][128][256]
@@ -308,6 +343,7 @@ struct TcState {
   Tensor x0, m4, m3, m2, m1, p1, p2, p3, p4, bott, c9, spec;
   Tensor t[RB_COUNT];
   int* err = nullptr;
+  float* head_part = nullptr;  // [max_batch][128][256][4] conv_flatten partials written by conv9_1's epilogue
   int* flags = nullptr;        // per-unit completion counts of a fused ResBlock launch (TcJob)
   int flags_cap = 0;
   long long* prof = nullptr;   // [kNumSMs][8] role timers of the selected conv launch (debug)
@@ -532,7 +568,8 @@ void add_sources(TcConv* p, const TcState* s, const Tensor& x, int plane0, const
 
 // One ResBlock: t = relu(conv3x3(x) + b1);  out = relu(conv3x3(t) + conv1x1(x) + b2 + b_res).
 int tc_res_block(TcState* s, int which, const Tensor& x, int x_plane0, Tensor& out, int out_plane0, int upsample,
-                 int B, cudaStream_t st) {
+                 int B, cudaStream_t st, const float* head_w = nullptr, float* head_out = nullptr,
+                 bool store_out = true) {
   const TcBlock& rb = s->rb[which];
   Tensor& t = s->t[which];
   const int N = rb.c1.n;
@@ -555,6 +592,8 @@ int tc_res_block(TcState* s, int which, const Tensor& x, int x_plane0, Tensor& o
   q.inv_scale = rb.inv_scale2;
   q.relu = 1;
   q.out = out.data; q.out_lo = out.lo; q.out_planes_total = out.planes; q.out_plane0 = out_plane0; q.upsample = upsample;
+  q.head_w = head_w; q.head_out = head_out;
+  if (head_w && !store_out) { q.out = nullptr; q.out_lo = nullptr; }
   q.err = s->err;
   // SS_TC_FUSE=1: both convolutions of the block in ONE persistent launch, conv2 trailing conv1 by SS_TC_LAG units
   // behind per-unit completion flags (TcJob).  Bit-identical results, t is read back from L2 instead of HBM and the
@@ -643,6 +682,8 @@ int tc_build(ss_ctx* ctx, Prec prec, TcState** out) {
   }
   SS_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&s->err), 4 * sizeof(int)));
   SS_CUDA_CHECK(cudaMemset(s->err, 0, 4 * sizeof(int)));
+  SS_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&s->head_part), (size_t)B * kMels * kFrames * 4 * sizeof(float)));
+  s->bytes += (size_t)B * kMels * kFrames * 4 * sizeof(float);
   s->flags_cap = B * (((kMels + 2) * (kFrames + 2) + 255) / 256);      // smallest unit: 256 positions
   SS_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&s->flags), (size_t)s->flags_cap * sizeof(int)));
   SS_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&s->prof), kNumSMs * 8 * sizeof(long long)));
@@ -703,9 +744,18 @@ int classify_tc_p(ss_ctx* ctx, TcState* s, const float* mel, int n_windows, floa
     SS_TRY(tc_res_block(s, RB_CONV6, s->m1, 0, s->m2, 12, 1, B, st));
     SS_TRY(tc_res_block(s, RB_CONV7, s->m2, 0, s->m3, 8, 1, B, st));
     SS_TRY(tc_res_block(s, RB_CONV8, s->m3, 0, s->m4, 4, 1, B, st));
-    SS_TRY(tc_res_block(s, RB_CONV9, s->m4, 0, s->c9, 0, 0, B, st));
-    mask_head_planar<P><<<dim3(kFrames / kHeadFrames, B), kHeadCols * kHeadGroups, 0, st>>>(
-        s->c9.data, s->c9.lo, ctx->head, logits + (int64_t)b0 * kFrames);
+    // conv9_1 with the mask head's conv_flatten folded into its epilogue (TcConv::head_w); the 32-channel output
+    // itself is stored only when the spec head will read it.  SS_TC_FUSE_HEAD=0 keeps the two-kernel form.
+    const char* fh = getenv("SS_TC_FUSE_HEAD");
+    if (fh == nullptr || atoi(fh) != 0) {
+      SS_TRY(tc_res_block(s, RB_CONV9, s->m4, 0, s->c9, 0, 0, B, st, ctx->head.flat_w, s->head_part, spec_out != nullptr));
+      mask_head_partials<<<dim3(kFrames / kHeadFrames, B), kHeadCols * kHeadGroups, 0, st>>>(
+          s->head_part, ctx->head, logits + (int64_t)b0 * kFrames);
+    } else {
+      SS_TRY(tc_res_block(s, RB_CONV9, s->m4, 0, s->c9, 0, 0, B, st));
+      mask_head_planar<P><<<dim3(kFrames / kHeadFrames, B), kHeadCols * kHeadGroups, 0, st>>>(
+          s->c9.data, s->c9.lo, ctx->head, logits + (int64_t)b0 * kFrames);
+    }
     SS_CUDA_CHECK(cudaGetLastError());
     count_launch();
     if (spec_out) {
@@ -748,6 +798,7 @@ void tc_destroy(ss_ctx* ctx) {
     }
     if (s->err) cudaFree(s->err);
     if (s->flags) cudaFree(s->flags);
+    if (s->head_part) cudaFree(s->head_part);
     if (s->prof) cudaFree(s->prof);
     delete s;
     ctx->tc[slot] = nullptr;

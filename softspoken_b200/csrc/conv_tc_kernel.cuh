@@ -208,6 +208,14 @@ struct TcConv {
   uint16_t* out;       // hi (or only) output tensor
   uint16_t* out_lo;    // residual output tensor (split precision), else null
   int out_planes_total, out_plane0, upsample;
+  // Mask-head fusion (N = 32, the last ResBlock of the mask path): when head_w is set the epilogue does not store
+  // the activations but their contraction with conv_flatten's weights for the position's mel row,
+  //   head_out[b][y][x][k] = sum_c act[c] * head_w[y][c][k]   (k < 4; pytorch_neural_nets.py:133-134,188-190),
+  // 16 bytes per position instead of 128: with out == null the 32-channel tensor is never written (it is kept only
+  // when the spec head will read it), and the head kernel just sums 128 rows per frame — in a fixed order, so
+  // results stay reproducible bit for bit and do not depend on the batch split.
+  const float* head_w;   // [128 mel][32][4] float32 or null
+  float* head_out;       // [B][128][256][4] float32
   int units_per_image, total_units;
   int stages;          // smem ring depth (<= kMaxStages)
   int cps;             // K-chunks a stage of a 1x1 source carries (>= 1; see the producer)
@@ -559,10 +567,31 @@ conv_tc_kernel(const TcJob job) {
           uint32_t v[32];
           tc_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * kAccCols + mt * TS + n0), v);
           if constexpr (Dual) {
-            uint32_t c[32];
-            tc_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * kAccCols + mt * TS + N + n0), c);
+            uint32_t cv[32];
+            tc_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * kAccCols + mt * TS + N + n0), cv);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(c[i]));
+            for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(cv[i]));
+          }
+          if constexpr (N == 32) {
+            if (c.head_w != nullptr) {
+              // fused conv_flatten partials: this position's 32 activations . head_w[y - 1][:, 0..3]
+              if (interior) {
+                const float4* wrow = reinterpret_cast<const float4*>(c.head_w) + (y - 1) * 32;
+                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                  float f = fmaf(__uint_as_float(v[i]), inv_scale, bias_p[i]);
+                  if (c.relu) f = fmaxf(f, 0.f);
+                  const float4 w = __ldg(wrow + i);
+                  acc.x = fmaf(f, w.x, acc.x);
+                  acc.y = fmaf(f, w.y, acc.y);
+                  acc.z = fmaf(f, w.z, acc.z);
+                  acc.w = fmaf(f, w.w, acc.w);
+                }
+                reinterpret_cast<float4*>(c.head_out)[((int64_t)b * p.H + (y - 1)) * p.W + (x - 1)] = acc;
+              }
+              if (c.out == nullptr) continue;      // nobody reads the activations themselves (no spec head requested)
+            }
           }
 #pragma unroll
           for (int g = 0; g < 4; ++g) {

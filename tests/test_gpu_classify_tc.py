@@ -51,7 +51,10 @@ def test_layerwise_against_oracle(engine, sd_seed0, clip60):
     sel = g["starts"][[0, 41, 77]]
     padded = torch.from_numpy(pp.pad_audio(clip60)).cuda()
     mel = engine.features(padded, torch.from_numpy(sel))
-    logits = engine.classify(mel)
+    # want_spec: conv9_1's output tensor (activation 9 below) is materialised only when the spec head will read it —
+    # otherwise its epilogue hands the mask head 4 partial sums per position (TcConv::head_w) and stores nothing else
+    logits, _ = engine.classify(mel, want_spec=True)
+    assert torch.equal(logits, engine.classify(mel))
     torch.cuda.synchronize()
     taps = {}
     _, mk = om.forward_from_mel(sd_seed0, mel.cpu().unsqueeze(1), want_spec=False, taps=taps)
@@ -170,7 +173,7 @@ def test_fused_resblock_launch_is_bit_identical(sd_seed0, clip60, monkeypatch):
         base = eng.classify(mel)
         for env in ({"SS_TC_FUSE": "1"}, {"SS_TC_FUSE": "1", "SS_TC_LAG": "3"}, {"SS_TC_FUSE": "1", "SS_TC_LAG": "100000"},
                     {"SS_TC_CPS": "1"}):
-            for k in ("SS_TC_FUSE", "SS_TC_LAG"):
+            for k in ("SS_TC_FUSE", "SS_TC_LAG", "SS_TC_CPS"):
                 monkeypatch.delenv(k, raising=False)
             for k, v in env.items():
                 monkeypatch.setenv(k, v)
@@ -180,3 +183,22 @@ def test_fused_resblock_launch_is_bit_identical(sd_seed0, clip60, monkeypatch):
         for k in ("SS_TC_FUSE", "SS_TC_LAG", "SS_TC_CPS"):
             monkeypatch.delenv(k, raising=False)
         eng.close()
+
+
+def test_fused_mask_head_close_to_two_kernel_form(sd_seed0, clip60, monkeypatch):
+    """conv_flatten folded into conv9_1's epilogue (default) against the separate mask-head kernel reading the stored
+    hi/lo activations (SS_TC_FUSE_HEAD=0): same arithmetic up to fp32 summation order and the 2^-22 split rounding."""
+    from oracle import postproc as pp
+    from softspoken_b200.engine import Engine
+    g = load_golden("model_seed0.npz")
+    padded = torch.from_numpy(pp.pad_audio(clip60)).cuda()
+    eng = Engine(sd_seed0, 0, max_batch=16, mode="f16x3")
+    mel = eng.features(padded, torch.from_numpy(g["starts"][:16]))
+    fused = eng.classify(mel)
+    monkeypatch.setenv("SS_TC_FUSE_HEAD", "0")
+    plain = eng.classify(mel)
+    monkeypatch.delenv("SS_TC_FUSE_HEAD")
+    err = float((fused - plain).abs().max() / plain.abs().max())
+    print(f"fused vs two-kernel mask head: rel diff {err:.3e}")
+    assert err <= 2e-6
+    eng.close()

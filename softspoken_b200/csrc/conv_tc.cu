@@ -345,6 +345,7 @@ struct TcState {
   int* err = nullptr;
   float* head_part = nullptr;  // [max_batch][128][256][4] conv_flatten partials written by conv9_1's epilogue
   int* flags = nullptr;        // per-unit completion counts of a fused ResBlock launch (TcJob)
+  int* flags2 = nullptr;
   int flags_cap = 0;
   long long* prof = nullptr;   // [kNumSMs][8] role timers of the selected conv launch (debug)
   int prof_layer = -1;         // launch index to capture (-1: none)
@@ -447,6 +448,7 @@ int pack_conv(TcState* st, const float* w, int taps, int cin, int cout, float sc
 
 constexpr size_t kSmemTail = (2 * kMaxStages + 4) * 8 + 2 * 128 * 4 + 16;   // barriers + bias of both phases + TMEM slot
 
+constexpr int kDefaultRing = 8;    // images of the intermediate tensor kept by a fused ResBlock launch (0: whole batch)
 constexpr int kDefaultLag = 160;   // units by which conv2 trails conv1 in a fused ResBlock launch (> one round of 148 CTAs)
 constexpr int kMinUnitsForPairs = 4 * kNumSMs;
 constexpr int kDefaultPairPolicy = 0;   // measured with the two-issuer kernel (batch 256): G = 1 everywhere is 2 % faster   // use two-group units only while >= 4 waves of them remain
@@ -456,22 +458,35 @@ int launch_conv_npg(TcJob job, int B, cudaStream_t st) {
   TcConv& p = job.c[0];
   constexpr int MT = TilesPerUnit<N, Dual>::value;
   const size_t sb = stage_bytes(N, p.W, G * MT, Dual);
-  int stages = (int)((kSmemBudget - kSmemTail) / sb);
-  if (stages > kMaxStages) stages = kMaxStages;
-  SS_REQUIRE(stages >= 2, SS_E_ARG, "conv stage of %zu bytes does not fit twice in shared memory", sb);
-  p.stages = stages;
-  {
-    // K-chunks of a 1x1 source per stage-sized slot (SS_TC_CPS caps it; 1 = one chunk per stage as for 3x3 sources)
-    const char* ce = getenv("SS_TC_CPS");
-    const int cap = ce ? atoi(ce) : 4;
-    const size_t chunk1 = (size_t)G * MT * 128 * 32 + (Dual ? 2 : 1) * (size_t)N * 32;
-    int cps = (int)(sb / chunk1);
-    if (cps > cap) cps = cap;
-    p.cps = cps < 1 ? 1 : cps;
+  // Ring slot size.  Every stage costs a fixed hand-over (full/empty barrier round trip and an MMA-issue bubble,
+  // ~500-1000 cycles measured with the tuning hooks), which a 3x3 stage hides behind its 9 x MT MMAs and a 1x1 stage
+  // (MT MMAs per chunk) does not: 1x1 sources therefore pack several K-chunks into one slot, and when a launch has
+  // many of them (the residual branch of a decoder block reads 64-256 channels) the slot is enlarged — down to three
+  // slots — so that up to `cap` chunks fit.  SS_TC_CPS caps the chunks per stage (1 = one chunk per stage everywhere).
+  const char* ce = getenv("SS_TC_CPS");
+  const int cap = ce ? atoi(ce) : 4;
+  const size_t chunk1 = (size_t)G * MT * 128 * 32 + (Dual ? 2 : 1) * (size_t)N * 32;
+  int most1 = 0;
+  for (int ph = 0; ph < job.n_phase; ++ph)
+    for (int i = 0; i < job.c[ph].n_src; ++i)
+      if (job.c[ph].src[i].taps == 1 && job.c[ph].src[i].n_chunks > most1) most1 = job.c[ph].src[i].n_chunks;
+  size_t stride = sb;
+  int cps = (int)(sb / chunk1);
+  for (int want = (most1 < cap ? most1 : cap); want > cps; --want) {
+    const size_t need = (size_t)want * chunk1;
+    if ((kSmemBudget - kSmemTail) / need >= 3) { stride = need > sb ? need : sb; cps = want; break; }
   }
+  if (cps > cap) cps = cap;
+  p.cps = cps < 1 ? 1 : cps;
+  stride = (stride + 127) & ~(size_t)127;
+  p.stage_stride = (int)stride;
+  int stages = (int)((kSmemBudget - kSmemTail) / stride);
+  if (stages > kMaxStages) stages = kMaxStages;
+  SS_REQUIRE(stages >= 2, SS_E_ARG, "conv stage of %zu bytes does not fit twice in shared memory", stride);
+  p.stages = stages;
   static const int debug = [] { const char* e = getenv("SS_TC_DEBUG"); return e ? atoi(e) : 0; }();
   p.debug = debug;
-  const size_t smem = (size_t)stages * sb + kSmemTail;
+  const size_t smem = (size_t)stages * stride + kSmemTail;
   static bool configured = false;
   if (!configured) {
     SS_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<N, P, Dual, G>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -488,6 +503,25 @@ int launch_conv_npg(TcJob job, int B, cudaStream_t st) {
     SS_REQUIRE(p.total_units <= job.flags_cap, SS_E_ARG, "fused ResBlock launch: %d units exceed the flag array",
                p.total_units);
     SS_CUDA_CHECK(cudaMemsetAsync(job.flags, 0, (size_t)p.total_units * sizeof(int), st));
+    // ring mode for the intermediate tensor (TcJob::ring): only when the ring is shorter than the batch and the
+    // units it makes a c[0] unit wait for precede that unit in the item order
+    const int lag_eff = job.lag < p.total_units ? job.lag : p.total_units;
+    int ring = job.ring_request > 0 ? job.ring_request : 0;
+    if (ring > 0) {
+      // the units a c[0] unit waits for must lie >= 2 rounds of the grid (296 items) before it in the item order, or
+      // the wait stalls for real: 2 (ring * units_per_image - lag) - 3 >= 2 * 148  (measured: a thin margin costs 35 %)
+      const int need = (lag_eff + 2 * kNumSMs + 8 + p.units_per_image - 1) / p.units_per_image;
+      if (ring < need) ring = need;
+      if (ring >= B) ring = 0;
+    }
+    job.ring = ring;
+    job.c[0].out_ring = ring;
+    for (int i = 0; i < job.c[1].n_src; ++i)
+      if (job.c[1].src[i].ring < 0) job.c[1].src[i].ring = ring;      // marked by the host: reads the intermediate
+    if (ring > 0) SS_CUDA_CHECK(cudaMemsetAsync(job.flags2, 0, (size_t)p.total_units * sizeof(int), st));
+  } else {
+    for (int i = 0; i < job.c[0].n_src; ++i)
+      if (job.c[0].src[i].ring < 0) job.c[0].src[i].ring = 0;
   }
   conv_tc_kernel<N, P, Dual, G><<<grid, kTcThreads, smem, st>>>(job);
   SS_CUDA_CHECK(cudaGetLastError());
@@ -543,27 +577,28 @@ int launch_conv(Prec prec, const TcJob& p, int N, int B, cudaStream_t st) {
 //    small (Ootomo & Yokota 2022 observe the same for mma.sync; tools/precision_study.py measures it here).
 enum class Terms { All, Corrections, Main };
 
-void add_sources(TcConv* p, const TcState* s, const Tensor& x, int plane0, const PackedConv& w, Terms terms) {
+void add_sources(TcConv* p, const TcState* s, const Tensor& x, int plane0, const PackedConv& w, Terms terms,
+                 int ring = 0) {
   const int part_elems = w.taps * w.n * 16;
   const int chunk_elems = w.parts * part_elems;
   if (!is_split(s->prec)) {
     if (terms != Terms::Corrections)
-      p->src[p->n_src++] = TcSource{x.data, x.planes, plane0, w.n_chunks, w.taps, 0, chunk_elems, w.w};
+      p->src[p->n_src++] = TcSource{x.data, x.planes, plane0, w.n_chunks, w.taps, 0, ring, chunk_elems, w.w};
     return;
   }
   if (w.dual) {
     if (terms != Terms::Corrections) {
-      p->src[p->n_src++] = TcSource{x.data, x.planes, plane0, w.n_chunks, w.taps, 1, chunk_elems, w.w};
-      p->src[p->n_src++] = TcSource{x.lo, x.planes, plane0, w.n_chunks, w.taps, 2, part_elems, w.w_hi};
+      p->src[p->n_src++] = TcSource{x.data, x.planes, plane0, w.n_chunks, w.taps, 1, ring, chunk_elems, w.w};
+      p->src[p->n_src++] = TcSource{x.lo, x.planes, plane0, w.n_chunks, w.taps, 2, ring, part_elems, w.w_hi};
     }
     return;
   }
   if (terms != Terms::Main) {
-    p->src[p->n_src++] = TcSource{x.lo, x.planes, plane0, w.n_chunks, w.taps, 0, chunk_elems, w.w};
-    p->src[p->n_src++] = TcSource{x.data, x.planes, plane0, w.n_chunks, w.taps, 0, chunk_elems, w.w + part_elems};
+    p->src[p->n_src++] = TcSource{x.lo, x.planes, plane0, w.n_chunks, w.taps, 0, ring, chunk_elems, w.w};
+    p->src[p->n_src++] = TcSource{x.data, x.planes, plane0, w.n_chunks, w.taps, 0, ring, chunk_elems, w.w + part_elems};
   }
   if (terms != Terms::Corrections)
-    p->src[p->n_src++] = TcSource{x.data, x.planes, plane0, w.n_chunks, w.taps, 0, chunk_elems, w.w};
+    p->src[p->n_src++] = TcSource{x.data, x.planes, plane0, w.n_chunks, w.taps, 0, ring, chunk_elems, w.w};
 }
 
 // One ResBlock: t = relu(conv3x3(x) + b1);  out = relu(conv3x3(t) + conv1x1(x) + b2 + b_res).
@@ -583,10 +618,10 @@ int tc_res_block(TcState* s, int which, const Tensor& x, int x_plane0, Tensor& o
   p.out = t.data; p.out_lo = t.lo; p.out_planes_total = t.planes; p.out_plane0 = 0; p.upsample = 0;
   p.err = s->err;
   TcConv q{};
-  add_sources(&q, s, t, 0, rb.c2, Terms::Corrections);
+  add_sources(&q, s, t, 0, rb.c2, Terms::Corrections, -1);     // -1: "the intermediate tensor", ring resolved at launch
   add_sources(&q, s, x, x_plane0, rb.res, Terms::Corrections);
   add_sources(&q, s, x, x_plane0, rb.res, Terms::Main);
-  add_sources(&q, s, t, 0, rb.c2, Terms::Main);
+  add_sources(&q, s, t, 0, rb.c2, Terms::Main, -1);
   q.H = x.H; q.W = x.W;
   q.bias = rb.bias2;
   q.inv_scale = rb.inv_scale2;
@@ -604,10 +639,13 @@ int tc_res_block(TcState* s, int which, const Tensor& x, int x_plane0, Tensor& o
   const char* le = getenv("SS_TC_LAG");
   const int fuse = fe ? atoi(fe) : 0;
   const int lag = le ? atoi(le) : kDefaultLag;
+  const char* re = getenv("SS_TC_RING");
   TcJob job{};
   job.flags = s->flags;
+  job.flags2 = s->flags2;
   job.flags_cap = s->flags_cap;
   job.lag = lag;
+  job.ring_request = fuse ? (re ? atoi(re) : kDefaultRing) : 0;
   if (fuse) {
     p.prof = (s->launch_index++ == s->prof_layer) ? s->prof : nullptr;
     job.c[0] = p; job.c[1] = q; job.n_phase = 2;
@@ -619,7 +657,7 @@ int tc_res_block(TcState* s, int which, const Tensor& x, int x_plane0, Tensor& o
   if (rc) return rc;
   q.prof = (s->launch_index++ == s->prof_layer) ? s->prof : nullptr;
   job.c[0] = q;
-  return launch_conv(s->prec, job, N, B, st);
+  return launch_conv(s->prec, job, N, B, st);     // (the -1 ring marks of q's sources resolve to 0 in the launcher)
 }
 
 template <Prec P>
@@ -686,6 +724,7 @@ int tc_build(ss_ctx* ctx, Prec prec, TcState** out) {
   s->bytes += (size_t)B * kMels * kFrames * 4 * sizeof(float);
   s->flags_cap = B * (((kMels + 2) * (kFrames + 2) + 255) / 256);      // smallest unit: 256 positions
   SS_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&s->flags), (size_t)s->flags_cap * sizeof(int)));
+  SS_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&s->flags2), (size_t)s->flags_cap * sizeof(int)));
   SS_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&s->prof), kNumSMs * 8 * sizeof(long long)));
   SS_CUDA_CHECK(cudaMemset(s->prof, 0, kNumSMs * 8 * sizeof(long long)));
 #define T(t, C, H, W) do { if ((rc = alloc_tensor(s, &s->t, B, C, H, W))) return rc; } while (0)
@@ -798,6 +837,7 @@ void tc_destroy(ss_ctx* ctx) {
     }
     if (s->err) cudaFree(s->err);
     if (s->flags) cudaFree(s->flags);
+    if (s->flags2) cudaFree(s->flags2);
     if (s->head_part) cudaFree(s->head_part);
     if (s->prof) cudaFree(s->prof);
     delete s;

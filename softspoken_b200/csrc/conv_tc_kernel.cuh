@@ -193,6 +193,8 @@ struct TcSource {
   int taps;            // 9 (3x3) or 1 (1x1, centre)
   int kind;            // 0: N columns into the main columns; 1: 2N columns (main | correction), dual weights;
                        // 2: N columns into the correction columns
+  int ring;            // 0: image b of the batch is image b of the tensor; R > 0: it lives in slot b % R (the
+                       // intermediate tensor of a fused ResBlock launch, see TcJob)
   int w_stride;        // 16-bit elements between consecutive chunks of `w`
   const uint16_t* w;   // plain: [n_chunks][parts][taps][2][N][8] (pointing at the part to use);
                        // dual:  [n_chunks][taps][2][2N][8] (rows 0..N-1 = w_hi, N..2N-1 = w_lo)
@@ -208,6 +210,7 @@ struct TcConv {
   uint16_t* out;       // hi (or only) output tensor
   uint16_t* out_lo;    // residual output tensor (split precision), else null
   int out_planes_total, out_plane0, upsample;
+  int out_ring;        // like TcSource::ring, for the output tensor
   // Mask-head fusion (N = 32, the last ResBlock of the mask path): when head_w is set the epilogue does not store
   // the activations but their contraction with conv_flatten's weights for the position's mel row,
   //   head_out[b][y][x][k] = sum_c act[c] * head_w[y][c][k]   (k < 4; pytorch_neural_nets.py:133-134,188-190),
@@ -219,6 +222,7 @@ struct TcConv {
   int units_per_image, total_units;
   int stages;          // smem ring depth (<= kMaxStages)
   int cps;             // K-chunks a stage of a 1x1 source carries (>= 1; see the producer)
+  int stage_stride;    // bytes per smem ring slot (>= the 3x3 stage; larger when that buys more 1x1 chunks per stage)
   int* err;            // [0] pipeline time-out code, [1] scratch of the tuning hooks, [2] fp16 range overflow seen
   long long* prof;     // optional [gridDim.x][8] cycle counters (role wait/busy times), may be null
   int debug;           // tuning experiments only: 1 = producer skips the copies, 2 = epilogue skips the stores
@@ -243,6 +247,15 @@ struct TcJob {
   int lag;             // units by which c[1] trails c[0]
   int* flags;          // [total_units], zeroed before the launch (fused launches only)
   int flags_cap;
+  // Ring mode (ring > 0): the intermediate tensor holds only `ring` images, image b in slot b % ring, so that it is
+  // rewritten while its lines are still dirty in L2 and never travels to HBM.  The c[0] unit (b, u) may overwrite
+  // what the c[1] units (b - ring, u-1 .. u+1) still read, so those bump flags2[unit] when they are done (their
+  // copies completed long before their epilogue runs) and the c[0] producer waits for them first.  The host only
+  // enables the ring when ring * units_per_image > lag + 2, i.e. when those units precede the waiting one in the
+  // item order (no deadlock), which also makes the wait a formality.
+  int ring;
+  int ring_request;    // host-side wish (images); the launcher derives `ring` from it
+  int* flags2;         // [total_units], zeroed before the launch
 };
 
 // item -> (phase, unit) of the interleaved schedule above (T units per phase, D = min(lag, T))
@@ -334,7 +347,7 @@ conv_tc_kernel(const TcJob job) {
   const int halo = Wp + 1;
   const int L = G * MT * 128 + 2 * halo;                // positions staged per plane
   const uint32_t a_bytes = (uint32_t)L * 32u;           // two planes
-  const uint32_t stage_sz = a_bytes + (uint32_t)kWpartsMax * 9u * N * 32u;
+  const uint32_t stage_sz = (uint32_t)p.stage_stride;   // >= a_bytes + kWpartsMax * 9 * N * 32 (host-checked)
   const int S = p.stages;
   const int cps = p.cps;
   const uint32_t run1 = (uint32_t)(G * MT * 128) * 16u;      // one plane of a 1x1 source's chunk (no halo)
@@ -383,6 +396,13 @@ conv_tc_kernel(const TcJob job) {
       const int b = u / p.units_per_image;
       const int lu = u - b * p.units_per_image;
       const int lo = lu * G * MT * 128;   // first staged position (= q0 - halo)
+      if (phase == 0 && job.ring > 0 && b >= job.ring) {
+        const int v0 = u - job.ring * p.units_per_image;       // same local unit, `ring` images earlier
+        ok = flag_wait(job.flags2 + v0, 8, p.err, 6);
+        if (ok && lu > 0) ok = flag_wait(job.flags2 + v0 - 1, 8, p.err, 6);
+        if (ok && lu < p.units_per_image - 1) ok = flag_wait(job.flags2 + v0 + 1, 8, p.err, 6);
+        if (!ok) break;
+      }
       if (phase == 1) {
         // the units of c[0] whose output this unit reads must be complete (see TcJob), and their generic-proxy
         // stores visible to the async proxy that performs the bulk copies
@@ -405,7 +425,8 @@ conv_tc_kernel(const TcJob job) {
           ok = mbar_wait_t(empty0 + 8 * st, ph ^ 1u, p.err, 1, w_empty);
           if (!ok) break;
           const uint32_t dst = smem_u32(stage0 + (size_t)st * stage_sz);
-          const uint16_t* plane = src.in + (((int64_t)b * src.planes_total + src.plane0 + 2 * kc) * HpWp + lo) * 8;
+          const int bs = src.ring ? b % src.ring : b;
+          const uint16_t* plane = src.in + (((int64_t)bs * src.planes_total + src.plane0 + 2 * kc) * HpWp + lo) * 8;
           if (dbg & 1) {
             if (elect_one()) mbar_arrive(full0 + 8 * st);
           } else if (src.taps == 1) {
@@ -548,7 +569,8 @@ conv_tc_kernel(const TcJob job) {
       const float* bias_p = bias_s + phase * N;
       const int64_t out_plane_stride = c.upsample ? (int64_t)(2 * p.H + 2) * Wp2 * 8 : (int64_t)HpWp * 8;
       const int b = u / p.units_per_image;
-      const int64_t img_off = ((int64_t)b * c.out_planes_total + c.out_plane0) * out_plane_stride;
+      const int bo = c.out_ring ? b % c.out_ring : b;
+      const int64_t img_off = ((int64_t)bo * c.out_planes_total + c.out_plane0) * out_plane_stride;
      for (int g = 0; g < G && ok; ++g) {
       const int buf = (G == 1) ? (k & 1) : g;
       const uint32_t f_parity = (G == 1) ? (((uint32_t)k >> 1) & 1u) : ((uint32_t)k & 1u);
@@ -646,6 +668,11 @@ conv_tc_kernel(const TcJob job) {
         __threadfence();
         __syncwarp();
         if (lane == 0) atomicAdd(job.flags + u, 1);
+      }
+      if (n_phase == 2 && phase == 1 && job.ring > 0) {
+        // this unit's copies of the intermediate tensor completed before its accumulators did: its slot may be reused
+        __syncwarp();
+        if (lane == 0) atomicAdd(job.flags2 + u, 1);
       }
     }
     if (out_of_range) p.err[2] = 1;

@@ -172,15 +172,16 @@ def test_fused_resblock_launch_is_bit_identical(sd_seed0, clip60, monkeypatch):
         monkeypatch.delenv("SS_TC_FUSE", raising=False)
         base = eng.classify(mel)
         for env in ({"SS_TC_FUSE": "1"}, {"SS_TC_FUSE": "1", "SS_TC_LAG": "3"}, {"SS_TC_FUSE": "1", "SS_TC_LAG": "100000"},
-                    {"SS_TC_CPS": "1"}):
-            for k in ("SS_TC_FUSE", "SS_TC_LAG", "SS_TC_CPS"):
+                    {"SS_TC_FUSE": "1", "SS_TC_RING": "0"}, {"SS_TC_FUSE": "1", "SS_TC_RING": "3"},
+                    {"SS_TC_FUSE": "1", "SS_TC_RING": "5", "SS_TC_LAG": "40"}, {"SS_TC_CPS": "1"}):
+            for k in ("SS_TC_FUSE", "SS_TC_LAG", "SS_TC_CPS", "SS_TC_RING"):
                 monkeypatch.delenv(k, raising=False)
             for k, v in env.items():
                 monkeypatch.setenv(k, v)
             got = eng.classify(mel)
             eng.check_health()
             assert torch.equal(base, got), (mode, env)
-        for k in ("SS_TC_FUSE", "SS_TC_LAG", "SS_TC_CPS"):
+        for k in ("SS_TC_FUSE", "SS_TC_LAG", "SS_TC_CPS", "SS_TC_RING"):
             monkeypatch.delenv(k, raising=False)
         eng.close()
 

@@ -51,11 +51,12 @@ def run_long(args):
     tiles = int(round(args.hours * 6))
     n = tiles * clip.size
     t0 = time.perf_counter()
-    audio = torch.empty(n, dtype=torch.float32).pin_memory()
+    audio = torch.empty(n, dtype=torch.int16 if args.pcm16 else torch.float32).pin_memory()
     view = audio.numpy()
     rng = np.random.default_rng(7)
     for i in range(tiles):
-        view[i * clip.size:(i + 1) * clip.size] = clip * np.float32(rng.uniform(0.5, 1.0))
+        tile = clip * np.float32(rng.uniform(0.5, 1.0))
+        view[i * clip.size:(i + 1) * clip.size] = np.rint(tile * 32767.0).astype(np.int16) if args.pcm16 else tile
     gen_s = time.perf_counter() - t0
     W = (n + 66150 + 13229) // 13230
     eng.reserve(n, 1 << 20)
@@ -77,12 +78,14 @@ def run_long(args):
     line = {
         "metric": "audio_hours_per_sec", "value": hours / dt, "unit": "audio-hours/s", "n_gpus": 1,
         "higher_is_better": True, "dtype": args.mode, "data": "synthetic",
-        "config": {"workload": f"config4: one {hours:.1f} h mono 22.05 kHz recording, host buffer streamed in chunks of "
+        "config": {"workload": f"config4: one {hours:.1f} h mono 22.05 kHz recording, host buffer "
+                               f"({'int16 samples of a PCM_16 file' if args.pcm16 else 'float32'}) streamed in chunks of "
                                "1024 windows (52,920-sample overlap), K5/K6 once over the whole timeline",
+                   "max_batch_windows": args.max_batch,
                    "windows": int(lg.shape[0]), "timeline_bins": int(lg.shape[0] * 51.2) + 256, "regions": int(len(reg)),
                    "planned_windows": int(W), "host_generation_s": round(gen_s, 1)},
         "x_realtime": hours * 3600.0 / dt, "seconds": dt,
-        "e2e": {"value": hours / dt, "unit": "audio-hours/s", "h2d_bytes_per_step": int(n * 4),
+        "e2e": {"value": hours / dt, "unit": "audio-hours/s", "h2d_bytes_per_step": int(n * (2 if args.pcm16 else 4)),
                 "d2h_bytes_per_step": int(lg.nbytes + reg.nbytes)},
         "checks": {"prefix_logits_bitwise_equal": same_logits, "prefix_regions_equal": same_regions,
                    "prefix_windows_compared": int(w_same)},
@@ -154,7 +157,8 @@ def main():
     ap.add_argument("--hours", type=float, default=24.0)
     ap.add_argument("--files", type=int, default=1000)
     ap.add_argument("--intervals", type=int, default=10000)
-    ap.add_argument("--max-batch", type=int, default=64)
+    ap.add_argument("--max-batch", type=int, default=1024)       # = the streaming chunk (1,024 windows)
+    ap.add_argument("--pcm16", action="store_true", help="config 4 from the int16 samples of a PCM_16 recording")
     ap.add_argument("--mode", default="f16x3")
     args = ap.parse_args()
     (run_long if args.what == "long" else run_silence)(args)

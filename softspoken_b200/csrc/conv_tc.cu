@@ -446,7 +446,7 @@ int pack_conv(TcState* st, const float* w, int taps, int cin, int cout, float sc
   return SS_OK;
 }
 
-constexpr size_t kSmemTail = (2 * kMaxStages + 4) * 8 + 2 * 128 * 4 + 16;   // barriers + bias of both phases + TMEM slot
+constexpr size_t kSmemTail = (2 * kMaxStages + 4) * 8 + 4 * 128 * 4 + 16;   // barriers + bias and scalar-residual weights of both phases + TMEM slot
 
 constexpr int kDefaultRing = 8;    // images of the intermediate tensor kept by a fused ResBlock launch (0: whole batch)
 constexpr int kDefaultLag = 160;   // units by which conv2 trails conv1 in a fused ResBlock launch (> one round of 148 CTAs)
@@ -604,7 +604,7 @@ void add_sources(TcConv* p, const TcState* s, const Tensor& x, int plane0, const
 // One ResBlock: t = relu(conv3x3(x) + b1);  out = relu(conv3x3(t) + conv1x1(x) + b2 + b_res).
 int tc_res_block(TcState* s, int which, const Tensor& x, int x_plane0, Tensor& out, int out_plane0, int upsample,
                  int B, cudaStream_t st, const float* head_w = nullptr, float* head_out = nullptr,
-                 bool store_out = true) {
+                 bool store_out = true, const float* res_x = nullptr, const float* res_w = nullptr) {
   const TcBlock& rb = s->rb[which];
   Tensor& t = s->t[which];
   const int N = rb.c1.n;
@@ -619,8 +619,13 @@ int tc_res_block(TcState* s, int which, const Tensor& x, int x_plane0, Tensor& o
   p.err = s->err;
   TcConv q{};
   add_sources(&q, s, t, 0, rb.c2, Terms::Corrections, -1);     // -1: "the intermediate tensor", ring resolved at launch
-  add_sources(&q, s, x, x_plane0, rb.res, Terms::Corrections);
-  add_sources(&q, s, x, x_plane0, rb.res, Terms::Main);
+  if (res_x == nullptr) {
+    add_sources(&q, s, x, x_plane0, rb.res, Terms::Corrections);
+    add_sources(&q, s, x, x_plane0, rb.res, Terms::Main);
+  } else {            // single-channel block input: the residual branch is an FMA in the epilogue (TcConv::res_x)
+    q.res_x = res_x;
+    q.res_w = res_w;
+  }
   add_sources(&q, s, t, 0, rb.c2, Terms::Main, -1);
   q.H = x.H; q.W = x.W;
   q.bias = rb.bias2;
@@ -770,7 +775,14 @@ int classify_tc_p(ss_ctx* ctx, TcState* s, const float* mel, int n_windows, floa
                                                                  s->x0.lo, n_pix);
     SS_CUDA_CHECK(cudaGetLastError());
     count_launch();
-    SS_TRY(tc_res_block(s, RB_CONV1, s->x0, 0, s->m4, 0, 0, B, st));
+    {
+      // conv1_1's input has one channel: its 1x1 residual is res_w[c] * mel in conv2's epilogue (SS_TC_SCALAR_RES=0
+      // keeps it as MMAs over the im2col'd operand tensor)
+      const char* sr = getenv("SS_TC_SCALAR_RES");
+      const bool scalar = sr == nullptr || atoi(sr) != 0;
+      SS_TRY(tc_res_block(s, RB_CONV1, s->x0, 0, s->m4, 0, 0, B, st, nullptr, nullptr, true,
+                          scalar ? mel + (int64_t)b0 * kMels * kFrames : nullptr, scalar ? ctx->rb[RB_CONV1].res.w : nullptr));
+    }
     SS_TRY(tc_pool_p<P>(s->m4, 0, 4, s->p1, B, st));
     SS_TRY(tc_res_block(s, RB_CONV2, s->p1, 0, s->m3, 0, 0, B, st));
     SS_TRY(tc_pool_p<P>(s->m3, 0, 8, s->p2, B, st));

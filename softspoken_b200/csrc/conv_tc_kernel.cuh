@@ -217,6 +217,11 @@ struct TcConv {
   // 16 bytes per position instead of 128: with out == null the 32-channel tensor is never written (it is kept only
   // when the spec head will read it), and the head kernel just sums 128 rows per frame — in a fixed order, so
   // results stay reproducible bit for bit and do not depend on the batch split.
+  // Scalar residual (conv1_1: the block input has ONE channel, so its 1x1 residual branch is res_w[c] * x per
+  // position — an FMA in the epilogue instead of two MMA stages that carry 15/16 zeros): res_x is the float32 input
+  // image [B][H][W] (the mel features), res_w the folded residual weights [N]; null = no scalar residual.
+  const float* res_x;
+  const float* res_w;
   const float* head_w;   // [128 mel][32][4] float32 or null
   float* head_out;       // [B][128][256][4] float32
   int units_per_image, total_units;
@@ -355,8 +360,8 @@ conv_tc_kernel(const TcJob job) {
   unsigned char* stage0 = smem;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)S * stage_sz);
   // bars: full[kMaxStages] | empty[kMaxStages] | acc_full[2] | acc_empty[2]
-  float* bias_s = reinterpret_cast<float*>(bars + 2 * kMaxStages + 4);       // [2][N]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bias_s + 2 * N);
+  float* bias_s = reinterpret_cast<float*>(bars + 2 * kMaxStages + 4);       // [2][N] bias, then [2][N] scalar-residual weights
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bias_s + 4 * N);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + kMaxStages);
@@ -373,7 +378,10 @@ conv_tc_kernel(const TcJob job) {
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  for (int i = threadIdx.x; i < n_phase * N; i += kTcThreads) bias_s[i] = job.c[i / N].bias[i % N];
+  for (int i = threadIdx.x; i < n_phase * N; i += kTcThreads) {
+    bias_s[i] = job.c[i / N].bias[i % N];
+    bias_s[2 * N + i] = job.c[i / N].res_w ? job.c[i / N].res_w[i % N] : 0.f;
+  }
   if (warp == 4) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
                  "n"(512));
@@ -584,6 +592,9 @@ conv_tc_kernel(const TcJob job) {
         const bool interior = (y >= 1) && (y <= p.H) && (x >= 1) && (x <= p.W);
         const bool in_tensor = pos < HpWp;
         const int64_t up = (int64_t)(2 * y - 1) * Wp2 + (2 * x - 1);
+        // scalar residual input of this position (0 outside the image or when the launch has none: the weights are 0 too)
+        const float rx = (c.res_x != nullptr && interior) ? __ldg(c.res_x + ((int64_t)b * p.H + (y - 1)) * p.W + (x - 1)) : 0.f;
+        const float* resw_p = bias_s + 2 * N + phase * N;
 #pragma unroll
         for (int n0 = 0; n0 < N; n0 += 32) {
           uint32_t v[32];
@@ -622,6 +633,10 @@ conv_tc_kernel(const TcJob job) {
             for (int h = 0; h < 4; ++h) {
               float f0 = fmaf(__uint_as_float(v[g * 8 + 2 * h]), inv_scale, bias_p[n0 + g * 8 + 2 * h]);
               float f1 = fmaf(__uint_as_float(v[g * 8 + 2 * h + 1]), inv_scale, bias_p[n0 + g * 8 + 2 * h + 1]);
+              if (c.res_x != nullptr) {
+                f0 = fmaf(rx, resw_p[n0 + g * 8 + 2 * h], f0);
+                f1 = fmaf(rx, resw_p[n0 + g * 8 + 2 * h + 1], f1);
+              }
               if (c.relu) { f0 = fmaxf(f0, 0.f); f1 = fmaxf(f1, 0.f); }
               if (!interior) { f0 = 0.f; f1 = 0.f; }
               if constexpr (PrecTraits<P>::fmt == 0) out_of_range |= (fmaxf(fabsf(f0), fabsf(f1)) > 65504.f);

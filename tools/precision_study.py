@@ -57,7 +57,8 @@ truth_acts, truth_logits = ref_taps(sd64, mel.double().unsqueeze(1))
 cpu_acts, cpu_logits = ref_taps(sd, mel.unsqueeze(1))
 rows["cpu f32 (reference arithmetic)"] = [rel(a, t) for a, t in zip(cpu_acts, truth_acts)] + [rel(cpu_logits, truth_logits)]
 for mode in ["fp32", "f16x3", "f16", "bf16"]:
-    lg = eng.classify(mel.cuda(), mode=mode).cpu()
+    lg, _ = eng.classify(mel.cuda(), want_spec=True, mode=mode)      # want_spec: conv9 is materialised only for the spec head
+    lg = lg.cpu()
     if mode == "fp32":
         rows["gpu fp32 (CUDA cores)"] = [float("nan")] * 10 + [rel(lg, truth_logits)]
         continue

@@ -47,25 +47,106 @@ def load_native_22050(path: str) -> np.ndarray:
     return load_mono_22050(path)
 
 
+class Journal:
+    """Restartable corpus runs.  The reference keeps no record of finished files —
+    `get_unprocessed_list` returns every file (root/code/frontend/silencer_ui.py:668-686), so a restart re-processes the
+    corpus and appends duplicate rows.  Here every rank appends one line per finished file to its own
+    `<prefix>.rank<r>` (no collective, flushed per group of files):
+
+        <sha1 of the file list>\t<file index>\t<start_bin>,<end_bin>;<start_bin>,<end_bin>;...
+
+    A later run — with ANY number of ranks — reads all `<prefix>.rank*`, skips the files found there (a file with no
+    detection has a line with an empty last field), shards only the rest and merges old and new triplets before the
+    rows are numbered, so the final CSV is byte-identical to an uninterrupted run.  Lines of another file list (hash
+    mismatch) and torn last lines are ignored."""
+
+    def __init__(self, prefix: str, files: Sequence[str], rank: int):
+        import hashlib
+        self.prefix = prefix
+        self.key = hashlib.sha1("\n".join(files).encode("utf-8", "surrogatepass")).hexdigest()
+        self.n_files = len(files)
+        self.path = f"{prefix}.rank{rank}"
+        self._fh = None
+
+    def load(self):
+        """-> {file_index: int32 [R,2]} of every complete line written for this file list by any earlier rank."""
+        import glob
+        done = {}
+        for path in sorted(glob.glob(glob.escape(self.prefix) + ".rank*")):
+            with open(path, "r") as f:
+                text = f.read()
+            lines = text.split("\n")[:-1]              # a line counts only once its newline is on disk
+            for ln in lines:
+                parts = ln.split("\t")
+                if len(parts) != 3 or parts[0] != self.key:
+                    continue
+                try:
+                    fi = int(parts[1])
+                    pairs = [tuple(int(v) for v in p.split(",")) for p in parts[2].split(";") if p]
+                except ValueError:
+                    continue
+                if 0 <= fi < self.n_files and all(len(p) == 2 for p in pairs):
+                    done[fi] = np.asarray(pairs, dtype=np.int32).reshape(-1, 2)
+        return done
+
+    def append(self, file_index: int, bins: np.ndarray) -> None:
+        if self._fh is None:
+            torn = False
+            if os.path.exists(self.path) and os.path.getsize(self.path) > 0:
+                with open(self.path, "rb") as f:
+                    f.seek(-1, os.SEEK_END)
+                    torn = f.read(1) != b"\n"
+            self._fh = open(self.path, "a")
+            if torn:                      # a crash left half a line: terminate it so that it cannot swallow the next one
+                self._fh.write("\n")
+        body = ";".join(f"{int(s)},{int(e)}" for s, e in np.asarray(bins).reshape(-1, 2))
+        self._fh.write(f"{self.key}\t{int(file_index)}\t{body}\n")
+
+    def sync(self) -> None:
+        if self._fh is not None:
+            self._fh.flush()
+            os.fsync(self._fh.fileno())
+
+    def close(self) -> None:
+        if self._fh is not None:
+            self.sync()
+            self._fh.close()
+            self._fh = None
+
+
 def detect_corpus(files: Sequence[str], detect_batch: Callable[[List[np.ndarray]], List[np.ndarray]],
                   load: Callable[[str], np.ndarray] = load_mono_22050, durations: Optional[Sequence[float]] = None,
-                  group_size: int = 8, device: Optional[torch.device] = None, next_id: int = 1):
+                  group_size: int = 8, device: Optional[torch.device] = None, next_id: int = 1,
+                  journal: Optional[str] = None):
     """-> list of CSV row dicts on rank 0 (None on the other ranks).
 
     `detect_batch(clips) -> [int32 [R,2] region bins per clip]` is `Engine.detect_host_batch` (or any stand-in
-    with that contract: the CPU tests drive this function with the oracle)."""
+    with that contract: the CPU tests drive this function with the oracle).  `journal`: path prefix of the
+    per-rank progress files that make the run restartable (`Journal`)."""
     world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
     rank = dist.get_rank() if world > 1 else 0
     if durations is None:
         durations = [wavio.duration_and_rate(f)[0] for f in files]
-    mine = ssdist.shard_files(durations, world)[rank]
-    parts = []
-    for g0 in range(0, len(mine), group_size):
-        idx = mine[g0:g0 + group_size]
-        clips = [load(files[i]) for i in idx]
-        for i, bins in zip(idx, detect_batch(clips)):
-            b = np.asarray(bins, dtype=np.int32).reshape(-1, 2)
-            parts.append(np.concatenate([np.full((len(b), 1), i, np.int32), b], axis=1))
+    jr = Journal(journal, files, rank) if journal else None
+    done = jr.load() if jr else {}
+    todo = [i for i in range(len(files)) if i not in done]
+    mine = [todo[k] for k in ssdist.shard_files([durations[i] for i in todo], world)[rank]]
+    # triplets of earlier runs enter the gather once, through rank 0
+    parts = [np.concatenate([np.full((len(b), 1), i, np.int32), b], axis=1) for i, b in sorted(done.items())] if rank == 0 else []
+    try:
+        for g0 in range(0, len(mine), group_size):
+            idx = mine[g0:g0 + group_size]
+            clips = [load(files[i]) for i in idx]
+            for i, bins in zip(idx, detect_batch(clips)):
+                b = np.asarray(bins, dtype=np.int32).reshape(-1, 2)
+                parts.append(np.concatenate([np.full((len(b), 1), i, np.int32), b], axis=1))
+                if jr:
+                    jr.append(i, b)
+            if jr:
+                jr.sync()
+    finally:
+        if jr:
+            jr.close()
     local = np.concatenate(parts) if parts else np.zeros((0, 3), np.int32)
     allrows = ssdist.gather_detections(local, device)
     if rank != 0:
@@ -96,7 +177,10 @@ def main(argv=None) -> int:
     ap.add_argument("out_csv")
     ap.add_argument("--checkpoint", default=None, help="reference checkpoint (.pth); seeded init if absent, as the reference")
     ap.add_argument("--mode", default=None)
-    ap.add_argument("--max-batch", type=int, default=256)
+    ap.add_argument("--max-batch", type=int, default=512)
+    ap.add_argument("--resume", action="store_true",
+                    help="keep per-rank progress files next to out_csv (<out_csv>.journal.rank<r>) and skip the files "
+                         "an earlier, interrupted run of the same file list already finished")
     args = ap.parse_args(argv)
     from . import checkpoint
     from .engine import Engine
@@ -115,7 +199,8 @@ def main(argv=None) -> int:
         print("No checkpoint found. Starting training from scratch.")     # NNDetector.py:52
         sd = checkpoint.synthetic_state_dict(0)
     eng = Engine(sd, local, max_batch=args.max_batch, **({"mode": args.mode} if args.mode else {}))
-    rows = detect_corpus(files, eng.detect_host_batch, load=load_native_22050, device=device)
+    rows = detect_corpus(files, eng.detect_host_batch, load=load_native_22050, device=device,
+                         journal=(args.out_csv + ".journal") if args.resume else None)
     if rows is not None:
         with open(args.out_csv, "w", newline="") as f:
             f.write(csv_text(rows))

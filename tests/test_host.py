@@ -258,3 +258,51 @@ def test_pcm16_host_helpers(tmp_path):
     assert wavio.read_wav_pcm16(pf) is None and corpus.load_native_22050(pf).dtype == np.float32
     x = (rng.standard_normal(10000) * 0.5).astype(np.float32)
     assert np.array_equal(wavio.encode_pcm16(x), osil.float_to_pcm16(x))
+
+
+def test_corpus_journal_resume(tmp_path):
+    """an interrupted corpus run resumed from its per-rank journal gives the CSV of an uninterrupted
+    run, skips the finished files (including those without detections), ignores a torn last line and the lines of
+    another file list."""
+    from softspoken_b200 import corpus
+    files = [f"/data/clip{i}.wav" for i in range(13)]
+    durations = [600.0] * len(files)
+    seen = []
+
+    def fake_load(path):
+        return np.full(4, float(files.index(path)), np.float32)
+
+    def make_detect(fail_after=None):
+        calls = {"n": 0}
+
+        def detect(clips):
+            calls["n"] += 1
+            if fail_after is not None and calls["n"] > fail_after:
+                raise RuntimeError("simulated crash")
+            out = []
+            for c in clips:
+                i = int(c[0])
+                seen.append(i)
+                out.append(np.sort(np.random.default_rng(i).integers(0, 51000, (i % 4, 2)), axis=1).astype(np.int32))
+            return out
+        return detect
+
+    clean = corpus.csv_text(corpus.detect_corpus(files, make_detect(), load=fake_load, durations=durations, group_size=3))
+    jp = os.path.join(tmp_path, "run.journal")
+    with pytest.raises(RuntimeError):
+        corpus.detect_corpus(files, make_detect(fail_after=2), load=fake_load, durations=durations, group_size=3, journal=jp)
+    first = corpus.Journal(jp, files, 0).load()
+    assert sorted(first) == [0, 1, 2, 3, 4, 5]                       # two groups of three files reached the disk
+    with open(jp + ".rank0", "a") as f:
+        f.write("deadbeef\t7\t1,2\n")                                # another file list
+        f.write(f"{corpus.Journal(jp, files, 0).key}\t8\t5,")         # torn line (no newline, half a pair)
+    del seen[:]
+    resumed = corpus.csv_text(corpus.detect_corpus(files, make_detect(), load=fake_load, durations=durations,
+                                                   group_size=3, journal=jp))
+    assert resumed == clean
+    assert sorted(seen) == list(range(6, 13))                        # nothing was recomputed
+    # a third run finds everything done and still writes the same CSV
+    del seen[:]
+    again = corpus.csv_text(corpus.detect_corpus(files, make_detect(), load=fake_load, durations=durations,
+                                                 group_size=3, journal=jp))
+    assert again == clean and seen == []

@@ -108,17 +108,37 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+__device__ __forceinline__ bool mbar_test_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+#ifndef SS_TC_SPIN
+#define SS_TC_SPIN 0
+#endif
 // Bounded wait: a protocol bug must not hang the GPU.  Returns false (and flags the error) on timeout.
+// kSpin (producer / MMA warps, -DSS_TC_SPIN=1 builds): poll with the non-blocking test_wait instead of the
+// suspending try_wait.
+template <bool kSpin = false>
 __device__ __noinline__ bool mbar_wait(uint32_t bar, uint32_t parity, int* err, int code) {
 #pragma unroll 1
-  for (uint32_t i = 0; i < kSpinLimit; ++i)
-    if (mbar_try_wait(bar, parity)) return true;
+  for (uint32_t i = 0; i < kSpinLimit; ++i) {
+    if constexpr (kSpin && SS_TC_SPIN) { if (mbar_test_wait(bar, parity)) return true; }
+    else { if (mbar_try_wait(bar, parity)) return true; }
+  }
   atomicExch(err, code);
   return false;
 }
+template <bool kSpin = false>
 __device__ __forceinline__ bool mbar_wait_t(uint32_t bar, uint32_t parity, int* err, int code, long long& acc) {
   const long long t0 = clock64();
-  const bool ok = mbar_wait(bar, parity, err, code);
+  const bool ok = mbar_wait<kSpin>(bar, parity, err, code);
   acc += clock64() - t0;
   return ok;
 }
@@ -127,8 +147,8 @@ __device__ __forceinline__ bool mbar_wait_t(uint32_t bar, uint32_t parity, int* 
 __device__ __forceinline__ bool mbar_wait_fast(uint32_t bar, uint32_t parity, int* err, int code, bool timing,
                                                long long& acc) {
   if (mbar_try_wait(bar, parity)) return true;
-  if (timing) return mbar_wait_t(bar, parity, err, code, acc);
-  return mbar_wait(bar, parity, err, code);
+  if (timing) return mbar_wait_t<true>(bar, parity, err, code, acc);
+  return mbar_wait<true>(bar, parity, err, code);
 }
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
@@ -430,7 +450,7 @@ conv_tc_kernel(const TcJob job) {
         for (int kc = 0; kc < src.n_chunks; kc += per_stage, ++it) {
           const int st = it % S;
           const uint32_t ph = (uint32_t)(it / S) & 1u;
-          ok = mbar_wait_t(empty0 + 8 * st, ph ^ 1u, p.err, 1, w_empty);
+          ok = mbar_wait_t<true>(empty0 + 8 * st, ph ^ 1u, p.err, 1, w_empty);
           if (!ok) break;
           const uint32_t dst = smem_u32(stage0 + (size_t)st * stage_sz);
           const int bs = src.ring ? b % src.ring : b;

@@ -446,7 +446,7 @@ int pack_conv(TcState* st, const float* w, int taps, int cin, int cout, float sc
   return SS_OK;
 }
 
-constexpr size_t kSmemTail = (2 * kMaxStages + 4) * 8 + 4 * 128 * 4 + 16;   // barriers + bias and scalar-residual weights of both phases + TMEM slot
+constexpr size_t kSmemTail = (2 * kMaxStages + 4) * 8 + 5 * 128 * 4 + 16;   // barriers + bias and scalar-residual weights of both phases + TMEM slot
 
 constexpr int kDefaultRing = 8;    // images of the intermediate tensor kept by a fused ResBlock launch (0: whole batch)
 constexpr int kDefaultLag = 160;   // units by which conv2 trails conv1 in a fused ResBlock launch (> one round of 148 CTAs)
@@ -496,6 +496,8 @@ int launch_conv_npg(TcJob job, int B, cudaStream_t st) {
   const int positions = p.H * (p.W + 2) - 2;          // (1,1) .. (H,W) in flattened padded coordinates
   p.units_per_image = (positions + G * MT * 128 - 1) / (G * MT * 128);
   p.total_units = p.units_per_image * B;
+  for (int ph = 0; ph < job.n_phase; ++ph)
+    SS_REQUIRE(job.c[ph].relu == 1, SS_E_ARG, "conv_tc_kernel applies ReLU unconditionally");
   const int items = p.total_units * job.n_phase;
   const int grid = items < kNumSMs ? items : kNumSMs;
   if (job.n_phase == 2) {

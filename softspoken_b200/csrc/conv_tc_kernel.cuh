@@ -74,6 +74,17 @@ __device__ __forceinline__ uint32_t pack_hi(float a, float b) {
     return *reinterpret_cast<uint32_t*>(&h);
   }
 }
+// same without the saturation (the caller has clamped already)
+template <Prec P>
+__device__ __forceinline__ uint32_t pack_rn(float a, float b) {
+  if constexpr (PrecTraits<P>::fmt == 1) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+  } else {
+    __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+  }
+}
 __device__ __forceinline__ uint32_t pack_lo_f16(float a, float b, uint32_t hi) {
   const float2 h = __half22float2(*reinterpret_cast<const __half2*>(&hi));
   __half2 l = __floats2half2_rn(a - h.x, b - h.y);
@@ -178,8 +189,8 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
         "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
         "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
       : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // One lane of a converged warp (the CUTLASS elect_one_sync idiom).  Keeping the role loops warp-uniform and
 // predicating only the issuing instruction lets the compiler hold descriptors in uniform registers, which
@@ -226,7 +237,7 @@ struct TcConv {
   int H, W;            // resolution of the inputs (and of the accumulator grid)
   const float* bias;   // [N]
   float inv_scale;     // accumulators are multiplied by this (weights are pre-scaled by a power of two) before the bias
-  int relu;
+  int relu;            // must be 1: every convolution on this path is followed by ReLU (the epilogue applies it always)
   uint16_t* out;       // hi (or only) output tensor
   uint16_t* out_lo;    // residual output tensor (split precision), else null
   int out_planes_total, out_plane0, upsample;
@@ -381,7 +392,8 @@ conv_tc_kernel(const TcJob job) {
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)S * stage_sz);
   // bars: full[kMaxStages] | empty[kMaxStages] | acc_full[2] | acc_empty[2]
   float* bias_s = reinterpret_cast<float*>(bars + 2 * kMaxStages + 4);       // [2][N] bias, then [2][N] scalar-residual weights
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bias_s + 4 * N);
+  float* zero_s = bias_s + 4 * N;                                            // [N] zeros: the "bias" of border positions
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(zero_s + N);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + kMaxStages);
@@ -402,6 +414,7 @@ conv_tc_kernel(const TcJob job) {
     bias_s[i] = job.c[i / N].bias[i % N];
     bias_s[2 * N + i] = job.c[i / N].res_w ? job.c[i / N].res_w[i % N] : 0.f;
   }
+  for (int i = threadIdx.x; i < N; i += kTcThreads) zero_s[i] = 0.f;
   if (warp == 4) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
                  "n"(512));
@@ -615,15 +628,21 @@ conv_tc_kernel(const TcJob job) {
         // scalar residual input of this position (0 outside the image or when the launch has none: the weights are 0 too)
         const float rx = (c.res_x != nullptr && interior) ? __ldg(c.res_x + ((int64_t)b * p.H + (y - 1)) * p.W + (x - 1)) : 0.f;
         const float* resw_p = bias_s + 2 * N + phase * N;
+        const float* bias_t = interior ? bias_p : zero_s;
+        const float scale_t = interior ? inv_scale : 0.f;
+        float vmax = 0.f;
 #pragma unroll
         for (int n0 = 0; n0 < N; n0 += 32) {
           uint32_t v[32];
           tc_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * kAccCols + mt * TS + n0), v);
           if constexpr (Dual) {
-            uint32_t cv[32];
+            uint32_t cv[32];      // both loads in flight under one wait
             tc_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * kAccCols + mt * TS + N + n0), cv);
+            tc_wait_ld();
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(cv[i]));
+          } else {
+            tc_wait_ld();
           }
           if constexpr (N == 32) {
             if (c.head_w != nullptr) {
@@ -634,7 +653,7 @@ conv_tc_kernel(const TcJob job) {
 #pragma unroll
                 for (int i = 0; i < 32; ++i) {
                   float f = fmaf(__uint_as_float(v[i]), inv_scale, bias_p[i]);
-                  if (c.relu) f = fmaxf(f, 0.f);
+                  f = fmaxf(f, 0.f);
                   const float4 w = __ldg(wrow + i);
                   acc.x = fmaf(f, w.x, acc.x);
                   acc.y = fmaf(f, w.y, acc.y);
@@ -649,18 +668,34 @@ conv_tc_kernel(const TcJob job) {
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
             uint32_t hw[4], lw[4];
+            // Border positions get scale 0 and a zero bias vector instead of a select per value: fma(acc, 0, 0) = +0.
+            // Every convolution of this network is followed by ReLU, so the fp16 clamp is one-sided and the range
+            // check a running maximum (tested once per tile).
+            const float4 b0 = *reinterpret_cast<const float4*>(bias_t + n0 + g * 8);
+            const float4 b1 = *reinterpret_cast<const float4*>(bias_t + n0 + g * 8 + 4);
+            const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+            float rw[8];
+            if (c.res_x != nullptr) {
+              const float4 r0 = *reinterpret_cast<const float4*>(resw_p + n0 + g * 8);
+              const float4 r1 = *reinterpret_cast<const float4*>(resw_p + n0 + g * 8 + 4);
+              rw[0] = r0.x; rw[1] = r0.y; rw[2] = r0.z; rw[3] = r0.w; rw[4] = r1.x; rw[5] = r1.y; rw[6] = r1.z; rw[7] = r1.w;
+            }
 #pragma unroll
             for (int h = 0; h < 4; ++h) {
-              float f0 = fmaf(__uint_as_float(v[g * 8 + 2 * h]), inv_scale, bias_p[n0 + g * 8 + 2 * h]);
-              float f1 = fmaf(__uint_as_float(v[g * 8 + 2 * h + 1]), inv_scale, bias_p[n0 + g * 8 + 2 * h + 1]);
+              float f0 = fmaf(__uint_as_float(v[g * 8 + 2 * h]), scale_t, bb[2 * h]);
+              float f1 = fmaf(__uint_as_float(v[g * 8 + 2 * h + 1]), scale_t, bb[2 * h + 1]);
               if (c.res_x != nullptr) {
-                f0 = fmaf(rx, resw_p[n0 + g * 8 + 2 * h], f0);
-                f1 = fmaf(rx, resw_p[n0 + g * 8 + 2 * h + 1], f1);
+                f0 = fmaf(rx, rw[2 * h], f0);
+                f1 = fmaf(rx, rw[2 * h + 1], f1);
               }
-              if (c.relu) { f0 = fmaxf(f0, 0.f); f1 = fmaxf(f1, 0.f); }
-              if (!interior) { f0 = 0.f; f1 = 0.f; }
-              if constexpr (PrecTraits<P>::fmt == 0) out_of_range |= (fmaxf(fabsf(f0), fabsf(f1)) > 65504.f);
-              hw[h] = pack_hi<P>(f0, f1);
+              f0 = fmaxf(f0, 0.f);
+              f1 = fmaxf(f1, 0.f);
+              if constexpr (PrecTraits<P>::fmt == 0) {
+                vmax = fmaxf(vmax, fmaxf(f0, f1));
+                f0 = fminf(f0, 65504.f);
+                f1 = fminf(f1, 65504.f);
+              }
+              hw[h] = pack_rn<P>(f0, f1);
               if constexpr (kSplit) lw[h] = pack_lo_f16(f0, f1, hw[h]);
               else lw[h] = 0u;
             }
@@ -691,8 +726,9 @@ conv_tc_kernel(const TcJob job) {
             }
           }
         }
+        if constexpr (PrecTraits<P>::fmt == 0) out_of_range |= (vmax > 65504.f);
       }
-      // all of this warp's TMEM reads of the buffer have completed (tcgen05.wait::ld in tc_ld32)
+      // all of this warp's TMEM reads of the buffer have completed (tcgen05.wait::ld after each load pair)
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(acce0 + 8 * buf);

@@ -112,6 +112,57 @@ __global__ void mel_to_planar(const float* __restrict__ mel, uint16_t* __restric
   store8<P>(out, out_lo, pix + (int64_t)Hp * Wp, hi8);
 }
 
+// conv1_1's first convolution on CUDA cores: t = relu(conv3x3(mel) + b1), C_in = 1 -> 32 channels, written as the
+// planar hi/lo operand tensor conv1_1's second convolution reads.  With one input channel the layer has nine MACs per
+// output value — as a tensor-core launch it was bound by its epilogue (5 k cycles per 512 positions against 0.35 k
+// of MMAs) and needed the im2col'd operand tensor of mel_to_planar; here it is a write-bound streaming kernel
+// (4.3 MB per window out, 0.13 MB in) in exact fp32, and x0 / mel_to_planar disappear from the path.
+// grid (128 / 8 row groups, 4 planes, B), 256 threads = the 256 frames of a mel row (a warp stores 512 contiguous
+// bytes); a thread walks 8 rows with its 72 weights in registers and a sliding 3 x 3 window of mel values.
+constexpr int kC1Rows = 8;     // mel rows per thread of conv1_direct (weights stay in registers across them)
+
+template <Prec P>
+__global__ void __launch_bounds__(kFrames)
+conv1_direct(const float* __restrict__ mel, const float* __restrict__ w /* [9][32] */, const float* __restrict__ bias,
+             uint16_t* __restrict__ out, uint16_t* __restrict__ out_lo, int* __restrict__ err) {
+  const int x = threadIdx.x, y0 = blockIdx.x * kC1Rows, pl = blockIdx.y;
+  const int64_t b = blockIdx.z;
+  float wr[9][8], br[8];
+#pragma unroll
+  for (int t = 0; t < 9; ++t)
+#pragma unroll
+    for (int k = 0; k < 8; ++k) wr[t][k] = __ldg(w + t * 32 + pl * 8 + k);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) br[k] = __ldg(bias + pl * 8 + k);
+  const float* img = mel + b * (int64_t)kMels * kFrames;
+  const int Wp = kFrames + 2, Hp = kMels + 2;
+  auto row3 = [&](int yy, float (&r)[3]) {       // mel[yy][x-1 .. x+1], zero outside the image
+    const bool in = (yy >= 0) && (yy < kMels);
+    r[0] = (in && x > 0) ? __ldg(img + yy * kFrames + x - 1) : 0.f;
+    r[1] = in ? __ldg(img + yy * kFrames + x) : 0.f;
+    r[2] = (in && x < kFrames - 1) ? __ldg(img + yy * kFrames + x + 1) : 0.f;
+  };
+  float m[3][3];
+  row3(y0 - 1, m[0]);
+  row3(y0, m[1]);
+  bool over = false;
+#pragma unroll
+  for (int r = 0; r < kC1Rows; ++r) {
+    row3(y0 + r + 1, m[(r + 2) % 3]);
+    float f[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      float acc = 0.f;
+#pragma unroll
+      for (int t = 0; t < 9; ++t) acc = fmaf(m[(r + t / 3) % 3][t % 3], wr[t][k], acc);
+      f[k] = fmaxf(acc + br[k], 0.f);
+      if constexpr (PrecTraits<P>::fmt == 0) over |= f[k] > 65504.f;
+    }
+    store8<P>(out, out_lo, ((b * 4 + pl) * Hp + (y0 + r + 1)) * (int64_t)Wp + (x + 1), f);
+  }
+  if (over) err[2] = 1;       // fp16 operand modes: the activation was saturated (SS_E_RANGE)
+}
+
 // MaxPool2d(2) on planar tensors: in planes [plane0, plane0+planes) of a tensor with in_planes_total planes at
 // H x W  ->  out [B][planes][H/2+2][W/2+2][8].  The max is taken on the reconstructed fp32 values.
 template <Prec P>
@@ -606,7 +657,8 @@ void add_sources(TcConv* p, const TcState* s, const Tensor& x, int plane0, const
 // One ResBlock: t = relu(conv3x3(x) + b1);  out = relu(conv3x3(t) + conv1x1(x) + b2 + b_res).
 int tc_res_block(TcState* s, int which, const Tensor& x, int x_plane0, Tensor& out, int out_plane0, int upsample,
                  int B, cudaStream_t st, const float* head_w = nullptr, float* head_out = nullptr,
-                 bool store_out = true, const float* res_x = nullptr, const float* res_w = nullptr) {
+                 bool store_out = true, const float* res_x = nullptr, const float* res_w = nullptr,
+                 bool c1_done = false) {
   const TcBlock& rb = s->rb[which];
   Tensor& t = s->t[which];
   const int N = rb.c1.n;
@@ -653,6 +705,11 @@ int tc_res_block(TcState* s, int which, const Tensor& x, int x_plane0, Tensor& o
   job.flags_cap = s->flags_cap;
   job.lag = lag;
   job.ring_request = fuse ? (re ? atoi(re) : kDefaultRing) : 0;
+  if (c1_done) {            // the intermediate tensor was produced by another kernel (conv1_direct): conv2 only
+    q.prof = (s->launch_index++ == s->prof_layer) ? s->prof : nullptr;
+    job.c[0] = q; job.n_phase = 1;
+    return launch_conv(s->prec, job, N, B, st);
+  }
   if (fuse) {
     p.prof = (s->launch_index++ == s->prof_layer) ? s->prof : nullptr;
     job.c[0] = p; job.c[1] = q; job.n_phase = 2;
@@ -773,17 +830,26 @@ int classify_tc_p(ss_ctx* ctx, TcState* s, const float* mel, int n_windows, floa
     const int B = (n_windows - b0 < s->max_batch) ? (n_windows - b0) : s->max_batch;
 #define SS_TRY(e) do { if ((rc = (e))) return rc; } while (0)
     const int64_t n_pix = (int64_t)B * kMels * kFrames;
-    mel_to_planar<P><<<(int)((n_pix + 255) / 256), 256, 0, st>>>(mel + (int64_t)b0 * kMels * kFrames, s->x0.data,
-                                                                 s->x0.lo, n_pix);
-    SS_CUDA_CHECK(cudaGetLastError());
-    count_launch();
-    {
-      // conv1_1's input has one channel: its 1x1 residual is res_w[c] * mel in conv2's epilogue (SS_TC_SCALAR_RES=0
-      // keeps it as MMAs over the im2col'd operand tensor)
+    const float* mel_b = mel + (int64_t)b0 * kMels * kFrames;
+    const char* dc = getenv("SS_TC_DIRECT_C1");
+    if (dc == nullptr || atoi(dc) != 0) {
+      // conv1_1: first convolution on CUDA cores straight from mel, second on the tensor cores with the
+      // single-channel residual as an epilogue FMA
+      conv1_direct<P><<<dim3(kMels / kC1Rows, 4, B), kFrames, 0, st>>>(mel_b, ctx->rb[RB_CONV1].c1.w, ctx->rb[RB_CONV1].c1.b,
+                                                           s->t[RB_CONV1].data, s->t[RB_CONV1].lo, s->err);
+      SS_CUDA_CHECK(cudaGetLastError());
+      count_launch();
+      SS_TRY(tc_res_block(s, RB_CONV1, s->x0, 0, s->m4, 0, 0, B, st, nullptr, nullptr, true, mel_b,
+                          ctx->rb[RB_CONV1].res.w, true));
+    } else {
+      // legacy form (A/B measurements, tests of the im2col'd operand tensor): both convolutions as tcgen05 launches
+      mel_to_planar<P><<<(int)((n_pix + 255) / 256), 256, 0, st>>>(mel_b, s->x0.data, s->x0.lo, n_pix);
+      SS_CUDA_CHECK(cudaGetLastError());
+      count_launch();
       const char* sr = getenv("SS_TC_SCALAR_RES");
       const bool scalar = sr == nullptr || atoi(sr) != 0;
       SS_TRY(tc_res_block(s, RB_CONV1, s->x0, 0, s->m4, 0, 0, B, st, nullptr, nullptr, true,
-                          scalar ? mel + (int64_t)b0 * kMels * kFrames : nullptr, scalar ? ctx->rb[RB_CONV1].res.w : nullptr));
+                          scalar ? mel_b : nullptr, scalar ? ctx->rb[RB_CONV1].res.w : nullptr));
     }
     SS_TRY(tc_pool_p<P>(s->m4, 0, 4, s->p1, B, st));
     SS_TRY(tc_res_block(s, RB_CONV2, s->p1, 0, s->m3, 0, 0, B, st));

@@ -43,7 +43,7 @@ def _dump(engine, which, n):
     return out.cpu()
 
 
-def test_layerwise_against_oracle(engine, sd_seed0, clip60):
+def test_layerwise_against_oracle(engine, sd_seed0, clip60, monkeypatch):
     from oracle import model as om
     from oracle import postproc as pp
     act_tol, logit_tol = TOL[engine.mode]
@@ -62,8 +62,15 @@ def test_layerwise_against_oracle(engine, sd_seed0, clip60):
     ref = {0: taps["conv1"], 1: taps["conv2"], 2: taps["conv3"], 3: taps["conv4"],
            4: taps["bottleneck"], 5: up(taps["encoder_out"]), 6: up(taps["conv6"]), 7: up(taps["conv7"]),
            8: up(taps["conv8"]), 9: taps["conv9"]}
-    # first operand tensor: the mel image unrolled into 9 shifted copies (im2col in K), channels 9..15 zero
+    # legacy form of conv1_1 (SS_TC_DIRECT_C1=0: both convolutions on the tensor cores): its first operand tensor is
+    # the mel image unrolled into 9 shifted copies (im2col in K), channels 9..15 zero; logits agree with the default
+    # form (first convolution on CUDA cores) to rounding
+    monkeypatch.setenv("SS_TC_DIRECT_C1", "0")
+    legacy, _ = engine.classify(mel, want_spec=True)
+    monkeypatch.delenv("SS_TC_DIRECT_C1")
+    assert float((legacy - logits).abs().max() / logits.abs().max()) <= 10 * logit_tol
     x0 = _dump(engine, 11, 3)
+    logits, _ = engine.classify(mel, want_spec=True)       # back to the default form for the dumps below
     m = mel.cpu()
     mp = torch.nn.functional.pad(m, (1, 1, 1, 1))
     e0 = max(float((x0[:, c] - mp[:, c // 3:c // 3 + 128, c % 3:c % 3 + 256]).abs().max() / m.abs().max())

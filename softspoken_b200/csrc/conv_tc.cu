@@ -792,7 +792,6 @@ int tc_build(ss_ctx* ctx, Prec prec, TcState** out) {
   SS_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&s->prof), kNumSMs * 8 * sizeof(long long)));
   SS_CUDA_CHECK(cudaMemset(s->prof, 0, kNumSMs * 8 * sizeof(long long)));
 #define T(t, C, H, W) do { if ((rc = alloc_tensor(s, &s->t, B, C, H, W))) return rc; } while (0)
-  T(x0, 16, 128, 256);
   T(m4, 64, 128, 256);
   T(p1, 32, 64, 128);
   T(m3, 128, 64, 128);
@@ -839,10 +838,13 @@ int classify_tc_p(ss_ctx* ctx, TcState* s, const float* mel, int n_windows, floa
                                                            s->t[RB_CONV1].data, s->t[RB_CONV1].lo, s->err);
       SS_CUDA_CHECK(cudaGetLastError());
       count_launch();
-      SS_TRY(tc_res_block(s, RB_CONV1, s->x0, 0, s->m4, 0, 0, B, st, nullptr, nullptr, true, mel_b,
+      // (the block-input argument only supplies the geometry here: conv2 reads t, the residual reads mel)
+      SS_TRY(tc_res_block(s, RB_CONV1, s->t[RB_CONV1], 0, s->m4, 0, 0, B, st, nullptr, nullptr, true, mel_b,
                           ctx->rb[RB_CONV1].res.w, true));
     } else {
-      // legacy form (A/B measurements, tests of the im2col'd operand tensor): both convolutions as tcgen05 launches
+      // legacy form (A/B measurements, tests of the im2col'd operand tensor): both convolutions as tcgen05 launches;
+      // its operand tensor is allocated on first use
+      if (!s->x0.alloc) SS_TRY(alloc_tensor(s, &s->x0, s->max_batch, 16, 128, 256));
       mel_to_planar<P><<<(int)((n_pix + 255) / 256), 256, 0, st>>>(mel_b, s->x0.data, s->x0.lo, n_pix);
       SS_CUDA_CHECK(cudaGetLastError());
       count_launch();

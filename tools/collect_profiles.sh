@@ -9,10 +9,10 @@ BQ="python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-other-modes"
 python bench.py > $P/${TAG}_bench.log 2> $P/${TAG}_bench.err
 python bench.py --impl reference --steps 2 --warmup 1 > $P/${TAG}_ref.log 2>&1
 $BQ > $P/${TAG}_plain_bench.log 2>&1 && \
-  ncu --metrics gpu__time_duration.sum --clock-control none -c 800 --csv --log-file $P/${TAG}_launches_bench.csv $BQ > $P/${TAG}_ncu_bench.log 2>&1
+  ncu --metrics gpu__time_duration.sum --clock-control none -k "regex:conv_tc_kernel|features_kernel|conv1_direct|pool_planar|mask_head|regions_kernel|average_kernel|scan_counts|mel_to_planar" -c 1200 --csv --log-file $P/${TAG}_launches_bench.csv $BQ > $P/${TAG}_ncu_bench.log 2>&1
 $PR > $P/${TAG}_plain.log 2>&1 && \
   ncu --metrics $M --clock-control none --csv --log-file $P/${TAG}_launches_f16x3.csv $PR > $P/${TAG}_ncu1.log 2>&1 && \
-  ncu --set full --clock-control none --import-source on -k regex:conv_tc_kernel -s 18 -c 2 -f -o $P/${TAG}_prof_conv $PR > $P/${TAG}_ncu2.log 2>&1 && \
+  ncu --set full --clock-control none --import-source on -k regex:conv_tc_kernel -s 17 -c 2 -f -o $P/${TAG}_prof_conv $PR > $P/${TAG}_ncu2.log 2>&1 && \
   ncu --set full --clock-control none --import-source on -k regex:features_kernel -c 1 -f -o $P/${TAG}_prof_feat $PR > $P/${TAG}_ncu3.log 2>&1
 python tools/bench_aux.py silence > $P/${TAG}_silence.log 2>&1
 python tools/bench_aux.py long > $P/${TAG}_long.log 2>&1

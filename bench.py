@@ -40,8 +40,8 @@ SR = 22050
 WINDOWS_PER_CLIP = 1005
 FLOP_PER_WINDOW_MASK = 6_359_672_832          # convs on the mask path, 2 x MAC, BN folded
 FEATURE_BYTES_PER_CLIP = 4 * (13_230_000 + 132_300) + WINDOWS_PER_CLIP * 128 * 256 * 4   # PCM once + mel once
-# DRAM bytes the classifier launches move per window (ncu, profiles/r1_launches_f16x3.txt: 93.9 GB / 1010 windows)
-CLASSIFIER_DRAM_BYTES_PER_WINDOW = {"f16x3": 93_000_000}
+# DRAM bytes the classifier launches move per window (ncu, profiles/r1_launches_f16x3.txt: 91.3 GB / 1010 windows)
+CLASSIFIER_DRAM_BYTES_PER_WINDOW = {"f16x3": 90_400_000}
 
 
 def peaks():

@@ -71,6 +71,8 @@ class SilenceWorker:
         self.engine = engine
         self._read = reader or _load_native
         self._write = writer or _write_pcm16
+        # PCM_16 files with the default reader / writer never leave the int16 domain (see _run_pcm16)
+        self._pcm16_route = reader is None and writer is None
 
     def run(self):
         erase_df = self.review_df[self.review_df['erase'] == 1]
@@ -85,6 +87,14 @@ class SilenceWorker:
                 break
             full_path = os.path.join(fpath, fname)
             self.signals.fileStarted.emit(full_path)
+            if self._pcm16_route:
+                done = self._run_pcm16(full_path, fname, group_rows)
+                if done is not None:
+                    if done:
+                        self.signals.fileComplete.emit(done)
+                    files_done += 1
+                    self.signals.overallProgress.emit(int(files_done / total_files * 100))
+                    continue
             try:
                 audio_data, sr = self._read(full_path)
             except Exception as e:                                  # silencer_ui.py:961-966
@@ -109,6 +119,42 @@ class SilenceWorker:
             files_done += 1
             self.signals.overallProgress.emit(int(files_done / total_files * 100))
         self.signals.finished.emit()
+
+    def _run_pcm16(self, full_path: str, fname: str, group_rows):
+        """PCM_16 input -> PCM_16 output without the float32 detour.  The reference decodes to float32
+        (`x / 32768`), zeroes slices and lets libsndfile encode again (`lrintf(x * 32767)`), so samples OUTSIDE the
+        erase intervals change too (16383 -> 16382); `ss_silence_pcm16_host(requantize=1)` applies exactly that
+        round trip per int16 sample on the device and zeroes the intervals: a quarter of the bytes over PCIe and no
+        float32 arrays on the host, same file bytes as the float32 route (tests/test_gpu_pcm16.py, the `files`
+        workload of tools/bench_aux.py).  -> output path, "" when writing failed, None when the file is not
+        PCM_16 or cannot be read here (the caller falls back to the float32 route and its error messages)."""
+        try:
+            got = wavio.read_wav_pcm16(full_path)
+        except Exception:
+            return None
+        if got is None:
+            return None
+        frames, sr = got
+        frames = np.ascontiguousarray(frames)
+        if not frames.flags.writeable:
+            frames = frames.copy()
+        n = frames.shape[0]
+        ch = 1 if frames.ndim == 1 else frames.shape[1]
+        table = []
+        for _, row in group_rows.iterrows():
+            s, e = row_to_samples(row['start_time'], row['end_time'], sr, n)
+            if e > s:
+                table.append((s * ch, e * ch))          # interleaved frames: all channels of [s, e) are contiguous
+        # requantisation touches every sample, so the kernel runs even when no interval survives clamping
+        self.engine.silence_pcm16_host(frames, np.asarray(table, dtype=np.int64).reshape(-1, 2), requantize=True)
+        base, _ = os.path.splitext(fname)
+        out_fullpath = os.path.join(self.output_dir, f"{base}_silenced.wav")
+        try:
+            wavio.write_wav_pcm16(out_fullpath, frames, sr)
+        except Exception as e:                                      # silencer_ui.py:999-1000
+            print(f"Error writing {out_fullpath}: {e}")
+            return ""
+        return out_fullpath
 
     def stop(self):
         self.stop_requested = True

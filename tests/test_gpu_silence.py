@@ -81,3 +81,41 @@ def test_config5_shape_intervals(engine):
     dev = torch.from_numpy(corpus).cuda().reshape(-1)
     engine.silence(dev, torch.from_numpy(table))
     assert np.array_equal(dev.cpu().numpy().reshape(n_files, clip_n), want)
+
+
+def test_silence_worker_pcm16_files_route_equals_float32_route(engine, tmp_path):
+    """PCM_16 wav files take the int16-domain route (no float32 detour); the files it writes must be byte-identical
+    to those of the float32 route (decode /32768 -> zero slices -> encode lrintf(x * 32767)), mono and stereo,
+    including a file whose only row clamps to nothing (it is still re-encoded) and rows past the end."""
+    from softspoken_b200 import wavio
+    from softspoken_b200.silencer import SilenceWorker, _load_native, _write_pcm16
+    rng = np.random.default_rng(12)
+    sr = 8000
+    src = tmp_path / "in"
+    src.mkdir()
+    mono = rng.integers(-32768, 32768, 40001).astype(np.int16)
+    mono[:8] = [32767, -32768, 16383, 16384, -16383, 1, -1, 0]
+    stereo = rng.integers(-32768, 32768, (30000, 2)).astype(np.int16)
+    wavio.write_wav_pcm16(str(src / "m.wav"), mono, sr)
+    wavio.write_wav_pcm16(str(src / "s.wav"), stereo, sr)
+    wavio.write_wav_pcm16(str(src / "untouched.wav"), mono[:5000], sr)
+    wavio.write_wav_float32(str(src / "f.wav"), (mono[:6000] / 32768.0).astype(np.float32), sr)   # not PCM_16: falls back
+    rows = [("m.wav", 0.0004, 0.75), ("m.wav", 2.5, 99.0), ("m.wav", 1.0, 1.0), ("s.wav", 0.1234, 0.5678),
+            ("s.wav", 3.7, 3.9), ("untouched.wav", 50.0, 60.0), ("f.wav", 0.1, 0.2)]
+    df = pd.DataFrame({"file_path": [str(src)] * len(rows), "file_name": [r[0] for r in rows],
+                       "start_time": [r[1] for r in rows], "end_time": [r[2] for r in rows], "erase": 1})
+    out_a, out_b = tmp_path / "a", tmp_path / "b"
+    out_a.mkdir(), out_b.mkdir()
+    fast = SilenceWorker(df, str(out_a), engine=engine)
+    assert fast._pcm16_route
+    fast.run()
+    slow = SilenceWorker(df, str(out_b), engine=engine, reader=_load_native, writer=_write_pcm16)
+    assert not slow._pcm16_route
+    slow.run()
+    names = sorted(p.name for p in out_a.iterdir())
+    assert names == ["f_silenced.wav", "m_silenced.wav", "s_silenced.wav", "untouched_silenced.wav"]
+    for name in names:
+        assert (out_a / name).read_bytes() == (out_b / name).read_bytes(), name
+    got, _ = wavio.read_wav_pcm16(str(out_a / "m_silenced.wav"))
+    assert not got[3:6000].any() and got[int(2.5 * sr):].max() == 0 and got[6001:int(2.5 * sr)].any()
+    assert [len(w.signals.fileComplete.log) for w in (fast, slow)] == [4, 4]

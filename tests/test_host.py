@@ -306,3 +306,40 @@ def test_corpus_journal_resume(tmp_path):
     again = corpus.csv_text(corpus.detect_corpus(files, make_detect(), load=fake_load, durations=durations,
                                                  group_size=3, journal=jp))
     assert again == clean and seen == []
+
+
+def test_corpus_prefetch_order_errors_and_early_exit():
+    """The reader thread hands groups over in order, a load failure surfaces at its own group (earlier groups are
+    still delivered), and abandoning the loop stops the reader instead of leaving it blocked on a full queue."""
+    import threading
+    import time
+    from softspoken_b200 import corpus
+    groups = [[0, 1, 2], [3, 4], [5], [6, 7, 8]]
+    loaded = []
+
+    def load(i):
+        loaded.append(i)
+        return np.full(4, i, np.int16)
+    for depth in (0, 1, 3):
+        loaded.clear()
+        got = list(corpus._prefetched(groups, load, depth=depth))
+        assert [g for g, _ in got] == groups and loaded == list(range(9))
+        assert all(int(c[0]) == i for g, clips in got for i, c in zip(g, clips))
+
+    def bad(i):
+        if i == 5:
+            raise OSError("unreadable file")
+        return np.zeros(1, np.int16)
+    seen = []
+    with pytest.raises(OSError, match="unreadable"):
+        for g, _ in corpus._prefetched(groups, bad, depth=2):
+            seen.append(g)
+    assert seen == groups[:2]
+    before = threading.active_count()
+    it = corpus._prefetched([[i] for i in range(100)], load, depth=1)
+    next(it)
+    it.close()                       # consumer gives up: the reader must notice and end
+    deadline = time.time() + 5
+    while threading.active_count() > before and time.time() < deadline:
+        time.sleep(0.05)
+    assert threading.active_count() <= before

@@ -2,6 +2,8 @@
 
     python tools/bench_aux.py long    [--hours 24]     # config 4: one long recording streamed in chunks
     python tools/bench_aux.py silence [--files 1000]   # config 5: 10k flagged intervals masked across the corpus
+    python tools/bench_aux.py files   [--files 24]     # config 2 from wav FILES: read + decode + upload + detect + CSV,
+                                                       # then review (all erase) + exports + "Silence Voices" to wavs
 
 config 4 — a synthetic 24 h mono 22,050 Hz recording (a seeded 10-minute clip tiled with a different gain per
 tile, so neighbouring hours differ) is handed to `ss_detect_host` as ONE host buffer; the library streams it in
@@ -151,9 +153,96 @@ def run_silence(args):
     eng.close()
 
 
+def run_files(args):
+    """The whole headless job on wav files ("a second number including host wav decode + H2D"):
+    N synthetic 10-minute PCM_16 clips are written to a scratch folder, then timed by wall clock:
+      detect  = softspoken_b200.corpus.detect_corpus (reader thread -> ss_detect_host_batch_pcm16 -> CSV text),
+                once with the reader thread and once reading in line as the reference does;
+      review  = softspoken_b200.review (minimum-length filter, all erase, review CSV + the three export trees);
+      silence = softspoken_b200.silencer.SilenceWorker (read wav, mask on the GPU, encode + write <stem>_silenced.wav).
+    Checked: same CSV text with and without the reader thread; every sample of a silenced file is the input sample
+    re-encoded, or zero inside an erase interval."""
+    import shutil
+    import tempfile
+    import pandas as pd
+    from softspoken_b200 import corpus, review, silencer, synth, wavio
+    n_files = min(args.files, 64)
+    root = tempfile.mkdtemp(prefix="ss_files_", dir=args.scratch)
+    try:
+        base = [synth.synth_pcm16(600.0, s) for s in range(4)]
+        files = []
+        for i in range(n_files):
+            p = os.path.join(root, f"site{i % 3}", f"clip_{i:04d}.wav")
+            os.makedirs(os.path.dirname(p), exist_ok=True)
+            wavio.write_wav_pcm16(p, np.roll(base[i % 4], 997 * i), SR)
+            files.append(p)
+        eng = load_engine(1005, args.mode)
+        hours = n_files * 600.0 / 3600.0
+        # warm-up on two files (page cache is warm either way: the files were just written)
+        corpus.detect_corpus(files[:2], eng.detect_host_batch, load=corpus.load_native_22050, group_size=2)
+        res = {}
+        for name, depth in (("inline", 0), ("prefetch", 2)):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            rows = corpus.detect_corpus(files, eng.detect_host_batch, load=corpus.load_native_22050, group_size=4, prefetch=depth)
+            text = corpus.csv_text(rows)
+            res[name] = (time.perf_counter() - t0, text)
+        assert res["inline"][1] == res["prefetch"][1]
+        det_csv = os.path.join(root, "p_detections.csv")
+        with open(det_csv, "w", newline="") as f:
+            f.write(res["prefetch"][1])
+        t0 = time.perf_counter()
+        table = review.ReviewTable.open(det_csv, None)
+        table.erase_all("2026-01-01 00:00:00")
+        df = review.save_review(table, os.path.join(root, "p_review.csv"), root, "p")
+        review_s = time.perf_counter() - t0
+        out_dir = os.path.join(root, "silenced")
+        os.makedirs(out_dir)
+        t0 = time.perf_counter()
+        silencer.SilenceWorker(pd.read_csv(os.path.join(root, "p_review.csv")), out_dir, engine=eng).run()
+        torch.cuda.synchronize()
+        silence_s = time.perf_counter() - t0
+        # check one file per folder sample by sample
+        ok, checked = True, 0
+        for p in files[:3]:
+            rows_f = df[(df["file_path"] == os.path.dirname(p)) & (df["file_name"] == os.path.basename(p))]
+            outp = os.path.join(out_dir, os.path.basename(p)[:-4] + "_silenced.wav")
+            if not len(rows_f):
+                continue
+            x, _ = wavio.read_wav(p)
+            want = wavio.encode_pcm16(x)
+            for s, e in zip(rows_f["start_time"], rows_f["end_time"]):
+                a, b = silencer.row_to_samples(s, e, SR, len(x))
+                want[a:b] = 0
+            got, _ = wavio.read_wav_pcm16(outp)
+            ok = ok and np.array_equal(got, want)
+            checked += 1
+        silenced = len({(a, b) for a, b in zip(df["file_path"], df["file_name"])})
+        line = {
+            "metric": "audio_hours_per_sec", "unit": "audio-hours/s", "n_gpus": 1, "higher_is_better": True,
+            "value": hours / res["prefetch"][0], "data": "synthetic", "dtype": args.mode,
+            "config": {"workload": f"config2 from files: {n_files} x 10-min mono PCM_16 wavs ({n_files * 26.46:.0f} MB) in {args.scratch}, "
+                                   "wall clock of read + RIFF parse + upload + detect + CSV rows (softspoken_b200.corpus)"},
+            "detect": {"with_reader_thread_s": res["prefetch"][0], "read_in_line_s": res["inline"][0],
+                       "audio_hours_per_s_in_line": hours / res["inline"][0], "detections": len(rows),
+                       "same_csv_both_ways": True},
+            "review": {"rows_after_minimum_length_filter": len(df), "seconds_incl_three_exports": review_s},
+            "silence_voices": {"files_written": silenced, "seconds": silence_s,
+                               "audio_hours_per_s": silenced * 600.0 / 3600.0 / silence_s if silenced else None,
+                               "files_checked_sample_exact": checked, "ok": bool(ok)},
+        }
+        print(json.dumps(line), flush=True)
+        assert ok
+        eng.close()
+    finally:
+        shutil.rmtree(root, ignore_errors=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("what", choices=["long", "silence"])
+    ap.add_argument("what", choices=["long", "silence", "files"])
+    ap.add_argument("--scratch", default="/dev/shm" if os.path.isdir("/dev/shm") else None,
+                    help="folder for the wav files of the `files` workload")
     ap.add_argument("--hours", type=float, default=24.0)
     ap.add_argument("--files", type=int, default=1000)
     ap.add_argument("--intervals", type=int, default=10000)
@@ -161,7 +250,7 @@ def main():
     ap.add_argument("--pcm16", action="store_true", help="config 4 from the int16 samples of a PCM_16 recording")
     ap.add_argument("--mode", default="f16x3")
     args = ap.parse_args()
-    (run_long if args.what == "long" else run_silence)(args)
+    {"long": run_long, "silence": run_silence, "files": run_files}[args.what](args)
 
 
 if __name__ == "__main__":

@@ -10,6 +10,7 @@ grouping and file naming are host logic kept bit-compatible with the reference.
 from __future__ import annotations
 
 import os
+from concurrent.futures import ThreadPoolExecutor
 from typing import Dict, List, Sequence, Tuple
 
 import numpy as np
@@ -71,7 +72,7 @@ class SilenceWorker:
         self.engine = engine
         self._read = reader or _load_native
         self._write = writer or _write_pcm16
-        # PCM_16 files with the default reader / writer never leave the int16 domain (see _run_pcm16)
+        # PCM_16 files with the default reader / writer never leave the int16 domain (see _silence_pcm16)
         self._pcm16_route = reader is None and writer is None
 
     def run(self):
@@ -79,61 +80,83 @@ class SilenceWorker:
         if erase_df.empty:
             self.signals.finished.emit()
             return
-        grouped = erase_df.groupby(['file_path', 'file_name'])
-        total_files = len(grouped)
-        files_done = 0
-        for (fpath, fname), group_rows in grouped:
-            if self.stop_requested:
-                break
-            full_path = os.path.join(fpath, fname)
-            self.signals.fileStarted.emit(full_path)
-            if self._pcm16_route:
-                done = self._run_pcm16(full_path, fname, group_rows)
-                if done is not None:
-                    if done:
-                        self.signals.fileComplete.emit(done)
-                    files_done += 1
-                    self.signals.overallProgress.emit(int(files_done / total_files * 100))
+        groups = [(fpath, fname, rows) for (fpath, fname), rows in erase_df.groupby(['file_path', 'file_name'])]
+        total_files = len(groups)
+        self._files_done = 0
+
+        def file_done(out_fullpath=None):
+            if out_fullpath is not None:
+                self.signals.fileComplete.emit(out_fullpath)
+            self._files_done += 1
+            self.signals.overallProgress.emit(int(self._files_done / total_files * 100))
+
+        # PCM_16 route: the next file is read and the previous one written on two helper threads while this thread
+        # drives the GPU (np.fromfile, file writes and the ctypes call all release the GIL).  At most one file waits
+        # to be written, so fileComplete(k - 1) may follow fileStarted(k); completions stay in file order.
+        pool = ThreadPoolExecutor(max_workers=2) if self._pcm16_route else None
+        pending = []                                   # [(write future, output path)], at most one
+
+        def read_ahead(k):
+            if pool is None or k >= len(groups):
+                return None
+            return pool.submit(_read_pcm16_or_none, os.path.join(groups[k][0], groups[k][1]))
+
+        def settle_write():
+            while pending:
+                fut, outp = pending.pop(0)
+                err = fut.result()
+                if err is not None:                                 # silencer_ui.py:999-1000
+                    print(f"Error writing {outp}: {err}")
+                file_done(outp)
+
+        nxt = read_ahead(0)
+        try:
+            for k, (fpath, fname, group_rows) in enumerate(groups):
+                if self.stop_requested:
+                    break
+                cur, nxt = nxt, read_ahead(k + 1)
+                full_path = os.path.join(fpath, fname)
+                self.signals.fileStarted.emit(full_path)
+                base, ext = os.path.splitext(fname)
+                out_fullpath = os.path.join(self.output_dir, f"{base}_silenced.wav")
+                rows = list(zip(group_rows['start_time'].tolist(), group_rows['end_time'].tolist()))
+                got = cur.result() if cur is not None else None
+                if got is not None:
+                    frames, sr = self._silence_pcm16(got, rows)
+                    settle_write()
+                    pending.append((pool.submit(_write_or_error, out_fullpath, frames, sr), out_fullpath))
                     continue
-            try:
-                audio_data, sr = self._read(full_path)
-            except Exception as e:                                  # silencer_ui.py:961-966
-                print(f"Error loading {full_path}: {e}")
-                files_done += 1
-                self.signals.overallProgress.emit(int(files_done / total_files * 100))
-                continue
-            if audio_data.ndim == 1:
-                audio_data = np.expand_dims(audio_data, axis=0)
-            audio_data = np.ascontiguousarray(audio_data, dtype=np.float32)
-            rows = [(row['start_time'], row['end_time']) for _, row in group_rows.iterrows()]
-            table = interval_table(rows, sr, audio_data.shape[0], audio_data.shape[1])
-            if len(table):
-                self.engine.silence_host(audio_data, table)
-            base, ext = os.path.splitext(fname)
-            out_fullpath = os.path.join(self.output_dir, f"{base}_silenced.wav")
-            try:
-                self._write(out_fullpath, audio_data.T, sr)
-            except Exception as e:                                  # silencer_ui.py:999-1000
-                print(f"Error writing {out_fullpath}: {e}")
-            self.signals.fileComplete.emit(out_fullpath)
-            files_done += 1
-            self.signals.overallProgress.emit(int(files_done / total_files * 100))
+                settle_write()
+                try:
+                    audio_data, sr = self._read(full_path)
+                except Exception as e:                                  # silencer_ui.py:961-966
+                    print(f"Error loading {full_path}: {e}")
+                    file_done()
+                    continue
+                if audio_data.ndim == 1:
+                    audio_data = np.expand_dims(audio_data, axis=0)
+                audio_data = np.ascontiguousarray(audio_data, dtype=np.float32)
+                table = interval_table(rows, sr, audio_data.shape[0], audio_data.shape[1])
+                if len(table):
+                    self.engine.silence_host(audio_data, table)
+                try:
+                    self._write(out_fullpath, audio_data.T, sr)
+                except Exception as e:                                  # silencer_ui.py:999-1000
+                    print(f"Error writing {out_fullpath}: {e}")
+                file_done(out_fullpath)
+            settle_write()
+        finally:
+            if pool is not None:
+                pool.shutdown(wait=True)
         self.signals.finished.emit()
 
-    def _run_pcm16(self, full_path: str, fname: str, group_rows):
+    def _silence_pcm16(self, got, rows):
         """PCM_16 input -> PCM_16 output without the float32 detour.  The reference decodes to float32
         (`x / 32768`), zeroes slices and lets libsndfile encode again (`lrintf(x * 32767)`), so samples OUTSIDE the
         erase intervals change too (16383 -> 16382); `ss_silence_pcm16_host(requantize=1)` applies exactly that
         round trip per int16 sample on the device and zeroes the intervals: a quarter of the bytes over PCIe and no
-        float32 arrays on the host, same file bytes as the float32 route (tests/test_gpu_pcm16.py, the `files`
-        workload of tools/bench_aux.py).  -> output path, "" when writing failed, None when the file is not
-        PCM_16 or cannot be read here (the caller falls back to the float32 route and its error messages)."""
-        try:
-            got = wavio.read_wav_pcm16(full_path)
-        except Exception:
-            return None
-        if got is None:
-            return None
+        float32 arrays on the host, same file bytes as the float32 route (tests/test_gpu_silence.py, the `files`
+        workload of tools/bench_aux.py).  `got` = `wavio.read_wav_pcm16(path)`; -> (int16 frames, sample rate)."""
         frames, sr = got
         frames = np.ascontiguousarray(frames)
         if not frames.flags.writeable:
@@ -141,23 +164,33 @@ class SilenceWorker:
         n = frames.shape[0]
         ch = 1 if frames.ndim == 1 else frames.shape[1]
         table = []
-        for _, row in group_rows.iterrows():
-            s, e = row_to_samples(row['start_time'], row['end_time'], sr, n)
+        for st, et in rows:
+            s, e = row_to_samples(st, et, sr, n)
             if e > s:
                 table.append((s * ch, e * ch))          # interleaved frames: all channels of [s, e) are contiguous
         # requantisation touches every sample, so the kernel runs even when no interval survives clamping
         self.engine.silence_pcm16_host(frames, np.asarray(table, dtype=np.int64).reshape(-1, 2), requantize=True)
-        base, _ = os.path.splitext(fname)
-        out_fullpath = os.path.join(self.output_dir, f"{base}_silenced.wav")
-        try:
-            wavio.write_wav_pcm16(out_fullpath, frames, sr)
-        except Exception as e:                                      # silencer_ui.py:999-1000
-            print(f"Error writing {out_fullpath}: {e}")
-            return ""
-        return out_fullpath
+        return frames, sr
 
     def stop(self):
         self.stop_requested = True
+
+
+def _read_pcm16_or_none(path: str):
+    """(int16 frames, sr) of a PCM_16 file; None for any other format or an unreadable file (the caller then takes
+    the float32 route, which owns the reference's error messages)."""
+    try:
+        return wavio.read_wav_pcm16(path)
+    except Exception:
+        return None
+
+
+def _write_or_error(path: str, frames: np.ndarray, sr: int):
+    try:
+        wavio.write_wav_pcm16(path, frames, sr)
+        return None
+    except Exception as e:
+        return e
 
 
 def _load_native(path: str):

@@ -343,3 +343,61 @@ def test_corpus_prefetch_order_errors_and_early_exit():
     while threading.active_count() > before and time.time() < deadline:
         time.sleep(0.05)
     assert threading.active_count() <= before
+
+
+def test_silence_worker_pcm16_pipeline_host_logic(tmp_path, capsys):
+    """SilenceWorker's file pipeline on CPU (reader / writer helper threads around the device call): a stand-in
+    engine applies the oracle's int16 round trip, so what is checked here is the host logic — every file written
+    once, in group order, bytes equal to the oracle's, an unreadable file reported with the reference's message
+    (silencer_ui.py:961-966) without stalling the files behind it, and a non-PCM_16 file taking the float32 route."""
+    from oracle import silence as osil
+    from softspoken_b200 import wavio
+    from softspoken_b200.silencer import SilenceWorker, interval_table
+
+    class FakeEngine:
+        def __init__(self):
+            self.calls = []
+
+        def silence_pcm16_host(self, pcm, intervals, requantize=True):
+            assert requantize and pcm.dtype == np.int16 and pcm.flags.writeable
+            self.calls.append("s16")
+            flat = pcm.reshape(-1)
+            req = osil.float_to_pcm16(osil.pcm16_to_float(flat))
+            for s, e in np.asarray(intervals).reshape(-1, 2):
+                req[s:e] = 0
+            flat[:] = req
+
+        def silence_host(self, audio, table):
+            self.calls.append("f32")
+            flat = audio.reshape(-1)
+            for s, e in table:
+                flat[s:e] = 0.0
+
+    rng = np.random.default_rng(5)
+    sr = 4000
+    src = tmp_path / "in"
+    src.mkdir()
+    clips = {}
+    for i in range(7):
+        shape = (9000 + 37 * i,) if i % 3 else (5000 + i, 2)
+        clips[f"c{i}.wav"] = rng.integers(-32768, 32768, shape).astype(np.int16)
+        wavio.write_wav_pcm16(str(src / f"c{i}.wav"), clips[f"c{i}.wav"], sr)
+    wavio.write_wav_float32(str(src / "f.wav"), rng.uniform(-1, 1, 6000).astype(np.float32), sr)
+    rows = [(f"c{i}.wav", 0.1 * i, 0.1 * i + 0.7) for i in range(7)] + [("c2.wav", 1.9, 5.0), ("gone.wav", 0.0, 1.0),
+                                                                        ("f.wav", 0.25, 0.5)]
+    df = pd.DataFrame({"file_path": [str(src)] * len(rows), "file_name": [r[0] for r in rows],
+                       "start_time": [r[1] for r in rows], "end_time": [r[2] for r in rows], "erase": 1})
+    out = tmp_path / "out"
+    out.mkdir()
+    eng = FakeEngine()
+    w = SilenceWorker(df, str(out), engine=eng)
+    w.run()
+    names = sorted(clips) + ["f.wav"]
+    assert [a[0] for a in w.signals.fileComplete.log] == [str(out / (n[:-4] + "_silenced.wav")) for n in sorted(names)]
+    assert [a[0] for a in w.signals.fileStarted.log] == [str(src / n) for n in sorted(names + ["gone.wav"])]
+    assert w.signals.overallProgress.log[-1] == (100,) and len(w.signals.finished.log) == 1
+    assert "Error loading" in capsys.readouterr().out and eng.calls.count("s16") == 7 and eng.calls.count("f32") == 1
+    for n, fr in clips.items():
+        want = osil.silence_pcm16(fr, sr, [(r[1], r[2]) for r in rows if r[0] == n])
+        got, got_sr = wavio.read_wav_pcm16(str(out / (n[:-4] + "_silenced.wav")))
+        assert got_sr == sr and np.array_equal(got, want), n

@@ -484,10 +484,8 @@ int ss_silence(ss_ctx* ctx, float* pcm_dev, int64_t n_elems, const ss_interval* 
 static int detect_tail(ss_ctx* ctx, int64_t n_samples, int64_t W, int32_t* regions_dev, int32_t* n_regions_dev,
                        int cap, cudaStream_t st) {
   const int64_t bins = timeline_bins(n_samples + 2 * (int64_t)kPadSamples);
-  int rc = launch_average(ctx->file_logits, (int)W, bins, ctx->file_avg, ctx->file_cnt, st);
-  if (rc) return rc;
-  return launch_regions(ctx->file_avg, ctx->file_cnt, bins, 0.1, kGapBins, regions_dev, n_regions_dev, cap,
-                        ctx->scan_tmp, ctx->scan_tmp_len, st);
+  return launch_average_regions(ctx->file_logits, (int)W, bins, ctx->file_avg, ctx->file_cnt, 0.1, kGapBins, regions_dev,
+                                n_regions_dev, cap, ctx->scan_tmp, ctx->scan_tmp_len, st);
 }
 
 static int detect_device_impl(ss_ctx* ctx, const void* pcm_dev, int fmt, int64_t n_samples, int mode,

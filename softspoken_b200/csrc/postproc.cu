@@ -20,95 +20,173 @@ namespace ss {
 
 namespace {
 
-__global__ void average_kernel(const float* __restrict__ logits, int n_windows, int64_t out_len,
-                               double* __restrict__ avg, int32_t* __restrict__ cnt) {
-  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= out_len) return;
-  int64_t i_hi = (5 * j + 2) / 256;                 // largest i with p_i <= j
-  if (i_hi > n_windows - 1) i_hi = n_windows - 1;
-  int64_t idx[8];
-  int n = 0;
-  for (int64_t i = i_hi; i >= 0 && n < 8; --i) {
-    const int64_t p = (256 * i + 2) / 5;
-    if (p + 255 < j) break;
-    idx[n++] = i;
+constexpr int kAvgThreads = 256;
+constexpr int kHotBins = 4;          // bins per thread of hot_bits_kernel
+
+// One thread per timeline bin.  The windows covering bin j are i_lo .. i_hi with
+//   i_hi = floor((5 j + 2) / 256)            (largest i with p_i <= j)
+//   i_lo = ceil((5 (j - 255) - 2) / 256)     (smallest i with p_i + 255 >= j),  clamped to [0, n_windows - 1]:
+// at most five (five consecutive window spacings add up to exactly 256 bins), so the gather is five predicated
+// loads in flight and five float64 additions in ascending window order — no index array, no local memory.
+// kBits: the thread also votes hot[j] = covered && avg > threshold and lane 0 stores the warp's 32-bit word, so
+// that K6 never has to read the float64 timeline back.
+// Index: uint32_t while 5 out_len + 2 fits (116 days of audio), else int64_t — the kernel is bound by instruction
+// issue, not by HBM, and 64-bit divisions by 5 were most of its instructions; p_i is divided once for i_lo and
+// carried forward (256 = 5 * 51 + 1: the quotient grows by 51, and by one more whenever the remainder wraps).
+template <bool kBits, typename Index>
+__global__ void __launch_bounds__(kAvgThreads)
+average_kernel(const float* __restrict__ logits, int n_windows, int64_t out_len, double* __restrict__ avg,
+               int32_t* __restrict__ cnt, double threshold, uint32_t* __restrict__ bits) {
+  const int64_t j64 = (int64_t)blockIdx.x * kAvgThreads + threadIdx.x;
+  const bool in = j64 < out_len;
+  bool hot = false;
+  if (in) {
+    const Index j = (Index)j64;
+    const Index j5 = 5 * j;
+    Index i_hi = (j5 + 2) >> 8;
+    if (i_hi > (Index)(n_windows - 1)) i_hi = (Index)(n_windows - 1);
+    const Index i_lo = j5 > 1277 ? (j5 - 1277 + 255) >> 8 : 0;       // ceil((5 (j - 255) - 2) / 256), clamped at 0
+    const int n = n_windows > 0 && i_hi >= i_lo ? (int)(i_hi - i_lo) + 1 : 0;
+    const Index t = 256 * i_lo + 2;
+    Index p = t / 5;
+    int r = (int)(t - 5 * p);
+    const float* src = logits + (int64_t)i_lo * 256 + (int64_t)(j - p);      // window i_lo, frame j - p
+    float v[5];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+      v[k] = (k < n) ? __ldg(src) : 0.f;
+      const int step = 51 + (r == 4);        // p_{i+1} - p_i
+      r = (r == 4) ? 0 : r + 1;
+      src += 256 - step;
+    }
+    double sum = 0.0;
+#pragma unroll
+    for (int k = 0; k < 5; ++k)
+      if (k < n) sum += (double)v[k];                  // ascending window index, as the reference's `+=` sequence
+    const double a = n ? sum / (double)n : __longlong_as_double(0x7ff8000000000000LL);
+    cnt[j64] = n;
+    avg[j64] = a;
+    hot = n >= 1 && a > threshold;
   }
-  double sum = 0.0;
-  for (int k = n - 1; k >= 0; --k) {                // ascending window index
-    const int64_t i = idx[k];
-    const int64_t p = (256 * i + 2) / 5;
-    sum += (double)__ldg(logits + i * 256 + (j - p));
+  if (kBits) {
+    const unsigned word = __ballot_sync(0xffffffffu, hot);
+    if ((threadIdx.x & 31) == 0 && in) bits[j64 >> 5] = word;      // bins past out_len vote 0
   }
-  cnt[j] = n;
-  avg[j] = n ? sum / (double)n : __longlong_as_double(0x7ff8000000000000LL);
+}
+
+template <bool kBits>
+static void launch_average_kernel(const float* logits, int n_windows, int64_t out_len, double* avg, int32_t* cnt,
+                                  double threshold, uint32_t* bits, cudaStream_t st) {
+  const int grid = (int)((out_len + kAvgThreads - 1) / kAvgThreads);
+  if (5 * out_len + 2 < ((int64_t)1 << 32) && (int64_t)n_windows * 256 + 2 < ((int64_t)1 << 32))
+    average_kernel<kBits, uint32_t><<<grid, kAvgThreads, 0, st>>>(logits, n_windows, out_len, avg, cnt, threshold, bits);
+  else
+    average_kernel<kBits, int64_t><<<grid, kAvgThreads, 0, st>>>(logits, n_windows, out_len, avg, cnt, threshold, bits);
+}
+
+// hot[j] = count[j] >= 1 && avg[j] > threshold as one bit per bin (the entry for callers that bring their own timeline)
+__global__ void __launch_bounds__(kAvgThreads)
+hot_bits_kernel(const double* __restrict__ avg, const int32_t* __restrict__ cnt, int64_t out_len, double threshold,
+                uint32_t* __restrict__ bits) {
+  // four bins per thread, kAvgThreads apart: eight independent loads in flight before the first vote
+  const int64_t j0 = (int64_t)blockIdx.x * (kAvgThreads * kHotBins) + threadIdx.x;
+  double a[kHotBins];
+  int32_t c[kHotBins];
+#pragma unroll
+  for (int b = 0; b < kHotBins; ++b) {
+    const int64_t j = j0 + b * kAvgThreads;
+    const bool in = j < out_len;
+    c[b] = in ? __ldg(cnt + j) : 0;
+    a[b] = in ? __ldg(avg + j) : 0.0;
+  }
+#pragma unroll
+  for (int b = 0; b < kHotBins; ++b) {
+    const int64_t j = j0 + b * kAvgThreads;
+    const unsigned word = __ballot_sync(0xffffffffu, c[b] >= 1 && a[b] > threshold);
+    if ((threadIdx.x & 31) == 0 && j < out_len) bits[j >> 5] = word;
+  }
 }
 
 constexpr int kScanThreads = 256;
-constexpr int kRounds = 4;
-constexpr int kTile = kScanThreads * kRounds;   // bins per CTA
+constexpr int kBinsPerThread = 16;
+constexpr int kTile = kScanThreads * kBinsPerThread;   // 4,096 bins = 128 words per CTA
 
-// PASS 0: count starts/ends per CTA.  PASS 1: rank and emit.
+// any bit set in positions [a, b] (inclusive, a <= b) of the bit string w?
+__device__ __forceinline__ bool any_bits(const uint32_t* w, int a, int b) {
+  const int wa = a >> 5, wb = b >> 5;
+  const uint32_t ma = 0xffffffffu << (a & 31), mb = 0xffffffffu >> (31 - (b & 31));
+  if (wa == wb) return (w[wa] & ma & mb) != 0u;
+  uint32_t acc = (w[wa] & ma) | (w[wb] & mb);
+  for (int k = wa + 1; k < wb; ++k) acc |= w[k];
+  return acc != 0u;
+}
+
+// PASS 0: count the merged-region starts / ends of each CTA's tile.  PASS 1: rank them and write the pairs.
+// The tile's hot bits plus a halo of `gap` bins each side sit in shared memory as words; a thread owns 16
+// consecutive bins, so ranks inside the CTA come from ONE block scan of (starts | ends << 16) counts.
 template <int PASS>
 __global__ void __launch_bounds__(kScanThreads)
-regions_kernel(const double* __restrict__ avg, const int32_t* __restrict__ cnt, int64_t out_len, double threshold,
-               int gap, int32_t* __restrict__ block_counts, int32_t* __restrict__ regions, int cap) {
-  extern __shared__ unsigned char hot[];           // [kTile + 2 gap], bin tile0 - gap at index 0
-  __shared__ int warp_s[kScanThreads / 32], warp_e[kScanThreads / 32];
-  __shared__ int base_s, base_e;
-  const int tid = threadIdx.x;
+regions_kernel(const uint32_t* __restrict__ bits, int64_t n_words, int gap, int32_t* __restrict__ block_counts,
+               int32_t* __restrict__ regions, int cap) {
+  extern __shared__ uint32_t w[];                  // [kTile / 32 + 2 hw], word 0 = global word tile0 / 32 - hw
+  __shared__ uint32_t warp_tot[kScanThreads / 32];
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int hw = (gap + 31) >> 5;
   const int64_t tile0 = (int64_t)blockIdx.x * kTile;
-  for (int i = tid; i < kTile + 2 * gap; i += kScanThreads) {
-    const int64_t j = tile0 - gap + i;
-    unsigned char h = 0;
-    if (j >= 0 && j < out_len) h = (cnt[j] >= 1 && avg[j] > threshold) ? 1 : 0;
-    hot[i] = h;
-  }
-  if (tid == 0) {
-    if (PASS == 1) { base_s = block_counts[2 * blockIdx.x]; base_e = block_counts[2 * blockIdx.x + 1]; }
-    else { base_s = 0; base_e = 0; }
+  const int64_t wbase = (tile0 >> 5) - hw;
+  for (int k = tid; k < kTile / 32 + 2 * hw; k += kScanThreads) {
+    const int64_t g = wbase + k;
+    w[k] = (g >= 0 && g < n_words) ? __ldg(bits + g) : 0u;
   }
   __syncthreads();
-
-  const int lane = tid & 31, wid = tid >> 5;
-  for (int r = 0; r < kRounds; ++r) {
-    const int li = r * kScanThreads + tid + gap;     // index into hot[]
-    const int64_t j = tile0 + r * kScanThreads + tid;
-    bool is_s = false, is_e = false;
-    if (hot[li]) {
-      is_s = true; is_e = true;
-      for (int d = 1; d <= gap; ++d) {
-        if (hot[li - d]) is_s = false;
-        if (hot[li + d]) is_e = false;
-      }
+  const int li0 = hw * 32 + tid * kBinsPerThread;     // my first bin as a bit index into w
+  const uint32_t mine = (w[li0 >> 5] >> (li0 & 31)) & 0xffffu;
+  uint32_t smask = 0u, emask = 0u;
+  if (gap >= kBinsPerThread - 1) {
+    // every hot bin but my lowest has a hot bin less than 16 <= gap + 1 bins before it, every one but my highest has
+    // one after it: two range tests per thread, whatever the data
+    if (mine) {
+      const int lo = __ffs(mine) - 1, hi = 31 - __clz(mine);
+      if (!any_bits(w, li0 + lo - gap, li0 + lo - 1)) smask = 1u << lo;
+      if (!any_bits(w, li0 + hi + 1, li0 + hi + gap)) emask = 1u << hi;
     }
-    const unsigned bs = __ballot_sync(0xffffffffu, is_s);
-    const unsigned be = __ballot_sync(0xffffffffu, is_e);
-    if (lane == 0) { warp_s[wid] = __popc(bs); warp_e[wid] = __popc(be); }
-    __syncthreads();
-    int off_s = 0, off_e = 0, tot_s = 0, tot_e = 0;
-#pragma unroll
-    for (int w = 0; w < kScanThreads / 32; ++w) {
-      if (w < wid) { off_s += warp_s[w]; off_e += warp_e[w]; }
-      tot_s += warp_s[w]; tot_e += warp_e[w];
+  } else {
+    for (uint32_t m = mine; m; m &= m - 1) {
+      const int b = __ffs(m) - 1;
+      const int li = li0 + b;
+      if (!any_bits(w, li - gap, li - 1)) smask |= 1u << b;
+      if (!any_bits(w, li + 1, li + gap)) emask |= 1u << b;
     }
-    if (PASS == 1) {
-      const unsigned below = (1u << lane) - 1u;
-      if (is_s) {
-        const int k = base_s + off_s + __popc(bs & below);
-        if (k < cap) regions[2 * k] = (int32_t)j;
-      }
-      if (is_e) {
-        const int k = base_e + off_e + __popc(be & below);
-        if (k < cap) regions[2 * k + 1] = (int32_t)j;
-      }
-    }
-    __syncthreads();
-    if (tid == 0) { base_s += tot_s; base_e += tot_e; }
-    __syncthreads();
   }
-  if (PASS == 0 && tid == 0) {
-    block_counts[2 * blockIdx.x] = base_s;
-    block_counts[2 * blockIdx.x + 1] = base_e;
+  const uint32_t c = (uint32_t)__popc(smask) | ((uint32_t)__popc(emask) << 16);
+  uint32_t incl = c;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+    if (lane >= d) incl += t;
+  }
+  if (lane == 31) warp_tot[wid] = incl;
+  __syncthreads();
+  uint32_t off = 0u, tot = 0u;
+#pragma unroll
+  for (int k = 0; k < kScanThreads / 32; ++k) {
+    if (k < wid) off += warp_tot[k];
+    tot += warp_tot[k];
+  }
+  if (PASS == 0) {
+    if (tid == 0) {
+      block_counts[2 * blockIdx.x] = (int32_t)(tot & 0xffffu);
+      block_counts[2 * blockIdx.x + 1] = (int32_t)(tot >> 16);
+    }
+  } else {
+    const uint32_t excl = off + incl - c;
+    int ks = block_counts[2 * blockIdx.x] + (int)(excl & 0xffffu);
+    int ke = block_counts[2 * blockIdx.x + 1] + (int)(excl >> 16);
+    const int64_t j0 = tile0 + tid * kBinsPerThread;
+    for (uint32_t m = smask; m; m &= m - 1, ++ks)
+      if (ks < cap) regions[2 * ks] = (int32_t)(j0 + __ffs(m) - 1);
+    for (uint32_t m = emask; m; m &= m - 1, ++ke)
+      if (ke < cap) regions[2 * ke + 1] = (int32_t)(j0 + __ffs(m) - 1);
   }
 }
 
@@ -153,41 +231,77 @@ scan_counts_kernel(int32_t* __restrict__ block_counts, int n_blocks, int32_t* __
 
 int launch_average(const float* logits, int n_windows, int64_t out_len, double* avg, int32_t* cnt, cudaStream_t st) {
   if (out_len <= 0) return SS_OK;
-  const int threads = 256;
-  average_kernel<<<(int)((out_len + threads - 1) / threads), threads, 0, st>>>(logits, n_windows, out_len, avg, cnt);
+  launch_average_kernel<false>(logits, n_windows, out_len, avg, cnt, 0.0, nullptr, st);
   SS_CUDA_CHECK(cudaGetLastError());
   count_launch();
   return SS_OK;
 }
 
-int64_t regions_scan_tmp_len(int64_t out_len) { return 2 * ((out_len + kTile - 1) / kTile) + 2; }
+// K6 scratch: [2 n_blocks + 2 per-CTA counts][(out_len + 31) / 32 + 2 hot-bit words]
+static int64_t count_words(int64_t out_len) { return 2 * ((out_len + kTile - 1) / kTile) + 2; }
+int64_t regions_scan_tmp_len(int64_t out_len) { return count_words(out_len) + (out_len + 31) / 32 + 2; }
+
+static int check_regions_args(int64_t out_len, int& gap_bins, int64_t scan_tmp_len) {
+  SS_REQUIRE(gap_bins >= 0 && gap_bins <= 4096, SS_E_ARG, "gap_bins %d out of range [0, 4096]", gap_bins);
+  SS_REQUIRE(out_len < ((int64_t)1 << 31), SS_E_ARG, "timeline of %lld bins exceeds int32 bin indices",
+             (long long)out_len);
+  SS_REQUIRE(scan_tmp_len >= regions_scan_tmp_len(out_len), SS_E_CAPACITY, "scan scratch too small");
+  // Two distinct runs are at least 2 bins apart, so gap 0 and 1 both mean "never merge"; a look-back of at
+  // least one bin is still needed to find where a run starts and ends.
+  if (gap_bins < 1) gap_bins = 1;
+  return SS_OK;
+}
+
+// count pass, scan of the per-CTA counts, emit pass — over the hot-bit words only (1 bit per bin)
+static int launch_regions_bits(const uint32_t* bits, int64_t out_len, int gap_bins, int32_t* regions, int32_t* n_regions,
+                               int cap, int32_t* counts, cudaStream_t st) {
+  const int n_blocks = (int)((out_len + kTile - 1) / kTile);
+  const int64_t n_words = (out_len + 31) / 32;
+  const size_t smem = (size_t)(kTile / 32 + 2 * ((gap_bins + 31) / 32)) * sizeof(uint32_t);
+  regions_kernel<0><<<n_blocks, kScanThreads, smem, st>>>(bits, n_words, gap_bins, counts, regions, cap);
+  SS_CUDA_CHECK(cudaGetLastError());
+  count_launch();
+  scan_counts_kernel<<<1, 1024, 0, st>>>(counts, n_blocks, n_regions);
+  SS_CUDA_CHECK(cudaGetLastError());
+  count_launch();
+  regions_kernel<1><<<n_blocks, kScanThreads, smem, st>>>(bits, n_words, gap_bins, counts, regions, cap);
+  SS_CUDA_CHECK(cudaGetLastError());
+  count_launch();
+  return SS_OK;
+}
 
 int launch_regions(const double* avg, const int32_t* cnt, int64_t out_len, double threshold, int gap_bins,
                    int32_t* regions, int32_t* n_regions, int cap, int32_t* scan_tmp, int64_t scan_tmp_len,
                    cudaStream_t st) {
-  SS_REQUIRE(gap_bins >= 0 && gap_bins <= 4096, SS_E_ARG, "gap_bins %d out of range [0, 4096]", gap_bins);
-  SS_REQUIRE(out_len < ((int64_t)1 << 31), SS_E_ARG, "timeline of %lld bins exceeds int32 bin indices",
-             (long long)out_len);
+  int rc = check_regions_args(out_len, gap_bins, scan_tmp_len);
+  if (rc) return rc;
   if (out_len <= 0) {
     SS_CUDA_CHECK(cudaMemsetAsync(n_regions, 0, sizeof(int32_t), st));
     return SS_OK;
   }
-  const int n_blocks = (int)((out_len + kTile - 1) / kTile);
-  SS_REQUIRE(scan_tmp_len >= 2 * (int64_t)n_blocks, SS_E_CAPACITY, "scan scratch too small");
-  // Two distinct runs are at least 2 bins apart, so gap 0 and 1 both mean "never merge"; a look-back of at
-  // least one bin is still needed to find where a run starts and ends.
-  if (gap_bins < 1) gap_bins = 1;
-  const size_t smem = kTile + 2 * gap_bins;
-  regions_kernel<0><<<n_blocks, kScanThreads, smem, st>>>(avg, cnt, out_len, threshold, gap_bins, scan_tmp, regions, cap);
+  uint32_t* bits = reinterpret_cast<uint32_t*>(scan_tmp + count_words(out_len));
+  hot_bits_kernel<<<(int)((out_len + kAvgThreads * kHotBins - 1) / (kAvgThreads * kHotBins)), kAvgThreads, 0, st>>>(
+      avg, cnt, out_len, threshold, bits);
   SS_CUDA_CHECK(cudaGetLastError());
   count_launch();
-  scan_counts_kernel<<<1, 1024, 0, st>>>(scan_tmp, n_blocks, n_regions);
+  return launch_regions_bits(bits, out_len, gap_bins, regions, n_regions, cap, scan_tmp, st);
+}
+
+// K5 + K6 of the detection pipeline: the averaging kernel votes the hot bits while the averages are in registers.
+int launch_average_regions(const float* logits, int n_windows, int64_t out_len, double* avg, int32_t* cnt,
+                           double threshold, int gap_bins, int32_t* regions, int32_t* n_regions, int cap,
+                           int32_t* scan_tmp, int64_t scan_tmp_len, cudaStream_t st) {
+  int rc = check_regions_args(out_len, gap_bins, scan_tmp_len);
+  if (rc) return rc;
+  if (out_len <= 0) {
+    SS_CUDA_CHECK(cudaMemsetAsync(n_regions, 0, sizeof(int32_t), st));
+    return SS_OK;
+  }
+  uint32_t* bits = reinterpret_cast<uint32_t*>(scan_tmp + count_words(out_len));
+  launch_average_kernel<true>(logits, n_windows, out_len, avg, cnt, threshold, bits, st);
   SS_CUDA_CHECK(cudaGetLastError());
   count_launch();
-  regions_kernel<1><<<n_blocks, kScanThreads, smem, st>>>(avg, cnt, out_len, threshold, gap_bins, scan_tmp, regions, cap);
-  SS_CUDA_CHECK(cudaGetLastError());
-  count_launch();
-  return SS_OK;
+  return launch_regions_bits(bits, out_len, gap_bins, regions, n_regions, cap, scan_tmp, st);
 }
 
 }  // namespace ss

@@ -179,6 +179,9 @@ int launch_regions(const double* avg, const int32_t* cnt, int64_t out_len, doubl
                    int32_t* regions, int32_t* n_regions, int cap, int32_t* scan_tmp, int64_t scan_tmp_len,
                    cudaStream_t st);
 int64_t regions_scan_tmp_len(int64_t out_len);
+int launch_average_regions(const float* logits, int n_windows, int64_t out_len, double* avg, int32_t* cnt,
+                           double threshold, int gap_bins, int32_t* regions, int32_t* n_regions, int cap,
+                           int32_t* scan_tmp, int64_t scan_tmp_len, cudaStream_t st);
 // silence.cu
 // zero [begin - shift, end - shift) ∩ [0, n_elems) of pcm for every interval
 int launch_silence(float* pcm, int64_t n_elems, int64_t shift, const ss_interval* iv, int n_intervals, cudaStream_t st);

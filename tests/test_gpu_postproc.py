@@ -54,10 +54,10 @@ def test_regions_property_random(engine):
     """Random timelines, thresholds and gaps vs the oracle's sequential scan (incl. empty / all-hot)."""
     from oracle import postproc as pp
     rng = np.random.default_rng(0)
-    for trial in range(40):
-        n = int(rng.choice([1, 2, 43, 255, 1024, 1025, 5000, 70001]))
+    for trial in range(120):
+        n = int(rng.choice([1, 2, 43, 255, 1024, 1025, 4096, 4097, 5000, 70001]))
         p_hot = float(rng.choice([0.0, 0.01, 0.2, 0.5, 0.97, 1.0]))
-        gap = int(rng.choice([0, 1, 42, 43, 300]))
+        gap = int(rng.choice([0, 1, 2, 14, 15, 16, 31, 32, 33, 42, 43, 300, 4096]))      # 15 = where the two-test fast path starts
         thr = float(rng.choice([0.1, 0.0, -0.3]))
         avg = np.where(rng.random(n) < p_hot, thr + rng.random(n) + 1e-9, thr - rng.random(n))
         avg[rng.random(n) < 0.05] = thr                       # exactly at threshold: not hot

@@ -153,6 +153,91 @@ def run_silence(args):
     eng.close()
 
 
+def run_postproc(args):
+    """K5 / K6 at the size where they stop being launch-bound: the timeline of a 24 h recording (144,005 windows,
+    7,373,312 bins).  Logits are synthetic (smooth noise around the threshold so that regions start and end all
+    along the timeline); timed with CUDA events on the launching stream, inputs larger than L2 (147 MB of logits,
+    88 MB of timeline).  Algorithmic bytes: K5 = W*1024 read + out_len*12 written; K6 (ss_regions on a
+    caller's timeline) = out_len*12 read once + regions written — its count and emit passes work on one hot bit per
+    bin; inside ss_detect_* the averaging kernel votes those bits itself and K6 reads no timeline at all.  Checked
+    against the oracle on a prefix."""
+    from oracle import postproc as pp               # checker only
+    from softspoken_b200 import spec
+    eng = load_engine(4, "bf16")
+    dev = torch.device("cuda", 0)
+    n = int(round(args.hours * 3600 * SR))
+    W = eng_plan_windows(n)
+    out_len = eng_timeline_bins(n + 2 * spec.PAD_SAMPLES)
+    g = torch.Generator(device=dev).manual_seed(5)
+    slow = torch.nn.functional.interpolate(torch.randn(1, 1, W // 16 + 2, device=dev, generator=g), size=W, mode="linear")[0, 0]
+    logits = (0.1 + 0.08 * slow[:, None] + 0.02 * torch.randn(W, 256, device=dev, generator=g)).contiguous()
+    stream = torch.cuda.current_stream()
+    times = {}
+    for _ in range(2):
+        avg, cnt = eng.average(logits, out_len)
+        reg = eng.regions(avg, cnt, cap=1 << 22)
+    reps = 5
+    for name, fn in (("K5", lambda: eng.average(logits, out_len)),):
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(reps):
+            fn()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        times[name] = e0.elapsed_time(e1) / reps / 1e3
+    # K6 through the device-level entry point (Engine.regions adds a D2H of the result): time it on the stream too
+    from softspoken_b200 import _lib
+    import ctypes as C
+    cap = 1 << 22
+    regd = torch.empty((cap, 2), dtype=torch.int32, device=dev)
+    nd = torch.zeros(1, dtype=torch.int32, device=dev)
+    def k6():
+        _lib.check(_lib.lib.ss_regions(eng._ctx, C.c_void_p(avg.data_ptr()), C.c_void_p(cnt.data_ptr()), out_len,
+                                       float(spec.THRESHOLD), int(spec.GAP_BINS), C.c_void_p(regd.data_ptr()),
+                                       C.c_void_p(nd.data_ptr()), cap, eng._stream()))
+    k6()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(reps):
+        k6()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    times["K6"] = e0.elapsed_time(e1) / reps / 1e3
+    n_reg = int(nd.item())
+    # oracle check on a prefix (windows are independent: the first bins depend on the first windows only)
+    Wp = 600
+    bins_p = (256 * (Wp - 1) + 2) // 5 + 256
+    ref_avg, ref_cnt = pp.average_idx(logits[:Wp].cpu().numpy().reshape(-1, 1, 256), bins_p * 3 / 256)
+    m = min(len(ref_avg), bins_p) - 300
+    ok = bool(np.array_equal(avg[:m].cpu().numpy(), np.asarray(ref_avg[:m], np.float64)))
+    peak, src = peaks()
+    b5 = W * 1024 + out_len * 12
+    b6 = out_len * 12 + n_reg * 8
+    line = {"metric": "postproc_GBps", "unit": "GB/s", "n_gpus": 1, "higher_is_better": True, "dtype": "f64 sums of f32, i32 bins",
+            "data": "synthetic", "value": (b5 + b6) / (times["K5"] + times["K6"]) / 1e9,
+            "config": {"workload": f"K5 + K6 on the timeline of a {args.hours:g} h recording: {W} windows, {out_len} bins, {n_reg} regions"},
+            "K5_average": {"ms": times["K5"] * 1e3, "algorithmic_bytes": b5, "GBps": b5 / times["K5"] / 1e9, "frac": b5 / times["K5"] / 1e9 / peak},
+            "K6_regions": {"ms": times["K6"] * 1e3, "algorithmic_bytes": b6, "GBps": b6 / times["K6"] / 1e9, "frac": b6 / times["K6"] / 1e9 / peak,
+                           "launches": 4},
+            "roofline": {"bound": "hbm", "peak": peak, "peak_source": src, "unit": "GB/s"},
+            "checks": {"prefix_bins_bitwise_equal_oracle": m, "ok": ok}}
+    print(json.dumps(line), flush=True)
+    assert ok
+    eng.close()
+
+
+def eng_plan_windows(n):
+    from softspoken_b200.engine import plan_windows
+    return plan_windows(n)
+
+
+def eng_timeline_bins(n_padded):
+    from softspoken_b200.engine import timeline_bins
+    return timeline_bins(n_padded)
+
+
 def run_files(args):
     """The whole headless job on wav files ("a second number including host wav decode + H2D"):
     N synthetic 10-minute PCM_16 clips are written to a scratch folder, then timed by wall clock:
@@ -240,7 +325,7 @@ def run_files(args):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("what", choices=["long", "silence", "files"])
+    ap.add_argument("what", choices=["long", "silence", "files", "postproc"])
     ap.add_argument("--scratch", default="/dev/shm" if os.path.isdir("/dev/shm") else None,
                     help="folder for the wav files of the `files` workload")
     ap.add_argument("--hours", type=float, default=24.0)
@@ -250,7 +335,7 @@ def main():
     ap.add_argument("--pcm16", action="store_true", help="config 4 from the int16 samples of a PCM_16 recording")
     ap.add_argument("--mode", default="f16x3")
     args = ap.parse_args()
-    {"long": run_long, "silence": run_silence, "files": run_files}[args.what](args)
+    {"long": run_long, "silence": run_silence, "files": run_files, "postproc": run_postproc}[args.what](args)
 
 
 if __name__ == "__main__":

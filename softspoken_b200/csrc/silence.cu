@@ -7,6 +7,8 @@
 // ranges of one packed buffer of float32 samples — or of int16 samples when a PCM_16 file is silenced without
 // ever leaving its storage format (pcm16.cu).  Write-only, HBM-bound: 16-byte stores on the aligned body,
 // scalar stores on the ragged head and tail.  Overlapping intervals are harmless (idempotent zero stores).
+#include <stdlib.h>
+
 #include "ss_common.cuh"
 
 namespace ss {
@@ -14,8 +16,11 @@ namespace ss {
 namespace {
 
 constexpr int kThreads = 256;
-constexpr int kVecsPerIter = kThreads * 4;   // 16-byte vectors per CTA iteration (4 per thread)
-constexpr int kChunksY = 32;
+constexpr int kVecsPerThread = 8;
+constexpr int kVecsPerIter = kThreads * kVecsPerThread;   // 16-byte vectors per CTA iteration: 32 KB
+// CTAs per interval.  A detection is 0.2-4 s (18-350 KB of float32 samples), i.e. 1-11 iterations: with 32 CTAs per
+// interval two thirds of the grid found nothing to do and the launch was bound by CTA turnover, not by stores.
+constexpr int kChunksY = 8;
 
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
@@ -40,13 +45,18 @@ silence_kernel(T* __restrict__ pcm, int64_t n_elems, int64_t shift, const ss_int
   float4* body = reinterpret_cast<float4*>(pcm + b4);
   const int64_t n4 = (e4 - b4) / kPerVec;
   const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);      // all-zero bits: 0.0f x 4 or int16 0 x 8
-  for (int64_t c = (int64_t)blockIdx.y * kVecsPerIter; c < n4; c += (int64_t)kChunksY * kVecsPerIter) {
+  for (int64_t c = (int64_t)blockIdx.y * kVecsPerIter; c < n4; c += (int64_t)gridDim.y * kVecsPerIter) {
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
+    for (int k = 0; k < kVecsPerThread; ++k) {
       const int64_t i = c + k * kThreads + threadIdx.x;
       if (i < n4) body[i] = z;
     }
   }
+}
+
+int chunks_y() {      // SS_SILENCE_Y: tuning override of the CTAs per interval
+  static const int y = [] { const char* e = getenv("SS_SILENCE_Y"); const int v = e ? atoi(e) : kChunksY; return v >= 1 && v <= 64 ? v : kChunksY; }();
+  return y;
 }
 
 }  // namespace
@@ -54,7 +64,7 @@ silence_kernel(T* __restrict__ pcm, int64_t n_elems, int64_t shift, const ss_int
 int launch_silence(float* pcm, int64_t n_elems, int64_t shift, const ss_interval* iv, int n_intervals,
                    cudaStream_t st) {
   if (n_intervals <= 0) return SS_OK;
-  dim3 grid(n_intervals, kChunksY);
+  dim3 grid(n_intervals, chunks_y());
   silence_kernel<float><<<grid, kThreads, 0, st>>>(pcm, n_elems, shift, iv, n_intervals);
   SS_CUDA_CHECK(cudaGetLastError());
   count_launch();
@@ -64,7 +74,7 @@ int launch_silence(float* pcm, int64_t n_elems, int64_t shift, const ss_interval
 int launch_silence_s16(int16_t* pcm, int64_t n_elems, int64_t shift, const ss_interval* iv, int n_intervals,
                        cudaStream_t st) {
   if (n_intervals <= 0) return SS_OK;
-  dim3 grid(n_intervals, kChunksY);
+  dim3 grid(n_intervals, chunks_y());
   silence_kernel<int16_t><<<grid, kThreads, 0, st>>>(pcm, n_elems, shift, iv, n_intervals);
   SS_CUDA_CHECK(cudaGetLastError());
   count_launch();

@@ -104,6 +104,22 @@ SS_API int ss_pad(ss_ctx* ctx, const float* pcm_dev, int64_t n_samples, float* p
 SS_API int ss_features(ss_ctx* ctx, const float* pcm_dev, int64_t n_padded, const int64_t* win_start_dev,
                 int n_windows, float* mel_out_dev, void* stream);
 
+/* K8 — review-screen spectrogram: voice_activity.wav_to_spec(data, trim_edges=False)
+ * (root/code/backend/voice_activity.py:148-154) = np.abs(librosa.stft(data, n_fft=512, win_length=512,
+ * hop_length=256)): periodic Hann, centred frames, zero padding.  mag_dev: [257 bins][ss_spectrogram_frames(n)]
+ * float32, frequency-major as librosa returns it.  max_dev: NULL, or one float that receives the largest
+ * magnitude (what the dB stage needs).  *_pcm16 reads the int16 samples of a PCM_16 file (value / 32768). */
+SS_API int64_t ss_spectrogram_frames(int64_t n_samples);
+SS_API int ss_spectrogram(ss_ctx* ctx, const float* pcm_dev, int64_t n_samples, float* mag_dev, float* max_dev,
+                   void* stream);
+SS_API int ss_spectrogram_pcm16(ss_ctx* ctx, const int16_t* pcm_dev, int64_t n_samples, float* mag_dev, float* max_dev,
+                         void* stream);
+/* The display transform of ReviewDetectionsScreen.display_spectrogram (root/code/frontend/review_detections.py:880-881),
+ * in place on mag_dev: np.abs(librosa.amplitude_to_db(S ** 2, ref=np.max)) in float32 (0 at the loudest cell, 80 at
+ * the floor; librosa squares its argument once more, so this is |40 log10(S / max S)| clipped at 80).
+ * max_dev: the float ss_spectrogram wrote. */
+SS_API int ss_spectrogram_db(ss_ctx* ctx, float* mag_dev, int64_t n_elems, const float* max_dev, void* stream);
+
 /* K2-K4 — SpecUNet_2D.forward after the front end (pytorch_neural_nets.py:156-195).
  * mel_dev: [n_windows][128][256].  logits_dev: [n_windows][256] raw mask logits (no sigmoid).
  * spec_out_dev: NULL, or [n_windows][2][128][256] for the separation head the reference

@@ -54,6 +54,10 @@ _SIGNATURES = {
     "ss_timeline_bins": (_i64, [_i64]),
     "ss_pad": (_int, [_p, _p, _i64, _p, _p]),
     "ss_features": (_int, [_p, _p, _i64, _p, _int, _p, _p]),
+    "ss_spectrogram_frames": (_i64, [_i64]),
+    "ss_spectrogram": (_int, [_p, _p, _i64, _p, _p, _p]),
+    "ss_spectrogram_pcm16": (_int, [_p, _p, _i64, _p, _p, _p]),
+    "ss_spectrogram_db": (_int, [_p, _p, _i64, _p, _p]),
     "ss_classify": (_int, [_p, _p, _int, _p, _p, _int, _p]),
     "ss_average": (_int, [_p, _p, _int, _i64, _p, _p, _p]),
     "ss_regions": (_int, [_p, _p, _p, _i64, C.c_double, _int, _p, _p, _int, _p]),

@@ -432,6 +432,37 @@ int ss_features(ss_ctx* ctx, const float* pcm_dev, int64_t n_padded, const int64
                          static_cast<cudaStream_t>(stream));
 }
 
+int64_t ss_spectrogram_frames(int64_t n_samples) { return n_samples < 0 ? 0 : 1 + n_samples / kHop; }
+
+static int spectrogram_impl(ss_ctx* ctx, const void* pcm_dev, int fmt, int64_t n_samples, float* mag_dev, float* max_dev,
+                            void* stream) {
+  int rc = check_ctx(ctx);
+  if (rc) return rc;
+  SS_REQUIRE(n_samples >= 0, SS_E_ARG, "negative size");
+  SS_REQUIRE(mag_dev && (pcm_dev || n_samples == 0), SS_E_ARG, "null device pointer");
+  return launch_spectrogram(ctx, pcm_dev, fmt, n_samples, mag_dev, reinterpret_cast<unsigned int*>(max_dev),
+                            static_cast<cudaStream_t>(stream));
+}
+
+int ss_spectrogram(ss_ctx* ctx, const float* pcm_dev, int64_t n_samples, float* mag_dev, float* max_dev, void* stream) {
+  return spectrogram_impl(ctx, pcm_dev, kSampleF32, n_samples, mag_dev, max_dev, stream);
+}
+
+int ss_spectrogram_pcm16(ss_ctx* ctx, const int16_t* pcm_dev, int64_t n_samples, float* mag_dev, float* max_dev,
+                         void* stream) {
+  return spectrogram_impl(ctx, pcm_dev, kSampleS16, n_samples, mag_dev, max_dev, stream);
+}
+
+int ss_spectrogram_db(ss_ctx* ctx, float* mag_dev, int64_t n_elems, const float* max_dev, void* stream) {
+  int rc = check_ctx(ctx);
+  if (rc) return rc;
+  SS_REQUIRE(n_elems >= 0, SS_E_ARG, "negative size");
+  if (n_elems == 0) return SS_OK;
+  SS_REQUIRE(mag_dev && max_dev, SS_E_ARG, "null device pointer");
+  return launch_spectrogram_db(mag_dev, n_elems, reinterpret_cast<const unsigned int*>(max_dev),
+                               static_cast<cudaStream_t>(stream));
+}
+
 int ss_classify(ss_ctx* ctx, const float* mel_dev, int n_windows, float* logits_dev, float* spec_out_dev, int mode,
                 void* stream) {
   int rc = check_ctx(ctx);

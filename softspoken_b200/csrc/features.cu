@@ -135,7 +135,8 @@ __device__ __forceinline__ float load_sample(const T* __restrict__ pcm, int64_t 
 
 // Passes 2 and 3 of the 512-point FFT whose pass-1 results sit in the warp's exchange buffer (A layout).
 // On return (re, im)[h][k2b] = X[t + 64 k2b] with t = lane + 32 h.
-__device__ __forceinline__ void fft512_tail(WarpSmem& ws, const Smem& s, int lane, float (&re)[2][8], float (&im)[2][8]) {
+template <typename Tables>      // anything with the pass-2 twiddles tw2[7][64]
+__device__ __forceinline__ void fft512_tail(WarpSmem& ws, const Tables& s, int lane, float (&re)[2][8], float (&im)[2][8]) {
   __syncwarp();
   // ---- pass 2: butterfly (k1, u) = (t >> 3, t & 7) transforms over v, twiddle W64^(u k2a)
 #pragma unroll
@@ -349,6 +350,175 @@ features_kernel(const T* __restrict__ pcm, int64_t valid_begin, int64_t valid_en
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// K8 — review-screen spectrogram: |STFT| with n_fft = win_length = 512, hop 256, centred frames and
+// zero padding, i.e. np.abs(librosa.stft(x, n_fft=512, win_length=512, hop_length=256))
+// (root/code/backend/voice_activity.py:148-154; settings.py:4-6).  Output [257 bins][T = 1 + n / 256 frames] float32,
+// frame t covering samples [256 t - 256, 256 t + 256).
+//
+// A warp transforms TWO consecutive frames with one 512-point complex FFT (the passes of K1): z[n] = w[n] (a[n] + i
+// b[n]) with a, b the two real frames, then X_a[k] = (Z[k] + conj Z[512-k]) / 2 and X_b[k] = (Z[k] - conj Z[512-k]) / 2i.
+// Eight warps = one tile of 16 frames; magnitudes go through a [bin][frame] shared tile (row stride 17) so that the
+// global stores are 64-byte row segments of the frequency-major output.  HBM-bound by definition
+// (4 B read + 4.02 B written per sample); the running maximum the dB stage needs is taken on the way.
+constexpr int kSpecGroups = 2;                              // independent halves of the CTA (8 warps each)
+constexpr int kSpecGroupWarps = kWarps / kSpecGroups;
+constexpr int kSpecTileFrames = 2 * kSpecGroupWarps;        // 16 frames per group tile: two per warp
+constexpr int kSpecRowStride = kSpecTileFrames + 1;
+
+struct SpecSmem {
+  float2 tw1[7][64];
+  float2 tw2[7][64];
+  float win[512];
+  float mag[kSpecGroups][257 * kSpecRowStride];
+  WarpSmem w[kWarps];
+};
+
+__device__ __forceinline__ void group_barrier(int group) {
+  asm volatile("bar.sync %0, %1;" ::"r"(1 + group), "n"(kSpecGroupWarps * 32) : "memory");
+}
+
+// The two halves of the CTA run their own tile loops behind their own named barriers, so one half's transforms
+// overlap the other's stores (one tile per CTA and a block barrier left every pipe under 30 % busy: 107 us per
+// 10-minute clip).
+template <typename T>
+__global__ void __launch_bounds__(kThreads, 1)
+stft512_kernel(const T* __restrict__ pcm, int64_t n, int64_t n_frames, const float2* __restrict__ tw512,
+               float* __restrict__ mag, unsigned int* __restrict__ max_bits) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  SpecSmem& s = *reinterpret_cast<SpecSmem*>(smem_raw);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int i = tid; i < 7 * 64; i += kThreads) {
+    const int k = i / 64 + 1, t = i % 64;
+    s.tw1[k - 1][t] = tw512[(t * k) & 511];
+    s.tw2[k - 1][t] = tw512[(8 * (t & 7) * k) & 511];
+  }
+  for (int i = tid; i < 512; i += kThreads) s.win[i] = 0.5f - 0.5f * cospif((float)i * (1.0f / 256.0f));   // periodic Hann
+  __syncthreads();
+  const int group = warp / kSpecGroupWarps, gw = warp % kSpecGroupWarps;
+  WarpSmem& ws = s.w[warp];
+  float* __restrict__ tile_s = s.mag[group];
+  float re[2][8], im[2][8];
+  float vmax = 0.f;
+  const int64_t n_tiles = (n_frames + kSpecTileFrames - 1) / kSpecTileFrames;
+  const int64_t tile_step = (int64_t)gridDim.x * kSpecGroups;
+#pragma unroll 1
+  for (int64_t tile = (int64_t)blockIdx.x * kSpecGroups + group; tile < n_tiles; tile += tile_step) {
+    const int64_t fa = tile * kSpecTileFrames + 2 * gw;       // frames fa (real part) and fa + 1 (imaginary part)
+    const int64_t g0 = fa * kHop - kHop;                      // first sample of frame fa; frame fa + 1 starts kHop later
+    const bool fast = g0 >= 0 && g0 + kHop + kWin <= n;       // warp-uniform: both frames inside the clip
+    {
+      // the 768 samples this warp reads in its next tile, pulled into L1 while this tile computes
+      const int64_t ng = g0 + tile_step * kSpecTileFrames * kHop + (int64_t)(128 / sizeof(T)) * lane;
+      if (lane < (int)((kHop + kWin) * sizeof(T) / 128) + 1 && ng >= 0 && ng < n)
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(pcm + ng));
+    }
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int t = lane + 32 * h;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int l = t + 64 * j;
+        float a, b;
+        if (fast) {
+          a = ld1(pcm + g0 + l);
+          b = ld1(pcm + g0 + kHop + l);
+        } else {
+          const int64_t ia = g0 + l, ib = ia + kHop;
+          a = (ia >= 0 && ia < n) ? ld1(pcm + ia) : 0.f;
+          b = (ib >= 0 && ib < n) ? ld1(pcm + ib) : 0.f;
+        }
+        const float wv = s.win[l];
+        re[h][j] = a * wv;
+        im[h][j] = b * wv;
+      }
+      dft8<false>(re[h], im[h]);
+#pragma unroll
+      for (int k1 = 0; k1 < 8; ++k1) {
+        if (k1) cmul(re[h][k1], im[h][k1], s.tw1[k1 - 1][t]);
+        ws.re[k1 * 72 + t] = re[h][k1];
+        ws.im[k1 * 72 + t] = im[h][k1];
+      }
+    }
+    fft512_tail(ws, s, lane, re, im);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+#pragma unroll
+      for (int k2b = 0; k2b < 8; ++k2b) {
+        const int q = lane + 32 * h + 64 * k2b;
+        ws.re[q] = re[h][k2b];
+        ws.im[q] = im[h][k2b];
+      }
+    }
+    __syncwarp();
+    for (int m = lane; m <= 256; m += 32) {
+      const int mm = (512 - m) & 511;
+      const float cr = ws.re[m], ci = ws.im[m], nr = ws.re[mm], ni = ws.im[mm];
+      const float ar = cr + nr, ai = ci - ni;          // 2 X_a[m]
+      const float br = cr - nr, bi = ci + ni;          // 2 i X_b[m]
+      tile_s[m * kSpecRowStride + 2 * gw] = 0.5f * sqrtf(ar * ar + ai * ai);
+      tile_s[m * kSpecRowStride + 2 * gw + 1] = 0.5f * sqrtf(br * br + bi * bi);
+    }
+    group_barrier(group);
+    // a warp stores two rows at a time: lanes 0-15 one bin, lanes 16-31 the next, 16 frames (64 bytes) each
+    const int64_t f = tile * kSpecTileFrames + (lane & 15);
+    if (f < n_frames) {
+      for (int row = 2 * gw + (lane >> 4); row <= 256; row += 2 * kSpecGroupWarps) {
+        const float v = tile_s[row * kSpecRowStride + (lane & 15)];
+        mag[(int64_t)row * n_frames + f] = v;
+        vmax = fmaxf(vmax, v);
+      }
+    }
+    group_barrier(group);      // the tile is rewritten by the group's next iteration
+  }
+  if (max_bits) {
+#pragma unroll
+    for (int d = 16; d; d >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, d));
+    if (lane == 0) atomicMax(max_bits, __float_as_uint(vmax));      // magnitudes are >= 0: their bit patterns order like the values
+  }
+}
+
+// The review screen's display transform (review_detections.py:880-881) on the magnitudes, in place:
+//   np.abs(librosa.amplitude_to_db(S ** 2, ref=np.max))  — librosa squares its argument once more, so with p = S^4 and
+// r = max(S)^4 (all float32, as numpy computes them) the value is |max(10 log10(max(1e-10, p)) - 10 log10(max(1e-10, r)),
+// -80)|: 0 at the loudest cell, 80 at the floor.
+__device__ __forceinline__ float spec_db_value(float m, float ref_db) {
+  const float p1 = m * m;
+  // numpy rounds the product and the difference separately; a fused multiply-subtract would leave 1e-6 at the
+  // loudest cell, where the reference has exactly 0
+  const float v = __fsub_rn(__fmul_rn(10.0f, log10f(fmaxf(1e-10f, p1 * p1))), ref_db);
+  return fabsf(fmaxf(v, -80.0f));
+}
+
+__global__ void __launch_bounds__(256)
+spec_db_kernel(float* __restrict__ mag, int64_t n_elems, const unsigned int* __restrict__ max_bits) {
+  const float smax = __uint_as_float(*max_bits);
+  const float r1 = smax * smax;
+  const float ref_db = __fmul_rn(10.0f, log10f(fmaxf(1e-10f, r1 * r1)));
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  // 16-byte vectors on the aligned body (two in flight per thread), scalars on the ragged head and tail
+  int64_t head = (int64_t)(((16 - (reinterpret_cast<uintptr_t>(mag) & 15)) & 15) / 4);
+  if (head > n_elems) head = n_elems;
+  const int64_t n4 = (n_elems - head) / 4;
+  float4* body = reinterpret_cast<float4*>(mag + head);
+  for (int64_t i = tid; i < n4; i += 2 * stride) {
+    const int64_t i2 = i + stride;
+    float4 a = body[i], b = i2 < n4 ? body[i2] : make_float4(0.f, 0.f, 0.f, 0.f);
+    a.x = spec_db_value(a.x, ref_db); a.y = spec_db_value(a.y, ref_db);
+    a.z = spec_db_value(a.z, ref_db); a.w = spec_db_value(a.w, ref_db);
+    body[i] = a;
+    if (i2 < n4) {
+      b.x = spec_db_value(b.x, ref_db); b.y = spec_db_value(b.y, ref_db);
+      b.z = spec_db_value(b.z, ref_db); b.w = spec_db_value(b.w, ref_db);
+      body[i2] = b;
+    }
+  }
+  if (tid < head) mag[tid] = spec_db_value(mag[tid], ref_db);
+  const int64_t tail0 = head + 4 * n4;
+  if (tid < n_elems - tail0) mag[tail0 + tid] = spec_db_value(mag[tail0 + tid], ref_db);
+}
+
 __global__ void pad_kernel(const float* __restrict__ src, int64_t n, float* __restrict__ dst, int64_t total) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
@@ -369,6 +539,37 @@ int features_init() {
                                      (int)sizeof(Smem)));
   SS_CUDA_CHECK(cudaFuncSetAttribute(features_kernel<int16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)sizeof(Smem)));
+  SS_CUDA_CHECK(cudaFuncSetAttribute(stft512_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)sizeof(SpecSmem)));
+  SS_CUDA_CHECK(cudaFuncSetAttribute(stft512_kernel<int16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)sizeof(SpecSmem)));
+  return SS_OK;
+}
+
+int launch_spectrogram(const ss_ctx* ctx, const void* pcm, int sample_fmt, int64_t n, float* mag, unsigned int* max_bits,
+                       cudaStream_t st) {
+  const int64_t n_frames = 1 + n / kHop;
+  const int64_t n_ctas = (n_frames + kSpecGroups * kSpecTileFrames - 1) / (kSpecGroups * kSpecTileFrames);
+  const int grid = (int)(n_ctas < kNumSMs ? n_ctas : kNumSMs);
+  if (max_bits) SS_CUDA_CHECK(cudaMemsetAsync(max_bits, 0, sizeof(unsigned int), st));
+  if (sample_fmt == kSampleS16)
+    stft512_kernel<int16_t><<<grid, kThreads, sizeof(SpecSmem), st>>>(static_cast<const int16_t*>(pcm), n, n_frames,
+                                                                      ctx->fe.tw512, mag, max_bits);
+  else
+    stft512_kernel<float><<<grid, kThreads, sizeof(SpecSmem), st>>>(static_cast<const float*>(pcm), n, n_frames,
+                                                                    ctx->fe.tw512, mag, max_bits);
+  SS_CUDA_CHECK(cudaGetLastError());
+  count_launch();
+  return SS_OK;
+}
+
+int launch_spectrogram_db(float* mag, int64_t n_elems, const unsigned int* max_bits, cudaStream_t st) {
+  if (n_elems <= 0) return SS_OK;
+  int64_t blocks = (n_elems / 4 + 255) / 256 + 1;
+  if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+  spec_db_kernel<<<(int)blocks, 256, 0, st>>>(mag, n_elems, max_bits);
+  SS_CUDA_CHECK(cudaGetLastError());
+  count_launch();
   return SS_OK;
 }
 

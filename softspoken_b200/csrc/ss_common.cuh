@@ -165,6 +165,10 @@ int launch_features_virtual(const ss_ctx* ctx, const void* pcm, int sample_fmt, 
                             int64_t offset, const int64_t* starts, int64_t w_base, int n_windows, float* mel,
                             cudaStream_t st);
 int launch_pad(const float* src, int64_t n, float* dst, cudaStream_t st);
+// K8 (review-screen spectrogram): magnitudes [257][1 + n / 256]; max_bits (optional) receives the bit pattern of the maximum
+int launch_spectrogram(const ss_ctx* ctx, const void* pcm, int sample_fmt, int64_t n, float* mag, unsigned int* max_bits,
+                       cudaStream_t st);
+int launch_spectrogram_db(float* mag, int64_t n_elems, const unsigned int* max_bits, cudaStream_t st);
 int launch_window_starts(int64_t* starts, int64_t n_windows, cudaStream_t st);
 // api.cu
 int ensure_workspace_f32(ss_ctx* ctx);

@@ -248,6 +248,21 @@ class Engine:
         check(lib.ss_silence_pcm16_host(self._ctx, C.c_void_p(pcm.ctypes.data), pcm.size,
                                         C.c_void_p(iv.ctypes.data), iv.shape[0], int(requantize)))
 
+    def spectrogram(self, pcm: torch.Tensor, db: bool = False) -> torch.Tensor:
+        """Mono clip on the device (float32, or int16 samples of a PCM_16 file) -> `[257, 1 + n // 256]` float32
+        magnitudes of the 512 / 256 STFT (K8, `voice_activity.wav_to_spec(trim_edges=False)`); `db=True` applies the
+        review screen's display transform in place (`ss_spectrogram_db`)."""
+        assert pcm.is_cuda and pcm.dim() == 1 and pcm.is_contiguous() and pcm.dtype in (torch.float32, torch.int16)
+        n = pcm.numel()
+        T = int(lib.ss_spectrogram_frames(n))
+        mag = torch.empty((257, T), dtype=torch.float32, device=self.device)
+        mx = torch.zeros(1, dtype=torch.float32, device=self.device)
+        fn = lib.ss_spectrogram_pcm16 if pcm.dtype == torch.int16 else lib.ss_spectrogram
+        check(fn(self._ctx, _ptr(pcm) if n else None, n, _ptr(mag), _ptr(mx), self._stream()))
+        if db:
+            check(lib.ss_spectrogram_db(self._ctx, _ptr(mag), mag.numel(), _ptr(mx), self._stream()))
+        return mag
+
     def _f32(self, t: torch.Tensor) -> torch.Tensor:
         if not isinstance(t, torch.Tensor):
             t = torch.as_tensor(np.asarray(t))

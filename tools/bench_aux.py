@@ -228,6 +228,66 @@ def run_postproc(args):
     eng.close()
 
 
+def run_spectrogram(args):
+    """K8 (review-screen spectrogram) at config-2 size: 10-minute clips, magnitudes and the dB display
+    transform; inputs rotate through four clips (4 x 106 MB of reads + writes: larger than L2).  Algorithmic bytes:
+    4 n read + 257 T 4 written for the STFT; 2 x 257 T 4 for the in-place dB pass."""
+    from oracle import spectrogram as osp            # checker only
+    from softspoken_b200 import synth
+    eng = load_engine(4, "bf16")
+    dev = torch.device("cuda", 0)
+    clips = [torch.from_numpy(synth.synth_audio(600.0, s)).to(dev) for s in range(4)]
+    n = clips[0].numel()
+    T = 1 + n // 256
+    stream = torch.cuda.current_stream()
+    outs = [eng.spectrogram(c) for c in clips]       # warm-up (and the buffers the dB pass runs on)
+    torch.cuda.synchronize()
+    reps = 3
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    from softspoken_b200 import _lib
+    import ctypes as C
+    reps = 10
+    mxs = torch.zeros(len(clips), device=dev)
+
+    def stft(i):      # the C-ABI call itself on preallocated buffers (Engine.spectrogram allocates its result)
+        _lib.check(_lib.lib.ss_spectrogram(eng._ctx, C.c_void_p(clips[i].data_ptr()), n, C.c_void_p(outs[i].data_ptr()),
+                                           C.c_void_p(mxs[i:].data_ptr()), eng._stream()))
+    for i in range(len(clips)):
+        stft(i)
+    torch.cuda.synchronize()
+    e0.record(stream)
+    for _ in range(reps):
+        for i in range(len(clips)):
+            stft(i)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    t_stft = e0.elapsed_time(e1) / (reps * len(clips)) / 1e3
+    mx = torch.tensor([float(o.max()) for o in outs], device=dev)
+    e0.record(stream)
+    for i, o in enumerate(outs):
+        _lib.check(_lib.lib.ss_spectrogram_db(eng._ctx, C.c_void_p(o.data_ptr()), o.numel(), C.c_void_p(mx[i:].data_ptr()), eng._stream()))
+    e1.record(stream)
+    torch.cuda.synchronize()
+    t_db = e0.elapsed_time(e1) / len(outs) / 1e3
+    x = clips[1][:2000000].cpu().numpy()
+    want = osp.stft_magnitude(x)
+    got = eng.spectrogram(clips[1][:2000000]).cpu().numpy()
+    err = float(np.abs(got - want).max() / want.max())
+    peak, src = peaks()
+    b1, b2 = 4 * n + 257 * T * 4, 2 * 257 * T * 4
+    line = {"metric": "spectrogram_GBps", "unit": "GB/s", "n_gpus": 1, "higher_is_better": True, "dtype": "f32", "data": "synthetic",
+            "value": b1 / t_stft / 1e9,
+            "config": {"workload": f"K8: 512/256 STFT magnitudes of 10-min mono clips ({n} samples -> [257, {T}]), pool of 4 clips"},
+            "K8_stft": {"ms": t_stft * 1e3, "algorithmic_bytes": b1, "GBps": b1 / t_stft / 1e9, "frac": b1 / t_stft / 1e9 / peak,
+                        "audio_hours_per_s": 600.0 / 3600.0 / t_stft},
+            "K8_db": {"ms": t_db * 1e3, "algorithmic_bytes": b2, "GBps": b2 / t_db / 1e9, "frac": b2 / t_db / 1e9 / peak},
+            "roofline": {"bound": "hbm", "peak": peak, "peak_source": src, "unit": "GB/s"},
+            "checks": {"max_rel_err_vs_oracle_2M_samples": err, "ok": err <= 1e-4}}
+    print(json.dumps(line), flush=True)
+    assert err <= 1e-4
+    eng.close()
+
+
 def eng_plan_windows(n):
     from softspoken_b200.engine import plan_windows
     return plan_windows(n)
@@ -325,7 +385,7 @@ def run_files(args):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("what", choices=["long", "silence", "files", "postproc"])
+    ap.add_argument("what", choices=["long", "silence", "files", "postproc", "spectrogram"])
     ap.add_argument("--scratch", default="/dev/shm" if os.path.isdir("/dev/shm") else None,
                     help="folder for the wav files of the `files` workload")
     ap.add_argument("--hours", type=float, default=24.0)
@@ -335,7 +395,7 @@ def main():
     ap.add_argument("--pcm16", action="store_true", help="config 4 from the int16 samples of a PCM_16 recording")
     ap.add_argument("--mode", default="f16x3")
     args = ap.parse_args()
-    {"long": run_long, "silence": run_silence, "files": run_files, "postproc": run_postproc}[args.what](args)
+    {"long": run_long, "silence": run_silence, "files": run_files, "postproc": run_postproc, "spectrogram": run_spectrogram}[args.what](args)
 
 
 if __name__ == "__main__":

@@ -157,3 +157,42 @@ def test_config2_clip_device_vs_host_paths(detector):
 def lib_windows(n):
     from softspoken_b200.engine import plan_windows
     return plan_windows(n)
+
+
+def test_headless_job_from_wav_files(detector, wavs, tmp_path):
+    """The whole GUI-less job on wav files: corpus driver (reader thread, int16 upload) -> detections CSV == the
+    golden CSV the reference wrote; review step (all erase) == the golden review CSV; "Silence Voices" back to wav
+    files == decode -> zero the rounded sample ranges -> re-encode, sample for sample."""
+    import json
+    import pandas as pd
+    from softspoken_b200 import corpus, review, silencer
+    d, files = wavs
+    eng = detector.model.engine
+    if eng.mode != "f16x3":
+        pytest.skip("one classifier mode is enough for the file pipeline")
+    rows = corpus.detect_corpus(files, eng.detect_host_batch, load=corpus.load_native_22050, group_size=1, prefetch=2)
+    text = corpus.csv_text(rows)
+    assert text.replace(d, "/data") == open(os.path.join(GOLDEN, "detections_seed0.csv")).read()
+    det_csv, rev_csv = str(tmp_path / "p_detections.csv"), str(tmp_path / "p_review.csv")
+    with open(det_csv, "w", newline="") as f:
+        f.write(text)
+    table = review.ReviewTable.open(det_csv, rev_csv)
+    for tick in range(len(table)):                 # the golden case clicked "erase" row by row, one second apart
+        table.label(tick, True, pd.Timestamp("2026-01-02 03:04:05") + pd.Timedelta(seconds=tick))
+    df = review.save_review(table, rev_csv)
+    with open(os.path.join(GOLDEN, "review_cases.json")) as f:
+        want_review = json.load(f)["seed0_erase_all"]["outputs"]["golden_review.csv"]
+    assert open(rev_csv).read().replace(d, "/data") == want_review
+    out = tmp_path / "silenced"
+    out.mkdir()
+    silencer.SilenceWorker(silencer.coerce_erase(pd.read_csv(rev_csv)), str(out), engine=eng).run()
+    for path in files:
+        x, sr = wavio.read_wav(path)
+        want = wavio.encode_pcm16(x)
+        mine = df[df["file_name"] == os.path.basename(path)]
+        assert len(mine) > 0
+        for s, e in zip(mine["start_time"], mine["end_time"]):
+            a, b = silencer.row_to_samples(s, e, sr, len(x))
+            want[a:b] = 0
+        got, got_sr = wavio.read_wav_pcm16(str(out / (os.path.basename(path)[:-4] + "_silenced.wav")))
+        assert got_sr == sr and np.array_equal(got, want)

@@ -166,13 +166,14 @@ def _prefetched(groups, load_one: Callable[[int], np.ndarray], depth: int = 2):
 def detect_corpus(files: Sequence[str], detect_batch: Callable[[List[np.ndarray]], List[np.ndarray]],
                   load: Callable[[str], np.ndarray] = load_mono_22050, durations: Optional[Sequence[float]] = None,
                   group_size: int = 8, device: Optional[torch.device] = None, next_id: int = 1,
-                  journal: Optional[str] = None, prefetch: int = 2):
+                  journal: Optional[str] = None, prefetch: int = 2, stats: Optional[dict] = None):
     """-> list of CSV row dicts on rank 0 (None on the other ranks).
 
     `detect_batch(clips) -> [int32 [R,2] region bins per clip]` is `Engine.detect_host_batch` (or any stand-in
     with that contract: the CPU tests drive this function with the oracle).  `journal`: path prefix of the
     per-rank progress files that make the run restartable (`Journal`).  `prefetch`: groups of files a reader
-    thread decodes ahead of the GPU (0 = read in line, as the reference does)."""
+    thread decodes ahead of the GPU (0 = read in line, as the reference does).  `stats`: a dict that receives where
+    this rank's wall time went (`wait_files_s`, `detect_s`, `gather_rows_s`)."""
     world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
     rank = dist.get_rank() if world > 1 else 0
     if durations is None:
@@ -184,9 +185,17 @@ def detect_corpus(files: Sequence[str], detect_batch: Callable[[List[np.ndarray]
     # triplets of earlier runs enter the gather once, through rank 0
     parts = [np.concatenate([np.full((len(b), 1), i, np.int32), b], axis=1) for i, b in sorted(done.items())] if rank == 0 else []
     groups = [mine[g0:g0 + group_size] for g0 in range(0, len(mine), group_size)]
+    import time
+    t_wait = t_detect = 0.0
+    t_mark = time.perf_counter()
     try:
         for idx, clips in _prefetched(groups, lambda i: load(files[i]), depth=prefetch):
-            for i, bins in zip(idx, detect_batch(clips)):
+            t_now = time.perf_counter()
+            t_wait += t_now - t_mark
+            results = detect_batch(clips)
+            t_mark = time.perf_counter()
+            t_detect += t_mark - t_now
+            for i, bins in zip(idx, results):
                 b = np.asarray(bins, dtype=np.int32).reshape(-1, 2)
                 parts.append(np.concatenate([np.full((len(b), 1), i, np.int32), b], axis=1))
                 if jr:
@@ -196,11 +205,13 @@ def detect_corpus(files: Sequence[str], detect_batch: Callable[[List[np.ndarray]
     finally:
         if jr:
             jr.close()
+    t_mark = time.perf_counter()
     local = np.concatenate(parts) if parts else np.zeros((0, 3), np.int32)
     allrows = ssdist.gather_detections(local, device)
-    if rank != 0:
-        return None
-    return ssdist.rows_from_triplets(list(files), allrows, next_id)
+    rows = ssdist.rows_from_triplets(list(files), allrows, next_id) if rank == 0 else None
+    if stats is not None:
+        stats.update(wait_files_s=t_wait, detect_s=t_detect, gather_rows_s=time.perf_counter() - t_mark)
+    return rows
 
 
 def csv_text(rows) -> str:
@@ -227,6 +238,8 @@ def main(argv=None) -> int:
     ap.add_argument("--checkpoint", default=None, help="reference checkpoint (.pth); seeded init if absent, as the reference")
     ap.add_argument("--mode", default=None)
     ap.add_argument("--max-batch", type=int, default=512)
+    ap.add_argument("--group-size", type=int, default=4,
+                    help="files per library call (uploads overlap compute inside a call; the reader thread loads the next groups meanwhile)")
     ap.add_argument("--resume", action="store_true",
                     help="keep per-rank progress files next to out_csv (<out_csv>.journal.rank<r>) and skip the files "
                          "an earlier, interrupted run of the same file list already finished")
@@ -248,12 +261,33 @@ def main(argv=None) -> int:
         print("No checkpoint found. Starting training from scratch.")     # NNDetector.py:52
         sd = checkpoint.synthetic_state_dict(0)
     eng = Engine(sd, local, max_batch=args.max_batch, **({"mode": args.mode} if args.mode else {}))
-    rows = detect_corpus(files, eng.detect_host_batch, load=load_native_22050, device=device,
-                         journal=(args.out_csv + ".journal") if args.resume else None)
+    import time
+    durations = [wavio.duration_and_rate(f)[0] for f in files]
+    # One-off costs out of the way before the clock starts: workspace allocation for the longest file (tens of GB for
+    # a 1,005-window batch), the first launch of every kernel, the NCCL communicator and its gather path.
+    t_init = time.perf_counter()
+    from . import detector, worker  # noqa: F401  (row building imports them: 0.9 s on first use)
+    eng.reserve(int(max(durations, default=0.0) * spec.SAMPLE_RATE) + 1)
+    eng.detect_host_batch([np.zeros(spec.SAMPLE_RATE, np.int16)])
+    if world > 1:
+        ssdist.gather_detections(np.zeros((0, 3), np.int32), device)
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    t_init = t0 - t_init
+    stats: dict = {}
+    rows = detect_corpus(files, eng.detect_host_batch, load=load_native_22050, durations=durations, device=device,
+                         group_size=max(1, args.group_size), stats=stats, journal=(args.out_csv + ".journal") if args.resume else None)
     if rows is not None:
         with open(args.out_csv, "w", newline="") as f:
             f.write(csv_text(rows))
+        dt = time.perf_counter() - t0          # rank 0 returns from the gather last: slowest rank + gather + CSV
+        hours = sum(durations) / 3600.0
         print(f"{len(rows)} detections in {len(files)} files -> {args.out_csv}")
+        print(f"{hours:.3f} audio-hours in {dt:.3f} s on {world} GPU(s): {hours / dt:.2f} audio-hours/s "
+              f"({hours * 3600 / dt:,.0f}x real time; file read + upload + detect + gather + CSV; "
+              f"{t_init:.1f} s of one-off initialisation before that)")
+        print("rank 0: " + ", ".join(f"{k} {v:.3f}" for k, v in stats.items()) + f", csv_s {time.perf_counter() - t0 - sum(stats.values()):.3f}")
     eng.close()
     if world > 1:
         dist.destroy_process_group()

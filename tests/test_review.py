@@ -169,3 +169,40 @@ def test_live_reference_agrees_on_a_fresh_case(tmp_path):
                                        {k: tuple(v) for k, v in case["durations"].items()})
     got, _ = _run(case, tmp_path)
     assert got == case["outputs"]
+
+
+def test_config5_sized_review_table(tmp_path):
+    """BASELINE config 5 size: 10,000 detections over 1,000 files through the review step and all three exporters
+    (host code must stay linear: the reference appends rows one `df.loc[len(df)]` at a time)."""
+    import time
+    from softspoken_b200 import synth
+    files, start, end = synth.synth_review_rows(10000, 1000, 600.0, 0)
+    det = pd.DataFrame({"ID": np.arange(1, 10001), "file_path": [f"/corpus/site{int(f) % 7}" for f in files],
+                        "file_name": [f"clip_{int(f):04d}.wav" for f in files], "start_time": start, "end_time": end,
+                        "erase": 0, "user_comment": "", "review_datetime": ""})
+    t0 = time.perf_counter()
+    table = review.ReviewTable.from_detections(det)
+    table.erase_all("2026-01-01 00:00:00")
+    df = review.save_review(table, str(tmp_path / "r.csv"), tmp_path, "p", duration_of=lambda p: 600.0)
+    dt = time.perf_counter() - t0
+    assert len(df) == int(((end - start) > 0.1).sum()) and (df["erase"] == 1).all()
+    names = df["file_name"].tolist()
+    assert names == sorted(names) and dt < 20.0
+    back = pd.read_csv(tmp_path / "r.csv")
+    assert np.allclose(back["start_time"], df["start_time"]) and len(back) == len(df)
+    raven = (tmp_path / "Raven Outputs" / "p" / "p.txt").read_text().splitlines()
+    assert len(raven) == len(df) + 1
+    listed = (tmp_path / "Raven Outputs" / "p" / "p_listfile.txt").read_text().splitlines()
+    # Begin Time = position in the file + 600 s for every file listed before it
+    first = raven[1].split("\t")
+    assert abs(float(first[3]) - df["start_time"].iloc[0]) < 1e-6 and first[8] == listed[0]
+    last = raven[-1].split("\t")
+    assert abs(float(last[3]) - (600.0 * (len(listed) - 1) + df["start_time"].iloc[-1])) < 1e-5
+
+
+def test_voice_activity_mirror_fails_loudly_without_an_engine():
+    from softspoken_b200 import voice_activity
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        voice_activity.wav_to_spec(np.zeros(1000, np.float32))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        voice_activity.spectrogram_db(np.zeros(1000, np.float32))

@@ -203,3 +203,35 @@ def _write_pcm16(path: str, data: np.ndarray, sr: int) -> None:
     float->short conversion could not be pinned in this image: parity is claimed for the
     float32 buffers handed to the writer, not for the encoded bytes."""
     wavio.write_wav_pcm16(path, wavio.encode_pcm16(data), sr)
+
+
+def main(argv=None) -> int:
+    """`python -m softspoken_b200.silencer review.csv out_dir`: the "Silence Voices" button without the GUI — the last
+    step after `softspoken_b200.corpus` (detections) and `softspoken_b200.review` (review CSV).  Rows are selected and
+    coerced as `SilenceVoicesScreen.load_review_data` does (silencer_ui.py:1098-1106)."""
+    import argparse
+    import time
+    ap = argparse.ArgumentParser(description="zero the erase == 1 intervals of a review CSV and write <stem>_silenced.wav files")
+    ap.add_argument("review_csv")
+    ap.add_argument("output_dir")
+    ap.add_argument("--device", type=int, default=0)
+    args = ap.parse_args(argv)
+    from . import checkpoint
+    from .engine import Engine
+    df = coerce_erase(pd.read_csv(args.review_csv))
+    os.makedirs(args.output_dir, exist_ok=True)
+    eng = Engine(checkpoint.synthetic_state_dict(0), args.device, max_batch=1)     # K7 needs no weights: any model will do
+    worker = SilenceWorker(df, args.output_dir, engine=eng)
+    done = []
+    worker.signals.fileComplete.connect(done.append)
+    t0 = time.perf_counter()
+    worker.run()
+    dt = time.perf_counter() - t0
+    eng.close()
+    n_rows = int((df["erase"] == 1).sum()) if "erase" in df.columns and len(df) else 0
+    print(f"{n_rows} intervals silenced in {len(done)} files -> {args.output_dir} ({dt:.2f} s)")
+    return 0
+
+
+if __name__ == "__main__":
+    raise SystemExit(main())

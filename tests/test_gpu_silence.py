@@ -119,3 +119,24 @@ def test_silence_worker_pcm16_files_route_equals_float32_route(engine, tmp_path)
     got, _ = wavio.read_wav_pcm16(str(out_a / "m_silenced.wav"))
     assert not got[3:6000].any() and got[int(2.5 * sr):].max() == 0 and got[6001:int(2.5 * sr)].any()
     assert [len(w.signals.fileComplete.log) for w in (fast, slow)] == [4, 4]
+
+
+def test_silencer_cli(tmp_path, capsys):
+    """`python -m softspoken_b200.silencer review.csv out_dir` end to end on two small files."""
+    from softspoken_b200 import silencer, wavio
+    rng = np.random.default_rng(3)
+    src = tmp_path / "in"
+    src.mkdir()
+    a = rng.integers(-20000, 20000, 30000).astype(np.int16)
+    wavio.write_wav_pcm16(str(src / "a.wav"), a, 22050)
+    wavio.write_wav_pcm16(str(src / "b.wav"), a[::-1].copy(), 22050)
+    pd.DataFrame({"ID": [1, 2, 3], "file_path": [str(src)] * 3, "file_name": ["a.wav", "b.wav", "a.wav"],
+                  "start_time": [0.1, 0.2, 0.9], "end_time": [0.3, 0.4, 1.0], "erase": [1, "junk", 1],
+                  "user_comment": "", "review_datetime": ""}).to_csv(tmp_path / "r.csv", index=False)
+    assert silencer.main([str(tmp_path / "r.csv"), str(tmp_path / "out")]) == 0
+    assert "2 intervals silenced in 1 files" in capsys.readouterr().out
+    got, _ = wavio.read_wav_pcm16(str(tmp_path / "out" / "a_silenced.wav"))
+    want = wavio.encode_pcm16(a.astype(np.float32) / np.float32(32768))
+    want[2205:6615] = 0
+    want[19845:22050] = 0
+    assert np.array_equal(got, want) and not (tmp_path / "out" / "b_silenced.wav").exists()

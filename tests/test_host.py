@@ -401,3 +401,66 @@ def test_silence_worker_pcm16_pipeline_host_logic(tmp_path, capsys):
         want = osil.silence_pcm16(fr, sr, [(r[1], r[2]) for r in rows if r[0] == n])
         got, got_sr = wavio.read_wav_pcm16(str(out / (n[:-4] + "_silenced.wav")))
         assert got_sr == sr and np.array_equal(got, want), n
+
+
+def _riff(chunks):
+    body = b"WAVE" + b"".join(cid + struct.pack("<I", len(data)) + data + (b"\x00" if len(data) & 1 else b"")
+                              for cid, data in chunks)
+    return b"RIFF" + struct.pack("<I", len(body)) + body
+
+
+def test_wav_parser_field_recorder_layouts(tmp_path):
+    """RIFF layouts field recorders really write: metadata chunks (LIST / ICMT-style, odd-sized, padded) between
+    `fmt ` and `data`, WAVE_FORMAT_EXTENSIBLE headers, 24- and 32-bit PCM, a `data` size field that overstates the
+    bytes present (recording cut off) and trailing chunks after `data`."""
+    rng = np.random.default_rng(8)
+    pcm = rng.integers(-32768, 32768, 1001).astype("<i2")
+    fmt16 = struct.pack("<HHIIHH", 1, 1, 22050, 44100, 2, 16)
+    p = str(tmp_path / "meta.wav")
+    with open(p, "wb") as f:
+        f.write(_riff([(b"fmt ", fmt16), (b"LIST", b"INFOICMT\x07\x00\x00\x00AudioM\x00"), (b"junk", b"abc"),
+                       (b"data", pcm.tobytes()), (b"bext", b"x" * 10)]))
+    x, sr = wavio.read_wav(p)
+    assert sr == 22050 and np.array_equal(x, pcm.astype(np.float32) / np.float32(32768))
+    got, sr2 = wavio.read_wav_pcm16(p)
+    assert sr2 == 22050 and np.array_equal(got, pcm)
+    assert wavio.duration_and_rate(p) == (1001 / 22050, 22050)
+    # WAVE_FORMAT_EXTENSIBLE wrapping PCM_16 stereo
+    st = rng.integers(-32768, 32768, (500, 2)).astype("<i2")
+    ext = struct.pack("<HHIIHH", 0xFFFE, 2, 48000, 192000, 4, 16) + struct.pack("<HHI", 22, 16, 3) + \
+        struct.pack("<H", 1) + b"\x00\x00\x00\x00\x10\x00\x80\x00\x00\xaa\x00\x38\x9b\x71"
+    p2 = str(tmp_path / "ext.wav")
+    with open(p2, "wb") as f:
+        f.write(_riff([(b"fmt ", ext), (b"data", st.tobytes())]))
+    y, sr = wavio.read_wav(p2)
+    assert sr == 48000 and y.shape == (2, 500) and np.array_equal(y, (st.astype(np.float32) / np.float32(32768)).T)
+    fr, _ = wavio.read_wav_pcm16(p2)
+    assert fr.shape == (500, 2) and np.array_equal(fr, st)
+    # 24-bit and 32-bit PCM: value / 2^23 and value / 2^31 (libsndfile's float read)
+    v24 = np.array([0, 1, -1, 8388607, -8388608, 123456, -654321], np.int32)
+    b24 = b"".join(int(v & 0xFFFFFF).to_bytes(3, "little") for v in v24)
+    p3 = str(tmp_path / "p24.wav")
+    with open(p3, "wb") as f:
+        f.write(_riff([(b"fmt ", struct.pack("<HHIIHH", 1, 1, 22050, 66150, 3, 24)), (b"data", b24)]))
+    z, _ = wavio.read_wav(p3)
+    assert np.array_equal(z, (v24.astype(np.float64) / 8388608.0).astype(np.float32))
+    assert wavio.read_wav_pcm16(p3) is None
+    v32 = np.array([0, 1, -1, 2147483647, -2147483648], "<i4")
+    p4 = str(tmp_path / "p32.wav")
+    with open(p4, "wb") as f:
+        f.write(_riff([(b"fmt ", struct.pack("<HHIIHH", 1, 1, 22050, 88200, 4, 32)), (b"data", v32.tobytes())]))
+    z, _ = wavio.read_wav(p4)
+    assert np.array_equal(z, (v32.astype(np.float64) / 2147483648.0).astype(np.float32))
+    # truncated recording: the data chunk claims more than the file holds -> the frames that are there
+    whole = _riff([(b"fmt ", fmt16), (b"data", pcm.tobytes())])
+    p5 = str(tmp_path / "cut.wav")
+    with open(p5, "wb") as f:
+        f.write(whole[:-501])
+    x5, _ = wavio.read_wav(p5)
+    assert len(x5) == (len(pcm) * 2 - 501) // 2 and np.array_equal(x5, (pcm[:len(x5)].astype(np.float32) / np.float32(32768)))
+    for bad in (b"RIFF\x04\x00\x00\x00WAVE", _riff([(b"data", b"\x00\x00")]), _riff([(b"fmt ", struct.pack("<HHIIHH", 85, 1, 8000, 8000, 1, 8)), (b"data", b"\x00")])):
+        pb = str(tmp_path / "bad2.wav")
+        with open(pb, "wb") as f:
+            f.write(bad)
+        with pytest.raises(wavio.WavError):
+            wavio.read_wav(pb)

@@ -190,6 +190,17 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
         "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
       : "r"(taddr));
 }
+#ifndef SS_TC_STCS
+#define SS_TC_STCS 0
+#endif
+// Epilogue store of one 16-byte vector.  -DSS_TC_STCS=1: st.global.cs (evict-first), an experiment.
+__device__ __forceinline__ void st16(uint16_t* p, uint4 v) {
+#if SS_TC_STCS
+  __stcs(reinterpret_cast<uint4*>(p), v);
+#else
+  *reinterpret_cast<uint4*>(p) = v;
+#endif
+}
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // One lane of a converged warp (the CUTLASS elect_one_sync idiom).  Keeping the role loops warp-uniform and
@@ -705,23 +716,23 @@ conv_tc_kernel(const TcJob job) {
               if (ph.x == 0x12345678u && lw[0] == 0x9abcdef0u) p.err[1] = 1;      // keep the values alive
             } else if (!c.upsample) {
               if (in_tensor) {
-                *reinterpret_cast<uint4*>(c.out + plane_off + (int64_t)pos * 8) = ph;
+                st16(c.out + plane_off + (int64_t)pos * 8, ph);
                 if constexpr (kSplit)
-                  *reinterpret_cast<uint4*>(c.out_lo + plane_off + (int64_t)pos * 8) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+                  st16(c.out_lo + plane_off + (int64_t)pos * 8, make_uint4(lw[0], lw[1], lw[2], lw[3]));
               }
             } else if (interior) {
               uint16_t* o = c.out + plane_off + up * 8;
-              *reinterpret_cast<uint4*>(o) = ph;
-              *reinterpret_cast<uint4*>(o + 8) = ph;
-              *reinterpret_cast<uint4*>(o + (int64_t)Wp2 * 8) = ph;
-              *reinterpret_cast<uint4*>(o + (int64_t)Wp2 * 8 + 8) = ph;
+              st16(o, ph);
+              st16(o + 8, ph);
+              st16(o + (int64_t)Wp2 * 8, ph);
+              st16(o + (int64_t)Wp2 * 8 + 8, ph);
               if constexpr (kSplit) {
                 const uint4 pl = make_uint4(lw[0], lw[1], lw[2], lw[3]);
                 uint16_t* ol = c.out_lo + plane_off + up * 8;
-                *reinterpret_cast<uint4*>(ol) = pl;
-                *reinterpret_cast<uint4*>(ol + 8) = pl;
-                *reinterpret_cast<uint4*>(ol + (int64_t)Wp2 * 8) = pl;
-                *reinterpret_cast<uint4*>(ol + (int64_t)Wp2 * 8 + 8) = pl;
+                st16(ol, pl);
+                st16(ol + 8, pl);
+                st16(ol + (int64_t)Wp2 * 8, pl);
+                st16(ol + (int64_t)Wp2 * 8 + 8, pl);
               }
             }
           }

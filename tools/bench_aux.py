@@ -163,11 +163,12 @@ def run_postproc(args):
     against the oracle on a prefix."""
     from oracle import postproc as pp               # checker only
     from softspoken_b200 import spec
+    from softspoken_b200.engine import plan_windows, timeline_bins
     eng = load_engine(4, "bf16")
     dev = torch.device("cuda", 0)
     n = int(round(args.hours * 3600 * SR))
-    W = eng_plan_windows(n)
-    out_len = eng_timeline_bins(n + 2 * spec.PAD_SAMPLES)
+    W = plan_windows(n)
+    out_len = timeline_bins(n + 2 * spec.PAD_SAMPLES)
     g = torch.Generator(device=dev).manual_seed(5)
     slow = torch.nn.functional.interpolate(torch.randn(1, 1, W // 16 + 2, device=dev, generator=g), size=W, mode="linear")[0, 0]
     logits = (0.1 + 0.08 * slow[:, None] + 0.02 * torch.randn(W, 256, device=dev, generator=g)).contiguous()
@@ -286,16 +287,6 @@ def run_spectrogram(args):
     print(json.dumps(line), flush=True)
     assert err <= 1e-4
     eng.close()
-
-
-def eng_plan_windows(n):
-    from softspoken_b200.engine import plan_windows
-    return plan_windows(n)
-
-
-def eng_timeline_bins(n_padded):
-    from softspoken_b200.engine import timeline_bins
-    return timeline_bins(n_padded)
 
 
 def run_files(args):

@@ -371,6 +371,11 @@ def run_b200(args):
             line["cpu_baseline"] = {"value": v, "unit": "audio-hours/s", "cores": threads, "kind": "port",
                                     "sample": f"{nwin} windows (batches of 32) of one 10-min clip in {dt:.1f} s, "
                                               "oracle port of the reference CPU detector incl. spec head"}
+            if threads >= 2:
+                # the reference itself runs on half the cores (settings.py:32, NNDetector.py:25): a short second sample
+                vh, nh, dth = cpu_detector_sample(sd, args.cpu_seconds / 3.0, threads // 2)
+                line["cpu_baseline"]["reference_default_threads"] = {
+                    "value": vh, "cores": threads // 2, "sample": f"{nh} windows in {dth:.1f} s"}
         print(json.dumps(line), flush=True)
     eng.close()
     if world > 1:

@@ -1,5 +1,6 @@
 """BASELINE.json configs 4 and 5 on one B200: one JSON line each (same vocabulary as bench.py).
 
+    python tools/bench_aux.py config1                  # config 1: one 60 s clip, CPU reference port next to the GPU path
     python tools/bench_aux.py long    [--hours 24]     # config 4: one long recording streamed in chunks
     python tools/bench_aux.py silence [--files 1000]   # config 5: 10k flagged intervals masked across the corpus
     python tools/bench_aux.py files   [--files 24]     # config 2 from wav FILES: read + decode + upload + detect + CSV,
@@ -150,6 +151,62 @@ def run_silence(args):
     }
     print(json.dumps(line), flush=True)
     assert ok
+    eng.close()
+
+
+def run_config1(args):
+    """BASELINE config 1: one synthetic 60 s mono clip.  The reference's CPU detector (oracle port of its exact
+    sequence: batches of 32 windows incl. the discarded spec head, float64 averaging, string-time regions) is timed on
+    all host cores and on half of them (the reference's own default, settings.py:32); the GPU path is one
+    `ss_detect_host` call on the same samples (median of 20).  The regions must be identical, and the CSV rows must be
+    the golden rows the real reference wrote for this clip."""
+    from oracle import model as om, postproc as pp          # the CPU side of the comparison
+    from softspoken_b200 import synth
+    from softspoken_b200.detector import region_bins_to_times
+    eng = load_engine(128, args.mode)
+    with open(os.path.join(ROOT, "tests", "golden", "head_seed0.json")) as f:
+        head = json.load(f)
+    from softspoken_b200 import checkpoint
+    sd = checkpoint.synthetic_state_dict(0, head)
+    audio = synth.synth_audio(60.0, 0)
+    padded = pp.pad_audio(audio)
+    starts = pp.plan_windows(60.0)
+    cpu = {}
+    ref_times = None
+    n_cores = os.cpu_count() or 1
+    for threads in sorted({n_cores, max(1, n_cores // 2)}, reverse=True):
+        torch.set_num_threads(threads)
+        t0 = time.perf_counter()
+        preds = []
+        for b0 in range(0, len(starts), 32):
+            x = torch.stack([torch.from_numpy(padded[i:i + 66150]) for i in starts[b0:b0 + 32]])
+            _, mk = om.forward(sd, x, want_spec=True)
+            preds.append(mk.numpy())
+        entries = pp.average_overlapping(np.vstack(preds), len(padded) / SR)
+        regions = pp.find_speech_regions(entries)
+        cpu[threads] = time.perf_counter() - t0
+        ref_times = pp.regions_to_times(regions)
+    bins, _ = eng.detect_host(audio, want_logits=True)       # warm-up
+    lat = []
+    for _ in range(20):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        bins = eng.detect_host(audio)
+        lat.append(time.perf_counter() - t0)
+    lat.sort()
+    gpu_s = lat[len(lat) // 2]
+    got_times = region_bins_to_times(bins)
+    same = got_times == ref_times
+    rows = pp.csv_text(pp.detection_rows("/data/clip_seed0.wav", got_times, 1)).splitlines()[1:]
+    golden = open(os.path.join(ROOT, "tests", "golden", "detections_seed0.csv")).read().splitlines()[1:1 + len(rows)]
+    line = {"metric": "audio_hours_per_sec", "unit": "audio-hours/s", "n_gpus": 1, "higher_is_better": True, "dtype": args.mode,
+            "data": "synthetic", "value": 60.0 / 3600.0 / gpu_s,
+            "config": {"workload": "config1: one 60 s mono 22.05 kHz clip (105 windows), host float32 buffer -> regions on the host"},
+            "gpu": {"median_ms": gpu_s * 1e3, "min_ms": lat[0] * 1e3, "regions": len(got_times)},
+            "cpu_reference_port": {str(k): {"seconds": v, "audio_hours_per_s": 60.0 / 3600.0 / v} for k, v in cpu.items()},
+            "checks": {"regions_identical_to_cpu": bool(same), "csv_rows_equal_golden_reference_rows": rows == golden}}
+    print(json.dumps(line), flush=True)
+    assert same and rows == golden
     eng.close()
 
 
@@ -376,7 +433,7 @@ def run_files(args):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("what", choices=["long", "silence", "files", "postproc", "spectrogram"])
+    ap.add_argument("what", choices=["long", "silence", "files", "postproc", "spectrogram", "config1"])
     ap.add_argument("--scratch", default="/dev/shm" if os.path.isdir("/dev/shm") else None,
                     help="folder for the wav files of the `files` workload")
     ap.add_argument("--hours", type=float, default=24.0)
@@ -386,7 +443,7 @@ def main():
     ap.add_argument("--pcm16", action="store_true", help="config 4 from the int16 samples of a PCM_16 recording")
     ap.add_argument("--mode", default="f16x3")
     args = ap.parse_args()
-    {"long": run_long, "silence": run_silence, "files": run_files, "postproc": run_postproc, "spectrogram": run_spectrogram}[args.what](args)
+    {"long": run_long, "silence": run_silence, "files": run_files, "postproc": run_postproc, "spectrogram": run_spectrogram, "config1": run_config1}[args.what](args)
 
 
 if __name__ == "__main__":

@@ -104,6 +104,18 @@ SS_API int ss_pad(ss_ctx* ctx, const float* pcm_dev, int64_t n_samples, float* p
 SS_API int ss_features(ss_ctx* ctx, const float* pcm_dev, int64_t n_padded, const int64_t* win_start_dev,
                 int n_windows, float* mel_out_dev, void* stream);
 
+/* K9 — sample-rate conversion to the detector's rate: stands where load_audio calls
+ * librosa.resample (root/code/backend/voice_activity.py:44-66; soxr "HQ" there — NOT restated here: this is a
+ * polyphase FIR with a caller-designed table, parity with the reference unpinned for resampled files).
+ *   out[m] = sum_{j=-T..T} pcm[(m * down) div up - j] * table[(j + T) * up + (m * down) mod up],  pcm = 0 outside
+ * n_out must be ceil(n_in * up / down) (librosa's output length); table_dev: [2 * taps_half + 1][up] float32
+ * (softspoken_b200/resample.py designs it: Kaiser-windowed sinc, unit DC gain per phase).
+ * *_pcm16 reads the int16 samples of a PCM_16 file (value / 32768). */
+SS_API int ss_resample(ss_ctx* ctx, const float* pcm_dev, int64_t n_in, float* out_dev, int64_t n_out, int up, int down,
+                int taps_half, const float* table_dev, void* stream);
+SS_API int ss_resample_pcm16(ss_ctx* ctx, const int16_t* pcm_dev, int64_t n_in, float* out_dev, int64_t n_out, int up,
+                      int down, int taps_half, const float* table_dev, void* stream);
+
 /* K8 — review-screen spectrogram: voice_activity.wav_to_spec(data, trim_edges=False)
  * (root/code/backend/voice_activity.py:148-154) = np.abs(librosa.stft(data, n_fft=512, win_length=512,
  * hop_length=256)): periodic Hann, centred frames, zero padding.  mag_dev: [257 bins][ss_spectrogram_frames(n)]

@@ -54,6 +54,8 @@ _SIGNATURES = {
     "ss_timeline_bins": (_i64, [_i64]),
     "ss_pad": (_int, [_p, _p, _i64, _p, _p]),
     "ss_features": (_int, [_p, _p, _i64, _p, _int, _p, _p]),
+    "ss_resample": (_int, [_p, _p, _i64, _p, _i64, _int, _int, _int, _p, _p]),
+    "ss_resample_pcm16": (_int, [_p, _p, _i64, _p, _i64, _int, _int, _int, _p, _p]),
     "ss_spectrogram_frames": (_i64, [_i64]),
     "ss_spectrogram": (_int, [_p, _p, _i64, _p, _p, _p]),
     "ss_spectrogram_pcm16": (_int, [_p, _p, _i64, _p, _p, _p]),

@@ -25,26 +25,31 @@ from . import dist as ssdist
 from . import spec, wavio
 
 
-def load_mono_22050(path: str) -> np.ndarray:
-    """`voice_activity.load_audio` for what the configs use: wav -> float32 mono at 22,050 Hz.  Multi-channel
-    files are averaged as `librosa.to_mono` does (voice_activity.py:61-63); other rates are refused (the
-    reference resamples with soxr, which this path does not restate — SURVEY §8c)."""
+def load_mono_22050(path: str, engine=None) -> np.ndarray:
+    """`voice_activity.load_audio` for a corpus file: wav -> float32 mono at 22,050 Hz.  Multi-channel files are
+    averaged as `librosa.to_mono` does (voice_activity.py:61-63).  Other rates go through the K9 resampling kernel
+    when an `engine` is given (this package's documented filter, not the reference's soxr: SURVEY §8c — such files
+    are outside the bit-exactness claims) and are refused without one."""
     x, sr = wavio.read_wav(path)
     if x.ndim > 1:
         x = np.mean(x, axis=0).astype(np.float32)
+    x = np.ascontiguousarray(x, dtype=np.float32)
     if sr != spec.SAMPLE_RATE:
-        raise ValueError(f"{path}: sample rate {sr} != {spec.SAMPLE_RATE} (resampling is outside this path)")
-    return np.ascontiguousarray(x, dtype=np.float32)
+        if engine is None:
+            raise ValueError(f"{path}: sample rate {sr} != {spec.SAMPLE_RATE} and no engine to resample it")
+        from .worker import resample_on_device
+        x = resample_on_device(x, sr, engine)
+    return x
 
 
-def load_native_22050(path: str) -> np.ndarray:
+def load_native_22050(path: str, engine=None) -> np.ndarray:
     """Like `load_mono_22050`, but a mono PCM_16 file is returned as its int16 samples (the library decodes them on
     the device: `ss_detect_host_batch_pcm16`), so the host never builds the float32 copy and the upload is half the
     size.  Detections are bit-identical to the float32 route (tests/test_gpu_pcm16.py)."""
     got = wavio.read_wav_pcm16(path)
     if got is not None and got[0].ndim == 1 and got[1] == spec.SAMPLE_RATE:
         return np.ascontiguousarray(got[0])
-    return load_mono_22050(path)
+    return load_mono_22050(path, engine)
 
 
 class Journal:
@@ -276,7 +281,8 @@ def main(argv=None) -> int:
     t0 = time.perf_counter()
     t_init = t0 - t_init
     stats: dict = {}
-    rows = detect_corpus(files, eng.detect_host_batch, load=load_native_22050, durations=durations, device=device,
+    rows = detect_corpus(files, eng.detect_host_batch, load=lambda path: load_native_22050(path, eng),
+                         durations=durations, device=device,
                          group_size=max(1, args.group_size), stats=stats, journal=(args.out_csv + ".journal") if args.resume else None)
     if rows is not None:
         with open(args.out_csv, "w", newline="") as f:

@@ -432,6 +432,29 @@ int ss_features(ss_ctx* ctx, const float* pcm_dev, int64_t n_padded, const int64
                          static_cast<cudaStream_t>(stream));
 }
 
+static int resample_impl(ss_ctx* ctx, const void* pcm_dev, int fmt, int64_t n_in, float* out_dev, int64_t n_out, int up,
+                         int down, int taps_half, const float* table_dev, void* stream) {
+  int rc = check_ctx(ctx);
+  if (rc) return rc;
+  SS_REQUIRE(n_in >= 0 && n_out >= 0 && up >= 1 && down >= 1, SS_E_ARG, "bad ss_resample arguments");
+  SS_REQUIRE(n_out == (n_in * up + down - 1) / down, SS_E_ARG, "n_out %lld != ceil(n_in * %d / %d) = %lld",
+             (long long)n_out, up, down, (long long)((n_in * up + down - 1) / down));
+  if (n_out == 0) return SS_OK;
+  SS_REQUIRE(pcm_dev && out_dev && table_dev, SS_E_ARG, "null device pointer");
+  return launch_resample(pcm_dev, fmt, n_in, out_dev, n_out, up, down, taps_half, table_dev,
+                         static_cast<cudaStream_t>(stream));
+}
+
+int ss_resample(ss_ctx* ctx, const float* pcm_dev, int64_t n_in, float* out_dev, int64_t n_out, int up, int down,
+                int taps_half, const float* table_dev, void* stream) {
+  return resample_impl(ctx, pcm_dev, kSampleF32, n_in, out_dev, n_out, up, down, taps_half, table_dev, stream);
+}
+
+int ss_resample_pcm16(ss_ctx* ctx, const int16_t* pcm_dev, int64_t n_in, float* out_dev, int64_t n_out, int up, int down,
+                      int taps_half, const float* table_dev, void* stream) {
+  return resample_impl(ctx, pcm_dev, kSampleS16, n_in, out_dev, n_out, up, down, taps_half, table_dev, stream);
+}
+
 int64_t ss_spectrogram_frames(int64_t n_samples) { return n_samples < 0 ? 0 : 1 + n_samples / kHop; }
 
 static int spectrogram_impl(ss_ctx* ctx, const void* pcm_dev, int fmt, int64_t n_samples, float* mag_dev, float* max_dev,

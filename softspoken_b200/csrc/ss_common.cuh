@@ -165,6 +165,9 @@ int launch_features_virtual(const ss_ctx* ctx, const void* pcm, int sample_fmt, 
                             int64_t offset, const int64_t* starts, int64_t w_base, int n_windows, float* mel,
                             cudaStream_t st);
 int launch_pad(const float* src, int64_t n, float* dst, cudaStream_t st);
+// resample.cu (K9): y[m] = sum_j x[mM div L - j] table[j + T][mM mod L], j = -T .. T; sample_fmt as for K1
+int launch_resample(const void* x, int sample_fmt, int64_t n_in, float* y, int64_t n_out, int L, int M, int taps_half,
+                    const float* table, cudaStream_t st);
 // K8 (review-screen spectrogram): magnitudes [257][1 + n / 256]; max_bits (optional) receives the bit pattern of the maximum
 int launch_spectrogram(const ss_ctx* ctx, const void* pcm, int sample_fmt, int64_t n, float* mag, unsigned int* max_bits,
                        cudaStream_t st);

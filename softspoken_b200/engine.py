@@ -28,6 +28,7 @@ class Engine:
         dev = torch.device(device) if not isinstance(device, int) else torch.device("cuda", device)
         self.device = torch.device("cuda", dev.index if dev.index is not None else torch.cuda.current_device())
         self.mode = mode
+        self._resample_tables = {}          # sr_in -> polyphase table on the device (K9)
         self.max_batch = int(max_batch)
         blob = checkpoint.pack_blob(state_dict)
         self._blob = blob
@@ -247,6 +248,23 @@ class Engine:
         self.reserve(max(self._reserved_samples, 0), max(self._region_cap, 1))
         check(lib.ss_silence_pcm16_host(self._ctx, C.c_void_p(pcm.ctypes.data), pcm.size,
                                         C.c_void_p(iv.ctypes.data), iv.shape[0], int(requantize)))
+
+    def resample(self, pcm: torch.Tensor, sr_in: int) -> torch.Tensor:
+        """Mono clip on the device at `sr_in` (float32, or int16 samples of a PCM_16 file) -> float32 at 22,050 Hz,
+        `ceil(n * 22050 / sr_in)` samples (K9; filter of `softspoken_b200.resample.design`).  Not soxr: see there."""
+        from . import resample as rs
+        assert pcm.is_cuda and pcm.dim() == 1 and pcm.is_contiguous() and pcm.dtype in (torch.float32, torch.int16)
+        L, M, T, table = rs.design(int(sr_in))
+        key = int(sr_in)
+        if key not in self._resample_tables:
+            self._resample_tables[key] = torch.from_numpy(table).to(self.device)
+        n = pcm.numel()
+        n_out = rs.out_len(n, sr_in)
+        out = torch.empty(n_out, dtype=torch.float32, device=self.device)
+        fn = lib.ss_resample_pcm16 if pcm.dtype == torch.int16 else lib.ss_resample
+        check(fn(self._ctx, _ptr(pcm) if n else None, n, _ptr(out) if n_out else None, n_out, L, M, T,
+                 _ptr(self._resample_tables[key]), self._stream()))
+        return out
 
     def spectrogram(self, pcm: torch.Tensor, db: bool = False) -> torch.Tensor:
         """Mono clip on the device (float32, or int16 samples of a PCM_16 file) -> `[257, 1 + n // 256]` float32

@@ -52,12 +52,13 @@ class WorkerSignals:
         self.message = Signal(str)
 
 
-def load_audio(path: str):
+def load_audio(path: str, engine=None):
     """`voice_activity.load_audio(path)` (root/code/backend/voice_activity.py:32-69): float32, mono, 22,050 Hz.
 
     Decode -> `(n,)` or `(C, n)`; more than one channel is averaged (`librosa.to_mono`); a decode error
-    prints and returns `(None, None)` like the reference.  Resampling (soxr, absent here) is the "next"
-    row f1 of SURVEY §8 and is refused explicitly rather than approximated."""
+    prints and returns `(None, None)` like the reference.  A file at another rate is resampled on the device
+    (`engine.resample`, K9) — with this package's documented filter, NOT the reference's soxr (absent here), so for
+    such files the detections are not covered by the bit-exactness claims; without an engine it is refused."""
     try:
         data, sr = wavio.read_wav(path)
     except Exception as e:                                     # voice_activity.py:39-41
@@ -66,10 +67,20 @@ def load_audio(path: str):
     if data.ndim > 1:
         data = np.mean(data, axis=0)                           # librosa.to_mono
     if sr != settings.vad_resample:
-        raise NotImplementedError(
-            f"{path}: sample rate {sr} != {settings.vad_resample}; resampling is outside the B200 hot path "
-            "(SURVEY §8 f1) — resample the corpus to 22,050 Hz first")
+        if engine is None:
+            raise NotImplementedError(
+                f"{path}: sample rate {sr} != {settings.vad_resample} and no engine was given to resample it "
+                "(there is no CPU resampler)")
+        data = resample_on_device(np.ascontiguousarray(data, dtype=np.float32), sr, engine)
+        sr = settings.vad_resample                             # the reference returns (data, target rate) too (:66-67)
     return (data, sr)
+
+
+def resample_on_device(data: np.ndarray, sr: int, engine) -> np.ndarray:
+    """Host mono clip at `sr` -> float32 at 22,050 Hz through the K9 kernel."""
+    import torch
+    x = torch.from_numpy(np.ascontiguousarray(data)).to(engine.device)
+    return engine.resample(x, int(sr)).cpu().numpy()
 
 
 class DetectionProject:
@@ -145,7 +156,7 @@ class ProcessWorker:
             if self.stop_requested:
                 break
             self.signals.fileStarted.emit(file)
-            audio_data, original_sr = load_audio(file)
+            audio_data, original_sr = load_audio(file, engine=getattr(getattr(self.detector, 'model', None), 'engine', None))
             if audio_data is None:
                 # the reference crashes here with a TypeError (worker.py:57-60); keep the
                 # exception type but say why

@@ -210,6 +210,46 @@ def run_config1(args):
     eng.close()
 
 
+def run_resample(args):
+    """K9 on a 10-minute clip recorded at 48 kHz and at 44.1 kHz (int16 samples, as a PCM_16 file stores them)."""
+    from oracle import resample as orr               # checker only
+    from softspoken_b200 import resample as rs
+    eng = load_engine(4, "bf16")
+    dev = torch.device("cuda", 0)
+    peak, src = peaks()
+    out = {}
+    for sr in (48000, 44100):
+        n = 600 * sr
+        g = torch.Generator(device=dev).manual_seed(sr)
+        pcm = (torch.randn(n, device=dev, generator=g) * 3000).clamp(-32768, 32767).to(torch.int16)
+        for _ in range(2):
+            y = eng.resample(pcm, sr)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 5
+        e0.record(torch.cuda.current_stream())
+        for _ in range(reps):
+            y = eng.resample(pcm, sr)
+        e1.record(torch.cuda.current_stream())
+        torch.cuda.synchronize()
+        dt = e0.elapsed_time(e1) / reps / 1e3
+        L, M, T, _ = rs.design(sr)
+        want = orr.resample(pcm[:200000].cpu().numpy().astype(np.float32) / np.float32(32768), sr)
+        got = eng.resample(pcm[:200000].contiguous(), sr).cpu().numpy()
+        err = float(np.abs(got[:-2000] - want[:-2000]).max())
+        b = 2 * n + 4 * y.numel()
+        out[str(sr)] = {"ms": dt * 1e3, "taps": 2 * T + 1, "up": L, "down": M, "algorithmic_bytes": b, "GBps": b / dt / 1e9,
+                        "frac": b / dt / 1e9 / peak, "gmacs_per_s": y.numel() * (2 * T + 1) / dt / 1e9,
+                        "audio_hours_per_s": 600.0 / 3600.0 / dt, "max_abs_err_vs_definition": err}
+    line = {"metric": "resample_audio_hours_per_sec", "unit": "audio-hours/s", "n_gpus": 1, "higher_is_better": True,
+            "dtype": "f32", "data": "synthetic", "value": out["48000"]["audio_hours_per_s"],
+            "config": {"workload": "K9: 10-minute mono PCM_16 clip at 48 kHz / 44.1 kHz -> float32 at 22,050 Hz on the device"},
+            "rates": out, "roofline": {"bound": "hbm", "peak": peak, "peak_source": src, "unit": "GB/s",
+                                       "note": "algorithmic bytes = 2 n_in + 4 n_out; at 139-297 taps per output the kernel is bound by FP32 / LSU issue"}}
+    print(json.dumps(line), flush=True)
+    eng.close()
+
+
 def run_postproc(args):
     """K5 / K6 at the size where they stop being launch-bound: the timeline of a 24 h recording (144,005 windows,
     7,373,312 bins).  Logits are synthetic (smooth noise around the threshold so that regions start and end all
@@ -433,7 +473,7 @@ def run_files(args):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("what", choices=["long", "silence", "files", "postproc", "spectrogram", "config1"])
+    ap.add_argument("what", choices=["long", "silence", "files", "postproc", "spectrogram", "config1", "resample"])
     ap.add_argument("--scratch", default="/dev/shm" if os.path.isdir("/dev/shm") else None,
                     help="folder for the wav files of the `files` workload")
     ap.add_argument("--hours", type=float, default=24.0)
@@ -443,7 +483,7 @@ def main():
     ap.add_argument("--pcm16", action="store_true", help="config 4 from the int16 samples of a PCM_16 recording")
     ap.add_argument("--mode", default="f16x3")
     args = ap.parse_args()
-    {"long": run_long, "silence": run_silence, "files": run_files, "postproc": run_postproc, "spectrogram": run_spectrogram, "config1": run_config1}[args.what](args)
+    {"long": run_long, "silence": run_silence, "files": run_files, "postproc": run_postproc, "spectrogram": run_spectrogram, "config1": run_config1, "resample": run_resample}[args.what](args)
 
 
 if __name__ == "__main__":

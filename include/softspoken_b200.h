@@ -107,7 +107,8 @@ SS_API int ss_features(ss_ctx* ctx, const float* pcm_dev, int64_t n_padded, cons
 /* K9 — sample-rate conversion to the detector's rate: stands where load_audio calls
  * librosa.resample (root/code/backend/voice_activity.py:44-66; soxr "HQ" there — NOT restated here: this is a
  * polyphase FIR with a caller-designed table, parity with the reference unpinned for resampled files).
- *   out[m] = sum_{j=-T..T} pcm[(m * down) div up - j] * table[(j + T) * up + (m * down) mod up],  pcm = 0 outside
+ *   out[m] = sum_{j=-T..T} pcm[(m * down) div up - j] * table[(j + T) * up + m mod up],  pcm = 0 outside;
+ *   column q = m mod up of the table holds the filter phase (q * down) mod up (visit order)
  * n_out must be ceil(n_in * up / down) (librosa's output length); table_dev: [2 * taps_half + 1][up] float32
  * (softspoken_b200/resample.py designs it: Kaiser-windowed sinc, unit DC gain per phase).
  * *_pcm16 reads the int16 samples of a PCM_16 file (value / 32768). */

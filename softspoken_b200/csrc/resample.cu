@@ -6,7 +6,8 @@
 // host designs once per input rate; parity with the reference is unpinned for resampled files.
 //
 //   output m  <->  input time m M / L = n0 + p / L      (n0 = m M div L, p = m M mod L)
-//   y[m] = sum_{j = -T .. T} x[n0 - j] * table[j + T][p],        x = 0 outside [0, n_in)
+//   y[m] = sum_{j = -T .. T} x[n0 - j] * table[j + T][m mod L],  x = 0 outside [0, n_in); column q = m mod L of the
+//   table holds phase p = (q M) mod L (visit order: the outputs of a warp read neighbouring columns)
 //
 // One thread per output sample, 256 consecutive outputs per CTA.  The input span of a CTA (256 M / L + 2 T + 2 samples)
 // is staged once in shared memory with the zero padding applied, so the inner loop is one shared-memory load, one
@@ -40,10 +41,10 @@ resample_kernel(const T* __restrict__ x, int64_t n_in, float* __restrict__ y, in
   if (m >= n_out) return;
   const int64_t pos = m * M;
   const int64_t n0 = pos / L;
-  const int p = (int)(pos - n0 * L);
+  const int q = (int)(m % L);      // table column: phase (m M) mod L in visit order, so a warp reads neighbouring columns
   // x[n0 - j] for j = -T .. T  =  xs[(n0 - base) - j]: walk the taps with j ascending, the samples descending
   const float* xp = xs + (int)(n0 - base) + taps_half;          // j = -T
-  const float* tp = table + p;
+  const float* tp = table + q;
   float acc0 = 0.f, acc1 = 0.f;                                  // two chains: the loop is latency-bound otherwise
   const int n_taps = 2 * taps_half + 1;
   int t = 0;

@@ -9,7 +9,8 @@ uses.  Without this step files at 44.1 / 48 kHz (what field recorders write) cou
 
 Definition (everything the kernel `resample_kernel` and the oracle share):
   L / M = 22050 / sr reduced;  output m sits at input time t_m = m M / L = n0 + p / L  (n0 = mM div L, p = mM mod L);
-  y[m] = sum_{j=-T..T} x[n0 - j] g[j][p],   g[j][p] = h(j + p / L),   x = 0 outside the clip;
+  y[m] = sum_{j=-T..T} x[n0 - j] g[j][p],   g[j][p] = h(j + p / L),   x = 0 outside the clip
+  (the device table stores g's columns in visit order: column m mod L holds phase p = (m M) mod L);
   h(t) = 2c sinc(2c t) kaiser(t / T_half; beta),  |t| <= T_half,  c = 0.5 min(1, L / M) ROLLOFF cycles per input sample,
   T_half = ZEROS / (2c),  T = ceil(T_half);  each phase row is normalised to unit DC gain.
 """
@@ -51,7 +52,7 @@ def kernel_value(t: np.ndarray, c: float, t_half: float) -> np.ndarray:
 
 @lru_cache(maxsize=16)
 def design(sr_in: int):
-    """-> (L, M, T, table float32 `[2T+1][L]` with table[j + T][p] = g[j][p])."""
+    """-> (L, M, T, table float32 `[2T+1][L]` with table[j + T][q] = g[j][(q M) mod L], q = m mod L)."""
     if sr_in <= 0:
         raise ValueError(f"sample rate {sr_in}")
     L, M = ratio(sr_in)
@@ -64,4 +65,8 @@ def design(sr_in: int):
     p = np.arange(L, dtype=np.float64)[None, :]
     g = kernel_value(j + p / L, c, t_half)
     g /= g.sum(axis=0, keepdims=True)                 # unit DC gain in every phase
-    return L, M, T, np.ascontiguousarray(g, dtype=np.float32)
+    # Columns in VISIT order: output m uses phase (m M) mod L, which depends on m mod L only, so column q = m mod L
+    # holds phase (q M) mod L and the 32 outputs of a warp read 32 neighbouring columns (one or two cache lines per
+    # tap instead of five with columns in phase order: the kernel was bound by exactly those L1 wavefronts).
+    visit = (np.arange(L, dtype=np.int64) * M) % L
+    return L, M, T, np.ascontiguousarray(g[:, visit], dtype=np.float32)

@@ -1,3 +1,5 @@
+# Lean round-end evidence run on one B200 (gpurun -- bash tools/collect_lean.sh): bench, reference arm, bench launch list,
+# config 4 / 5 and post-processing lines; every program runs plain before any profiler pass.  Outputs: gpurun_out/r95_*.
 TAG=r95
 P=gpurun_out
 BQ="python bench.py --steps 1 --warmup 3 --no-cpu-baseline --no-other-modes"

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define SS_ABI_VERSION 1
+#define SS_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define SS_API __attribute__((visibility("default")))
@@ -86,6 +86,18 @@ SS_API int ss_ctx_device_bytes(ss_ctx* ctx, size_t* bytes);
  * `region_cap` regions per clip.  Grows only; a detect call beyond the reservation fails with
  * SS_E_CAPACITY instead of allocating. */
 SS_API int ss_ctx_reserve(ss_ctx* ctx, int64_t max_samples, int region_cap);
+
+/* Margin-guided refinement of the file-level calls (ss_detect_*).  A detection is the comparison `avg > 0.1`
+ * (NNDetector.py:120) on an average of up to five window logits; the tensor-core classifier's logits carry more
+ * rounding noise than the reference's float32 (operand precisions), so a bin whose average falls inside the
+ * noise band could land on the other side of the threshold.  With eps > 0 every window covering a bin with
+ * |avg - 0.1| < eps is classified again in `refine_mode` (SS_MODE_FP32: the reference's own arithmetic class) and
+ * K5 / K6 run on the patched logits.  The calls then synchronise their stream once per clip (the host needs the
+ * number of marked windows).  eps = 0 switches the refinement off; a call whose `mode` equals refine_mode skips it.
+ * Default: see DESIGN.md.  ss_ctx_refine_stats: {windows classified, windows refined, clips, clips with at least one
+ * refined window} since creation or the last reset. */
+SS_API int ss_ctx_set_refine(ss_ctx* ctx, double eps, int refine_mode);
+SS_API int ss_ctx_refine_stats(ss_ctx* ctx, uint64_t* stats4, int reset);
 
 /* NNDetector.plan_detection_job (NNDetector.py:65-80): number of 3 s windows of a clip of
  * `n_samples` samples at 22,050 Hz once padded (worker.py:58-62); starts are i * 13230. */
@@ -159,7 +171,8 @@ SS_API int ss_silence(ss_ctx* ctx, float* pcm_dev, int64_t n_elems, const ss_int
 
 /* File-level path on device-resident audio: pad -> K1 -> K2/K3 -> K5 -> K6
  * (ProcessWorker.run per-file body, worker.py:57-97).  pcm_dev is the UNPADDED clip.
- * Results stay on the device; regions as in ss_regions.  logits_out_dev may be NULL. */
+ * Results stay on the device; regions as in ss_regions.  logits_out_dev may be NULL.  Enqueues only, except that an
+ * active refinement (ss_ctx_set_refine) synchronises `stream` once inside the call. */
 SS_API int ss_detect_device(ss_ctx* ctx, const float* pcm_dev, int64_t n_samples, int mode,
                      int32_t* regions_dev, int32_t* n_regions_dev, int cap, float* logits_out_dev,
                      void* stream);
@@ -230,6 +243,11 @@ SS_API int ss_silence_host(ss_ctx* ctx, float* pcm_host, int64_t n_elems, const 
  * Also surfaces a tcgen05 pipeline time-out of that call as SS_E_CUDA. */
 SS_API int ss_debug_activation(ss_ctx* ctx, int which, int n_windows, float* out_dev, int* C, int* H, int* W,
                                void* stream);
+
+/* Test instrumentation: every device allocation of the context (activation tensors, scratch, staging) sits between
+ * guard bands holding a byte pattern; this call synchronises the device and counts the guard bytes that no longer
+ * hold it (0 = no kernel wrote outside its buffers).  n_bands (optional) receives the number of bands checked. */
+SS_API int ss_debug_check_guards(ss_ctx* ctx, uint64_t* bad_bytes, int* n_bands);
 
 /* Test instrumentation: choose which tcgen05 conv launch of the next tensor-core ss_classify call (same mode as the last one) records
  * per-CTA role timers (-1: none) and read back the previous capture ([148][8] int64 cycles; NULL to skip). */

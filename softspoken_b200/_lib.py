@@ -16,7 +16,7 @@ SS_E_ARG, SS_E_CUDA, SS_E_BLOB, SS_E_CAPACITY, SS_E_NODEVICE, SS_E_RANGE = -1, -
 MODE_FP32, MODE_BF16, MODE_F16, MODE_F16X3 = 0, 1, 2, 3
 MODES = {"fp32": MODE_FP32, "bf16": MODE_BF16, "f16": MODE_F16, "f16x3": MODE_F16X3}
 DEFAULT_MODE = "f16x3"   # fp32-grade logits on tensor cores: the mode detections are bit-exact in
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 
 class SoftspokenError(RuntimeError):
@@ -50,6 +50,8 @@ _SIGNATURES = {
     "ss_ctx_destroy": (_int, [_p]),
     "ss_ctx_device_bytes": (_int, [_p, C.POINTER(C.c_size_t)]),
     "ss_ctx_reserve": (_int, [_p, _i64, _int]),
+    "ss_ctx_set_refine": (_int, [_p, C.c_double, _int]),
+    "ss_ctx_refine_stats": (_int, [_p, C.POINTER(C.c_uint64), _int]),
     "ss_plan_windows": (_i64, [_i64]),
     "ss_timeline_bins": (_i64, [_i64]),
     "ss_pad": (_int, [_p, _p, _i64, _p, _p]),
@@ -76,6 +78,7 @@ _SIGNATURES = {
     "ss_silence_pcm16_host": (_int, [_p, _p, _i64, _p, _int, _int]),
     "ss_check_health": (_int, [_p, _p]),
     "ss_silence_host": (_int, [_p, _p, _i64, _p, _int]),
+    "ss_debug_check_guards": (_int, [_p, C.POINTER(C.c_uint64), C.POINTER(_int)]),
     "ss_debug_tc_profile": (_int, [_p, _int, _p]),
     "ss_debug_activation": (_int, [_p, _int, _int, _p, C.POINTER(_int), C.POINTER(_int), C.POINTER(_int), _p]),
 }

@@ -184,7 +184,14 @@ def detect_corpus(files: Sequence[str], detect_batch: Callable[[List[np.ndarray]
     if durations is None:
         durations = [wavio.duration_and_rate(f)[0] for f in files]
     jr = Journal(journal, files, rank) if journal else None
-    done = jr.load() if jr else {}
+    # What earlier runs finished must be ONE view shared by all ranks: a rank that read the progress files a moment
+    # later would see lines another rank had just appended, shard a different `todo` list, and files would be
+    # detected twice or not at all.  Rank 0 reads, everybody takes its answer; nobody appends before that.
+    done = jr.load() if (jr and rank == 0) else {}
+    if jr and world > 1:
+        box = [done]
+        dist.broadcast_object_list(box, src=0, device=device)
+        done = box[0]
     todo = [i for i in range(len(files)) if i not in done]
     mine = [todo[k] for k in ssdist.shard_files([durations[i] for i in todo], world)[rank]]
     # triplets of earlier runs enter the gather once, through rank 0

@@ -22,6 +22,31 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+void register_guard(ss_ctx* ctx, const void* ptr, size_t bytes, const void* owner) {
+  ctx->guards.push_back(GuardBand{static_cast<const unsigned char*>(ptr), bytes, owner});
+}
+
+void unregister_guards(ss_ctx* ctx, const void* owner) {
+  size_t k = 0;
+  for (size_t i = 0; i < ctx->guards.size(); ++i)
+    if (ctx->guards[i].owner != owner) ctx->guards[k++] = ctx->guards[i];
+  ctx->guards.resize(k);
+}
+
+// one CTA per guard band: count the bytes that no longer hold the pattern
+__global__ void __launch_bounds__(256)
+check_guards_kernel(const GuardBand* __restrict__ bands, unsigned long long* __restrict__ bad) {
+  const GuardBand g = bands[blockIdx.x];
+  const uint32_t want = 0x01010101u * kGuardPattern;
+  unsigned int n = 0;
+  const uint32_t* w = reinterpret_cast<const uint32_t*>(g.ptr);        // bands are 256-byte aligned multiples of 256
+  for (size_t i = threadIdx.x; i < g.bytes / 4; i += blockDim.x) {
+    const uint32_t x = w[i] ^ want;
+    n += ((x & 0xffu) != 0) + ((x & 0xff00u) != 0) + ((x & 0xff0000u) != 0) + ((x & 0xff000000u) != 0);
+  }
+  if (n) atomicAdd(bad, (unsigned long long)n);
+}
+
 namespace {
 
 constexpr uint32_t kBlobMagic = 0x53534232u;   // 'SSB2' (softspoken_b200/checkpoint.py)
@@ -29,6 +54,9 @@ constexpr uint32_t kBlobVersion = 2;
 constexpr int64_t kChunkWindows = 1024;        // windows per streamed chunk in ss_detect_*
 constexpr int kIntervalCap = 1 << 20;
 constexpr int kBatchSlots = 8;                 // clips in flight inside ss_detect_host_batch
+constexpr int kRefineBatch = 128;              // windows per pass of the margin-guided refinement
+constexpr int kRefineFirst = 4096;             // list entries fetched together with the count
+constexpr double kDefaultRefineEps = 0.0;      // off: the first pass is in the reference's own noise class (ss_ctx_set_refine)
 
 struct BlobEntry {
   uint64_t off, count;
@@ -86,11 +114,32 @@ const RbSpec kResBlocks[RB_COUNT] = {
     {"conv_bottleneck", 128, 128}, {"encoder_out", 128, 128}, {"conv6", 256, 96},    {"conv7", 192, 64},
     {"conv8", 128, 32},          {"conv9_1", 64, 32},      {"spec_output_conv.0", 32, 32}};
 
+// Every device allocation of the context sits between two guard bands filled with kGuardPattern; ss_debug_check_guards
+// counts the guard bytes that no longer hold it (compute-sanitizer is not available on the B200 pool, so this is the
+// out-of-bounds-write net of the test suite).
 template <typename T>
 int dev_alloc(ss_ctx* ctx, T** p, size_t count) {
-  SS_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(p), count * sizeof(T)));
-  ctx->device_bytes += count * sizeof(T);
+  const size_t body = (count * sizeof(T) + 255) & ~(size_t)255;
+  unsigned char* base = nullptr;
+  SS_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&base), body + 2 * kCtxGuardBytes));
+  SS_CUDA_CHECK(cudaMemset(base, kGuardPattern, kCtxGuardBytes));
+  SS_CUDA_CHECK(cudaMemset(base + kCtxGuardBytes + body, kGuardPattern, kCtxGuardBytes));
+  *p = reinterpret_cast<T*>(base + kCtxGuardBytes);
+  ctx->allocs[*p] = base;
+  register_guard(ctx, base, kCtxGuardBytes, base);
+  register_guard(ctx, base + kCtxGuardBytes + body, kCtxGuardBytes, base);
+  ctx->device_bytes += body + 2 * kCtxGuardBytes;
   return SS_OK;
+}
+
+void dev_free(ss_ctx* ctx, const void* p) {
+  if (!p) return;
+  auto it = ctx->allocs.find(p);
+  if (it == ctx->allocs.end()) return;
+  unsigned char* base = static_cast<unsigned char*>(it->second);
+  ctx->allocs.erase(it);
+  unregister_guards(ctx, base);
+  cudaFree(base);
 }
 
 int upload_tables(ss_ctx* ctx, const BlobView& v) {
@@ -195,6 +244,123 @@ int run_windows(ss_ctx* ctx, const void* pcm, int fmt, int64_t valid_begin, int6
   return SS_OK;
 }
 
+// Where the samples of the clip in flight can be read back from while its flagged windows are refined.
+struct ClipSource {
+  const void* base;        // element 0 = unpadded sample `first`
+  int64_t first, last;     // unpadded samples [first, last) are present at `base`
+  cudaMemcpyKind kind;     // cudaMemcpyDeviceToDevice (resident clip, staging buffer) or cudaMemcpyHostToDevice
+  int fmt;                 // kSampleF32 / kSampleS16
+};
+
+int classify_any(ss_ctx* ctx, int mode, const float* mel, int n, float* logits, cudaStream_t st) {
+  if (mode == SS_MODE_FP32) return classify_fp32(ctx, mel, n, logits, nullptr, st);
+  return classify_tc(ctx, mode, mel, n, logits, nullptr, st);
+}
+
+bool refine_active(const ss_ctx* ctx, int mode) {
+  return ctx->refine_eps > 0.0 && mode != ctx->refine_mode && ctx->win_flags != nullptr;
+}
+
+// (Re)size the refinement scratch to the file reservation.  Called from ss_ctx_reserve / ss_ctx_set_refine only.
+int reserve_refine(ss_ctx* ctx) {
+  if (!(ctx->refine_eps > 0.0) || !ctx->file_logits) return SS_OK;
+  int rc;
+  const int64_t W = ctx->file_cap_windows > 0 ? ctx->file_cap_windows : 1;
+  if (ctx->refine_cap_windows < W) {
+    SS_CUDA_CHECK(cudaDeviceSynchronize());
+    if (ctx->win_flags) dev_free(ctx, ctx->win_flags);
+    if (ctx->refine_list) dev_free(ctx, ctx->refine_list);
+    if (ctx->refine_host) cudaFreeHost(ctx->refine_host);
+    ctx->win_flags = nullptr; ctx->refine_list = nullptr; ctx->refine_host = nullptr;
+    if ((rc = dev_alloc(ctx, &ctx->win_flags, (size_t)W))) return rc;
+    if ((rc = dev_alloc(ctx, &ctx->refine_list, (size_t)W + 1))) return rc;
+    SS_CUDA_CHECK(cudaMallocHost(reinterpret_cast<void**>(&ctx->refine_host), ((size_t)W + 1) * sizeof(int32_t)));
+    ctx->refine_cap_windows = W;
+  }
+  if (!ctx->refine_raw) {
+    float* raw = nullptr;
+    if ((rc = dev_alloc(ctx, &raw, (size_t)kRefineBatch * kWindowSamplesUsed))) return rc;
+    ctx->refine_raw = raw;
+    if ((rc = dev_alloc(ctx, &ctx->refine_starts, (size_t)kRefineBatch))) return rc;
+    if ((rc = dev_alloc(ctx, &ctx->refine_logits, (size_t)kRefineBatch * kFrames))) return rc;
+    int64_t starts[kRefineBatch];
+    for (int k = 0; k < kRefineBatch; ++k) starts[k] = (int64_t)k * kWindowSamplesUsed;
+    SS_CUDA_CHECK(cudaMemcpy(ctx->refine_starts, starts, sizeof(starts), cudaMemcpyHostToDevice));
+  }
+  if (ctx->refine_mode == SS_MODE_FP32 && (rc = ensure_workspace_f32(ctx))) return rc;
+  return SS_OK;
+}
+
+// K5 (+ refinement) + K6 of one clip whose first-pass logits are in ctx->file_logits.
+//
+// Margin-guided refinement.  The tensor-core classifier's logits carry ~1e-5 of rounding noise (operand
+// precisions), the reference's own float32 a few 1e-6, and a detection is a comparison `avg > 0.1`: a bin whose
+// average lies inside the noise band can land on the other side of the threshold.  K5 therefore marks the (at most
+// five) windows covering every bin with |avg - 0.1| < refine_eps; the marked windows are gathered (their 65,536
+// samples each, from wherever the clip still is), run through K1 and the classifier again in refine_mode and
+// scattered over their first-pass logits; K5 runs once more and K6 sees only the refined decisions.  Costs one
+// stream synchronisation per clip (the host needs the count) plus the second pass over the marked windows.
+int finish_clip(ss_ctx* ctx, const ClipSource& src, int64_t n_samples, int64_t W, int mode, int32_t* regions_dev,
+                int32_t* nreg_dev, int cap, cudaStream_t st) {
+  const int64_t bins = timeline_bins(n_samples + 2 * (int64_t)kPadSamples);
+  ctx->stat_windows += (uint64_t)W;
+  ctx->stat_clips += 1;
+  if (!refine_active(ctx, mode) || W <= 0)
+    return launch_average_regions(ctx->file_logits, (int)W, bins, ctx->file_avg, ctx->file_cnt, 0.1, kGapBins, regions_dev,
+                                  nreg_dev, cap, ctx->scan_tmp, ctx->scan_tmp_len, st);
+  SS_REQUIRE(W <= ctx->refine_cap_windows, SS_E_CAPACITY, "refinement scratch holds %lld windows, clip has %lld",
+             (long long)ctx->refine_cap_windows, (long long)W);
+  int rc;
+  SS_CUDA_CHECK(cudaMemsetAsync(ctx->win_flags, 0, (size_t)W, st));
+  if ((rc = launch_average_bits(ctx->file_logits, (int)W, bins, ctx->file_avg, ctx->file_cnt, 0.1, ctx->scan_tmp,
+                                ctx->scan_tmp_len, ctx->refine_eps, ctx->win_flags, st))) return rc;
+  if ((rc = launch_compact_flags(ctx->win_flags, (int)W, ctx->refine_list + 1, ctx->refine_list, st))) return rc;
+  const int64_t first = W < kRefineFirst ? W : kRefineFirst;
+  SS_CUDA_CHECK(cudaMemcpyAsync(ctx->refine_host, ctx->refine_list, (size_t)(1 + first) * sizeof(int32_t),
+                                cudaMemcpyDeviceToHost, st));
+  SS_CUDA_CHECK(cudaStreamSynchronize(st));
+  const int64_t n_ref = ctx->refine_host[0];
+  if (n_ref > first) {
+    SS_CUDA_CHECK(cudaMemcpyAsync(ctx->refine_host + 1 + first, ctx->refine_list + 1 + first,
+                                  (size_t)(n_ref - first) * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    SS_CUDA_CHECK(cudaStreamSynchronize(st));
+  }
+  if (n_ref > 0) {
+    ctx->stat_refined += (uint64_t)n_ref;
+    ctx->stat_clips_refined += 1;
+    const size_t esz = (src.fmt == kSampleS16) ? sizeof(int16_t) : sizeof(float);
+    char* raw = static_cast<char*>(ctx->refine_raw);
+    for (int64_t k0 = 0; k0 < n_ref; k0 += kRefineBatch) {
+      const int nb = (int)((n_ref - k0 < kRefineBatch) ? (n_ref - k0) : kRefineBatch);
+      for (int k = 0; k < nb; ++k) {
+        // window w = padded samples [w * 13230, + 65536) = unpadded [a, a + 65536), zero outside the clip
+        const int64_t w = ctx->refine_host[1 + k0 + k];
+        const int64_t a = w * kStepSamples - kPadSamples;
+        const int64_t lo = a < 0 ? 0 : a;
+        const int64_t hi = (a + kWindowSamplesUsed < n_samples) ? a + kWindowSamplesUsed : n_samples;
+        char* slot = raw + (size_t)k * kWindowSamplesUsed * esz;
+        if (lo > a || hi < a + kWindowSamplesUsed)
+          SS_CUDA_CHECK(cudaMemsetAsync(slot, 0, (size_t)kWindowSamplesUsed * esz, st));
+        if (hi > lo) {
+          SS_REQUIRE(lo >= src.first && hi <= src.last, SS_E_ARG,
+                     "refinement: window %lld needs samples [%lld, %lld), the source holds [%lld, %lld)", (long long)w,
+                     (long long)lo, (long long)hi, (long long)src.first, (long long)src.last);
+          SS_CUDA_CHECK(cudaMemcpyAsync(slot + (size_t)(lo - a) * esz,
+                                        static_cast<const char*>(src.base) + (size_t)(lo - src.first) * esz,
+                                        (size_t)(hi - lo) * esz, src.kind, st));
+        }
+      }
+      if ((rc = launch_features_virtual(ctx, ctx->refine_raw, src.fmt, 0, (int64_t)nb * kWindowSamplesUsed, 0,
+                                        ctx->refine_starts, 0, nb, ctx->file_mel, st))) return rc;
+      if ((rc = classify_any(ctx, ctx->refine_mode, ctx->file_mel, nb, ctx->refine_logits, st))) return rc;
+      if ((rc = launch_scatter_rows(ctx->refine_logits, ctx->refine_list + 1 + k0, nb, ctx->file_logits, st))) return rc;
+    }
+    if ((rc = launch_average_bits(ctx->file_logits, (int)W, bins, ctx->file_avg, ctx->file_cnt, 0.1, ctx->scan_tmp,
+                                  ctx->scan_tmp_len, 0.0, nullptr, st))) return rc;
+  }
+  return launch_regions_after_bits(bins, kGapBins, regions_dev, nreg_dev, cap, ctx->scan_tmp, ctx->scan_tmp_len, st);
+}
+
 }  // namespace
 
 int check_ctx_public(ss_ctx* ctx) { return check_ctx(ctx); }
@@ -262,6 +428,8 @@ int ss_ctx_create(int device, const void* blob, size_t blob_bytes, int max_batch
   ctx->device = device;
   ctx->max_batch = max_batch_windows;
   ctx->chunk_windows = kChunkWindows;
+  ctx->refine_eps = kDefaultRefineEps;
+  ctx->refine_mode = SS_MODE_FP32;
 #define FAIL_IF(e) do { if ((rc = (e))) { ss_ctx_destroy(ctx); return rc; } } while (0)
   FAIL_IF(dev_alloc(ctx, &ctx->blob_dev, v.payload_floats));
   {
@@ -345,15 +513,21 @@ int ss_ctx_destroy(ss_ctx* ctx) {
   float* bufs[] = {ctx->blob_dev, const_cast<float*>(ctx->fe.tw_a_re), w.conv1, w.pool1, w.conv2, w.pool2, w.conv3,
                    w.pool3, w.conv4, w.pool4, w.bott, w.enc, w.conv6, w.conv7, w.conv8, w.conv9, w.spec, w.tmp_t,
                    w.tmp_r, ctx->file_mel, ctx->file_logits, ctx->stage_buf[0], ctx->stage_buf[1]};
-  for (float* p : bufs) if (p) cudaFree(p);
-  if (ctx->file_avg) cudaFree(ctx->file_avg);
-  if (ctx->file_cnt) cudaFree(ctx->file_cnt);
-  if (ctx->file_regions) cudaFree(ctx->file_regions);
-  if (ctx->file_nreg) cudaFree(ctx->file_nreg);
-  if (ctx->slot_nreg) cudaFree(ctx->slot_nreg);
+  for (float* p : bufs) if (p) dev_free(ctx, p);
+  if (ctx->file_avg) dev_free(ctx, ctx->file_avg);
+  if (ctx->file_cnt) dev_free(ctx, ctx->file_cnt);
+  if (ctx->file_regions) dev_free(ctx, ctx->file_regions);
+  if (ctx->file_nreg) dev_free(ctx, ctx->file_nreg);
+  if (ctx->slot_nreg) dev_free(ctx, ctx->slot_nreg);
   if (ctx->slot_host) cudaFreeHost(ctx->slot_host);
-  if (ctx->scan_tmp) cudaFree(ctx->scan_tmp);
-  if (ctx->intervals) cudaFree(ctx->intervals);
+  if (ctx->scan_tmp) dev_free(ctx, ctx->scan_tmp);
+  if (ctx->intervals) dev_free(ctx, ctx->intervals);
+  if (ctx->win_flags) dev_free(ctx, ctx->win_flags);
+  if (ctx->refine_list) dev_free(ctx, ctx->refine_list);
+  if (ctx->refine_host) cudaFreeHost(ctx->refine_host);
+  if (ctx->refine_raw) dev_free(ctx, ctx->refine_raw);
+  if (ctx->refine_starts) dev_free(ctx, ctx->refine_starts);
+  if (ctx->refine_logits) dev_free(ctx, ctx->refine_logits);
   for (int i = 0; i < 2; ++i) {
     if (ctx->ev_copied[i]) cudaEventDestroy(ctx->ev_copied[i]);
     if (ctx->ev_consumed[i]) cudaEventDestroy(ctx->ev_consumed[i]);
@@ -388,7 +562,7 @@ int ss_ctx_reserve(ss_ctx* ctx, int64_t max_samples, int region_cap) {
     SS_CUDA_CHECK(cudaDeviceSynchronize());
     const int64_t W = plan_windows(max_samples);
     const int64_t bins = timeline_bins(max_samples + 2 * (int64_t)kPadSamples) + 1;
-    if (ctx->file_logits) { cudaFree(ctx->file_logits); cudaFree(ctx->file_avg); cudaFree(ctx->file_cnt); cudaFree(ctx->scan_tmp); }
+    if (ctx->file_logits) { dev_free(ctx, ctx->file_logits); dev_free(ctx, ctx->file_avg); dev_free(ctx, ctx->file_cnt); dev_free(ctx, ctx->scan_tmp); }
     ctx->file_logits = nullptr; ctx->file_avg = nullptr; ctx->file_cnt = nullptr; ctx->scan_tmp = nullptr;
     if ((rc = dev_alloc(ctx, &ctx->file_logits, (size_t)(W > 0 ? W : 1) * kFrames))) return rc;
     if ((rc = dev_alloc(ctx, &ctx->file_avg, (size_t)bins))) return rc;
@@ -400,8 +574,8 @@ int ss_ctx_reserve(ss_ctx* ctx, int64_t max_samples, int region_cap) {
   }
   if (region_cap > ctx->file_region_cap) {
     SS_CUDA_CHECK(cudaDeviceSynchronize());
-    if (ctx->file_regions) cudaFree(ctx->file_regions);
-    if (ctx->slot_nreg) cudaFree(ctx->slot_nreg);
+    if (ctx->file_regions) dev_free(ctx, ctx->file_regions);
+    if (ctx->slot_nreg) dev_free(ctx, ctx->slot_nreg);
     if (ctx->slot_host) cudaFreeHost(ctx->slot_host);
     ctx->file_regions = nullptr; ctx->slot_nreg = nullptr; ctx->slot_host = nullptr;
     // kBatchSlots region buffers (slot 0 doubles as the single-clip buffer) + counters + a pinned host mirror
@@ -411,6 +585,23 @@ int ss_ctx_reserve(ss_ctx* ctx, int64_t max_samples, int region_cap) {
                                  (size_t)kBatchSlots * ((size_t)region_cap * 2 + 1) * sizeof(int32_t)));
     ctx->file_region_cap = region_cap;
   }
+  return reserve_refine(ctx);
+}
+
+int ss_ctx_set_refine(ss_ctx* ctx, double eps, int refine_mode) {
+  int rc = check_ctx(ctx);
+  if (rc) return rc;
+  SS_REQUIRE(eps >= 0.0 && eps < 0.1, SS_E_ARG, "refinement margin %g out of [0, 0.1)", eps);
+  SS_REQUIRE(valid_mode(refine_mode), SS_E_ARG, "unknown classifier mode %d", refine_mode);
+  ctx->refine_eps = eps;
+  ctx->refine_mode = refine_mode;
+  return reserve_refine(ctx);
+}
+
+int ss_ctx_refine_stats(ss_ctx* ctx, uint64_t* stats4, int reset) {
+  SS_REQUIRE(ctx && stats4, SS_E_ARG, "null argument");
+  stats4[0] = ctx->stat_windows; stats4[1] = ctx->stat_refined; stats4[2] = ctx->stat_clips; stats4[3] = ctx->stat_clips_refined;
+  if (reset) ctx->stat_windows = ctx->stat_refined = ctx->stat_clips = ctx->stat_clips_refined = 0;
   return SS_OK;
 }
 
@@ -535,13 +726,6 @@ int ss_silence(ss_ctx* ctx, float* pcm_dev, int64_t n_elems, const ss_interval* 
   return launch_silence(pcm_dev, n_elems, 0, intervals_dev, n_intervals, static_cast<cudaStream_t>(stream));
 }
 
-static int detect_tail(ss_ctx* ctx, int64_t n_samples, int64_t W, int32_t* regions_dev, int32_t* n_regions_dev,
-                       int cap, cudaStream_t st) {
-  const int64_t bins = timeline_bins(n_samples + 2 * (int64_t)kPadSamples);
-  return launch_average_regions(ctx->file_logits, (int)W, bins, ctx->file_avg, ctx->file_cnt, 0.1, kGapBins, regions_dev,
-                                n_regions_dev, cap, ctx->scan_tmp, ctx->scan_tmp_len, st);
-}
-
 static int detect_device_impl(ss_ctx* ctx, const void* pcm_dev, int fmt, int64_t n_samples, int mode,
                               int32_t* regions_dev, int32_t* n_regions_dev, int cap, float* logits_out_dev,
                               void* stream) {
@@ -559,7 +743,8 @@ static int detect_device_impl(ss_ctx* ctx, const void* pcm_dev, int fmt, int64_t
   rc = run_windows(ctx, pcm_dev, fmt, kPadSamples, kPadSamples + n_samples, kPadSamples, 0, W, mode, ctx->file_logits,
                    st);
   if (rc) return rc;
-  rc = detect_tail(ctx, n_samples, W, regions_dev, n_regions_dev, cap, st);
+  const ClipSource src{pcm_dev, 0, n_samples, cudaMemcpyDeviceToDevice, fmt};
+  rc = finish_clip(ctx, src, n_samples, W, mode, regions_dev, n_regions_dev, cap, st);
   if (rc) return rc;
   if (logits_out_dev && W > 0)
     SS_CUDA_CHECK(cudaMemcpyAsync(logits_out_dev, ctx->file_logits, (size_t)W * kFrames * sizeof(float),
@@ -579,36 +764,83 @@ int ss_detect_device_pcm16(ss_ctx* ctx, const int16_t* pcm_dev, int64_t n_sample
                             stream);
 }
 
-// Enqueue one host clip: chunked H2D on the copy stream (double-buffered staging), K1-K3 per chunk and K5/K6 on the
-// compute stream, regions left in `regions_dev` / `nreg_dev`.  Does not synchronise.
-static int enqueue_detect_host(ss_ctx* ctx, const void* pcm_host, int fmt, int64_t n_samples, int mode,
-                               int32_t* regions_dev, int32_t* nreg_dev, int cap) {
+// One streamed chunk of a host clip: windows [w0, w1) need the unpadded samples [s0, s1), staged in stage_buf[buf].
+struct Chunk {
+  int64_t w0 = 0, w1 = 0, s0 = 0, s1 = 0;
+  int buf = 0;
+  bool valid = false;
+};
+
+static Chunk plan_chunk(const ss_ctx* ctx, int64_t n_samples, int64_t W, int64_t w0) {
+  Chunk c;
+  c.w0 = w0;
+  c.w1 = (w0 + ctx->chunk_windows < W) ? w0 + ctx->chunk_windows : W;
+  // padded sample range the chunk's kept frames touch: [w0*step - 256 (reflection stays >= w0*step), ...)
+  const int64_t plo = c.w0 * kStepSamples, phi = (c.w1 - 1) * kStepSamples + kWindowSamplesUsed;
+  c.s0 = plo - kPadSamples;       // unpadded coordinates
+  c.s1 = phi - kPadSamples;
+  if (c.s0 < 0) c.s0 = 0;
+  if (c.s1 > n_samples) c.s1 = n_samples;
+  if (c.s1 < c.s0) c.s1 = c.s0;
+  return c;
+}
+
+// H2D of a chunk on the copy stream into the next staging buffer (waits until that buffer's last reader is done).
+static int upload_chunk(ss_ctx* ctx, const void* pcm_host, int fmt, Chunk* c) {
   const size_t esz = (fmt == kSampleS16) ? sizeof(int16_t) : sizeof(float);   // the staging buffers hold either type
-  cudaStream_t cs = ctx->compute_stream, xs = ctx->copy_stream;
+  cudaStream_t xs = ctx->copy_stream;
+  c->buf = ctx->stage_next;
+  ctx->stage_next ^= 1;
+  SS_CUDA_CHECK(cudaStreamWaitEvent(xs, ctx->ev_consumed[c->buf], 0));   // staging buffer free again
+  if (c->s1 > c->s0)
+    SS_CUDA_CHECK(cudaMemcpyAsync(ctx->stage_buf[c->buf], static_cast<const char*>(pcm_host) + (size_t)c->s0 * esz,
+                                  (size_t)(c->s1 - c->s0) * esz, cudaMemcpyHostToDevice, xs));
+  SS_CUDA_CHECK(cudaEventRecord(ctx->ev_copied[c->buf], xs));
+  c->valid = true;
+  return SS_OK;
+}
+
+// One host clip: chunked H2D on the copy stream (double-buffered staging), K1-K3 per chunk, then K5 (+ refinement)
+// and K6 on the compute stream, regions left in `regions_dev` / `nreg_dev`.  `pre`: the clip's first chunk if a
+// previous call already uploaded it.  `next_pcm`: the clip that follows (or null) — its first chunk is uploaded
+// before this clip's K5 synchronises the host, so that the copy engine keeps working; returned in `next_pre`.
+static int detect_host_clip(ss_ctx* ctx, const void* pcm_host, int fmt, int64_t n_samples, int mode,
+                            int32_t* regions_dev, int32_t* nreg_dev, int cap, const Chunk* pre,
+                            const void* next_pcm, int64_t next_n, Chunk* next_pre) {
+  cudaStream_t cs = ctx->compute_stream;
   const int64_t W = plan_windows(n_samples);
   int rc;
+  Chunk cur;
   for (int64_t w0 = 0; w0 < W; w0 += ctx->chunk_windows) {
-    const int buf = ctx->stage_next;
-    ctx->stage_next ^= 1;
-    const int64_t w1 = (w0 + ctx->chunk_windows < W) ? w0 + ctx->chunk_windows : W;
-    // padded sample range the chunk's kept frames touch: [w0*step - 256 (reflection stays >= w0*step), ...)
-    const int64_t plo = w0 * kStepSamples, phi = (w1 - 1) * kStepSamples + kWindowSamplesUsed;
-    int64_t s0 = plo - kPadSamples, s1 = phi - kPadSamples;     // unpadded coordinates
-    if (s0 < 0) s0 = 0;
-    if (s1 > n_samples) s1 = n_samples;
-    if (s1 < s0) s1 = s0;
-    SS_CUDA_CHECK(cudaStreamWaitEvent(xs, ctx->ev_consumed[buf], 0));   // staging buffer free again
-    if (s1 > s0)
-      SS_CUDA_CHECK(cudaMemcpyAsync(ctx->stage_buf[buf], static_cast<const char*>(pcm_host) + (size_t)s0 * esz,
-                                    (size_t)(s1 - s0) * esz, cudaMemcpyHostToDevice, xs));
-    SS_CUDA_CHECK(cudaEventRecord(ctx->ev_copied[buf], xs));
-    SS_CUDA_CHECK(cudaStreamWaitEvent(cs, ctx->ev_copied[buf], 0));
-    rc = run_windows(ctx, ctx->stage_buf[buf], fmt, kPadSamples + s0, kPadSamples + s1, kPadSamples + s0, w0, w1, mode,
-                     ctx->file_logits, cs);
+    if (w0 == 0 && pre && pre->valid) {
+      cur = *pre;
+    } else {
+      cur = plan_chunk(ctx, n_samples, W, w0);
+      if ((rc = upload_chunk(ctx, pcm_host, fmt, &cur))) return rc;
+    }
+    SS_CUDA_CHECK(cudaStreamWaitEvent(cs, ctx->ev_copied[cur.buf], 0));
+    rc = run_windows(ctx, ctx->stage_buf[cur.buf], fmt, kPadSamples + cur.s0, kPadSamples + cur.s1, kPadSamples + cur.s0,
+                     cur.w0, cur.w1, mode, ctx->file_logits, cs);
     if (rc) return rc;
-    SS_CUDA_CHECK(cudaEventRecord(ctx->ev_consumed[buf], cs));
+    SS_CUDA_CHECK(cudaEventRecord(ctx->ev_consumed[cur.buf], cs));
   }
-  return detect_tail(ctx, n_samples, W, regions_dev, nreg_dev, cap, cs);
+  if (next_pre) {
+    *next_pre = Chunk{};
+    const int64_t Wn = next_pcm ? plan_windows(next_n) : 0;
+    if (Wn > 0) {
+      *next_pre = plan_chunk(ctx, next_n, Wn, 0);
+      if ((rc = upload_chunk(ctx, next_pcm, fmt, next_pre))) return rc;
+    }
+  }
+  // the flagged windows' samples: a clip of one chunk is still whole in its staging buffer, a longer one is read
+  // back from the host buffer
+  ClipSource src{pcm_host, 0, n_samples, cudaMemcpyHostToDevice, fmt};
+  const bool staged = W > 0 && W <= ctx->chunk_windows;
+  if (staged) src = ClipSource{ctx->stage_buf[cur.buf], cur.s0, cur.s1, cudaMemcpyDeviceToDevice, fmt};
+  rc = finish_clip(ctx, src, n_samples, W, mode, regions_dev, nreg_dev, cap, cs);
+  if (rc) return rc;
+  if (staged) SS_CUDA_CHECK(cudaEventRecord(ctx->ev_consumed[cur.buf], cs));   // the refinement read the buffer again
+  return SS_OK;
 }
 
 static int check_tc_health(ss_ctx* ctx, int mode, cudaStream_t cs) {
@@ -636,7 +868,8 @@ static int detect_host_impl(ss_ctx* ctx, const void* pcm_host, int fmt, int64_t 
   SS_REQUIRE(valid_mode(mode), SS_E_ARG, "unknown classifier mode %d", mode);
   cudaStream_t cs = ctx->compute_stream;
   const int64_t W = plan_windows(n_samples);
-  rc = enqueue_detect_host(ctx, pcm_host, fmt, n_samples, mode, ctx->file_regions, ctx->file_nreg, cap);
+  rc = detect_host_clip(ctx, pcm_host, fmt, n_samples, mode, ctx->file_regions, ctx->file_nreg, cap, nullptr, nullptr, 0,
+                        nullptr);
   if (rc) return rc;
   int32_t nreg = 0;
   SS_CUDA_CHECK(cudaMemcpyAsync(&nreg, ctx->file_nreg, sizeof(int32_t), cudaMemcpyDeviceToHost, cs));
@@ -680,14 +913,18 @@ static int detect_host_batch_impl(ss_ctx* ctx, int n_clips, const void* const* p
   }
   cudaStream_t cs = ctx->compute_stream;
   const size_t slot_ints = (size_t)ctx->file_region_cap * 2;
+  Chunk pre;          // first chunk of the next clip, uploaded ahead
   for (int g0 = 0; g0 < n_clips; g0 += kBatchSlots) {
     const int g1 = (g0 + kBatchSlots < n_clips) ? g0 + kBatchSlots : n_clips;
-    // enqueue the whole group: clip k+1's upload overlaps clip k's compute; results land in pinned host slots
+    // clip k+1's upload overlaps clip k's compute (its first chunk is enqueued before clip k's K5 synchronises the
+    // host for the refinement count); results land in pinned host slots and are harvested once per group
     for (int i = g0; i < g1; ++i) {
       const int slot = i - g0;
       int32_t* reg_dev = ctx->file_regions + (size_t)slot * slot_ints;
       int32_t* host_slot = ctx->slot_host + (size_t)slot * (slot_ints + 1);
-      rc = enqueue_detect_host(ctx, pcm_host[i], fmt, n_samples[i], mode, reg_dev, ctx->slot_nreg + slot, cap);
+      const Chunk mine = pre;
+      rc = detect_host_clip(ctx, pcm_host[i], fmt, n_samples[i], mode, reg_dev, ctx->slot_nreg + slot, cap, &mine,
+                            i + 1 < n_clips ? pcm_host[i + 1] : nullptr, i + 1 < n_clips ? n_samples[i + 1] : 0, &pre);
       if (rc) return rc;
       SS_CUDA_CHECK(cudaMemcpyAsync(host_slot, ctx->slot_nreg + slot, sizeof(int32_t), cudaMemcpyDeviceToHost, cs));
       if (cap > 0)
@@ -814,6 +1051,29 @@ extern "C" int ss_debug_activation(ss_ctx* ctx, int which, int n_windows, float*
   if (rc) return rc;
   SS_REQUIRE(C && H && W && n_windows >= 0, SS_E_ARG, "bad ss_debug_activation arguments");
   return ss::tc_debug_dump(ctx, which, n_windows, out_dev, C, H, W, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int ss_debug_check_guards(ss_ctx* ctx, uint64_t* bad_bytes, int* n_bands) {
+  int rc = ss::check_ctx_public(ctx);
+  if (rc) return rc;
+  SS_REQUIRE(bad_bytes, SS_E_ARG, "null argument");
+  *bad_bytes = 0;
+  if (n_bands) *n_bands = (int)ctx->guards.size();
+  if (ctx->guards.empty()) return SS_OK;
+  SS_CUDA_CHECK(cudaDeviceSynchronize());
+  ss::GuardBand* bands = nullptr;
+  unsigned long long* bad = nullptr;
+  SS_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&bands), ctx->guards.size() * sizeof(ss::GuardBand) + 8));
+  bad = reinterpret_cast<unsigned long long*>(bands + ctx->guards.size());
+  SS_CUDA_CHECK(cudaMemcpy(bands, ctx->guards.data(), ctx->guards.size() * sizeof(ss::GuardBand), cudaMemcpyHostToDevice));
+  SS_CUDA_CHECK(cudaMemset(bad, 0, 8));
+  ss::check_guards_kernel<<<(int)ctx->guards.size(), 256>>>(bands, bad);
+  unsigned long long h = 0;
+  cudaError_t e = cudaMemcpy(&h, bad, 8, cudaMemcpyDeviceToHost);
+  cudaFree(bands);
+  if (e != cudaSuccess) { ss::set_error("guard check failed: %s", cudaGetErrorString(e)); return SS_E_CUDA; }
+  *bad_bytes = h;
+  return SS_OK;
 }
 
 extern "C" int ss_debug_tc_profile(ss_ctx* ctx, int select_launch, long long* out_host) {

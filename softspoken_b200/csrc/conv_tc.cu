@@ -410,24 +410,34 @@ bool is_split(Prec p) { return p == Prec::F16x3; }
 // Layers whose doubled C_out still fits one MMA cheaply use the dual layout (see conv_tc_kernel.cuh).
 bool is_dual(Prec p, int n) { return is_split(p) && n <= 64; }
 
-int alloc_tensor(TcState* st, Tensor* t, int B, int C, int H, int W) {
+// body: zero (the one-pixel borders are never written afterwards); guard bands before / after: kGuardPattern, a small
+// finite number in either 16-bit format.  The first and last staged runs of a launch read into the bands (halo
+// over-reads); those values only reach accumulators of border positions, which the epilogue forces to zero, or of
+// positions past the tensor, which it does not store.  Nothing may WRITE there: ss_debug_check_guards verifies it.
+int alloc_guarded(ss_ctx* ctx, TcState* st, uint16_t** alloc, uint16_t** data, size_t body) {
+  const size_t bytes = body + 2 * (size_t)kGuardBytes;
+  unsigned char* base = nullptr;
+  SS_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&base), bytes));
+  *alloc = reinterpret_cast<uint16_t*>(base);
+  SS_CUDA_CHECK(cudaMemset(base, kGuardPattern, kGuardBytes));
+  SS_CUDA_CHECK(cudaMemset(base + kGuardBytes, 0, body));
+  SS_CUDA_CHECK(cudaMemset(base + kGuardBytes + body, kGuardPattern, kGuardBytes));
+  *data = reinterpret_cast<uint16_t*>(base + kGuardBytes);
+  register_guard(ctx, base, kGuardBytes, base);
+  register_guard(ctx, base + kGuardBytes + body, kGuardBytes, base);
+  st->bytes += bytes;
+  return SS_OK;
+}
+
+int alloc_tensor(ss_ctx* ctx, TcState* st, Tensor* t, int B, int C, int H, int W) {
   t->planes = C / 8;
   t->H = H;
   t->W = W;
   const size_t body = (size_t)B * t->planes * (H + 2) * (W + 2) * 8 * sizeof(uint16_t);
-  const size_t bytes = body + 2 * (size_t)kGuardBytes;
-  // zero borders + guards: never overwritten with non-zero values afterwards
-  SS_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&t->alloc), bytes));
-  SS_CUDA_CHECK(cudaMemset(t->alloc, 0, bytes));
-  t->data = reinterpret_cast<uint16_t*>(reinterpret_cast<unsigned char*>(t->alloc) + kGuardBytes);
-  st->bytes += bytes;
-  if (is_split(st->prec)) {
-    SS_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&t->alloc_lo), bytes));
-    SS_CUDA_CHECK(cudaMemset(t->alloc_lo, 0, bytes));
-    t->lo = reinterpret_cast<uint16_t*>(reinterpret_cast<unsigned char*>(t->alloc_lo) + kGuardBytes);
-    st->bytes += bytes;
-  }
-  return SS_OK;
+  int rc = alloc_guarded(ctx, st, &t->alloc, &t->data, body);
+  if (rc) return rc;
+  if (is_split(st->prec)) rc = alloc_guarded(ctx, st, &t->alloc_lo, &t->lo, body);
+  return rc;
 }
 
 uint16_t to_bits_bf16(float v) { __nv_bfloat16 h = __float2bfloat16(v); uint16_t b; memcpy(&b, &h, 2); return b; }
@@ -549,6 +559,22 @@ int launch_conv_npg(TcJob job, int B, cudaStream_t st) {
   p.total_units = p.units_per_image * B;
   for (int ph = 0; ph < job.n_phase; ++ph)
     SS_REQUIRE(job.c[ph].relu == 1, SS_E_ARG, "conv_tc_kernel applies ReLU unconditionally");
+  // Split-K sub-accumulation (TcConv::n_sub): the K-chunks of the 3x3 sources are cut into groups so that an MMA
+  // chain covers 9 taps x a few chunks (+ its share of the 1x1 residual chunks) instead of 9 C_in / 16.  Every group
+  // costs a TMEM buffer turn (drain by the epilogue warps, barrier round trip), which the small-resolution layers
+  // (<= 32 x 64: a fifth of the time) hide easily and the full-resolution ones less so: one chunk per group in the
+  // deep layers (SS_TC_SUB_DEEP caps the groups), at most SS_TC_SUB groups in the layers at 64 x 128 and above.
+  static const int sub_big = [] { const char* e = getenv("SS_TC_SUB"); return e ? atoi(e) : 4; }();
+  static const int sub_deep = [] { const char* e = getenv("SS_TC_SUB_DEEP"); return e ? atoi(e) : 16; }();
+  for (int ph = 0; ph < job.n_phase; ++ph) {
+    int most = 1;
+    for (int i = 0; i < job.c[ph].n_src; ++i)
+      if (job.c[ph].src[i].taps == 9 && job.c[ph].src[i].n_chunks > most) most = job.c[ph].src[i].n_chunks;
+    const bool sub_ok = PrecTraits<P>::split && G == 1;
+    int cap = (p.H >= 64) ? sub_big : sub_deep;
+    if (cap < 1) cap = 1;
+    job.c[ph].n_sub = sub_ok ? (most < cap ? most : cap) : 1;
+  }
   const int items = p.total_units * job.n_phase;
   const int grid = items < kNumSMs ? items : kNumSMs;
   if (job.n_phase == 2) {
@@ -735,11 +761,30 @@ int tc_pool_p(const Tensor& in, int plane0, int planes, Tensor& out, int B, cuda
 }
 
 // Built lazily on the first call of a mode, so that nobody pays for a workspace they do not use.
+void tc_free_state(ss_ctx* ctx, TcState* s);
+
+int tc_build_state(ss_ctx* ctx, Prec prec, TcState* s);
+
+// The slot is published only when the whole state exists: a failed build (out of memory is realistic: 18-36 GB of
+// workspace at max_batch 1005) frees what it got and leaves the slot empty, so the next call retries the build
+// instead of launching kernels on a partial state.
 int tc_build(ss_ctx* ctx, Prec prec, TcState** out) {
   const int slot = (int)prec;
   if (ctx->tc[slot]) { *out = static_cast<TcState*>(ctx->tc[slot]); return SS_OK; }
   TcState* s = new TcState();
+  const int rc = tc_build_state(ctx, prec, s);
+  if (rc) {
+    cudaGetLastError();
+    tc_free_state(ctx, s);
+    return rc;
+  }
   ctx->tc[slot] = s;
+  ctx->device_bytes += s->bytes;
+  *out = s;
+  return SS_OK;
+}
+
+int tc_build_state(ss_ctx* ctx, Prec prec, TcState* s) {
   s->prec = prec;
   s->max_batch = ctx->max_batch;
   const int B = ctx->max_batch;
@@ -791,7 +836,7 @@ int tc_build(ss_ctx* ctx, Prec prec, TcState** out) {
   SS_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&s->flags2), (size_t)s->flags_cap * sizeof(int)));
   SS_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&s->prof), kNumSMs * 8 * sizeof(long long)));
   SS_CUDA_CHECK(cudaMemset(s->prof, 0, kNumSMs * 8 * sizeof(long long)));
-#define T(t, C, H, W) do { if ((rc = alloc_tensor(s, &s->t, B, C, H, W))) return rc; } while (0)
+#define T(t, C, H, W) do { if ((rc = alloc_tensor(ctx, s, &s->t, B, C, H, W))) return rc; } while (0)
   T(m4, 64, 128, 256);
   T(p1, 32, 64, 128);
   T(m3, 128, 64, 128);
@@ -815,8 +860,6 @@ int tc_build(ss_ctx* ctx, Prec prec, TcState** out) {
   T(t[RB_CONV9], 32, 128, 256);
   T(t[RB_SPEC], 32, 128, 256);
 #undef T
-  ctx->device_bytes += s->bytes;
-  *out = s;
   return SS_OK;
 }
 
@@ -844,7 +887,7 @@ int classify_tc_p(ss_ctx* ctx, TcState* s, const float* mel, int n_windows, floa
     } else {
       // legacy form (A/B measurements, tests of the im2col'd operand tensor): both convolutions as tcgen05 launches;
       // its operand tensor is allocated on first use
-      if (!s->x0.alloc) SS_TRY(alloc_tensor(s, &s->x0, s->max_batch, 16, 128, 256));
+      if (!s->x0.alloc) SS_TRY(alloc_tensor(ctx, s, &s->x0, s->max_batch, 16, 128, 256));
       mel_to_planar<P><<<(int)((n_pix + 255) / 256), 256, 0, st>>>(mel_b, s->x0.data, s->x0.lo, n_pix);
       SS_CUDA_CHECK(cudaGetLastError());
       count_launch();
@@ -902,27 +945,38 @@ bool prec_of_mode(int mode, Prec* p) {
 
 }  // namespace
 
+namespace {
+void tc_free_state(ss_ctx* ctx, TcState* s) {
+  auto free_guarded = [&](uint16_t* alloc) {
+    if (!alloc) return;
+    unregister_guards(ctx, alloc);
+    cudaFree(alloc);
+  };
+  Tensor* ts[] = {&s->x0, &s->m4, &s->m3, &s->m2, &s->m1, &s->p1, &s->p2, &s->p3, &s->p4, &s->bott, &s->c9, &s->spec};
+  for (Tensor* t : ts) { free_guarded(t->alloc); free_guarded(t->alloc_lo); }
+  for (int i = 0; i < RB_COUNT; ++i) {
+    free_guarded(s->t[i].alloc);
+    free_guarded(s->t[i].alloc_lo);
+    for (PackedConv* pc : {&s->rb[i].c1, &s->rb[i].c2, &s->rb[i].res}) {
+      if (pc->w) cudaFree(pc->w);
+      if (pc->w_hi) cudaFree(pc->w_hi);
+    }
+    if (s->rb[i].bias2) cudaFree(s->rb[i].bias2);
+  }
+  if (s->err) cudaFree(s->err);
+  if (s->flags) cudaFree(s->flags);
+  if (s->flags2) cudaFree(s->flags2);
+  if (s->head_part) cudaFree(s->head_part);
+  if (s->prof) cudaFree(s->prof);
+  delete s;
+}
+}  // namespace
+
 void tc_destroy(ss_ctx* ctx) {
   for (int slot = 0; slot < 3; ++slot) {
     TcState* s = static_cast<TcState*>(ctx->tc[slot]);
     if (!s) continue;
-    Tensor* ts[] = {&s->x0, &s->m4, &s->m3, &s->m2, &s->m1, &s->p1, &s->p2, &s->p3, &s->p4, &s->bott, &s->c9, &s->spec};
-    for (Tensor* t : ts) { if (t->alloc) cudaFree(t->alloc); if (t->alloc_lo) cudaFree(t->alloc_lo); }
-    for (int i = 0; i < RB_COUNT; ++i) {
-      if (s->t[i].alloc) cudaFree(s->t[i].alloc);
-      if (s->t[i].alloc_lo) cudaFree(s->t[i].alloc_lo);
-      for (PackedConv* pc : {&s->rb[i].c1, &s->rb[i].c2, &s->rb[i].res}) {
-        if (pc->w) cudaFree(pc->w);
-        if (pc->w_hi) cudaFree(pc->w_hi);
-      }
-      if (s->rb[i].bias2) cudaFree(s->rb[i].bias2);
-    }
-    if (s->err) cudaFree(s->err);
-    if (s->flags) cudaFree(s->flags);
-    if (s->flags2) cudaFree(s->flags2);
-    if (s->head_part) cudaFree(s->head_part);
-    if (s->prof) cudaFree(s->prof);
-    delete s;
+    tc_free_state(ctx, s);
     ctx->tc[slot] = nullptr;
   }
 }

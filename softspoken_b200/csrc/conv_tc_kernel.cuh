@@ -54,6 +54,10 @@ constexpr uint32_t kSpinLimit = 1u << 22;
 #define SS_TC_DEBUG_HOOKS 0
 #endif
 constexpr bool kDebugHooks = SS_TC_DEBUG_HOOKS != 0;
+// -DSS_TC_SUBACC=0 builds the split-precision kernels without the split-K sub-accumulation path (A/B timing only)
+#ifndef SS_TC_SUBACC
+#define SS_TC_SUBACC 1
+#endif
 
 enum class Prec : int { Bf16 = 0, F16 = 1, F16x3 = 2 };
 
@@ -267,6 +271,15 @@ struct TcConv {
   const float* head_w;   // [128 mel][32][4] float32 or null
   float* head_out;       // [B][128][256][4] float32
   int units_per_image, total_units;
+  // Split-K sub-accumulation (split precision, G = 1).  The tensor core rounds its fp32 accumulator toward zero after
+  // every MMA and aligns the 16 products of an MMA to the accumulator's exponent with only ~2 guard bits: a chain of
+  // n accumulating MMAs ends ~2.3 n ulp short of the exact sum, a bias that grows linearly with the chain
+  // (tools/acc_chain_test.cu: 7e-7 relative after 36 MMAs, 2.8e-6 after 144) and was the whole gap between f16x3 and
+  // float32 logits.  A unit's K-chunks are therefore cut into n_sub consecutive groups ("sub-items": chunks
+  // [j n / n_sub, (j+1) n / n_sub) of EVERY source); each group accumulates from zero in its own TMEM buffer (the two
+  // buffers alternate between sub-items exactly as they did between units) and the epilogue warps add the groups in
+  // registers, in float32 round-to-nearest, before bias / ReLU.  n_sub = 1 is the plain single chain.
+  int n_sub;
   int stages;          // smem ring depth (<= kMaxStages)
   int cps;             // K-chunks a stage of a 1x1 source carries (>= 1; see the producer)
   int stage_stride;    // bytes per smem ring slot (>= the 3x3 stage; larger when that buys more 1x1 chunks per stage)
@@ -304,6 +317,12 @@ struct TcJob {
   int ring_request;    // host-side wish (images); the launcher derives `ring` from it
   int* flags2;         // [total_units], zeroed before the launch
 };
+
+// chunk range [lo, hi) of a source with n chunks inside sub-item j of n_sub
+__device__ __forceinline__ void sub_range(int n, int j, int n_sub, int& lo, int& hi) {
+  lo = (j * n) / n_sub;
+  hi = ((j + 1) * n) / n_sub;
+}
 
 // item -> (phase, unit) of the interleaved schedule above (T units per phase, D = min(lag, T))
 __device__ __forceinline__ void decode_item(int i, int T, int D, int n_phase, int& phase, int& unit) {
@@ -387,6 +406,7 @@ conv_tc_kernel(const TcJob job) {
   constexpr int MT = TilesPerUnit<N, Dual>::value;
   constexpr int TS = TilesPerUnit<N, Dual>::TS;
   constexpr bool kSplit = PrecTraits<P>::split;
+  constexpr bool kSubAcc = kSplit && G == 1 && SS_TC_SUBACC != 0;   // split-K sub-accumulation (TcConv::n_sub) is compiled in
   constexpr int kWpartsMax = Dual ? 2 : 1;   // weight rows per tap and K-half staged per chunk, in units of N
   const int dbg = kDebugHooks ? p.debug : 0;
   const int Wp = p.W + 2, Hp = p.H + 2;
@@ -464,6 +484,8 @@ conv_tc_kernel(const TcJob job) {
         if (!ok) break;
         asm volatile("fence.proxy.async.global;" ::: "memory");
       }
+      const int n_sub = kSubAcc ? c.n_sub : 1;
+      for (int sub = 0; sub < n_sub && ok; ++sub)
       for (int s = 0; s < c.n_src && ok; ++s) {
         const TcSource& src = c.src[s];
         const uint32_t w_bytes = (uint32_t)((Dual && src.kind == 1 ? 2 : 1) * src.taps) * N * 32u;
@@ -471,7 +493,9 @@ conv_tc_kernel(const TcJob job) {
         // [chunk][plane][run1] activations, then [chunk] weights at w1_off.  (One chunk per stage left these
         // sources bound by the per-stage hand-over and by load latency: 4 MMAs per 18 KB stage.)
         const int per_stage = (src.taps == 1) ? cps : 1;
-        for (int kc = 0; kc < src.n_chunks; kc += per_stage, ++it) {
+        int kc_lo, kc_hi;
+        sub_range(src.n_chunks, sub, n_sub, kc_lo, kc_hi);
+        for (int kc = kc_lo; kc < kc_hi; kc += per_stage, ++it) {
           const int st = it % S;
           const uint32_t ph = (uint32_t)(it / S) & 1u;
           ok = mbar_wait_t<true>(empty0 + 8 * st, ph ^ 1u, p.err, 1, w_empty);
@@ -482,7 +506,7 @@ conv_tc_kernel(const TcJob job) {
           if (dbg & 1) {
             if (elect_one()) mbar_arrive(full0 + 8 * st);
           } else if (src.taps == 1) {
-            const int n = (src.n_chunks - kc < per_stage) ? (src.n_chunks - kc) : per_stage;
+            const int n = (kc_hi - kc < per_stage) ? (kc_hi - kc) : per_stage;
             if (elect_one()) {
               mbar_expect_tx(full0 + 8 * st, (uint32_t)n * (2u * run1 + w_bytes));
               for (int j = 0; j < n; ++j) {
@@ -519,14 +543,11 @@ conv_tc_kernel(const TcJob job) {
     const uint32_t a_lo_base = ((uint32_t)L & 0x3FFFu) << 16;            // LBO = L * 16 bytes
     const uint32_t a1_lo_base = ((run1 >> 4) & 0x3FFFu) << 16;           // 1x1 stages: LBO = run1
     int k = 0;
+    int kk = 0;                    // TMEM buffer turns taken so far: one per unit, or one per sub-item (kSubAcc)
     bool ok = true;
     long long w_acce = 0, w_full = 0;
     const bool timing = p.prof != nullptr;
     const long long t_begin = clock64();
-    // total K-chunks of a unit, to recognise the last one
-    int chunks_of[2] = {0, 0};
-    for (int ph2 = 0; ph2 < n_phase; ++ph2)
-      for (int s = 0; s < job.c[ph2].n_src; ++s) chunks_of[ph2] += job.c[ph2].src[s].n_chunks;
     // The tensor pipe accepts only a couple of MMAs ahead of execution, so every cycle this loop spends between two
     // bursts of MMAs is a pipe bubble: the ring position is carried incrementally (no division), the leader lane is
     // elected once, waits probe inline, and a stage costs one commit.
@@ -539,12 +560,20 @@ conv_tc_kernel(const TcJob job) {
       int phase, u;
       decode_item(item, T, D, n_phase, phase, u);
       const TcConv& c = job.c[phase];
-      const int chunks_per_unit = chunks_of[phase];
-      // G = 1: this unit owns buffer k & 1 (tiles split between the warps); G = 2: warp `me` owns buffer `me`
-      const int buf = (G == 1) ? (k & 1) : me;
-      const uint32_t e_parity = (G == 1) ? ((((uint32_t)k >> 1) & 1u) ^ 1u) : (((uint32_t)k & 1u) ^ 1u);
-      const uint32_t d_unit = tmem_base + (uint32_t)(buf * kAccCols) + (G == 1 ? (uint32_t)(me * MTW * TS) : 0u);
+      const int n_sub = kSubAcc ? c.n_sub : 1;
       const uint32_t a_tile0 = (uint32_t)((G == 1 ? me * MTW : me * MT) * 128);     // first position of my tiles
+     for (int sub = 0; sub < n_sub && ok; ++sub, ++kk) {
+      // K-chunks of this accumulation group, to recognise the last one
+      int chunks_per_unit = 0;
+      for (int s = 0; s < c.n_src; ++s) {
+        int lo_s, hi_s;
+        sub_range(c.src[s].n_chunks, sub, n_sub, lo_s, hi_s);
+        chunks_per_unit += hi_s - lo_s;
+      }
+      // G = 1: this turn owns buffer kk & 1 (tiles split between the warps); G = 2: warp `me` owns buffer `me`
+      const int buf = (G == 1) ? (kk & 1) : me;
+      const uint32_t e_parity = (G == 1) ? ((((uint32_t)kk >> 1) & 1u) ^ 1u) : (((uint32_t)kk & 1u) ^ 1u);
+      const uint32_t d_unit = tmem_base + (uint32_t)(buf * kAccCols) + (G == 1 ? (uint32_t)(me * MTW * TS) : 0u);
       int c_in_unit = 0;
       for (int s = 0; s < c.n_src && ok; ++s) {
         const TcSource& src = c.src[s];
@@ -553,11 +582,13 @@ conv_tc_kernel(const TcJob job) {
         const uint32_t idesc = dual_src ? idesc_2n : idesc_n;
         const uint32_t col0 = (Dual && src.kind == 2) ? (uint32_t)N : 0u;
         const uint32_t b_lo_base = ((uint32_t)(dual_src ? 2 * N : N) & 0x3FFFu) << 16;   // LBO = rows * 16 bytes
-        const int taps = src.taps, n_chunks = src.n_chunks;
+        const int taps = src.taps;
         const int per_stage = (taps == 1) ? cps : 1;
         const uint32_t w_bytes16 = (uint32_t)((dual_src ? 2 : 1) * N * 2);             // 1x1 chunk weights >> 4
-        for (int kc = 0; kc < n_chunks && ok; kc += per_stage) {
-          const int n = (n_chunks - kc < per_stage) ? (n_chunks - kc) : per_stage;
+        int kc_lo, kc_hi;
+        sub_range(src.n_chunks, sub, n_sub, kc_lo, kc_hi);
+        for (int kc = kc_lo; kc < kc_hi && ok; kc += per_stage) {
+          const int n = (kc_hi - kc < per_stage) ? (kc_hi - kc) : per_stage;
           if (!ready && !(dbg & 4)) ok = mbar_wait_fast(full0 + 8 * st, ph, p.err, 2, timing, w_full);
           if (!ok) break;
           if (c_in_unit == 0) {                            // the epilogue must have drained the buffer
@@ -584,7 +615,7 @@ conv_tc_kernel(const TcJob job) {
               if (dual_src) issue_group<MTW, TS, 2 * N>(d_unit + col0, a_lo0, b_lo0, idesc, 9, tap_off, accumulate);
               else issue_group<MTW, TS, N>(d_unit + col0, a_lo0, b_lo0, idesc, 9, tap_off, accumulate);
             }
-            if (c_in_unit + n == chunks_per_unit) tc_commit(accf0 + 8 * buf);   // my tiles of this unit are complete
+            if (c_in_unit + n == chunks_per_unit) tc_commit(accf0 + 8 * buf);   // my tiles of this group are complete
             if (!(dbg & 4)) tc_commit(empty0 + 8 * st);   // my reads of the stage retire with these MMAs
           }
           __syncwarp();
@@ -595,6 +626,7 @@ conv_tc_kernel(const TcJob job) {
           ready = !(dbg & 4) && mbar_try_wait(full0 + 8 * st, ph);
         }
       }
+     }
     }
     __syncwarp();
     if (p.prof && lane == 0 && me == 0) {
@@ -609,10 +641,12 @@ conv_tc_kernel(const TcJob job) {
     const int tile_par = warp >= 6 ? 1 : 0;    // the two warps of a quadrant take alternate tiles
     const int Wp2 = 2 * p.W + 2;
     int k = 0;
+    int kk = 0;                    // TMEM buffer turns taken so far (see the MMA warps)
     bool ok = true;
     bool out_of_range = false;     // fp16 operand modes: an activation left the fp16 range (it was saturated)
     long long w_accf = 0;
     const long long t_begin = clock64();
+    constexpr int kMyTiles = kSubAcc ? MT / 2 : 1;     // tiles of a unit this warp owns (sub-accumulation keeps them all)
     for (int item; (item = item_of(k)) < n_items && ok; ++k) {
       int phase, u;
       decode_item(item, T, D, n_phase, phase, u);
@@ -623,15 +657,11 @@ conv_tc_kernel(const TcJob job) {
       const int b = u / p.units_per_image;
       const int bo = c.out_ring ? b % c.out_ring : b;
       const int64_t img_off = ((int64_t)bo * c.out_planes_total + c.out_plane0) * out_plane_stride;
-     for (int g = 0; g < G && ok; ++g) {
-      const int buf = (G == 1) ? (k & 1) : g;
-      const uint32_t f_parity = (G == 1) ? (((uint32_t)k >> 1) & 1u) : ((uint32_t)k & 1u);
-      const int q0 = halo + ((u - b * p.units_per_image) * G + g) * MT * 128;
-      ok = mbar_wait_t(accf0 + 8 * buf, f_parity, p.err, 3, w_accf);
-      if (!ok) break;
-      tc_fence_after();
-      for (int mt = tile_par; mt < MT; mt += 2) {
-        const int pos = q0 + mt * 128 + quad * 32 + lane;
+      float vmax = 0.f;
+
+      // Everything after the accumulators of one tile's 32-column block [n0, n0 + 32) are final: undo the weight
+      // scale, bias, scalar residual, ReLU, (mask-head partials,) 16-bit pack, stores.
+      auto finalize = [&](const uint32_t (&v)[32], const int n0, const int pos) {
         const int y = pos / Wp, x = pos - y * Wp;
         const bool interior = (y >= 1) && (y <= p.H) && (x >= 1) && (x <= p.W);
         const bool in_tensor = pos < HpWp;
@@ -641,109 +671,171 @@ conv_tc_kernel(const TcJob job) {
         const float* resw_p = bias_s + 2 * N + phase * N;
         const float* bias_t = interior ? bias_p : zero_s;
         const float scale_t = interior ? inv_scale : 0.f;
-        float vmax = 0.f;
+        if constexpr (N == 32) {
+          if (c.head_w != nullptr) {
+            // fused conv_flatten partials: this position's 32 activations . head_w[y - 1][:, 0..3]
+            if (interior) {
+              const float4* wrow = reinterpret_cast<const float4*>(c.head_w) + (y - 1) * 32;
+              float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-        for (int n0 = 0; n0 < N; n0 += 32) {
-          uint32_t v[32];
-          tc_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * kAccCols + mt * TS + n0), v);
-          if constexpr (Dual) {
-            uint32_t cv[32];      // both loads in flight under one wait
-            tc_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * kAccCols + mt * TS + N + n0), cv);
-            tc_wait_ld();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(cv[i]));
-          } else {
-            tc_wait_ld();
-          }
-          if constexpr (N == 32) {
-            if (c.head_w != nullptr) {
-              // fused conv_flatten partials: this position's 32 activations . head_w[y - 1][:, 0..3]
-              if (interior) {
-                const float4* wrow = reinterpret_cast<const float4*>(c.head_w) + (y - 1) * 32;
-                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                  float f = fmaf(__uint_as_float(v[i]), inv_scale, bias_p[i]);
-                  f = fmaxf(f, 0.f);
-                  const float4 w = __ldg(wrow + i);
-                  acc.x = fmaf(f, w.x, acc.x);
-                  acc.y = fmaf(f, w.y, acc.y);
-                  acc.z = fmaf(f, w.z, acc.z);
-                  acc.w = fmaf(f, w.w, acc.w);
-                }
-                reinterpret_cast<float4*>(c.head_out)[((int64_t)b * p.H + (y - 1)) * p.W + (x - 1)] = acc;
+              for (int i = 0; i < 32; ++i) {
+                float f = fmaf(__uint_as_float(v[i]), inv_scale, bias_p[i]);
+                f = fmaxf(f, 0.f);
+                const float4 w = __ldg(wrow + i);
+                acc.x = fmaf(f, w.x, acc.x);
+                acc.y = fmaf(f, w.y, acc.y);
+                acc.z = fmaf(f, w.z, acc.z);
+                acc.w = fmaf(f, w.w, acc.w);
               }
-              if (c.out == nullptr) continue;      // nobody reads the activations themselves (no spec head requested)
+              reinterpret_cast<float4*>(c.head_out)[((int64_t)b * p.H + (y - 1)) * p.W + (x - 1)] = acc;
             }
+            if (c.out == nullptr) return;      // nobody reads the activations themselves (no spec head requested)
+          }
+        }
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint32_t hw[4], lw[4];
+          // Border positions get scale 0 and a zero bias vector instead of a select per value: fma(acc, 0, 0) = +0.
+          // Every convolution of this network is followed by ReLU, so the fp16 clamp is one-sided and the range
+          // check a running maximum (tested once per unit).
+          const float4 b0 = *reinterpret_cast<const float4*>(bias_t + n0 + g * 8);
+          const float4 b1 = *reinterpret_cast<const float4*>(bias_t + n0 + g * 8 + 4);
+          const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+          float rw[8];
+          if (c.res_x != nullptr) {
+            const float4 r0 = *reinterpret_cast<const float4*>(resw_p + n0 + g * 8);
+            const float4 r1 = *reinterpret_cast<const float4*>(resw_p + n0 + g * 8 + 4);
+            rw[0] = r0.x; rw[1] = r0.y; rw[2] = r0.z; rw[3] = r0.w; rw[4] = r1.x; rw[5] = r1.y; rw[6] = r1.z; rw[7] = r1.w;
           }
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            uint32_t hw[4], lw[4];
-            // Border positions get scale 0 and a zero bias vector instead of a select per value: fma(acc, 0, 0) = +0.
-            // Every convolution of this network is followed by ReLU, so the fp16 clamp is one-sided and the range
-            // check a running maximum (tested once per tile).
-            const float4 b0 = *reinterpret_cast<const float4*>(bias_t + n0 + g * 8);
-            const float4 b1 = *reinterpret_cast<const float4*>(bias_t + n0 + g * 8 + 4);
-            const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-            float rw[8];
+          for (int h = 0; h < 4; ++h) {
+            float f0 = fmaf(__uint_as_float(v[g * 8 + 2 * h]), scale_t, bb[2 * h]);
+            float f1 = fmaf(__uint_as_float(v[g * 8 + 2 * h + 1]), scale_t, bb[2 * h + 1]);
             if (c.res_x != nullptr) {
-              const float4 r0 = *reinterpret_cast<const float4*>(resw_p + n0 + g * 8);
-              const float4 r1 = *reinterpret_cast<const float4*>(resw_p + n0 + g * 8 + 4);
-              rw[0] = r0.x; rw[1] = r0.y; rw[2] = r0.z; rw[3] = r0.w; rw[4] = r1.x; rw[5] = r1.y; rw[6] = r1.z; rw[7] = r1.w;
+              f0 = fmaf(rx, rw[2 * h], f0);
+              f1 = fmaf(rx, rw[2 * h + 1], f1);
             }
-#pragma unroll
-            for (int h = 0; h < 4; ++h) {
-              float f0 = fmaf(__uint_as_float(v[g * 8 + 2 * h]), scale_t, bb[2 * h]);
-              float f1 = fmaf(__uint_as_float(v[g * 8 + 2 * h + 1]), scale_t, bb[2 * h + 1]);
-              if (c.res_x != nullptr) {
-                f0 = fmaf(rx, rw[2 * h], f0);
-                f1 = fmaf(rx, rw[2 * h + 1], f1);
-              }
-              f0 = fmaxf(f0, 0.f);
-              f1 = fmaxf(f1, 0.f);
-              if constexpr (PrecTraits<P>::fmt == 0) {
-                vmax = fmaxf(vmax, fmaxf(f0, f1));
-                f0 = fminf(f0, 65504.f);
-                f1 = fminf(f1, 65504.f);
-              }
-              hw[h] = pack_rn<P>(f0, f1);
-              if constexpr (kSplit) lw[h] = pack_lo_f16(f0, f1, hw[h]);
-              else lw[h] = 0u;
+            f0 = fmaxf(f0, 0.f);
+            f1 = fmaxf(f1, 0.f);
+            if constexpr (PrecTraits<P>::fmt == 0) {
+              vmax = fmaxf(vmax, fmaxf(f0, f1));
+              f0 = fminf(f0, 65504.f);
+              f1 = fminf(f1, 65504.f);
             }
-            const uint4 ph = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-            const int64_t plane_off = img_off + (int64_t)(n0 / 8 + g) * out_plane_stride;
-            if (dbg & 2) {
-              if (ph.x == 0x12345678u && lw[0] == 0x9abcdef0u) p.err[1] = 1;      // keep the values alive
-            } else if (!c.upsample) {
-              if (in_tensor) {
-                st16(c.out + plane_off + (int64_t)pos * 8, ph);
-                if constexpr (kSplit)
-                  st16(c.out_lo + plane_off + (int64_t)pos * 8, make_uint4(lw[0], lw[1], lw[2], lw[3]));
-              }
-            } else if (interior) {
-              uint16_t* o = c.out + plane_off + up * 8;
-              st16(o, ph);
-              st16(o + 8, ph);
-              st16(o + (int64_t)Wp2 * 8, ph);
-              st16(o + (int64_t)Wp2 * 8 + 8, ph);
-              if constexpr (kSplit) {
-                const uint4 pl = make_uint4(lw[0], lw[1], lw[2], lw[3]);
-                uint16_t* ol = c.out_lo + plane_off + up * 8;
-                st16(ol, pl);
-                st16(ol + 8, pl);
-                st16(ol + (int64_t)Wp2 * 8, pl);
-                st16(ol + (int64_t)Wp2 * 8 + 8, pl);
-              }
+            hw[h] = pack_rn<P>(f0, f1);
+            if constexpr (kSplit) lw[h] = pack_lo_f16(f0, f1, hw[h]);
+            else lw[h] = 0u;
+          }
+          const uint4 ph = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+          const int64_t plane_off = img_off + (int64_t)(n0 / 8 + g) * out_plane_stride;
+          if (dbg & 2) {
+            if (ph.x == 0x12345678u && lw[0] == 0x9abcdef0u) p.err[1] = 1;      // keep the values alive
+          } else if (!c.upsample) {
+            if (in_tensor) {
+              st16(c.out + plane_off + (int64_t)pos * 8, ph);
+              if constexpr (kSplit)
+                st16(c.out_lo + plane_off + (int64_t)pos * 8, make_uint4(lw[0], lw[1], lw[2], lw[3]));
+            }
+          } else if (interior) {
+            uint16_t* o = c.out + plane_off + up * 8;
+            st16(o, ph);
+            st16(o + 8, ph);
+            st16(o + (int64_t)Wp2 * 8, ph);
+            st16(o + (int64_t)Wp2 * 8 + 8, ph);
+            if constexpr (kSplit) {
+              const uint4 pl = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+              uint16_t* ol = c.out_lo + plane_off + up * 8;
+              st16(ol, pl);
+              st16(ol + 8, pl);
+              st16(ol + (int64_t)Wp2 * 8, pl);
+              st16(ol + (int64_t)Wp2 * 8 + 8, pl);
             }
           }
         }
-        if constexpr (PrecTraits<P>::fmt == 0) out_of_range |= (vmax > 65504.f);
+      };
+      // one tile's 32-column block of TMEM buffer `buf` (dual layout: main + correction columns, both loads in flight
+      // under one wait)
+      auto load_block = [&](uint32_t (&v)[32], const int buf, const int mt, const int n0) {
+        tc_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * kAccCols + mt * TS + n0), v);
+        if constexpr (Dual) {
+          uint32_t cv[32];
+          tc_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * kAccCols + mt * TS + N + n0), cv);
+          tc_wait_ld();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(cv[i]));
+        } else {
+          tc_wait_ld();
+        }
+      };
+
+      if constexpr (kSubAcc) {
+        // n_sub accumulation groups of this unit arrive one buffer turn after the other; their sums live in registers
+        // (this warp's MT / 2 tiles x N columns of its 32 positions) and are added in float32, round to nearest.
+        const int n_sub = c.n_sub;
+        const int q0 = halo + (u - b * p.units_per_image) * MT * 128;
+        float acc[kMyTiles][N];
+        for (int sub = 0; sub < n_sub && ok; ++sub, ++kk) {
+          const int buf = kk & 1;
+          const uint32_t f_parity = ((uint32_t)kk >> 1) & 1u;
+          ok = mbar_wait_t(accf0 + 8 * buf, f_parity, p.err, 3, w_accf);
+          if (!ok) break;
+          tc_fence_after();
+#pragma unroll
+          for (int ti = 0; ti < kMyTiles; ++ti) {
+#pragma unroll
+            for (int n0 = 0; n0 < N; n0 += 32) {
+              uint32_t v[32];
+              load_block(v, buf, tile_par + 2 * ti, n0);
+              if (sub == 0) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) acc[ti][n0 + i] = __uint_as_float(v[i]);
+              } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) acc[ti][n0 + i] += __uint_as_float(v[i]);
+              }
+            }
+          }
+          // all of this warp's TMEM reads of the buffer have completed (tcgen05.wait::ld after each load pair)
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(acce0 + 8 * buf);
+        }
+        if (!ok) break;
+#pragma unroll
+        for (int ti = 0; ti < kMyTiles; ++ti) {
+          const int pos = q0 + (tile_par + 2 * ti) * 128 + quad * 32 + lane;
+#pragma unroll
+          for (int n0 = 0; n0 < N; n0 += 32) {
+            uint32_t v[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(acc[ti][n0 + i]);
+            finalize(v, n0, pos);
+          }
+        }
+      } else {
+       for (int g = 0; g < G && ok; ++g, ++kk) {
+        const int buf = (G == 1) ? (kk & 1) : g;
+        const uint32_t f_parity = (G == 1) ? (((uint32_t)kk >> 1) & 1u) : ((uint32_t)k & 1u);
+        const int q0 = halo + ((u - b * p.units_per_image) * G + g) * MT * 128;
+        ok = mbar_wait_t(accf0 + 8 * buf, f_parity, p.err, 3, w_accf);
+        if (!ok) break;
+        tc_fence_after();
+        for (int mt = tile_par; mt < MT; mt += 2) {
+          const int pos = q0 + mt * 128 + quad * 32 + lane;
+#pragma unroll
+          for (int n0 = 0; n0 < N; n0 += 32) {
+            uint32_t v[32];
+            load_block(v, buf, mt, n0);
+            finalize(v, n0, pos);
+          }
+        }
+        // all of this warp's TMEM reads of the buffer have completed (tcgen05.wait::ld after each load pair)
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(acce0 + 8 * buf);
+       }
       }
-      // all of this warp's TMEM reads of the buffer have completed (tcgen05.wait::ld after each load pair)
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(acce0 + 8 * buf);
-     }
+      if constexpr (PrecTraits<P>::fmt == 0) out_of_range |= (vmax > 65504.f);
       if (n_phase == 2 && phase == 0) {
         // publish this warp's share of the unit to the c[1] producers of other CTAs (release at gpu scope)
         asm volatile("fence.proxy.async.global;" ::: "memory");

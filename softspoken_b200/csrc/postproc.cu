@@ -33,10 +33,13 @@ constexpr int kHotBins = 4;          // bins per thread of hot_bits_kernel
 // Index: uint32_t while 5 out_len + 2 fits (116 days of audio), else int64_t — the kernel is bound by instruction
 // issue, not by HBM, and 64-bit divisions by 5 were most of its instructions; p_i is divided once for i_lo and
 // carried forward (256 = 5 * 51 + 1: the quotient grows by 51, and by one more whenever the remainder wraps).
+// flags (optional, with kBits): margin-guided refinement — a bin whose average lies within `eps` of the threshold
+// marks its covering windows in flags[] (one byte per window); see ss_ctx_set_refine.
 template <bool kBits, typename Index>
 __global__ void __launch_bounds__(kAvgThreads)
 average_kernel(const float* __restrict__ logits, int n_windows, int64_t out_len, double* __restrict__ avg,
-               int32_t* __restrict__ cnt, double threshold, uint32_t* __restrict__ bits) {
+               int32_t* __restrict__ cnt, double threshold, uint32_t* __restrict__ bits, double eps,
+               unsigned char* __restrict__ flags) {
   const int64_t j64 = (int64_t)blockIdx.x * kAvgThreads + threadIdx.x;
   const bool in = j64 < out_len;
   bool hot = false;
@@ -67,6 +70,11 @@ average_kernel(const float* __restrict__ logits, int n_windows, int64_t out_len,
     cnt[j64] = n;
     avg[j64] = a;
     hot = n >= 1 && a > threshold;
+    if (kBits && flags != nullptr && n >= 1 && fabs(a - threshold) < eps) {
+#pragma unroll
+      for (int k = 0; k < 5; ++k)
+        if (k < n) flags[(int64_t)i_lo + k] = 1;
+    }
   }
   if (kBits) {
     const unsigned word = __ballot_sync(0xffffffffu, hot);
@@ -76,12 +84,50 @@ average_kernel(const float* __restrict__ logits, int n_windows, int64_t out_len,
 
 template <bool kBits>
 static void launch_average_kernel(const float* logits, int n_windows, int64_t out_len, double* avg, int32_t* cnt,
-                                  double threshold, uint32_t* bits, cudaStream_t st) {
+                                  double threshold, uint32_t* bits, cudaStream_t st, double eps = 0.0,
+                                  unsigned char* flags = nullptr) {
   const int grid = (int)((out_len + kAvgThreads - 1) / kAvgThreads);
   if (5 * out_len + 2 < ((int64_t)1 << 32) && (int64_t)n_windows * 256 + 2 < ((int64_t)1 << 32))
-    average_kernel<kBits, uint32_t><<<grid, kAvgThreads, 0, st>>>(logits, n_windows, out_len, avg, cnt, threshold, bits);
+    average_kernel<kBits, uint32_t><<<grid, kAvgThreads, 0, st>>>(logits, n_windows, out_len, avg, cnt, threshold, bits,
+                                                                  eps, flags);
   else
-    average_kernel<kBits, int64_t><<<grid, kAvgThreads, 0, st>>>(logits, n_windows, out_len, avg, cnt, threshold, bits);
+    average_kernel<kBits, int64_t><<<grid, kAvgThreads, 0, st>>>(logits, n_windows, out_len, avg, cnt, threshold, bits,
+                                                                 eps, flags);
+}
+
+// Refinement bookkeeping: flags[0 .. n) (one byte per window) -> ascending list of the flagged window indices and
+// their number.  One CTA; ballot + block scan per 1,024 windows.
+__global__ void __launch_bounds__(1024)
+compact_flags_kernel(const unsigned char* __restrict__ flags, int n, int32_t* __restrict__ list,
+                     int32_t* __restrict__ count) {
+  __shared__ int warp_tot[32];
+  __shared__ int carry;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  if (tid == 0) carry = 0;
+  __syncthreads();
+  for (int base = 0; base < n; base += 1024) {
+    const int i = base + tid;
+    const bool f = i < n && flags[i] != 0;
+    const unsigned m = __ballot_sync(0xffffffffu, f);
+    if (lane == 0) warp_tot[wid] = __popc(m);
+    __syncthreads();
+    int off = carry, tot = 0;
+    for (int w = 0; w < 32; ++w) {
+      if (w < wid) off += warp_tot[w];
+      tot += warp_tot[w];
+    }
+    if (f) list[off + __popc(m & ((1u << lane) - 1u))] = i;
+    __syncthreads();
+    if (tid == 0) carry += tot;
+    __syncthreads();
+  }
+  if (tid == 0) *count = carry;
+}
+
+// logits[list[k]][0 .. 256) = rows[k][0 .. 256): the refined windows replace their first-pass logits
+__global__ void __launch_bounds__(256)
+scatter_rows_kernel(const float* __restrict__ rows, const int32_t* __restrict__ list, float* __restrict__ logits) {
+  logits[(int64_t)list[blockIdx.x] * kFrames + threadIdx.x] = rows[(int64_t)blockIdx.x * kFrames + threadIdx.x];
 }
 
 // hot[j] = count[j] >= 1 && avg[j] > threshold as one bit per bin (the entry for callers that bring their own timeline)
@@ -287,10 +333,25 @@ int launch_regions(const double* avg, const int32_t* cnt, int64_t out_len, doubl
   return launch_regions_bits(bits, out_len, gap_bins, regions, n_regions, cap, scan_tmp, st);
 }
 
-// K5 + K6 of the detection pipeline: the averaging kernel votes the hot bits while the averages are in registers.
-int launch_average_regions(const float* logits, int n_windows, int64_t out_len, double* avg, int32_t* cnt,
-                           double threshold, int gap_bins, int32_t* regions, int32_t* n_regions, int cap,
-                           int32_t* scan_tmp, int64_t scan_tmp_len, cudaStream_t st) {
+// K5 of the detection pipeline: the averaging kernel votes the hot bits (into the K6 scratch) while the averages are
+// in registers and, when `win_flags` is given, marks the windows covering a bin within `eps` of the threshold.
+int launch_average_bits(const float* logits, int n_windows, int64_t out_len, double* avg, int32_t* cnt,
+                        double threshold, int32_t* scan_tmp, int64_t scan_tmp_len, double eps,
+                        unsigned char* win_flags, cudaStream_t st) {
+  int gap = 1;
+  int rc = check_regions_args(out_len, gap, scan_tmp_len);
+  if (rc) return rc;
+  if (out_len <= 0) return SS_OK;
+  uint32_t* bits = reinterpret_cast<uint32_t*>(scan_tmp + count_words(out_len));
+  launch_average_kernel<true>(logits, n_windows, out_len, avg, cnt, threshold, bits, st, eps, win_flags);
+  SS_CUDA_CHECK(cudaGetLastError());
+  count_launch();
+  return SS_OK;
+}
+
+// K6 on the hot bits launch_average_bits left in the scratch.
+int launch_regions_after_bits(int64_t out_len, int gap_bins, int32_t* regions, int32_t* n_regions, int cap,
+                              int32_t* scan_tmp, int64_t scan_tmp_len, cudaStream_t st) {
   int rc = check_regions_args(out_len, gap_bins, scan_tmp_len);
   if (rc) return rc;
   if (out_len <= 0) {
@@ -298,10 +359,30 @@ int launch_average_regions(const float* logits, int n_windows, int64_t out_len, 
     return SS_OK;
   }
   uint32_t* bits = reinterpret_cast<uint32_t*>(scan_tmp + count_words(out_len));
-  launch_average_kernel<true>(logits, n_windows, out_len, avg, cnt, threshold, bits, st);
+  return launch_regions_bits(bits, out_len, gap_bins, regions, n_regions, cap, scan_tmp, st);
+}
+
+int launch_average_regions(const float* logits, int n_windows, int64_t out_len, double* avg, int32_t* cnt,
+                           double threshold, int gap_bins, int32_t* regions, int32_t* n_regions, int cap,
+                           int32_t* scan_tmp, int64_t scan_tmp_len, cudaStream_t st) {
+  int rc = launch_average_bits(logits, n_windows, out_len, avg, cnt, threshold, scan_tmp, scan_tmp_len, 0.0, nullptr, st);
+  if (rc) return rc;
+  return launch_regions_after_bits(out_len, gap_bins, regions, n_regions, cap, scan_tmp, scan_tmp_len, st);
+}
+
+int launch_compact_flags(const unsigned char* flags, int n, int32_t* list, int32_t* count, cudaStream_t st) {
+  compact_flags_kernel<<<1, 1024, 0, st>>>(flags, n, list, count);
   SS_CUDA_CHECK(cudaGetLastError());
   count_launch();
-  return launch_regions_bits(bits, out_len, gap_bins, regions, n_regions, cap, scan_tmp, st);
+  return SS_OK;
+}
+
+int launch_scatter_rows(const float* rows, const int32_t* list, int n, float* logits, cudaStream_t st) {
+  if (n <= 0) return SS_OK;
+  scatter_rows_kernel<<<n, kFrames, 0, st>>>(rows, list, logits);
+  SS_CUDA_CHECK(cudaGetLastError());
+  count_launch();
+  return SS_OK;
 }
 
 }  // namespace ss

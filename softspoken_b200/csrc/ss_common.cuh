@@ -5,7 +5,9 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <map>
 #include <string>
+#include <vector>
 
 #include "../../include/softspoken_b200.h"
 
@@ -26,6 +28,18 @@ constexpr int kFreqs = 1025;
 constexpr int kMaxMelTaps = 32;    // rows of the feature kernel's transposed tap table
 constexpr int kGapBins = 42;                       // 0.5 s break (worker.py:97) on the 256/3 Hz timeline
 constexpr int kNumSMs = 148;
+
+// Guard bands (ss_debug_check_guards): kGuardPattern reads as a small finite number in fp16, bf16 and fp32 alike, so
+// the halo over-reads of the convolution kernel's first / last staged runs stay harmless.
+constexpr unsigned char kGuardPattern = 0x3C;
+constexpr size_t kCtxGuardBytes = 4096;
+struct GuardBand {
+  const unsigned char* ptr;
+  size_t bytes;
+  const void* owner;      // allocation the band belongs to
+};
+void register_guard(ss_ctx* ctx, const void* ptr, size_t bytes, const void* owner);
+void unregister_guards(ss_ctx* ctx, const void* owner);
 
 void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
@@ -149,6 +163,20 @@ struct ss_ctx {
   cudaEvent_t ev_consumed[2] = {nullptr, nullptr};
   cudaStream_t compute_stream = nullptr;
   cudaStream_t copy_stream = nullptr;
+  // margin-guided refinement (ss_ctx_set_refine): windows covering a bin whose average lies within refine_eps of the
+  // threshold are classified again in refine_mode and K5 runs again on the patched logits
+  double refine_eps = 0.0;
+  int refine_mode = SS_MODE_FP32;
+  unsigned char* win_flags = nullptr;   // [refine_cap_windows] marks of the clip in flight
+  int64_t refine_cap_windows = 0;
+  int32_t* refine_list = nullptr;       // [1 + refine_cap_windows] device: count, then ascending window indices
+  int32_t* refine_host = nullptr;       // pinned mirror of refine_list
+  void* refine_raw = nullptr;           // [kRefineBatch][65536] samples (float32 or int16) of the windows being refined
+  int64_t* refine_starts = nullptr;     // [kRefineBatch] k * 65536
+  float* refine_logits = nullptr;       // [kRefineBatch][256]
+  uint64_t stat_windows = 0, stat_refined = 0, stat_clips = 0, stat_clips_refined = 0;
+  std::map<const void*, void*> allocs;          // user pointer -> cudaMalloc base of the context's own allocations
+  std::vector<ss::GuardBand> guards;
 };
 
 namespace ss {
@@ -189,6 +217,15 @@ int64_t regions_scan_tmp_len(int64_t out_len);
 int launch_average_regions(const float* logits, int n_windows, int64_t out_len, double* avg, int32_t* cnt,
                            double threshold, int gap_bins, int32_t* regions, int32_t* n_regions, int cap,
                            int32_t* scan_tmp, int64_t scan_tmp_len, cudaStream_t st);
+// the two halves of launch_average_regions; win_flags (optional, one byte per window, zeroed by the caller) receives
+// a mark for every window covering a bin whose average lies within eps of the threshold
+int launch_average_bits(const float* logits, int n_windows, int64_t out_len, double* avg, int32_t* cnt,
+                        double threshold, int32_t* scan_tmp, int64_t scan_tmp_len, double eps,
+                        unsigned char* win_flags, cudaStream_t st);
+int launch_regions_after_bits(int64_t out_len, int gap_bins, int32_t* regions, int32_t* n_regions, int cap,
+                              int32_t* scan_tmp, int64_t scan_tmp_len, cudaStream_t st);
+int launch_compact_flags(const unsigned char* flags, int n, int32_t* list, int32_t* count, cudaStream_t st);
+int launch_scatter_rows(const float* rows, const int32_t* list, int n, float* logits, cudaStream_t st);
 // silence.cu
 // zero [begin - shift, end - shift) ∩ [0, n_elems) of pcm for every interval
 int launch_silence(float* pcm, int64_t n_elems, int64_t shift, const ss_interval* iv, int n_intervals, cudaStream_t st);

@@ -97,7 +97,11 @@ class NNDetector:
         starts = torch.from_numpy(idx - lo).to(eng.device)
         mel = eng.features(span, starts)
         logits, spec_out = eng.classify(mel, want_spec=True)
-        return spec_out.cpu().numpy(), logits.unsqueeze(1).cpu().numpy()
+        out = spec_out.cpu().numpy(), logits.unsqueeze(1).cpu().numpy()
+        # ss_classify only enqueues: a pipeline time-out or an activation beyond the fp16 range (an fp16-operand mode
+        # on a checkpoint it does not fit) must fail this call, not end up as garbage rows in the detections CSV
+        eng.check_health()
+        return out
 
     # ------------------------------------------------------------------ NNDetector.py:103-143
     def find_speech_regions(self, averaged_detections, break_duration=0.5):

@@ -70,6 +70,8 @@ def rows_from_triplets(files: Sequence[str], triplets: np.ndarray, next_id: int 
     from .detector import region_bins_to_times
     from .worker import detection_rows
     rows: List[dict] = []
+    # a file detected twice (e.g. by two runs that both journalled it) contributes its regions once
+    triplets = np.unique(np.asarray(triplets, dtype=np.int32).reshape(-1, 3), axis=0)
     for fi in range(len(files)):
         sel = triplets[triplets[:, 0] == fi][:, 1:3]
         new = detection_rows(files[fi], region_bins_to_times(sel), next_id)

@@ -66,6 +66,24 @@ class Engine:
             raise ValueError(f"unknown mode {m!r}; expected one of {sorted(_lib.MODES)}")
         return _lib.MODES[m]
 
+    def set_refine(self, eps: float, mode: str = "fp32") -> None:
+        """Margin-guided refinement of the detect_* calls (`ss_ctx_set_refine`): windows covering a timeline bin whose
+        average lies within `eps` of the 0.1 threshold are classified again in `mode`; 0 switches it off."""
+        check(lib.ss_ctx_set_refine(self._ctx, float(eps), _lib.MODES[mode]))
+
+    def refine_stats(self, reset: bool = False) -> dict:
+        st = (C.c_uint64 * 4)()
+        check(lib.ss_ctx_refine_stats(self._ctx, st, int(reset)))
+        return {"windows": int(st[0]), "windows_refined": int(st[1]), "clips": int(st[2]),
+                "clips_refined": int(st[3])}
+
+    def check_guards(self) -> int:
+        """Bytes of the guard bands around the context's device allocations that a kernel overwrote (0 = none)."""
+        bad, n = C.c_uint64(), C.c_int()
+        check(lib.ss_debug_check_guards(self._ctx, C.byref(bad), C.byref(n)))
+        assert n.value > 0
+        return int(bad.value)
+
     def device_bytes(self) -> int:
         n = C.c_size_t()
         check(lib.ss_ctx_device_bytes(self._ctx, C.byref(n)))
@@ -167,8 +185,8 @@ class Engine:
         fn = lib.ss_detect_host_pcm16 if pcm16 else lib.ss_detect_host
         check(fn(self._ctx, ptr, n, self._mode(mode), C.c_void_p(reg.ctypes.data), cap, C.byref(k),
                  C.c_void_p(lg.ctypes.data) if want_logits else None))
-        if k.value > cap:
-            raise _lib.SoftspokenError(_lib.SS_E_CAPACITY, f"{k.value} regions exceed capacity {cap}")
+        if k.value > cap:             # the kernel reports the true count: once more with room for it
+            return self.detect_host(audio, mode, cap=k.value, want_logits=want_logits)
         out = reg[:k.value].copy()
         return (out, lg) if want_logits else out
 
@@ -198,8 +216,11 @@ class Engine:
         out = []
         for i in range(n):
             if cnt[i] > cap:
-                raise _lib.SoftspokenError(_lib.SS_E_CAPACITY, f"clip {i}: {cnt[i]} regions exceed capacity {cap}")
-            out.append(reg[i, :cnt[i]].copy())
+                # a long or busy recording: the kernel reported the true count, run that clip again with room for it
+                # (one long file must not abort a corpus run that has already done the work for the others)
+                out.append(self.detect_host(keep[i], mode, cap=int(cnt[i])))
+            else:
+                out.append(reg[i, :cnt[i]].copy())
         return out
 
     def check_health(self) -> None:

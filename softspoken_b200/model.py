@@ -71,6 +71,7 @@ class SpecUNet_2D:
         starts = torch.arange(B, device=eng.device, dtype=torch.int64) * n
         mel = eng.features(x.reshape(-1), starts)
         logits, spec_out = eng.classify(mel, want_spec=True)
+        eng.check_health()       # synchronises: invalid logits (time-out, fp16 overflow) raise here instead of flowing on
         return spec_out, logits.unsqueeze(1)
 
     __call__ = forward

@@ -73,3 +73,14 @@ def synth_review_rows(n_rows: int, n_files: int, clip_s: float = 600.0, seed: in
     start = np.round(rng.uniform(0.0, clip_s - 2.0, n_rows), 3)
     end = np.round(start + rng.uniform(0.2, 4.0, n_rows), 3)
     return files.astype(np.int64), start, end
+
+
+def stream_hour_pcm16(stream_seed: int, hour: int, sr: int = spec.SAMPLE_RATE) -> np.ndarray:
+    """Hour `hour` of the long synthetic recording `stream_seed`: the recording is the
+    concatenation of independently seeded one-hour clips, so it never has to exist whole and any prefix can be
+    regenerated on another host (360 bursts per hour)."""
+    return synth_pcm16(3600.0, 100_000 + 1_000 * int(stream_seed) + int(hour), sr)
+
+
+def stream_hour(stream_seed: int, hour: int, sr: int = spec.SAMPLE_RATE) -> np.ndarray:
+    return pcm16_to_float32(stream_hour_pcm16(stream_seed, hour, sr))

@@ -22,7 +22,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(_lib.lib, n), f"{n} declared in include/softspoken_b200.h but not exported"
     assert set(names) == set(_lib.EXPORTS)
-    assert _lib.lib.ss_abi_version() == 1
+    assert _lib.lib.ss_abi_version() == _lib.ABI_VERSION == 2
 
 
 def test_constants_match_reference_settings():

@@ -88,3 +88,26 @@ def test_oracle_is_bit_exact_against_live_reference(sd_seed0, clip60):
         sp_r, mk_r = det.model(x)
     sp_o, mk_o = om.forward(sd_seed0, x)
     assert torch.equal(sp_r, sp_o) and torch.equal(mk_r, mk_o)
+
+
+def test_oracle_reproduces_scale_goldens(sd_seed0):
+    """The config-scale goldens (real reference, oracle/make_golden_scale.py): the oracle network on the first
+    reference batch of clip 0 and the oracle post-processing on all of its logits give the reference's results."""
+    import numpy as np
+    import torch
+    from oracle import model as om, postproc as pp
+    from softspoken_b200 import synth
+    g = np.load(os.path.join(GOLDEN, "scale_clip_seed0.npz"))
+    audio = synth.synth_audio(600.0, 0)
+    padded = pp.pad_audio(audio)
+    starts = pp.plan_windows(600.0)
+    assert len(starts) == g["logits"].shape[0] == 1005 and len(padded) == int(g["n_padded"])
+    x = torch.stack([torch.from_numpy(padded[i:i + 66150]) for i in starts[:32]])
+    _, mk = om.forward(sd_seed0, x, want_spec=False)
+    assert np.abs(mk[:, 0].numpy() - g["logits"][:32]).max() <= 1e-6      # oneDNN thread-count noise is ~3e-8
+    avg, cnt = pp.average_idx(g["logits"].reshape(-1, 1, 256), len(padded) / 22050)
+    n = int(g["n_emitted"])
+    assert int((cnt >= 1).sum()) == n
+    assert np.array_equal(avg[:n] > 0.1, np.unpackbits(g["hot_bits"])[:n].astype(bool))
+    assert np.array_equal(pp.find_speech_regions_idx(avg, cnt), g["region_bins"])
+    assert abs(float(np.abs(avg[:n] - 0.1).min()) - float(g["min_margin"])) < 1e-18

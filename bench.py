@@ -40,8 +40,34 @@ SR = 22050
 WINDOWS_PER_CLIP = 1005
 FLOP_PER_WINDOW_MASK = 6_359_672_832          # convs on the mask path, 2 x MAC, BN folded
 FEATURE_BYTES_PER_CLIP = 4 * (13_230_000 + 132_300) + WINDOWS_PER_CLIP * 128 * 256 * 4   # PCM once + mel once
-# DRAM bytes the classifier launches move per window (ncu, profiles/r1_launches_f16x3.txt: 91.3 GB / 1010 windows)
-CLASSIFIER_DRAM_BYTES_PER_WINDOW = {"f16x3": 90_400_000}
+TRAFFIC_FILE = os.path.join(ROOT, "profiles", "r2_traffic.json")
+
+
+def kernel_source_hash() -> str:
+    """sha1 over the CUDA sources: ties an ncu traffic record to the kernels it was taken from."""
+    import glob
+    import hashlib
+    h = hashlib.sha1()
+    for f in sorted(glob.glob(os.path.join(ROOT, "softspoken_b200", "csrc", "*.cu*"))):
+        with open(f, "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()[:12]
+
+
+def measured_traffic(mode: str, kernel: str):
+    """DRAM bytes per window of a kernel family from the ncu record tools/collect_profiles.sh wrote for THIS build
+    (profiles/r2_traffic.json carries the hash of the CUDA sources it was taken from; a record of other sources is
+    stale and reported as null rather than as a number of some earlier kernel)."""
+    try:
+        with open(TRAFFIC_FILE) as f:
+            rec = json.load(f)
+    except (OSError, ValueError):
+        return None, f"{os.path.relpath(TRAFFIC_FILE, ROOT)} missing"
+    if rec.get("kernel_source_sha1") != kernel_source_hash():
+        return None, f"{os.path.relpath(TRAFFIC_FILE, ROOT)} is stale (taken from sources {rec.get('kernel_source_sha1')})"
+    v = rec.get("dram_bytes_per_window", {}).get(mode, {}).get(kernel)
+    return v, (f"ncu dram__bytes_read.sum + dram__bytes_write.sum, {rec.get('how', '')} "
+               f"(sources {rec.get('kernel_source_sha1')}, {rec.get('when', '')})")
 
 
 def peaks():
@@ -159,31 +185,41 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
-def device_clips(n_clips: int, device, seed0: int):
-    """Pool of synthetic 10-minute clips generated on the device (noise + AM harmonic bursts), quantised to
-    PCM_16 levels like a decoded wav."""
-    n = int(CLIP_S * SR)
-    out = []
-    t = torch.arange(n, device=device, dtype=torch.float32) / SR
-    for c in range(n_clips):
-        g = torch.Generator(device=device).manual_seed(seed0 + c)
-        x = torch.randn(n, device=device, generator=g) * 0.05
-        rng = np.random.default_rng(seed0 + c)
-        for _ in range(60):
-            s = float(rng.uniform(0, CLIP_S - 2.0)); ln = float(rng.uniform(0.5, 2.0)); f0 = float(rng.uniform(120, 240))
-            i0, i1 = int(s * SR), int((s + ln) * SR)
-            tt = t[i0:i1] - s
-            env = torch.sin(np.pi * tt / ln) ** 2 * (0.6 + 0.4 * torch.sin(2 * np.pi * 4.0 * tt))
-            h = sum(torch.sin(2 * np.pi * k * f0 * tt) / k for k in range(1, 9))
-            x[i0:i1] += 0.25 * env * h
-        x = torch.clamp(torch.round(x * 32767.0), -32768, 32767) / 32768.0
-        out.append(x.contiguous())
-    return out
+def pool_clips(n_clips: int, seed0: int):
+    """The bench pool: 10-minute clips of the seeded generator every test uses (`synth.synth_pcm16(600, seed)`: noise +
+    60 speech-like bursts, PCM_16 levels).  Clips 0 and 1 of rank 0 are the clips whose reference results are frozen
+    in tests/golden/scale_clip_seed{0,1}.npz (tests/test_gpu_scale.py)."""
+    from softspoken_b200 import synth
+    return [synth.synth_pcm16(CLIP_S, seed0 + c) for c in range(n_clips)]
+
+
+def write_corpus(pool16, n_files: int, root: str, distinct: bool):
+    """`n_files` PCM_16 wavs under `root` (tmpfs): the pool clips written once each, the rest hard links to them
+    (or full copies with `distinct`)."""
+    import shutil
+    from softspoken_b200 import wavio
+    os.makedirs(root, exist_ok=True)
+    base = []
+    for c, pcm in enumerate(pool16):
+        path = os.path.join(root, f"pool_{c}.wav")
+        wavio.write_wav_pcm16(path, pcm, SR)
+        base.append(path)
+    files = []
+    for i in range(n_files):
+        path = os.path.join(root, f"clip_{i:05d}.wav")
+        if os.path.exists(path):
+            os.remove(path)
+        if distinct:
+            shutil.copyfile(base[i % len(base)], path)
+        else:
+            os.link(base[i % len(base)], path)
+        files.append(path)
+    return files
 
 
 def run_b200(args):
     import torch.distributed as dist
-    from softspoken_b200 import _lib, dist as ssdist
+    from softspoken_b200 import _lib, corpus, dist as ssdist
     from softspoken_b200.engine import Engine
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -197,14 +233,18 @@ def run_b200(args):
 
     sd = load_state_dict()
     eng = Engine(sd, local, max_batch=args.max_batch, mode=args.mode)
+    if args.refine_eps is not None:
+        eng.set_refine(args.refine_eps)
     n = int(CLIP_S * SR)
     cap = 4096
     eng.reserve(n, cap)
     C = args.clips_per_step
-    pool = device_clips(args.pool, device, seed0=1000 * rank)
-    pinned = [p.cpu().pin_memory() for p in pool]
-    # the same clips as the int16 samples a PCM_16 wav stores (the pool is quantised to k / 32768, so this is exact)
-    pinned16 = [(p * 32768.0).round().to(torch.int16).cpu().pin_memory() for p in pool]
+    pool16 = pool_clips(args.pool, seed0=args.pool * rank)
+    # host side: pinned int16 (what a PCM_16 wav stores) and pinned float32 (what load_audio returns: k / 32768, exact);
+    # device side: the float32 clips resident in HBM
+    pinned16 = [torch.from_numpy(p).pin_memory() for p in pool16]
+    pinned = [(torch.from_numpy(p).to(torch.float32) / 32768.0).pin_memory() for p in pool16]
+    pool = [p.to(device) for p in pinned]
     reg_bufs = [(torch.empty((cap, 2), dtype=torch.int32, device=device), torch.zeros(1, dtype=torch.int32, device=device))
                 for _ in range(C)]
     stream = torch.cuda.current_stream(device)
@@ -218,34 +258,36 @@ def run_b200(args):
     import ctypes as Cc
     from softspoken_b200._lib import lib, check, MODES
 
+    # Config 3 (N > 1): files shard per rank, every rank keeps its (file, start_bin, end_bin) triplets and ONE gather
+    # to rank 0 closes the run (softspoken_b200/dist.py) — inside the timed region, after the last step.
+    trip: list = []
+
     def step_device(s):
-        trip = []
         for j in range(C):
             clip = pool[(s * C + j) % len(pool)]
             reg, cnt = reg_bufs[j]
             check(lib.ss_detect_device(eng._ctx, Cc.c_void_p(clip.data_ptr()), n, MODES[args.mode],
                                        Cc.c_void_p(reg.data_ptr()), Cc.c_void_p(cnt.data_ptr()), cap, None,
                                        Cc.c_void_p(stream.cuda_stream)))
-        if world > 1:                                   # config 3: detections gathered to rank 0
-            for j in range(C):
-                reg, cnt = reg_bufs[j]
+            if world > 1:                               # the step's detections leave the reusable device buffers
                 k = int(cnt.item())
-                fi = torch.full((k, 1), (s * C + j) * world + rank, dtype=torch.int32, device=device)
-                trip.append(torch.cat([fi, reg[:k]], 1).cpu().numpy())
-            ssdist.gather_detections(np.concatenate(trip) if trip else np.zeros((0, 3), np.int32), device)
+                fi = np.full((k, 1), (s * C + j) * world + rank, np.int32)
+                trip.append(np.concatenate([fi, reg[:k].cpu().numpy()], 1))
 
     def step_host(s, src=None):
         total_regions = 0
-        trip = []
         src = pinned if src is None else src
         clips = [src[(s * C + j) % len(src)] for j in range(C)]
         for j, bins in enumerate(eng.detect_host_batch(clips, cap=cap)):   # one C-ABI call per step
             total_regions += len(bins)
             if world > 1:
                 trip.append(np.concatenate([np.full((len(bins), 1), (s * C + j) * world + rank, np.int32), bins], 1))
-        if world > 1:
-            ssdist.gather_detections(np.concatenate(trip) if trip else np.zeros((0, 3), np.int32), device)
         return total_regions
+
+    def gather_all():
+        rows = ssdist.gather_detections(np.concatenate(trip) if trip else np.zeros((0, 3), np.int32), device)
+        trip.clear()
+        return rows
 
     def timed(fn, steps, warmup):
         sampler = ClockSampler(local) if rank == 0 else None
@@ -253,6 +295,8 @@ def run_b200(args):
             sampler.start()
         for s in range(warmup):
             fn(s)
+        if world > 1:
+            gather_all()                                 # warm the gather path too
         sync_all()
         if sampler:
             sampler.mark(True)
@@ -264,6 +308,8 @@ def run_b200(args):
         for s in range(steps):
             last = fn(warmup + s)
         e1.record(stream)
+        if world > 1:
+            gather_all()
         sync_all()
         wall = time.perf_counter() - t0
         if sampler:
@@ -276,8 +322,10 @@ def run_b200(args):
         return dev_s, wall, launches, clocks, last
 
     dev_s, wall_s, launches, clocks, _ = timed(step_device, args.steps, args.warmup)
-    t_dev = max(dev_s, 1e-9) if world == 1 else wall_s        # multi-rank steps include the host-side gather
+    t_dev = max(dev_s, 1e-9) if world == 1 else wall_s        # multi-rank runs end with the gather to rank 0
+    eng.refine_stats(reset=True)
     e_dev_s, e_wall_s, _, _, n_regions = timed(step_host, args.steps, max(1, args.warmup // 2))
+    refine = eng.refine_stats()
     _, e16_wall_s, _, _, n_regions16 = timed(lambda s: step_host(s, pinned16), args.steps, max(1, args.warmup // 2))
 
     def max_over_ranks(x):
@@ -294,6 +342,47 @@ def run_b200(args):
     value = hours / t_dev
     e2e = hours / t_e2e
     e2e16 = hours / t_e2e16
+
+    # ---- from wav files (the real config 2 / 3 job): `corpus_files` PCM_16 wavs in tmpfs, sharded per file over the
+    # ranks, read + parsed + uploaded + detected by softspoken_b200.corpus.detect_corpus, ONE gather at the end
+    files_line = None
+    n_files = args.corpus_files if args.corpus_files >= 0 else 8 * world
+    if n_files > 0:
+        root = os.path.join(args.corpus_dir, f"ss_bench_{os.getuid()}")
+        t_w = time.perf_counter()
+        if rank == 0:
+            files = write_corpus(pool16, n_files, root, args.corpus_distinct)
+        sync_all()
+        if rank != 0:
+            files = [os.path.join(root, f"clip_{i:05d}.wav") for i in range(n_files)]
+        t_w = time.perf_counter() - t_w
+        durations = [CLIP_S] * n_files
+        stats: dict = {}
+        load = lambda path: corpus.load_native_22050(path, eng)
+        corpus.detect_corpus(files[:2 * world], eng.detect_host_batch, load=load, durations=durations[:2 * world],
+                             device=device, group_size=args.corpus_group)      # warm-up: page cache, reader thread
+        sync_all()
+        t0 = time.perf_counter()
+        rows = corpus.detect_corpus(files, eng.detect_host_batch, load=load, durations=durations, device=device,
+                                    group_size=args.corpus_group, stats=stats)
+        if rank == 0:
+            text = corpus.csv_text(rows)
+        t_files = max_over_ranks(time.perf_counter() - t0)
+        if rank == 0:
+            import hashlib
+            files_line = {"value": n_files * CLIP_S / 3600.0 / t_files, "unit": "audio-hours/s", "files": n_files,
+                          "seconds": t_files, "x_realtime": n_files * CLIP_S / t_files,
+                          "storage": f"{args.corpus_dir} ({'distinct copies' if args.corpus_distinct else 'hard links'} of "
+                                     f"{args.pool} PCM_16 clips, 26.5 MB each)",
+                          "rank0_split_s": {k: round(v, 4) for k, v in stats.items()},
+                          "rows": len(rows), "csv_sha1": hashlib.sha1(text.encode()).hexdigest(),
+                          "corpus_write_s": round(t_w, 2), "group_size": args.corpus_group,
+                          "what": "wall clock of softspoken_b200.corpus.detect_corpus: file read + RIFF parse + int16 "
+                                  "upload + detect + one gather + row building + CSV text; max over ranks"}
+        sync_all()
+        if rank == 0 and not args.keep_corpus:
+            import shutil
+            shutil.rmtree(root, ignore_errors=True)
 
     # ---- per-kernel-family times for the roofline: one clip's 1,005 windows, CUDA events on torch's stream
     pk = peaks()
@@ -315,7 +404,7 @@ def run_b200(args):
 
     t_feat = ev_time(lambda: eng.features(padded, starts), 5)
     mel = eng.features(padded, starts)
-    t_cls = ev_time(lambda: eng.classify(mel, mode=args.mode), 2)
+    t_cls = ev_time(lambda: eng.classify(mel, mode=args.mode), 3)
     achieved_tf = FLOP_PER_WINDOW_MASK * WINDOWS_PER_CLIP / t_cls / 1e12
     achieved_gbs = FEATURE_BYTES_PER_CLIP / t_feat / 1e9
     other_modes = {}
@@ -325,9 +414,12 @@ def run_b200(args):
                 t_m = ev_time(lambda: eng.classify(mel, mode=m), 2)
                 other_modes[m] = {"ms_per_clip": 1e3 * t_m, "tflops": FLOP_PER_WINDOW_MASK * WINDOWS_PER_CLIP / t_m / 1e12,
                                   "frac": FLOP_PER_WINDOW_MASK * WINDOWS_PER_CLIP / t_m / 1e12 / pk["tflops_sustained"]}
+    bad_guard_bytes = eng.check_guards()
 
     line = None
     if rank == 0:
+        tr_cls, tr_cls_src = measured_traffic(args.mode, "classifier")
+        tr_feat, tr_feat_src = measured_traffic(args.mode, "features")
         line = {
             "metric": "audio_hours_per_sec", "value": value, "unit": "audio-hours/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_dev / args.steps,
@@ -335,8 +427,12 @@ def run_b200(args):
             "dtype": {"fp32": "f32", "bf16": "bf16", "f16": "f16", "f16x3": "f16x3 (fp16 hi/lo split operands, fp32 accumulate)"}[args.mode],
             "data": "synthetic",
             "config": {"workload": f"config2: 1000x10-min mono 22.05 kHz corpus, step = {C} clip(s)/GPU "
-                                   f"({C * WINDOWS_PER_CLIP} windows) through pad+features+classifier+average+regions",
+                                   f"({C * WINDOWS_PER_CLIP} windows) through pad+features+classifier+average+regions"
+                                   + ("; config3: files sharded per rank, one gather of the detections to rank 0 inside "
+                                      "the timed region" if world > 1 else ""),
                        "classifier_mode": args.mode, "clips_per_step_per_gpu": C, "pool_clips": len(pool),
+                       "pool": "synth.synth_pcm16(600 s, seed): seeds 0.. on rank 0 — clips 0 and 1 are the clips of "
+                               "tests/golden/scale_clip_seed{0,1}.npz (reference results frozen)",
                        "l2": f"inputs larger than L2: pool of {len(pool)} clips x 53 MB rotates; "
                              "classifier activations stream through a per-batch workspace",
                        "max_batch_windows": args.max_batch, "parallelism": f"files sharded over {world} GPU(s)"},
@@ -348,21 +444,27 @@ def run_b200(args):
             "e2e_pcm16": {"value": e2e16, "unit": "audio-hours/s", "h2d_bytes_per_step": C * n * 2,
                           "d2h_bytes_per_step": int(C * 4 + (n_regions16 or 0) * 8), "x_realtime": e2e16 * 3600.0,
                           "same_regions_as_float32": bool(n_regions16 == n_regions)},
+            "e2e_files": files_line,
+            "refinement": {"eps": args.refine_eps if args.refine_eps is not None else 0.0, "mode": "fp32",
+                           "windows": refine["windows"], "windows_refined": refine["windows_refined"],
+                           "note": "margin-guided fp32 re-classification (ss_ctx_set_refine); off by default since "
+                                   "the split-K sub-accumulation put f16x3 logits in the reference's own noise class "
+                                   "(profiles/r2_scale_parity.json)"},
+            "guard_bytes_overwritten": int(bad_guard_bytes),
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "tensor", "kernel": "classifier (conv stack, ss_classify)", "achieved": achieved_tf,
                          "peak": pk["tflops_sustained"], "unit": "TFLOP/s", "frac": achieved_tf / pk["tflops_sustained"],
                          "frac_of_burst_peak": achieved_tf / pk["tflops_burst"],
-                         "traffic": CLASSIFIER_DRAM_BYTES_PER_WINDOW.get(args.mode, 0) * WINDOWS_PER_CLIP or None,
-                         "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum over the classifier launches of "
-                                           "profiles/r1_launches_f16x3_metrics.csv, per window x 1005",
+                         "traffic": (tr_cls * WINDOWS_PER_CLIP) if tr_cls else None, "traffic_source": tr_cls_src,
                          "peak_source": pk["source"], "ms_per_clip": 1e3 * t_cls,
                          "executed_mma_flops_factor": 3 if args.mode == "f16x3" else 1,
                          "single_pass_modes": other_modes,
                          "algorithmic_flops_per_launch_group": FLOP_PER_WINDOW_MASK * WINDOWS_PER_CLIP},
             "roofline_features": {"bound": "hbm", "kernel": "features_kernel (K1)", "achieved": achieved_gbs,
                                   "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": achieved_gbs / pk["hbm_gbs"],
-                                  "traffic": None, "peak_source": pk["source"], "ms_per_clip": 1e3 * t_feat,
+                                  "traffic": (tr_feat * WINDOWS_PER_CLIP) if tr_feat else None,
+                                  "traffic_source": tr_feat_src, "peak_source": pk["source"], "ms_per_clip": 1e3 * t_feat,
                                   "algorithmic_bytes_per_launch": FEATURE_BYTES_PER_CLIP},
         }
         if world == 1 and not args.no_cpu_baseline:
@@ -370,7 +472,9 @@ def run_b200(args):
             v, nwin, dt = cpu_detector_sample(sd, args.cpu_seconds, threads)
             line["cpu_baseline"] = {"value": v, "unit": "audio-hours/s", "cores": threads, "kind": "port",
                                     "sample": f"{nwin} windows (batches of 32) of one 10-min clip in {dt:.1f} s, "
-                                              "oracle port of the reference CPU detector incl. spec head"}
+                                              "oracle port of the reference CPU detector incl. spec head",
+                                    "port_vs_real_reference": "profiles/r2_reference_vs_port.json (build container: the "
+                                                              "real NNDetector.process_batch timed beside the port)"}
             if threads >= 2:
                 # the reference itself runs on half the cores (settings.py:32, NNDetector.py:25): a short second sample
                 vh, nh, dth = cpu_detector_sample(sd, args.cpu_seconds / 3.0, threads // 2)
@@ -395,6 +499,13 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--ref-step-seconds", type=float, default=10.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--refine-eps", type=float, default=None, help="margin-guided refinement (ss_ctx_set_refine); default: library default")
+    ap.add_argument("--corpus-files", type=int, default=-1,
+                    help="wav files of the from-files leg (e2e_files); -1 = 8 per GPU, 0 = skip, 1000 = the real config 3")
+    ap.add_argument("--corpus-dir", default="/dev/shm")
+    ap.add_argument("--corpus-distinct", action="store_true", help="full copies instead of hard links")
+    ap.add_argument("--corpus-group", type=int, default=4)
+    ap.add_argument("--keep-corpus", action="store_true")
     ap.add_argument("--no-other-modes", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

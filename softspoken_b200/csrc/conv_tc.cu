@@ -548,10 +548,14 @@ int launch_conv_npg(TcJob job, int B, cudaStream_t st) {
   static const int debug = [] { const char* e = getenv("SS_TC_DEBUG"); return e ? atoi(e) : 0; }();
   p.debug = debug;
   const size_t smem = (size_t)stages * stride + kSmemTail;
+  constexpr bool kCanSub = PrecTraits<P>::split && G == 1;
   static bool configured = false;
   if (!configured) {
-    SS_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<N, P, Dual, G>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    SS_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<N, P, Dual, G, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)kSmemBudget));
+    if constexpr (kCanSub)
+      SS_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<N, P, Dual, G, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)kSmemBudget));
     configured = true;
   }
   const int positions = p.H * (p.W + 2) - 2;          // (1,1) .. (H,W) in flattened padded coordinates
@@ -561,19 +565,52 @@ int launch_conv_npg(TcJob job, int B, cudaStream_t st) {
     SS_REQUIRE(job.c[ph].relu == 1, SS_E_ARG, "conv_tc_kernel applies ReLU unconditionally");
   // Split-K sub-accumulation (TcConv::n_sub): the K-chunks of the 3x3 sources are cut into groups so that an MMA
   // chain covers 9 taps x a few chunks (+ its share of the 1x1 residual chunks) instead of 9 C_in / 16.  Every group
-  // costs a TMEM buffer turn (drain by the epilogue warps, barrier round trip), which the small-resolution layers
-  // (<= 32 x 64: a fifth of the time) hide easily and the full-resolution ones less so: one chunk per group in the
-  // deep layers (SS_TC_SUB_DEEP caps the groups), at most SS_TC_SUB groups in the layers at 64 x 128 and above.
-  static const int sub_big = [] { const char* e = getenv("SS_TC_SUB"); return e ? atoi(e) : 4; }();
+  // costs a TMEM buffer turn (drain by the epilogue warps, barrier round trip).  Measured (tools/sub_sweep.sh,
+  // profiles/r2_sub_accumulation.txt): the logit error falls from 2.6e-5 to 5.5e-6 of float64 truth — the reference's
+  // own float32 sits at 4.4e-6 — with one chunk per group in the layers at 32 x 64 and below alone (their chains
+  // are the long ones: up to 144 x 3 MMAs), for +8 % of classifier time; groups in the layers at 64 x 128 and above
+  // (chains of 18-72) buy nothing measurable for another +12 %.  Hence: SS_TC_SUB_DEEP groups (default: every chunk)
+  // in the deep layers, SS_TC_SUB (default 1: the plain kernel) in the big ones.
+  static const int sub_big = [] { const char* e = getenv("SS_TC_SUB"); return e ? atoi(e) : 1; }();
   static const int sub_deep = [] { const char* e = getenv("SS_TC_SUB_DEEP"); return e ? atoi(e) : 16; }();
   for (int ph = 0; ph < job.n_phase; ++ph) {
     int most = 1;
     for (int i = 0; i < job.c[ph].n_src; ++i)
       if (job.c[ph].src[i].taps == 9 && job.c[ph].src[i].n_chunks > most) most = job.c[ph].src[i].n_chunks;
-    const bool sub_ok = PrecTraits<P>::split && G == 1;
     int cap = (p.H >= 64) ? sub_big : sub_deep;
     if (cap < 1) cap = 1;
-    job.c[ph].n_sub = sub_ok ? (most < cap ? most : cap) : 1;
+    job.c[ph].n_sub = kCanSub ? (most < cap ? most : cap) : 1;
+  }
+  bool any_sub = false;
+  for (int ph = 0; ph < job.n_phase; ++ph) any_sub |= job.c[ph].n_sub > 1;
+  // Stage program of a unit (TcJob::prog): accumulation group by accumulation group, source by source, the chunks of
+  // the group (a source's n chunks are dealt out n / n_sub per group, one more to the first n % n_sub), `cps` chunks
+  // of a 1x1 source per stage.  Every group holds at least one chunk of the widest 3x3 source (n_sub <= its chunks);
+  // in the dual layout sources come in (kind 1, kind 2) pairs with equal chunk counts, so a group always starts with
+  // a kind-1 stage, whose first MMA initialises both column groups.
+  for (int ph = 0; ph < job.n_phase; ++ph) {
+    const TcConv& c = job.c[ph];
+    int len = 0;
+    for (int sub = 0; sub < c.n_sub; ++sub) {
+      const int first_of_group = len;
+      for (int si = 0; si < c.n_src; ++si) {
+        const TcSource& src = c.src[si];
+        const int q = src.n_chunks / c.n_sub, r = src.n_chunks % c.n_sub;
+        const int lo = sub * q + (sub < r ? sub : r), hi = lo + q + (sub < r ? 1 : 0);
+        const int per_stage = (src.taps == 1) ? p.cps : 1;
+        for (int kc = lo; kc < hi; kc += per_stage) {
+          const int n = (hi - kc < per_stage) ? (hi - kc) : per_stage;
+          SS_REQUIRE(len < kMaxProg && kc < 64 && n < 8 && si < 8, SS_E_ARG, "conv stage program too long (%d stages)", len);
+          job.prog[ph][len] = prog_entry(si, kc, n, len == first_of_group, false, src.taps == 9, src.kind);
+          ++len;
+        }
+      }
+      SS_REQUIRE(len > first_of_group, SS_E_ARG, "empty accumulation group %d of %d", sub, c.n_sub);
+      SS_REQUIRE(!Dual || ((job.prog[ph][first_of_group] >> 15) & 3u) == 1u, SS_E_ARG,
+                 "dual layout: accumulation group %d does not start with a dual source", sub);
+      job.prog[ph][len - 1] |= 1u << 13;
+    }
+    job.prog_len[ph] = len;
   }
   const int items = p.total_units * job.n_phase;
   const int grid = items < kNumSMs ? items : kNumSMs;
@@ -602,7 +639,12 @@ int launch_conv_npg(TcJob job, int B, cudaStream_t st) {
     for (int i = 0; i < job.c[0].n_src; ++i)
       if (job.c[0].src[i].ring < 0) job.c[0].src[i].ring = 0;
   }
-  conv_tc_kernel<N, P, Dual, G><<<grid, kTcThreads, smem, st>>>(job);
+  if constexpr (kCanSub) {
+    if (any_sub) conv_tc_kernel<N, P, Dual, G, true><<<grid, kTcThreads, smem, st>>>(job);
+    else conv_tc_kernel<N, P, Dual, G, false><<<grid, kTcThreads, smem, st>>>(job);
+  } else {
+    conv_tc_kernel<N, P, Dual, G, false><<<grid, kTcThreads, smem, st>>>(job);
+  }
   SS_CUDA_CHECK(cudaGetLastError());
   count_launch();
   return SS_OK;

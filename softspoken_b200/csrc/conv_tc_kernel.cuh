@@ -54,10 +54,7 @@ constexpr uint32_t kSpinLimit = 1u << 22;
 #define SS_TC_DEBUG_HOOKS 0
 #endif
 constexpr bool kDebugHooks = SS_TC_DEBUG_HOOKS != 0;
-// -DSS_TC_SUBACC=0 builds the split-precision kernels without the split-K sub-accumulation path (A/B timing only)
-#ifndef SS_TC_SUBACC
-#define SS_TC_SUBACC 1
-#endif
+
 
 enum class Prec : int { Bf16 = 0, F16 = 1, F16x3 = 2 };
 
@@ -301,8 +298,21 @@ struct TcConv {
 // the launch has one tail instead of two.  Every item depends only on items with a smaller index and CTAs take
 // their items in increasing order, so the lowest unfinished item can always run: no deadlock while all CTAs are
 // resident (grid <= SM count, one CTA per SM); all waits are bounded and flag p.err instead of hanging.
+// One staged K-step of a unit ("stage program", built by the host: launch_conv_npg).  The producer and the MMA
+// issuers walk the same flat list instead of nested sub-item / source / chunk loops: the MMA-issuing thread's
+// bookkeeping between two bursts of MMAs is a tensor-pipe bubble, so it is one table look-up per stage.
+//   bits 0-2 source | 3-8 first chunk | 9-11 chunks in the stage | 12 first stage of an accumulation group
+//   | 13 last stage of the group | 14 the source is 3x3 | 15-16 source kind
+constexpr int kMaxProg = 96;
+__host__ __device__ constexpr uint32_t prog_entry(int src, int kc, int n, bool first, bool last, bool taps9, int kind) {
+  return (uint32_t)src | ((uint32_t)kc << 3) | ((uint32_t)n << 9) | ((uint32_t)first << 12) | ((uint32_t)last << 13) |
+         ((uint32_t)taps9 << 14) | ((uint32_t)kind << 15);
+}
+
 struct TcJob {
   TcConv c[2];
+  uint32_t prog[2][kMaxProg];   // stage program of a unit of each phase
+  int prog_len[2];
   int n_phase;
   int lag;             // units by which c[1] trails c[0]
   int* flags;          // [total_units], zeroed before the launch (fused launches only)
@@ -317,12 +327,6 @@ struct TcJob {
   int ring_request;    // host-side wish (images); the launcher derives `ring` from it
   int* flags2;         // [total_units], zeroed before the launch
 };
-
-// chunk range [lo, hi) of a source with n chunks inside sub-item j of n_sub
-__device__ __forceinline__ void sub_range(int n, int j, int n_sub, int& lo, int& hi) {
-  lo = (j * n) / n_sub;
-  hi = ((j + 1) * n) / n_sub;
-}
 
 // item -> (phase, unit) of the interleaved schedule above (T units per phase, D = min(lag, T))
 __device__ __forceinline__ void decode_item(int i, int T, int D, int n_phase, int& phase, int& unit) {
@@ -390,7 +394,9 @@ __device__ __forceinline__ void issue_group(uint32_t d0, uint32_t a_lo0, uint32_
   }
 }
 
-template <int N, Prec P, bool Dual, int G>
+// Sub: the split-K sub-accumulation path (TcConv::n_sub > 1) is compiled in — a separate instantiation, because
+// keeping a unit's sums in registers across buffer turns costs the plain single-chain launches 7 % (measured).
+template <int N, Prec P, bool Dual, int G, bool Sub = false>
 __global__ void __launch_bounds__(kTcThreads, 1)
 conv_tc_kernel(const TcJob job) {
   extern __shared__ __align__(128) unsigned char smem[];
@@ -406,7 +412,8 @@ conv_tc_kernel(const TcJob job) {
   constexpr int MT = TilesPerUnit<N, Dual>::value;
   constexpr int TS = TilesPerUnit<N, Dual>::TS;
   constexpr bool kSplit = PrecTraits<P>::split;
-  constexpr bool kSubAcc = kSplit && G == 1 && SS_TC_SUBACC != 0;   // split-K sub-accumulation (TcConv::n_sub) is compiled in
+  constexpr bool kSubAcc = Sub;
+  static_assert(!Sub || (kSplit && G == 1), "sub-accumulation belongs to the split precision, one group per unit");
   constexpr int kWpartsMax = Dual ? 2 : 1;   // weight rows per tap and K-half staged per chunk, in units of N
   const int dbg = kDebugHooks ? p.debug : 0;
   const int Wp = p.W + 2, Hp = p.H + 2;
@@ -484,48 +491,44 @@ conv_tc_kernel(const TcJob job) {
         if (!ok) break;
         asm volatile("fence.proxy.async.global;" ::: "memory");
       }
-      const int n_sub = kSubAcc ? c.n_sub : 1;
-      for (int sub = 0; sub < n_sub && ok; ++sub)
-      for (int s = 0; s < c.n_src && ok; ++s) {
-        const TcSource& src = c.src[s];
-        const uint32_t w_bytes = (uint32_t)((Dual && src.kind == 1 ? 2 : 1) * src.taps) * N * 32u;
-        // A 1x1 source has no halo and a ninth of the weights, so a stage-sized slot takes `cps` of its K-chunks:
-        // [chunk][plane][run1] activations, then [chunk] weights at w1_off.  (One chunk per stage left these
-        // sources bound by the per-stage hand-over and by load latency: 4 MMAs per 18 KB stage.)
-        const int per_stage = (src.taps == 1) ? cps : 1;
-        int kc_lo, kc_hi;
-        sub_range(src.n_chunks, sub, n_sub, kc_lo, kc_hi);
-        for (int kc = kc_lo; kc < kc_hi; kc += per_stage, ++it) {
-          const int st = it % S;
-          const uint32_t ph = (uint32_t)(it / S) & 1u;
-          ok = mbar_wait_t<true>(empty0 + 8 * st, ph ^ 1u, p.err, 1, w_empty);
-          if (!ok) break;
-          const uint32_t dst = smem_u32(stage0 + (size_t)st * stage_sz);
-          const int bs = src.ring ? b % src.ring : b;
-          const uint16_t* plane = src.in + (((int64_t)bs * src.planes_total + src.plane0 + 2 * kc) * HpWp + lo) * 8;
-          if (dbg & 1) {
-            if (elect_one()) mbar_arrive(full0 + 8 * st);
-          } else if (src.taps == 1) {
-            const int n = (kc_hi - kc < per_stage) ? (kc_hi - kc) : per_stage;
-            if (elect_one()) {
-              mbar_expect_tx(full0 + 8 * st, (uint32_t)n * (2u * run1 + w_bytes));
-              for (int j = 0; j < n; ++j) {
-                const uint16_t* pj = plane + (int64_t)2 * j * HpWp * 8 + (int64_t)halo * 8;    // centre tap only
-                bulk_g2s(dst + (uint32_t)(2 * j) * run1, pj, run1, full0 + 8 * st);
-                bulk_g2s(dst + (uint32_t)(2 * j + 1) * run1, pj + (int64_t)HpWp * 8, run1, full0 + 8 * st);
-                bulk_g2s(dst + w1_off + (uint32_t)j * w_bytes, src.w + (int64_t)(kc + j) * src.w_stride, w_bytes,
-                         full0 + 8 * st);
-              }
+      const int n_prog = job.prog_len[phase];
+      for (int pi = 0; pi < n_prog && ok; ++pi, ++it) {
+        const uint32_t e = job.prog[phase][pi];
+        const TcSource& src = c.src[e & 7u];
+        const int kc = (int)((e >> 3) & 63u), n = (int)((e >> 9) & 7u);
+        const bool taps9 = (e >> 14) & 1u;
+        const uint32_t w_bytes = (uint32_t)((Dual && ((e >> 15) & 3u) == 1u ? 2 : 1) * (taps9 ? 9 : 1)) * N * 32u;
+        const int st = it % S;
+        const uint32_t ph = (uint32_t)(it / S) & 1u;
+        ok = mbar_wait_t<true>(empty0 + 8 * st, ph ^ 1u, p.err, 1, w_empty);
+        if (!ok) break;
+        const uint32_t dst = smem_u32(stage0 + (size_t)st * stage_sz);
+        const int bs = src.ring ? b % src.ring : b;
+        const uint16_t* plane = src.in + (((int64_t)bs * src.planes_total + src.plane0 + 2 * kc) * HpWp + lo) * 8;
+        if (dbg & 1) {
+          if (elect_one()) mbar_arrive(full0 + 8 * st);
+        } else if (!taps9) {
+          // A 1x1 source has no halo and a ninth of the weights, so a stage-sized slot takes up to `cps` of its
+          // K-chunks: [chunk][plane][run1] activations, then [chunk] weights at w1_off.  (One chunk per stage left
+          // these sources bound by the per-stage hand-over and by load latency: 4 MMAs per 18 KB stage.)
+          if (elect_one()) {
+            mbar_expect_tx(full0 + 8 * st, (uint32_t)n * (2u * run1 + w_bytes));
+            for (int j = 0; j < n; ++j) {
+              const uint16_t* pj = plane + (int64_t)2 * j * HpWp * 8 + (int64_t)halo * 8;    // centre tap only
+              bulk_g2s(dst + (uint32_t)(2 * j) * run1, pj, run1, full0 + 8 * st);
+              bulk_g2s(dst + (uint32_t)(2 * j + 1) * run1, pj + (int64_t)HpWp * 8, run1, full0 + 8 * st);
+              bulk_g2s(dst + w1_off + (uint32_t)j * w_bytes, src.w + (int64_t)(kc + j) * src.w_stride, w_bytes,
+                       full0 + 8 * st);
             }
-          } else if (elect_one()) {
-            const uint32_t run = (uint32_t)L * 16u;
-            mbar_expect_tx(full0 + 8 * st, 2u * run + w_bytes);
-            bulk_g2s(dst, plane, run, full0 + 8 * st);
-            bulk_g2s(dst + run, plane + (int64_t)HpWp * 8, run, full0 + 8 * st);
-            bulk_g2s(dst + a_bytes, src.w + (int64_t)kc * src.w_stride, w_bytes, full0 + 8 * st);
           }
-          __syncwarp();
+        } else if (elect_one()) {
+          const uint32_t run = (uint32_t)L * 16u;
+          mbar_expect_tx(full0 + 8 * st, 2u * run + w_bytes);
+          bulk_g2s(dst, plane, run, full0 + 8 * st);
+          bulk_g2s(dst + run, plane + (int64_t)HpWp * 8, run, full0 + 8 * st);
+          bulk_g2s(dst + a_bytes, src.w + (int64_t)kc * src.w_stride, w_bytes, full0 + 8 * st);
         }
+        __syncwarp();
       }
     }
     if (p.prof && lane == 0) p.prof[blockIdx.x * 8 + 0] = w_empty;
@@ -559,74 +562,65 @@ conv_tc_kernel(const TcJob job) {
     for (int item; (item = item_of(k)) < n_items && ok; ++k) {
       int phase, u;
       decode_item(item, T, D, n_phase, phase, u);
-      const TcConv& c = job.c[phase];
-      const int n_sub = kSubAcc ? c.n_sub : 1;
       const uint32_t a_tile0 = (uint32_t)((G == 1 ? me * MTW : me * MT) * 128);     // first position of my tiles
-     for (int sub = 0; sub < n_sub && ok; ++sub, ++kk) {
-      // K-chunks of this accumulation group, to recognise the last one
-      int chunks_per_unit = 0;
-      for (int s = 0; s < c.n_src; ++s) {
-        int lo_s, hi_s;
-        sub_range(c.src[s].n_chunks, sub, n_sub, lo_s, hi_s);
-        chunks_per_unit += hi_s - lo_s;
-      }
-      // G = 1: this turn owns buffer kk & 1 (tiles split between the warps); G = 2: warp `me` owns buffer `me`
-      const int buf = (G == 1) ? (kk & 1) : me;
-      const uint32_t e_parity = (G == 1) ? ((((uint32_t)kk >> 1) & 1u) ^ 1u) : (((uint32_t)kk & 1u) ^ 1u);
-      const uint32_t d_unit = tmem_base + (uint32_t)(buf * kAccCols) + (G == 1 ? (uint32_t)(me * MTW * TS) : 0u);
-      int c_in_unit = 0;
-      for (int s = 0; s < c.n_src && ok; ++s) {
-        const TcSource& src = c.src[s];
+      const int n_prog = job.prog_len[phase];
+      int buf = 0;
+      uint32_t d_unit = 0u;
+      bool accumulate_next = false;
+      for (int pi = 0; pi < n_prog && ok; ++pi) {
+        const uint32_t e = job.prog[phase][pi];
+        const int n = (int)((e >> 9) & 7u);
+        const bool first = (e >> 12) & 1u, last = (e >> 13) & 1u, taps9 = (e >> 14) & 1u;
+        const uint32_t kind = (e >> 15) & 3u;
         // per-source MMA shape: the dual product writes 2N columns, a correction-only source the upper N
-        const bool dual_src = Dual && src.kind == 1;
+        const bool dual_src = Dual && kind == 1u;
         const uint32_t idesc = dual_src ? idesc_2n : idesc_n;
-        const uint32_t col0 = (Dual && src.kind == 2) ? (uint32_t)N : 0u;
+        const uint32_t col0 = (Dual && kind == 2u) ? (uint32_t)N : 0u;
         const uint32_t b_lo_base = ((uint32_t)(dual_src ? 2 * N : N) & 0x3FFFu) << 16;   // LBO = rows * 16 bytes
-        const int taps = src.taps;
-        const int per_stage = (taps == 1) ? cps : 1;
-        const uint32_t w_bytes16 = (uint32_t)((dual_src ? 2 : 1) * N * 2);             // 1x1 chunk weights >> 4
-        int kc_lo, kc_hi;
-        sub_range(src.n_chunks, sub, n_sub, kc_lo, kc_hi);
-        for (int kc = kc_lo; kc < kc_hi && ok; kc += per_stage) {
-          const int n = (kc_hi - kc < per_stage) ? (kc_hi - kc) : per_stage;
-          if (!ready && !(dbg & 4)) ok = mbar_wait_fast(full0 + 8 * st, ph, p.err, 2, timing, w_full);
+        if (!ready && !(dbg & 4)) ok = mbar_wait_fast(full0 + 8 * st, ph, p.err, 2, timing, w_full);
+        if (!ok) break;
+        if (first) {
+          // a new accumulation group takes the next TMEM buffer turn (G = 1: buffer kk & 1, tiles split between the
+          // warps; G = 2: warp `me` owns buffer `me`); the epilogue must have drained it
+          buf = (G == 1) ? (kk & 1) : me;
+          const uint32_t e_parity = (G == 1) ? ((((uint32_t)kk >> 1) & 1u) ^ 1u) : (((uint32_t)kk & 1u) ^ 1u);
+          d_unit = tmem_base + (uint32_t)(buf * kAccCols) + (G == 1 ? (uint32_t)(me * MTW * TS) : 0u);
+          ++kk;
+          accumulate_next = false;
+          ok = mbar_wait_fast(acce0 + 8 * buf, e_parity, p.err, 4, timing, w_acce);
           if (!ok) break;
-          if (c_in_unit == 0) {                            // the epilogue must have drained the buffer
-            ok = mbar_wait_fast(acce0 + 8 * buf, e_parity, p.err, 4, timing, w_acce);
-            if (!ok) break;
-          }
-          tc_fence_after();
-          if (leader) {
-            if (dbg & 8) { if (a0 == 0xdeadbeefu) p.err[1] = (int)(d_unit + idesc); }   // issue nothing
-            else if (taps == 1) {
-              // compact 1x1 stage: chunk j at a0 + 2 j run1 (plane stride run1), its weights at a0 + w1_off + j w_bytes
-              const uint32_t a1 = (a1_lo_base | (a0 >> 4)) + a_tile0;
-              const uint32_t b1 = b_lo_base | ((a0 + w1_off) >> 4);
-              for (int j = 0; j < n; ++j) {
-                const uint32_t accumulate = (c_in_unit + j) > 0 ? 1u : 0u;
-                const uint32_t aj = a1 + (uint32_t)j * (2u * run1 >> 4), bj = b1 + (uint32_t)j * w_bytes16;
-                if (dual_src) issue_group<MTW, TS, 2 * N>(d_unit + col0, aj, bj, idesc, 1, tap_off, accumulate);
-                else issue_group<MTW, TS, N>(d_unit + col0, aj, bj, idesc, 1, tap_off, accumulate);
-              }
-            } else {
-              const uint32_t accumulate = c_in_unit > 0 ? 1u : 0u;
-              const uint32_t a_lo0 = (a_lo_base | ((a0 >> 4) + (uint32_t)halo)) + a_tile0;   // centre tap, my first tile
-              const uint32_t b_lo0 = b_lo_base | ((a0 + a_bytes) >> 4);
-              if (dual_src) issue_group<MTW, TS, 2 * N>(d_unit + col0, a_lo0, b_lo0, idesc, 9, tap_off, accumulate);
-              else issue_group<MTW, TS, N>(d_unit + col0, a_lo0, b_lo0, idesc, 9, tap_off, accumulate);
-            }
-            if (c_in_unit + n == chunks_per_unit) tc_commit(accf0 + 8 * buf);   // my tiles of this group are complete
-            if (!(dbg & 4)) tc_commit(empty0 + 8 * st);   // my reads of the stage retire with these MMAs
-          }
-          __syncwarp();
-          c_in_unit += n;
-          a0 += stage_sz;
-          if (++st == S) { st = 0; ph ^= 1u; a0 = stage_base; }
-          // probe the next stage now: the answer travels while this iteration winds down
-          ready = !(dbg & 4) && mbar_try_wait(full0 + 8 * st, ph);
         }
+        tc_fence_after();
+        if (leader) {
+          if (dbg & 8) { if (a0 == 0xdeadbeefu) p.err[1] = (int)(d_unit + idesc); }   // issue nothing
+          else if (!taps9) {
+            // compact 1x1 stage: chunk j at a0 + 2 j run1 (plane stride run1), its weights at a0 + w1_off + j w_bytes
+            const uint32_t w_bytes16 = (uint32_t)((dual_src ? 2 : 1) * N * 2);             // 1x1 chunk weights >> 4
+            const uint32_t a1 = (a1_lo_base | (a0 >> 4)) + a_tile0;
+            const uint32_t b1 = b_lo_base | ((a0 + w1_off) >> 4);
+            for (int j = 0; j < n; ++j) {
+              const uint32_t accumulate = (accumulate_next || j > 0) ? 1u : 0u;
+              const uint32_t aj = a1 + (uint32_t)j * (2u * run1 >> 4), bj = b1 + (uint32_t)j * w_bytes16;
+              if (dual_src) issue_group<MTW, TS, 2 * N>(d_unit + col0, aj, bj, idesc, 1, tap_off, accumulate);
+              else issue_group<MTW, TS, N>(d_unit + col0, aj, bj, idesc, 1, tap_off, accumulate);
+            }
+          } else {
+            const uint32_t accumulate = accumulate_next ? 1u : 0u;
+            const uint32_t a_lo0 = (a_lo_base | ((a0 >> 4) + (uint32_t)halo)) + a_tile0;   // centre tap, my first tile
+            const uint32_t b_lo0 = b_lo_base | ((a0 + a_bytes) >> 4);
+            if (dual_src) issue_group<MTW, TS, 2 * N>(d_unit + col0, a_lo0, b_lo0, idesc, 9, tap_off, accumulate);
+            else issue_group<MTW, TS, N>(d_unit + col0, a_lo0, b_lo0, idesc, 9, tap_off, accumulate);
+          }
+          if (last) tc_commit(accf0 + 8 * buf);         // my tiles of this accumulation group are complete
+          if (!(dbg & 4)) tc_commit(empty0 + 8 * st);   // my reads of the stage retire with these MMAs
+        }
+        __syncwarp();
+        accumulate_next = true;
+        a0 += stage_sz;
+        if (++st == S) { st = 0; ph ^= 1u; a0 = stage_base; }
+        // probe the next stage now: the answer travels while this iteration winds down
+        ready = !(dbg & 4) && mbar_try_wait(full0 + 8 * st, ph);
       }
-     }
     }
     __syncwarp();
     if (p.prof && lane == 0 && me == 0) {

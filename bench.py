@@ -363,10 +363,10 @@ def run_b200(args):
                              device=device, group_size=args.corpus_group)      # warm-up: page cache, reader thread
         sync_all()
         t0 = time.perf_counter()
-        rows = corpus.detect_corpus(files, eng.detect_host_batch, load=load, durations=durations, device=device,
-                                    group_size=args.corpus_group, stats=stats)
+        text = corpus.detect_corpus(files, eng.detect_host_batch, load=load, durations=durations, device=device,
+                                    group_size=args.corpus_group, stats=stats, as_csv=True)
         if rank == 0:
-            text = corpus.csv_text(rows)
+            rows = text.splitlines()[1:]
         t_files = max_over_ranks(time.perf_counter() - t0)
         if rank == 0:
             import hashlib

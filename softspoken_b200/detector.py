@@ -197,6 +197,28 @@ def plan_windows_from_duration(audio_len_seconds: float) -> np.ndarray:
     return np.arange(num_windows) * samples_per_step
 
 
+_ROW_TIMES = np.zeros(0, dtype=np.float64)      # _ROW_TIMES[idx] = float(bin_time_str(idx)) - 3, grown on demand
+
+
+def _row_times(idx: np.ndarray) -> np.ndarray:
+    """`float(f"{idx / (256 / 3):.4f}") - 3` per bin index: the string round trip of NNDetector.py:185 and the shift
+    of worker.py:100, evaluated by Python exactly as the reference does — once per distinct bin (a corpus of
+    10-minute clips asks for the same 51,661 bins a quarter of a million times)."""
+    global _ROW_TIMES
+    idx = np.asarray(idx, dtype=np.int64)
+    if idx.size == 0:
+        return np.zeros(0, dtype=np.float64)
+    top = int(idx.max()) + 1
+    if top > len(_ROW_TIMES):
+        if top - len(_ROW_TIMES) > 8 * idx.size + 65536:          # a few bins of a very long timeline: no table
+            return np.array([float(bin_time_str(int(j))) - 3 for j in idx], dtype=np.float64)
+        top = max(top, min(2 * len(_ROW_TIMES), 1 << 20))           # grow geometrically while the table is small
+        ext = np.array([float(bin_time_str(j)) - 3 for j in range(len(_ROW_TIMES), top)], dtype=np.float64)
+        _ROW_TIMES = np.concatenate([_ROW_TIMES, ext])
+    return _ROW_TIMES[idx]
+
+
 def region_bins_to_times(bins: np.ndarray) -> List[Tuple[float, float]]:
     """(start_bin, end_bin) -> (float(start_str) - 3, float(end_str) - 3) (NNDetector.py:185; worker.py:100)."""
-    return [(float(bin_time_str(int(s))) - 3, float(bin_time_str(int(e))) - 3) for s, e in np.asarray(bins)]
+    b = np.asarray(bins, dtype=np.int64).reshape(-1, 2)
+    return list(zip(_row_times(b[:, 0]).tolist(), _row_times(b[:, 1]).tolist()))

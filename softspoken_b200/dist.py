@@ -71,9 +71,12 @@ def rows_from_triplets(files: Sequence[str], triplets: np.ndarray, next_id: int 
     from .worker import detection_rows
     rows: List[dict] = []
     # a file detected twice (e.g. by two runs that both journalled it) contributes its regions once
-    triplets = np.unique(np.asarray(triplets, dtype=np.int32).reshape(-1, 3), axis=0)
+    triplets = np.asarray(triplets, dtype=np.int32).reshape(-1, 3)
+    _, first = np.unique(triplets, axis=0, return_index=True)
+    triplets = _order(triplets[np.sort(first)])                  # first occurrences, in file order, regions as given
+    bounds = np.searchsorted(triplets[:, 0], np.arange(len(files) + 1))
     for fi in range(len(files)):
-        sel = triplets[triplets[:, 0] == fi][:, 1:3]
+        sel = triplets[bounds[fi]:bounds[fi + 1], 1:3]
         new = detection_rows(files[fi], region_bins_to_times(sel), next_id)
         next_id += len(new)
         rows += new

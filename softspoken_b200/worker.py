@@ -190,8 +190,9 @@ def next_detection_id(df: pd.DataFrame) -> int:
 def detection_rows(file: str, regions, next_id: int) -> List[dict]:
     """worker.py:103-124."""
     rows = []
+    file_path, file_name = dirname(file), basename(file)
     for (start_time, end_time) in regions:
-        rows.append({'ID': next_id, 'file_path': dirname(file), 'file_name': basename(file),
+        rows.append({'ID': next_id, 'file_path': file_path, 'file_name': file_name,
                      'start_time': start_time, 'end_time': end_time, 'erase': 0,
                      'user_comment': '', 'review_datetime': ''})
         next_id += 1

@@ -193,6 +193,12 @@ def _corpus_worker(rank, world, port, q, files, durations):
         return out
 
     rows = corpus.detect_corpus(files, fake_detect, load=fake_load, durations=durations, group_size=3)
+    if rank == 0:
+        # the direct text writer (no row dicts) prints the same bytes
+        text = corpus.detect_corpus(files, fake_detect, load=fake_load, durations=durations, group_size=3, as_csv=True)
+        assert text == corpus.csv_text(rows)
+    elif world > 1:
+        corpus.detect_corpus(files, fake_detect, load=fake_load, durations=durations, group_size=3, as_csv=True)
     q.put(corpus.csv_text(rows) if rank == 0 else (rows is None))
     if world > 1:
         dist.destroy_process_group()

@@ -1,8 +1,11 @@
 #!/bin/bash
-# Retry a gpurun call while the pod answers "busy" (exit code 3, nothing charged).  usage: gpurun_retry.sh <timeout> '<command>'
+# Retry a gpurun call while the pod answers "busy" (exit code 3, nothing charged).
+# usage: [GPUS=N] gpurun_retry.sh <timeout> '<command>'
 t=$1; shift
-for i in $(seq 1 40); do
-  /usr/local/graft/bin/gpurun --timeout "$t" -- "$@"
+extra=""
+if [ -n "$GPUS" ]; then extra="--gpus $GPUS"; fi
+for i in $(seq 1 60); do
+  /usr/local/graft/bin/gpurun $extra --timeout "$t" -- "$@"
   rc=$?
   if [ $rc -ne 3 ]; then exit $rc; fi
   sleep 45

@@ -199,6 +199,9 @@ def write_corpus(pool16, n_files: int, root: str, distinct: bool):
     import shutil
     from softspoken_b200 import wavio
     os.makedirs(root, exist_ok=True)
+    if distinct and shutil.disk_usage(root).free < (n_files + len(pool16) + 8) * (pool16[0].nbytes + 4096):
+        print(f"[bench] {root}: not enough room for {n_files} distinct files, using hard links", file=sys.stderr)
+        distinct = False
     base = []
     for c, pcm in enumerate(pool16):
         path = os.path.join(root, f"pool_{c}.wav")
@@ -214,7 +217,7 @@ def write_corpus(pool16, n_files: int, root: str, distinct: bool):
         else:
             os.link(base[i % len(base)], path)
         files.append(path)
-    return files
+    return files, distinct
 
 
 def run_b200(args):
@@ -351,7 +354,7 @@ def run_b200(args):
         root = os.path.join(args.corpus_dir, f"ss_bench_{os.getuid()}")
         t_w = time.perf_counter()
         if rank == 0:
-            files = write_corpus(pool16, n_files, root, args.corpus_distinct)
+            files, was_distinct = write_corpus(pool16, n_files, root, args.corpus_distinct)
         sync_all()
         if rank != 0:
             files = [os.path.join(root, f"clip_{i:05d}.wav") for i in range(n_files)]
@@ -368,14 +371,26 @@ def run_b200(args):
         if rank == 0:
             rows = text.splitlines()[1:]
         t_files = max_over_ranks(time.perf_counter() - t0)
+        one_rank_sha = None
+        if args.corpus_check_1rank and world > 1:
+            # the same list through ONE rank (rank 0; the others wait): the N-rank CSV must be byte-identical
+            if rank == 0:
+                import hashlib
+                t1 = time.perf_counter()
+                text1 = corpus.detect_corpus(files, eng.detect_host_batch, load=load, durations=durations, device=device,
+                                             group_size=args.corpus_group, as_csv=True, local_only=True)
+                one_rank_sha = {"csv_sha1": hashlib.sha1(text1.encode()).hexdigest(), "identical": text1 == text,
+                                "seconds": time.perf_counter() - t1}
+            sync_all()
         if rank == 0:
             import hashlib
             files_line = {"value": n_files * CLIP_S / 3600.0 / t_files, "unit": "audio-hours/s", "files": n_files,
                           "seconds": t_files, "x_realtime": n_files * CLIP_S / t_files,
-                          "storage": f"{args.corpus_dir} ({'distinct copies' if args.corpus_distinct else 'hard links'} of "
+                          "storage": f"{args.corpus_dir} ({'distinct copies' if was_distinct else 'hard links'} of "
                                      f"{args.pool} PCM_16 clips, 26.5 MB each)",
                           "rank0_split_s": {k: round(v, 4) for k, v in stats.items()},
                           "rows": len(rows), "csv_sha1": hashlib.sha1(text.encode()).hexdigest(),
+                          "one_rank_run_of_the_same_list": one_rank_sha,
                           "corpus_write_s": round(t_w, 2), "group_size": args.corpus_group,
                           "what": "wall clock of softspoken_b200.corpus.detect_corpus: file read + RIFF parse + int16 "
                                   "upload + detect + one gather + row building + CSV text; max over ranks"}
@@ -506,12 +521,21 @@ def main():
     ap.add_argument("--corpus-distinct", action="store_true", help="full copies instead of hard links")
     ap.add_argument("--corpus-group", type=int, default=4)
     ap.add_argument("--keep-corpus", action="store_true")
+    ap.add_argument("--corpus-check-1rank", action="store_true",
+                    help="N > 1: rank 0 also runs the whole list alone and compares the CSV text")
     ap.add_argument("--no-other-modes", action="store_true")
     args = ap.parse_args()
+    # stdout carries the ONE JSON line of the contract: whatever libraries print there meanwhile (NCCL announces its
+    # version on stdout) goes to stderr instead
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(real_stdout, "w")
     if args.impl == "reference":
         run_reference(args)
     else:
         run_b200(args)
+    sys.stdout.flush()
 
 
 if __name__ == "__main__":

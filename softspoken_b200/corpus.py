@@ -172,7 +172,7 @@ def detect_corpus(files: Sequence[str], detect_batch: Callable[[List[np.ndarray]
                   load: Callable[[str], np.ndarray] = load_mono_22050, durations: Optional[Sequence[float]] = None,
                   group_size: int = 8, device: Optional[torch.device] = None, next_id: int = 1,
                   journal: Optional[str] = None, prefetch: int = 2, stats: Optional[dict] = None,
-                  as_csv: bool = False):
+                  as_csv: bool = False, local_only: bool = False):
     """-> list of CSV row dicts on rank 0 (None on the other ranks); with `as_csv` the CSV text itself
     (`csv_text_from_triplets`: the same bytes without building a dict per row).
 
@@ -181,8 +181,8 @@ def detect_corpus(files: Sequence[str], detect_batch: Callable[[List[np.ndarray]
     per-rank progress files that make the run restartable (`Journal`).  `prefetch`: groups of files a reader
     thread decodes ahead of the GPU (0 = read in line, as the reference does).  `stats`: a dict that receives where
     this rank's wall time went (`wait_files_s`, `detect_s`, `gather_rows_s`)."""
-    world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
-    rank = dist.get_rank() if world > 1 else 0
+    world = dist.get_world_size() if dist.is_available() and dist.is_initialized() and not local_only else 1
+    rank = dist.get_rank() if world > 1 else 0          # local_only: this process does the whole list by itself
     if durations is None:
         durations = [wavio.duration_and_rate(f)[0] for f in files]
     jr = Journal(journal, files, rank) if journal else None
@@ -221,7 +221,7 @@ def detect_corpus(files: Sequence[str], detect_batch: Callable[[List[np.ndarray]
             jr.close()
     t_mark = time.perf_counter()
     local = np.concatenate(parts) if parts else np.zeros((0, 3), np.int32)
-    allrows = ssdist.gather_detections(local, device)
+    allrows = ssdist._order(local) if local_only else ssdist.gather_detections(local, device)
     if rank != 0:
         rows = None
     elif as_csv:

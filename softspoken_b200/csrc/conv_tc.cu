@@ -414,17 +414,20 @@ bool is_dual(Prec p, int n) { return is_split(p) && n <= 64; }
 // finite number in either 16-bit format.  The first and last staged runs of a launch read into the bands (halo
 // over-reads); those values only reach accumulators of border positions, which the epilogue forces to zero, or of
 // positions past the tensor, which it does not store.  Nothing may WRITE there: ss_debug_check_guards verifies it.
+// The tensor starts 16 bytes past a 32-byte boundary: the up-sampling epilogue writes every value to the position
+// pair (2x - 1, 2x) of two rows, and with that offset a pair is one aligned 32-byte store (conv_tc_kernel.cuh:st32x2).
 int alloc_guarded(ss_ctx* ctx, TcState* st, uint16_t** alloc, uint16_t** data, size_t body) {
-  const size_t bytes = body + 2 * (size_t)kGuardBytes;
+  const size_t inner = body + 32;           // 16 bytes of slack either side of the tensor
+  const size_t bytes = inner + 2 * (size_t)kGuardBytes;
   unsigned char* base = nullptr;
   SS_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&base), bytes));
   *alloc = reinterpret_cast<uint16_t*>(base);
   SS_CUDA_CHECK(cudaMemset(base, kGuardPattern, kGuardBytes));
-  SS_CUDA_CHECK(cudaMemset(base + kGuardBytes, 0, body));
-  SS_CUDA_CHECK(cudaMemset(base + kGuardBytes + body, kGuardPattern, kGuardBytes));
-  *data = reinterpret_cast<uint16_t*>(base + kGuardBytes);
+  SS_CUDA_CHECK(cudaMemset(base + kGuardBytes, 0, inner));
+  SS_CUDA_CHECK(cudaMemset(base + kGuardBytes + inner, kGuardPattern, kGuardBytes));
+  *data = reinterpret_cast<uint16_t*>(base + kGuardBytes + 16);
   register_guard(ctx, base, kGuardBytes, base);
-  register_guard(ctx, base + kGuardBytes + body, kGuardBytes, base);
+  register_guard(ctx, base + kGuardBytes + inner, kGuardBytes, base);
   st->bytes += bytes;
   return SS_OK;
 }
@@ -754,6 +757,8 @@ int tc_res_block(TcState* s, int which, const Tensor& x, int x_plane0, Tensor& o
   q.inv_scale = rb.inv_scale2;
   q.relu = 1;
   q.out = out.data; q.out_lo = out.lo; q.out_planes_total = out.planes; q.out_plane0 = out_plane0; q.upsample = upsample;
+  const char* pe = getenv("SS_TC_PAIR_STORE");
+  q.pair_store = pe ? atoi(pe) : 1;
   q.head_w = head_w; q.head_out = head_out;
   if (head_w && !store_out) { q.out = nullptr; q.out_lo = nullptr; }
   q.err = s->err;

@@ -202,6 +202,13 @@ __device__ __forceinline__ void st16(uint16_t* p, uint4 v) {
   *reinterpret_cast<uint4*>(p) = v;
 #endif
 }
+// The same 16-byte vector to two neighbouring positions as ONE 32-byte store (STG.256; p is 32-byte aligned, see
+// conv_tc.cu:alloc_guarded): the 2 x 2 replication of the up-sampling epilogue is two of these per row pair instead of
+// four 16-byte stores, each warp writing whole 32-byte sectors.
+__device__ __forceinline__ void st32x2(uint16_t* p, uint4 v) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
+               : "memory");
+}
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // One lane of a converged warp (the CUTLASS elect_one_sync idiom).  Keeping the role loops warp-uniform and
@@ -277,6 +284,7 @@ struct TcConv {
   // buffers alternate between sub-items exactly as they did between units) and the epilogue warps add the groups in
   // registers, in float32 round-to-nearest, before bias / ReLU.  n_sub = 1 is the plain single chain.
   int n_sub;
+  int pair_store;      // up-sampling epilogue: 1 = one 32-byte store per position pair (default), 0 = two 16-byte stores
   int stages;          // smem ring depth (<= kMaxStages)
   int cps;             // K-chunks a stage of a 1x1 source carries (>= 1; see the producer)
   int stage_stride;    // bytes per smem ring slot (>= the 3x3 stage; larger when that buys more 1x1 chunks per stage)
@@ -732,17 +740,27 @@ conv_tc_kernel(const TcJob job) {
             }
           } else if (interior) {
             uint16_t* o = c.out + plane_off + up * 8;
-            st16(o, ph);
-            st16(o + 8, ph);
-            st16(o + (int64_t)Wp2 * 8, ph);
-            st16(o + (int64_t)Wp2 * 8 + 8, ph);
+            if (c.pair_store) {
+              st32x2(o, ph);
+              st32x2(o + (int64_t)Wp2 * 8, ph);
+            } else {
+              st16(o, ph);
+              st16(o + 8, ph);
+              st16(o + (int64_t)Wp2 * 8, ph);
+              st16(o + (int64_t)Wp2 * 8 + 8, ph);
+            }
             if constexpr (kSplit) {
               const uint4 pl = make_uint4(lw[0], lw[1], lw[2], lw[3]);
               uint16_t* ol = c.out_lo + plane_off + up * 8;
-              st16(ol, pl);
-              st16(ol + 8, pl);
-              st16(ol + (int64_t)Wp2 * 8, pl);
-              st16(ol + (int64_t)Wp2 * 8 + 8, pl);
+              if (c.pair_store) {
+                st32x2(ol, pl);
+                st32x2(ol + (int64_t)Wp2 * 8, pl);
+              } else {
+                st16(ol, pl);
+                st16(ol + 8, pl);
+                st16(ol + (int64_t)Wp2 * 8, pl);
+                st16(ol + (int64_t)Wp2 * 8 + 8, pl);
+              }
             }
           }
         }

@@ -777,6 +777,10 @@ int tc_res_block(TcState* s, int which, const Tensor& x, int x_plane0, Tensor& o
   job.flags2 = s->flags2;
   job.flags_cap = s->flags_cap;
   job.lag = lag;
+  const char* ly = getenv("SS_TC_LAYOUT");
+  job.layout = ly ? atoi(ly) : 1;
+  const char* ep = getenv("SS_TC_EPI");
+  job.epi = ep ? atoi(ep) : 3;
   job.ring_request = fuse ? (re ? atoi(re) : kDefaultRing) : 0;
   if (c1_done) {            // the intermediate tensor was produced by another kernel (conv1_direct): conv2 only
     q.prof = (s->launch_index++ == s->prof_layer) ? s->prof : nullptr;

@@ -45,7 +45,7 @@ namespace tc {
 
 constexpr int kMaxStages = 8;
 constexpr int kMaxSources = 6;
-constexpr int kTcThreads = 352;          // warps 0-3 and 6-9: epilogue; warp 4: producer; warps 5 and 10: MMA issuers
+constexpr int kTcThreads = 352;          // 11 warps: 8 epilogue, 1 producer, 2 MMA issuers (roles: see the kernel)
 constexpr int kAccCols = 256;             // TMEM columns per accumulator buffer (two buffers = all 512)
 constexpr uint32_t kSpinLimit = 1u << 22;
 // Tuning experiments (SS_TC_DEBUG: 1 skip the copies, 2 skip the stores, 4 skip the stage barriers, 8 skip the MMAs)
@@ -322,6 +322,8 @@ struct TcJob {
   uint32_t prog[2][kMaxProg];   // stage program of a unit of each phase
   int prog_len[2];
   int n_phase;
+  int layout;          // warp-role layout (see the kernel): 1 = critical roles on the highest warp ids (default)
+  int epi;             // epilogue operand fetch: bit 0 = scalar residual preloaded before the accumulator wait (A/B runs)
   int lag;             // units by which c[1] trails c[0]
   int* flags;          // [total_units], zeroed before the launch (fused launches only)
   int flags_cap;
@@ -442,6 +444,13 @@ conv_tc_kernel(const TcJob job) {
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(zero_s + N);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // Warp roles.  The warp scheduler of an SM sub-partition (warp id % 4) prefers its highest-numbered eligible warp, so
+  // the latency-critical roles sit on top of their sub-partitions: producer = warp 8 (above epilogue warps 0 and 4),
+  // MMA issuers = warps 9 and 10 (above 1, 5 and 2, 6); epilogue = warps 0-7.  (layout 0, kept for A/B runs:
+  // producer 4, MMA 5 and 10, epilogue 0-3 and 6-9 — the MMA warp 5 then loses its issue slots to epilogue warp 9
+  // whenever that one has an instruction ready.)
+  const bool top_roles = job.layout != 0;
+  const int w_prod = top_roles ? 8 : 4, w_mma0 = top_roles ? 9 : 5, w_mma1 = 10;
   const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + kMaxStages);
   const uint32_t accf0 = smem_u32(bars + 2 * kMaxStages), acce0 = smem_u32(bars + 2 * kMaxStages + 2);
 
@@ -461,7 +470,7 @@ conv_tc_kernel(const TcJob job) {
     bias_s[2 * N + i] = job.c[i / N].res_w ? job.c[i / N].res_w[i % N] : 0.f;
   }
   for (int i = threadIdx.x; i < N; i += kTcThreads) zero_s[i] = 0.f;
-  if (warp == 4) {
+  if (warp == w_prod) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
                  "n"(512));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
@@ -471,7 +480,7 @@ conv_tc_kernel(const TcJob job) {
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 4) {
+  if (warp == w_prod) {
     // ===================================================================== producer (warp-uniform)
     int it = 0;
     bool ok = true;
@@ -540,9 +549,9 @@ conv_tc_kernel(const TcJob job) {
       }
     }
     if (p.prof && lane == 0) p.prof[blockIdx.x * 8 + 0] = w_empty;
-  } else if (warp == 5 || warp == 10) {
+  } else if (warp == w_mma0 || warp == w_mma1) {
     // ===================================================================== MMA issuers (warp-uniform)
-    const int me = (warp == 5) ? 0 : 1;             // which half of the accumulator tiles this warp issues for
+    const int me = (warp == w_mma0) ? 0 : 1;        // which half of the accumulator tiles this warp issues for
     constexpr int MTW = (G == 2) ? MT : MT / 2;     // tiles per warp and stage
     static_assert(G == 2 || MT % 2 == 0, "tiles must split evenly between the two MMA warps");
     constexpr uint32_t idesc_n = instr_desc(N, PrecTraits<P>::fmt);
@@ -575,8 +584,10 @@ conv_tc_kernel(const TcJob job) {
       int buf = 0;
       uint32_t d_unit = 0u;
       bool accumulate_next = false;
+      uint32_t e_next = job.prog[phase][0];
       for (int pi = 0; pi < n_prog && ok; ++pi) {
-        const uint32_t e = job.prog[phase][pi];
+        const uint32_t e = e_next;
+        e_next = job.prog[phase][pi + 1 < n_prog ? pi + 1 : pi];      // fetched a stage ahead (constant-bank latency)
         const int n = (int)((e >> 9) & 7u);
         const bool first = (e >> 12) & 1u, last = (e >> 13) & 1u, taps9 = (e >> 14) & 1u;
         const uint32_t kind = (e >> 15) & 3u;
@@ -599,6 +610,11 @@ conv_tc_kernel(const TcJob job) {
           if (!ok) break;
         }
         tc_fence_after();
+        // Look ahead: a non-blocking probe of the NEXT stage's full barrier goes out before this stage's MMAs and is
+        // read after them, so its latency (~150 cycles) runs under the MMAs instead of between two bursts of them.
+        const int st_n = (st + 1 == S) ? 0 : st + 1;
+        const uint32_t ph_n = (st + 1 == S) ? (ph ^ 1u) : ph;
+        const bool probe = !(dbg & 4) && mbar_test_wait(full0 + 8 * st_n, ph_n);
         if (leader) {
           if (dbg & 8) { if (a0 == 0xdeadbeefu) p.err[1] = (int)(d_unit + idesc); }   // issue nothing
           else if (!taps9) {
@@ -625,9 +641,11 @@ conv_tc_kernel(const TcJob job) {
         __syncwarp();
         accumulate_next = true;
         a0 += stage_sz;
-        if (++st == S) { st = 0; ph ^= 1u; a0 = stage_base; }
-        // probe the next stage now: the answer travels while this iteration winds down
-        ready = !(dbg & 4) && mbar_try_wait(full0 + 8 * st, ph);
+        st = st_n;
+        ph = ph_n;
+        if (st == 0) a0 = stage_base;
+        // the early probe usually says yes (the producer runs a ring ahead); otherwise ask again, suspending
+        ready = probe || (!(dbg & 4) && mbar_try_wait(full0 + 8 * st, ph));
       }
     }
     __syncwarp();
@@ -640,7 +658,7 @@ conv_tc_kernel(const TcJob job) {
   } else {
     // ===================================================================== epilogue (warps 0-3 and 6-9)
     const int quad = warp & 3;                 // TMEM lane quadrant this warp may read
-    const int tile_par = warp >= 6 ? 1 : 0;    // the two warps of a quadrant take alternate tiles
+    const int tile_par = top_roles ? (warp >> 2) : (warp >= 6 ? 1 : 0);    // the two warps of a quadrant take alternate tiles
     const int Wp2 = 2 * p.W + 2;
     int k = 0;
     int kk = 0;                    // TMEM buffer turns taken so far (see the MMA warps)
@@ -663,19 +681,33 @@ conv_tc_kernel(const TcJob job) {
 
       // Everything after the accumulators of one tile's 32-column block [n0, n0 + 32) are final: undo the weight
       // scale, bias, scalar residual, ReLU, (mask-head partials,) 16-bit pack, stores.
-      auto finalize = [&](const uint32_t (&v)[32], const int n0, const int pos) {
+      // The scalar residual input of a tile's position (conv1_1: mel; 0 outside the image or without one) is fetched
+      // BEFORE the wait for the accumulators: the CTA's shared memory takes the whole L1 carve-out, so the load is an
+      // L2 round trip, which otherwise sits between the accumulator load and the first FMA (-7 % on conv1_1.c2).
+      struct TilePre { float rx; };
+      auto preload = [&](const int pos) {
+        TilePre t;
+        const int y = pos / Wp, x = pos - y * Wp;
+        const bool interior = (y >= 1) && (y <= p.H) && (x >= 1) && (x <= p.W);
+        t.rx = (c.res_x != nullptr && interior && (job.epi & 1))
+                   ? __ldg(c.res_x + ((int64_t)b * p.H + (y - 1)) * p.W + (x - 1)) : 0.f;
+        return t;
+      };
+      auto finalize = [&](const uint32_t (&v)[32], const int n0, const int pos, const TilePre& pre) {
         const int y = pos / Wp, x = pos - y * Wp;
         const bool interior = (y >= 1) && (y <= p.H) && (x >= 1) && (x <= p.W);
         const bool in_tensor = pos < HpWp;
         const int64_t up = (int64_t)(2 * y - 1) * Wp2 + (2 * x - 1);
-        // scalar residual input of this position (0 outside the image or when the launch has none: the weights are 0 too)
-        const float rx = (c.res_x != nullptr && interior) ? __ldg(c.res_x + ((int64_t)b * p.H + (y - 1)) * p.W + (x - 1)) : 0.f;
+        const float rx = (job.epi & 1) ? pre.rx
+                         : ((c.res_x != nullptr && interior) ? __ldg(c.res_x + ((int64_t)b * p.H + (y - 1)) * p.W + (x - 1)) : 0.f);
         const float* resw_p = bias_s + 2 * N + phase * N;
         const float* bias_t = interior ? bias_p : zero_s;
         const float scale_t = interior ? inv_scale : 0.f;
         if constexpr (N == 32) {
           if (c.head_w != nullptr) {
             // fused conv_flatten partials: this position's 32 activations . head_w[y - 1][:, 0..3]
+            // (the weights come straight from L2, channel by channel: staging the warp's rows in shared memory or
+            // broadcasting them with shuffles measured 16 % / 26 % slower on this launch, profiles/r2_tuning.txt)
             if (interior) {
               const float4* wrow = reinterpret_cast<const float4*>(c.head_w) + (y - 1) * 32;
               float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -816,12 +848,13 @@ conv_tc_kernel(const TcJob job) {
 #pragma unroll
         for (int ti = 0; ti < kMyTiles; ++ti) {
           const int pos = q0 + (tile_par + 2 * ti) * 128 + quad * 32 + lane;
+          const TilePre pre = preload(pos);
 #pragma unroll
           for (int n0 = 0; n0 < N; n0 += 32) {
             uint32_t v[32];
 #pragma unroll
             for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(acc[ti][n0 + i]);
-            finalize(v, n0, pos);
+            finalize(v, n0, pos, pre);
           }
         }
       } else {
@@ -829,17 +862,23 @@ conv_tc_kernel(const TcJob job) {
         const int buf = (G == 1) ? (kk & 1) : g;
         const uint32_t f_parity = (G == 1) ? (((uint32_t)kk >> 1) & 1u) : ((uint32_t)k & 1u);
         const int q0 = halo + ((u - b * p.units_per_image) * G + g) * MT * 128;
+        // this warp's tiles: tile_par, tile_par + 2, ...; the global operands of a tile are fetched one tile ahead
+        // (the first before the wait for the accumulators), the loop stays rolled (code size)
+        TilePre cur = preload(q0 + tile_par * 128 + quad * 32 + lane);
         ok = mbar_wait_t(accf0 + 8 * buf, f_parity, p.err, 3, w_accf);
         if (!ok) break;
         tc_fence_after();
+#pragma unroll 1
         for (int mt = tile_par; mt < MT; mt += 2) {
           const int pos = q0 + mt * 128 + quad * 32 + lane;
+          const TilePre nxt = (mt + 2 < MT) ? preload(pos + 256) : cur;
 #pragma unroll
           for (int n0 = 0; n0 < N; n0 += 32) {
             uint32_t v[32];
             load_block(v, buf, mt, n0);
-            finalize(v, n0, pos);
+            finalize(v, n0, pos, cur);
           }
+          cur = nxt;
         }
         // all of this warp's TMEM reads of the buffer have completed (tcgen05.wait::ld after each load pair)
         tc_fence_before();
@@ -869,7 +908,7 @@ conv_tc_kernel(const TcJob job) {
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == w_prod) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512));
   }
 }

@@ -47,41 +47,62 @@ def peaks():
     return 6650.0, "fallback"
 
 
-def run_long(args):
+def _stream_hour16(args):
     from softspoken_b200 import synth
-    eng = load_engine(args.max_batch, args.mode)
-    clip = synth.synth_audio(600.0, 0)
-    tiles = int(round(args.hours * 6))
-    n = tiles * clip.size
+    return synth.stream_hour_pcm16(*args)
+
+
+def run_long(args):
+    """Config 4: one long recording streamed from a host buffer.  The recording is `hours` independently seeded
+    one-hour clips (`synth.stream_hour`: it never has to exist anywhere but in the buffer it is generated into); its
+    first hour is the clip whose reference results are frozen in tests/golden/scale_stream_hour0.npz, so the run is
+    checked against the REAL reference on every window and detection row that lies inside that hour — and against
+    a GPU run of the hour alone, bit for bit (chunking must not change a result)."""
+    import multiprocessing as mp
+    from tools import scale_parity
+    n_hours = int(round(args.hours))
+    g = np.load(os.path.join(ROOT, "tests", "golden", "scale_stream_hour0.npz"))
+    seed = int(g["stream_seed"])
+    n_hour = 3600 * SR
+    n = n_hours * n_hour
     t0 = time.perf_counter()
     audio = torch.empty(n, dtype=torch.int16 if args.pcm16 else torch.float32).pin_memory()
     view = audio.numpy()
-    rng = np.random.default_rng(7)
-    for i in range(tiles):
-        tile = clip * np.float32(rng.uniform(0.5, 1.0))
-        view[i * clip.size:(i + 1) * clip.size] = np.rint(tile * 32767.0).astype(np.int16) if args.pcm16 else tile
+    with mp.get_context("spawn").Pool(min(8, os.cpu_count() or 1)) as pool:      # spawn: the parent already holds a CUDA context (pinned buffer)
+        for h, pcm in enumerate(pool.imap(_stream_hour16, [(seed, h) for h in range(n_hours)])):
+            view[h * n_hour:(h + 1) * n_hour] = pcm if args.pcm16 else pcm.astype(np.float32) / np.float32(32768.0)
     gen_s = time.perf_counter() - t0
+    eng = load_engine(args.max_batch, args.mode)
     W = (n + 66150 + 13229) // 13230
     eng.reserve(n, 1 << 20)
-    # warm-up on the first 30 minutes, which is also the prefix reference
-    n_pre = 3 * clip.size
-    reg_pre, lg_pre = eng.detect_host(audio[:n_pre], want_logits=True, cap=1 << 20)
+    # warm-up on the first hour, which is also the prefix reference
+    reg_pre, lg_pre = eng.detect_host(audio[:n_hour], want_logits=True, cap=1 << 20)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     reg, lg = eng.detect_host(audio, want_logits=True, cap=1 << 20)
     dt = time.perf_counter() - t0
-    # windows that lie entirely inside the prefix (and its leading pad) see identical samples in both runs
-    w_same = (n_pre + 66150 - 65536) // 13230
+    # windows that lie entirely inside the first hour (and its leading pad) see identical samples in both runs
+    w_same = (n_hour + 66150 - 65536) // 13230
     same_logits = bool(np.array_equal(lg[:w_same], lg_pre[:w_same]))
     safe_bin = int((w_same - 5) * 51.2)
     a = reg[reg[:, 1] < safe_bin]
     b = reg_pre[reg_pre[:, 1] < safe_bin]
     same_regions = bool(np.array_equal(a, b))
+    # against the reference: logits of the golden's windows (every 4th) that lie inside the hour, and every
+    # reference row that ends before the last bin the hour alone determines
+    stride = int(g["logits_stride"])
+    ref_lg = g["logits"]
+    k = (w_same + stride - 1) // stride
+    ref_err = float(np.max(np.abs(lg[:w_same:stride].astype(np.float64) - ref_lg[:k])))
+    ref_rows = {tuple(r) for r in g["region_bins"].tolist() if r[1] < safe_bin}
+    got_rows = {tuple(r) for r in a.astype(np.int64).tolist()}
+    hour_alone = scale_parity.compare("hour0", reg_pre, lg_pre)
     hours = n / SR / 3600.0
     line = {
         "metric": "audio_hours_per_sec", "value": hours / dt, "unit": "audio-hours/s", "n_gpus": 1,
         "higher_is_better": True, "dtype": args.mode, "data": "synthetic",
-        "config": {"workload": f"config4: one {hours:.1f} h mono 22.05 kHz recording, host buffer "
+        "config": {"workload": f"config4: one {hours:.1f} h mono 22.05 kHz recording ({n_hours} independently seeded hours, "
+                               f"synth.stream_hour({seed}, h)), host buffer "
                                f"({'int16 samples of a PCM_16 file' if args.pcm16 else 'float32'}) streamed in chunks of "
                                "1024 windows (52,920-sample overlap), K5/K6 once over the whole timeline",
                    "max_batch_windows": args.max_batch,
@@ -90,11 +111,15 @@ def run_long(args):
         "x_realtime": hours * 3600.0 / dt, "seconds": dt,
         "e2e": {"value": hours / dt, "unit": "audio-hours/s", "h2d_bytes_per_step": int(n * (2 if args.pcm16 else 4)),
                 "d2h_bytes_per_step": int(lg.nbytes + reg.nbytes)},
-        "checks": {"prefix_logits_bitwise_equal": same_logits, "prefix_regions_equal": same_regions,
-                   "prefix_windows_compared": int(w_same)},
+        "checks": {"prefix_logits_bitwise_equal_to_hour_alone": same_logits, "prefix_regions_equal_to_hour_alone": same_regions,
+                   "prefix_windows_compared": int(w_same),
+                   "vs_reference_inside_hour0": {"max_logit_err": ref_err, "reference_rows": len(ref_rows),
+                                                 "differing_rows": len(ref_rows ^ got_rows)},
+                   "hour0_alone_vs_reference": hour_alone},
     }
     print(json.dumps(line), flush=True)
     assert same_logits and same_regions
+    assert ref_err <= 1e-4 and len(ref_rows ^ got_rows) <= 2 * hour_alone["differing_bins"]
     eng.close()
 
 

@@ -779,6 +779,8 @@ int tc_res_block(TcState* s, int which, const Tensor& x, int x_plane0, Tensor& o
   job.lag = lag;
   const char* ly = getenv("SS_TC_LAYOUT");
   job.layout = ly ? atoi(ly) : 1;
+  const char* hf = getenv("SS_TC_FENCE");
+  job.heavy_fence = hf ? atoi(hf) : 0;
   const char* ep = getenv("SS_TC_EPI");
   job.epi = ep ? atoi(ep) : 3;
   job.ring_request = fuse ? (re ? atoi(re) : kDefaultRing) : 0;

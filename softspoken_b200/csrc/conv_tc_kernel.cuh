@@ -323,6 +323,7 @@ struct TcJob {
   int prog_len[2];
   int n_phase;
   int layout;          // warp-role layout (see the kernel): 1 = critical roles on the highest warp ids (default)
+  int heavy_fence;     // fused launches publish a unit with __threadfence + atomicAdd instead of a release-reduction (A/B)
   int epi;             // epilogue operand fetch: bit 0 = scalar residual preloaded before the accumulator wait (A/B runs)
   int lag;             // units by which c[1] trails c[0]
   int* flags;          // [total_units], zeroed before the launch (fused launches only)
@@ -888,11 +889,17 @@ conv_tc_kernel(const TcJob job) {
       }
       if constexpr (PrecTraits<P>::fmt == 0) out_of_range |= (vmax > 65504.f);
       if (n_phase == 2 && phase == 0) {
-        // publish this warp's share of the unit to the c[1] producers of other CTAs (release at gpu scope)
+        // publish this warp's share of the unit to the c[1] producers of other CTAs: the lanes' stores are ordered
+        // before lane 0's release by the warp barrier, and the release-reduction makes them visible at gpu scope
+        // (a full __threadfence() + atomicAdd here stalled every epilogue warp until its stores had drained:
+        // SS_TC_FENCE=1 keeps that form for A/B runs)
         asm volatile("fence.proxy.async.global;" ::: "memory");
-        __threadfence();
+        if (job.heavy_fence) __threadfence();
         __syncwarp();
-        if (lane == 0) atomicAdd(job.flags + u, 1);
+        if (lane == 0) {
+          if (job.heavy_fence) atomicAdd(job.flags + u, 1);
+          else asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(job.flags + u), "r"(1) : "memory");
+        }
       }
       if (n_phase == 2 && phase == 1 && job.ring > 0) {
         // this unit's copies of the intermediate tensor completed before its accumulators did: its slot may be reused

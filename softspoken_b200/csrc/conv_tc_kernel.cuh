@@ -364,6 +364,21 @@ __device__ __noinline__ bool flag_wait(const int* f, int want, int* err, int cod
   return false;
 }
 
+// Bounded wait for `want` arrivals on each of the flags f[-1], f[0], f[+1] (those with `lo` / `hi` set): lanes 0-2 of
+// the (converged) warp poll one flag each, so the three acquire loads are one L2 round trip, not three in a row.
+__device__ __noinline__ bool flag_wait3(const int* f, bool lo, bool hi, int want, int* err, int code) {
+  const int lane = threadIdx.x & 31;
+  const bool mine = lane == 1 || (lane == 0 && lo) || (lane == 2 && hi);
+#pragma unroll 1
+  for (uint32_t i = 0; i < kSpinLimit; ++i) {
+    const bool ok = !mine || ld_acquire(f + lane - 1) >= want;
+    if (__all_sync(0xffffffffu, ok)) return true;
+    __nanosleep(64);
+  }
+  if (lane == 0) atomicExch(err, code);
+  return false;
+}
+
 // 128-position tiles per work unit: one 256-column TMEM accumulator buffer holds MT tiles of N columns.
 // (TS = TMEM columns per tile: N, or 2N in the dual layout).
 template <int N, bool Dual>
@@ -495,17 +510,16 @@ conv_tc_kernel(const TcJob job) {
       const int lo = lu * G * MT * 128;   // first staged position (= q0 - halo)
       if (phase == 0 && job.ring > 0 && b >= job.ring) {
         const int v0 = u - job.ring * p.units_per_image;       // same local unit, `ring` images earlier
-        ok = flag_wait(job.flags2 + v0, 8, p.err, 6);
-        if (ok && lu > 0) ok = flag_wait(job.flags2 + v0 - 1, 8, p.err, 6);
-        if (ok && lu < p.units_per_image - 1) ok = flag_wait(job.flags2 + v0 + 1, 8, p.err, 6);
+        ok = flag_wait3(job.flags2 + v0, lu > 0, lu < p.units_per_image - 1, 8, p.err, 6);
         if (!ok) break;
       }
       if (phase == 1) {
         // the units of c[0] whose output this unit reads must be complete (see TcJob), and their generic-proxy
         // stores visible to the async proxy that performs the bulk copies
-        ok = flag_wait(job.flags + u, 8, p.err, 5);
-        if (ok && lu > 0) ok = flag_wait(job.flags + u - 1, 8, p.err, 5);
-        if (ok && lu < p.units_per_image - 1) ok = flag_wait(job.flags + u + 1, 8, p.err, 5);
+        // (three acquire loads at once, one per lane: one L2 round trip instead of three in a row, during which this
+        // warp stages nothing; reading them one item AHEAD was slower still — an acquire load holds back the bulk
+        // copies issued after it)
+        ok = flag_wait3(job.flags + u, lu > 0, lu < p.units_per_image - 1, 8, p.err, 5);
         if (!ok) break;
         asm volatile("fence.proxy.async.global;" ::: "memory");
       }

@@ -210,3 +210,42 @@ def test_fused_mask_head_close_to_two_kernel_form(sd_seed0, clip60, monkeypatch)
     print(f"fused vs two-kernel mask head: rel diff {err:.3e}")
     assert err <= 2e-6
     eng.close()
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_other_checkpoints(seed, clip60):
+    """Three more seeded checkpoints (different weights, BatchNorm statistics and head biases: the per-layer weight
+    scale of the fp16 modes and the range check are data-dependent): every tensor-core mode against the fp32 oracle
+    on the same mel features, and the f16x3 region decisions of a 60 s clip against the oracle's where the oracle
+    decides with a margin."""
+    from oracle import model as om
+    from oracle import postproc as pp
+    from softspoken_b200 import checkpoint, spec
+    from softspoken_b200.engine import Engine
+    sd = checkpoint.synthetic_state_dict(seed)
+    # BatchNorm scales that differ from layer to layer by up to 4x: exercises the per-layer weight scaling
+    for k, v in list(sd.items()):
+        if k.endswith(".weight") and v.dim() == 1:
+            sd[k] = v * (0.5, 1.0, 2.0, 1.0)[sum(map(ord, k)) % 4]
+    padded = pp.pad_audio(clip60)
+    starts = pp.plan_windows(60.0)
+    x = torch.stack([torch.from_numpy(padded[i:i + spec.WINDOW_SAMPLES]) for i in starts])
+    eng = Engine(sd, 0, max_batch=48, mode="f16x3")
+    mel = eng.features(torch.from_numpy(padded).cuda(), torch.from_numpy(starts))
+    _, mk = om.forward_from_mel(sd, mel.cpu().unsqueeze(1), want_spec=False)
+    ref = mk[:, 0]
+    scale = max(1.0, float(ref.abs().max()))
+    for mode in ("f16x3", "f16", "bf16"):
+        got = eng.classify(mel, mode=mode).cpu()
+        eng.check_health()
+        err = float((got - ref).abs().max()) / scale
+        assert err <= TOL[mode][1], (seed, mode, err)
+    # decisions: wherever the oracle's averaged timeline keeps 1e-4 (of the logit scale) from the threshold, f16x3 agrees
+    got = eng.classify(mel, mode="f16x3").cpu().numpy()
+    secs = len(padded) / 22050
+    avg_r, cnt = pp.average_idx(ref.numpy().reshape(-1, 1, 256), secs)
+    avg_g, _ = pp.average_idx(got.reshape(-1, 1, 256), secs)
+    m = (cnt >= 1) & (np.abs(avg_r - 0.1) >= 1e-4 * scale)
+    assert np.array_equal(avg_r[m] > 0.1, avg_g[m] > 0.1)
+    assert eng.check_guards() == 0
+    eng.close()

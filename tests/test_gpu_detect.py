@@ -196,3 +196,18 @@ def test_headless_job_from_wav_files(detector, wavs, tmp_path):
             want[a:b] = 0
         got, got_sr = wavio.read_wav_pcm16(str(out / (os.path.basename(path)[:-4] + "_silenced.wav")))
         assert got_sr == sr and np.array_equal(got, want)
+
+
+def test_region_capacity_is_grown_not_fatal(sd_seed0, clip60):
+    """a clip with more regions than the caller's capacity used to abort the call (and, in a corpus run, the
+    whole job after the work was done).  The kernel reports the true count; the engine runs that clip again with room."""
+    from softspoken_b200.engine import Engine
+    eng = Engine(sd_seed0, 0, max_batch=32)
+    want = eng.detect_host(clip60)
+    assert len(want) > 4
+    assert np.array_equal(eng.detect_host(clip60, cap=2), want)
+    short = clip60[: 22050 * 5]
+    outs = eng.detect_host_batch([clip60, short, clip60], cap=3)
+    assert np.array_equal(outs[0], want) and np.array_equal(outs[2], want)
+    assert np.array_equal(outs[1], eng.detect_host(short))
+    eng.close()

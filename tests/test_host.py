@@ -470,3 +470,63 @@ def test_wav_parser_field_recorder_layouts(tmp_path):
             f.write(bad)
         with pytest.raises(wavio.WavError):
             wavio.read_wav(pb)
+
+
+def _resume_worker(rank, world, port, q, files, durations, jp, delay):
+    import time
+    import torch.distributed as dist
+    from softspoken_b200 import corpus
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    seen = []
+
+    def fake_load(path):
+        return np.full(4, float(files.index(path)), np.float32)
+
+    def detect(clips):
+        out = []
+        for c in clips:
+            i = int(c[0])
+            seen.append(i)
+            out.append(np.sort(np.random.default_rng(i).integers(0, 51000, (i % 4, 2)), axis=1).astype(np.int32))
+        return out
+    time.sleep(delay[rank])          # a rank that reaches the journal late must not see what the others just wrote
+    rows = corpus.detect_corpus(files, detect, load=fake_load, durations=durations, group_size=2, journal=jp, prefetch=0)
+    q.put((rank, seen, corpus.csv_text(rows) if rank == 0 else None))
+    dist.destroy_process_group()
+
+
+def test_corpus_journal_resume_two_ranks_one_view(tmp_path):
+    """with --resume every rank used to read the progress files on its own; a rank arriving late saw the
+    lines another rank had just appended, sharded a different remainder, and files were detected twice or not at all.
+    Now rank 0 reads and broadcasts ONE view: each unfinished file is detected exactly once, the CSV is the clean one."""
+    import torch.multiprocessing as mp
+    from softspoken_b200 import corpus
+    files = [f"/data/clip{i}.wav" for i in range(17)]
+    durations = [600.0] * len(files)
+
+    def fake_load(path):
+        return np.full(4, float(files.index(path)), np.float32)
+
+    def detect(clips):
+        return [np.sort(np.random.default_rng(int(c[0])).integers(0, 51000, (int(c[0]) % 4, 2)), axis=1).astype(np.int32)
+                for c in clips]
+    clean = corpus.csv_text(corpus.detect_corpus(files, detect, load=fake_load, durations=durations))
+    jp = os.path.join(tmp_path, "run.journal")
+    jr = corpus.Journal(jp, files, 0)
+    for i in (0, 3, 4):                                   # what an earlier, interrupted run had finished
+        jr.append(i, detect([fake_load(files[i])])[0])
+    jr.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() + 911) % 2000
+    procs = [ctx.Process(target=_resume_worker, args=(r, 2, port, q, files, durations, jp, (0.0, 1.5))) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(60)
+    seen = sorted(i for _, s, _ in res for i in s)
+    assert seen == [i for i in range(17) if i not in (0, 3, 4)]          # exactly once each, none of the finished ones
+    assert [t for _, _, t in res if t is not None][0] == clean

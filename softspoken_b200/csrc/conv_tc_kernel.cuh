@@ -1,15 +1,17 @@
 // The tcgen05 implicit-GEMM convolution kernel of conv_tc.cu (see that file's header for the layout).
 //
-// Persistent, warp-specialised, one CTA per SM:
-//   warp 4     producer  — cp.async.bulk (1-D TMA) of activation runs + packed weights into an smem ring
-//   warps 5,10 MMA       — one elected thread per warp issues tcgen05.mma into the two 256-column TMEM buffers.
+// Persistent, warp-specialised, one CTA per SM, 11 warps (default role layout; TcJob::layout):
+//   warp 8     producer  — cp.async.bulk (1-D TMA) of activation runs + packed weights into an smem ring
+//   warps 9,10 MMA       — one elected thread per warp issues tcgen05.mma into the two 256-column TMEM buffers.
 //              Each warp owns half of every unit's accumulator tiles (G = 2: one group each; G = 1: half the tiles)
 //              and walks every stage for them.  The tensor pipe queues only a couple of MMAs, so whatever an issuer
 //              does between two MMAs (barrier probes, descriptor set-up: ~500 cycles per stage) would be a pipe
 //              bubble; with two independent issuers one warp's bookkeeping runs under the other's MMAs.  Every
 //              accumulator tile still has a single issuing thread and a fixed order, so results are deterministic.
-//   warps 0-3, 6-9  epilogue — tcgen05.ld -> bias / ReLU / border mask -> 16-bit pack -> 16-byte global stores
-//              (a warp reads the TMEM lane quadrant warp % 4; the two warps of a quadrant take alternate tiles)
+//   warps 0-7  epilogue — tcgen05.ld -> (sum of the accumulation groups) -> bias / ReLU / border mask -> 16-bit pack
+//              -> 16- / 32-byte global stores (a warp reads the TMEM lane quadrant warp % 4; the two warps of a
+//              quadrant take alternate tiles)
+// Producer and MMA issuers walk a flat per-unit stage program built by the host (TcJob::prog).
 // The three roles are decoupled by mbarriers (full/empty per smem stage, acc_full/acc_empty per TMEM
 // buffer), so the loads of unit k+1, the MMAs of unit k and the epilogue of unit k-1 overlap.
 //

@@ -164,7 +164,11 @@ conv1_direct(const float* __restrict__ mel, const float* __restrict__ w /* [9][3
 }
 
 // MaxPool2d(2) on planar tensors: in planes [plane0, plane0+planes) of a tensor with in_planes_total planes at
-// H x W  ->  out [B][planes][H/2+2][W/2+2][8].  The max is taken on the reconstructed fp32 values.
+// H x W  ->  out [B][planes][H/2+2][W/2+2][8].  The max is taken on the reconstructed fp32 values; in the split
+// precision the pooled operand pair is the (hi, lo) pair OF the window's maximum, not a fresh split of hi + lo: the
+// two differ when lo is exactly half an ulp of hi (one value in 4,096: hi + lo then sits midway between two fp16
+// numbers and rounds to the even one), and keeping the pair makes this kernel and the pool folded into the
+// convolution epilogue (TcConv::rows, which splits the float32 maximum it still holds) write the same bits.
 template <Prec P>
 __global__ void pool_planar(const uint16_t* __restrict__ in, const uint16_t* __restrict__ in_lo, int in_planes_total,
                             int plane0, int planes, int H, int W, uint16_t* __restrict__ out,
@@ -179,18 +183,52 @@ __global__ void pool_planar(const uint16_t* __restrict__ in, const uint16_t* __r
   const int64_t b = r / planes;
   const int Wp = W + 2, Hp = H + 2, Wq = W2 + 2, Hq = H2 + 2;
   const int64_t src = ((b * in_planes_total + plane0 + pl) * Hp + (2 * y + 1)) * (int64_t)Wp + (2 * x + 1);
-  float a[8], c[8];
-  load8<P>(in, in_lo, src, a);
-  load8<P>(in, in_lo, src + 1, c);
+  const int64_t dst = ((b * planes + pl) * Hq + (y + 1)) * (int64_t)Wq + (x + 1);
+  if constexpr (PrecTraits<P>::split) {
+    const int64_t offs[4] = {src, src + 1, src + Wp, src + Wp + 1};
+    uint4 hv[4], lv[4];
 #pragma unroll
-  for (int k = 0; k < 8; ++k) a[k] = fmaxf(a[k], c[k]);
-  load8<P>(in, in_lo, src + Wp, c);
+    for (int k = 0; k < 4; ++k) {
+      hv[k] = __ldg(reinterpret_cast<const uint4*>(in) + offs[k]);
+      lv[k] = __ldg(reinterpret_cast<const uint4*>(in_lo) + offs[k]);
+    }
+    uint32_t bh[4] = {hv[0].x, hv[0].y, hv[0].z, hv[0].w}, bl[4] = {lv[0].x, lv[0].y, lv[0].z, lv[0].w};
+    float2 best[4];
 #pragma unroll
-  for (int k = 0; k < 8; ++k) a[k] = fmaxf(a[k], c[k]);
-  load8<P>(in, in_lo, src + Wp + 1, c);
+    for (int h = 0; h < 4; ++h) {
+      const float2 a = unpack2<P>(bh[h]), c = unpack2<P>(bl[h]);
+      best[h] = make_float2(a.x + c.x, a.y + c.y);
+    }
 #pragma unroll
-  for (int k = 0; k < 8; ++k) a[k] = fmaxf(a[k], c[k]);
-  store8<P>(out, out_lo, ((b * planes + pl) * Hq + (y + 1)) * (int64_t)Wq + (x + 1), a);
+    for (int k = 1; k < 4; ++k) {
+      const uint32_t ch[4] = {hv[k].x, hv[k].y, hv[k].z, hv[k].w}, cl[4] = {lv[k].x, lv[k].y, lv[k].z, lv[k].w};
+#pragma unroll
+      for (int h = 0; h < 4; ++h) {
+        const float2 a = unpack2<P>(ch[h]), c = unpack2<P>(cl[h]);
+        const float vx = a.x + c.x, vy = a.y + c.y;
+        const uint32_t m = (vx > best[h].x ? 0x0000ffffu : 0u) | (vy > best[h].y ? 0xffff0000u : 0u);
+        bh[h] = (bh[h] & ~m) | (ch[h] & m);
+        bl[h] = (bl[h] & ~m) | (cl[h] & m);
+        best[h].x = fmaxf(best[h].x, vx);
+        best[h].y = fmaxf(best[h].y, vy);
+      }
+    }
+    reinterpret_cast<uint4*>(out)[dst] = make_uint4(bh[0], bh[1], bh[2], bh[3]);
+    reinterpret_cast<uint4*>(out_lo)[dst] = make_uint4(bl[0], bl[1], bl[2], bl[3]);
+  } else {
+    float a[8], c[8];
+    load8<P>(in, in_lo, src, a);
+    load8<P>(in, in_lo, src + 1, c);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a[k] = fmaxf(a[k], c[k]);
+    load8<P>(in, in_lo, src + Wp, c);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a[k] = fmaxf(a[k], c[k]);
+    load8<P>(in, in_lo, src + Wp + 1, c);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) a[k] = fmaxf(a[k], c[k]);
+    store8<P>(out, out_lo, dst, a);
+  }
 }
 
 // Mask head on planar conv9 [B][4][130][258][8] (same arithmetic as head.cu:mask_head_f32, fp32 math).
@@ -521,7 +559,15 @@ template <int N, Prec P, bool Dual, int G>
 int launch_conv_npg(TcJob job, int B, cudaStream_t st) {
   TcConv& p = job.c[0];
   constexpr int MT = TilesPerUnit<N, Dual>::value;
-  const size_t sb = stage_bytes(N, p.W, G * MT, Dual);
+  // Row-aligned units with the MaxPool folded into the epilogue (TcConv::rows): decided by the caller, which must know
+  // whether the pooled tensor was written; here only the geometry is checked.
+  constexpr bool kCanRows = PrecTraits<P>::split && Dual && G == 1 && (N == 32 || N == 64);
+  const bool rows = p.rows != 0;
+  SS_REQUIRE(!rows || (kCanRows && job.n_phase == 1 && p.W == (MT / 2) * 128 && p.H % 2 == 0 && p.pool_out && p.pool_lo &&
+                       !p.upsample && !p.head_w && p.out && p.out_lo),
+             SS_E_ARG, "row-aligned conv launch: unsupported geometry (N %d, %d x %d)", N, p.H, p.W);
+  const size_t rows_extra = rows ? 64 : 0;       // two more positions per staged plane pair (conv_tc_kernel.cuh: kRowsExtra)
+  const size_t sb = stage_bytes(N, p.W, G * MT, Dual) + rows_extra;
   // Ring slot size.  Every stage costs a fixed hand-over (full/empty barrier round trip and an MMA-issue bubble,
   // ~500-1000 cycles measured with the tuning hooks), which a 3x3 stage hides behind its 9 x MT MMAs and a 1x1 stage
   // (MT MMAs per chunk) does not: 1x1 sources therefore pack several K-chunks into one slot, and when a launch has
@@ -529,7 +575,7 @@ int launch_conv_npg(TcJob job, int B, cudaStream_t st) {
   // slots — so that up to `cap` chunks fit.  SS_TC_CPS caps the chunks per stage (1 = one chunk per stage everywhere).
   const char* ce = getenv("SS_TC_CPS");
   const int cap = ce ? atoi(ce) : 4;
-  const size_t chunk1 = (size_t)G * MT * 128 * 32 + (Dual ? 2 : 1) * (size_t)N * 32;
+  const size_t chunk1 = (size_t)G * MT * 128 * 32 + rows_extra + (Dual ? 2 : 1) * (size_t)N * 32;
   int most1 = 0;
   for (int ph = 0; ph < job.n_phase; ++ph)
     for (int i = 0; i < job.c[ph].n_src; ++i)
@@ -562,7 +608,7 @@ int launch_conv_npg(TcJob job, int B, cudaStream_t st) {
     configured = true;
   }
   const int positions = p.H * (p.W + 2) - 2;          // (1,1) .. (H,W) in flattened padded coordinates
-  p.units_per_image = (positions + G * MT * 128 - 1) / (G * MT * 128);
+  p.units_per_image = rows ? p.H / 2 : (positions + G * MT * 128 - 1) / (G * MT * 128);
   p.total_units = p.units_per_image * B;
   for (int ph = 0; ph < job.n_phase; ++ph)
     SS_REQUIRE(job.c[ph].relu == 1, SS_E_ARG, "conv_tc_kernel applies ReLU unconditionally");
@@ -642,7 +688,18 @@ int launch_conv_npg(TcJob job, int B, cudaStream_t st) {
     for (int i = 0; i < job.c[0].n_src; ++i)
       if (job.c[0].src[i].ring < 0) job.c[0].src[i].ring = 0;
   }
-  if constexpr (kCanSub) {
+  if (rows) {
+    SS_REQUIRE(!any_sub, SS_E_ARG, "row-aligned conv launch: sub-accumulation is not available in this geometry");
+    if constexpr (kCanRows) {
+      static bool configured_rows = false;
+      if (!configured_rows) {
+        SS_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<N, P, Dual, G, false, true>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget));
+        configured_rows = true;
+      }
+      conv_tc_kernel<N, P, Dual, G, false, true><<<grid, kTcThreads, smem, st>>>(job);
+    }
+  } else if constexpr (kCanSub) {
     if (any_sub) conv_tc_kernel<N, P, Dual, G, true><<<grid, kTcThreads, smem, st>>>(job);
     else conv_tc_kernel<N, P, Dual, G, false><<<grid, kTcThreads, smem, st>>>(job);
   } else {
@@ -729,7 +786,7 @@ void add_sources(TcConv* p, const TcState* s, const Tensor& x, int plane0, const
 int tc_res_block(TcState* s, int which, const Tensor& x, int x_plane0, Tensor& out, int out_plane0, int upsample,
                  int B, cudaStream_t st, const float* head_w = nullptr, float* head_out = nullptr,
                  bool store_out = true, const float* res_x = nullptr, const float* res_w = nullptr,
-                 bool c1_done = false) {
+                 bool c1_done = false, Tensor* pool = nullptr, bool* pooled = nullptr) {
   const TcBlock& rb = s->rb[which];
   Tensor& t = s->t[which];
   const int N = rb.c1.n;
@@ -784,6 +841,25 @@ int tc_res_block(TcState* s, int which, const Tensor& x, int x_plane0, Tensor& o
   const char* ep = getenv("SS_TC_EPI");
   job.epi = ep ? atoi(ep) : 3;
   job.ring_request = fuse ? (re ? atoi(re) : kDefaultRing) : 0;
+  // MaxPool2d(2) of the block output folded into conv2's epilogue (row-aligned units, TcConv::rows): split precision,
+  // dual layout, image width = the tiles of a unit's row (conv1_1: 256 = 2 x 128 at N = 32; conv2_1: 128 at N = 64),
+  // separate launches, plain accumulation chain, one group per unit.  SS_TC_POOL_FOLD=0 keeps pool_planar (A/B runs).
+  if (pooled) *pooled = false;
+  if (pool && is_dual(s->prec, N) && !fuse && !upsample && !head_w) {
+    const char* pf = getenv("SS_TC_POOL_FOLD");
+    const char* sb = getenv("SS_TC_SUB");
+    const char* pp = getenv("SS_TC_PAIRS");
+    const int tiles_per_row = (N == 32) ? 2 : 1;          // MT / 2 of the dual layout
+    const bool plain = (sb == nullptr || atoi(sb) <= 1) && (pp == nullptr || (atoi(pp) & 1) == 0);
+    const int fold_mask = pf ? atoi(pf) : 3;              // bit 0: conv1_1 (N = 32), bit 1: conv2_1 (N = 64)
+    if ((fold_mask & (N == 32 ? 1 : 2)) != 0 && plain && x.W == tiles_per_row * 128 && x.H % 2 == 0 &&
+        pool->planes == N / 8 && pool->H == x.H / 2 && pool->W == x.W / 2) {
+      q.rows = 1;
+      q.pool_out = pool->data;
+      q.pool_lo = pool->lo;
+      if (pooled) *pooled = true;
+    }
+  }
   if (c1_done) {            // the intermediate tensor was produced by another kernel (conv1_direct): conv2 only
     q.prof = (s->launch_index++ == s->prof_layer) ? s->prof : nullptr;
     job.c[0] = q; job.n_phase = 1;
@@ -926,6 +1002,7 @@ int classify_tc_p(ss_ctx* ctx, TcState* s, const float* mel, int n_windows, floa
 #define SS_TRY(e) do { if ((rc = (e))) return rc; } while (0)
     const int64_t n_pix = (int64_t)B * kMels * kFrames;
     const float* mel_b = mel + (int64_t)b0 * kMels * kFrames;
+    bool pooled1 = false;
     const char* dc = getenv("SS_TC_DIRECT_C1");
     if (dc == nullptr || atoi(dc) != 0) {
       // conv1_1: first convolution on CUDA cores straight from mel, second on the tensor cores with the
@@ -936,7 +1013,7 @@ int classify_tc_p(ss_ctx* ctx, TcState* s, const float* mel, int n_windows, floa
       count_launch();
       // (the block-input argument only supplies the geometry here: conv2 reads t, the residual reads mel)
       SS_TRY(tc_res_block(s, RB_CONV1, s->t[RB_CONV1], 0, s->m4, 0, 0, B, st, nullptr, nullptr, true, mel_b,
-                          ctx->rb[RB_CONV1].res.w, true));
+                          ctx->rb[RB_CONV1].res.w, true, &s->p1, &pooled1));
     } else {
       // legacy form (A/B measurements, tests of the im2col'd operand tensor): both convolutions as tcgen05 launches;
       // its operand tensor is allocated on first use
@@ -949,9 +1026,11 @@ int classify_tc_p(ss_ctx* ctx, TcState* s, const float* mel, int n_windows, floa
       SS_TRY(tc_res_block(s, RB_CONV1, s->x0, 0, s->m4, 0, 0, B, st, nullptr, nullptr, true,
                           scalar ? mel_b : nullptr, scalar ? ctx->rb[RB_CONV1].res.w : nullptr));
     }
-    SS_TRY(tc_pool_p<P>(s->m4, 0, 4, s->p1, B, st));
-    SS_TRY(tc_res_block(s, RB_CONV2, s->p1, 0, s->m3, 0, 0, B, st));
-    SS_TRY(tc_pool_p<P>(s->m3, 0, 8, s->p2, B, st));
+    if (!pooled1) SS_TRY(tc_pool_p<P>(s->m4, 0, 4, s->p1, B, st));
+    bool pooled2 = false;
+    SS_TRY(tc_res_block(s, RB_CONV2, s->p1, 0, s->m3, 0, 0, B, st, nullptr, nullptr, true, nullptr, nullptr, false,
+                        &s->p2, &pooled2));
+    if (!pooled2) SS_TRY(tc_pool_p<P>(s->m3, 0, 8, s->p2, B, st));
     SS_TRY(tc_res_block(s, RB_CONV3, s->p2, 0, s->m2, 0, 0, B, st));
     SS_TRY(tc_pool_p<P>(s->m2, 0, 12, s->p3, B, st));
     SS_TRY(tc_res_block(s, RB_CONV4, s->p3, 0, s->m1, 0, 0, B, st));
@@ -1052,16 +1131,23 @@ int classify_tc(ss_ctx* ctx, int mode, const float* mel, int n_windows, float* l
 
 // Debug / parity localisation: copy one internal activation of the last tensor-core classify call to NCHW f32.
 // which: 0 conv1, 1 conv2, 2 conv3, 3 conv4, 4 bottleneck, 5 up(encoder_out), 6 up(conv6), 7 up(conv7),
-//        8 up(conv8), 9 conv9, 10 t(conv1_1.conv1), 11 x0 (16 ch).
+//        8 up(conv8), 9 conv9, 10 t(conv1_1.conv1), 11 x0 (16 ch), 12 pool(conv1), 13 pool(conv2).
 int tc_debug_dump(ss_ctx* ctx, int which, int n_windows, float* out, int* C, int* H, int* W, cudaStream_t st) {
   TcState* s = ctx->tc_last >= 0 ? static_cast<TcState*>(ctx->tc[ctx->tc_last]) : nullptr;
   SS_REQUIRE(s, SS_E_ARG, "tensor-core path not initialised");
   struct Sel { const Tensor* t; int plane0, c; };
   const Sel table[] = {{&s->m4, 0, 32}, {&s->m3, 0, 64}, {&s->m2, 0, 96}, {&s->m1, 0, 128}, {&s->bott, 0, 128},
                        {&s->m1, 16, 128}, {&s->m2, 12, 96}, {&s->m3, 8, 64}, {&s->m4, 4, 32}, {&s->c9, 0, 32},
-                       {&s->t[RB_CONV1], 0, 32}, {&s->x0, 0, 16}};
+                       {&s->t[RB_CONV1], 0, 32}, {&s->x0, 0, 16}, {&s->p1, 0, 32}, {&s->p2, 0, 64}};
+  // + 0x100: twice the hi operands alone, + 0x200: twice the lo operands alone (split precision; parity localisation)
+  const int part = which & 0x300;
+  which &= 0xff;
   SS_REQUIRE(which >= 0 && which < (int)(sizeof(table) / sizeof(table[0])), SS_E_ARG, "bad activation id %d", which);
-  const Sel& e = table[which];
+  Sel e = table[which];
+  Tensor alias = *e.t;
+  if (part == 0x100) alias.lo = alias.data;
+  if (part == 0x200) alias.data = alias.lo;
+  e.t = &alias;
   *C = e.c; *H = e.t->H; *W = e.t->W;
   if (out) {
     const int64_t total = (int64_t)n_windows * e.c * e.t->H * e.t->W;

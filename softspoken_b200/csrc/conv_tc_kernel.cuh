@@ -193,6 +193,14 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
         "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
       : "r"(taddr));
 }
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr));
+}
 #ifndef SS_TC_STCS
 #define SS_TC_STCS 0
 #endif
@@ -287,6 +295,17 @@ struct TcConv {
   // registers, in float32 round-to-nearest, before bias / ReLU.  n_sub = 1 is the plain single chain.
   int n_sub;
   int pair_store;      // up-sampling epilogue: 1 = one 32-byte store per position pair (default), 0 = two 16-byte stores
+  // Row-aligned units with MaxPool2d(2) folded into the epilogue (kernel template parameter Rows; dual layout, G = 1,
+  // W = 128 * MT / 2).  A unit is the image-row pair (2Y+1, 2Y+2) of the padded tensor: MT / 2 tiles of 128 interior
+  // positions per row, so border positions are never computed (the tensor's zero border stays as allocated) and the
+  // 2 x 2 windows of the pool lie inside the unit — vertically in the same epilogue thread (its two tiles), horizontally
+  // in neighbouring lanes.  The epilogue stores the activations as usual and, from the float32 values it still holds,
+  // the pooled tensor [B][N/8][H/2+2][W/2+2][8] (hi / lo): pool_planar's read of the full-resolution tensor and its
+  // launch disappear.  max commutes with the monotonic hi/lo split, so the pooled operands are bit-identical to
+  // pool_planar's.
+  int rows;
+  uint16_t* pool_out;
+  uint16_t* pool_lo;
   int stages;          // smem ring depth (<= kMaxStages)
   int cps;             // K-chunks a stage of a 1x1 source carries (>= 1; see the producer)
   int stage_stride;    // bytes per smem ring slot (>= the 3x3 stage; larger when that buys more 1x1 chunks per stage)
@@ -424,7 +443,7 @@ __device__ __forceinline__ void issue_group(uint32_t d0, uint32_t a_lo0, uint32_
 
 // Sub: the split-K sub-accumulation path (TcConv::n_sub > 1) is compiled in — a separate instantiation, because
 // keeping a unit's sums in registers across buffer turns costs the plain single-chain launches 7 % (measured).
-template <int N, Prec P, bool Dual, int G, bool Sub = false>
+template <int N, Prec P, bool Dual, int G, bool Sub = false, bool Rows = false>
 __global__ void __launch_bounds__(kTcThreads, 1)
 conv_tc_kernel(const TcJob job) {
   extern __shared__ __align__(128) unsigned char smem[];
@@ -442,17 +461,19 @@ conv_tc_kernel(const TcJob job) {
   constexpr bool kSplit = PrecTraits<P>::split;
   constexpr bool kSubAcc = Sub;
   static_assert(!Sub || (kSplit && G == 1), "sub-accumulation belongs to the split precision, one group per unit");
+  static_assert(!Rows || (Dual && G == 1 && !Sub && N % 32 == 0), "row-aligned units: dual layout, one group, plain chain");
+  constexpr int kRowsExtra = Rows ? 2 : 0;   // the two border positions between the unit's two image rows
   constexpr int kWpartsMax = Dual ? 2 : 1;   // weight rows per tap and K-half staged per chunk, in units of N
   const int dbg = kDebugHooks ? p.debug : 0;
   const int Wp = p.W + 2, Hp = p.H + 2;
   const int HpWp = Hp * Wp;
   const int halo = Wp + 1;
-  const int L = G * MT * 128 + 2 * halo;                // positions staged per plane
+  const int L = G * MT * 128 + 2 * halo + kRowsExtra;   // positions staged per plane
   const uint32_t a_bytes = (uint32_t)L * 32u;           // two planes
   const uint32_t stage_sz = (uint32_t)p.stage_stride;   // >= a_bytes + kWpartsMax * 9 * N * 32 (host-checked)
   const int S = p.stages;
   const int cps = p.cps;
-  const uint32_t run1 = (uint32_t)(G * MT * 128) * 16u;      // one plane of a 1x1 source's chunk (no halo)
+  const uint32_t run1 = (uint32_t)(G * MT * 128 + kRowsExtra) * 16u;      // one plane of a 1x1 source's chunk (no halo)
   const uint32_t w1_off = (uint32_t)cps * 2u * run1;          // weights of a 1x1 stage follow its cps chunk slots
   unsigned char* stage0 = smem;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)S * stage_sz);
@@ -509,7 +530,7 @@ conv_tc_kernel(const TcJob job) {
       const TcConv& c = job.c[phase];
       const int b = u / p.units_per_image;
       const int lu = u - b * p.units_per_image;
-      const int lo = lu * G * MT * 128;   // first staged position (= q0 - halo)
+      const int lo = Rows ? lu * 2 * Wp : lu * G * MT * 128;   // first staged position (= q0 - halo; Rows: start of padded row 2 lu)
       if (phase == 0 && job.ring > 0 && b >= job.ring) {
         const int v0 = u - job.ring * p.units_per_image;       // same local unit, `ring` images earlier
         ok = flag_wait3(job.flags2 + v0, lu > 0, lu < p.units_per_image - 1, 8, p.err, 6);
@@ -596,7 +617,8 @@ conv_tc_kernel(const TcJob job) {
     for (int item; (item = item_of(k)) < n_items && ok; ++k) {
       int phase, u;
       decode_item(item, T, D, n_phase, phase, u);
-      const uint32_t a_tile0 = (uint32_t)((G == 1 ? me * MTW : me * MT) * 128);     // first position of my tiles
+      // first position of my tiles (Rows: warp `me` issues for the tiles of image row `me` of the unit's pair)
+      const uint32_t a_tile0 = Rows ? (uint32_t)(me * Wp) : (uint32_t)((G == 1 ? me * MTW : me * MT) * 128);
       const int n_prog = job.prog_len[phase];
       int buf = 0;
       uint32_t d_unit = 0u;
@@ -829,7 +851,97 @@ conv_tc_kernel(const TcJob job) {
         }
       };
 
-      if constexpr (kSubAcc) {
+      if constexpr (Rows) {
+        // Row-aligned unit = image rows (2 lu, 2 lu + 1), 0-based.  This warp owns the vertical tile pair (A above B)
+        // of its 32 columns: W = 256 (two tiles per row): column half `tile_par`, all N = 32 channels; W = 128 (one tile
+        // per row): the whole row, channel block `tile_par` of the N = 64.  Every position is interior.
+        constexpr int TPR = MT / 2;                      // tiles per image row
+        static_assert(TPR == 1 || TPR == 2, "row-aligned units are a pair of image rows");
+        static_assert(TPR == 2 ? N == 32 : N == 64, "channel blocks of the two epilogue warps of a quadrant");
+        const int lu = u - b * p.units_per_image;
+        const int buf = kk & 1;
+        const uint32_t f_parity = ((uint32_t)kk >> 1) & 1u;
+        ++kk;
+        const int mtA = (TPR == 2) ? tile_par : 0, mtB = mtA + TPR;
+        const int nb = (TPR == 2) ? 0 : 32 * tile_par;   // first channel of my block
+        const int xc = (TPR == 2 ? tile_par * 128 : 0) + quad * 32 + lane;      // interior column, 0-based
+        const int64_t posA = (int64_t)(2 * lu + 1) * Wp + (xc + 1);
+        float rxA = 0.f, rxB = 0.f;
+        if (c.res_x != nullptr) {
+          const float* rp = c.res_x + ((int64_t)b * p.H + 2 * lu) * p.W + xc;
+          rxA = __ldg(rp);
+          rxB = __ldg(rp + p.W);
+        }
+        const float* resw_p = bias_s + 2 * N + phase * N;
+        const int Wq = (p.W >> 1) + 2, Hq = (p.H >> 1) + 2;
+        const int64_t pool_plane_stride = (int64_t)Hq * Wq * 8;
+        const int64_t pool_off = (int64_t)b * (N / 8) * pool_plane_stride + ((int64_t)(lu + 1) * Wq + ((xc >> 1) + 1)) * 8;
+        ok = mbar_wait_t(accf0 + 8 * buf, f_parity, p.err, 3, w_accf);
+        if (!ok) break;
+        tc_fence_after();
+        const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * kAccCols);
+#pragma unroll
+        for (int c0 = 0; c0 < 32; c0 += 16) {
+          uint32_t am[16], ac[16], bm[16], bc[16];
+          tc_ld16(t_row + (uint32_t)(mtA * TS + nb + c0), am);
+          tc_ld16(t_row + (uint32_t)(mtA * TS + N + nb + c0), ac);
+          tc_ld16(t_row + (uint32_t)(mtB * TS + nb + c0), bm);
+          tc_ld16(t_row + (uint32_t)(mtB * TS + N + nb + c0), bc);
+          tc_wait_ld();
+#pragma unroll
+          for (int g = 0; g < 2; ++g) {
+            const int ch = nb + c0 + g * 8;              // first of these 8 channels
+            const float4 b0 = *reinterpret_cast<const float4*>(bias_p + ch);
+            const float4 b1 = *reinterpret_cast<const float4*>(bias_p + ch + 4);
+            const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+            float rw[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            if (c.res_x != nullptr) {
+              const float4 r0 = *reinterpret_cast<const float4*>(resw_p + ch);
+              const float4 r1 = *reinterpret_cast<const float4*>(resw_p + ch + 4);
+              rw[0] = r0.x; rw[1] = r0.y; rw[2] = r0.z; rw[3] = r0.w; rw[4] = r1.x; rw[5] = r1.y; rw[6] = r1.z; rw[7] = r1.w;
+            }
+            uint32_t ah[4], al[4], bh[4], bl[4], ph[4], pl[4];
+#pragma unroll
+            for (int h = 0; h < 4; ++h) {
+              const int i0 = g * 8 + 2 * h, i1 = i0 + 1;
+              float a0 = fmaf(__uint_as_float(am[i0]) + __uint_as_float(ac[i0]), inv_scale, bb[2 * h]);
+              float a1 = fmaf(__uint_as_float(am[i1]) + __uint_as_float(ac[i1]), inv_scale, bb[2 * h + 1]);
+              float q0v = fmaf(__uint_as_float(bm[i0]) + __uint_as_float(bc[i0]), inv_scale, bb[2 * h]);
+              float q1v = fmaf(__uint_as_float(bm[i1]) + __uint_as_float(bc[i1]), inv_scale, bb[2 * h + 1]);
+              if (c.res_x != nullptr) {
+                a0 = fmaf(rxA, rw[2 * h], a0);
+                a1 = fmaf(rxA, rw[2 * h + 1], a1);
+                q0v = fmaf(rxB, rw[2 * h], q0v);
+                q1v = fmaf(rxB, rw[2 * h + 1], q1v);
+              }
+              a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); q0v = fmaxf(q0v, 0.f); q1v = fmaxf(q1v, 0.f);
+              // the 2 x 2 window: this thread's two rows, then the neighbouring column (lanes 2k, 2k + 1)
+              float m0 = fmaxf(a0, q0v), m1 = fmaxf(a1, q1v);
+              m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1));
+              m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1));
+              vmax = fmaxf(vmax, fmaxf(m0, m1));
+              a0 = fminf(a0, 65504.f); a1 = fminf(a1, 65504.f); q0v = fminf(q0v, 65504.f); q1v = fminf(q1v, 65504.f);
+              m0 = fminf(m0, 65504.f); m1 = fminf(m1, 65504.f);
+              ah[h] = pack_rn<P>(a0, a1); al[h] = pack_lo_f16(a0, a1, ah[h]);
+              bh[h] = pack_rn<P>(q0v, q1v); bl[h] = pack_lo_f16(q0v, q1v, bh[h]);
+              ph[h] = pack_rn<P>(m0, m1); pl[h] = pack_lo_f16(m0, m1, ph[h]);
+            }
+            const int64_t plane_off = img_off + (int64_t)(ch / 8) * out_plane_stride;
+            st16(c.out + plane_off + posA * 8, make_uint4(ah[0], ah[1], ah[2], ah[3]));
+            st16(c.out_lo + plane_off + posA * 8, make_uint4(al[0], al[1], al[2], al[3]));
+            st16(c.out + plane_off + (posA + Wp) * 8, make_uint4(bh[0], bh[1], bh[2], bh[3]));
+            st16(c.out_lo + plane_off + (posA + Wp) * 8, make_uint4(bl[0], bl[1], bl[2], bl[3]));
+            if ((lane & 1) == 0) {
+              const int64_t po = pool_off + (int64_t)(ch / 8) * pool_plane_stride;
+              st16(c.pool_out + po, make_uint4(ph[0], ph[1], ph[2], ph[3]));
+              st16(c.pool_lo + po, make_uint4(pl[0], pl[1], pl[2], pl[3]));
+            }
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(acce0 + 8 * buf);
+      } else if constexpr (kSubAcc) {
         // n_sub accumulation groups of this unit arrive one buffer turn after the other; their sums live in registers
         // (this warp's MT / 2 tiles x N columns of its 32 positions) and are added in float32, round to nearest.
         const int n_sub = c.n_sub;

@@ -193,6 +193,42 @@ def test_fused_resblock_launch_is_bit_identical(sd_seed0, clip60, monkeypatch):
         eng.close()
 
 
+def test_folded_maxpool_is_bit_identical(sd_seed0, clip60, monkeypatch):
+    """conv1_1 / conv2_1 second launches on row-aligned units with MaxPool2d(2) in the epilogue (default, f16x3) against
+    the flat geometry + pool_planar (SS_TC_POOL_FOLD=0): the same MMAs per output position and max commuting with the
+    monotonic hi / lo split make every activation, hence every logit, bit-identical; batch sizes around the grid size
+    and an odd one; nothing may be written outside the tensors (the borders are no longer rewritten by the epilogue).
+    (pool_planar keeps the operand pair OF the maximum for the same reason: a fresh split of hi + lo differs from it
+    when lo is exactly half an ulp of hi, one value in 4,096.)"""
+    from oracle import postproc as pp
+    from softspoken_b200.engine import Engine
+    g = load_golden("model_seed0.npz")
+    padded = torch.from_numpy(pp.pad_audio(clip60)).cuda()
+    eng = Engine(sd_seed0, 0, max_batch=53, mode="f16x3")
+    for n in (1, 5, 48, 53):
+        mel = eng.features(padded, torch.from_numpy(g["starts"][:n]))
+        monkeypatch.setenv("SS_TC_POOL_FOLD", "0")
+        plain = eng.classify(mel)
+        # 0 conv1, 1 conv2 (full resolution); 12 / 13 the pooled tensors: hi operands alone (+ 0x100), lo alone (+ 0x200)
+        ids = (0, 1, 12 + 0x100, 12 + 0x200, 13 + 0x100, 13 + 0x200)
+        acts_plain = [_dump(eng, w, n) for w in ids]
+        monkeypatch.delenv("SS_TC_POOL_FOLD")
+        folded = eng.classify(mel)
+        acts_folded = [_dump(eng, w, n) for w in ids]
+        eng.check_health()
+        for w, a, b in zip(ids, acts_plain, acts_folded):
+            assert torch.equal(a, b), (n, hex(w))
+        pooled = (acts_folded[2] + acts_folded[3]) / 2           # the dumps of one part return it twice
+        assert torch.equal(pooled, torch.nn.functional.max_pool2d(acts_folded[0], 2)), n
+        assert torch.equal(plain, folded), n
+        # the flat geometry after the row-aligned one, in the same tensors: borders still zero
+        monkeypatch.setenv("SS_TC_POOL_FOLD", "0")
+        assert torch.equal(plain, eng.classify(mel)), n
+        monkeypatch.delenv("SS_TC_POOL_FOLD")
+    assert eng.check_guards() == 0
+    eng.close()
+
+
 def test_fused_mask_head_close_to_two_kernel_form(sd_seed0, clip60, monkeypatch):
     """conv_flatten folded into conv9_1's epilogue (default) against the separate mask-head kernel reading the stored
     hi/lo activations (SS_TC_FUSE_HEAD=0): same arithmetic up to fp32 summation order and the 2^-22 split rounding."""

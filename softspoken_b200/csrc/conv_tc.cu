@@ -563,9 +563,10 @@ int launch_conv_npg(TcJob job, int B, cudaStream_t st) {
   // whether the pooled tensor was written; here only the geometry is checked.
   constexpr bool kCanRows = PrecTraits<P>::split && Dual && G == 1 && (N == 32 || N == 64);
   const bool rows = p.rows != 0;
-  SS_REQUIRE(!rows || (kCanRows && job.n_phase == 1 && p.W == (MT / 2) * 128 && p.H % 2 == 0 && p.pool_out && p.pool_lo &&
-                       !p.upsample && !p.head_w && p.out && p.out_lo),
+  SS_REQUIRE(!rows || (kCanRows && job.n_phase == 1 && p.W == (MT / 2) * 128 && p.H % 2 == 0),
              SS_E_ARG, "row-aligned conv launch: unsupported geometry (N %d, %d x %d)", N, p.H, p.W);
+  SS_REQUIRE(!p.pool_out || (rows && p.pool_lo && !p.upsample && !p.head_w && p.out && p.out_lo), SS_E_ARG,
+             "folded MaxPool needs a row-aligned launch that stores its activations");
   const size_t rows_extra = rows ? 64 : 0;       // two more positions per staged plane pair (conv_tc_kernel.cuh: kRowsExtra)
   const size_t sb = stage_bytes(N, p.W, G * MT, Dual) + rows_extra;
   // Ring slot size.  Every stage costs a fixed hand-over (full/empty barrier round trip and an MMA-issue bubble,
@@ -845,15 +846,24 @@ int tc_res_block(TcState* s, int which, const Tensor& x, int x_plane0, Tensor& o
   // dual layout, image width = the tiles of a unit's row (conv1_1: 256 = 2 x 128 at N = 32; conv2_1: 128 at N = 64),
   // separate launches, plain accumulation chain, one group per unit.  SS_TC_POOL_FOLD=0 keeps pool_planar (A/B runs).
   if (pooled) *pooled = false;
-  if (pool && is_dual(s->prec, N) && !fuse && !upsample && !head_w) {
-    const char* pf = getenv("SS_TC_POOL_FOLD");
+  // Row-aligned units (TcConv::rows) for every launch whose geometry allows them: dual layout, image width = the
+  // tiles of a unit's row (256 = 2 x 128 at N = 32: conv1_1, conv9_1; 128 at N = 64: conv2_1, conv8), separate
+  // launches, plain accumulation chain, one group per unit.  No border position is computed (64 / 32 units per image
+  // instead of 65.5 / 33.5) and the 2 x 2 windows of a MaxPool lie inside a unit.  SS_TC_ROWS=0: flat units (A/B runs).
+  bool rows_ok = false;
+  if (is_dual(s->prec, N) && !fuse) {
+    const char* rw = getenv("SS_TC_ROWS");
     const char* sb = getenv("SS_TC_SUB");
     const char* pp = getenv("SS_TC_PAIRS");
     const int tiles_per_row = (N == 32) ? 2 : 1;          // MT / 2 of the dual layout
     const bool plain = (sb == nullptr || atoi(sb) <= 1) && (pp == nullptr || (atoi(pp) & 1) == 0);
+    rows_ok = plain && x.W == tiles_per_row * 128 && x.H % 2 == 0;
+    if (rows_ok && (rw == nullptr || atoi(rw) != 0)) { p.rows = 1; q.rows = 1; }
+  }
+  if (pool && rows_ok && !upsample && !head_w) {
+    const char* pf = getenv("SS_TC_POOL_FOLD");
     const int fold_mask = pf ? atoi(pf) : 3;              // bit 0: conv1_1 (N = 32), bit 1: conv2_1 (N = 64)
-    if ((fold_mask & (N == 32 ? 1 : 2)) != 0 && plain && x.W == tiles_per_row * 128 && x.H % 2 == 0 &&
-        pool->planes == N / 8 && pool->H == x.H / 2 && pool->W == x.W / 2) {
+    if ((fold_mask & (N == 32 ? 1 : 2)) != 0 && pool->planes == N / 8 && pool->H == x.H / 2 && pool->W == x.W / 2) {
       q.rows = 1;
       q.pool_out = pool->data;
       q.pool_lo = pool->lo;

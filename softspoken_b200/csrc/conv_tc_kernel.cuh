@@ -851,7 +851,9 @@ conv_tc_kernel(const TcJob job) {
         }
       };
 
-      if constexpr (Rows) {
+      bool unit_done = false;      // the folded-pool epilogue below took the unit
+      if constexpr (Rows) if (c.pool_out != nullptr) {
+        unit_done = true;
         // Row-aligned unit = image rows (2 lu, 2 lu + 1), 0-based.  This warp owns the vertical tile pair (A above B)
         // of its 32 columns: W = 256 (two tiles per row): column half `tile_par`, all N = 32 channels; W = 128 (one tile
         // per row): the whole row, channel block `tile_par` of the N = 64.  Every position is interior.
@@ -941,7 +943,8 @@ conv_tc_kernel(const TcJob job) {
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(acce0 + 8 * buf);
-      } else if constexpr (kSubAcc) {
+      }
+      if constexpr (kSubAcc) {
         // n_sub accumulation groups of this unit arrive one buffer turn after the other; their sums live in registers
         // (this warp's MT / 2 tiles x N columns of its 32 positions) and are added in float32, round to nearest.
         const int n_sub = c.n_sub;
@@ -986,21 +989,28 @@ conv_tc_kernel(const TcJob job) {
             finalize(v, n0, pos, pre);
           }
         }
-      } else {
+      } else if (!unit_done) {
        for (int g = 0; g < G && ok; ++g, ++kk) {
         const int buf = (G == 1) ? (kk & 1) : g;
         const uint32_t f_parity = (G == 1) ? (((uint32_t)kk >> 1) & 1u) : ((uint32_t)k & 1u);
-        const int q0 = halo + ((u - b * p.units_per_image) * G + g) * MT * 128;
+        // first position of tile mt of the unit: consecutive runs of 128, or (row-aligned units) MT / 2 tiles in each
+        // of the image rows 2 lu + 1 and 2 lu + 2 of the padded tensor
+        const int q0 = Rows ? (2 * (u - b * p.units_per_image) + 1) * Wp + 1
+                            : halo + ((u - b * p.units_per_image) * G + g) * MT * 128;
+        auto tile_pos = [&](const int mt) {
+          if constexpr (Rows) return q0 + (mt / (MT / 2)) * Wp + (mt % (MT / 2)) * 128 + quad * 32 + lane;
+          else return q0 + mt * 128 + quad * 32 + lane;
+        };
         // this warp's tiles: tile_par, tile_par + 2, ...; the global operands of a tile are fetched one tile ahead
         // (the first before the wait for the accumulators), the loop stays rolled (code size)
-        TilePre cur = preload(q0 + tile_par * 128 + quad * 32 + lane);
+        TilePre cur = preload(tile_pos(tile_par));
         ok = mbar_wait_t(accf0 + 8 * buf, f_parity, p.err, 3, w_accf);
         if (!ok) break;
         tc_fence_after();
 #pragma unroll 1
         for (int mt = tile_par; mt < MT; mt += 2) {
-          const int pos = q0 + mt * 128 + quad * 32 + lane;
-          const TilePre nxt = (mt + 2 < MT) ? preload(pos + 256) : cur;
+          const int pos = tile_pos(mt);
+          const TilePre nxt = (mt + 2 < MT) ? preload(tile_pos(mt + 2)) : cur;
 #pragma unroll
           for (int n0 = 0; n0 < N; n0 += 32) {
             uint32_t v[32];

@@ -193,11 +193,12 @@ def test_fused_resblock_launch_is_bit_identical(sd_seed0, clip60, monkeypatch):
         eng.close()
 
 
-def test_folded_maxpool_is_bit_identical(sd_seed0, clip60, monkeypatch):
-    """conv1_1 / conv2_1 second launches on row-aligned units with MaxPool2d(2) in the epilogue (default, f16x3) against
-    the flat geometry + pool_planar (SS_TC_POOL_FOLD=0): the same MMAs per output position and max commuting with the
-    monotonic hi / lo split make every activation, hence every logit, bit-identical; batch sizes around the grid size
-    and an odd one; nothing may be written outside the tensors (the borders are no longer rewritten by the epilogue).
+def test_row_aligned_units_and_folded_maxpool_are_bit_identical(sd_seed0, clip60, monkeypatch):
+    """Row-aligned work units (default for the f16x3 launches at 128 x 256 / N = 32 and 64 x 128 / N = 64: conv1_1, conv2_1,
+    conv8, conv9_1) and MaxPool2d(2) folded into the conv1_1 / conv2_1 epilogues, against flat units + pool_planar
+    (SS_TC_ROWS=0 SS_TC_POOL_FOLD=0): the same MMAs per output position and max commuting with the monotonic hi / lo
+    split make every activation, hence every logit, bit-identical; batch sizes around the grid size and an odd one;
+    nothing may be written outside the tensors (row-aligned launches never rewrite the zero borders).
     (pool_planar keeps the operand pair OF the maximum for the same reason: a fresh split of hi + lo differs from it
     when lo is exactly half an ulp of hi, one value in 4,096.)"""
     from oracle import postproc as pp
@@ -205,26 +206,35 @@ def test_folded_maxpool_is_bit_identical(sd_seed0, clip60, monkeypatch):
     g = load_golden("model_seed0.npz")
     padded = torch.from_numpy(pp.pad_audio(clip60)).cuda()
     eng = Engine(sd_seed0, 0, max_batch=53, mode="f16x3")
+    knobs = ("SS_TC_ROWS", "SS_TC_POOL_FOLD")
+    # 0 conv1, 1 conv2, 7 up(conv7), 8 up(conv8) (written by row-aligned up-sampling epilogues), 10 conv1_1's
+    # intermediate; 12 / 13 the pooled tensors: hi operands alone (+ 0x100), lo alone (+ 0x200)
+    ids = (0, 1, 7, 8, 10, 12 + 0x100, 12 + 0x200, 13 + 0x100, 13 + 0x200)
+
+    def run(env, mel, n):
+        for k in knobs:
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        logits = eng.classify(mel)
+        acts = [_dump(eng, w, n) for w in ids]
+        eng.check_health()
+        for k in knobs:
+            monkeypatch.delenv(k, raising=False)
+        return logits, acts
+
     for n in (1, 5, 48, 53):
         mel = eng.features(padded, torch.from_numpy(g["starts"][:n]))
-        monkeypatch.setenv("SS_TC_POOL_FOLD", "0")
-        plain = eng.classify(mel)
-        # 0 conv1, 1 conv2 (full resolution); 12 / 13 the pooled tensors: hi operands alone (+ 0x100), lo alone (+ 0x200)
-        ids = (0, 1, 12 + 0x100, 12 + 0x200, 13 + 0x100, 13 + 0x200)
-        acts_plain = [_dump(eng, w, n) for w in ids]
-        monkeypatch.delenv("SS_TC_POOL_FOLD")
-        folded = eng.classify(mel)
-        acts_folded = [_dump(eng, w, n) for w in ids]
-        eng.check_health()
-        for w, a, b in zip(ids, acts_plain, acts_folded):
-            assert torch.equal(a, b), (n, hex(w))
-        pooled = (acts_folded[2] + acts_folded[3]) / 2           # the dumps of one part return it twice
-        assert torch.equal(pooled, torch.nn.functional.max_pool2d(acts_folded[0], 2)), n
-        assert torch.equal(plain, folded), n
-        # the flat geometry after the row-aligned one, in the same tensors: borders still zero
-        monkeypatch.setenv("SS_TC_POOL_FOLD", "0")
-        assert torch.equal(plain, eng.classify(mel)), n
-        monkeypatch.delenv("SS_TC_POOL_FOLD")
+        plain, acts_plain = run({"SS_TC_ROWS": "0", "SS_TC_POOL_FOLD": "0"}, mel, n)
+        for env in ({}, {"SS_TC_POOL_FOLD": "0"}, {"SS_TC_ROWS": "0"}, {"SS_TC_POOL_FOLD": "1"}, {"SS_TC_POOL_FOLD": "2"}):
+            got, acts = run(env, mel, n)
+            for w, a, b in zip(ids, acts_plain, acts):
+                assert torch.equal(a, b), (n, env, hex(w))
+            assert torch.equal(plain, got), (n, env)
+        pooled = (acts_plain[5] + acts_plain[6]) / 2           # the dumps of one part return it twice
+        assert torch.equal(pooled, torch.nn.functional.max_pool2d(acts_plain[0], 2)), n
+        # flat units after row-aligned ones, in the same tensors: the borders are still zero
+        assert torch.equal(plain, run({"SS_TC_ROWS": "0", "SS_TC_POOL_FOLD": "0"}, mel, n)[0]), n
     assert eng.check_guards() == 0
     eng.close()
 

@@ -418,6 +418,11 @@ struct PackedConv {
 
 struct TcBlock {
   PackedConv res, c1, c2;
+  // Decoder blocks at 128 x 256 and 64 x 128 (split precision): conv1 of cat([skip, up(below)]) packed as two sources —
+  // the skip channels with their nine taps, the up-sampled channels ("rowdup", conv_tc_kernel.cuh) with the twelve
+  // row-merged tap matrices [top: w(-1,.), w(0,.)+w(+1,.) | bottom: w(-1,.)+w(0,.), w(+1,.)].  skip_cin = 0: not built.
+  PackedConv c1_skip, c1_up;
+  int skip_cin = 0;
   float* bias2 = nullptr;       // b2 + b_res (the fused second launch)
   const float* bias1 = nullptr;
   float inv_scale1 = 1.f, inv_scale2 = 1.f;
@@ -549,6 +554,11 @@ int pack_conv(TcState* st, const float* w, int taps, int cin, int cout, float sc
 }
 
 constexpr size_t kSmemTail = (2 * kMaxStages + 4) * 8 + 5 * 128 * 4 + 16;   // barriers + bias and scalar-residual weights of both phases + TMEM slot
+// Launches with row-merged taps stage 12 tap matrices per chunk: four ring slots of conv9_1's first convolution
+// (57,600 bytes each) fit only with the device's whole opt-in shared memory and a tail sized for the launch's N
+// (three slots measured +2 % on that launch, which cancels what the merged taps save).
+constexpr size_t kSmemBudgetMax = 227 * 1024;
+constexpr size_t smem_tail_n(int n) { return (2 * kMaxStages + 4) * 8 + 5 * (size_t)n * 4 + 16; }
 
 constexpr int kDefaultRing = 8;    // images of the intermediate tensor kept by a fused ResBlock launch (0: whole batch)
 constexpr int kDefaultLag = 160;   // units by which conv2 trails conv1 in a fused ResBlock launch (> one round of 148 CTAs)
@@ -563,12 +573,19 @@ int launch_conv_npg(TcJob job, int B, cudaStream_t st) {
   // whether the pooled tensor was written; here only the geometry is checked.
   constexpr bool kCanRows = PrecTraits<P>::split && Dual && G == 1 && (N == 32 || N == 64);
   const bool rows = p.rows != 0;
-  SS_REQUIRE(!rows || (kCanRows && job.n_phase == 1 && p.W == (MT / 2) * 128 && p.H % 2 == 0),
+  const int tpr = p.W / 128;                     // tiles per image row of a row-aligned unit
+  SS_REQUIRE(!rows || (kCanRows && job.n_phase == 1 && (tpr == 1 || tpr == 2) && p.W == tpr * 128 &&
+                       MT % (2 * tpr) == 0 && p.H % (MT / tpr) == 0),
              SS_E_ARG, "row-aligned conv launch: unsupported geometry (N %d, %d x %d)", N, p.H, p.W);
-  SS_REQUIRE(!p.pool_out || (rows && p.pool_lo && !p.upsample && !p.head_w && p.out && p.out_lo), SS_E_ARG,
-             "folded MaxPool needs a row-aligned launch that stores its activations");
-  const size_t rows_extra = rows ? 64 : 0;       // two more positions per staged plane pair (conv_tc_kernel.cuh: kRowsExtra)
-  const size_t sb = stage_bytes(N, p.W, G * MT, Dual) + rows_extra;
+  const int unit_rows = rows ? MT / tpr : 0;
+  SS_REQUIRE(!p.pool_out || (rows && unit_rows == 2 && p.pool_lo && !p.upsample && !p.head_w && p.out && p.out_lo),
+             SS_E_ARG, "folded MaxPool needs a row-aligned launch on row pairs that stores its activations");
+  bool any_dup = false;
+  for (int i = 0; i < p.n_src; ++i) any_dup |= p.src[i].taps == 12;
+  SS_REQUIRE(!any_dup || rows, SS_E_ARG, "row-merged taps need a row-aligned launch");
+  const size_t rows_extra = rows ? (size_t)(2 * unit_rows - 2) * 32 : 0;   // border positions between the unit's rows (kRowsExtra)
+  const size_t sb = stage_bytes(N, p.W, G * MT, Dual, any_dup ? 12 : 9) + rows_extra;
+  const size_t budget = any_dup ? kSmemBudgetMax : kSmemBudget, tail = any_dup ? smem_tail_n(N) : kSmemTail;
   // Ring slot size.  Every stage costs a fixed hand-over (full/empty barrier round trip and an MMA-issue bubble,
   // ~500-1000 cycles measured with the tuning hooks), which a 3x3 stage hides behind its 9 x MT MMAs and a 1x1 stage
   // (MT MMAs per chunk) does not: 1x1 sources therefore pack several K-chunks into one slot, and when a launch has
@@ -585,19 +602,20 @@ int launch_conv_npg(TcJob job, int B, cudaStream_t st) {
   int cps = (int)(sb / chunk1);
   for (int want = (most1 < cap ? most1 : cap); want > cps; --want) {
     const size_t need = (size_t)want * chunk1;
-    if ((kSmemBudget - kSmemTail) / need >= 3) { stride = need > sb ? need : sb; cps = want; break; }
+    if ((budget - tail) / need >= 3) { stride = need > sb ? need : sb; cps = want; break; }
   }
   if (cps > cap) cps = cap;
   p.cps = cps < 1 ? 1 : cps;
   stride = (stride + 127) & ~(size_t)127;
   p.stage_stride = (int)stride;
-  int stages = (int)((kSmemBudget - kSmemTail) / stride);
+  int stages = (int)((budget - tail) / stride);
   if (stages > kMaxStages) stages = kMaxStages;
+  { const char* ms = getenv("SS_TC_MAX_STAGES"); if (ms && atoi(ms) >= 2 && stages > atoi(ms)) stages = atoi(ms); }   // tuning
   SS_REQUIRE(stages >= 2, SS_E_ARG, "conv stage of %zu bytes does not fit twice in shared memory", stride);
   p.stages = stages;
   static const int debug = [] { const char* e = getenv("SS_TC_DEBUG"); return e ? atoi(e) : 0; }();
   p.debug = debug;
-  const size_t smem = (size_t)stages * stride + kSmemTail;
+  const size_t smem = (size_t)stages * stride + tail;
   constexpr bool kCanSub = PrecTraits<P>::split && G == 1;
   static bool configured = false;
   if (!configured) {
@@ -609,7 +627,7 @@ int launch_conv_npg(TcJob job, int B, cudaStream_t st) {
     configured = true;
   }
   const int positions = p.H * (p.W + 2) - 2;          // (1,1) .. (H,W) in flattened padded coordinates
-  p.units_per_image = rows ? p.H / 2 : (positions + G * MT * 128 - 1) / (G * MT * 128);
+  p.units_per_image = rows ? p.H / unit_rows : (positions + G * MT * 128 - 1) / (G * MT * 128);
   p.total_units = p.units_per_image * B;
   for (int ph = 0; ph < job.n_phase; ++ph)
     SS_REQUIRE(job.c[ph].relu == 1, SS_E_ARG, "conv_tc_kernel applies ReLU unconditionally");
@@ -626,7 +644,7 @@ int launch_conv_npg(TcJob job, int B, cudaStream_t st) {
   for (int ph = 0; ph < job.n_phase; ++ph) {
     int most = 1;
     for (int i = 0; i < job.c[ph].n_src; ++i)
-      if (job.c[ph].src[i].taps == 9 && job.c[ph].src[i].n_chunks > most) most = job.c[ph].src[i].n_chunks;
+      if (job.c[ph].src[i].taps >= 9 && job.c[ph].src[i].n_chunks > most) most = job.c[ph].src[i].n_chunks;
     int cap = (p.H >= 64) ? sub_big : sub_deep;
     if (cap < 1) cap = 1;
     job.c[ph].n_sub = kCanSub ? (most < cap ? most : cap) : 1;
@@ -651,7 +669,7 @@ int launch_conv_npg(TcJob job, int B, cudaStream_t st) {
         for (int kc = lo; kc < hi; kc += per_stage) {
           const int n = (hi - kc < per_stage) ? (hi - kc) : per_stage;
           SS_REQUIRE(len < kMaxProg && kc < 64 && n < 8 && si < 8, SS_E_ARG, "conv stage program too long (%d stages)", len);
-          job.prog[ph][len] = prog_entry(si, kc, n, len == first_of_group, false, src.taps == 9, src.kind);
+          job.prog[ph][len] = prog_entry(si, kc, n, len == first_of_group, false, src.taps >= 9, src.kind, src.taps == 12);
           ++len;
         }
       }
@@ -694,11 +712,15 @@ int launch_conv_npg(TcJob job, int B, cudaStream_t st) {
     if constexpr (kCanRows) {
       static bool configured_rows = false;
       if (!configured_rows) {
-        SS_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<N, P, Dual, G, false, true>,
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget));
+        SS_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<N, P, Dual, G, false, 1>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudgetMax));
+        if constexpr (MT % 4 == 0)
+          SS_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<N, P, Dual, G, false, 2>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudgetMax));
         configured_rows = true;
       }
-      conv_tc_kernel<N, P, Dual, G, false, true><<<grid, kTcThreads, smem, st>>>(job);
+      if (tpr == 1) conv_tc_kernel<N, P, Dual, G, false, 1><<<grid, kTcThreads, smem, st>>>(job);
+      else if constexpr (MT % 4 == 0) conv_tc_kernel<N, P, Dual, G, false, 2><<<grid, kTcThreads, smem, st>>>(job);
     }
   } else if constexpr (kCanSub) {
     if (any_sub) conv_tc_kernel<N, P, Dual, G, true><<<grid, kTcThreads, smem, st>>>(job);
@@ -792,8 +814,6 @@ int tc_res_block(TcState* s, int which, const Tensor& x, int x_plane0, Tensor& o
   Tensor& t = s->t[which];
   const int N = rb.c1.n;
   TcConv p{};
-  add_sources(&p, s, x, x_plane0, rb.c1, Terms::Corrections);
-  add_sources(&p, s, x, x_plane0, rb.c1, Terms::Main);
   p.H = x.H; p.W = x.W;
   p.bias = rb.bias1;
   p.inv_scale = rb.inv_scale1;
@@ -851,16 +871,31 @@ int tc_res_block(TcState* s, int which, const Tensor& x, int x_plane0, Tensor& o
   // launches, plain accumulation chain, one group per unit.  No border position is computed (64 / 32 units per image
   // instead of 65.5 / 33.5) and the 2 x 2 windows of a MaxPool lie inside a unit.  SS_TC_ROWS=0: flat units (A/B runs).
   bool rows_ok = false;
+  int unit_rows = 0;
   if (is_dual(s->prec, N) && !fuse) {
     const char* rw = getenv("SS_TC_ROWS");
     const char* sb = getenv("SS_TC_SUB");
     const char* pp = getenv("SS_TC_PAIRS");
-    const int tiles_per_row = (N == 32) ? 2 : 1;          // MT / 2 of the dual layout
+    const int mt = (N == 32) ? 4 : 2;                     // tiles per unit of the dual layout
+    const int tpr = x.W / 128;                            // tiles per image row
     const bool plain = (sb == nullptr || atoi(sb) <= 1) && (pp == nullptr || (atoi(pp) & 1) == 0);
-    rows_ok = plain && x.W == tiles_per_row * 128 && x.H % 2 == 0;
+    rows_ok = plain && (tpr == 1 || tpr == 2) && x.W == tpr * 128 && mt % (2 * tpr) == 0 && x.H % (mt / tpr) == 0;
+    unit_rows = rows_ok ? mt / tpr : 0;
     if (rows_ok && (rw == nullptr || atoi(rw) != 0)) { p.rows = 1; q.rows = 1; }
   }
-  if (pool && rows_ok && !upsample && !head_w) {
+  // conv1 of a decoder block on a row-aligned launch: the up-sampled half of its input as a "rowdup" source (six tap
+  // MMAs per tile instead of nine; SS_TC_TAPMERGE=0 keeps the nine)
+  {
+    const char* tm = getenv("SS_TC_TAPMERGE");
+    if (p.rows && rb.skip_cin > 0 && (tm == nullptr || atoi(tm) != 0)) {
+      add_sources(&p, s, x, x_plane0, rb.c1_skip, Terms::Main);
+      add_sources(&p, s, x, x_plane0 + rb.skip_cin / 8, rb.c1_up, Terms::Main);
+    } else {
+      add_sources(&p, s, x, x_plane0, rb.c1, Terms::Corrections);
+      add_sources(&p, s, x, x_plane0, rb.c1, Terms::Main);
+    }
+  }
+  if (pool && rows_ok && unit_rows == 2 && !upsample && !head_w) {
     const char* pf = getenv("SS_TC_POOL_FOLD");
     const int fold_mask = pf ? atoi(pf) : 3;              // bit 0: conv1_1 (N = 32), bit 1: conv2_1 (N = 64)
     if ((fold_mask & (N == 32 ? 1 : 2)) != 0 && pool->planes == N / 8 && pool->H == x.H / 2 && pool->W == x.W / 2) {
@@ -944,6 +979,7 @@ int tc_build_state(ss_ctx* ctx, Prec prec, TcState* s) {
     if ((rc = fetch(rb.res, &wr, &br))) return rc;
     const float s1 = weight_scale(prec, {&w1});
     const float s2 = weight_scale(prec, {&w2, &wr});       // conv2 and the residual share one accumulator
+    float s1_used = s1;
     if (i == RB_CONV1) {
       // C_in = 1: the nine taps become input channels 0..8 of a 1x1 convolution over the im2col'd operand
       // tensor written by mel_to_planar; the residual 1x1 reads the centre tap (channel 4).
@@ -958,8 +994,41 @@ int tc_build_state(ss_ctx* ctx, Prec prec, TcState* s) {
       if ((rc = pack_conv(s, w1.data(), 9, rb.c1.cin, rb.c1.cout, s1, &s->rb[i].c1))) return rc;
       if ((rc = pack_conv(s, wr.data(), 1, rb.res.cin, rb.res.cout, s2, &s->rb[i].res))) return rc;
     }
+    if ((i == RB_CONV8 || i == RB_CONV9) && is_dual(prec, rb.c1.cout)) {
+      // cat([skip, up]): the first half of the input channels is the encoder's skip tensor, the second the 2x
+      // up-sampled output of the block below (classify_tc_p: out_plane0 of conv7 / conv8 = half of the planes)
+      const int cin = rb.c1.cin, co = rb.c1.cout, cs = cin / 2, cu = cin - cs;
+      std::vector<float> ws((size_t)9 * cs * co), wu((size_t)12 * cu * co);
+      auto w_at = [&](int t, int c, int n) { return w1[((size_t)t * cin + c) * co + n]; };
+      for (int t = 0; t < 9; ++t)
+        for (int c = 0; c < cs; ++c)
+          for (int n = 0; n < co; ++n) ws[((size_t)t * cs + c) * co + n] = w_at(t, c, n);
+      for (int dx = 0; dx < 3; ++dx)
+        for (int c = 0; c < cu; ++c)
+          for (int n = 0; n < co; ++n) {
+            const float wm = w_at(0 + dx, cs + c, n), w0 = w_at(3 + dx, cs + c, n), wp = w_at(6 + dx, cs + c, n);
+            wu[((size_t)(0 + dx) * cu + c) * co + n] = wm;            // top rows: input row y - 1
+            wu[((size_t)(3 + dx) * cu + c) * co + n] = w0 + wp;       //           rows y, y + 1 (identical)
+            wu[((size_t)(6 + dx) * cu + c) * co + n] = wm + w0;       // bottom rows: rows y - 1, y (identical)
+            wu[((size_t)(9 + dx) * cu + c) * co + n] = wp;            //              row y + 1
+          }
+      const float s1m = weight_scale(prec, {&w1, &wu});
+      SS_REQUIRE(s1m == s1 || s1m * 2.f == s1, SS_E_BLOB, "row-merged weights of block %d need an unexpected scale", i);
+      // one scale per accumulator: the merged matrices may be up to twice the largest single weight
+      if (s1m != s1) {
+        PackedConv old = s->rb[i].c1;
+        if (old.w) cudaFree(old.w);
+        if (old.w_hi) cudaFree(old.w_hi);
+        s->rb[i].c1 = PackedConv{};
+        if ((rc = pack_conv(s, w1.data(), 9, rb.c1.cin, rb.c1.cout, s1m, &s->rb[i].c1))) return rc;
+        s1_used = s1m;
+      }
+      if ((rc = pack_conv(s, ws.data(), 9, cs, co, s1m, &s->rb[i].c1_skip))) return rc;
+      if ((rc = pack_conv(s, wu.data(), 12, cu, co, s1m, &s->rb[i].c1_up))) return rc;
+      s->rb[i].skip_cin = cs;
+    }
     if ((rc = pack_conv(s, w2.data(), 9, rb.c2.cin, rb.c2.cout, s2, &s->rb[i].c2))) return rc;
-    s->rb[i].inv_scale1 = 1.f / s1;
+    s->rb[i].inv_scale1 = 1.f / s1_used;
     s->rb[i].inv_scale2 = 1.f / s2;
     for (size_t k = 0; k < b2.size(); ++k) b2[k] += br[k];
     SS_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&s->rb[i].bias2), b2.size() * 4));
@@ -1099,7 +1168,7 @@ void tc_free_state(ss_ctx* ctx, TcState* s) {
   for (int i = 0; i < RB_COUNT; ++i) {
     free_guarded(s->t[i].alloc);
     free_guarded(s->t[i].alloc_lo);
-    for (PackedConv* pc : {&s->rb[i].c1, &s->rb[i].c2, &s->rb[i].res}) {
+    for (PackedConv* pc : {&s->rb[i].c1, &s->rb[i].c2, &s->rb[i].res, &s->rb[i].c1_skip, &s->rb[i].c1_up}) {
       if (pc->w) cudaFree(pc->w);
       if (pc->w_hi) cudaFree(pc->w_hi);
     }

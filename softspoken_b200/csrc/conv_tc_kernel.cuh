@@ -250,7 +250,7 @@ struct TcSource {
   int planes_total;    // C/8 of that tensor
   int plane0;          // first plane this convolution reads
   int n_chunks;        // C_in / 16
-  int taps;            // 9 (3x3) or 1 (1x1, centre)
+  int taps;            // 9 (3x3), 1 (1x1, centre) or 12 (3x3 over a row-replicated image: see "rowdup" below)
   int kind;            // 0: N columns into the main columns; 1: 2N columns (main | correction), dual weights;
                        // 2: N columns into the correction columns
   int ring;            // 0: image b of the batch is image b of the tensor; R > 0: it lives in slot b % R (the
@@ -331,11 +331,18 @@ struct TcConv {
 // issuers walk the same flat list instead of nested sub-item / source / chunk loops: the MMA-issuing thread's
 // bookkeeping between two bursts of MMAs is a tensor-pipe bubble, so it is one table look-up per stage.
 //   bits 0-2 source | 3-8 first chunk | 9-11 chunks in the stage | 12 first stage of an accumulation group
-//   | 13 last stage of the group | 14 the source is 3x3 | 15-16 source kind
+//   | 13 last stage of the group | 14 the source is 3x3 | 15-16 source kind | 17 "rowdup" 3x3 source
+//
+// "rowdup" (row-aligned launches only): the source planes hold a nearest-neighbour 2x up-sampled image, i.e. image rows
+// 2k and 2k+1 are identical.  For an output row at the TOP of such a pair the taps dy = 0 and dy = +1 read the same
+// data, for one at the BOTTOM dy = -1 and dy = 0 do, so each tile needs SIX tap MMAs instead of nine with weights
+// merged on the host: top rows w(-1,.), w(0,.)+w(+1,.) on input rows (y-1, y); bottom rows w(-1,.)+w(0,.), w(+1,.) on
+// (y, y+1).  The stage carries the 12 tap matrices [top 6 | bottom 6]; a tile's row parity picks its half.
 constexpr int kMaxProg = 96;
-__host__ __device__ constexpr uint32_t prog_entry(int src, int kc, int n, bool first, bool last, bool taps9, int kind) {
+__host__ __device__ constexpr uint32_t prog_entry(int src, int kc, int n, bool first, bool last, bool taps9, int kind,
+                                                  bool dup = false) {
   return (uint32_t)src | ((uint32_t)kc << 3) | ((uint32_t)n << 9) | ((uint32_t)first << 12) | ((uint32_t)last << 13) |
-         ((uint32_t)taps9 << 14) | ((uint32_t)kind << 15);
+         ((uint32_t)taps9 << 14) | ((uint32_t)kind << 15) | ((uint32_t)dup << 17);
 }
 
 struct TcJob {
@@ -408,8 +415,8 @@ struct TilesPerUnit {
   static constexpr int value = (TS == 96) ? 2 : kAccCols / TS;
 };
 
-__host__ __device__ inline size_t stage_bytes(int N, int W, int tiles, bool dual) {
-  return ((size_t)tiles * 128 + 2 * (size_t)(W + 3)) * 32 + (dual ? 2 : 1) * 9 * (size_t)N * 32;
+__host__ __device__ inline size_t stage_bytes(int N, int W, int tiles, bool dual, int wtaps = 9) {
+  return ((size_t)tiles * 128 + 2 * (size_t)(W + 3)) * 32 + (dual ? 2 : 1) * (size_t)wtaps * (size_t)N * 32;
 }
 
 // The MMAs of one K-chunk for one group of MT tiles: straight-line, every descriptor is (loop-invariant high
@@ -418,7 +425,7 @@ __host__ __device__ inline size_t stage_bytes(int N, int W, int tiles, bool dual
 // tools/umma_bench.cu).  BN = weight rows per tap and K-half in the stage (N, or 2N for dual weights).
 template <int MT, int TS, int BN>
 __device__ __forceinline__ void issue_group(uint32_t d0, uint32_t a_lo0, uint32_t b_lo0, uint32_t idesc, int taps,
-                                            const int (&tap_off)[9], uint32_t accumulate) {
+                                            const int (&tap_off)[9], uint32_t accumulate, const uint32_t tile_step = 128u) {
   const uint32_t a_hi = (128u >> 4) | (1u << 14), b_hi = a_hi;
   if (taps == 9) {
 #pragma unroll
@@ -427,7 +434,7 @@ __device__ __forceinline__ void issue_group(uint32_t d0, uint32_t a_lo0, uint32_
       const uint32_t a_lo_tap = a_lo0 + (uint32_t)tap_off[tap];
 #pragma unroll
       for (int mt = 0; mt < MT; ++mt) {
-        const uint64_t da = ((uint64_t)a_hi << 32) | (uint64_t)(a_lo_tap + (uint32_t)(mt * 128));
+        const uint64_t da = ((uint64_t)a_hi << 32) | (uint64_t)(a_lo_tap + (uint32_t)mt * tile_step);
         tc_mma(d0 + (uint32_t)(mt * TS), da, db, idesc, tap == 0 ? accumulate : 1u);
       }
     }
@@ -435,15 +442,41 @@ __device__ __forceinline__ void issue_group(uint32_t d0, uint32_t a_lo0, uint32_
     const uint64_t db = ((uint64_t)b_hi << 32) | (uint64_t)b_lo0;
 #pragma unroll
     for (int mt = 0; mt < MT; ++mt) {
-      const uint64_t da = ((uint64_t)a_hi << 32) | (uint64_t)(a_lo0 + (uint32_t)(mt * 128));
+      const uint64_t da = ((uint64_t)a_hi << 32) | (uint64_t)(a_lo0 + (uint32_t)mt * tile_step);
       tc_mma(d0 + (uint32_t)(mt * TS), da, db, idesc, accumulate);
+    }
+  }
+}
+
+// The six tap MMAs per tile of a "rowdup" source (see prog_entry).  A tile of row parity `par` reads input rows
+// (y - 1 + par, y + par) — the first six entries of tap_off shifted by par rows — with tap matrices [6 par, 6 par + 6)
+// of the stage.  kParFromTile: the warp's tiles alternate parity (one tile per image row, two tiles per warp);
+// otherwise all of its tiles lie in rows of parity `par_warp`.
+template <int MT, int TS, int BN, bool kParFromTile>
+__device__ __forceinline__ void issue_group_dup(uint32_t d0, uint32_t a_lo0, uint32_t b_lo0, uint32_t idesc,
+                                                const int (&tap_off)[9], uint32_t accumulate, const uint32_t tile_step,
+                                                const uint32_t row_step, const uint32_t par_warp) {
+  const uint32_t a_hi = (128u >> 4) | (1u << 14), b_hi = a_hi;
+  if constexpr (!kParFromTile) {
+    a_lo0 += par_warp * row_step;
+    b_lo0 += par_warp * (uint32_t)(6 * BN * 2);
+  }
+#pragma unroll
+  for (int tap = 0; tap < 6; ++tap) {
+#pragma unroll
+    for (int mt = 0; mt < MT; ++mt) {
+      const uint32_t par = kParFromTile ? (uint32_t)(mt & 1) : 0u;
+      const uint64_t db = ((uint64_t)b_hi << 32) | (uint64_t)(b_lo0 + (uint32_t)((par * 6 + tap) * BN * 2));
+      const uint64_t da = ((uint64_t)a_hi << 32) |
+                          (uint64_t)(a_lo0 + (uint32_t)tap_off[tap] + (uint32_t)mt * tile_step + par * row_step);
+      tc_mma(d0 + (uint32_t)(mt * TS), da, db, idesc, tap == 0 ? accumulate : 1u);
     }
   }
 }
 
 // Sub: the split-K sub-accumulation path (TcConv::n_sub > 1) is compiled in — a separate instantiation, because
 // keeping a unit's sums in registers across buffer turns costs the plain single-chain launches 7 % (measured).
-template <int N, Prec P, bool Dual, int G, bool Sub = false, bool Rows = false>
+template <int N, Prec P, bool Dual, int G, bool Sub = false, int Rows = 0>
 __global__ void __launch_bounds__(kTcThreads, 1)
 conv_tc_kernel(const TcJob job) {
   extern __shared__ __align__(128) unsigned char smem[];
@@ -461,8 +494,12 @@ conv_tc_kernel(const TcJob job) {
   constexpr bool kSplit = PrecTraits<P>::split;
   constexpr bool kSubAcc = Sub;
   static_assert(!Sub || (kSplit && G == 1), "sub-accumulation belongs to the split precision, one group per unit");
-  static_assert(!Rows || (Dual && G == 1 && !Sub && N % 32 == 0), "row-aligned units: dual layout, one group, plain chain");
-  constexpr int kRowsExtra = Rows ? 2 : 0;   // the two border positions between the unit's two image rows
+  // Rows = tiles of 128 positions per image row (0: flat units of consecutive positions).  A row-aligned unit is
+  // kUnitRows = MT / Rows consecutive image rows starting at an even one.
+  static_assert(Rows == 0 || ((Rows == 1 || Rows == 2) && Dual && G == 1 && !Sub && N % 32 == 0 && MT % (2 * Rows) == 0),
+                "row-aligned units: dual layout, one group, plain chain, an even number of rows");
+  constexpr int kUnitRows = Rows ? MT / (Rows ? Rows : 1) : 0;
+  constexpr int kRowsExtra = Rows ? 2 * kUnitRows - 2 : 0;   // the border positions between the unit's image rows
   constexpr int kWpartsMax = Dual ? 2 : 1;   // weight rows per tap and K-half staged per chunk, in units of N
   const int dbg = kDebugHooks ? p.debug : 0;
   const int Wp = p.W + 2, Hp = p.H + 2;
@@ -530,7 +567,7 @@ conv_tc_kernel(const TcJob job) {
       const TcConv& c = job.c[phase];
       const int b = u / p.units_per_image;
       const int lu = u - b * p.units_per_image;
-      const int lo = Rows ? lu * 2 * Wp : lu * G * MT * 128;   // first staged position (= q0 - halo; Rows: start of padded row 2 lu)
+      const int lo = Rows ? lu * kUnitRows * Wp : lu * G * MT * 128;   // first staged position (= q0 - halo; Rows: start of a padded row)
       if (phase == 0 && job.ring > 0 && b >= job.ring) {
         const int v0 = u - job.ring * p.units_per_image;       // same local unit, `ring` images earlier
         ok = flag_wait3(job.flags2 + v0, lu > 0, lu < p.units_per_image - 1, 8, p.err, 6);
@@ -552,7 +589,8 @@ conv_tc_kernel(const TcJob job) {
         const TcSource& src = c.src[e & 7u];
         const int kc = (int)((e >> 3) & 63u), n = (int)((e >> 9) & 7u);
         const bool taps9 = (e >> 14) & 1u;
-        const uint32_t w_bytes = (uint32_t)((Dual && ((e >> 15) & 3u) == 1u ? 2 : 1) * (taps9 ? 9 : 1)) * N * 32u;
+        const bool dup = (e >> 17) & 1u;
+        const uint32_t w_bytes = (uint32_t)((Dual && ((e >> 15) & 3u) == 1u ? 2 : 1) * (dup ? 12 : (taps9 ? 9 : 1))) * N * 32u;
         const int st = it % S;
         const uint32_t ph = (uint32_t)(it / S) & 1u;
         ok = mbar_wait_t<true>(empty0 + 8 * st, ph ^ 1u, p.err, 1, w_empty);
@@ -618,7 +656,9 @@ conv_tc_kernel(const TcJob job) {
       int phase, u;
       decode_item(item, T, D, n_phase, phase, u);
       // first position of my tiles (Rows: warp `me` issues for the tiles of image row `me` of the unit's pair)
-      const uint32_t a_tile0 = Rows ? (uint32_t)(me * Wp) : (uint32_t)((G == 1 ? me * MTW : me * MT) * 128);
+      const uint32_t a_tile0 = Rows == 2 ? (uint32_t)(me * Wp) : Rows == 1 ? (uint32_t)(me * MTW * Wp)
+                                                                        : (uint32_t)((G == 1 ? me * MTW : me * MT) * 128);
+      const uint32_t tile_step = Rows == 1 ? (uint32_t)Wp : 128u;      // between this warp's consecutive tiles
       const int n_prog = job.prog_len[phase];
       int buf = 0;
       uint32_t d_unit = 0u;
@@ -628,7 +668,7 @@ conv_tc_kernel(const TcJob job) {
         const uint32_t e = e_next;
         e_next = job.prog[phase][pi + 1 < n_prog ? pi + 1 : pi];      // fetched a stage ahead (constant-bank latency)
         const int n = (int)((e >> 9) & 7u);
-        const bool first = (e >> 12) & 1u, last = (e >> 13) & 1u, taps9 = (e >> 14) & 1u;
+        const bool first = (e >> 12) & 1u, last = (e >> 13) & 1u, taps9 = (e >> 14) & 1u, dup = (e >> 17) & 1u;
         const uint32_t kind = (e >> 15) & 3u;
         // per-source MMA shape: the dual product writes 2N columns, a correction-only source the upper N
         const bool dual_src = Dual && kind == 1u;
@@ -664,14 +704,23 @@ conv_tc_kernel(const TcJob job) {
             for (int j = 0; j < n; ++j) {
               const uint32_t accumulate = (accumulate_next || j > 0) ? 1u : 0u;
               const uint32_t aj = a1 + (uint32_t)j * (2u * run1 >> 4), bj = b1 + (uint32_t)j * w_bytes16;
-              if (dual_src) issue_group<MTW, TS, 2 * N>(d_unit + col0, aj, bj, idesc, 1, tap_off, accumulate);
-              else issue_group<MTW, TS, N>(d_unit + col0, aj, bj, idesc, 1, tap_off, accumulate);
+              if (dual_src) issue_group<MTW, TS, 2 * N>(d_unit + col0, aj, bj, idesc, 1, tap_off, accumulate, tile_step);
+              else issue_group<MTW, TS, N>(d_unit + col0, aj, bj, idesc, 1, tap_off, accumulate, tile_step);
             }
           } else {
             const uint32_t accumulate = accumulate_next ? 1u : 0u;
             const uint32_t a_lo0 = (a_lo_base | ((a0 >> 4) + (uint32_t)halo)) + a_tile0;   // centre tap, my first tile
             const uint32_t b_lo0 = b_lo_base | ((a0 + a_bytes) >> 4);
-            if (dual_src) issue_group<MTW, TS, 2 * N>(d_unit + col0, a_lo0, b_lo0, idesc, 9, tap_off, accumulate);
+            if constexpr (Rows != 0) {
+              if (dup) {
+                // a warp's tiles share a row parity (`me`) unless it issues for two consecutive rows
+                constexpr bool kParFromTile = (Rows == 1 && MTW == 2);
+                static_assert(Rows == 2 || MTW <= 2, "rowdup: at most two rows per MMA warp");
+                if (dual_src) issue_group_dup<MTW, TS, 2 * N, kParFromTile>(d_unit + col0, a_lo0, b_lo0, idesc, tap_off, accumulate, tile_step, (uint32_t)Wp, (uint32_t)me);
+                else issue_group_dup<MTW, TS, N, kParFromTile>(d_unit + col0, a_lo0, b_lo0, idesc, tap_off, accumulate, tile_step, (uint32_t)Wp, (uint32_t)me);
+              } else if (dual_src) issue_group<MTW, TS, 2 * N>(d_unit + col0, a_lo0, b_lo0, idesc, 9, tap_off, accumulate, tile_step);
+              else issue_group<MTW, TS, N>(d_unit + col0, a_lo0, b_lo0, idesc, 9, tap_off, accumulate, tile_step);
+            } else if (dual_src) issue_group<MTW, TS, 2 * N>(d_unit + col0, a_lo0, b_lo0, idesc, 9, tap_off, accumulate);
             else issue_group<MTW, TS, N>(d_unit + col0, a_lo0, b_lo0, idesc, 9, tap_off, accumulate);
           }
           if (last) tc_commit(accf0 + 8 * buf);         // my tiles of this accumulation group are complete
@@ -852,7 +901,7 @@ conv_tc_kernel(const TcJob job) {
       };
 
       bool unit_done = false;      // the folded-pool epilogue below took the unit
-      if constexpr (Rows) if (c.pool_out != nullptr) {
+      if constexpr (Rows != 0 && kUnitRows == 2) if (c.pool_out != nullptr) {
         unit_done = true;
         // Row-aligned unit = image rows (2 lu, 2 lu + 1), 0-based.  This warp owns the vertical tile pair (A above B)
         // of its 32 columns: W = 256 (two tiles per row): column half `tile_par`, all N = 32 channels; W = 128 (one tile
@@ -995,10 +1044,10 @@ conv_tc_kernel(const TcJob job) {
         const uint32_t f_parity = (G == 1) ? (((uint32_t)kk >> 1) & 1u) : ((uint32_t)k & 1u);
         // first position of tile mt of the unit: consecutive runs of 128, or (row-aligned units) MT / 2 tiles in each
         // of the image rows 2 lu + 1 and 2 lu + 2 of the padded tensor
-        const int q0 = Rows ? (2 * (u - b * p.units_per_image) + 1) * Wp + 1
+        const int q0 = Rows ? (kUnitRows * (u - b * p.units_per_image) + 1) * Wp + 1
                             : halo + ((u - b * p.units_per_image) * G + g) * MT * 128;
         auto tile_pos = [&](const int mt) {
-          if constexpr (Rows) return q0 + (mt / (MT / 2)) * Wp + (mt % (MT / 2)) * 128 + quad * 32 + lane;
+          if constexpr (Rows != 0) return q0 + (mt / Rows) * Wp + (mt % Rows) * 128 + quad * 32 + lane;
           else return q0 + mt * 128 + quad * 32 + lane;
         };
         // this warp's tiles: tile_par, tile_par + 2, ...; the global operands of a tile are fetched one tile ahead

@@ -177,6 +177,8 @@ def test_fused_resblock_launch_is_bit_identical(sd_seed0, clip60, monkeypatch):
         eng = Engine(sd_seed0, 0, max_batch=48, mode=mode)
         mel = eng.features(padded, torch.from_numpy(g["starts"][:48]))
         monkeypatch.delenv("SS_TC_FUSE", raising=False)
+        # (the fused launch keeps flat units and nine taps: compare with the same summation order)
+        monkeypatch.setenv("SS_TC_TAPMERGE", "0")
         base = eng.classify(mel)
         for env in ({"SS_TC_FUSE": "1"}, {"SS_TC_FUSE": "1", "SS_TC_LAG": "3"}, {"SS_TC_FUSE": "1", "SS_TC_LAG": "100000"},
                     {"SS_TC_FUSE": "1", "SS_TC_RING": "0"}, {"SS_TC_FUSE": "1", "SS_TC_RING": "3"},
@@ -188,7 +190,7 @@ def test_fused_resblock_launch_is_bit_identical(sd_seed0, clip60, monkeypatch):
             got = eng.classify(mel)
             eng.check_health()
             assert torch.equal(base, got), (mode, env)
-        for k in ("SS_TC_FUSE", "SS_TC_LAG", "SS_TC_CPS", "SS_TC_RING"):
+        for k in ("SS_TC_FUSE", "SS_TC_LAG", "SS_TC_CPS", "SS_TC_RING", "SS_TC_TAPMERGE"):
             monkeypatch.delenv(k, raising=False)
         eng.close()
 
@@ -206,7 +208,7 @@ def test_row_aligned_units_and_folded_maxpool_are_bit_identical(sd_seed0, clip60
     g = load_golden("model_seed0.npz")
     padded = torch.from_numpy(pp.pad_audio(clip60)).cuda()
     eng = Engine(sd_seed0, 0, max_batch=53, mode="f16x3")
-    knobs = ("SS_TC_ROWS", "SS_TC_POOL_FOLD")
+    knobs = ("SS_TC_ROWS", "SS_TC_POOL_FOLD", "SS_TC_TAPMERGE")
     # 0 conv1, 1 conv2, 7 up(conv7), 8 up(conv8) (written by row-aligned up-sampling epilogues), 10 conv1_1's
     # intermediate; 12 / 13 the pooled tensors: hi operands alone (+ 0x100), lo alone (+ 0x200)
     ids = (0, 1, 7, 8, 10, 12 + 0x100, 12 + 0x200, 13 + 0x100, 13 + 0x200)
@@ -227,7 +229,8 @@ def test_row_aligned_units_and_folded_maxpool_are_bit_identical(sd_seed0, clip60
         mel = eng.features(padded, torch.from_numpy(g["starts"][:n]))
         plain, acts_plain = run({"SS_TC_ROWS": "0", "SS_TC_POOL_FOLD": "0"}, mel, n)
         for env in ({}, {"SS_TC_POOL_FOLD": "0"}, {"SS_TC_ROWS": "0"}, {"SS_TC_POOL_FOLD": "1"}, {"SS_TC_POOL_FOLD": "2"}):
-            got, acts = run(env, mel, n)
+            # (row-merged taps change the summation, not the sum: they have their own test below)
+            got, acts = run(dict(env, SS_TC_TAPMERGE="0"), mel, n)
             for w, a, b in zip(ids, acts_plain, acts):
                 assert torch.equal(a, b), (n, env, hex(w))
             assert torch.equal(plain, got), (n, env)
@@ -235,6 +238,34 @@ def test_row_aligned_units_and_folded_maxpool_are_bit_identical(sd_seed0, clip60
         assert torch.equal(pooled, torch.nn.functional.max_pool2d(acts_plain[0], 2)), n
         # flat units after row-aligned ones, in the same tensors: the borders are still zero
         assert torch.equal(plain, run({"SS_TC_ROWS": "0", "SS_TC_POOL_FOLD": "0"}, mel, n)[0]), n
+    assert eng.check_guards() == 0
+    eng.close()
+
+
+def test_row_merged_taps_of_upsampled_inputs(sd_seed0, clip60, monkeypatch):
+    """conv8 / conv9_1's first convolutions read cat([skip, up(below)]); image rows 2k and 2k+1 of the up-sampled half are
+    identical, so on row-aligned units its nine taps become six with weights merged on the host (w(0,.)+w(+1,.) for
+    output rows at the top of a pair, w(-1,.)+w(0,.) at the bottom: conv_tc_kernel.cuh "rowdup").  Same sums, another
+    summation order: activations and logits agree with the nine-tap form to float32 rounding, and with the oracle
+    within the usual tolerance (test_layerwise_against_oracle runs with the merged taps, the default)."""
+    from oracle import postproc as pp
+    from softspoken_b200.engine import Engine
+    g = load_golden("model_seed0.npz")
+    padded = torch.from_numpy(pp.pad_audio(clip60)).cuda()
+    eng = Engine(sd_seed0, 0, max_batch=24, mode="f16x3")
+    for n in (3, 24):
+        mel = eng.features(padded, torch.from_numpy(g["starts"][:n]))
+        monkeypatch.setenv("SS_TC_TAPMERGE", "0")
+        nine = eng.classify(mel)
+        up8_nine = _dump(eng, 8, n)
+        monkeypatch.delenv("SS_TC_TAPMERGE")
+        six = eng.classify(mel)
+        up8_six = _dump(eng, 8, n)
+        eng.check_health()
+        e_act = float((up8_six - up8_nine).abs().max() / up8_nine.abs().max())
+        e_log = float((six - nine).abs().max() / nine.abs().max())
+        print(f"row-merged taps vs nine taps ({n} windows): up(conv8) rel diff {e_act:.2e}, logits rel diff {e_log:.2e}")
+        assert 0 < e_act <= 2e-6 and e_log <= 3e-6, (e_act, e_log)     # 0 would mean the knob does nothing
     assert eng.check_guards() == 0
     eng.close()
 

@@ -553,12 +553,12 @@ int pack_conv(TcState* st, const float* w, int taps, int cin, int cout, float sc
   return SS_OK;
 }
 
-constexpr size_t kSmemTail = (2 * kMaxStages + 4) * 8 + 5 * 128 * 4 + 16;   // barriers + bias and scalar-residual weights of both phases + TMEM slot
+constexpr size_t kSmemTail = (2 * kMaxStages + 6) * 8 + 5 * 128 * 4 + 16;   // barriers + bias and scalar-residual weights of both phases + TMEM slot
 // Launches with row-merged taps stage 12 tap matrices per chunk: four ring slots of conv9_1's first convolution
 // (57,600 bytes each) fit only with the device's whole opt-in shared memory and a tail sized for the launch's N
 // (three slots measured +2 % on that launch, which cancels what the merged taps save).
 constexpr size_t kSmemBudgetMax = 227 * 1024;
-constexpr size_t smem_tail_n(int n) { return (2 * kMaxStages + 4) * 8 + 5 * (size_t)n * 4 + 16; }
+constexpr size_t smem_tail_n(int n) { return (2 * kMaxStages + 6) * 8 + 5 * (size_t)n * 4 + 16; }
 
 constexpr int kDefaultRing = 8;    // images of the intermediate tensor kept by a fused ResBlock launch (0: whole batch)
 constexpr int kDefaultLag = 160;   // units by which conv2 trails conv1 in a fused ResBlock launch (> one round of 148 CTAs)
@@ -584,8 +584,55 @@ int launch_conv_npg(TcJob job, int B, cudaStream_t st) {
   for (int i = 0; i < p.n_src; ++i) any_dup |= p.src[i].taps == 12;
   SS_REQUIRE(!any_dup || rows, SS_E_ARG, "row-merged taps need a row-aligned launch");
   const size_t rows_extra = rows ? (size_t)(2 * unit_rows - 2) * 32 : 0;   // border positions between the unit's rows (kRowsExtra)
-  const size_t sb = stage_bytes(N, p.W, G * MT, Dual, any_dup ? 12 : 9) + rows_extra;
-  const size_t budget = any_dup ? kSmemBudgetMax : kSmemBudget, tail = any_dup ? smem_tail_n(N) : kSmemTail;
+  // Resident weights (TcConv::wres): row-aligned dual launches whose packed weights fit in shared memory next to a
+  // ring of at least four activation-only slots.  SS_TC_WRES=0: weights travel with every chunk (A/B runs).
+  size_t wres = 0;
+  const size_t a_only = ((size_t)G * MT * 128 + 2 * (size_t)(p.W + 3)) * 32 + rows_extra;
+  if (rows && kCanRows) {
+    const char* wr = getenv("SS_TC_WRES");      // read per call: A/B runs compare the two in one process
+    const int want_res = wr ? atoi(wr) : 1;
+    size_t total = 0;
+    bool paired = true;
+    for (int i = 0; i < p.n_src; ++i) {
+      const TcSource& src = p.src[i];
+      if (src.kind == 1) total += (size_t)src.n_chunks * src.taps * N * 64;
+      else paired &= src.kind == 2 && i > 0 && p.src[i - 1].kind == 1 && p.src[i - 1].n_chunks == src.n_chunks &&
+                     p.src[i - 1].taps == src.taps;
+    }
+    // Measured launch by launch (profiles/r2_tuning_experiments.txt, section 12): -8 % on conv1_1.c2, -4 % / -9 % on conv2_1's
+    // two launches; +5 % together with row-merged taps (conv9_1.c1) and +6 .. +13 % where a 1x1 source has more
+    // chunks than an activation-only slot holds (conv8 / conv9_1's second launches: their residual branches need more
+    // stages then, and every stage costs a fixed hand-over).  Hence: no merged taps, and every 1x1 source in one slot.
+    int most1x1 = 0;
+    for (int i = 0; i < p.n_src; ++i)
+      if (p.src[i].taps == 1 && p.src[i].n_chunks > most1x1) most1x1 = p.src[i].n_chunks;
+    const size_t chunk1_a = (size_t)G * MT * 128 * 32 + rows_extra;
+    const bool suits = !any_dup && (size_t)most1x1 * chunk1_a <= a_only;
+    if ((want_res == 2 || (want_res && suits)) && paired && total > 0 &&
+        total + 4 * a_only + smem_tail_n(N) <= kSmemBudgetMax)
+      wres = total;
+  }
+  p.wres = (int)wres;
+  if (wres) {
+    int off = 0;
+    for (int i = 0; i < p.n_src; ++i) {
+      TcSource& src = p.src[i];
+      if (src.kind == 1) {
+        src.wres_off = off;
+        src.wres_stride = src.taps * N * 64;
+        src.wres_bytes = src.n_chunks * src.wres_stride;
+        off += src.wres_bytes;
+      } else {
+        src.wres_off = p.src[i - 1].wres_off;
+        src.wres_stride = p.src[i - 1].wres_stride;
+        src.wres_bytes = 0;
+      }
+      src.w_rows = 2 * N;
+    }
+  }
+  const size_t sb = wres ? a_only : stage_bytes(N, p.W, G * MT, Dual, any_dup ? 12 : 9) + rows_extra;
+  const bool big = any_dup || wres;
+  const size_t budget = (big ? kSmemBudgetMax : kSmemBudget) - wres, tail = big ? smem_tail_n(N) : kSmemTail;
   // Ring slot size.  Every stage costs a fixed hand-over (full/empty barrier round trip and an MMA-issue bubble,
   // ~500-1000 cycles measured with the tuning hooks), which a 3x3 stage hides behind its 9 x MT MMAs and a 1x1 stage
   // (MT MMAs per chunk) does not: 1x1 sources therefore pack several K-chunks into one slot, and when a launch has
@@ -593,7 +640,7 @@ int launch_conv_npg(TcJob job, int B, cudaStream_t st) {
   // slots — so that up to `cap` chunks fit.  SS_TC_CPS caps the chunks per stage (1 = one chunk per stage everywhere).
   const char* ce = getenv("SS_TC_CPS");
   const int cap = ce ? atoi(ce) : 4;
-  const size_t chunk1 = (size_t)G * MT * 128 * 32 + rows_extra + (Dual ? 2 : 1) * (size_t)N * 32;
+  const size_t chunk1 = (size_t)G * MT * 128 * 32 + rows_extra + (wres ? 0 : (Dual ? 2 : 1) * (size_t)N * 32);
   int most1 = 0;
   for (int ph = 0; ph < job.n_phase; ++ph)
     for (int i = 0; i < job.c[ph].n_src; ++i)
@@ -615,7 +662,7 @@ int launch_conv_npg(TcJob job, int B, cudaStream_t st) {
   p.stages = stages;
   static const int debug = [] { const char* e = getenv("SS_TC_DEBUG"); return e ? atoi(e) : 0; }();
   p.debug = debug;
-  const size_t smem = (size_t)stages * stride + tail;
+  const size_t smem = wres + (size_t)stages * stride + tail;
   constexpr bool kCanSub = PrecTraits<P>::split && G == 1;
   static bool configured = false;
   if (!configured) {
@@ -670,6 +717,8 @@ int launch_conv_npg(TcJob job, int B, cudaStream_t st) {
           const int n = (hi - kc < per_stage) ? (hi - kc) : per_stage;
           SS_REQUIRE(len < kMaxProg && kc < 64 && n < 8 && si < 8, SS_E_ARG, "conv stage program too long (%d stages)", len);
           job.prog[ph][len] = prog_entry(si, kc, n, len == first_of_group, false, src.taps >= 9, src.kind, src.taps == 12);
+          if (ph == 0 && wres)
+            job.prog_b[len] = (uint32_t)((src.wres_off + kc * src.wres_stride) >> 4) | ((uint32_t)(src.wres_stride >> 4) << 16);
           ++len;
         }
       }
@@ -682,6 +731,9 @@ int launch_conv_npg(TcJob job, int B, cudaStream_t st) {
   }
   const int items = p.total_units * job.n_phase;
   const int grid = items < kNumSMs ? items : kNumSMs;
+  if (getenv("SS_TC_VERBOSE"))
+    fprintf(stderr, "conv launch N=%d %dx%d rows=%d dup=%d wres=%zu stride=%zu stages=%d cps=%d prog=%d units/img=%d smem=%zu\n", N,
+            p.H, p.W, (int)rows, (int)any_dup, wres, stride, stages, p.cps, job.prog_len[0], p.units_per_image, smem);
   if (job.n_phase == 2) {
     SS_REQUIRE(p.W + 3 <= G * MT * 128, SS_E_ARG, "fused ResBlock launch: halo %d exceeds the unit", p.W + 3);
     SS_REQUIRE(p.total_units <= job.flags_cap, SS_E_ARG, "fused ResBlock launch: %d units exceed the flag array",

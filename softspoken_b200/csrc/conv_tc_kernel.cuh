@@ -258,6 +258,10 @@ struct TcSource {
   int w_stride;        // 16-bit elements between consecutive chunks of `w`
   const uint16_t* w;   // plain: [n_chunks][parts][taps][2][N][8] (pointing at the part to use);
                        // dual:  [n_chunks][taps][2][2N][8] (rows 0..N-1 = w_hi, N..2N-1 = w_lo)
+  // Resident weights (TcConv::wres > 0, dual layout): where this source's chunk 0 sits in the resident region, the
+  // bytes between consecutive chunks, and the rows of a K-half block there (2N: a kind-2 source reads the w_hi rows of
+  // its kind-1 sibling's dual matrices instead of a copy of its own).  wres_bytes > 0: this source brings the block in.
+  int wres_off, wres_stride, w_rows, wres_bytes;
 };
 
 struct TcConv {
@@ -304,6 +308,11 @@ struct TcConv {
   // launch disappear.  max commutes with the monotonic hi/lo split, so the pooled operands are bit-identical to
   // pool_planar's.
   int rows;
+  // Resident weights: the launch's packed weights (wres bytes, at the start of shared memory) are loaded ONCE per CTA
+  // and the ring slots carry activations only.  Re-staging them with every K-chunk of every unit was 29 % (N = 32 at
+  // 128 x 256) to 62 % (N = 64 at 64 x 128) of the L2 -> shared-memory traffic of these launches and kept the ring at
+  // four slots; without them a slot is 16-33 KB and the ring 4-8 deep.  0: weights travel with every chunk.
+  int wres;
   uint16_t* pool_out;
   uint16_t* pool_lo;
   int stages;          // smem ring depth (<= kMaxStages)
@@ -348,6 +357,10 @@ __host__ __device__ constexpr uint32_t prog_entry(int src, int kc, int n, bool f
 struct TcJob {
   TcConv c[2];
   uint32_t prog[2][kMaxProg];   // stage program of a unit of each phase
+  // resident weights (phase 0 only): per stage, bits 0-15 = (offset of its first chunk's weights in the resident
+  // region) >> 4, bits 16-31 = (bytes between consecutive chunks) >> 4 — fetched a stage ahead like the program word,
+  // so that no dependent parameter look-up sits between two bursts of MMAs
+  uint32_t prog_b[kMaxProg];
   int prog_len[2];
   int n_phase;
   int layout;          // warp-role layout (see the kernel): 1 = critical roles on the highest warp ids (default)
@@ -512,10 +525,11 @@ conv_tc_kernel(const TcJob job) {
   const int cps = p.cps;
   const uint32_t run1 = (uint32_t)(G * MT * 128 + kRowsExtra) * 16u;      // one plane of a 1x1 source's chunk (no halo)
   const uint32_t w1_off = (uint32_t)cps * 2u * run1;          // weights of a 1x1 stage follow its cps chunk slots
-  unsigned char* stage0 = smem;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)S * stage_sz);
-  // bars: full[kMaxStages] | empty[kMaxStages] | acc_full[2] | acc_empty[2]
-  float* bias_s = reinterpret_cast<float*>(bars + 2 * kMaxStages + 4);       // [2][N] bias, then [2][N] scalar-residual weights
+  const uint32_t wres = (uint32_t)p.wres;                    // resident weights ahead of the ring (0: none)
+  unsigned char* stage0 = smem + wres;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stage0 + (size_t)S * stage_sz);
+  // bars: full[kMaxStages] | empty[kMaxStages] | acc_full[2] | acc_empty[2] | resident weights | (pad)
+  float* bias_s = reinterpret_cast<float*>(bars + 2 * kMaxStages + 6);       // [2][N] bias, then [2][N] scalar-residual weights
   float* zero_s = bias_s + 4 * N;                                            // [N] zeros: the "bias" of border positions
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(zero_s + N);
 
@@ -529,6 +543,7 @@ conv_tc_kernel(const TcJob job) {
   const int w_prod = top_roles ? 8 : 4, w_mma0 = top_roles ? 9 : 5, w_mma1 = 10;
   const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + kMaxStages);
   const uint32_t accf0 = smem_u32(bars + 2 * kMaxStages), acce0 = smem_u32(bars + 2 * kMaxStages + 2);
+  const uint32_t wbar = smem_u32(bars + 2 * kMaxStages + 4);
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < S; ++s) {
@@ -539,6 +554,7 @@ conv_tc_kernel(const TcJob job) {
       mbar_init(accf0 + 8 * i, G == 2 ? 1 : 2);   // G = 2: the buffer's owner; G = 1: both MMA warps
       mbar_init(acce0 + 8 * i, 8);       // one arrival per epilogue warp
     }
+    mbar_init(wbar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   for (int i = threadIdx.x; i < n_phase * N; i += kTcThreads) {
@@ -561,6 +577,14 @@ conv_tc_kernel(const TcJob job) {
     int it = 0;
     bool ok = true;
     long long w_empty = 0;
+    if (wres && elect_one()) {
+      // the launch's weights, once: one bulk copy per kind-1 source (its chunks are contiguous in the dual layout)
+      mbar_expect_tx(wbar, wres);
+      for (int i = 0; i < p.n_src; ++i)
+        if (p.src[i].wres_bytes > 0)
+          bulk_g2s(smem_u32(smem) + (uint32_t)p.src[i].wres_off, p.src[i].w, (uint32_t)p.src[i].wres_bytes, wbar);
+    }
+    __syncwarp();
     for (int r = 0, item; (item = item_of(r)) < n_items && ok && !(dbg & 4); ++r) {
       int phase, u;
       decode_item(item, T, D, n_phase, phase, u);
@@ -590,7 +614,8 @@ conv_tc_kernel(const TcJob job) {
         const int kc = (int)((e >> 3) & 63u), n = (int)((e >> 9) & 7u);
         const bool taps9 = (e >> 14) & 1u;
         const bool dup = (e >> 17) & 1u;
-        const uint32_t w_bytes = (uint32_t)((Dual && ((e >> 15) & 3u) == 1u ? 2 : 1) * (dup ? 12 : (taps9 ? 9 : 1))) * N * 32u;
+        const uint32_t w_bytes =
+            wres ? 0u : (uint32_t)((Dual && ((e >> 15) & 3u) == 1u ? 2 : 1) * (dup ? 12 : (taps9 ? 9 : 1))) * N * 32u;
         const int st = it % S;
         const uint32_t ph = (uint32_t)(it / S) & 1u;
         ok = mbar_wait_t<true>(empty0 + 8 * st, ph ^ 1u, p.err, 1, w_empty);
@@ -610,8 +635,9 @@ conv_tc_kernel(const TcJob job) {
               const uint16_t* pj = plane + (int64_t)2 * j * HpWp * 8 + (int64_t)halo * 8;    // centre tap only
               bulk_g2s(dst + (uint32_t)(2 * j) * run1, pj, run1, full0 + 8 * st);
               bulk_g2s(dst + (uint32_t)(2 * j + 1) * run1, pj + (int64_t)HpWp * 8, run1, full0 + 8 * st);
-              bulk_g2s(dst + w1_off + (uint32_t)j * w_bytes, src.w + (int64_t)(kc + j) * src.w_stride, w_bytes,
-                       full0 + 8 * st);
+              if (w_bytes)
+                bulk_g2s(dst + w1_off + (uint32_t)j * w_bytes, src.w + (int64_t)(kc + j) * src.w_stride, w_bytes,
+                         full0 + 8 * st);
             }
           }
         } else if (elect_one()) {
@@ -619,7 +645,7 @@ conv_tc_kernel(const TcJob job) {
           mbar_expect_tx(full0 + 8 * st, 2u * run + w_bytes);
           bulk_g2s(dst, plane, run, full0 + 8 * st);
           bulk_g2s(dst + run, plane + (int64_t)HpWp * 8, run, full0 + 8 * st);
-          bulk_g2s(dst + a_bytes, src.w + (int64_t)kc * src.w_stride, w_bytes, full0 + 8 * st);
+          if (w_bytes) bulk_g2s(dst + a_bytes, src.w + (int64_t)kc * src.w_stride, w_bytes, full0 + 8 * st);
         }
         __syncwarp();
       }
@@ -649,6 +675,9 @@ conv_tc_kernel(const TcJob job) {
     // elected once, waits probe inline, and a stage costs one commit.
     const uint32_t leader = elect_one();
     const uint32_t stage_base = smem_u32(stage0);
+    const uint32_t res_base = smem_u32(smem);
+    if (wres) ok = mbar_wait(wbar, 0u, p.err, 7);
+    tc_fence_after();
     int st = 0;
     uint32_t ph = 0, a0 = stage_base;
     bool ready = false;            // the full barrier of the stage about to be consumed was already seen complete
@@ -664,9 +693,15 @@ conv_tc_kernel(const TcJob job) {
       uint32_t d_unit = 0u;
       bool accumulate_next = false;
       uint32_t e_next = job.prog[phase][0];
+      uint32_t pb_next = (Rows != 0) ? job.prog_b[0] : 0u;
       for (int pi = 0; pi < n_prog && ok; ++pi) {
         const uint32_t e = e_next;
         e_next = job.prog[phase][pi + 1 < n_prog ? pi + 1 : pi];      // fetched a stage ahead (constant-bank latency)
+        uint32_t pb = 0u;
+        if constexpr (Rows != 0) {
+          pb = pb_next;
+          pb_next = job.prog_b[pi + 1 < n_prog ? pi + 1 : pi];
+        }
         const int n = (int)((e >> 9) & 7u);
         const bool first = (e >> 12) & 1u, last = (e >> 13) & 1u, taps9 = (e >> 14) & 1u, dup = (e >> 17) & 1u;
         const uint32_t kind = (e >> 15) & 3u;
@@ -674,7 +709,12 @@ conv_tc_kernel(const TcJob job) {
         const bool dual_src = Dual && kind == 1u;
         const uint32_t idesc = dual_src ? idesc_2n : idesc_n;
         const uint32_t col0 = (Dual && kind == 2u) ? (uint32_t)N : 0u;
-        const uint32_t b_lo_base = ((uint32_t)(dual_src ? 2 * N : N) & 0x3FFFu) << 16;   // LBO = rows * 16 bytes
+        // resident weights (row-aligned dual launches): every B operand is a slice of a dual matrix, whose K-half blocks
+        // have 2N rows whatever the MMA's N
+        const bool wide = dual_src || (Rows != 0 && wres != 0);
+        const uint32_t b_lo_base = ((uint32_t)(wide ? 2 * N : N) & 0x3FFFu) << 16;   // LBO = rows * 16 bytes
+        // resident: this stage's first chunk (>> 4), chunk stride (>> 4)
+        const uint32_t b_res = (res_base >> 4) + (pb & 0xffffu), b_res_step = pb >> 16;
         if (!ready && !(dbg & 4)) ok = mbar_wait_fast(full0 + 8 * st, ph, p.err, 2, timing, w_full);
         if (!ok) break;
         if (first) {
@@ -698,9 +738,9 @@ conv_tc_kernel(const TcJob job) {
           if (dbg & 8) { if (a0 == 0xdeadbeefu) p.err[1] = (int)(d_unit + idesc); }   // issue nothing
           else if (!taps9) {
             // compact 1x1 stage: chunk j at a0 + 2 j run1 (plane stride run1), its weights at a0 + w1_off + j w_bytes
-            const uint32_t w_bytes16 = (uint32_t)((dual_src ? 2 : 1) * N * 2);             // 1x1 chunk weights >> 4
+            const uint32_t w_bytes16 = (Rows != 0 && wres) ? b_res_step : (uint32_t)((dual_src ? 2 : 1) * N * 2);   // 1x1 chunk weights >> 4
             const uint32_t a1 = (a1_lo_base | (a0 >> 4)) + a_tile0;
-            const uint32_t b1 = b_lo_base | ((a0 + w1_off) >> 4);
+            const uint32_t b1 = b_lo_base | ((Rows != 0 && wres) ? b_res : ((a0 + w1_off) >> 4));
             for (int j = 0; j < n; ++j) {
               const uint32_t accumulate = (accumulate_next || j > 0) ? 1u : 0u;
               const uint32_t aj = a1 + (uint32_t)j * (2u * run1 >> 4), bj = b1 + (uint32_t)j * w_bytes16;
@@ -710,15 +750,16 @@ conv_tc_kernel(const TcJob job) {
           } else {
             const uint32_t accumulate = accumulate_next ? 1u : 0u;
             const uint32_t a_lo0 = (a_lo_base | ((a0 >> 4) + (uint32_t)halo)) + a_tile0;   // centre tap, my first tile
-            const uint32_t b_lo0 = b_lo_base | ((a0 + a_bytes) >> 4);
+            const uint32_t b_lo0 = b_lo_base | ((Rows != 0 && wres) ? b_res : ((a0 + a_bytes) >> 4));
             if constexpr (Rows != 0) {
+              // (the tap matrices of a B operand are 2 x rows-of-its-K-half-block x 16 bytes apart: template BN)
               if (dup) {
                 // a warp's tiles share a row parity (`me`) unless it issues for two consecutive rows
                 constexpr bool kParFromTile = (Rows == 1 && MTW == 2);
                 static_assert(Rows == 2 || MTW <= 2, "rowdup: at most two rows per MMA warp");
-                if (dual_src) issue_group_dup<MTW, TS, 2 * N, kParFromTile>(d_unit + col0, a_lo0, b_lo0, idesc, tap_off, accumulate, tile_step, (uint32_t)Wp, (uint32_t)me);
+                if (wide) issue_group_dup<MTW, TS, 2 * N, kParFromTile>(d_unit + col0, a_lo0, b_lo0, idesc, tap_off, accumulate, tile_step, (uint32_t)Wp, (uint32_t)me);
                 else issue_group_dup<MTW, TS, N, kParFromTile>(d_unit + col0, a_lo0, b_lo0, idesc, tap_off, accumulate, tile_step, (uint32_t)Wp, (uint32_t)me);
-              } else if (dual_src) issue_group<MTW, TS, 2 * N>(d_unit + col0, a_lo0, b_lo0, idesc, 9, tap_off, accumulate, tile_step);
+              } else if (wide) issue_group<MTW, TS, 2 * N>(d_unit + col0, a_lo0, b_lo0, idesc, 9, tap_off, accumulate, tile_step);
               else issue_group<MTW, TS, N>(d_unit + col0, a_lo0, b_lo0, idesc, 9, tap_off, accumulate, tile_step);
             } else if (dual_src) issue_group<MTW, TS, 2 * N>(d_unit + col0, a_lo0, b_lo0, idesc, 9, tap_off, accumulate);
             else issue_group<MTW, TS, N>(d_unit + col0, a_lo0, b_lo0, idesc, 9, tap_off, accumulate);

@@ -208,7 +208,7 @@ def test_row_aligned_units_and_folded_maxpool_are_bit_identical(sd_seed0, clip60
     g = load_golden("model_seed0.npz")
     padded = torch.from_numpy(pp.pad_audio(clip60)).cuda()
     eng = Engine(sd_seed0, 0, max_batch=53, mode="f16x3")
-    knobs = ("SS_TC_ROWS", "SS_TC_POOL_FOLD", "SS_TC_TAPMERGE")
+    knobs = ("SS_TC_ROWS", "SS_TC_POOL_FOLD", "SS_TC_TAPMERGE", "SS_TC_WRES")
     # 0 conv1, 1 conv2, 7 up(conv7), 8 up(conv8) (written by row-aligned up-sampling epilogues), 10 conv1_1's
     # intermediate; 12 / 13 the pooled tensors: hi operands alone (+ 0x100), lo alone (+ 0x200)
     ids = (0, 1, 7, 8, 10, 12 + 0x100, 12 + 0x200, 13 + 0x100, 13 + 0x200)
@@ -228,7 +228,8 @@ def test_row_aligned_units_and_folded_maxpool_are_bit_identical(sd_seed0, clip60
     for n in (1, 5, 48, 53):
         mel = eng.features(padded, torch.from_numpy(g["starts"][:n]))
         plain, acts_plain = run({"SS_TC_ROWS": "0", "SS_TC_POOL_FOLD": "0"}, mel, n)
-        for env in ({}, {"SS_TC_POOL_FOLD": "0"}, {"SS_TC_ROWS": "0"}, {"SS_TC_POOL_FOLD": "1"}, {"SS_TC_POOL_FOLD": "2"}):
+        for env in ({}, {"SS_TC_POOL_FOLD": "0"}, {"SS_TC_ROWS": "0"}, {"SS_TC_POOL_FOLD": "1"}, {"SS_TC_POOL_FOLD": "2"},
+                    {"SS_TC_WRES": "0"}, {"SS_TC_WRES": "0", "SS_TC_POOL_FOLD": "0"}):
             # (row-merged taps change the summation, not the sum: they have their own test below)
             got, acts = run(dict(env, SS_TC_TAPMERGE="0"), mel, n)
             for w, a, b in zip(ids, acts_plain, acts):

@@ -142,6 +142,72 @@ void dev_free(ss_ctx* ctx, const void* p) {
   cudaFree(base);
 }
 
+// K1's two-band walk of the filterbank (FrontEnd::mel_rec).  Possible when every band is non-empty, band starts and
+// ends are non-decreasing and band m + 2 starts after band m ends — every bin then lies in at most two consecutive
+// bands, one even- and one odd-numbered.  The bands are cut into kFeatureWarps contiguous groups whose widest bin span
+// is minimal; a group's records cover the bins from its first band's start to its last band's end and carry the
+// weights of its own bands only.  Returns SS_OK with n_rec = 0 when the bank does not have that shape.
+int build_mel_walk(ss_ctx* ctx, const int* ms, const int* mc, const int* mo, const float* taps) {
+  ctx->fe.n_rec = 0;
+  std::vector<int> lo(kMels), hi(kMels);
+  for (int m = 0; m < kMels; ++m) {
+    if (mc[m] <= 0) return SS_OK;
+    lo[m] = ms[m];
+    hi[m] = ms[m] + mc[m] - 1;
+    if (m >= 1 && (lo[m] < lo[m - 1] || hi[m] < hi[m - 1])) return SS_OK;
+    if (m >= 2 && lo[m] <= hi[m - 2]) return SS_OK;
+  }
+  auto groups_for = [&](int span, std::vector<int>* first) {
+    first->clear();
+    for (int m = 0; m < kMels;) {
+      first->push_back(m);
+      int k = m;
+      while (k + 1 < kMels && hi[k + 1] - lo[m] + 1 <= span) ++k;
+      m = k + 1;
+    }
+    return (int)first->size();
+  };
+  int span = 0;
+  for (int m = 0; m < kMels; ++m) span = mc[m] > span ? mc[m] : span;
+  std::vector<int> first;
+  while (groups_for(span, &first) > kFeatureWarps) ++span;
+  std::vector<float4> rec;
+  std::vector<int> begin(kFeatureWarps + 1, 0);
+  for (int g = 0; g < kFeatureWarps; ++g) {
+    begin[g] = (int)rec.size();
+    if (g >= (int)first.size()) continue;
+    const int ja = first[g], jb = g + 1 < (int)first.size() ? first[g + 1] : kMels;
+    for (int k = lo[ja]; k <= hi[jb - 1]; ++k) {
+      float w[2] = {0.f, 0.f};
+      int emit = 0;
+      for (int m = ja; m < jb; ++m) {
+        if (k < lo[m] || k > hi[m]) continue;
+        w[m & 1] = taps[mo[m] + (k - lo[m])];
+        if (k == hi[m]) emit |= (m + 1) << (8 * (m & 1));
+      }
+      float4 r;
+      r.x = w[0];
+      r.y = w[1];
+      memcpy(&r.z, &k, 4);
+      memcpy(&r.w, &emit, 4);
+      rec.push_back(r);
+    }
+  }
+  begin[kFeatureWarps] = (int)rec.size();
+  if ((int)rec.size() > kMaxMelRec) return SS_OK;
+  float4* d_rec = nullptr;
+  int* d_begin = nullptr;
+  int rc = dev_alloc(ctx, &d_rec, rec.size());
+  if (rc) return rc;
+  if ((rc = dev_alloc(ctx, &d_begin, begin.size()))) return rc;
+  SS_CUDA_CHECK(cudaMemcpy(d_rec, rec.data(), rec.size() * sizeof(float4), cudaMemcpyHostToDevice));
+  SS_CUDA_CHECK(cudaMemcpy(d_begin, begin.data(), begin.size() * sizeof(int), cudaMemcpyHostToDevice));
+  ctx->fe.mel_rec = d_rec;
+  ctx->fe.mel_rec_begin = d_begin;
+  ctx->fe.n_rec = (int)rec.size();
+  return SS_OK;
+}
+
 int upload_tables(ss_ctx* ctx, const BlobView& v) {
   // Twiddle tables are formed in double and rounded once.
   const BlobEntry& we = v.entries.at("window");
@@ -460,6 +526,15 @@ int ss_ctx_create(int device, const void* blob, size_t blob_bytes, int max_batch
         return SS_E_BLOB;
       }
     }
+  }
+  {
+    // SS_MEL_WALK=0 keeps K1's band-by-band walk of the sparse taps (A/B runs, and the path of non-triangular banks)
+    const char* mw = getenv("SS_MEL_WALK");
+    if (mw == nullptr || atoi(mw) != 0)
+      FAIL_IF(build_mel_walk(ctx, reinterpret_cast<const int*>(v.payload + v.entries.at("mel_start").off),
+                             reinterpret_cast<const int*>(v.payload + v.entries.at("mel_count").off),
+                             reinterpret_cast<const int*>(v.payload + v.entries.at("mel_offs").off),
+                             v.payload + v.entries.at("mel_taps").off));
   }
   FAIL_IF(upload_tables(ctx, v));
   for (int i = 0; i < RB_COUNT; ++i) {

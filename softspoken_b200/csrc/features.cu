@@ -24,7 +24,7 @@ namespace ss {
 
 namespace {
 
-constexpr int kWarps = 16;
+constexpr int kWarps = kFeatureWarps;
 constexpr int kThreads = kWarps * 32;
 constexpr int kFramesPerTile = 32;
 constexpr int kFramesPerWarp = kFramesPerTile / kWarps;
@@ -35,6 +35,7 @@ constexpr int kOddQ = 186;      // bins 4q+1 and 4q+3, q <= 185 (k <= 743)
 constexpr int kRows = 2 * kOddQ + kEvenBins;   // power rows: [4q+1 | 4q+3 | 2m]
 constexpr int kRowStride = kFramesPerTile + 1;
 constexpr int kMaxTaps = 2048;
+constexpr int kMaxRec = kMaxMelRec;
 
 struct WarpSmem {
   float re[kEx];
@@ -46,9 +47,8 @@ struct Smem {
   float2 tw2[7][64];            // W64^(u k2a), k2a = 1..7, u = t & 7
   float tw_a_re[512], tw_a_im[512], win[512];
   float2 tw1024[kEvenBins];
-  float taps[kMaxTaps];
-  int tap_row[kMaxTaps];         // row offset (row * kRowStride) of each tap's bin in the power tile
-  int mcount[kMels], moffs[kMels];
+  float4 rec[kMaxRec];           // two-band walk (FrontEnd::mel_rec) with .z = row offset of the bin in the power tile
+  int rec_begin[kWarps + 1];
   float P[kRows * kRowStride];  // power spectrum tile [row(bin)][frame]
   WarpSmem w[kWarps];
 };
@@ -198,13 +198,12 @@ features_kernel(const T* __restrict__ pcm, int64_t valid_begin, int64_t valid_en
     s.win[i] = fe.window[i];
   }
   for (int i = tid; i < kEvenBins; i += kThreads) s.tw1024[i] = fe.tw1024[i];
-  for (int i = tid; i < fe.n_taps; i += kThreads) s.taps[i] = fe.mel_taps[i];
-  if (tid < kMels) {
-    const int k0 = fe.mel_start[tid], cnt = fe.mel_count[tid], off = fe.mel_offs[tid];
-    s.mcount[tid] = cnt;
-    s.moffs[tid] = off;
-    for (int i = 0; i < cnt; ++i) s.tap_row[off + i] = row_of_bin(k0 + i) * kRowStride;
+  for (int i = tid; i < fe.n_rec; i += kThreads) {
+    float4 r = fe.mel_rec[i];
+    r.z = __int_as_float(row_of_bin(__float_as_int(r.z)) * kRowStride);
+    s.rec[i] = r;
   }
+  if (tid <= kWarps) s.rec_begin[tid] = fe.n_rec > 0 ? fe.mel_rec_begin[tid] : 0;
   __syncthreads();
 
   WarpSmem& ws = s.w[warp];
@@ -337,14 +336,46 @@ features_kernel(const T* __restrict__ pcm, int64_t valid_begin, int64_t valid_en
 
     // ======================================================================= phase 2: mel (lane = frame)
     float* __restrict__ out = mel + ((int64_t)w * kMels) * kFrames + frame0 + lane;
+    const float* __restrict__ Pl = s.P + lane;
+    if (fe.n_rec > 0) {
+      // Two-band walk: a bin of a triangular bank lies in two consecutive bands, one even- and one odd-numbered.  The
+      // warp walks the bins of its (contiguous) bands once — one broadcast record + one conflict-free power load per
+      // bin — feeding both bands' sums, and stores a band when its last bin has passed.  Every band still sums its bins
+      // in ascending order (a zero weight adds exactly nothing), so the result has the bits of the band-by-band walk
+      // at half its shared-memory loads, which bound this kernel (74 % of the pipe's wavefronts).
+      float acc_e = 0.f, acc_o = 0.f;
+      const int r1 = s.rec_begin[warp + 1];
+      int r = s.rec_begin[warp];
+      float4 rec = r < r1 ? s.rec[r] : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 1
-    for (int j = 0; j < kBandsPerWarp; ++j) {
-      const int band = warp + kWarps * j;              // interleaved: narrow and wide bands mix in every warp
-      const int cnt = s.mcount[band], off = s.moffs[band];
-      const float* __restrict__ Pl = s.P + lane;
-      float acc = 0.f;
-      for (int i = off; i < off + cnt; ++i) acc = fmaf(s.taps[i], Pl[s.tap_row[i]], acc);
-      out[(int64_t)band * kFrames] = sqrtf(log10f(acc + 1.0f));
+      for (; r < r1; ++r) {
+        const float4 cur = rec;
+        if (r + 1 < r1) rec = s.rec[r + 1];
+        const float pw = Pl[__float_as_int(cur.z)];
+        acc_e = fmaf(cur.x, pw, acc_e);
+        acc_o = fmaf(cur.y, pw, acc_o);
+        const int emit = __float_as_int(cur.w);
+        if (emit) {                                     // warp-uniform
+          if (emit & 0xff) {
+            out[(int64_t)((emit & 0xff) - 1) * kFrames] = sqrtf(log10f(acc_e + 1.0f));
+            acc_e = 0.f;
+          }
+          if (emit >> 8) {
+            out[(int64_t)((emit >> 8) - 1) * kFrames] = sqrtf(log10f(acc_o + 1.0f));
+            acc_o = 0.f;
+          }
+        }
+      }
+    } else {
+      // any other sparse bank: band by band, taps straight from the blob (bands interleaved over the warps)
+#pragma unroll 1
+      for (int j = 0; j < kBandsPerWarp; ++j) {
+        const int band = warp + kWarps * j;
+        const int k0 = __ldg(fe.mel_start + band), cnt = __ldg(fe.mel_count + band), off = __ldg(fe.mel_offs + band);
+        float acc = 0.f;
+        for (int i = 0; i < cnt; ++i) acc = fmaf(__ldg(fe.mel_taps + off + i), Pl[row_of_bin(k0 + i) * kRowStride], acc);
+        out[(int64_t)band * kFrames] = sqrtf(log10f(acc + 1.0f));
+      }
     }
     __syncthreads();   // the power tile is rewritten by the next work tile
   }
@@ -578,6 +609,7 @@ int launch_features_virtual(const ss_ctx* ctx, const void* pcm, int sample_fmt, 
                             cudaStream_t st) {
   if (n_windows <= 0) return SS_OK;
   SS_REQUIRE(ctx->fe.n_taps <= kMaxTaps, SS_E_BLOB, "mel filterbank has %d taps (> %d)", ctx->fe.n_taps, kMaxTaps);
+  SS_REQUIRE(ctx->fe.n_rec <= kMaxRec, SS_E_BLOB, "mel filterbank walk has %d records (> %d)", ctx->fe.n_rec, kMaxRec);
   const int n_tiles = n_windows * (kFrames / kFramesPerTile);
   const int grid = n_tiles < kNumSMs ? n_tiles : kNumSMs;
   if (sample_fmt == kSampleS16)

@@ -26,6 +26,8 @@ constexpr int kFrames = 256;                       // pytorch_neural_nets.py:150
 constexpr int kMels = 128;                         // pytorch_neural_nets.py:87
 constexpr int kFreqs = 1025;
 constexpr int kMaxMelTaps = 32;    // rows of the feature kernel's transposed tap table
+constexpr int kMaxMelRec = 1280;   // records of K1's two-band filterbank walk (743 bins + the overlap of the warps' ranges)
+constexpr int kFeatureWarps = 16;  // warps of K1's CTA: the walk is cut into this many ranges
 constexpr int kGapBins = 42;                       // 0.5 s break (worker.py:97) on the 256/3 Hz timeline
 constexpr int kNumSMs = 148;
 
@@ -85,6 +87,13 @@ struct FrontEnd {
   const int* mel_offs = nullptr;      // [128]
   const float* mel_taps = nullptr;    // [n_taps]
   int n_taps = 0;
+  // "Two-band walk" of the filterbank for K1's mel phase (built at ss_ctx_create when every bin lies in at most two
+  // CONSECUTIVE bands, as in any triangular bank; n_rec = 0 otherwise and K1 walks the sparse taps band by band):
+  // the bins of a warp's bands in ascending order, each as {weight in its even-numbered band, weight in its
+  // odd-numbered band, bin, emit}, emit = (even band that ends at this bin + 1) | (odd band that ends here + 1) << 8.
+  const float4* mel_rec = nullptr;    // [n_rec]
+  const int* mel_rec_begin = nullptr; // [17] record range of each of the 16 warps
+  int n_rec = 0;
 };
 
 enum { RB_CONV1 = 0, RB_CONV2, RB_CONV3, RB_CONV4, RB_BOTTLENECK, RB_ENCODER_OUT, RB_CONV6, RB_CONV7,

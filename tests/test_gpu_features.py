@@ -84,3 +84,46 @@ def test_virtual_padding_equals_materialised_padding(engine, clip60):
     _, _, lg = engine.detect_device(torch.from_numpy(clip).cuda(), want_logits=True)
     b = engine.classify(a)
     assert torch.equal(lg, b)
+
+
+def test_two_band_walk_has_the_bits_of_the_band_by_band_walk(sd_seed0, clip60, monkeypatch):
+    """K1's mel phase walks the bins of a warp's bands once, feeding the two bands a bin belongs to (default for
+    triangular banks, FrontEnd::mel_rec); SS_MEL_WALK=0 (read at context creation) keeps the band-by-band walk of the
+    sparse taps.  Same ascending order of the bins within every band, so the same bits."""
+    from oracle import postproc as pp
+    from softspoken_b200.engine import Engine
+    padded = torch.from_numpy(_padded(clip60)).cuda()
+    starts = torch.from_numpy(pp.plan_windows(60.0))
+    eng = Engine(sd_seed0, 0, max_batch=8, mode="fp32")
+    walk = eng.features(padded, starts)
+    eng.close()
+    monkeypatch.setenv("SS_MEL_WALK", "0")
+    eng = Engine(sd_seed0, 0, max_batch=8, mode="fp32")
+    monkeypatch.delenv("SS_MEL_WALK")
+    plain = eng.features(padded, starts)
+    eng.close()
+    assert torch.equal(walk, plain)
+
+
+def test_non_triangular_filterbank_takes_the_general_path(sd_seed0, clip60):
+    """A bank whose bands overlap three deep (every band widened by half of its upper neighbour) cannot be walked two
+    bands at a time: the context falls back to the band-by-band walk, and the features still match the oracle."""
+    from collections import OrderedDict
+    from oracle import features as of
+    from oracle import postproc as pp
+    from softspoken_b200.engine import Engine
+    fb = checkpoint.mel_filterbank().clone()
+    wide = fb.clone()
+    wide[:, :90] += 0.5 * fb[:, 1:91]              # bands 0..89 now reach into band m + 2's support; all stay <= 32 taps
+    sd = OrderedDict((k, v.clone()) for k, v in sd_seed0.items())
+    sd["mel_spectrogram.mel_scale.fb"] = wide
+    padded_np = _padded(clip60)
+    starts = pp.plan_windows(60.0)[:16]
+    eng = Engine(sd, 0, max_batch=8, mode="fp32")
+    mel = eng.features(torch.from_numpy(padded_np).cuda(), torch.from_numpy(starts)).cpu().numpy()
+    eng.close()
+    x = torch.stack([torch.from_numpy(padded_np[i:i + spec.WINDOW_SAMPLES]) for i in starts])
+    ref = of.log_mel(x, checkpoint.hann_window(), wide).numpy()
+    err = np.max(np.abs(mel - ref)) / np.max(np.abs(ref))
+    print(f"K1 with a three-deep overlapping bank vs oracle: {err:.3e}")
+    assert err <= REL_TOL

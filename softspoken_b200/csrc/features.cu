@@ -135,8 +135,9 @@ __device__ __forceinline__ float load_sample(const T* __restrict__ pcm, int64_t 
 
 // Passes 2 and 3 of the 512-point FFT whose pass-1 results sit in the warp's exchange buffer (A layout).
 // On return (re, im)[h][k2b] = X[t + 64 k2b] with t = lane + 32 h.
-template <typename Tables>      // anything with the pass-2 twiddles tw2[7][64]
-__device__ __forceinline__ void fft512_tail(WarpSmem& ws, const Tables& s, int lane, float (&re)[2][8], float (&im)[2][8]) {
+// tw2r[k - 1] = W64^(u k), u = lane & 7: the pass-2 twiddles depend on t = lane + 32 h only through t & 7, so both
+// halves use the same seven values — kept in registers by the caller (14 shared-memory wavefronts per transform less).
+__device__ __forceinline__ void fft512_tail(WarpSmem& ws, const float2 (&tw2r)[7], int lane, float (&re)[2][8], float (&im)[2][8]) {
   __syncwarp();
   // ---- pass 2: butterfly (k1, u) = (t >> 3, t & 7) transforms over v, twiddle W64^(u k2a)
 #pragma unroll
@@ -155,7 +156,7 @@ __device__ __forceinline__ void fft512_tail(WarpSmem& ws, const Tables& s, int l
     dft8<false>(re[h], im[h]);
 #pragma unroll
     for (int k2a = 0; k2a < 8; ++k2a) {
-      if (k2a) cmul(re[h][k2a], im[h][k2a], s.tw2[k2a - 1][t]);
+      if (k2a) cmul(re[h][k2a], im[h][k2a], tw2r[k2a - 1]);
       ws.re[(k2a * 8 + k1) * 9 + u] = re[h][k2a];
       ws.im[(k2a * 8 + k1) * 9 + u] = im[h][k2a];
     }
@@ -208,6 +209,9 @@ features_kernel(const T* __restrict__ pcm, int64_t valid_begin, int64_t valid_en
 
   WarpSmem& ws = s.w[warp];
   float re[2][8], im[2][8];
+  float2 tw2r[7];
+#pragma unroll
+  for (int k = 0; k < 7; ++k) tw2r[k] = s.tw2[k][lane & 7];
 
 #pragma unroll 1
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -263,7 +267,7 @@ features_kernel(const T* __restrict__ pcm, int64_t valid_begin, int64_t valid_en
           ws.im[k1 * 72 + t] = im[h][k1];
         }
       }
-      fft512_tail(ws, s, lane, re, im);
+      fft512_tail(ws, tw2r, lane, re, im);
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
 #pragma unroll
@@ -306,7 +310,7 @@ features_kernel(const T* __restrict__ pcm, int64_t valid_begin, int64_t valid_en
           ws.im[k1 * 72 + t] = im[h][k1];
         }
       }
-      fft512_tail(ws, s, lane, re, im);
+      fft512_tail(ws, tw2r, lane, re, im);
       // C[q] parked in the exchange buffer, plain layout
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
@@ -430,6 +434,9 @@ stft512_kernel(const T* __restrict__ pcm, int64_t n, int64_t n_frames, const flo
   WarpSmem& ws = s.w[warp];
   float* __restrict__ tile_s = s.mag[group];
   float re[2][8], im[2][8];
+  float2 tw2r[7];
+#pragma unroll
+  for (int k = 0; k < 7; ++k) tw2r[k] = s.tw2[k][lane & 7];
   float vmax = 0.f;
   const int64_t n_tiles = (n_frames + kSpecTileFrames - 1) / kSpecTileFrames;
   const int64_t tile_step = (int64_t)gridDim.x * kSpecGroups;
@@ -471,7 +478,7 @@ stft512_kernel(const T* __restrict__ pcm, int64_t n, int64_t n_frames, const flo
         ws.im[k1 * 72 + t] = im[h][k1];
       }
     }
-    fft512_tail(ws, s, lane, re, im);
+    fft512_tail(ws, tw2r, lane, re, im);
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
 #pragma unroll

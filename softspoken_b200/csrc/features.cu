@@ -212,6 +212,12 @@ features_kernel(const T* __restrict__ pcm, int64_t valid_begin, int64_t valid_en
   float2 tw2r[7];
 #pragma unroll
   for (int k = 0; k < 7; ++k) tw2r[k] = s.tw2[k][lane & 7];
+  // ... and the pass-1 twiddles W512^(t k1) of the lane's two columns t = lane, lane + 32
+  float2 tw1r[2][7];
+#pragma unroll
+  for (int h = 0; h < 2; ++h)
+#pragma unroll
+    for (int k = 0; k < 7; ++k) tw1r[h][k] = s.tw1[k][lane + 32 * h];
 
 #pragma unroll 1
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -262,7 +268,7 @@ features_kernel(const T* __restrict__ pcm, int64_t valid_begin, int64_t valid_en
         dft8<false>(re[h], im[h]);
 #pragma unroll
         for (int k1 = 0; k1 < 8; ++k1) {
-          if (k1) cmul(re[h][k1], im[h][k1], s.tw1[k1 - 1][t]);
+          if (k1) cmul(re[h][k1], im[h][k1], tw1r[h][k1 - 1]);
           ws.re[k1 * 72 + t] = re[h][k1];
           ws.im[k1 * 72 + t] = im[h][k1];
         }
@@ -305,7 +311,7 @@ features_kernel(const T* __restrict__ pcm, int64_t valid_begin, int64_t valid_en
         dft8<true>(re[h], im[h]);
 #pragma unroll
         for (int k1 = 0; k1 < 8; ++k1) {
-          if (k1) cmul(re[h][k1], im[h][k1], s.tw1[k1 - 1][t]);
+          if (k1) cmul(re[h][k1], im[h][k1], tw1r[h][k1 - 1]);
           ws.re[k1 * 72 + t] = re[h][k1];
           ws.im[k1 * 72 + t] = im[h][k1];
         }

@@ -317,28 +317,35 @@ features_kernel(const T* __restrict__ pcm, int64_t valid_begin, int64_t valid_en
         }
       }
       fft512_tail(ws, tw2r, lane, re, im);
-      // C[q] parked in the exchange buffer, plain layout
+      // ---- even bins: U[m] = (C[m] + conj C[512-m])/2 + W1024^m (C[m] - conj C[512-m])/(2i), m <= 371.
+      // This lane holds C[m] for m = t + 64 k2b, t = lane + 32 h; C[512 - m] sits at column 64 - t, i.e. in lane
+      // 32 - lane under (h ^ 1, 7 - k2b) — one shuffle per value instead of a round trip of all 512 values through the
+      // exchange buffer (lane 0 keeps its own partners: t = 0 pairs with k2b' = 8 - k2b, t = 32 with itself).
+      {
+        const int src_lane = (32 - lane) & 31;
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
+        for (int h = 0; h < 2; ++h) {
 #pragma unroll
-        for (int k2b = 0; k2b < 8; ++k2b) {
-          const int q = lane + 32 * h + 64 * k2b;
-          ws.re[q] = re[h][k2b];
-          ws.im[q] = im[h][k2b];
+          for (int k2b = 0; k2b < 6; ++k2b) {
+            const int m = lane + 32 * h + 64 * k2b;
+            float nr = __shfl_sync(0xffffffffu, re[h ^ 1][7 - k2b], src_lane);
+            float ni = __shfl_sync(0xffffffffu, im[h ^ 1][7 - k2b], src_lane);
+            if (lane == 0) {
+              nr = h ? re[1][7 - k2b] : re[0][(8 - k2b) & 7];
+              ni = h ? im[1][7 - k2b] : im[0][(8 - k2b) & 7];
+            }
+            ni = -ni;
+            if (m < kEvenBins) {
+              const float cr = re[h][k2b], ci = im[h][k2b];
+              const float er = 0.5f * (cr + nr), ei = 0.5f * (ci + ni);
+              const float dr = cr - nr, di = ci - ni;
+              float orr = 0.5f * di, oi = -0.5f * dr;
+              cmul(orr, oi, s.tw1024[m]);
+              const float ur = er + orr, ui = ei + oi;
+              Pf[(2 * kOddQ + m) * kRowStride] = ur * ur + ui * ui;
+            }
+          }
         }
-      }
-      __syncwarp();
-      // ---- even bins: U[m] = (C[m] + conj C[512-m])/2 + W1024^m (C[m] - conj C[512-m])/(2i)
-      for (int m = lane; m < kEvenBins; m += 32) {
-        const int mm = (512 - m) & 511;
-        const float cr = ws.re[m], ci = ws.im[m];
-        const float nr = ws.re[mm], ni = -ws.im[mm];
-        const float er = 0.5f * (cr + nr), ei = 0.5f * (ci + ni);
-        const float dr = cr - nr, di = ci - ni;
-        float orr = 0.5f * di, oi = -0.5f * dr;
-        cmul(orr, oi, s.tw1024[m]);
-        const float ur = er + orr, ui = ei + oi;
-        Pf[(2 * kOddQ + m) * kRowStride] = ur * ur + ui * ui;
       }
       __syncwarp();   // the exchange buffer is reused by the next frame
     }

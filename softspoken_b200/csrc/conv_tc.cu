@@ -384,9 +384,10 @@ __global__ void spec_out_planar(const uint16_t* __restrict__ x, const uint16_t* 
 }
 
 // planar -> NCHW f32 (debug / parity localisation only)
+// halfrows: the tensor is a half-row tensor (TcSource::in_up): H / 2 + 2 rows, row 1 + y / 2 holds image row y
 template <Prec P>
 __global__ void planar_to_nchw(const uint16_t* __restrict__ in, const uint16_t* __restrict__ in_lo, int planes_total,
-                               int plane0, int C, int H, int W, float* __restrict__ out, int64_t total) {
+                               int plane0, int C, int H, int W, float* __restrict__ out, int64_t total, int halfrows) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const int x = (int)(i % W);
@@ -394,9 +395,10 @@ __global__ void planar_to_nchw(const uint16_t* __restrict__ in, const uint16_t* 
   const int y = (int)(r % H); r /= H;
   const int c = (int)(r % C);
   const int64_t b = r / C;
-  const int Wp = W + 2, Hp = H + 2;
+  const int Wp = W + 2, Hp = halfrows ? H / 2 + 2 : H + 2;
+  const int row = halfrows ? (y >> 1) + 1 : y + 1;
   float a[8];
-  load8<P>(in, in_lo, ((b * planes_total + plane0 + c / 8) * Hp + (y + 1)) * (int64_t)Wp + (x + 1), a);
+  load8<P>(in, in_lo, ((b * planes_total + plane0 + c / 8) * Hp + row) * (int64_t)Wp + (x + 1), a);
   out[i] = a[c & 7];
 }
 
@@ -435,6 +437,10 @@ struct TcState {
   int max_batch = 0;
   TcBlock rb[RB_COUNT];
   Tensor x0, m4, m3, m2, m1, p1, p2, p3, p4, bott, c9, spec;
+  // half-row tensors (split precision): up(conv8) for conv9_1 [B][4][64 + 2][258][8], up(conv7) for conv8
+  // [B][8][32 + 2][130][8] — the up-sampled halves of the two largest decoder inputs with only their columns replicated
+  Tensor u4, u3;
+  bool halfrows_last = false;    // the most recent classify call used them (ss_debug_activation 7 / 8 read them then)
   Tensor t[RB_COUNT];
   int* err = nullptr;
   float* head_part = nullptr;  // [max_batch][128][256][4] conv_flatten partials written by conv9_1's epilogue
@@ -716,7 +722,12 @@ int launch_conv_npg(TcJob job, int B, cudaStream_t st) {
         for (int kc = lo; kc < hi; kc += per_stage) {
           const int n = (hi - kc < per_stage) ? (hi - kc) : per_stage;
           SS_REQUIRE(len < kMaxProg && kc < 64 && n < 8 && si < 8, SS_E_ARG, "conv stage program too long (%d stages)", len);
-          job.prog[ph][len] = prog_entry(si, kc, n, len == first_of_group, false, src.taps >= 9, src.kind, src.taps == 12);
+          const bool half = src.in_up != nullptr && kc + n > src.up_chunk0;
+          const int nfull = half ? (src.up_chunk0 > kc ? src.up_chunk0 - kc : 0) : 0;
+          SS_REQUIRE(!half || (rows && (src.taps == 12 || src.taps == 1)), SS_E_ARG,
+                     "half-row sources belong to row-aligned launches (merged taps or 1x1)");
+          job.prog[ph][len] = prog_entry(si, kc, n, len == first_of_group, false, src.taps >= 9, src.kind, src.taps == 12,
+                                         half, nfull);
           if (ph == 0 && wres)
             job.prog_b[len] = (uint32_t)((src.wres_off + kc * src.wres_stride) >> 4) | ((uint32_t)(src.wres_stride >> 4) << 16);
           ++len;
@@ -833,8 +844,10 @@ int launch_conv(Prec prec, const TcJob& p, int N, int B, cudaStream_t st) {
 //    small (Ootomo & Yokota 2022 observe the same for mma.sync; tools/precision_study.py measures it here).
 enum class Terms { All, Corrections, Main };
 
+// up / up_chunk0 (dual layout only): the K-chunks from up_chunk0 on are read from the half-row tensor `up`
+// (TcSource::in_up) instead of from the planes of x that follow.
 void add_sources(TcConv* p, const TcState* s, const Tensor& x, int plane0, const PackedConv& w, Terms terms,
-                 int ring = 0) {
+                 int ring = 0, const Tensor* up = nullptr, int up_chunk0 = 0) {
   const int part_elems = w.taps * w.n * 16;
   const int chunk_elems = w.parts * part_elems;
   if (!is_split(s->prec)) {
@@ -844,8 +857,15 @@ void add_sources(TcConv* p, const TcState* s, const Tensor& x, int plane0, const
   }
   if (w.dual) {
     if (terms != Terms::Corrections) {
-      p->src[p->n_src++] = TcSource{x.data, x.planes, plane0, w.n_chunks, w.taps, 1, ring, chunk_elems, w.w};
-      p->src[p->n_src++] = TcSource{x.lo, x.planes, plane0, w.n_chunks, w.taps, 2, ring, part_elems, w.w_hi};
+      TcSource hi{x.data, x.planes, plane0, w.n_chunks, w.taps, 1, ring, chunk_elems, w.w};
+      TcSource lo{x.lo, x.planes, plane0, w.n_chunks, w.taps, 2, ring, part_elems, w.w_hi};
+      if (up) {
+        hi.in_up = up->data; lo.in_up = up->lo;
+        hi.up_chunk0 = lo.up_chunk0 = up_chunk0;
+        hi.up_planes_total = lo.up_planes_total = up->planes;
+      }
+      p->src[p->n_src++] = hi;
+      p->src[p->n_src++] = lo;
     }
     return;
   }
@@ -861,7 +881,10 @@ void add_sources(TcConv* p, const TcState* s, const Tensor& x, int plane0, const
 int tc_res_block(TcState* s, int which, const Tensor& x, int x_plane0, Tensor& out, int out_plane0, int upsample,
                  int B, cudaStream_t st, const float* head_w = nullptr, float* head_out = nullptr,
                  bool store_out = true, const float* res_x = nullptr, const float* res_w = nullptr,
-                 bool c1_done = false, Tensor* pool = nullptr, bool* pooled = nullptr) {
+                 bool c1_done = false, Tensor* pool = nullptr, bool* pooled = nullptr, const Tensor* x_up = nullptr) {
+  // x_up: the up-sampled half of the block input lives in a half-row tensor (the caller made the block below write it
+  // with upsample == 2, and has checked that this block's launches are row-aligned with merged taps); x then
+  // supplies the skip half only.  upsample == 2: this block's output goes to the half-row tensor `out`.
   const TcBlock& rb = s->rb[which];
   Tensor& t = s->t[which];
   const int N = rb.c1.n;
@@ -876,7 +899,7 @@ int tc_res_block(TcState* s, int which, const Tensor& x, int x_plane0, Tensor& o
   add_sources(&q, s, t, 0, rb.c2, Terms::Corrections, -1);     // -1: "the intermediate tensor", ring resolved at launch
   if (res_x == nullptr) {
     add_sources(&q, s, x, x_plane0, rb.res, Terms::Corrections);
-    add_sources(&q, s, x, x_plane0, rb.res, Terms::Main);
+    add_sources(&q, s, x, x_plane0, rb.res, Terms::Main, 0, x_up, x_up ? rb.skip_cin / 16 : 0);
   } else {            // single-channel block input: the residual branch is an FMA in the epilogue (TcConv::res_x)
     q.res_x = res_x;
     q.res_w = res_w;
@@ -939,7 +962,12 @@ int tc_res_block(TcState* s, int which, const Tensor& x, int x_plane0, Tensor& o
   // MMAs per tile instead of nine; SS_TC_TAPMERGE=0 keeps the nine)
   {
     const char* tm = getenv("SS_TC_TAPMERGE");
-    if (p.rows && rb.skip_cin > 0 && (tm == nullptr || atoi(tm) != 0)) {
+    if (x_up) {
+      SS_REQUIRE(p.rows && rb.skip_cin > 0 && (tm == nullptr || atoi(tm) != 0), SS_E_ARG,
+                 "half-row block input needs a row-aligned launch with merged taps");
+      add_sources(&p, s, x, x_plane0, rb.c1_skip, Terms::Main);
+      add_sources(&p, s, *x_up, 0, rb.c1_up, Terms::Main, 0, x_up, 0);
+    } else if (p.rows && rb.skip_cin > 0 && (tm == nullptr || atoi(tm) != 0)) {
       add_sources(&p, s, x, x_plane0, rb.c1_skip, Terms::Main);
       add_sources(&p, s, x, x_plane0 + rb.skip_cin / 8, rb.c1_up, Terms::Main);
     } else {
@@ -1106,6 +1134,10 @@ int tc_build_state(ss_ctx* ctx, Prec prec, TcState* s) {
   T(m1, 256, 16, 32);
   T(p4, 128, 8, 16);
   T(bott, 128, 8, 16);
+  if (is_split(prec)) {
+    T(u4, 32, 64, 256);
+    T(u3, 64, 32, 128);
+  }
   T(c9, 32, 128, 256);
   T(spec, 32, 128, 256);
   T(t[RB_CONV1], 32, 128, 256);
@@ -1169,17 +1201,39 @@ int classify_tc_p(ss_ctx* ctx, TcState* s, const float* mel, int n_windows, floa
     SS_TRY(tc_res_block(s, RB_BOTTLENECK, s->p4, 0, s->bott, 0, 0, B, st));
     SS_TRY(tc_res_block(s, RB_ENCODER_OUT, s->bott, 0, s->m1, 16, 1, B, st));   // -> up, cat after conv4
     SS_TRY(tc_res_block(s, RB_CONV6, s->m1, 0, s->m2, 12, 1, B, st));
-    SS_TRY(tc_res_block(s, RB_CONV7, s->m2, 0, s->m3, 8, 1, B, st));
-    SS_TRY(tc_res_block(s, RB_CONV8, s->m3, 0, s->m4, 4, 1, B, st));
+    // Half-row tensors for the up-sampled halves of conv8's and conv9_1's inputs (TcSource::in_up): the split
+    // precision with everything their consumers need — row-aligned launches, merged taps, separate launches, the
+    // plain accumulation chain.  SS_TC_HALFROWS=0: 2 x 2 replicated planes of m3 / m4 as in every other mode.
+    bool halfrows = false;
+    if constexpr (PrecTraits<P>::split) {
+      auto off = [](const char* name) { const char* e = getenv(name); return e != nullptr && atoi(e) == 0; };
+      auto on = [](const char* name) { const char* e = getenv(name); return e != nullptr && atoi(e) != 0; };
+      const char* sb = getenv("SS_TC_SUB");
+      const char* pp = getenv("SS_TC_PAIRS");
+      halfrows = !off("SS_TC_HALFROWS") && !off("SS_TC_ROWS") && !off("SS_TC_TAPMERGE") && !on("SS_TC_FUSE") &&
+                 (sb == nullptr || atoi(sb) <= 1) && (pp == nullptr || (atoi(pp) & 1) == 0);
+    }
+    s->halfrows_last = halfrows;
+    if (halfrows) {
+      SS_TRY(tc_res_block(s, RB_CONV7, s->m2, 0, s->u3, 0, 2, B, st));
+      SS_TRY(tc_res_block(s, RB_CONV8, s->m3, 0, s->u4, 0, 2, B, st, nullptr, nullptr, true, nullptr, nullptr, false,
+                          nullptr, nullptr, &s->u3));
+    } else {
+      SS_TRY(tc_res_block(s, RB_CONV7, s->m2, 0, s->m3, 8, 1, B, st));
+      SS_TRY(tc_res_block(s, RB_CONV8, s->m3, 0, s->m4, 4, 1, B, st));
+    }
+    const Tensor* up9 = halfrows ? &s->u4 : nullptr;
     // conv9_1 with the mask head's conv_flatten folded into its epilogue (TcConv::head_w); the 32-channel output
     // itself is stored only when the spec head will read it.  SS_TC_FUSE_HEAD=0 keeps the two-kernel form.
     const char* fh = getenv("SS_TC_FUSE_HEAD");
     if (fh == nullptr || atoi(fh) != 0) {
-      SS_TRY(tc_res_block(s, RB_CONV9, s->m4, 0, s->c9, 0, 0, B, st, ctx->head.flat_w, s->head_part, spec_out != nullptr));
+      SS_TRY(tc_res_block(s, RB_CONV9, s->m4, 0, s->c9, 0, 0, B, st, ctx->head.flat_w, s->head_part, spec_out != nullptr,
+                          nullptr, nullptr, false, nullptr, nullptr, up9));
       mask_head_partials<<<dim3(kFrames / kHeadFrames, B), kHeadCols * kHeadGroups, 0, st>>>(
           s->head_part, ctx->head, logits + (int64_t)b0 * kFrames);
     } else {
-      SS_TRY(tc_res_block(s, RB_CONV9, s->m4, 0, s->c9, 0, 0, B, st));
+      SS_TRY(tc_res_block(s, RB_CONV9, s->m4, 0, s->c9, 0, 0, B, st, nullptr, nullptr, true, nullptr, nullptr, false,
+                          nullptr, nullptr, up9));
       mask_head_planar<P><<<dim3(kFrames / kHeadFrames, B), kHeadCols * kHeadGroups, 0, st>>>(
           s->c9.data, s->c9.lo, ctx->head, logits + (int64_t)b0 * kFrames);
     }
@@ -1215,7 +1269,8 @@ void tc_free_state(ss_ctx* ctx, TcState* s) {
     unregister_guards(ctx, alloc);
     cudaFree(alloc);
   };
-  Tensor* ts[] = {&s->x0, &s->m4, &s->m3, &s->m2, &s->m1, &s->p1, &s->p2, &s->p3, &s->p4, &s->bott, &s->c9, &s->spec};
+  Tensor* ts[] = {&s->x0, &s->m4, &s->m3, &s->m2, &s->m1, &s->p1, &s->p2, &s->p3, &s->p4, &s->bott, &s->c9, &s->spec,
+                  &s->u4, &s->u3};
   for (Tensor* t : ts) { free_guarded(t->alloc); free_guarded(t->alloc_lo); }
   for (int i = 0; i < RB_COUNT; ++i) {
     free_guarded(s->t[i].alloc);
@@ -1275,6 +1330,15 @@ int tc_debug_dump(ss_ctx* ctx, int which, int n_windows, float* out, int* C, int
   which &= 0xff;
   SS_REQUIRE(which >= 0 && which < (int)(sizeof(table) / sizeof(table[0])), SS_E_ARG, "bad activation id %d", which);
   Sel e = table[which];
+  // up(conv7) / up(conv8) live in the half-row tensors when the last call used them (full image geometry for the dump)
+  int halfrows = 0;
+  Tensor full_geom;
+  if (s->halfrows_last && (which == 7 || which == 8)) {
+    full_geom = which == 7 ? s->u3 : s->u4;
+    full_geom.H *= 2;
+    e = Sel{&full_geom, 0, e.c};
+    halfrows = 1;
+  }
   Tensor alias = *e.t;
   if (part == 0x100) alias.lo = alias.data;
   if (part == 0x200) alias.data = alias.lo;
@@ -1284,9 +1348,9 @@ int tc_debug_dump(ss_ctx* ctx, int which, int n_windows, float* out, int* C, int
     const int64_t total = (int64_t)n_windows * e.c * e.t->H * e.t->W;
     const int grid = (int)((total + 255) / 256);
     switch (s->prec) {
-      case Prec::Bf16: planar_to_nchw<Prec::Bf16><<<grid, 256, 0, st>>>(e.t->data, e.t->lo, e.t->planes, e.plane0, e.c, e.t->H, e.t->W, out, total); break;
-      case Prec::F16: planar_to_nchw<Prec::F16><<<grid, 256, 0, st>>>(e.t->data, e.t->lo, e.t->planes, e.plane0, e.c, e.t->H, e.t->W, out, total); break;
-      case Prec::F16x3: planar_to_nchw<Prec::F16x3><<<grid, 256, 0, st>>>(e.t->data, e.t->lo, e.t->planes, e.plane0, e.c, e.t->H, e.t->W, out, total); break;
+      case Prec::Bf16: planar_to_nchw<Prec::Bf16><<<grid, 256, 0, st>>>(e.t->data, e.t->lo, e.t->planes, e.plane0, e.c, e.t->H, e.t->W, out, total, halfrows); break;
+      case Prec::F16: planar_to_nchw<Prec::F16><<<grid, 256, 0, st>>>(e.t->data, e.t->lo, e.t->planes, e.plane0, e.c, e.t->H, e.t->W, out, total, halfrows); break;
+      case Prec::F16x3: planar_to_nchw<Prec::F16x3><<<grid, 256, 0, st>>>(e.t->data, e.t->lo, e.t->planes, e.plane0, e.c, e.t->H, e.t->W, out, total, halfrows); break;
     }
     SS_CUDA_CHECK(cudaGetLastError());
   }

@@ -262,6 +262,13 @@ struct TcSource {
   // bytes between consecutive chunks, and the rows of a K-half block there (2N: a kind-2 source reads the w_hi rows of
   // its kind-1 sibling's dual matrices instead of a copy of its own).  wres_bytes > 0: this source brings the block in.
   int wres_off, wres_stride, w_rows, wres_bytes;
+  // Half-row tensor (row-aligned launches): K-chunks >= up_chunk0 are the nearest-neighbour 2x up-sampled output of
+  // the block below, stored with its COLUMNS replicated only: [B][up_planes_total][H/2 + 2][W + 2][8], row 1 + k of
+  // the tensor = image rows 2k and 2k + 1 (TcConv::upsample == 2 writes it).  The producer stages padded image row
+  // rho from tensor row ((rho - 1) >> 1) + 1, one bulk copy per row: the up-sampled half of a decoder input is
+  // written once and read from DRAM once per pair of rows instead of twice.  null: every chunk comes from `in`.
+  const uint16_t* in_up;
+  int up_chunk0, up_planes_total;
 };
 
 struct TcConv {
@@ -273,7 +280,9 @@ struct TcConv {
   int relu;            // must be 1: every convolution on this path is followed by ReLU (the epilogue applies it always)
   uint16_t* out;       // hi (or only) output tensor
   uint16_t* out_lo;    // residual output tensor (split precision), else null
-  int out_planes_total, out_plane0, upsample;
+  int out_planes_total, out_plane0;
+  int upsample;        // 0: store at the position; 1: 2 x 2 replicated store into a tensor at twice the resolution;
+                       // 2: 2 x 1 (columns only) into a half-row tensor (TcSource::in_up)
   int out_ring;        // like TcSource::ring, for the output tensor
   // Mask-head fusion (N = 32, the last ResBlock of the mask path): when head_w is set the epilogue does not store
   // the activations but their contraction with conv_flatten's weights for the position's mel row,
@@ -341,6 +350,7 @@ struct TcConv {
 // bookkeeping between two bursts of MMAs is a tensor-pipe bubble, so it is one table look-up per stage.
 //   bits 0-2 source | 3-8 first chunk | 9-11 chunks in the stage | 12 first stage of an accumulation group
 //   | 13 last stage of the group | 14 the source is 3x3 | 15-16 source kind | 17 "rowdup" 3x3 source
+//   | 18 chunks from a half-row tensor | 19-21 ordinary chunks ahead of them (1x1 stages)
 //
 // "rowdup" (row-aligned launches only): the source planes hold a nearest-neighbour 2x up-sampled image, i.e. image rows
 // 2k and 2k+1 are identical.  For an output row at the TOP of such a pair the taps dy = 0 and dy = +1 read the same
@@ -349,9 +359,12 @@ struct TcConv {
 // (y, y+1).  The stage carries the 12 tap matrices [top 6 | bottom 6]; a tile's row parity picks its half.
 constexpr int kMaxProg = 96;
 __host__ __device__ constexpr uint32_t prog_entry(int src, int kc, int n, bool first, bool last, bool taps9, int kind,
-                                                  bool dup = false) {
+                                                  bool dup = false, bool half = false, int nfull = 0) {
+  // bit 18: the stage has chunks staged from a half-row tensor (TcSource::in_up) — as the tensor stores them, i.e.
+  // one staged row per PAIR of image rows; bits 19-21: how many leading chunks of a 1x1 stage are ordinary ones
   return (uint32_t)src | ((uint32_t)kc << 3) | ((uint32_t)n << 9) | ((uint32_t)first << 12) | ((uint32_t)last << 13) |
-         ((uint32_t)taps9 << 14) | ((uint32_t)kind << 15) | ((uint32_t)dup << 17);
+         ((uint32_t)taps9 << 14) | ((uint32_t)kind << 15) | ((uint32_t)dup << 17) | ((uint32_t)half << 18) |
+         ((uint32_t)nfull << 19);
 }
 
 struct TcJob {
@@ -465,7 +478,10 @@ __device__ __forceinline__ void issue_group(uint32_t d0, uint32_t a_lo0, uint32_
 // (y - 1 + par, y + par) — the first six entries of tap_off shifted by par rows — with tap matrices [6 par, 6 par + 6)
 // of the stage.  kParFromTile: the warp's tiles alternate parity (one tile per image row, two tiles per warp);
 // otherwise all of its tiles lie in rows of parity `par_warp`.
-template <int MT, int TS, int BN, bool kParFromTile>
+// kTap0 = 0: the staged rows are image rows (offsets tap_off[0..5]: rows -1 and 0 of the tile's own row + par);
+// kTap0 = 3: the stage holds half rows (one per pair of image rows) and a_lo0 points at the first of the tile's two
+// half rows (offsets tap_off[3..8]: rows 0 and +1), row_step = 0.
+template <int MT, int TS, int BN, bool kParFromTile, int kTap0 = 0>
 __device__ __forceinline__ void issue_group_dup(uint32_t d0, uint32_t a_lo0, uint32_t b_lo0, uint32_t idesc,
                                                 const int (&tap_off)[9], uint32_t accumulate, const uint32_t tile_step,
                                                 const uint32_t row_step, const uint32_t par_warp) {
@@ -481,7 +497,7 @@ __device__ __forceinline__ void issue_group_dup(uint32_t d0, uint32_t a_lo0, uin
       const uint32_t par = kParFromTile ? (uint32_t)(mt & 1) : 0u;
       const uint64_t db = ((uint64_t)b_hi << 32) | (uint64_t)(b_lo0 + (uint32_t)((par * 6 + tap) * BN * 2));
       const uint64_t da = ((uint64_t)a_hi << 32) |
-                          (uint64_t)(a_lo0 + (uint32_t)tap_off[tap] + (uint32_t)mt * tile_step + par * row_step);
+                          (uint64_t)(a_lo0 + (uint32_t)tap_off[tap + kTap0] + (uint32_t)mt * tile_step + par * row_step);
       tc_mma(d0 + (uint32_t)(mt * TS), da, db, idesc, tap == 0 ? accumulate : 1u);
     }
   }
@@ -623,8 +639,48 @@ conv_tc_kernel(const TcJob job) {
         const uint32_t dst = smem_u32(stage0 + (size_t)st * stage_sz);
         const int bs = src.ring ? b % src.ring : b;
         const uint16_t* plane = src.in + (((int64_t)bs * src.planes_total + src.plane0 + 2 * kc) * HpWp + lo) * 8;
+        const int Hh = (p.H >> 1) + 2;       // rows of a half-row tensor
         if (dbg & 1) {
           if (elect_one()) mbar_arrive(full0 + 8 * st);
+        } else if (Rows != 0 && src.in_up != nullptr && kc + n > src.up_chunk0) {
+          // the stage has chunks that live in the half-row tensor: for those, one bulk copy per staged image row and
+          // plane (a 3x3 stage is one chunk; the chunks of a 1x1 stage are routed one by one)
+          // Staged as the tensor stores them: a 3x3 chunk as the kUnitRows / 2 + 2 half rows that cover the unit's rows
+          // and its halo (ONE copy per plane, 25-33 % fewer bytes than image rows), a 1x1 chunk as the unit's own
+          // kUnitRows / 2 half rows; the MMA issuers map image rows to half rows.
+          if (elect_one()) {
+            const int hr0 = (kUnitRows / 2) * lu;        // tensor row of the half row above the unit's first row pair
+            if (taps9) {
+              const uint32_t run = (uint32_t)((kUnitRows / 2 + 2) * Wp) * 16u;
+              const uint16_t* base =
+                  src.in_up + (((int64_t)bs * src.up_planes_total + 2 * (kc - src.up_chunk0)) * Hh + hr0) * Wp * 8;
+              mbar_expect_tx(full0 + 8 * st, 2u * run + w_bytes);
+              bulk_g2s(dst, base, run, full0 + 8 * st);
+              bulk_g2s(dst + run, base + (int64_t)Hh * Wp * 8, run, full0 + 8 * st);
+              if (w_bytes) bulk_g2s(dst + a_bytes, src.w + (int64_t)kc * src.w_stride, w_bytes, full0 + 8 * st);
+            } else {
+              const uint32_t run1h = (uint32_t)((kUnitRows / 2 - 1) * Wp + p.W) * 16u;
+              int n_half = kc + n - src.up_chunk0;
+              if (n_half > n) n_half = n;
+              mbar_expect_tx(full0 + 8 * st, (uint32_t)(n - n_half) * 2u * run1 + (uint32_t)n_half * 2u * run1h + (uint32_t)n * w_bytes);
+#pragma unroll 1
+              for (int j = 0; j < n; ++j) {
+                if (kc + j >= src.up_chunk0) {
+                  const uint16_t* pj = src.in_up + ((((int64_t)bs * src.up_planes_total + 2 * (kc + j - src.up_chunk0)) * Hh +
+                                                     hr0 + 1) * Wp + 1) * 8;
+                  bulk_g2s(dst + (uint32_t)(2 * j) * run1, pj, run1h, full0 + 8 * st);
+                  bulk_g2s(dst + (uint32_t)(2 * j + 1) * run1, pj + (int64_t)Hh * Wp * 8, run1h, full0 + 8 * st);
+                } else {
+                  const uint16_t* pj = plane + (int64_t)2 * j * HpWp * 8 + (int64_t)halo * 8;
+                  bulk_g2s(dst + (uint32_t)(2 * j) * run1, pj, run1, full0 + 8 * st);
+                  bulk_g2s(dst + (uint32_t)(2 * j + 1) * run1, pj + (int64_t)HpWp * 8, run1, full0 + 8 * st);
+                }
+                if (w_bytes)
+                  bulk_g2s(dst + w1_off + (uint32_t)j * w_bytes, src.w + (int64_t)(kc + j) * src.w_stride, w_bytes,
+                           full0 + 8 * st);
+              }
+            }
+          }
         } else if (!taps9) {
           // A 1x1 source has no halo and a ninth of the weights, so a stage-sized slot takes up to `cps` of its
           // K-chunks: [chunk][plane][run1] activations, then [chunk] weights at w1_off.  (One chunk per stage left
@@ -688,6 +744,8 @@ conv_tc_kernel(const TcJob job) {
       const uint32_t a_tile0 = Rows == 2 ? (uint32_t)(me * Wp) : Rows == 1 ? (uint32_t)(me * MTW * Wp)
                                                                         : (uint32_t)((G == 1 ? me * MTW : me * MT) * 128);
       const uint32_t tile_step = Rows == 1 ? (uint32_t)Wp : 128u;      // between this warp's consecutive tiles
+      // the same for chunks staged as half rows: (first image row of the warp's tiles in the unit) >> 1 staged rows down
+      const uint32_t a_tile0_half = Rows == 1 ? (uint32_t)(((me * MTW) >> 1) * Wp) : 0u;
       const int n_prog = job.prog_len[phase];
       int buf = 0;
       uint32_t d_unit = 0u;
@@ -704,6 +762,8 @@ conv_tc_kernel(const TcJob job) {
         }
         const int n = (int)((e >> 9) & 7u);
         const bool first = (e >> 12) & 1u, last = (e >> 13) & 1u, taps9 = (e >> 14) & 1u, dup = (e >> 17) & 1u;
+        const bool half = (e >> 18) & 1u;                 // chunks staged as half rows (TcSource::in_up)
+        const int nfull = (int)((e >> 19) & 7u);
         const uint32_t kind = (e >> 15) & 3u;
         // per-source MMA shape: the dual product writes 2N columns, a correction-only source the upper N
         const bool dual_src = Dual && kind == 1u;
@@ -743,9 +803,19 @@ conv_tc_kernel(const TcJob job) {
             const uint32_t b1 = b_lo_base | ((Rows != 0 && wres) ? b_res : ((a0 + w1_off) >> 4));
             for (int j = 0; j < n; ++j) {
               const uint32_t accumulate = (accumulate_next || j > 0) ? 1u : 0u;
-              const uint32_t aj = a1 + (uint32_t)j * (2u * run1 >> 4), bj = b1 + (uint32_t)j * w_bytes16;
-              if (dual_src) issue_group<MTW, TS, 2 * N>(d_unit + col0, aj, bj, idesc, 1, tap_off, accumulate, tile_step);
-              else issue_group<MTW, TS, N>(d_unit + col0, aj, bj, idesc, 1, tap_off, accumulate, tile_step);
+              uint32_t aj = a1 + (uint32_t)j * (2u * run1 >> 4);
+              const uint32_t bj = b1 + (uint32_t)j * w_bytes16;
+              uint32_t step_j = tile_step;
+              if constexpr (Rows != 0) {
+                if (half && j >= nfull) {
+                  // half rows: the tile in image row r of the unit reads staged row r >> 1 (both tiles of a warp that
+                  // issues for two consecutive rows read the same one)
+                  aj = aj - a_tile0 + a_tile0_half;
+                  if (Rows == 1 && MTW == 2) step_j = 0u;
+                }
+              }
+              if (dual_src) issue_group<MTW, TS, 2 * N>(d_unit + col0, aj, bj, idesc, 1, tap_off, accumulate, step_j);
+              else issue_group<MTW, TS, N>(d_unit + col0, aj, bj, idesc, 1, tap_off, accumulate, step_j);
             }
           } else {
             const uint32_t accumulate = accumulate_next ? 1u : 0u;
@@ -757,7 +827,13 @@ conv_tc_kernel(const TcJob job) {
                 // a warp's tiles share a row parity (`me`) unless it issues for two consecutive rows
                 constexpr bool kParFromTile = (Rows == 1 && MTW == 2);
                 static_assert(Rows == 2 || MTW <= 2, "rowdup: at most two rows per MMA warp");
-                if (wide) issue_group_dup<MTW, TS, 2 * N, kParFromTile>(d_unit + col0, a_lo0, b_lo0, idesc, tap_off, accumulate, tile_step, (uint32_t)Wp, (uint32_t)me);
+                if (half) {
+                  // staged: kUnitRows / 2 + 2 half rows per plane; the tile in image row r (parity par) reads staged
+                  // rows (r >> 1) + par and the next: row `me` for both of a warp's tiles in one row, me + tile otherwise
+                  const uint32_t ah = ((((uint32_t)((kUnitRows / 2 + 2) * Wp)) & 0x3FFFu) << 16 | ((a0 >> 4) + 1u)) + (uint32_t)(me * Wp);
+                  if (wide) issue_group_dup<MTW, TS, 2 * N, kParFromTile, 3>(d_unit + col0, ah, b_lo0, idesc, tap_off, accumulate, tile_step, 0u, (uint32_t)me);
+                  else issue_group_dup<MTW, TS, N, kParFromTile, 3>(d_unit + col0, ah, b_lo0, idesc, tap_off, accumulate, tile_step, 0u, (uint32_t)me);
+                } else if (wide) issue_group_dup<MTW, TS, 2 * N, kParFromTile>(d_unit + col0, a_lo0, b_lo0, idesc, tap_off, accumulate, tile_step, (uint32_t)Wp, (uint32_t)me);
                 else issue_group_dup<MTW, TS, N, kParFromTile>(d_unit + col0, a_lo0, b_lo0, idesc, tap_off, accumulate, tile_step, (uint32_t)Wp, (uint32_t)me);
               } else if (wide) issue_group<MTW, TS, 2 * N>(d_unit + col0, a_lo0, b_lo0, idesc, 9, tap_off, accumulate, tile_step);
               else issue_group<MTW, TS, N>(d_unit + col0, a_lo0, b_lo0, idesc, 9, tap_off, accumulate, tile_step);
@@ -802,7 +878,8 @@ conv_tc_kernel(const TcJob job) {
       const TcConv& c = job.c[phase];
       const float inv_scale = c.inv_scale;
       const float* bias_p = bias_s + phase * N;
-      const int64_t out_plane_stride = c.upsample ? (int64_t)(2 * p.H + 2) * Wp2 * 8 : (int64_t)HpWp * 8;
+      const int64_t out_plane_stride = c.upsample == 1 ? (int64_t)(2 * p.H + 2) * Wp2 * 8
+                                       : c.upsample == 2 ? (int64_t)(p.H + 2) * Wp2 * 8 : (int64_t)HpWp * 8;
       const int b = u / p.units_per_image;
       const int bo = c.out_ring ? b % c.out_ring : b;
       const int64_t img_off = ((int64_t)bo * c.out_planes_total + c.out_plane0) * out_plane_stride;
@@ -826,7 +903,8 @@ conv_tc_kernel(const TcJob job) {
         const int y = pos / Wp, x = pos - y * Wp;
         const bool interior = (y >= 1) && (y <= p.H) && (x >= 1) && (x <= p.W);
         const bool in_tensor = pos < HpWp;
-        const int64_t up = (int64_t)(2 * y - 1) * Wp2 + (2 * x - 1);
+        // (half-row tensor: row y of the tensor holds image rows 2y - 1 and 2y of the up-sampled image)
+        const int64_t up = (int64_t)(c.upsample == 2 ? y : 2 * y - 1) * Wp2 + (2 * x - 1);
         const float rx = (job.epi & 1) ? pre.rx
                          : ((c.res_x != nullptr && interior) ? __ldg(c.res_x + ((int64_t)b * p.H + (y - 1)) * p.W + (x - 1)) : 0.f);
         const float* resw_p = bias_s + 2 * N + phase * N;
@@ -901,7 +979,9 @@ conv_tc_kernel(const TcJob job) {
             }
           } else if (interior) {
             uint16_t* o = c.out + plane_off + up * 8;
-            if (c.pair_store) {
+            if (c.upsample == 2) {
+              st32x2(o, ph);
+            } else if (c.pair_store) {
               st32x2(o, ph);
               st32x2(o + (int64_t)Wp2 * 8, ph);
             } else {
@@ -913,7 +993,9 @@ conv_tc_kernel(const TcJob job) {
             if constexpr (kSplit) {
               const uint4 pl = make_uint4(lw[0], lw[1], lw[2], lw[3]);
               uint16_t* ol = c.out_lo + plane_off + up * 8;
-              if (c.pair_store) {
+              if (c.upsample == 2) {
+                st32x2(ol, pl);
+              } else if (c.pair_store) {
                 st32x2(ol, pl);
                 st32x2(ol + (int64_t)Wp2 * 8, pl);
               } else {

@@ -208,7 +208,7 @@ def test_row_aligned_units_and_folded_maxpool_are_bit_identical(sd_seed0, clip60
     g = load_golden("model_seed0.npz")
     padded = torch.from_numpy(pp.pad_audio(clip60)).cuda()
     eng = Engine(sd_seed0, 0, max_batch=53, mode="f16x3")
-    knobs = ("SS_TC_ROWS", "SS_TC_POOL_FOLD", "SS_TC_TAPMERGE", "SS_TC_WRES")
+    knobs = ("SS_TC_ROWS", "SS_TC_POOL_FOLD", "SS_TC_TAPMERGE", "SS_TC_WRES", "SS_TC_HALFROWS")
     # 0 conv1, 1 conv2, 7 up(conv7), 8 up(conv8) (written by row-aligned up-sampling epilogues), 10 conv1_1's
     # intermediate; 12 / 13 the pooled tensors: hi operands alone (+ 0x100), lo alone (+ 0x200)
     ids = (0, 1, 7, 8, 10, 12 + 0x100, 12 + 0x200, 13 + 0x100, 13 + 0x200)
@@ -267,6 +267,17 @@ def test_row_merged_taps_of_upsampled_inputs(sd_seed0, clip60, monkeypatch):
         e_log = float((six - nine).abs().max() / nine.abs().max())
         print(f"row-merged taps vs nine taps ({n} windows): up(conv8) rel diff {e_act:.2e}, logits rel diff {e_log:.2e}")
         assert 0 < e_act <= 2e-6 and e_log <= 3e-6, (e_act, e_log)     # 0 would mean the knob does nothing
+        # The up-sampled halves of conv8's / conv9_1's inputs in half-row tensors (columns replicated only; default with
+        # merged taps) against 2 x 2 replicated planes of m3 / m4 (SS_TC_HALFROWS=0): storage only, the same bits.
+        up7_six = _dump(eng, 7, n)
+        monkeypatch.setenv("SS_TC_HALFROWS", "0")
+        full = eng.classify(mel)
+        up7_full, up8_full = _dump(eng, 7, n), _dump(eng, 8, n)
+        monkeypatch.delenv("SS_TC_HALFROWS")
+        eng.check_health()
+        assert torch.equal(up7_full, up7_six) and torch.equal(up8_full, up8_six), n
+        assert torch.equal(full, six), n
+        assert torch.equal(eng.classify(mel), six), n          # and back, in the same tensors
     assert eng.check_guards() == 0
     eng.close()
 

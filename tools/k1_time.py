@@ -1,5 +1,7 @@
+"""K1 alone: CUDA-event time of ss_features over one 10-minute clip, band-by-band mel walk (SS_MEL_WALK=0) against the
+two-band walk, two contexts each, median of 15 (profiles/r2_tuning_experiments.txt, section 13)."""
 import json, os, sys, torch, statistics
-ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from softspoken_b200 import checkpoint, synth
 from softspoken_b200.engine import Engine

@@ -1,5 +1,7 @@
+"""Print the launch configuration (geometry, ring depth, resident weights, stage program length) of every tcgen05 conv
+launch of one classify call (SS_TC_VERBOSE=1)."""
 import json, os, sys, torch
-ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from softspoken_b200 import checkpoint
 from softspoken_b200.engine import Engine

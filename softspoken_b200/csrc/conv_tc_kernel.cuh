@@ -516,7 +516,12 @@ conv_tc_kernel(const TcJob job) {
   // Round r of the persistent loop: CTA j takes item r * grid + (j + r) % grid.  The rotation matters for fused
   // launches: items alternate c[0] / c[1], the grid is even, and without it a CTA would see one phase only (the two
   // phases cost differently, so half the SMs would finish early).  Items still increase with r for every CTA.
-  auto item_of = [](int r) { return r * (int)gridDim.x + (int)((blockIdx.x + (unsigned)r) % gridDim.x); };
+  // (single-convolution launches need no rotation, and the MMA issuers should not pay an integer division at every
+  // unit boundary — whatever they do between two units is a tensor-pipe bubble; job.layout bit 1 keeps it for A/B runs)
+  const bool rotate = n_phase == 2 || (job.layout & 2) != 0;
+  auto item_of = [rotate](int r) {
+    return r * (int)gridDim.x + (rotate ? (int)((blockIdx.x + (unsigned)r) % gridDim.x) : (int)blockIdx.x);
+  };
   static_assert(!Dual || PrecTraits<P>::split, "the dual layout belongs to the split precision");
   constexpr int MT = TilesPerUnit<N, Dual>::value;
   constexpr int TS = TilesPerUnit<N, Dual>::TS;
@@ -737,6 +742,9 @@ conv_tc_kernel(const TcJob job) {
     int st = 0;
     uint32_t ph = 0, a0 = stage_base;
     bool ready = false;            // the full barrier of the stage about to be consumed was already seen complete
+    uint32_t e_next = job.prog[0][0];
+    uint32_t pb_next = (Rows != 0) ? job.prog_b[0] : 0u;
+    const int n_prog0 = job.prog_len[0];
     for (int item; (item = item_of(k)) < n_items && ok; ++k) {
       int phase, u;
       decode_item(item, T, D, n_phase, phase, u);
@@ -746,19 +754,23 @@ conv_tc_kernel(const TcJob job) {
       const uint32_t tile_step = Rows == 1 ? (uint32_t)Wp : 128u;      // between this warp's consecutive tiles
       // the same for chunks staged as half rows: (first image row of the warp's tiles in the unit) >> 1 staged rows down
       const uint32_t a_tile0_half = Rows == 1 ? (uint32_t)(((me * MTW) >> 1) * Wp) : 0u;
-      const int n_prog = job.prog_len[phase];
+      const int n_prog = (n_phase == 2) ? job.prog_len[phase] : n_prog0;
       int buf = 0;
       uint32_t d_unit = 0u;
       bool accumulate_next = false;
-      uint32_t e_next = job.prog[phase][0];
-      uint32_t pb_next = (Rows != 0) ? job.prog_b[0] : 0u;
+      // (single-phase launches: the first entry of the next unit's program was fetched during this unit's last stage;
+      // job.layout bit 2 reloads it here, for A/B runs)
+      if (n_phase == 2 || (job.layout & 4)) {
+        e_next = job.prog[phase][0];
+        if constexpr (Rows != 0) pb_next = job.prog_b[0];
+      }
       for (int pi = 0; pi < n_prog && ok; ++pi) {
         const uint32_t e = e_next;
-        e_next = job.prog[phase][pi + 1 < n_prog ? pi + 1 : pi];      // fetched a stage ahead (constant-bank latency)
+        e_next = job.prog[phase][pi + 1 < n_prog ? pi + 1 : 0];      // fetched a stage ahead (constant-bank latency)
         uint32_t pb = 0u;
         if constexpr (Rows != 0) {
           pb = pb_next;
-          pb_next = job.prog_b[pi + 1 < n_prog ? pi + 1 : pi];
+          pb_next = job.prog_b[pi + 1 < n_prog ? pi + 1 : 0];
         }
         const int n = (int)((e >> 9) & 7u);
         const bool first = (e >> 12) & 1u, last = (e >> 13) & 1u, taps9 = (e >> 14) & 1u, dup = (e >> 17) & 1u;
@@ -890,17 +902,21 @@ conv_tc_kernel(const TcJob job) {
       // The scalar residual input of a tile's position (conv1_1: mel; 0 outside the image or without one) is fetched
       // BEFORE the wait for the accumulators: the CTA's shared memory takes the whole L1 carve-out, so the load is an
       // L2 round trip, which otherwise sits between the accumulator load and the first FMA (-7 % on conv1_1.c2).
-      struct TilePre { float rx; };
-      auto preload = [&](const int pos) {
+      // (row, column) of the position travel with it: one integer division per tile in flat units, none in row-aligned
+      // ones, where the caller knows the row (y_known >= 0)
+      struct TilePre { float rx; int y, x; };
+      auto preload = [&](const int pos, const int y_known = -1) {
         TilePre t;
-        const int y = pos / Wp, x = pos - y * Wp;
+        const int y = y_known >= 0 ? y_known : pos / Wp, x = pos - y * Wp;
+        t.y = y;
+        t.x = x;
         const bool interior = (y >= 1) && (y <= p.H) && (x >= 1) && (x <= p.W);
         t.rx = (c.res_x != nullptr && interior && (job.epi & 1))
                    ? __ldg(c.res_x + ((int64_t)b * p.H + (y - 1)) * p.W + (x - 1)) : 0.f;
         return t;
       };
       auto finalize = [&](const uint32_t (&v)[32], const int n0, const int pos, const TilePre& pre) {
-        const int y = pos / Wp, x = pos - y * Wp;
+        const int y = pre.y, x = pre.x;
         const bool interior = (y >= 1) && (y <= p.H) && (x >= 1) && (x <= p.W);
         const bool in_tensor = pos < HpWp;
         // (half-row tensor: row y of the tensor holds image rows 2y - 1 and 2y of the up-sampled image)
@@ -1173,16 +1189,20 @@ conv_tc_kernel(const TcJob job) {
           if constexpr (Rows != 0) return q0 + (mt / Rows) * Wp + (mt % Rows) * 128 + quad * 32 + lane;
           else return q0 + mt * 128 + quad * 32 + lane;
         };
+        auto tile_row = [&](const int mt) {        // padded image row of tile mt, where the geometry knows it
+          if constexpr (Rows != 0) return kUnitRows * (u - b * p.units_per_image) + 1 + mt / Rows;
+          else return -1;
+        };
         // this warp's tiles: tile_par, tile_par + 2, ...; the global operands of a tile are fetched one tile ahead
         // (the first before the wait for the accumulators), the loop stays rolled (code size)
-        TilePre cur = preload(tile_pos(tile_par));
+        TilePre cur = preload(tile_pos(tile_par), tile_row(tile_par));
         ok = mbar_wait_t(accf0 + 8 * buf, f_parity, p.err, 3, w_accf);
         if (!ok) break;
         tc_fence_after();
 #pragma unroll 1
         for (int mt = tile_par; mt < MT; mt += 2) {
           const int pos = tile_pos(mt);
-          const TilePre nxt = (mt + 2 < MT) ? preload(tile_pos(mt + 2)) : cur;
+          const TilePre nxt = (mt + 2 < MT) ? preload(tile_pos(mt + 2), tile_row(mt + 2)) : cur;
 #pragma unroll
           for (int n0 = 0; n0 < N; n0 += 32) {
             uint32_t v[32];

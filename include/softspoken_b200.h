@@ -240,6 +240,9 @@ SS_API int ss_silence_host(ss_ctx* ctx, float* pcm_host, int64_t n_elems, const 
 
 /* Test instrumentation (parity localisation, not part of the drop-in surface): copy internal activation
  * `which` of the last tensor-core ss_classify call to out_dev as NCHW float32 and report its shape.
+ * which: 0-3 conv1..conv4, 4 bottleneck, 5-8 up(encoder_out) .. up(conv8), 9 conv9, 10 conv1_1's intermediate,
+ * 11 the im2col'd mel operand (legacy form), 12 / 13 MaxPool(conv1) / MaxPool(conv2); + 0x100: twice the hi operands
+ * alone, + 0x200: twice the lo operands alone (split precision).
  * Also surfaces a tcgen05 pipeline time-out of that call as SS_E_CUDA. */
 SS_API int ss_debug_activation(ss_ctx* ctx, int which, int n_windows, float* out_dev, int* C, int* H, int* W,
                                void* stream);

@@ -229,7 +229,7 @@ def test_row_aligned_units_and_folded_maxpool_are_bit_identical(sd_seed0, clip60
         mel = eng.features(padded, torch.from_numpy(g["starts"][:n]))
         plain, acts_plain = run({"SS_TC_ROWS": "0", "SS_TC_POOL_FOLD": "0"}, mel, n)
         for env in ({}, {"SS_TC_POOL_FOLD": "0"}, {"SS_TC_ROWS": "0"}, {"SS_TC_POOL_FOLD": "1"}, {"SS_TC_POOL_FOLD": "2"},
-                    {"SS_TC_WRES": "0"}, {"SS_TC_WRES": "0", "SS_TC_POOL_FOLD": "0"}):
+                    {"SS_TC_WRES": "0"}, {"SS_TC_WRES": "0", "SS_TC_POOL_FOLD": "0"}, {"SS_TC_WRES": "2"}):
             # (row-merged taps change the summation, not the sum: they have their own test below)
             got, acts = run(dict(env, SS_TC_TAPMERGE="0"), mel, n)
             for w, a, b in zip(ids, acts_plain, acts):
@@ -278,6 +278,11 @@ def test_row_merged_taps_of_upsampled_inputs(sd_seed0, clip60, monkeypatch):
         assert torch.equal(up7_full, up7_six) and torch.equal(up8_full, up8_six), n
         assert torch.equal(full, six), n
         assert torch.equal(eng.classify(mel), six), n          # and back, in the same tensors
+        # resident weights wherever they fit (SS_TC_WRES=2: also next to merged taps, half rows and long 1x1 sources,
+        # where the launcher leaves them off by default because they are slower there): the same bits
+        monkeypatch.setenv("SS_TC_WRES", "2")
+        assert torch.equal(eng.classify(mel), six), n
+        monkeypatch.delenv("SS_TC_WRES")
     assert eng.check_guards() == 0
     eng.close()
 

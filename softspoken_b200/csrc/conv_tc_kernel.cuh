@@ -22,6 +22,12 @@
 // bound by exactly that traffic).  The groups still complete one after the other (group 0's MMAs of the last
 // chunk are issued, and committed, before group 1's), so the epilogue of a group overlaps the MMAs of the next.
 //
+// Row-aligned units (template parameter Rows, dual layout at image widths of 128 / 256): a unit is 2 or 4 whole image
+// rows instead of consecutive positions of the padded image, which makes four things possible (all documented at the
+// TcConv / TcSource fields they add): MaxPool2d(2) in the epilogue (TcConv::pool_out), six instead of nine tap MMAs on
+// up-sampled inputs ("rowdup" sources, prog_entry), inputs stored with one row per row pair (TcSource::in_up,
+// TcConv::upsample == 2) and the launch's weights resident in shared memory (TcConv::wres).
+//
 // Operand precision is a template parameter:
 //   Bf16   — bf16 operands, one pass (throughput mode; ~4e-2 relative logit error over the 25-layer stack);
 //   F16    — fp16 operands, one pass (8x finer mantissa at the same cost);

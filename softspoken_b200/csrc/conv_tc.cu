@@ -169,10 +169,12 @@ conv1_direct(const float* __restrict__ mel, const float* __restrict__ w /* [9][3
 // two differ when lo is exactly half an ulp of hi (one value in 4,096: hi + lo then sits midway between two fp16
 // numbers and rounds to the even one), and keeping the pair makes this kernel and the pool folded into the
 // convolution epilogue (TcConv::rows, which splits the float32 maximum it still holds) write the same bits.
+// Tensors are addressed through (image stride, plane stride) in positions: image- or plane-major (Tensor).
 template <Prec P>
-__global__ void pool_planar(const uint16_t* __restrict__ in, const uint16_t* __restrict__ in_lo, int in_planes_total,
-                            int plane0, int planes, int H, int W, uint16_t* __restrict__ out,
-                            uint16_t* __restrict__ out_lo, int64_t total) {
+__global__ void pool_planar(const uint16_t* __restrict__ in, const uint16_t* __restrict__ in_lo, int64_t in_img_stride,
+                            int64_t in_plane_stride, int plane0, int planes, int H, int W, uint16_t* __restrict__ out,
+                            uint16_t* __restrict__ out_lo, int64_t out_img_stride, int64_t out_plane_stride,
+                            int64_t total) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const int W2 = W >> 1, H2 = H >> 1;
@@ -182,8 +184,9 @@ __global__ void pool_planar(const uint16_t* __restrict__ in, const uint16_t* __r
   const int pl = (int)(r % planes);
   const int64_t b = r / planes;
   const int Wp = W + 2, Hp = H + 2, Wq = W2 + 2, Hq = H2 + 2;
-  const int64_t src = ((b * in_planes_total + plane0 + pl) * Hp + (2 * y + 1)) * (int64_t)Wp + (2 * x + 1);
-  const int64_t dst = ((b * planes + pl) * Hq + (y + 1)) * (int64_t)Wq + (x + 1);
+  (void)Hp; (void)Hq;
+  const int64_t src = b * in_img_stride + (plane0 + pl) * in_plane_stride + (int64_t)(2 * y + 1) * Wp + (2 * x + 1);
+  const int64_t dst = b * out_img_stride + pl * out_plane_stride + (int64_t)(y + 1) * Wq + (x + 1);
   if constexpr (PrecTraits<P>::split) {
     const int64_t offs[4] = {src, src + 1, src + Wp, src + Wp + 1};
     uint4 hv[4], lv[4];
@@ -386,8 +389,9 @@ __global__ void spec_out_planar(const uint16_t* __restrict__ x, const uint16_t* 
 // planar -> NCHW f32 (debug / parity localisation only)
 // halfrows: the tensor is a half-row tensor (TcSource::in_up): H / 2 + 2 rows, row 1 + y / 2 holds image row y
 template <Prec P>
-__global__ void planar_to_nchw(const uint16_t* __restrict__ in, const uint16_t* __restrict__ in_lo, int planes_total,
-                               int plane0, int C, int H, int W, float* __restrict__ out, int64_t total, int halfrows) {
+__global__ void planar_to_nchw(const uint16_t* __restrict__ in, const uint16_t* __restrict__ in_lo, int64_t img_stride,
+                               int64_t plane_stride, int plane0, int C, int H, int W, float* __restrict__ out,
+                               int64_t total, int halfrows) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const int x = (int)(i % W);
@@ -395,10 +399,10 @@ __global__ void planar_to_nchw(const uint16_t* __restrict__ in, const uint16_t* 
   const int y = (int)(r % H); r /= H;
   const int c = (int)(r % C);
   const int64_t b = r / C;
-  const int Wp = W + 2, Hp = halfrows ? H / 2 + 2 : H + 2;
+  const int Wp = W + 2;
   const int row = halfrows ? (y >> 1) + 1 : y + 1;
   float a[8];
-  load8<P>(in, in_lo, ((b * planes_total + plane0 + c / 8) * Hp + row) * (int64_t)Wp + (x + 1), a);
+  load8<P>(in, in_lo, b * img_stride + (plane0 + c / 8) * plane_stride + (int64_t)row * Wp + (x + 1), a);
   out[i] = a[c & 7];
 }
 
@@ -409,6 +413,13 @@ struct Tensor {
   uint16_t* alloc_lo = nullptr;   // split precision only
   uint16_t* lo = nullptr;
   int planes = 0, H = 0, W = 0;
+  // plane-major: [C/8][cap][H+2][W+2][8] instead of [B][C/8][H+2][W+2][8] — the padded images of a batch are then
+  // contiguous in every plane, which is what packed work units stage with one bulk copy (TcConv::packed)
+  bool plane_major = false;
+  int cap = 0;                    // images the tensor was allocated for
+  int64_t hw() const { return (int64_t)(H + 2) * (W + 2); }
+  int64_t img_stride() const { return plane_major ? hw() : planes * hw(); }        // in positions (16-byte vectors)
+  int64_t plane_stride() const { return plane_major ? cap * hw() : hw(); }
 };
 
 struct PackedConv {
@@ -481,10 +492,12 @@ int alloc_guarded(ss_ctx* ctx, TcState* st, uint16_t** alloc, uint16_t** data, s
   return SS_OK;
 }
 
-int alloc_tensor(ss_ctx* ctx, TcState* st, Tensor* t, int B, int C, int H, int W) {
+int alloc_tensor(ss_ctx* ctx, TcState* st, Tensor* t, int B, int C, int H, int W, bool plane_major = false) {
   t->planes = C / 8;
   t->H = H;
   t->W = W;
+  t->plane_major = plane_major;
+  t->cap = B;
   const size_t body = (size_t)B * t->planes * (H + 2) * (W + 2) * 8 * sizeof(uint16_t);
   int rc = alloc_guarded(ctx, st, &t->alloc, &t->data, body);
   if (rc) return rc;
@@ -682,6 +695,22 @@ int launch_conv_npg(TcJob job, int B, cudaStream_t st) {
   const int positions = p.H * (p.W + 2) - 2;          // (1,1) .. (H,W) in flattened padded coordinates
   p.units_per_image = rows ? p.H / unit_rows : (positions + G * MT * 128 - 1) / (G * MT * 128);
   p.total_units = p.units_per_image * B;
+  // Packed units (TcConv::packed) for the images of 16 x 32 and below, whose last unit is mostly air: the batch as one
+  // stream of positions.  SS_TC_PACK=0: units per image (A/B runs).
+  p.packed = 0;
+  p.batch = B;
+  {
+    const char* pk = getenv("SS_TC_PACK");
+    bool contiguous = true;      // every source plane-major: the stream of padded images is contiguous in each plane
+    for (int i = 0; i < p.n_src; ++i) contiguous &= p.src[i].img_stride == (int64_t)(p.H + 2) * (p.W + 2) && !p.src[i].in_up;
+    if (!rows && contiguous && job.n_phase == 1 && p.H * p.W <= 512 && !p.head_w && !p.res_x &&
+        (pk == nullptr || atoi(pk) != 0)) {
+      const int64_t stream = (int64_t)(B - 1) * (p.H + 2) * (p.W + 2) + positions;
+      p.packed = 1;
+      p.total_units = (int)((stream + G * MT * 128 - 1) / (G * MT * 128));
+      p.units_per_image = p.total_units;      // every unit is a unit of "image 0": positions run on across images
+    }
+  }
   for (int ph = 0; ph < job.n_phase; ++ph)
     SS_REQUIRE(job.c[ph].relu == 1, SS_E_ARG, "conv_tc_kernel applies ReLU unconditionally");
   // Split-K sub-accumulation (TcConv::n_sub): the K-chunks of the 3x3 sources are cut into groups so that an MMA
@@ -850,9 +879,17 @@ void add_sources(TcConv* p, const TcState* s, const Tensor& x, int plane0, const
                  int ring = 0, const Tensor* up = nullptr, int up_chunk0 = 0) {
   const int part_elems = w.taps * w.n * 16;
   const int chunk_elems = w.parts * part_elems;
+  const int first = p->n_src;
+  auto set_strides = [&]() {
+    for (int i = first; i < p->n_src; ++i) {
+      p->src[i].img_stride = x.img_stride();
+      p->src[i].plane_stride = x.plane_stride();
+    }
+  };
   if (!is_split(s->prec)) {
     if (terms != Terms::Corrections)
       p->src[p->n_src++] = TcSource{x.data, x.planes, plane0, w.n_chunks, w.taps, 0, ring, chunk_elems, w.w};
+    set_strides();
     return;
   }
   if (w.dual) {
@@ -867,6 +904,7 @@ void add_sources(TcConv* p, const TcState* s, const Tensor& x, int plane0, const
       p->src[p->n_src++] = hi;
       p->src[p->n_src++] = lo;
     }
+    set_strides();
     return;
   }
   if (terms != Terms::Main) {
@@ -875,6 +913,7 @@ void add_sources(TcConv* p, const TcState* s, const Tensor& x, int plane0, const
   }
   if (terms != Terms::Corrections)
     p->src[p->n_src++] = TcSource{x.data, x.planes, plane0, w.n_chunks, w.taps, 0, ring, chunk_elems, w.w};
+  set_strides();
 }
 
 // One ResBlock: t = relu(conv3x3(x) + b1);  out = relu(conv3x3(t) + conv1x1(x) + b2 + b_res).
@@ -894,6 +933,7 @@ int tc_res_block(TcState* s, int which, const Tensor& x, int x_plane0, Tensor& o
   p.inv_scale = rb.inv_scale1;
   p.relu = 1;
   p.out = t.data; p.out_lo = t.lo; p.out_planes_total = t.planes; p.out_plane0 = 0; p.upsample = 0;
+  p.o_img_stride = t.img_stride(); p.o_plane_stride = t.plane_stride();
   p.err = s->err;
   TcConv q{};
   add_sources(&q, s, t, 0, rb.c2, Terms::Corrections, -1);     // -1: "the intermediate tensor", ring resolved at launch
@@ -910,6 +950,7 @@ int tc_res_block(TcState* s, int which, const Tensor& x, int x_plane0, Tensor& o
   q.inv_scale = rb.inv_scale2;
   q.relu = 1;
   q.out = out.data; q.out_lo = out.lo; q.out_planes_total = out.planes; q.out_plane0 = out_plane0; q.upsample = upsample;
+  q.o_img_stride = out.img_stride(); q.o_plane_stride = out.plane_stride();
   const char* pe = getenv("SS_TC_PAIR_STORE");
   q.pair_store = pe ? atoi(pe) : 1;
   q.head_w = head_w; q.head_out = head_out;
@@ -1007,8 +1048,9 @@ int tc_res_block(TcState* s, int which, const Tensor& x, int x_plane0, Tensor& o
 template <Prec P>
 int tc_pool_p(const Tensor& in, int plane0, int planes, Tensor& out, int B, cudaStream_t st) {
   const int64_t total = (int64_t)B * planes * (in.H / 2) * (in.W / 2);
-  pool_planar<P><<<(int)((total + 255) / 256), 256, 0, st>>>(in.data, in.lo, in.planes, plane0, planes, in.H, in.W,
-                                                             out.data, out.lo, total);
+  pool_planar<P><<<(int)((total + 255) / 256), 256, 0, st>>>(in.data, in.lo, in.img_stride(), in.plane_stride(), plane0,
+                                                             planes, in.H, in.W, out.data, out.lo, out.img_stride(),
+                                                             out.plane_stride(), total);
   SS_CUDA_CHECK(cudaGetLastError());
   count_launch();
   return SS_OK;
@@ -1130,10 +1172,12 @@ int tc_build_state(ss_ctx* ctx, Prec prec, TcState* s) {
   T(m3, 128, 64, 128);
   T(p2, 64, 32, 64);
   T(m2, 192, 32, 64);
-  T(p3, 96, 16, 32);
-  T(m1, 256, 16, 32);
-  T(p4, 128, 8, 16);
-  T(bott, 128, 8, 16);
+  // the tensors of the layers at 16 x 32 and 8 x 16 are plane-major (Tensor::plane_major): packed work units
+#define TP(t, C, H, W) do { if ((rc = alloc_tensor(ctx, s, &s->t, B, C, H, W, true))) return rc; } while (0)
+  TP(p3, 96, 16, 32);
+  TP(m1, 256, 16, 32);
+  TP(p4, 128, 8, 16);
+  TP(bott, 128, 8, 16);
   if (is_split(prec)) {
     T(u4, 32, 64, 256);
     T(u3, 64, 32, 128);
@@ -1143,10 +1187,11 @@ int tc_build_state(ss_ctx* ctx, Prec prec, TcState* s) {
   T(t[RB_CONV1], 32, 128, 256);
   T(t[RB_CONV2], 64, 64, 128);
   T(t[RB_CONV3], 96, 32, 64);
-  T(t[RB_CONV4], 128, 16, 32);
-  T(t[RB_BOTTLENECK], 128, 8, 16);
-  T(t[RB_ENCODER_OUT], 128, 8, 16);
-  T(t[RB_CONV6], 96, 16, 32);
+  TP(t[RB_CONV4], 128, 16, 32);
+  TP(t[RB_BOTTLENECK], 128, 8, 16);
+  TP(t[RB_ENCODER_OUT], 128, 8, 16);
+  TP(t[RB_CONV6], 96, 16, 32);
+#undef TP
   T(t[RB_CONV7], 64, 32, 64);
   T(t[RB_CONV8], 32, 64, 128);
   T(t[RB_CONV9], 32, 128, 256);
@@ -1333,8 +1378,11 @@ int tc_debug_dump(ss_ctx* ctx, int which, int n_windows, float* out, int* C, int
   // up(conv7) / up(conv8) live in the half-row tensors when the last call used them (full image geometry for the dump)
   int halfrows = 0;
   Tensor full_geom;
+  int64_t is = e.t->img_stride(), ps = e.t->plane_stride();
   if (s->halfrows_last && (which == 7 || which == 8)) {
     full_geom = which == 7 ? s->u3 : s->u4;
+    is = full_geom.img_stride();
+    ps = full_geom.plane_stride();
     full_geom.H *= 2;
     e = Sel{&full_geom, 0, e.c};
     halfrows = 1;
@@ -1348,9 +1396,9 @@ int tc_debug_dump(ss_ctx* ctx, int which, int n_windows, float* out, int* C, int
     const int64_t total = (int64_t)n_windows * e.c * e.t->H * e.t->W;
     const int grid = (int)((total + 255) / 256);
     switch (s->prec) {
-      case Prec::Bf16: planar_to_nchw<Prec::Bf16><<<grid, 256, 0, st>>>(e.t->data, e.t->lo, e.t->planes, e.plane0, e.c, e.t->H, e.t->W, out, total, halfrows); break;
-      case Prec::F16: planar_to_nchw<Prec::F16><<<grid, 256, 0, st>>>(e.t->data, e.t->lo, e.t->planes, e.plane0, e.c, e.t->H, e.t->W, out, total, halfrows); break;
-      case Prec::F16x3: planar_to_nchw<Prec::F16x3><<<grid, 256, 0, st>>>(e.t->data, e.t->lo, e.t->planes, e.plane0, e.c, e.t->H, e.t->W, out, total, halfrows); break;
+      case Prec::Bf16: planar_to_nchw<Prec::Bf16><<<grid, 256, 0, st>>>(e.t->data, e.t->lo, is, ps, e.plane0, e.c, e.t->H, e.t->W, out, total, halfrows); break;
+      case Prec::F16: planar_to_nchw<Prec::F16><<<grid, 256, 0, st>>>(e.t->data, e.t->lo, is, ps, e.plane0, e.c, e.t->H, e.t->W, out, total, halfrows); break;
+      case Prec::F16x3: planar_to_nchw<Prec::F16x3><<<grid, 256, 0, st>>>(e.t->data, e.t->lo, is, ps, e.plane0, e.c, e.t->H, e.t->W, out, total, halfrows); break;
     }
     SS_CUDA_CHECK(cudaGetLastError());
   }

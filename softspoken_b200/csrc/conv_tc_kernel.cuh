@@ -275,6 +275,10 @@ struct TcSource {
   // written once and read from DRAM once per pair of rows instead of twice.  null: every chunk comes from `in`.
   const uint16_t* in_up;
   int up_chunk0, up_planes_total;
+  // Where image b / plane k of `in` starts, in positions (16-byte vectors): image-major tensors [B][C/8][..] have
+  // img_stride = planes * (H+2)(W+2), plane_stride = (H+2)(W+2); plane-major ones [C/8][B_cap][..] (the small images
+  // of the deep layers, see TcConv::packed) img_stride = (H+2)(W+2), plane_stride = B_cap * (H+2)(W+2).
+  int64_t img_stride, plane_stride;
 };
 
 struct TcConv {
@@ -287,6 +291,7 @@ struct TcConv {
   uint16_t* out;       // hi (or only) output tensor
   uint16_t* out_lo;    // residual output tensor (split precision), else null
   int out_planes_total, out_plane0;
+  int64_t o_img_stride, o_plane_stride;   // the same two strides of the OUTPUT tensor (in its own geometry)
   int upsample;        // 0: store at the position; 1: 2 x 2 replicated store into a tensor at twice the resolution;
                        // 2: 2 x 1 (columns only) into a half-row tensor (TcSource::in_up)
   int out_ring;        // like TcSource::ring, for the output tensor
@@ -304,6 +309,16 @@ struct TcConv {
   const float* head_w;   // [128 mel][32][4] float32 or null
   float* head_out;       // [B][128][256][4] float32
   int units_per_image, total_units;
+  // Packed units (flat geometry, small images in plane-major tensors): the padded images of the batch are ONE stream
+  // of positions g = b * (H+2)(W+2) + q — contiguous in every plane of a plane-major tensor — and a unit is MT*128
+  // consecutive positions of the stream, wherever images begin and end: an 8 x 16 image has 180 padded positions, so
+  // one 256-position unit per image computes 30 % air (16 x 32: 612 positions in three units, 20 %).  Taps that leave
+  // an image read its neighbour's zero border rows or feed border positions only, exactly as inside one image.  The
+  // launcher sets units_per_image = total_units (every unit belongs to "image 0", positions run on), so the producer
+  // and the MMA issuers need nothing new; the epilogue finds each position's image.  `batch` = images in the stream.
+  // (With image-major tensors a staged run needs one bulk copy per image it touches: measured 20-86 % SLOWER on these
+  // launches — small bulk copies are what a stage can least afford — hence the layout.)
+  int packed, batch;
   // Split-K sub-accumulation (split precision, G = 1).  The tensor core rounds its fp32 accumulator toward zero after
   // every MMA and aligns the 16 products of an MMA to the accumulator's exponent with only ~2 guard bits: a chain of
   // n accumulating MMAs ends ~2.3 n ulp short of the exact sum, a bias that grows linearly with the chain
@@ -649,7 +664,8 @@ conv_tc_kernel(const TcJob job) {
         if (!ok) break;
         const uint32_t dst = smem_u32(stage0 + (size_t)st * stage_sz);
         const int bs = src.ring ? b % src.ring : b;
-        const uint16_t* plane = src.in + (((int64_t)bs * src.planes_total + src.plane0 + 2 * kc) * HpWp + lo) * 8;
+        const int64_t pstride = src.plane_stride * 8;      // 16-bit elements between consecutive planes
+        const uint16_t* plane = src.in + ((int64_t)bs * src.img_stride + (int64_t)(src.plane0 + 2 * kc) * src.plane_stride + lo) * 8;
         const int Hh = (p.H >> 1) + 2;       // rows of a half-row tensor
         if (dbg & 1) {
           if (elect_one()) mbar_arrive(full0 + 8 * st);
@@ -682,9 +698,9 @@ conv_tc_kernel(const TcJob job) {
                   bulk_g2s(dst + (uint32_t)(2 * j) * run1, pj, run1h, full0 + 8 * st);
                   bulk_g2s(dst + (uint32_t)(2 * j + 1) * run1, pj + (int64_t)Hh * Wp * 8, run1h, full0 + 8 * st);
                 } else {
-                  const uint16_t* pj = plane + (int64_t)2 * j * HpWp * 8 + (int64_t)halo * 8;
+                  const uint16_t* pj = plane + (int64_t)2 * j * pstride + (int64_t)halo * 8;
                   bulk_g2s(dst + (uint32_t)(2 * j) * run1, pj, run1, full0 + 8 * st);
-                  bulk_g2s(dst + (uint32_t)(2 * j + 1) * run1, pj + (int64_t)HpWp * 8, run1, full0 + 8 * st);
+                  bulk_g2s(dst + (uint32_t)(2 * j + 1) * run1, pj + pstride, run1, full0 + 8 * st);
                 }
                 if (w_bytes)
                   bulk_g2s(dst + w1_off + (uint32_t)j * w_bytes, src.w + (int64_t)(kc + j) * src.w_stride, w_bytes,
@@ -699,9 +715,9 @@ conv_tc_kernel(const TcJob job) {
           if (elect_one()) {
             mbar_expect_tx(full0 + 8 * st, (uint32_t)n * (2u * run1 + w_bytes));
             for (int j = 0; j < n; ++j) {
-              const uint16_t* pj = plane + (int64_t)2 * j * HpWp * 8 + (int64_t)halo * 8;    // centre tap only
+              const uint16_t* pj = plane + (int64_t)2 * j * pstride + (int64_t)halo * 8;    // centre tap only
               bulk_g2s(dst + (uint32_t)(2 * j) * run1, pj, run1, full0 + 8 * st);
-              bulk_g2s(dst + (uint32_t)(2 * j + 1) * run1, pj + (int64_t)HpWp * 8, run1, full0 + 8 * st);
+              bulk_g2s(dst + (uint32_t)(2 * j + 1) * run1, pj + pstride, run1, full0 + 8 * st);
               if (w_bytes)
                 bulk_g2s(dst + w1_off + (uint32_t)j * w_bytes, src.w + (int64_t)(kc + j) * src.w_stride, w_bytes,
                          full0 + 8 * st);
@@ -711,7 +727,7 @@ conv_tc_kernel(const TcJob job) {
           const uint32_t run = (uint32_t)L * 16u;
           mbar_expect_tx(full0 + 8 * st, 2u * run + w_bytes);
           bulk_g2s(dst, plane, run, full0 + 8 * st);
-          bulk_g2s(dst + run, plane + (int64_t)HpWp * 8, run, full0 + 8 * st);
+          bulk_g2s(dst + run, plane + pstride, run, full0 + 8 * st);
           if (w_bytes) bulk_g2s(dst + a_bytes, src.w + (int64_t)kc * src.w_stride, w_bytes, full0 + 8 * st);
         }
         __syncwarp();
@@ -896,11 +912,10 @@ conv_tc_kernel(const TcJob job) {
       const TcConv& c = job.c[phase];
       const float inv_scale = c.inv_scale;
       const float* bias_p = bias_s + phase * N;
-      const int64_t out_plane_stride = c.upsample == 1 ? (int64_t)(2 * p.H + 2) * Wp2 * 8
-                                       : c.upsample == 2 ? (int64_t)(p.H + 2) * Wp2 * 8 : (int64_t)HpWp * 8;
+      const int64_t out_plane_stride = c.o_plane_stride * 8;      // 16-bit elements between planes of the output tensor
       const int b = u / p.units_per_image;
       const int bo = c.out_ring ? b % c.out_ring : b;
-      const int64_t img_off = ((int64_t)bo * c.out_planes_total + c.out_plane0) * out_plane_stride;
+      const int64_t img_off = ((int64_t)bo * c.o_img_stride + (int64_t)c.out_plane0 * c.o_plane_stride) * 8;
       float vmax = 0.f;
 
       // Everything after the accumulators of one tile's 32-column block [n0, n0 + 32) are final: undo the weight
@@ -910,13 +925,21 @@ conv_tc_kernel(const TcJob job) {
       // L2 round trip, which otherwise sits between the accumulator load and the first FMA (-7 % on conv1_1.c2).
       // (row, column) of the position travel with it: one integer division per tile in flat units, none in row-aligned
       // ones, where the caller knows the row (y_known >= 0)
-      struct TilePre { float rx; int y, x; };
+      // Packed units: `pos` runs over the stream of the batch's images; the tile carries its image and the position in it.
+      struct TilePre { float rx; int y, x, b, q; };
+      const bool packed = Rows == 0 && p.packed != 0;
       auto preload = [&](const int pos, const int y_known = -1) {
         TilePre t;
-        const int y = y_known >= 0 ? y_known : pos / Wp, x = pos - y * Wp;
-        t.y = y;
+        t.b = b;
+        t.q = pos;
+        if (packed) {
+          t.b = pos / HpWp;
+          t.q = pos - t.b * HpWp;
+        }
+        const int y = y_known >= 0 ? y_known : t.q / Wp, x = t.q - y * Wp;
+        t.y = (packed && t.b >= p.batch) ? 0 : y;      // past the last image: a border position (stores nothing)
         t.x = x;
-        const bool interior = (y >= 1) && (y <= p.H) && (x >= 1) && (x <= p.W);
+        const bool interior = (t.y >= 1) && (y <= p.H) && (x >= 1) && (x <= p.W);
         t.rx = (c.res_x != nullptr && interior && (job.epi & 1))
                    ? __ldg(c.res_x + ((int64_t)b * p.H + (y - 1)) * p.W + (x - 1)) : 0.f;
         return t;
@@ -924,7 +947,10 @@ conv_tc_kernel(const TcJob job) {
       auto finalize = [&](const uint32_t (&v)[32], const int n0, const int pos, const TilePre& pre) {
         const int y = pre.y, x = pre.x;
         const bool interior = (y >= 1) && (y <= p.H) && (x >= 1) && (x <= p.W);
-        const bool in_tensor = pos < HpWp;
+        const bool in_tensor = packed ? pre.b < p.batch : pos < HpWp;
+        const int64_t img_off_t =
+            packed ? ((int64_t)pre.b * c.o_img_stride + (int64_t)c.out_plane0 * c.o_plane_stride) * 8 : img_off;
+        const int q = pre.q;                  // position inside the image
         // (half-row tensor: row y of the tensor holds image rows 2y - 1 and 2y of the up-sampled image)
         const int64_t up = (int64_t)(c.upsample == 2 ? y : 2 * y - 1) * Wp2 + (2 * x - 1);
         const float rx = (job.epi & 1) ? pre.rx
@@ -990,14 +1016,14 @@ conv_tc_kernel(const TcJob job) {
             else lw[h] = 0u;
           }
           const uint4 ph = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-          const int64_t plane_off = img_off + (int64_t)(n0 / 8 + g) * out_plane_stride;
+          const int64_t plane_off = img_off_t + (int64_t)(n0 / 8 + g) * out_plane_stride;
           if (dbg & 2) {
             if (ph.x == 0x12345678u && lw[0] == 0x9abcdef0u) p.err[1] = 1;      // keep the values alive
           } else if (!c.upsample) {
             if (in_tensor) {
-              st16(c.out + plane_off + (int64_t)pos * 8, ph);
+              st16(c.out + plane_off + (int64_t)q * 8, ph);
               if constexpr (kSplit)
-                st16(c.out_lo + plane_off + (int64_t)pos * 8, make_uint4(lw[0], lw[1], lw[2], lw[3]));
+                st16(c.out_lo + plane_off + (int64_t)q * 8, make_uint4(lw[0], lw[1], lw[2], lw[3]));
             }
           } else if (interior) {
             uint16_t* o = c.out + plane_off + up * 8;

@@ -287,6 +287,33 @@ def test_row_merged_taps_of_upsampled_inputs(sd_seed0, clip60, monkeypatch):
     eng.close()
 
 
+def test_packed_units_are_bit_identical(sd_seed0, clip60, monkeypatch):
+    """The layers at 16 x 32 and 8 x 16 take their work units from the batch's images as ONE stream of positions (default,
+    TcConv::packed) instead of image by image (SS_TC_PACK=0): same MMAs per output position, so the same bits — in every
+    tensor-core mode, for batch sizes where units straddle one, two and many images, and with nothing written outside
+    the tensors (the last unit runs past the last image)."""
+    from oracle import postproc as pp
+    from softspoken_b200.engine import Engine
+    g = load_golden("model_seed0.npz")
+    padded = torch.from_numpy(pp.pad_audio(clip60)).cuda()
+    for mode in ("f16x3", "bf16", "f16"):
+        eng = Engine(sd_seed0, 0, max_batch=53, mode=mode)
+        for n in (1, 2, 3, 7, 53):
+            mel = eng.features(padded, torch.from_numpy(g["starts"][:n]))
+            monkeypatch.setenv("SS_TC_PACK", "0")
+            plain = eng.classify(mel)
+            acts_plain = [_dump(eng, w, n) for w in (3, 4, 5, 6)]       # conv4, bottleneck, up(encoder_out), up(conv6)
+            monkeypatch.delenv("SS_TC_PACK")
+            got = eng.classify(mel)
+            acts = [_dump(eng, w, n) for w in (3, 4, 5, 6)]
+            eng.check_health()
+            for w, a, b in zip((3, 4, 5, 6), acts_plain, acts):
+                assert torch.equal(a, b), (mode, n, w)
+            assert torch.equal(plain, got), (mode, n)
+        assert eng.check_guards() == 0
+        eng.close()
+
+
 def test_fused_mask_head_close_to_two_kernel_form(sd_seed0, clip60, monkeypatch):
     """conv_flatten folded into conv9_1's epilogue (default) against the separate mask-head kernel reading the stored
     hi/lo activations (SS_TC_FUSE_HEAD=0): same arithmetic up to fp32 summation order and the 2^-22 split rounding."""

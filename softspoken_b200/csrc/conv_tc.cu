@@ -695,15 +695,15 @@ int launch_conv_npg(TcJob job, int B, cudaStream_t st) {
   const int positions = p.H * (p.W + 2) - 2;          // (1,1) .. (H,W) in flattened padded coordinates
   p.units_per_image = rows ? p.H / unit_rows : (positions + G * MT * 128 - 1) / (G * MT * 128);
   p.total_units = p.units_per_image * B;
-  // Packed units (TcConv::packed) for the images of 16 x 32 and below, whose last unit is mostly air: the batch as one
-  // stream of positions.  SS_TC_PACK=0: units per image (A/B runs).
+  // Packed units (TcConv::packed) for the images of 32 x 64 and below (plane-major tensors), whose last unit is partly
+  // or mostly air: the batch as one stream of positions.  SS_TC_PACK=0: units per image (A/B runs).
   p.packed = 0;
   p.batch = B;
   {
     const char* pk = getenv("SS_TC_PACK");
     bool contiguous = true;      // every source plane-major: the stream of padded images is contiguous in each plane
     for (int i = 0; i < p.n_src; ++i) contiguous &= p.src[i].img_stride == (int64_t)(p.H + 2) * (p.W + 2) && !p.src[i].in_up;
-    if (!rows && contiguous && job.n_phase == 1 && p.H * p.W <= 512 && !p.head_w && !p.res_x &&
+    if (!rows && contiguous && job.n_phase == 1 && p.H * p.W <= 2048 && !p.head_w && !p.res_x &&
         (pk == nullptr || atoi(pk) != 0)) {
       const int64_t stream = (int64_t)(B - 1) * (p.H + 2) * (p.W + 2) + positions;
       p.packed = 1;
@@ -1023,6 +1023,8 @@ int tc_res_block(TcState* s, int which, const Tensor& x, int x_plane0, Tensor& o
       q.rows = 1;
       q.pool_out = pool->data;
       q.pool_lo = pool->lo;
+      q.pool_img_stride = pool->img_stride();
+      q.pool_plane_stride = pool->plane_stride();
       if (pooled) *pooled = true;
     }
   }
@@ -1170,10 +1172,10 @@ int tc_build_state(ss_ctx* ctx, Prec prec, TcState* s) {
   T(m4, 64, 128, 256);
   T(p1, 32, 64, 128);
   T(m3, 128, 64, 128);
-  T(p2, 64, 32, 64);
-  T(m2, 192, 32, 64);
-  // the tensors of the layers at 16 x 32 and 8 x 16 are plane-major (Tensor::plane_major): packed work units
+  // the tensors of the layers at 32 x 64 and below are plane-major (Tensor::plane_major): packed work units
 #define TP(t, C, H, W) do { if ((rc = alloc_tensor(ctx, s, &s->t, B, C, H, W, true))) return rc; } while (0)
+  TP(p2, 64, 32, 64);
+  TP(m2, 192, 32, 64);
   TP(p3, 96, 16, 32);
   TP(m1, 256, 16, 32);
   TP(p4, 128, 8, 16);
@@ -1186,13 +1188,13 @@ int tc_build_state(ss_ctx* ctx, Prec prec, TcState* s) {
   T(spec, 32, 128, 256);
   T(t[RB_CONV1], 32, 128, 256);
   T(t[RB_CONV2], 64, 64, 128);
-  T(t[RB_CONV3], 96, 32, 64);
+  TP(t[RB_CONV3], 96, 32, 64);
   TP(t[RB_CONV4], 128, 16, 32);
   TP(t[RB_BOTTLENECK], 128, 8, 16);
   TP(t[RB_ENCODER_OUT], 128, 8, 16);
   TP(t[RB_CONV6], 96, 16, 32);
+  TP(t[RB_CONV7], 64, 32, 64);
 #undef TP
-  T(t[RB_CONV7], 64, 32, 64);
   T(t[RB_CONV8], 32, 64, 128);
   T(t[RB_CONV9], 32, 128, 256);
   T(t[RB_SPEC], 32, 128, 256);

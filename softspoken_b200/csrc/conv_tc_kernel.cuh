@@ -345,6 +345,7 @@ struct TcConv {
   int wres;
   uint16_t* pool_out;
   uint16_t* pool_lo;
+  int64_t pool_img_stride, pool_plane_stride;     // of the pooled tensor, in positions
   int stages;          // smem ring depth (<= kMaxStages)
   int cps;             // K-chunks a stage of a 1x1 source carries (>= 1; see the producer)
   int stage_stride;    // bytes per smem ring slot (>= the 3x3 stage; larger when that buys more 1x1 chunks per stage)
@@ -1096,8 +1097,8 @@ conv_tc_kernel(const TcJob job) {
         }
         const float* resw_p = bias_s + 2 * N + phase * N;
         const int Wq = (p.W >> 1) + 2, Hq = (p.H >> 1) + 2;
-        const int64_t pool_plane_stride = (int64_t)Hq * Wq * 8;
-        const int64_t pool_off = (int64_t)b * (N / 8) * pool_plane_stride + ((int64_t)(lu + 1) * Wq + ((xc >> 1) + 1)) * 8;
+        const int64_t pool_plane_stride = c.pool_plane_stride * 8;
+        const int64_t pool_off = ((int64_t)b * c.pool_img_stride + (int64_t)(lu + 1) * Wq + ((xc >> 1) + 1)) * 8;
         ok = mbar_wait_t(accf0 + 8 * buf, f_parity, p.err, 3, w_accf);
         if (!ok) break;
         tc_fence_after();

@@ -288,7 +288,7 @@ def test_row_merged_taps_of_upsampled_inputs(sd_seed0, clip60, monkeypatch):
 
 
 def test_packed_units_are_bit_identical(sd_seed0, clip60, monkeypatch):
-    """The layers at 16 x 32 and 8 x 16 take their work units from the batch's images as ONE stream of positions (default,
+    """The layers at 32 x 64, 16 x 32 and 8 x 16 take their work units from the batch's images as ONE stream of positions (default,
     TcConv::packed) instead of image by image (SS_TC_PACK=0): same MMAs per output position, so the same bits — in every
     tensor-core mode, for batch sizes where units straddle one, two and many images, and with nothing written outside
     the tensors (the last unit runs past the last image)."""
@@ -302,12 +302,12 @@ def test_packed_units_are_bit_identical(sd_seed0, clip60, monkeypatch):
             mel = eng.features(padded, torch.from_numpy(g["starts"][:n]))
             monkeypatch.setenv("SS_TC_PACK", "0")
             plain = eng.classify(mel)
-            acts_plain = [_dump(eng, w, n) for w in (3, 4, 5, 6)]       # conv4, bottleneck, up(encoder_out), up(conv6)
+            acts_plain = [_dump(eng, w, n) for w in (2, 3, 4, 5, 6, 7, 13)]   # conv3, conv4, bottleneck, up(encoder_out), up(conv6), up(conv7), pool(conv2)
             monkeypatch.delenv("SS_TC_PACK")
             got = eng.classify(mel)
-            acts = [_dump(eng, w, n) for w in (3, 4, 5, 6)]
+            acts = [_dump(eng, w, n) for w in (2, 3, 4, 5, 6, 7, 13)]
             eng.check_health()
-            for w, a, b in zip((3, 4, 5, 6), acts_plain, acts):
+            for w, a, b in zip((2, 3, 4, 5, 6, 7, 13), acts_plain, acts):
                 assert torch.equal(a, b), (mode, n, w)
             assert torch.equal(plain, got), (mode, n)
         assert eng.check_guards() == 0

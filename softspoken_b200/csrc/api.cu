@@ -536,6 +536,11 @@ int ss_ctx_create(int device, const void* blob, size_t blob_bytes, int max_batch
                              reinterpret_cast<const int*>(v.payload + v.entries.at("mel_offs").off),
                              v.payload + v.entries.at("mel_taps").off));
   }
+  {
+    // SS_K1_PACKED=0 keeps K1's scalar phase 1 (A/B runs and the packed-vs-scalar bit comparison of the tests)
+    const char* pk = getenv("SS_K1_PACKED");
+    ctx->fe.packed = (pk == nullptr || atoi(pk) != 0) ? 1 : 0;
+  }
   FAIL_IF(upload_tables(ctx, v));
   for (int i = 0; i < RB_COUNT; ++i) {
     const RbSpec& s = kResBlocks[i];

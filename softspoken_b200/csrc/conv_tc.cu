@@ -34,6 +34,8 @@
 
 #include <vector>
 
+#include <type_traits>
+
 #include "conv_tc_kernel.cuh"
 #include "ss_common.cuh"
 
@@ -71,9 +73,10 @@ __device__ __forceinline__ void load8(const uint16_t* __restrict__ hi, const uin
   }
 }
 
+// Returns the packed maximum of the four hi words (range_track; meaningful for non-negative values in the fp16 modes).
 template <Prec P>
-__device__ __forceinline__ void store8(uint16_t* __restrict__ hi, uint16_t* __restrict__ lo, int64_t pix,
-                                       const float (&f)[8]) {
+__device__ __forceinline__ uint32_t store8(uint16_t* __restrict__ hi, uint16_t* __restrict__ lo, int64_t pix,
+                                           const float (&f)[8]) {
   uint32_t hw[4], lw[4];
 #pragma unroll
   for (int h = 0; h < 4; ++h) {
@@ -82,6 +85,8 @@ __device__ __forceinline__ void store8(uint16_t* __restrict__ hi, uint16_t* __re
   }
   reinterpret_cast<uint4*>(hi)[pix] = make_uint4(hw[0], hw[1], hw[2], hw[3]);
   if constexpr (PrecTraits<P>::split) reinterpret_cast<uint4*>(lo)[pix] = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+  if constexpr (PrecTraits<P>::fmt == 0) return range_track(range_track(hw[0], hw[1]), range_track(hw[2], hw[3]));
+  else return 0u;
 }
 
 // ------------------------------------------------------------------------------------------ small kernels
@@ -127,13 +132,15 @@ conv1_direct(const float* __restrict__ mel, const float* __restrict__ w /* [9][3
              uint16_t* __restrict__ out, uint16_t* __restrict__ out_lo, int* __restrict__ err) {
   const int x = threadIdx.x, y0 = blockIdx.x * kC1Rows, pl = blockIdx.y;
   const int64_t b = blockIdx.z;
-  float wr[9][8], br[8];
+  // channel pairs (k, k + 1) as the halves of packed registers: nine FFMA2 per two output values (the kernel sat at
+  // 60 % of the issue rate and 70 % of HBM with scalar FFMAs — 16 instructions per 4 bytes written)
+  float2 wr[9][4], br[4];
 #pragma unroll
   for (int t = 0; t < 9; ++t)
 #pragma unroll
-    for (int k = 0; k < 8; ++k) wr[t][k] = __ldg(w + t * 32 + pl * 8 + k);
+    for (int k = 0; k < 4; ++k) wr[t][k] = __ldg(reinterpret_cast<const float2*>(w + t * 32 + pl * 8) + k);
 #pragma unroll
-  for (int k = 0; k < 8; ++k) br[k] = __ldg(bias + pl * 8 + k);
+  for (int k = 0; k < 4; ++k) br[k] = __ldg(reinterpret_cast<const float2*>(bias + pl * 8) + k);
   const float* img = mel + b * (int64_t)kMels * kFrames;
   const int Wp = kFrames + 2, Hp = kMels + 2;
   auto row3 = [&](int yy, float (&r)[3]) {       // mel[yy][x-1 .. x+1], zero outside the image
@@ -145,22 +152,23 @@ conv1_direct(const float* __restrict__ mel, const float* __restrict__ w /* [9][3
   float m[3][3];
   row3(y0 - 1, m[0]);
   row3(y0, m[1]);
-  bool over = false;
+  uint32_t hmax = 0u;
 #pragma unroll
   for (int r = 0; r < kC1Rows; ++r) {
     row3(y0 + r + 1, m[(r + 2) % 3]);
     float f[8];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      float acc = 0.f;
+    for (int k = 0; k < 4; ++k) {
+      float2 acc = make_float2(0.f, 0.f);      // each half: fma(m, w, acc) tap by tap from zero, as the scalar loop did
 #pragma unroll
-      for (int t = 0; t < 9; ++t) acc = fmaf(m[(r + t / 3) % 3][t % 3], wr[t][k], acc);
-      f[k] = fmaxf(acc + br[k], 0.f);
-      if constexpr (PrecTraits<P>::fmt == 0) over |= f[k] > 65504.f;
+      for (int t = 0; t < 9; ++t) acc = fma2(bc2(m[(r + t / 3) % 3][t % 3]), wr[t][k], acc);
+      acc = add2(acc, br[k]);
+      f[2 * k] = fmaxf(acc.x, 0.f);
+      f[2 * k + 1] = fmaxf(acc.y, 0.f);
     }
-    store8<P>(out, out_lo, ((b * 4 + pl) * Hp + (y0 + r + 1)) * (int64_t)Wp + (x + 1), f);
+    hmax = range_track(hmax, store8<P>(out, out_lo, ((b * 4 + pl) * Hp + (y0 + r + 1)) * (int64_t)Wp + (x + 1), f));
   }
-  if (over) err[2] = 1;       // fp16 operand modes: the activation was saturated (SS_E_RANGE)
+  if (PrecTraits<P>::fmt == 0 && range_hit(hmax)) err[2] = 1;       // fp16 operand modes: the activation was saturated (SS_E_RANGE)
 }
 
 // MaxPool2d(2) on planar tensors: in planes [plane0, plane0+planes) of a tensor with in_planes_total planes at
@@ -683,15 +691,6 @@ int launch_conv_npg(TcJob job, int B, cudaStream_t st) {
   p.debug = debug;
   const size_t smem = wres + (size_t)stages * stride + tail;
   constexpr bool kCanSub = PrecTraits<P>::split && G == 1;
-  static bool configured = false;
-  if (!configured) {
-    SS_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<N, P, Dual, G, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)kSmemBudget));
-    if constexpr (kCanSub)
-      SS_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<N, P, Dual, G, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)kSmemBudget));
-    configured = true;
-  }
   const int positions = p.H * (p.W + 2) - 2;          // (1,1) .. (H,W) in flattened padded coordinates
   p.units_per_image = rows ? p.H / unit_rows : (positions + G * MT * 128 - 1) / (G * MT * 128);
   p.total_units = p.units_per_image * B;
@@ -799,27 +798,76 @@ int launch_conv_npg(TcJob job, int B, cudaStream_t st) {
     for (int i = 0; i < job.c[0].n_src; ++i)
       if (job.c[0].src[i].ring < 0) job.c[0].src[i].ring = 0;
   }
+  // Which epilogue the launch needs picks the instantiation (conv_tc_kernel's Epi): 1 the folded MaxPool, 2 the general
+  // one with the fused mask-head partials, 0 the general one alone.
+  bool any_head = false;
+  for (int ph = 0; ph < job.n_phase; ++ph) any_head |= job.c[ph].head_w != nullptr;
+  SS_REQUIRE(!any_head || N == 32, SS_E_ARG, "the fused mask head belongs to the 32-channel launch");
+  auto launch = [&](auto sub_c, auto rows_c, auto epi_c) -> int {
+    constexpr bool kS = decltype(sub_c)::value;
+    constexpr int kR = decltype(rows_c)::value, kE = decltype(epi_c)::value;
+    auto* kernel = conv_tc_kernel<N, P, Dual, G, kS, kR, kE>;
+    static bool configured_k = false;      // one flag per instantiation of this call operator
+    if (!configured_k) {
+      SS_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)(kR ? kSmemBudgetMax : kSmemBudget)));
+      configured_k = true;
+    }
+    kernel<<<grid, kTcThreads, smem, st>>>(job);
+    return SS_OK;
+  };
+  using std::integral_constant;
+  using False = integral_constant<bool, false>;
+  using True = integral_constant<bool, true>;
+  int rc = SS_OK;
   if (rows) {
     SS_REQUIRE(!any_sub, SS_E_ARG, "row-aligned conv launch: sub-accumulation is not available in this geometry");
     if constexpr (kCanRows) {
-      static bool configured_rows = false;
-      if (!configured_rows) {
-        SS_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<N, P, Dual, G, false, 1>,
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudgetMax));
-        if constexpr (MT % 4 == 0)
-          SS_CUDA_CHECK(cudaFuncSetAttribute(conv_tc_kernel<N, P, Dual, G, false, 2>,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudgetMax));
-        configured_rows = true;
+      // (tpr = tiles per image row; the folded pool needs units of two rows: MT / tpr == 2)
+      if (tpr == 1) {
+        if constexpr (MT == 2) {
+          if (p.pool_out) rc = launch(False{}, integral_constant<int, 1>{}, integral_constant<int, 1>{});
+          else rc = launch(False{}, integral_constant<int, 1>{}, integral_constant<int, 0>{});
+        } else if constexpr (N == 32) {
+          SS_REQUIRE(!p.pool_out, SS_E_ARG, "folded pool: the unit is not a pair of rows");
+          if (any_head) rc = launch(False{}, integral_constant<int, 1>{}, integral_constant<int, 2>{});
+          else rc = launch(False{}, integral_constant<int, 1>{}, integral_constant<int, 0>{});
+        } else {
+          SS_REQUIRE(!p.pool_out, SS_E_ARG, "folded pool: the unit is not a pair of rows");
+          rc = launch(False{}, integral_constant<int, 1>{}, integral_constant<int, 0>{});
+        }
+      } else if constexpr (MT % 4 == 0) {
+        if constexpr (MT == 4) {
+          if (p.pool_out) rc = launch(False{}, integral_constant<int, 2>{}, integral_constant<int, 1>{});
+          else if (N == 32 && any_head) {
+            if constexpr (N == 32) rc = launch(False{}, integral_constant<int, 2>{}, integral_constant<int, 2>{});
+          } else rc = launch(False{}, integral_constant<int, 2>{}, integral_constant<int, 0>{});
+        } else {
+          SS_REQUIRE(!p.pool_out && !any_head, SS_E_ARG, "row-aligned launch: no such epilogue in this geometry");
+          rc = launch(False{}, integral_constant<int, 2>{}, integral_constant<int, 0>{});
+        }
       }
-      if (tpr == 1) conv_tc_kernel<N, P, Dual, G, false, 1><<<grid, kTcThreads, smem, st>>>(job);
-      else if constexpr (MT % 4 == 0) conv_tc_kernel<N, P, Dual, G, false, 2><<<grid, kTcThreads, smem, st>>>(job);
     }
-  } else if constexpr (kCanSub) {
-    if (any_sub) conv_tc_kernel<N, P, Dual, G, true><<<grid, kTcThreads, smem, st>>>(job);
-    else conv_tc_kernel<N, P, Dual, G, false><<<grid, kTcThreads, smem, st>>>(job);
   } else {
-    conv_tc_kernel<N, P, Dual, G, false><<<grid, kTcThreads, smem, st>>>(job);
+    SS_REQUIRE(!p.pool_out, SS_E_ARG, "folded pool without row-aligned units");
+    if constexpr (N == 32) {
+      if constexpr (kCanSub) {
+        if (any_sub) rc = any_head ? launch(True{}, integral_constant<int, 0>{}, integral_constant<int, 2>{})
+                                   : launch(True{}, integral_constant<int, 0>{}, integral_constant<int, 0>{});
+        else rc = any_head ? launch(False{}, integral_constant<int, 0>{}, integral_constant<int, 2>{})
+                           : launch(False{}, integral_constant<int, 0>{}, integral_constant<int, 0>{});
+      } else {
+        rc = any_head ? launch(False{}, integral_constant<int, 0>{}, integral_constant<int, 2>{})
+                      : launch(False{}, integral_constant<int, 0>{}, integral_constant<int, 0>{});
+      }
+    } else if constexpr (kCanSub) {
+      rc = any_sub ? launch(True{}, integral_constant<int, 0>{}, integral_constant<int, 0>{})
+                   : launch(False{}, integral_constant<int, 0>{}, integral_constant<int, 0>{});
+    } else {
+      rc = launch(False{}, integral_constant<int, 0>{}, integral_constant<int, 0>{});
+    }
   }
+  if (rc) return rc;
   SS_CUDA_CHECK(cudaGetLastError());
   count_launch();
   return SS_OK;

@@ -72,20 +72,29 @@ template <> struct PrecTraits<Prec::F16> { static constexpr bool split = false; 
 template <> struct PrecTraits<Prec::F16x3> { static constexpr bool split = true; static constexpr uint32_t fmt = 0; };
 
 // two floats -> one packed pair of 16-bit operands (and the packed residuals for the split format)
+// fp16 saturates instead of overflowing to inf (activations beyond +-65504 are outside what this mode carries): the
+// conversion itself clamps (cvt.rn.satfinite.f16x2.f32 -> F2FP.SATFINITE, no FMNMX pair per value), and a kernel
+// detects that it happened from the packed result (range_track / range_hit below).
+__device__ __forceinline__ uint32_t cvt_f16x2_sat(float a, float b) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));      // a -> low half
+  return r;
+}
 template <Prec P>
 __device__ __forceinline__ uint32_t pack_hi(float a, float b) {
   if constexpr (PrecTraits<P>::fmt == 1) {
     __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<uint32_t*>(&h);
   } else {
-    // fp16 saturates instead of overflowing to inf (activations beyond +-65504 are outside what this mode carries)
-    __half2 h = __floats2half2_rn(fminf(fmaxf(a, -65504.f), 65504.f), fminf(fmaxf(b, -65504.f), 65504.f));
-    return *reinterpret_cast<uint32_t*>(&h);
+    return cvt_f16x2_sat(a, b);
   }
 }
-// same without the saturation (the caller has clamped already)
+// (one name was the saturating form, the other not, while the clamp was a pair of FMNMX in the caller)
 template <Prec P>
-__device__ __forceinline__ uint32_t pack_rn(float a, float b) {
+__device__ __forceinline__ uint32_t pack_rn(float a, float b) { return pack_hi<P>(a, b); }
+// the plain conversion, for callers that clamp themselves (the folded-pool epilogue, see there)
+template <Prec P>
+__device__ __forceinline__ uint32_t pack_plain(float a, float b) {
   if constexpr (PrecTraits<P>::fmt == 1) {
     __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<uint32_t*>(&h);
@@ -94,9 +103,19 @@ __device__ __forceinline__ uint32_t pack_rn(float a, float b) {
     return *reinterpret_cast<uint32_t*>(&h);
   }
 }
+// Range check of the fp16 operand modes on NON-NEGATIVE packed pairs (everything here is stored after a ReLU): a
+// running packed maximum (one HMNMX2 per pair of values), tested once per unit.  An activation of 65,488 or more
+// rounds or saturates to the fp16 maximum 0x7BFF and counts as out of range (SS_E_RANGE).
+__device__ __forceinline__ uint32_t range_track(uint32_t running, uint32_t packed) {
+  const __half2 m = __hmax2(*reinterpret_cast<const __half2*>(&running), *reinterpret_cast<const __half2*>(&packed));
+  return *reinterpret_cast<const uint32_t*>(&m);
+}
+__device__ __forceinline__ bool range_hit(uint32_t running) {
+  return (running & 0x7fffu) >= 0x7bffu || ((running >> 16) & 0x7fffu) >= 0x7bffu;
+}
 __device__ __forceinline__ uint32_t pack_lo_f16(float a, float b, uint32_t hi) {
-  const float2 h = __half22float2(*reinterpret_cast<const __half2*>(&hi));
-  __half2 l = __floats2half2_rn(a - h.x, b - h.y);
+  const float2 d = sub2(make_float2(a, b), __half22float2(*reinterpret_cast<const __half2*>(&hi)));   // one FADD2
+  __half2 l = __floats2half2_rn(d.x, d.y);
   return *reinterpret_cast<uint32_t*>(&l);
 }
 template <Prec P>
@@ -527,7 +546,12 @@ __device__ __forceinline__ void issue_group_dup(uint32_t d0, uint32_t a_lo0, uin
 
 // Sub: the split-K sub-accumulation path (TcConv::n_sub > 1) is compiled in — a separate instantiation, because
 // keeping a unit's sums in registers across buffer turns costs the plain single-chain launches 7 % (measured).
-template <int N, Prec P, bool Dual, int G, bool Sub = false, int Rows = 0>
+// Epi: which epilogue the instantiation carries — 0 the general one (`finalize`), 1 the folded-MaxPool epilogue of
+// row-aligned units and nothing else, 2 the general one with the fused mask-head partials (N = 32).  The three used to
+// share one kernel; its code (4,300 instructions in the N = 32 row-aligned instantiation) is what the MMA-issuing warps
+// compete with for the instruction cache, and every change to one epilogue moved the time of launches that never run
+// it by +-10 % (profiles/r2_tuning_experiments.txt, section 17).
+template <int N, Prec P, bool Dual, int G, bool Sub = false, int Rows = 0, int Epi = 0>
 __global__ void __launch_bounds__(kTcThreads, 1)
 conv_tc_kernel(const TcJob job) {
   extern __shared__ __align__(128) unsigned char smem[];
@@ -917,7 +941,8 @@ conv_tc_kernel(const TcJob job) {
       const int b = u / p.units_per_image;
       const int bo = c.out_ring ? b % c.out_ring : b;
       const int64_t img_off = ((int64_t)bo * c.o_img_stride + (int64_t)c.out_plane0 * c.o_plane_stride) * 8;
-      float vmax = 0.f;
+      uint32_t hmax = 0u;          // fp16 operand modes: running packed maximum of the stored values (range_track)
+      float vmax = 0.f;            // ... and the float maximum of the folded-pool epilogue
 
       // Everything after the accumulators of one tile's 32-column block [n0, n0 + 32) are final: undo the weight
       // scale, bias, scalar residual, ReLU, (mask-head partials,) 16-bit pack, stores.
@@ -959,25 +984,29 @@ conv_tc_kernel(const TcJob job) {
         const float* resw_p = bias_s + 2 * N + phase * N;
         const float* bias_t = interior ? bias_p : zero_s;
         const float scale_t = interior ? inv_scale : 0.f;
-        if constexpr (N == 32) {
+        if constexpr (N == 32 && Epi == 2) {
           if (c.head_w != nullptr) {
             // fused conv_flatten partials: this position's 32 activations . head_w[y - 1][:, 0..3]
             // (the weights come straight from L2, channel by channel: staging the warp's rows in shared memory or
             // broadcasting them with shuffles measured 16 % / 26 % slower on this launch, profiles/r2_tuning.txt)
             if (interior) {
               const float4* wrow = reinterpret_cast<const float4*>(c.head_w) + (y - 1) * 32;
-              float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+              // (packed pairs, ss_common.cuh: the same fmas in the same order, two per instruction — this loop is
+              // 192 of the launch's ~350 epilogue instructions per position)
+              float2 acc_xy = make_float2(0.f, 0.f), acc_zw = make_float2(0.f, 0.f);
 #pragma unroll
-              for (int i = 0; i < 32; ++i) {
-                float f = fmaf(__uint_as_float(v[i]), inv_scale, bias_p[i]);
-                f = fmaxf(f, 0.f);
-                const float4 w = __ldg(wrow + i);
-                acc.x = fmaf(f, w.x, acc.x);
-                acc.y = fmaf(f, w.y, acc.y);
-                acc.z = fmaf(f, w.z, acc.z);
-                acc.w = fmaf(f, w.w, acc.w);
+              for (int i = 0; i < 32; i += 2) {
+                const float2 f2 = fma2(make_float2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])), bc2(inv_scale),
+                                       *reinterpret_cast<const float2*>(bias_p + i));
+                const float fa = fmaxf(f2.x, 0.f), fb = fmaxf(f2.y, 0.f);
+                const float4 wa = __ldg(wrow + i), wb = __ldg(wrow + i + 1);
+                acc_xy = fma2(bc2(fa), make_float2(wa.x, wa.y), acc_xy);
+                acc_zw = fma2(bc2(fa), make_float2(wa.z, wa.w), acc_zw);
+                acc_xy = fma2(bc2(fb), make_float2(wb.x, wb.y), acc_xy);
+                acc_zw = fma2(bc2(fb), make_float2(wb.z, wb.w), acc_zw);
               }
-              reinterpret_cast<float4*>(c.head_out)[((int64_t)b * p.H + (y - 1)) * p.W + (x - 1)] = acc;
+              reinterpret_cast<float4*>(c.head_out)[((int64_t)b * p.H + (y - 1)) * p.W + (x - 1)] =
+                  make_float4(acc_xy.x, acc_xy.y, acc_zw.x, acc_zw.y);
             }
             if (c.out == nullptr) return;      // nobody reads the activations themselves (no spec head requested)
           }
@@ -999,20 +1028,13 @@ conv_tc_kernel(const TcJob job) {
           }
 #pragma unroll
           for (int h = 0; h < 4; ++h) {
-            float f0 = fmaf(__uint_as_float(v[g * 8 + 2 * h]), scale_t, bb[2 * h]);
-            float f1 = fmaf(__uint_as_float(v[g * 8 + 2 * h + 1]), scale_t, bb[2 * h + 1]);
-            if (c.res_x != nullptr) {
-              f0 = fmaf(rx, rw[2 * h], f0);
-              f1 = fmaf(rx, rw[2 * h + 1], f1);
-            }
-            f0 = fmaxf(f0, 0.f);
-            f1 = fmaxf(f1, 0.f);
-            if constexpr (PrecTraits<P>::fmt == 0) {
-              vmax = fmaxf(vmax, fmaxf(f0, f1));
-              f0 = fminf(f0, 65504.f);
-              f1 = fminf(f1, 65504.f);
-            }
+            float2 f01 = fma2(make_float2(__uint_as_float(v[g * 8 + 2 * h]), __uint_as_float(v[g * 8 + 2 * h + 1])),
+                              bc2(scale_t), make_float2(bb[2 * h], bb[2 * h + 1]));
+            if (c.res_x != nullptr) f01 = fma2(bc2(rx), make_float2(rw[2 * h], rw[2 * h + 1]), f01);
+            const float f0 = fmaxf(f01.x, 0.f);
+            const float f1 = fmaxf(f01.y, 0.f);
             hw[h] = pack_rn<P>(f0, f1);
+            if constexpr (PrecTraits<P>::fmt == 0) hmax = range_track(hmax, hw[h]);
             if constexpr (kSplit) lw[h] = pack_lo_f16(f0, f1, hw[h]);
             else lw[h] = 0u;
           }
@@ -1066,15 +1088,19 @@ conv_tc_kernel(const TcJob job) {
           tc_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(buf * kAccCols + mt * TS + N + n0), cv);
           tc_wait_ld();
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) + __uint_as_float(cv[i]));
+          for (int i = 0; i < 32; i += 2) {
+            const float2 sum = add2(make_float2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])),
+                                    make_float2(__uint_as_float(cv[i]), __uint_as_float(cv[i + 1])));
+            v[i] = __float_as_uint(sum.x);
+            v[i + 1] = __float_as_uint(sum.y);
+          }
         } else {
           tc_wait_ld();
         }
       };
 
-      bool unit_done = false;      // the folded-pool epilogue below took the unit
-      if constexpr (Rows != 0 && kUnitRows == 2) if (c.pool_out != nullptr) {
-        unit_done = true;
+      if constexpr (Epi == 1) {
+        static_assert(Epi != 1 || (Rows != 0 && kUnitRows == 2), "the folded pool belongs to row-aligned units of two rows");
         // Row-aligned unit = image rows (2 lu, 2 lu + 1), 0-based.  This warp owns the vertical tile pair (A above B)
         // of its 32 columns: W = 256 (two tiles per row): column half `tile_par`, all N = 32 channels; W = 128 (one tile
         // per row): the whole row, channel block `tile_par` of the N = 64.  Every position is interior.
@@ -1127,27 +1153,28 @@ conv_tc_kernel(const TcJob job) {
 #pragma unroll
             for (int h = 0; h < 4; ++h) {
               const int i0 = g * 8 + 2 * h, i1 = i0 + 1;
-              float a0 = fmaf(__uint_as_float(am[i0]) + __uint_as_float(ac[i0]), inv_scale, bb[2 * h]);
-              float a1 = fmaf(__uint_as_float(am[i1]) + __uint_as_float(ac[i1]), inv_scale, bb[2 * h + 1]);
-              float q0v = fmaf(__uint_as_float(bm[i0]) + __uint_as_float(bc[i0]), inv_scale, bb[2 * h]);
-              float q1v = fmaf(__uint_as_float(bm[i1]) + __uint_as_float(bc[i1]), inv_scale, bb[2 * h + 1]);
+              const float2 bb2 = make_float2(bb[2 * h], bb[2 * h + 1]), rw2 = make_float2(rw[2 * h], rw[2 * h + 1]);
+              float2 a01 = fma2(add2(make_float2(__uint_as_float(am[i0]), __uint_as_float(am[i1])),
+                                     make_float2(__uint_as_float(ac[i0]), __uint_as_float(ac[i1]))), bc2(inv_scale), bb2);
+              float2 q01 = fma2(add2(make_float2(__uint_as_float(bm[i0]), __uint_as_float(bm[i1])),
+                                     make_float2(__uint_as_float(bc[i0]), __uint_as_float(bc[i1]))), bc2(inv_scale), bb2);
               if (c.res_x != nullptr) {
-                a0 = fmaf(rxA, rw[2 * h], a0);
-                a1 = fmaf(rxA, rw[2 * h + 1], a1);
-                q0v = fmaf(rxB, rw[2 * h], q0v);
-                q1v = fmaf(rxB, rw[2 * h + 1], q1v);
+                a01 = fma2(bc2(rxA), rw2, a01);
+                q01 = fma2(bc2(rxB), rw2, q01);
               }
-              a0 = fmaxf(a0, 0.f); a1 = fmaxf(a1, 0.f); q0v = fmaxf(q0v, 0.f); q1v = fmaxf(q1v, 0.f);
+              float a0 = fmaxf(a01.x, 0.f), a1 = fmaxf(a01.y, 0.f), q0v = fmaxf(q01.x, 0.f), q1v = fmaxf(q01.y, 0.f);
               // the 2 x 2 window: this thread's two rows, then the neighbouring column (lanes 2k, 2k + 1)
               float m0 = fmaxf(a0, q0v), m1 = fmaxf(a1, q1v);
               m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1));
               m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1));
+              // (this path keeps the explicit clamp and a float running maximum: with the saturating conversion and
+              // the packed maximum of `finalize` conv1_1.c2 measured 14 % SLOWER, profiles/r2_tuning_experiments.txt 17)
               vmax = fmaxf(vmax, fmaxf(m0, m1));
               a0 = fminf(a0, 65504.f); a1 = fminf(a1, 65504.f); q0v = fminf(q0v, 65504.f); q1v = fminf(q1v, 65504.f);
               m0 = fminf(m0, 65504.f); m1 = fminf(m1, 65504.f);
-              ah[h] = pack_rn<P>(a0, a1); al[h] = pack_lo_f16(a0, a1, ah[h]);
-              bh[h] = pack_rn<P>(q0v, q1v); bl[h] = pack_lo_f16(q0v, q1v, bh[h]);
-              ph[h] = pack_rn<P>(m0, m1); pl[h] = pack_lo_f16(m0, m1, ph[h]);
+              ah[h] = pack_plain<P>(a0, a1); al[h] = pack_lo_f16(a0, a1, ah[h]);
+              bh[h] = pack_plain<P>(q0v, q1v); bl[h] = pack_lo_f16(q0v, q1v, bh[h]);
+              ph[h] = pack_plain<P>(m0, m1); pl[h] = pack_lo_f16(m0, m1, ph[h]);
             }
             const int64_t plane_off = img_off + (int64_t)(ch / 8) * out_plane_stride;
             st16(c.out + plane_off + posA * 8, make_uint4(ah[0], ah[1], ah[2], ah[3]));
@@ -1210,7 +1237,7 @@ conv_tc_kernel(const TcJob job) {
             finalize(v, n0, pos, pre);
           }
         }
-      } else if (!unit_done) {
+      } else if constexpr (Epi != 1) {
        for (int g = 0; g < G && ok; ++g, ++kk) {
         const int buf = (G == 1) ? (kk & 1) : g;
         const uint32_t f_parity = (G == 1) ? (((uint32_t)kk >> 1) & 1u) : ((uint32_t)k & 1u);
@@ -1250,7 +1277,7 @@ conv_tc_kernel(const TcJob job) {
         if (lane == 0) mbar_arrive(acce0 + 8 * buf);
        }
       }
-      if constexpr (PrecTraits<P>::fmt == 0) out_of_range |= (vmax > 65504.f);
+      if constexpr (PrecTraits<P>::fmt == 0) out_of_range |= range_hit(hmax) || vmax > 65504.f;
       if (n_phase == 2 && phase == 0) {
         // publish this warp's share of the unit to the c[1] producers of other CTAs: the lanes' stores are ordered
         // before lane 0's release by the warp barrier, and the release-reduction makes them visible at gpu scope

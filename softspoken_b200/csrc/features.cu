@@ -32,6 +32,7 @@ constexpr int kBandsPerWarp = kMels / kWarps;
 constexpr int kEx = 8 * 72;     // exchange A: [k1][t] with row stride 72; exchange B: [k2a*8+k1][u] with row stride 9
 constexpr int kEvenBins = 372;  // even bins 2m, m <= 371  (k <= 742)
 constexpr int kOddQ = 186;      // bins 4q+1 and 4q+3, q <= 185 (k <= 743)
+constexpr int kEvenPairs = 2 * 6 * 32;   // packed path: 6 x 32 pairs of W1024^m real parts, then of imaginary parts
 constexpr int kRows = 2 * kOddQ + kEvenBins;   // power rows: [4q+1 | 4q+3 | 2m]
 constexpr int kRowStride = kFramesPerTile + 1;
 constexpr int kMaxTaps = 2048;
@@ -46,7 +47,7 @@ struct Smem {
   float2 tw1[7][64];            // W512^(t k1), k1 = 1..7
   float2 tw2[7][64];            // W64^(u k2a), k2a = 1..7, u = t & 7
   float tw_a_re[512], tw_a_im[512], win[512];
-  float2 tw1024[kEvenBins];
+  float2 tw1024[kEvenPairs];      // scalar path: [m]; packed path: [x pairs | y pairs], see the prologue
   float4 rec[kMaxRec];           // two-band walk (FrontEnd::mel_rec) with .z = row offset of the bin in the power tile
   int rec_begin[kWarps + 1];
   float P[kRows * kRowStride];  // power spectrum tile [row(bin)][frame]
@@ -113,6 +114,124 @@ __device__ __forceinline__ void cmul(float& r, float& i, float2 w) {
   i = ni;
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Packed pairs.  sm_100 issues two fp32 operations per instruction on a 64-bit register pair (add / sub / mul /
+// fma.rn.f32x2 -> SASS FADD2 / FMUL2 / FFMA2), each half rounded exactly as the scalar instruction would.  K1 is bound
+// by instruction issue, and a lane's two columns of a transform (t = lane and t = lane + 32) go through the same
+// instruction stream on independent data: the packed path keeps them as the two halves of a pair (.x: column lane,
+// .y: column lane + 32), which halves the floating-point instructions of phase 1.  Every operation below is written
+// with the contraction the compiler chose for the scalar path (products fused into the sum or difference that
+// consumes them, first operand fused), so the two paths are meant to agree bit for bit; tests compare them.
+
+// The second half of dft8: from the four even-half and four odd-half sums to the eight outputs.
+__device__ __forceinline__ void dft8p_finish(float2 (&re)[8], float2 (&im)[8], float2 e0r, float2 e0i, float2 e1r, float2 e1i,
+                                             float2 e2r, float2 e2i, float2 e3r, float2 e3i, float2 o0r, float2 o0i, float2 o1r,
+                                             float2 o1i, float2 o2r, float2 o2i, float2 o3r, float2 o3i) {
+  const float2 c = bc2(0.70710678118654752440f), nc = bc2(-0.70710678118654752440f);
+  const float2 a1 = add2(o1r, o1i), b1 = sub2(o1i, o1r);      // p1 = (a1 + i b1) c
+  const float2 a3 = sub2(o3i, o3r), b3 = add2(o3r, o3i);      // p3 = (a3 - i b3) c
+  re[0] = add2(e0r, o0r); im[0] = add2(e0i, o0i);
+  re[4] = sub2(e0r, o0r); im[4] = sub2(e0i, o0i);
+  re[1] = fma2(a1, c, e1r);  im[1] = fma2(b1, c, e1i);
+  re[5] = fma2(a1, nc, e1r); im[5] = fma2(b1, nc, e1i);
+  re[2] = add2(e2r, o2i); im[2] = sub2(e2i, o2r);
+  re[6] = sub2(e2r, o2i); im[6] = add2(e2i, o2r);
+  re[3] = fma2(a3, c, e3r);  im[3] = fma2(b3, nc, e3i);
+  re[7] = fma2(a3, nc, e3r); im[7] = fma2(b3, c, e3i);
+}
+
+// dft8<false> on pairs (inputs already in registers)
+__device__ __forceinline__ void dft8p(float2 (&re)[8], float2 (&im)[8]) {
+  const float2 s0r = add2(re[0], re[4]), s0i = add2(im[0], im[4]);
+  const float2 s1r = sub2(re[0], re[4]), s1i = sub2(im[0], im[4]);
+  const float2 s2r = add2(re[2], re[6]), s2i = add2(im[2], im[6]);
+  const float2 s3r = sub2(re[2], re[6]), s3i = sub2(im[2], im[6]);
+  const float2 t0r = add2(re[1], re[5]), t0i = add2(im[1], im[5]);
+  const float2 t1r = sub2(re[1], re[5]), t1i = sub2(im[1], im[5]);
+  const float2 t2r = add2(re[3], re[7]), t2i = add2(im[3], im[7]);
+  const float2 t3r = sub2(re[3], re[7]), t3i = sub2(im[3], im[7]);
+  dft8p_finish(re, im, add2(s0r, s2r), add2(s0i, s2i), add2(s1r, s3i), sub2(s1i, s3r), sub2(s0r, s2r), sub2(s0i, s2i),
+               sub2(s1r, s3i), add2(s1i, s3r), add2(t0r, t2r), add2(t0i, t2i), add2(t1r, t3i), sub2(t1i, t3r),
+               sub2(t0r, t2r), sub2(t0i, t2i), sub2(t1r, t3i), add2(t1i, t3r));
+}
+
+// dft8<false> of v[j] = x[j] (wr[j] + i wi[j]): the products of j < 4 are fused into the first sums and differences
+// (fma(x0, w0, x4 w4), fma(x0, w0, -(x4 w4))), those of j >= 4 are rounded on their own — as in the scalar path.
+__device__ __forceinline__ void dft8p_windowed(const float2 (&x)[8], const float2 (&wr)[8], const float2 (&wi)[8],
+                                               float2 (&re)[8], float2 (&im)[8]) {
+  float2 pr[4], pi[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    pr[j] = mul2(x[j + 4], wr[j + 4]);
+    pi[j] = mul2(x[j + 4], wi[j + 4]);
+  }
+  const float2 s0r = fma2(x[0], wr[0], pr[0]), s0i = fma2(x[0], wi[0], pi[0]);
+  const float2 s1r = fma2(x[0], wr[0], neg2(pr[0])), s1i = fma2(x[0], wi[0], neg2(pi[0]));
+  const float2 s2r = fma2(x[2], wr[2], pr[2]), s2i = fma2(x[2], wi[2], pi[2]);
+  const float2 s3r = fma2(x[2], wr[2], neg2(pr[2])), s3i = fma2(x[2], wi[2], neg2(pi[2]));
+  const float2 t0r = fma2(x[1], wr[1], pr[1]), t0i = fma2(x[1], wi[1], pi[1]);
+  const float2 t1r = fma2(x[1], wr[1], neg2(pr[1])), t1i = fma2(x[1], wi[1], neg2(pi[1]));
+  const float2 t2r = fma2(x[3], wr[3], pr[3]), t2i = fma2(x[3], wi[3], pi[3]);
+  const float2 t3r = fma2(x[3], wr[3], neg2(pr[3])), t3i = fma2(x[3], wi[3], neg2(pi[3]));
+  dft8p_finish(re, im, add2(s0r, s2r), add2(s0i, s2i), add2(s1r, s3i), sub2(s1i, s3r), sub2(s0r, s2r), sub2(s0i, s2i),
+               sub2(s1r, s3i), add2(s1i, s3r), add2(t0r, t2r), add2(t0i, t2i), add2(t1r, t3i), sub2(t1i, t3r),
+               sub2(t0r, t2r), sub2(t0i, t2i), sub2(t1r, t3i), add2(t1i, t3r));
+}
+
+// dft8<true> of v[j] = xe[j] we[j] + i xo[j] wo[j], j < 4 (v[4..7] = 0): the products of j < 2 are fused into the
+// sums and differences that consume them, those of j = 2, 3 are rounded on their own — as in the scalar path.
+__device__ __forceinline__ void dft8p_low4(const float2 (&xe)[4], const float2 (&xo)[4], const float2 (&we)[4],
+                                           const float2 (&wo)[4], float2 (&re)[8], float2 (&im)[8]) {
+  const float2 r2 = mul2(xe[2], we[2]), i2 = mul2(xo[2], wo[2]);
+  const float2 r3 = mul2(xe[3], we[3]), i3 = mul2(xo[3], wo[3]);
+  dft8p_finish(re, im,
+               fma2(xe[0], we[0], r2), fma2(xo[0], wo[0], i2),                  // e0 = v0 + v2
+               fma2(xe[0], we[0], i2), fma2(xo[0], wo[0], neg2(r2)),            // e1 = v0 - i v2
+               fma2(xe[0], we[0], neg2(r2)), fma2(xo[0], wo[0], neg2(i2)),      // e2 = v0 - v2
+               fma2(xe[0], we[0], neg2(i2)), fma2(xo[0], wo[0], r2),            // e3 = v0 + i v2
+               fma2(xe[1], we[1], r3), fma2(xo[1], wo[1], i3),
+               fma2(xe[1], we[1], i3), fma2(xo[1], wo[1], neg2(r3)),
+               fma2(xe[1], we[1], neg2(r3)), fma2(xo[1], wo[1], neg2(i3)),
+               fma2(xe[1], we[1], neg2(i3)), fma2(xo[1], wo[1], r3));
+}
+
+// (r + i i) *= (wx + i wy), per half
+__device__ __forceinline__ void cmul2(float2& r, float2& i, float2 wx, float2 wy) {
+  const float2 nr = fma2(r, wx, neg2(mul2(i, wy)));
+  const float2 ni = fma2(r, wy, mul2(i, wx));
+  r = nr;
+  i = ni;
+}
+
+// fft512_tail on pairs: (re, im)[k2b].x = X[lane + 64 k2b], .y = X[lane + 32 + 64 k2b].
+__device__ __forceinline__ void fft512_tail_p(WarpSmem& ws, const float2 (&tw2r)[7], int lane, float2 (&re)[8], float2 (&im)[8]) {
+  const int k1 = lane >> 3, u = lane & 7;      // column lane + 32: k1 + 4, same u
+  __syncwarp();
+#pragma unroll
+  for (int v = 0; v < 8; ++v) {
+    re[v] = make_float2(ws.re[k1 * 72 + u + 8 * v], ws.re[(k1 + 4) * 72 + u + 8 * v]);
+    im[v] = make_float2(ws.im[k1 * 72 + u + 8 * v], ws.im[(k1 + 4) * 72 + u + 8 * v]);
+  }
+  __syncwarp();
+  dft8p(re, im);
+#pragma unroll
+  for (int k2a = 0; k2a < 8; ++k2a) {
+    if (k2a) cmul2(re[k2a], im[k2a], bc2(tw2r[k2a - 1].x), bc2(tw2r[k2a - 1].y));
+    ws.re[(k2a * 8 + k1) * 9 + u] = re[k2a].x;
+    ws.re[(k2a * 8 + k1 + 4) * 9 + u] = re[k2a].y;
+    ws.im[(k2a * 8 + k1) * 9 + u] = im[k2a].x;
+    ws.im[(k2a * 8 + k1 + 4) * 9 + u] = im[k2a].y;
+  }
+  __syncwarp();
+#pragma unroll
+  for (int uu = 0; uu < 8; ++uu) {
+    re[uu] = make_float2(ws.re[lane * 9 + uu], ws.re[(lane + 32) * 9 + uu]);
+    im[uu] = make_float2(ws.im[lane * 9 + uu], ws.im[(lane + 32) * 9 + uu]);
+  }
+  __syncwarp();
+  dft8p(re, im);
+}
+
 // Sample `l` (relative to the window start, may be negative for frame 0 -> torch 'reflect') of the
 // virtual padded clip: indices inside [valid_begin, valid_end) map to pcm[idx - offset], the rest are 0.
 // Sample types: float32 (what `load_audio` returns) or the int16 of a PCM_16 file, decoded on the fly exactly as
@@ -177,7 +296,128 @@ __device__ __forceinline__ void fft512_tail(WarpSmem& ws, const float2 (&tw2r)[7
   for (int h = 0; h < 2; ++h) dft8<false>(re[h], im[h]);
 }
 
+// Phase 1 of one frame on packed pairs: what the scalar body of features_kernel does for (h = 0, h = 1) at once.
 template <typename T>
+__device__ __forceinline__ void frame_spectra_packed(Smem& s, WarpSmem& ws, const T* __restrict__ pcm, const T* __restrict__ src,
+                                                     int64_t wstart, int l0, int64_t valid_begin, int64_t valid_end,
+                                                     int64_t offset, bool fast, bool fast2, int lane,
+                                                     const float2 (&tw1r)[2][7], const float2 (&tw2r)[7], float* __restrict__ Pf) {
+  float2 re[8], im[8];
+  const float2* __restrict__ twa_re = reinterpret_cast<const float2*>(s.tw_a_re) + lane;
+  const float2* __restrict__ twa_im = reinterpret_cast<const float2*>(s.tw_a_im) + lane;
+  const float2* __restrict__ win_e = reinterpret_cast<const float2*>(s.win) + lane;
+  const float2* __restrict__ win_o = win_e + 128;
+  // ------------------------------- FFT_A: a[n] = x[n] w[n] e^{-2 pi i n / 2048}
+  {
+    float2 x[8], wr[8], wi[8];
+    if (fast) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) x[j] = make_float2(ld1(src + lane + 64 * j), ld1(src + lane + 32 + 64 * j));
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        x[j] = make_float2(load_sample(pcm, wstart, l0 + lane + 64 * j, valid_begin, valid_end, offset),
+                           load_sample(pcm, wstart, l0 + lane + 32 + 64 * j, valid_begin, valid_end, offset));
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      wr[j] = twa_re[32 * j];
+      wi[j] = twa_im[32 * j];
+    }
+    dft8p_windowed(x, wr, wi, re, im);
+  }
+#pragma unroll
+  for (int k1 = 0; k1 < 8; ++k1) {
+    if (k1)
+      cmul2(re[k1], im[k1], make_float2(tw1r[0][k1 - 1].x, tw1r[1][k1 - 1].x), make_float2(tw1r[0][k1 - 1].y, tw1r[1][k1 - 1].y));
+    ws.re[k1 * 72 + lane] = re[k1].x;
+    ws.re[k1 * 72 + lane + 32] = re[k1].y;
+    ws.im[k1 * 72 + lane] = im[k1].x;
+    ws.im[k1 * 72 + lane + 32] = im[k1].y;
+  }
+  fft512_tail_p(ws, tw2r, lane, re, im);
+#pragma unroll
+  for (int k2b = 0; k2b < 8; ++k2b) {
+    const int q0 = lane + 64 * k2b, q1 = q0 + 32;
+    const float2 pw = fma2(re[k2b], re[k2b], mul2(im[k2b], im[k2b]));
+    if (q0 < kOddQ) Pf[q0 * kRowStride] = pw.x;                              // bin 4q+1
+    if (q0 > 511 - kOddQ) Pf[(kOddQ + 511 - q0) * kRowStride] = pw.x;        // bin 4(511-q)+3 (conjugate symmetry)
+    if (q1 < kOddQ) Pf[q1 * kRowStride] = pw.y;
+    if (q1 > 511 - kOddQ) Pf[(kOddQ + 511 - q1) * kRowStride] = pw.y;
+  }
+  // ------------------------------- FFT_B: c[n] = x[2n] w[2n] + i x[2n+1] w[2n+1], n < 256 (rest zero)
+  {
+    float2 xe[4], xo[4], we[4], wo[4];
+    if (fast2) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 a = ld2(src + 2 * (lane + 64 * j)), b = ld2(src + 2 * (lane + 32 + 64 * j));
+        xe[j] = make_float2(a.x, b.x);
+        xo[j] = make_float2(a.y, b.y);
+      }
+    } else if (fast) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        xe[j] = make_float2(ld1(src + 2 * (lane + 64 * j)), ld1(src + 2 * (lane + 32 + 64 * j)));
+        xo[j] = make_float2(ld1(src + 2 * (lane + 64 * j) + 1), ld1(src + 2 * (lane + 32 + 64 * j) + 1));
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        xe[j] = make_float2(load_sample(pcm, wstart, l0 + 2 * (lane + 64 * j), valid_begin, valid_end, offset),
+                            load_sample(pcm, wstart, l0 + 2 * (lane + 32 + 64 * j), valid_begin, valid_end, offset));
+        xo[j] = make_float2(load_sample(pcm, wstart, l0 + 2 * (lane + 64 * j) + 1, valid_begin, valid_end, offset),
+                            load_sample(pcm, wstart, l0 + 2 * (lane + 32 + 64 * j) + 1, valid_begin, valid_end, offset));
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      we[j] = win_e[32 * j];
+      wo[j] = win_o[32 * j];
+    }
+    dft8p_low4(xe, xo, we, wo, re, im);
+  }
+#pragma unroll
+  for (int k1 = 0; k1 < 8; ++k1) {
+    if (k1)
+      cmul2(re[k1], im[k1], make_float2(tw1r[0][k1 - 1].x, tw1r[1][k1 - 1].x), make_float2(tw1r[0][k1 - 1].y, tw1r[1][k1 - 1].y));
+    ws.re[k1 * 72 + lane] = re[k1].x;
+    ws.re[k1 * 72 + lane + 32] = re[k1].y;
+    ws.im[k1 * 72 + lane] = im[k1].x;
+    ws.im[k1 * 72 + lane + 32] = im[k1].y;
+  }
+  fft512_tail_p(ws, tw2r, lane, re, im);
+  // ---- even bins (see the scalar path): the partner C[512 - m] of column lane sits in lane 32 - lane's column
+  // lane' + 32 and vice versa, i.e. in the OTHER half of the pair (7 - k2b) there.
+  {
+    const int src_lane = (32 - lane) & 31;
+    const float2* __restrict__ twx = s.tw1024 + lane;      // pairs of real parts, then (at + 192) of imaginary parts
+#pragma unroll
+    for (int k2b = 0; k2b < 6; ++k2b) {
+      const int m0 = lane + 64 * k2b, m1 = m0 + 32;
+      float2 nr = make_float2(__shfl_sync(0xffffffffu, re[7 - k2b].y, src_lane), __shfl_sync(0xffffffffu, re[7 - k2b].x, src_lane));
+      float2 ni = make_float2(__shfl_sync(0xffffffffu, im[7 - k2b].y, src_lane), __shfl_sync(0xffffffffu, im[7 - k2b].x, src_lane));
+      if (lane == 0) {
+        nr = make_float2(re[(8 - k2b) & 7].x, re[7 - k2b].y);
+        ni = make_float2(im[(8 - k2b) & 7].x, im[7 - k2b].y);
+      }
+      // with n = conj C[512 - m] = nr - i ni:  e = (c + n) / 2,  o = (c - n) / (2 i) = (di - i dr) / 2
+      const float2 sr = add2(re[k2b], nr), si = sub2(im[k2b], ni);
+      const float2 dr = sub2(re[k2b], nr), di = add2(im[k2b], ni);
+      float2 orr = mul2(di, bc2(0.5f)), oi = mul2(dr, bc2(-0.5f));
+      cmul2(orr, oi, twx[32 * k2b], twx[192 + 32 * k2b]);
+      const float2 ur = fma2(sr, bc2(0.5f), orr), ui = fma2(si, bc2(0.5f), oi);
+      const float2 pw = fma2(ur, ur, mul2(ui, ui));
+      if (m0 < kEvenBins) Pf[(2 * kOddQ + m0) * kRowStride] = pw.x;
+      if (m1 < kEvenBins) Pf[(2 * kOddQ + m1) * kRowStride] = pw.y;
+    }
+  }
+}
+
+
+// kPk: phase 1 on packed pairs (FADD2 / FMUL2 / FFMA2, see above); the scalar path is kept for A/B runs (SS_K1_PACKED=0)
+// and as the statement of what the packed one must reproduce.
+template <typename T, bool kPk>
 __global__ void __launch_bounds__(kThreads, 1)
 features_kernel(const T* __restrict__ pcm, int64_t valid_begin, int64_t valid_end, int64_t offset,
                 const int64_t* __restrict__ starts, int64_t w_base, int n_tiles, FrontEnd fe, float* __restrict__ mel) {
@@ -193,12 +433,31 @@ features_kernel(const T* __restrict__ pcm, int64_t valid_begin, int64_t valid_en
     s.tw1[k - 1][t] = fe.tw512[(t * k) & 511];
     s.tw2[k - 1][t] = fe.tw512[(8 * (t & 7) * k) & 511];
   }
-  for (int i = tid; i < 512; i += kThreads) {
-    s.tw_a_re[i] = fe.tw_a_re[i];
-    s.tw_a_im[i] = fe.tw_a_im[i];
-    s.win[i] = fe.window[i];
+  if constexpr (kPk) {
+    // tables as pairs (column lane, column lane + 32), one 8-byte load per pair:
+    //   tw_a_re / tw_a_im [j * 32 + lane] = table[lane + 64 j], table[lane + 32 + 64 j]          (j < 8)
+    //   win [j * 32 + lane] = window[2 n], window[2 (n + 32)], n = lane + 64 j (j < 4); [128 + ...] = the odd samples'
+    //   tw1024 [k * 32 + lane] = Re W1024^m, Re W1024^(m + 32), m = lane + 64 k (k < 6); [192 + ...] = the imaginary parts
+    for (int i = tid; i < 512; i += kThreads) {
+      const int h = i & 1, l = (i >> 1) & 31, j = i >> 6;
+      s.tw_a_re[i] = fe.tw_a_re[l + 32 * h + 64 * j];
+      s.tw_a_im[i] = fe.tw_a_im[l + 32 * h + 64 * j];
+      const int odd = j >> 2;
+      s.win[i] = fe.window[2 * (l + 32 * h + 64 * (j & 3)) + odd];
+    }
+    for (int i = tid; i < 2 * kEvenPairs; i += kThreads) {       // i counts floats: [part][k][lane][h]
+      const int h = i & 1, l = (i >> 1) & 31, k = (i >> 6) % 6, part = i / (6 * 64);
+      const float2 w = fe.tw1024[l + 32 * h + 64 * k];       // m < 384: inside the 512-entry table
+      reinterpret_cast<float*>(s.tw1024)[i] = part ? w.y : w.x;
+    }
+  } else {
+    for (int i = tid; i < 512; i += kThreads) {
+      s.tw_a_re[i] = fe.tw_a_re[i];
+      s.tw_a_im[i] = fe.tw_a_im[i];
+      s.win[i] = fe.window[i];
+    }
+    for (int i = tid; i < kEvenBins; i += kThreads) s.tw1024[i] = fe.tw1024[i];
   }
-  for (int i = tid; i < kEvenBins; i += kThreads) s.tw1024[i] = fe.tw1024[i];
   for (int i = tid; i < fe.n_rec; i += kThreads) {
     float4 r = fe.mel_rec[i];
     r.z = __int_as_float(row_of_bin(__float_as_int(r.z)) * kRowStride);
@@ -247,6 +506,11 @@ features_kernel(const T* __restrict__ pcm, int64_t valid_begin, int64_t valid_en
         }
       }
 
+      if constexpr (kPk) {
+        frame_spectra_packed<T>(s, ws, pcm, src, wstart, l0, valid_begin, valid_end, offset, fast, fast2, lane, tw1r, tw2r, Pf);
+        __syncwarp();
+        continue;
+      }
       // ------------------------------- FFT_A: a[n] = x[n] w[n] e^{-2 pi i n / 2048}
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
@@ -586,9 +850,13 @@ __global__ void window_starts_kernel(int64_t* starts, int64_t n) {
 }  // namespace
 
 int features_init() {
-  SS_CUDA_CHECK(cudaFuncSetAttribute(features_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  SS_CUDA_CHECK(cudaFuncSetAttribute(features_kernel<float, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)sizeof(Smem)));
-  SS_CUDA_CHECK(cudaFuncSetAttribute(features_kernel<int16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  SS_CUDA_CHECK(cudaFuncSetAttribute(features_kernel<int16_t, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)sizeof(Smem)));
+  SS_CUDA_CHECK(cudaFuncSetAttribute(features_kernel<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)sizeof(Smem)));
+  SS_CUDA_CHECK(cudaFuncSetAttribute(features_kernel<int16_t, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)sizeof(Smem)));
   SS_CUDA_CHECK(cudaFuncSetAttribute(stft512_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)sizeof(SpecSmem)));
@@ -632,12 +900,16 @@ int launch_features_virtual(const ss_ctx* ctx, const void* pcm, int sample_fmt, 
   SS_REQUIRE(ctx->fe.n_rec <= kMaxRec, SS_E_BLOB, "mel filterbank walk has %d records (> %d)", ctx->fe.n_rec, kMaxRec);
   const int n_tiles = n_windows * (kFrames / kFramesPerTile);
   const int grid = n_tiles < kNumSMs ? n_tiles : kNumSMs;
-  if (sample_fmt == kSampleS16)
-    features_kernel<int16_t><<<grid, kThreads, sizeof(Smem), st>>>(static_cast<const int16_t*>(pcm), valid_begin,
-                                                                   valid_end, offset, starts, w_base, n_tiles, ctx->fe, mel);
-  else
-    features_kernel<float><<<grid, kThreads, sizeof(Smem), st>>>(static_cast<const float*>(pcm), valid_begin, valid_end,
-                                                                 offset, starts, w_base, n_tiles, ctx->fe, mel);
+  auto launch = [&](auto kernel, auto* samples) {
+    kernel<<<grid, kThreads, sizeof(Smem), st>>>(samples, valid_begin, valid_end, offset, starts, w_base, n_tiles, ctx->fe, mel);
+  };
+  if (sample_fmt == kSampleS16) {
+    if (ctx->fe.packed) launch(features_kernel<int16_t, true>, static_cast<const int16_t*>(pcm));
+    else launch(features_kernel<int16_t, false>, static_cast<const int16_t*>(pcm));
+  } else {
+    if (ctx->fe.packed) launch(features_kernel<float, true>, static_cast<const float*>(pcm));
+    else launch(features_kernel<float, false>, static_cast<const float*>(pcm));
+  }
   SS_CUDA_CHECK(cudaGetLastError());
   count_launch();
   return SS_OK;

@@ -94,6 +94,7 @@ struct FrontEnd {
   const float4* mel_rec = nullptr;    // [n_rec]
   const int* mel_rec_begin = nullptr; // [17] record range of each of the 16 warps
   int n_rec = 0;
+  int packed = 1;                     // K1 phase 1 on packed pairs (FFMA2); SS_K1_PACKED=0 at ss_ctx_create: the scalar path
 };
 
 enum { RB_CONV1 = 0, RB_CONV2, RB_CONV3, RB_CONV4, RB_BOTTLENECK, RB_ENCODER_OUT, RB_CONV6, RB_CONV7,
@@ -251,5 +252,35 @@ int classify_tc(ss_ctx* ctx, int mode, const float* mel, int n_windows, float* l
 int tc_error_flag(ss_ctx* ctx, int* flag, int* range_flag, cudaStream_t st);
 int tc_debug_profile(ss_ctx* ctx, int select_launch, long long* out_host);
 int tc_debug_dump(ss_ctx* ctx, int which, int n_windows, float* out, int* C, int* H, int* W, cudaStream_t st);
+
+// ------------------------------------------------------------------------------------------------------------
+// Packed fp32 pairs.  sm_100 issues two fp32 operations per instruction on a 64-bit register pair (PTX add / sub / mul /
+// fma.rn.f32x2 -> SASS FADD2 / FMUL2 / FFMA2), each half rounded exactly as the scalar instruction would be.  The
+// kernels that are bound by instruction issue rather than by a pipe (K1's transforms, conv1_direct) run their
+// arithmetic on pairs of independent values through these.
+#ifdef __CUDACC__
+#define SS_P2_BINARY(name, op)                                                                                   \
+  __device__ __forceinline__ float2 name(float2 a, float2 b) {                                                   \
+    float2 d;                                                                                                    \
+    asm("{.reg .b64 ra, rb, rd; mov.b64 ra, {%2, %3}; mov.b64 rb, {%4, %5}; " op " rd, ra, rb; mov.b64 {%0, %1}, rd;}" \
+        : "=f"(d.x), "=f"(d.y)                                                                                   \
+        : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));                                                               \
+    return d;                                                                                                    \
+  }
+SS_P2_BINARY(add2, "add.rn.f32x2")
+SS_P2_BINARY(sub2, "sub.rn.f32x2")
+SS_P2_BINARY(mul2, "mul.rn.f32x2")
+#undef SS_P2_BINARY
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
+  float2 d;
+  asm("{.reg .b64 ra, rb, rc, rd; mov.b64 ra, {%2, %3}; mov.b64 rb, {%4, %5}; mov.b64 rc, {%6, %7}; "
+      "fma.rn.f32x2 rd, ra, rb, rc; mov.b64 {%0, %1}, rd;}"
+      : "=f"(d.x), "=f"(d.y)
+      : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+  return d;
+}
+__device__ __forceinline__ float2 neg2(float2 a) { return make_float2(-a.x, -a.y); }
+__device__ __forceinline__ float2 bc2(float v) { return make_float2(v, v); }
+#endif  // __CUDACC__
 
 }  // namespace ss

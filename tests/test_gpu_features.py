@@ -127,3 +127,37 @@ def test_non_triangular_filterbank_takes_the_general_path(sd_seed0, clip60):
     err = np.max(np.abs(mel - ref)) / np.max(np.abs(ref))
     print(f"K1 with a three-deep overlapping bank vs oracle: {err:.3e}")
     assert err <= REL_TOL
+
+
+def test_packed_phase1_against_the_scalar_path(sd_seed0, clip60, monkeypatch):
+    """K1's phase 1 runs on packed pairs (FADD2 / FMUL2 / FFMA2: a lane's two transform columns as the halves of a
+    64-bit register pair) by default; SS_K1_PACKED=0 (read at context creation) keeps the scalar path.  Each packed
+    half is rounded as the scalar instruction would be and the packed path spells out the contraction the compiler
+    chose for the scalar one, so the two are expected to agree bit for bit; what is ASSERTED is a bound two orders of
+    magnitude below the parity budget, over whole windows incl. the reflected first frame, the virtual zero padding
+    (slow sample path) and int16 samples."""
+    from oracle import postproc as pp
+    from softspoken_b200.engine import Engine
+    padded = torch.from_numpy(_padded(clip60)).cuda()
+    starts = torch.from_numpy(pp.plan_windows(60.0))
+    clip = torch.from_numpy(clip60[: 22050 * 9]).cuda()
+    pcm16 = torch.from_numpy((clip60[: 22050 * 9] * 32767.0).astype(np.int16)).cuda()
+
+    def run():
+        eng = Engine(sd_seed0, 0, max_batch=8, mode="fp32")
+        mel = eng.features(padded, starts)
+        _, _, lg = eng.detect_device(clip, want_logits=True)          # virtual padding: frames that straddle the clip's ends
+        _, _, lg16 = eng.detect_device(pcm16, want_logits=True)
+        eng.close()
+        return mel, lg, lg16
+
+    packed = run()
+    monkeypatch.setenv("SS_K1_PACKED", "0")
+    scalar = run()
+    monkeypatch.delenv("SS_K1_PACKED")
+    d = float((packed[0] - scalar[0]).abs().max() / scalar[0].abs().max())
+    same = [bool(torch.equal(a, b)) for a, b in zip(packed, scalar)]
+    print(f"K1 packed vs scalar: mel max|d|/max = {d:.3e}; bit-identical (mel, logits f32, logits s16): {same}")
+    assert d <= 1e-6
+    for a, b in zip(packed[1:], scalar[1:]):
+        assert float((a - b).abs().max()) <= 1e-5 * max(1.0, float(b.abs().max()))

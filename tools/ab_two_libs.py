@@ -1,0 +1,86 @@
+"""A/B of two BUILDS of the library in one process: the current one against tools/bin/libsoftspoken_b200_prev.so (the
+previous commit's sources, built in a scratch worktree) — for changes that have no runtime knob.  Both libraries are
+loaded side by side (the package is imported a second time under another name with SOFTSPOKEN_B200_LIB pointing at the
+other file), their classifiers run alternately on the same input: whole-classifier CUDA-event time (median of `reps`,
+L2 flushed in between), MMA-warp kilocycles per launch, bit-identity of the logits.
+
+    python tools/ab_two_libs.py [reps] [mode] [reps of the per-launch profile]
+"""
+import ctypes as C
+import importlib.util
+import json
+import os
+import statistics
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+reps = int(sys.argv[1]) if len(sys.argv) > 1 else 7
+mode = sys.argv[2] if len(sys.argv) > 2 else "f16x3"
+preps = int(sys.argv[3]) if len(sys.argv) > 3 else 3
+
+
+def load_package(alias, lib_path):
+    """softspoken_b200 imported as `alias`, bound to `lib_path`."""
+    if lib_path:
+        os.environ["SOFTSPOKEN_B200_LIB"] = lib_path
+    else:
+        os.environ.pop("SOFTSPOKEN_B200_LIB", None)
+    spec = importlib.util.spec_from_file_location(alias, os.path.join(ROOT, "softspoken_b200", "__init__.py"),
+                                                  submodule_search_locations=[os.path.join(ROOT, "softspoken_b200")])
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules[alias] = mod
+    spec.loader.exec_module(mod)
+    eng = importlib.import_module(alias + ".engine")
+    lib = importlib.import_module(alias + "._lib")
+    os.environ.pop("SOFTSPOKEN_B200_LIB", None)
+    return mod, eng, lib
+
+
+with open(os.path.join(ROOT, "tests", "golden", "head_seed0.json")) as f:
+    head = json.load(f)
+builds = []
+for alias, path in (("ss_prev", os.path.join(ROOT, "tools", "bin", "libsoftspoken_b200_prev.so")), ("ss_new", None)):
+    mod, eng_mod, lib_mod = load_package(alias, path)
+    ck = importlib.import_module(alias + ".checkpoint")
+    eng = eng_mod.Engine(ck.synthetic_state_dict(0, head), 0, max_batch=1005, mode=mode)
+    builds.append((alias, eng, lib_mod))
+    print(alias, "->", lib_mod.LIB_PATH, file=sys.stderr)
+torch.manual_seed(0)
+mel = torch.rand(1005, 128, 256, device="cuda") * 1.5
+times, outs = [[], []], [None, None]
+for r in range(reps + 1):
+    for e, (alias, eng, lib_mod) in enumerate(builds):
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda").zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); lg = eng.classify(mel); b.record()
+        torch.cuda.synchronize()
+        eng.check_health()
+        if r > 0:
+            times[e].append(a.elapsed_time(b))
+        outs[e] = lg
+        del flush
+ma, mb = statistics.median(times[0]), statistics.median(times[1])
+print(f"{mode}: prev {ma:.3f} ms   new {mb:.3f} ms   new/prev {mb / ma:.4f}   bit-identical: {bool(torch.equal(outs[0], outs[1]))}"
+      f"   (median of {reps}; min prev {min(times[0]):.3f} new {min(times[1]):.3f})")
+if mode == "f16x3":
+    names = ["conv1_1.c2"]
+    for rb in ["conv2_1", "conv3_1", "conv4_1", "bottleneck", "encoder_out", "conv6", "conv7", "conv8", "conv9_1"]:
+        names += [rb + ".c1", rb + ".c2+res"]
+    buf = np.zeros((148, 8), np.int64)
+    res = np.zeros((2, len(names), preps))
+    for r in range(preps):
+        for e, (alias, eng, lib_mod) in enumerate(builds):
+            for i in range(len(names)):
+                lib_mod.check(lib_mod.lib.ss_debug_tc_profile(eng._ctx, i, None))
+                eng.classify(mel)
+                lib_mod.check(lib_mod.lib.ss_debug_tc_profile(eng._ctx, -1, C.c_void_p(buf.ctypes.data)))
+                res[e, i, r] = buf[buf[:, 7] > 0][:, 3].max()
+    med = np.median(res, axis=2)
+    print(f"{'launch':20s} {'prev kcyc':>10s} {'new kcyc':>10s}  new/prev")
+    for i, n in enumerate(names):
+        print(f"{n:20s} {med[0, i] / 1e3:10.1f} {med[1, i] / 1e3:10.1f}  {med[1, i] / med[0, i]:.3f}")
+    print(f"{'sum':20s} {med[0].sum() / 1e3:10.1f} {med[1].sum() / 1e3:10.1f}  {med[1].sum() / med[0].sum():.3f}")

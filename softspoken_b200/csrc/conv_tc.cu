@@ -800,21 +800,32 @@ int launch_conv_npg(TcJob job, int B, cudaStream_t st) {
   }
   // Which epilogue the launch needs picks the instantiation (conv_tc_kernel's Epi): 1 the folded MaxPool, 2 the general
   // one with the fused mask-head partials, 0 the general one alone.
-  bool any_head = false;
-  for (int ph = 0; ph < job.n_phase; ++ph) any_head |= job.c[ph].head_w != nullptr;
-  SS_REQUIRE(!any_head || N == 32, SS_E_ARG, "the fused mask head belongs to the 32-channel launch");
-  auto launch = [&](auto sub_c, auto rows_c, auto epi_c) -> int {
-    constexpr bool kS = decltype(sub_c)::value;
-    constexpr int kR = decltype(rows_c)::value, kE = decltype(epi_c)::value;
-    auto* kernel = conv_tc_kernel<N, P, Dual, G, kS, kR, kE>;
-    static bool configured_k = false;      // one flag per instantiation of this call operator
+  bool any_head = false, any_resx = false;
+  for (int ph = 0; ph < job.n_phase; ++ph) {
+    any_head |= job.c[ph].head_w != nullptr;
+    any_resx |= job.c[ph].res_x != nullptr;
+  }
+  SS_REQUIRE(!(any_head || any_resx) || N == 32, SS_E_ARG, "fused mask head / scalar residual: 32-channel launches only");
+  SS_REQUIRE(!(any_head && any_resx), SS_E_ARG, "no launch has both the fused mask head and the scalar residual");
+  bool any_up = false;
+  for (int ph = 0; ph < job.n_phase; ++ph) any_up |= job.c[ph].upsample != 0;
+  auto launch_k = [&](auto* kernel, bool& configured_k, bool rows_k) -> int {
     if (!configured_k) {
       SS_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)(kR ? kSmemBudgetMax : kSmemBudget)));
+                                         (int)(rows_k ? kSmemBudgetMax : kSmemBudget)));
       configured_k = true;
     }
     kernel<<<grid, kTcThreads, smem, st>>>(job);
     return SS_OK;
+  };
+  auto launch = [&](auto sub_c, auto rows_c, auto epi_c) -> int {
+    constexpr bool kS = decltype(sub_c)::value;
+    constexpr int kR = decltype(rows_c)::value, kE = decltype(epi_c)::value;
+    static bool configured_up = false, configured_noup = false;      // per instantiation of this call operator
+    if constexpr (kE != 1) {      // (the folded-pool epilogue has no such stores either way)
+      if (!any_up) return launch_k(conv_tc_kernel<N, P, Dual, G, kS, kR, kE, true>, configured_noup, kR != 0);
+    }
+    return launch_k(conv_tc_kernel<N, P, Dual, G, kS, kR, kE, false>, configured_up, kR != 0);
   };
   using std::integral_constant;
   using False = integral_constant<bool, false>;
@@ -830,6 +841,7 @@ int launch_conv_npg(TcJob job, int B, cudaStream_t st) {
           else rc = launch(False{}, integral_constant<int, 1>{}, integral_constant<int, 0>{});
         } else if constexpr (N == 32) {
           SS_REQUIRE(!p.pool_out, SS_E_ARG, "folded pool: the unit is not a pair of rows");
+          SS_REQUIRE(!any_resx, SS_E_ARG, "scalar residual: no such epilogue in this geometry");
           if (any_head) rc = launch(False{}, integral_constant<int, 1>{}, integral_constant<int, 2>{});
           else rc = launch(False{}, integral_constant<int, 1>{}, integral_constant<int, 0>{});
         } else {
@@ -839,8 +851,11 @@ int launch_conv_npg(TcJob job, int B, cudaStream_t st) {
       } else if constexpr (MT % 4 == 0) {
         if constexpr (MT == 4) {
           if (p.pool_out) rc = launch(False{}, integral_constant<int, 2>{}, integral_constant<int, 1>{});
-          else if (N == 32 && any_head) {
-            if constexpr (N == 32) rc = launch(False{}, integral_constant<int, 2>{}, integral_constant<int, 2>{});
+          else if (N == 32 && (any_head || any_resx)) {
+            if constexpr (N == 32) {
+              if (any_head) rc = launch(False{}, integral_constant<int, 2>{}, integral_constant<int, 2>{});
+              else rc = launch(False{}, integral_constant<int, 2>{}, integral_constant<int, 3>{});
+            }
           } else rc = launch(False{}, integral_constant<int, 2>{}, integral_constant<int, 0>{});
         } else {
           SS_REQUIRE(!p.pool_out && !any_head, SS_E_ARG, "row-aligned launch: no such epilogue in this geometry");
@@ -851,15 +866,13 @@ int launch_conv_npg(TcJob job, int B, cudaStream_t st) {
   } else {
     SS_REQUIRE(!p.pool_out, SS_E_ARG, "folded pool without row-aligned units");
     if constexpr (N == 32) {
-      if constexpr (kCanSub) {
-        if (any_sub) rc = any_head ? launch(True{}, integral_constant<int, 0>{}, integral_constant<int, 2>{})
-                                   : launch(True{}, integral_constant<int, 0>{}, integral_constant<int, 0>{});
-        else rc = any_head ? launch(False{}, integral_constant<int, 0>{}, integral_constant<int, 2>{})
-                           : launch(False{}, integral_constant<int, 0>{}, integral_constant<int, 0>{});
-      } else {
-        rc = any_head ? launch(False{}, integral_constant<int, 0>{}, integral_constant<int, 2>{})
-                      : launch(False{}, integral_constant<int, 0>{}, integral_constant<int, 0>{});
-      }
+      auto by_epi = [&](auto sub_c) -> int {
+        if (any_head) return launch(sub_c, integral_constant<int, 0>{}, integral_constant<int, 2>{});
+        if (any_resx) return launch(sub_c, integral_constant<int, 0>{}, integral_constant<int, 3>{});
+        return launch(sub_c, integral_constant<int, 0>{}, integral_constant<int, 0>{});
+      };
+      if constexpr (kCanSub) rc = any_sub ? by_epi(True{}) : by_epi(False{});
+      else rc = by_epi(False{});
     } else if constexpr (kCanSub) {
       rc = any_sub ? launch(True{}, integral_constant<int, 0>{}, integral_constant<int, 0>{})
                    : launch(False{}, integral_constant<int, 0>{}, integral_constant<int, 0>{});

@@ -550,8 +550,11 @@ __device__ __forceinline__ void issue_group_dup(uint32_t d0, uint32_t a_lo0, uin
 // row-aligned units and nothing else, 2 the general one with the fused mask-head partials (N = 32).  The three used to
 // share one kernel; its code (4,300 instructions in the N = 32 row-aligned instantiation) is what the MMA-issuing warps
 // compete with for the instruction cache, and every change to one epilogue moved the time of launches that never run
-// it by +-10 % (profiles/r2_tuning_experiments.txt, section 17).
-template <int N, Prec P, bool Dual, int G, bool Sub = false, int Rows = 0, int Epi = 0>
+// it by +-10 % (profiles/r2_tuning_experiments.txt, section 17).  3 = the general one with conv1_1's scalar residual
+// (TcConv::res_x; the folded-pool epilogue of N = 32 carries it too).
+// NoUp: the launch stores no up-sampled output (TcConv::upsample == 0 in every phase): the replicated-store variants
+// of `finalize` are not compiled (they are copied 4 N / 32 times into the unrolled epilogue).
+template <int N, Prec P, bool Dual, int G, bool Sub = false, int Rows = 0, int Epi = 0, bool NoUp = false>
 __global__ void __launch_bounds__(kTcThreads, 1)
 conv_tc_kernel(const TcJob job) {
   extern __shared__ __align__(128) unsigned char smem[];
@@ -573,6 +576,7 @@ conv_tc_kernel(const TcJob job) {
   constexpr int TS = TilesPerUnit<N, Dual>::TS;
   constexpr bool kSplit = PrecTraits<P>::split;
   constexpr bool kSubAcc = Sub;
+  constexpr bool kResX = N == 32 && (Epi == 1 || Epi == 3);      // conv1_1's scalar residual (TcConv::res_x) is compiled in
   static_assert(!Sub || (kSplit && G == 1), "sub-accumulation belongs to the split precision, one group per unit");
   // Rows = tiles of 128 positions per image row (0: flat units of consecutive positions).  A row-aligned unit is
   // kUnitRows = MT / Rows consecutive image rows starting at an even one.
@@ -966,7 +970,7 @@ conv_tc_kernel(const TcJob job) {
         t.y = (packed && t.b >= p.batch) ? 0 : y;      // past the last image: a border position (stores nothing)
         t.x = x;
         const bool interior = (t.y >= 1) && (y <= p.H) && (x >= 1) && (x <= p.W);
-        t.rx = (c.res_x != nullptr && interior && (job.epi & 1))
+        t.rx = ((kResX && c.res_x != nullptr) && interior && (job.epi & 1))
                    ? __ldg(c.res_x + ((int64_t)b * p.H + (y - 1)) * p.W + (x - 1)) : 0.f;
         return t;
       };
@@ -980,7 +984,7 @@ conv_tc_kernel(const TcJob job) {
         // (half-row tensor: row y of the tensor holds image rows 2y - 1 and 2y of the up-sampled image)
         const int64_t up = (int64_t)(c.upsample == 2 ? y : 2 * y - 1) * Wp2 + (2 * x - 1);
         const float rx = (job.epi & 1) ? pre.rx
-                         : ((c.res_x != nullptr && interior) ? __ldg(c.res_x + ((int64_t)b * p.H + (y - 1)) * p.W + (x - 1)) : 0.f);
+                         : (((kResX && c.res_x != nullptr) && interior) ? __ldg(c.res_x + ((int64_t)b * p.H + (y - 1)) * p.W + (x - 1)) : 0.f);
         const float* resw_p = bias_s + 2 * N + phase * N;
         const float* bias_t = interior ? bias_p : zero_s;
         const float scale_t = interior ? inv_scale : 0.f;
@@ -1021,7 +1025,7 @@ conv_tc_kernel(const TcJob job) {
           const float4 b1 = *reinterpret_cast<const float4*>(bias_t + n0 + g * 8 + 4);
           const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
           float rw[8];
-          if (c.res_x != nullptr) {
+          if ((kResX && c.res_x != nullptr)) {
             const float4 r0 = *reinterpret_cast<const float4*>(resw_p + n0 + g * 8);
             const float4 r1 = *reinterpret_cast<const float4*>(resw_p + n0 + g * 8 + 4);
             rw[0] = r0.x; rw[1] = r0.y; rw[2] = r0.z; rw[3] = r0.w; rw[4] = r1.x; rw[5] = r1.y; rw[6] = r1.z; rw[7] = r1.w;
@@ -1030,7 +1034,7 @@ conv_tc_kernel(const TcJob job) {
           for (int h = 0; h < 4; ++h) {
             float2 f01 = fma2(make_float2(__uint_as_float(v[g * 8 + 2 * h]), __uint_as_float(v[g * 8 + 2 * h + 1])),
                               bc2(scale_t), make_float2(bb[2 * h], bb[2 * h + 1]));
-            if (c.res_x != nullptr) f01 = fma2(bc2(rx), make_float2(rw[2 * h], rw[2 * h + 1]), f01);
+            if ((kResX && c.res_x != nullptr)) f01 = fma2(bc2(rx), make_float2(rw[2 * h], rw[2 * h + 1]), f01);
             const float f0 = fmaxf(f01.x, 0.f);
             const float f1 = fmaxf(f01.y, 0.f);
             hw[h] = pack_rn<P>(f0, f1);
@@ -1042,13 +1046,13 @@ conv_tc_kernel(const TcJob job) {
           const int64_t plane_off = img_off_t + (int64_t)(n0 / 8 + g) * out_plane_stride;
           if (dbg & 2) {
             if (ph.x == 0x12345678u && lw[0] == 0x9abcdef0u) p.err[1] = 1;      // keep the values alive
-          } else if (!c.upsample) {
+          } else if (NoUp || !c.upsample) {
             if (in_tensor) {
               st16(c.out + plane_off + (int64_t)q * 8, ph);
               if constexpr (kSplit)
                 st16(c.out_lo + plane_off + (int64_t)q * 8, make_uint4(lw[0], lw[1], lw[2], lw[3]));
             }
-          } else if (interior) {
+          } else if constexpr (!NoUp) if (interior) {
             uint16_t* o = c.out + plane_off + up * 8;
             if (c.upsample == 2) {
               st32x2(o, ph);
@@ -1116,7 +1120,7 @@ conv_tc_kernel(const TcJob job) {
         const int xc = (TPR == 2 ? tile_par * 128 : 0) + quad * 32 + lane;      // interior column, 0-based
         const int64_t posA = (int64_t)(2 * lu + 1) * Wp + (xc + 1);
         float rxA = 0.f, rxB = 0.f;
-        if (c.res_x != nullptr) {
+        if ((kResX && c.res_x != nullptr)) {
           const float* rp = c.res_x + ((int64_t)b * p.H + 2 * lu) * p.W + xc;
           rxA = __ldg(rp);
           rxB = __ldg(rp + p.W);
@@ -1144,7 +1148,7 @@ conv_tc_kernel(const TcJob job) {
             const float4 b1 = *reinterpret_cast<const float4*>(bias_p + ch + 4);
             const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
             float rw[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-            if (c.res_x != nullptr) {
+            if ((kResX && c.res_x != nullptr)) {
               const float4 r0 = *reinterpret_cast<const float4*>(resw_p + ch);
               const float4 r1 = *reinterpret_cast<const float4*>(resw_p + ch + 4);
               rw[0] = r0.x; rw[1] = r0.y; rw[2] = r0.z; rw[3] = r0.w; rw[4] = r1.x; rw[5] = r1.y; rw[6] = r1.z; rw[7] = r1.w;
@@ -1158,7 +1162,7 @@ conv_tc_kernel(const TcJob job) {
                                      make_float2(__uint_as_float(ac[i0]), __uint_as_float(ac[i1]))), bc2(inv_scale), bb2);
               float2 q01 = fma2(add2(make_float2(__uint_as_float(bm[i0]), __uint_as_float(bm[i1])),
                                      make_float2(__uint_as_float(bc[i0]), __uint_as_float(bc[i1]))), bc2(inv_scale), bb2);
-              if (c.res_x != nullptr) {
+              if ((kResX && c.res_x != nullptr)) {
                 a01 = fma2(bc2(rxA), rw2, a01);
                 q01 = fma2(bc2(rxB), rw2, q01);
               }
@@ -1168,7 +1172,8 @@ conv_tc_kernel(const TcJob job) {
               m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1));
               m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1));
               // (this path keeps the explicit clamp and a float running maximum: with the saturating conversion and
-              // the packed maximum of `finalize` conv1_1.c2 measured 14 % SLOWER, profiles/r2_tuning_experiments.txt 17)
+              // the packed maximum of `finalize` conv1_1.c2 measured 14 % SLOWER, profiles/r2_tuning_experiments.txt 17 —
+              // with or without the saturating conversion, in a kernel of its own too)
               vmax = fmaxf(vmax, fmaxf(m0, m1));
               a0 = fminf(a0, 65504.f); a1 = fminf(a1, 65504.f); q0v = fminf(q0v, 65504.f); q1v = fminf(q1v, 65504.f);
               m0 = fminf(m0, 65504.f); m1 = fminf(m1, 65504.f);
@@ -1206,16 +1211,43 @@ conv_tc_kernel(const TcJob job) {
           tc_fence_after();
 #pragma unroll
           for (int ti = 0; ti < kMyTiles; ++ti) {
+            if constexpr (Dual) {
+              // 16 columns at a time: the unit's sums hold N registers per tile, and two 32-column blocks (main and
+              // correction columns) on top of them spilled — to L2, the CTA's shared memory leaves next to no L1
+              // (conv7: -4 % / -2 %; the non-dual layers, one block per load, were 2-5 % faster as they are)
 #pragma unroll
-            for (int n0 = 0; n0 < N; n0 += 32) {
-              uint32_t v[32];
-              load_block(v, buf, tile_par + 2 * ti, n0);
-              if (sub == 0) {
+              for (int n0 = 0; n0 < N; n0 += 16) {
+                uint32_t v[16], cv[16];
+                const uint32_t t_blk = tmem_base + ((uint32_t)(quad * 32) << 16) +
+                                       (uint32_t)(buf * kAccCols + (tile_par + 2 * ti) * TS + n0);
+                tc_ld16(t_blk, v);
+                tc_ld16(t_blk + (uint32_t)N, cv);
+                tc_wait_ld();
 #pragma unroll
-                for (int i = 0; i < 32; ++i) acc[ti][n0 + i] = __uint_as_float(v[i]);
-              } else {
+                for (int i = 0; i < 16; i += 2) {
+                  const float2 sum = add2(make_float2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])),
+                                          make_float2(__uint_as_float(cv[i]), __uint_as_float(cv[i + 1])));
+                  if (sub == 0) {
+                    acc[ti][n0 + i] = sum.x;
+                    acc[ti][n0 + i + 1] = sum.y;
+                  } else {
+                    acc[ti][n0 + i] += sum.x;
+                    acc[ti][n0 + i + 1] += sum.y;
+                  }
+                }
+              }
+            } else {
 #pragma unroll
-                for (int i = 0; i < 32; ++i) acc[ti][n0 + i] += __uint_as_float(v[i]);
+              for (int n0 = 0; n0 < N; n0 += 32) {
+                uint32_t v[32];
+                load_block(v, buf, tile_par + 2 * ti, n0);
+                if (sub == 0) {
+#pragma unroll
+                  for (int i = 0; i < 32; ++i) acc[ti][n0 + i] = __uint_as_float(v[i]);
+                } else {
+#pragma unroll
+                  for (int i = 0; i < 32; ++i) acc[ti][n0 + i] += __uint_as_float(v[i]);
+                }
               }
             }
           }

@@ -43,7 +43,12 @@ def load_package(alias, lib_path):
 with open(os.path.join(ROOT, "tests", "golden", "head_seed0.json")) as f:
     head = json.load(f)
 builds = []
-for alias, path in (("ss_prev", os.path.join(ROOT, "tools", "bin", "libsoftspoken_b200_prev.so")), ("ss_new", None)):
+# AB_LIBS="name=path,name=path,..." compares any number of builds (first = the baseline); default: prev against current
+pairs = [("ss_prev", os.path.join(ROOT, "tools", "bin", "libsoftspoken_b200_prev.so")), ("ss_new", None)]
+if os.environ.get("AB_LIBS"):
+    pairs = [(kv.split("=")[0], os.path.join(ROOT, kv.split("=")[1]) if kv.split("=")[1] else None)
+             for kv in os.environ["AB_LIBS"].split(",")]
+for alias, path in pairs:
     mod, eng_mod, lib_mod = load_package(alias, path)
     ck = importlib.import_module(alias + ".checkpoint")
     eng = eng_mod.Engine(ck.synthetic_state_dict(0, head), 0, max_batch=1005, mode=mode)
@@ -51,7 +56,8 @@ for alias, path in (("ss_prev", os.path.join(ROOT, "tools", "bin", "libsoftspoke
     print(alias, "->", lib_mod.LIB_PATH, file=sys.stderr)
 torch.manual_seed(0)
 mel = torch.rand(1005, 128, 256, device="cuda") * 1.5
-times, outs = [[], []], [None, None]
+NB = len(builds)
+times, outs = [[] for _ in builds], [None] * NB
 for r in range(reps + 1):
     for e, (alias, eng, lib_mod) in enumerate(builds):
         flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda").zero_()
@@ -63,15 +69,16 @@ for r in range(reps + 1):
             times[e].append(a.elapsed_time(b))
         outs[e] = lg
         del flush
-ma, mb = statistics.median(times[0]), statistics.median(times[1])
-print(f"{mode}: prev {ma:.3f} ms   new {mb:.3f} ms   new/prev {mb / ma:.4f}   bit-identical: {bool(torch.equal(outs[0], outs[1]))}"
-      f"   (median of {reps}; min prev {min(times[0]):.3f} new {min(times[1]):.3f})")
-if mode == "f16x3":
+med = [statistics.median(t) for t in times]
+for e, (alias, _, _) in enumerate(builds):
+    print(f"{mode}: {alias:12s} {med[e]:.3f} ms   vs {builds[0][0]} {med[e] / med[0]:.4f}   bit-identical to it: "
+          f"{bool(torch.equal(outs[0], outs[e]))}   (median of {reps}; min {min(times[e]):.3f})")
+if mode == "f16x3" and preps > 0:
     names = ["conv1_1.c2"]
     for rb in ["conv2_1", "conv3_1", "conv4_1", "bottleneck", "encoder_out", "conv6", "conv7", "conv8", "conv9_1"]:
         names += [rb + ".c1", rb + ".c2+res"]
     buf = np.zeros((148, 8), np.int64)
-    res = np.zeros((2, len(names), preps))
+    res = np.zeros((NB, len(names), preps))
     for r in range(preps):
         for e, (alias, eng, lib_mod) in enumerate(builds):
             for i in range(len(names)):
@@ -79,8 +86,10 @@ if mode == "f16x3":
                 eng.classify(mel)
                 lib_mod.check(lib_mod.lib.ss_debug_tc_profile(eng._ctx, -1, C.c_void_p(buf.ctypes.data)))
                 res[e, i, r] = buf[buf[:, 7] > 0][:, 3].max()
-    med = np.median(res, axis=2)
-    print(f"{'launch':20s} {'prev kcyc':>10s} {'new kcyc':>10s}  new/prev")
+    medl = np.median(res, axis=2)
+    print(f"{'launch (kcyc)':20s} " + " ".join(f"{b[0]:>10s}" for b in builds) + "   ratios to " + builds[0][0])
     for i, n in enumerate(names):
-        print(f"{n:20s} {med[0, i] / 1e3:10.1f} {med[1, i] / 1e3:10.1f}  {med[1, i] / med[0, i]:.3f}")
-    print(f"{'sum':20s} {med[0].sum() / 1e3:10.1f} {med[1].sum() / 1e3:10.1f}  {med[1].sum() / med[0].sum():.3f}")
+        print(f"{n:20s} " + " ".join(f"{medl[e, i] / 1e3:10.1f}" for e in range(NB)) + "   " +
+              " ".join(f"{medl[e, i] / medl[0, i]:.3f}" for e in range(1, NB)))
+    print(f"{'sum':20s} " + " ".join(f"{medl[e].sum() / 1e3:10.1f}" for e in range(NB)) + "   " +
+          " ".join(f"{medl[e].sum() / medl[0].sum():.3f}" for e in range(1, NB)))

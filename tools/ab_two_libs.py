@@ -1,10 +1,13 @@
-"""A/B of two BUILDS of the library in one process: the current one against tools/bin/libsoftspoken_b200_prev.so (the
-previous commit's sources, built in a scratch worktree) — for changes that have no runtime knob.  Both libraries are
-loaded side by side (the package is imported a second time under another name with SOFTSPOKEN_B200_LIB pointing at the
-other file), their classifiers run alternately on the same input: whole-classifier CUDA-event time (median of `reps`,
-L2 flushed in between), MMA-warp kilocycles per launch, bit-identity of the logits.
+"""A/B of BUILDS of the library in one process — for changes that have no runtime knob.  Default: the current build
+against tools/bin/libsoftspoken_b200_prev.so (the previous commit's sources built in a scratch worktree:
+`git worktree add /tmp/prev HEAD && make -C /tmp/prev/softspoken_b200/csrc && cp .../libsoftspoken_b200.so tools/bin/...`);
+AB_LIBS="name=path,name=path,..." compares any builds (at most three fit in 180 GB at max_batch 1005; the first is the
+baseline; an empty path = the current build).  The libraries are loaded side by side (the package is imported once per
+build under another name with SOFTSPOKEN_B200_LIB pointing at the file) and their classifiers run alternately on the
+same input: whole-classifier CUDA-event time (median of `reps`, L2 flushed in between), MMA-warp kilocycles per launch
+(median of `preps`; deterministic to ~0.2 %), bit-identity of the logits.
 
-    python tools/ab_two_libs.py [reps] [mode] [reps of the per-launch profile]
+    [AB_LIBS=...] python tools/ab_two_libs.py [reps] [mode] [preps]
 """
 import ctypes as C
 import importlib.util

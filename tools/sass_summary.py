@@ -4,7 +4,8 @@
 
 Per kernel of softspoken_b200/libsoftspoken_b200.so: counts of the SASS mnemonics that prove the tcgen05 / TMEM / TMA
 path (`cuobjdump -sass`: UTCHMMA = tcgen05.mma kind::f16, LDTM / STTM = tcgen05.ld / st, UBLKCP = cp.async.bulk,
-UTMALDG = tensor-map TMA, UTCBAR = tcgen05.commit, SYNCS = mbarrier, HMMA = legacy mma.sync) and the registers,
+UTMALDG = tensor-map TMA, UTCBAR = tcgen05.commit, SYNCS = mbarrier, HMMA = legacy mma.sync, FFMA2 / FADD2 / FMUL2 = the packed fp32 pair
+instructions of sm_100) and the registers,
 spills and static shared memory ptxas reported for it (softspoken_b200/csrc/*.ptxas.log).
 """
 import glob
@@ -15,7 +16,8 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SO = os.path.join(ROOT, "softspoken_b200", "libsoftspoken_b200.so")
-MNEMONICS = ["UTCHMMA", "LDTM", "STTM", "UBLKCP", "UTMALDG", "UTCBAR", "SYNCS", "HMMA", "LDGSTS", "REDUX", "SHFL"]
+MNEMONICS = ["UTCHMMA", "LDTM", "STTM", "UBLKCP", "UTMALDG", "UTCBAR", "SYNCS", "HMMA", "LDGSTS", "REDUX", "SHFL",
+             "FFMA2", "FADD2", "FMUL2"]
 
 
 def demangle(names):
